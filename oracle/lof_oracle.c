@@ -1,0 +1,490 @@
+/*
+ * lof_oracle.c -- CPU ORACLE (plain C) for the LoFloat virtual-rounding hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY -- see lof_oracle.h for the usage rules and the pinning story.
+ * Every function cites the reference lines it restates.
+ */
+#include "lof_oracle.h"
+
+#include <math.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------------------
+ * Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11).
+ * Not a reference function: the reference has no reproducible RNG (see lof_oracle.h).
+ * Known-answer vectors from the Random123 distribution are checked in
+ * tests/test_oracle_golden.py.
+ * ---------------------------------------------------------------------------------- */
+void lofo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int round = 0; round < 10; ++round) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+uint32_t lofo_rand_word(const lofo_rng* rng, uint64_t index, uint32_t stream)
+{
+    if (!rng) return 0u;
+    if (rng->fixed) return rng->fixed_word;
+    const uint64_t blk = index >> 2;
+    uint32_t ctr[4] = { (uint32_t)blk, (uint32_t)(blk >> 32),
+                        (uint32_t)rng->offset, (uint32_t)(rng->offset >> 32) ^ stream };
+    uint32_t key[2] = { (uint32_t)rng->seed, (uint32_t)(rng->seed >> 32) };
+    uint32_t out[4];
+    lofo_philox4x32_10(ctr, key, out);
+    return out[index & 3u];
+}
+
+/* ------------------------------------------------------------------------------------
+ * container conversions
+ * ---------------------------------------------------------------------------------- */
+static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint64_t d2u(double f) { uint64_t u; memcpy(&u, &f, 8); return u; }
+static inline double u2d(uint64_t u) { double f; memcpy(&f, &u, 8); return f; }
+
+static inline float half_bits_to_float(uint16_t h)
+{
+    uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    uint32_t exp = (h >> 10) & 0x1Fu;
+    uint32_t man = h & 0x3FFu;
+    if (exp == 0x1F) return u2f(sign | 0x7F800000u | (man << 13));
+    if (exp == 0) {
+        float v = (float)man * 0x1p-24f;    /* subnormal: exact */
+        return sign ? -v : v;
+    }
+    return u2f(sign | ((exp + 112u) << 23) | (man << 13));
+}
+
+/* float -> IEEE half, round-to-nearest-even (what c10::Half(float) does) */
+static inline uint16_t float_to_half_bits(float f)
+{
+    uint32_t x = f2u(f);
+    uint32_t sign = (x >> 16) & 0x8000u;
+    uint32_t a = x & 0x7FFFFFFFu;
+    if (a > 0x7F800000u) return (uint16_t)(sign | 0x7E00u);            /* NaN */
+    if (a >= 0x47800000u) return (uint16_t)(sign | 0x7C00u);           /* >= 65536 -> inf (incl. rounding) */
+    if (a < 0x33000000u) return (uint16_t)sign;                        /* < 2^-25 -> 0 */
+    int e = (int)(a >> 23) - 127;
+    uint32_t man = (a & 0x7FFFFFu) | 0x800000u;
+    int shift = (e < -14) ? (13 + (-14 - e)) : 13;
+    uint32_t q = man >> shift;
+    uint32_t rem = man & ((1u << shift) - 1u);
+    uint32_t halfway = 1u << (shift - 1);
+    if (rem > halfway || (rem == halfway && (q & 1u))) q += 1u;
+    uint32_t h;
+    if (e < -14) h = q;                                                /* subnormal (carry into normal is fine) */
+    else h = ((uint32_t)(e + 15) << 10) + (q - 0x400u);                /* q in [0x400, 0x800] */
+    if (h >= 0x7C00u) h = 0x7C00u;
+    return (uint16_t)(sign | h);
+}
+
+static inline float bf16_bits_to_float(uint16_t h) { return u2f((uint32_t)h << 16); }
+
+static inline uint16_t float_to_bf16_bits(float f)
+{
+    uint32_t x = f2u(f);
+    if ((x & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((x >> 16) | 0x0040u);
+    uint32_t lsb = (x >> 16) & 1u;
+    x += 0x7FFFu + lsb;
+    return (uint16_t)(x >> 16);
+}
+
+/* ------------------------------------------------------------------------------------
+ * integer rounding core, one instantiation per container width
+ * ---------------------------------------------------------------------------------- */
+#define SFX b32
+#define BITS_T uint32_t
+#include "lof_oracle_core.inc"
+#undef SFX
+#undef BITS_T
+
+#define SFX b16
+#define BITS_T uint16_t
+#include "lof_oracle_core.inc"
+#undef SFX
+#undef BITS_T
+
+#define SFX b64
+#define BITS_T uint64_t
+#include "lof_oracle_core.inc"
+#undef SFX
+#undef BITS_T
+
+/* ------------------------------------------------------------------------------------
+ * virtual_round bodies, one instantiation per source type
+ * ---------------------------------------------------------------------------------- */
+/* float (Traits<float>, lo_float.h:2641-2653) */
+#define TSFX f32
+#define SFX b32
+#define BITS_T uint32_t
+#define KBITS 32
+#define KMANT 23
+#define KBIAS 127
+#define QNAN_BITS 0x7FC00000u
+#define INF_BITS 0x7F800000u
+#define TO_FLOAT(b) u2f(b)
+#define FROM_DOUBLE(d) f2u((float)(d))
+#define IS_NAN(b) (((b) & 0x7FFFFFFFu) > 0x7F800000u)
+#include "lof_oracle_type.inc"
+#undef TSFX
+#undef SFX
+#undef BITS_T
+#undef KBITS
+#undef KMANT
+#undef KBIAS
+#undef QNAN_BITS
+#undef INF_BITS
+#undef TO_FLOAT
+#undef FROM_DOUBLE
+#undef IS_NAN
+
+/* double (Traits<double>, lo_float.h:2656-2668); get_float() narrows with RN (:2689) */
+#define TSFX f64
+#define SFX b64
+#define BITS_T uint64_t
+#define KBITS 64
+#define KMANT 52
+#define KBIAS 1023
+#define QNAN_BITS 0x7FF8000000000000ull
+#define INF_BITS 0x7FF0000000000000ull
+#define TO_FLOAT(b) ((float)u2d(b))
+#define FROM_DOUBLE(d) d2u((double)(d))
+#define IS_NAN(b) (((b) & 0x7FFFFFFFFFFFFFFFull) > 0x7FF0000000000000ull)
+#include "lof_oracle_type.inc"
+#undef TSFX
+#undef SFX
+#undef BITS_T
+#undef KBITS
+#undef KMANT
+#undef KBIAS
+#undef QNAN_BITS
+#undef INF_BITS
+#undef TO_FLOAT
+#undef FROM_DOUBLE
+#undef IS_NAN
+
+/* c10::Half (Traits<c10::Half>, lo_float.h:2626-2638); from_double goes double->float->half */
+#define TSFX f16
+#define SFX b16
+#define BITS_T uint16_t
+#define KBITS 16
+#define KMANT 10
+#define KBIAS 15
+#define QNAN_BITS 0x7E00u
+#define INF_BITS 0x7C00u
+#define TO_FLOAT(b) half_bits_to_float(b)
+#define FROM_DOUBLE(d) float_to_half_bits((float)(d))
+#define IS_NAN(b) (((b) & 0x7FFFu) > 0x7C00u)
+#include "lof_oracle_type.inc"
+#undef TSFX
+#undef SFX
+#undef BITS_T
+#undef KBITS
+#undef KMANT
+#undef KBIAS
+#undef QNAN_BITS
+#undef INF_BITS
+#undef TO_FLOAT
+#undef FROM_DOUBLE
+#undef IS_NAN
+
+/* bfloat16: NOT a reference source type (LoPy_bind.cpp:83,133 dispatches float/double/half
+ * only).  Defined by analogy: 16-bit container, 7 mantissa bits, bias 127. */
+#define TSFX bf16
+#define SFX b16
+#define BITS_T uint16_t
+#define KBITS 16
+#define KMANT 7
+#define KBIAS 127
+#define QNAN_BITS 0x7FC0u
+#define INF_BITS 0x7F80u
+#define TO_FLOAT(b) bf16_bits_to_float(b)
+#define FROM_DOUBLE(d) float_to_bf16_bits((float)(d))
+#define IS_NAN(b) (((b) & 0x7FFFu) > 0x7F80u)
+#include "lof_oracle_type.inc"
+#undef TSFX
+#undef SFX
+#undef BITS_T
+#undef KBITS
+#undef KMANT
+#undef KBIAS
+#undef QNAN_BITS
+#undef INF_BITS
+#undef TO_FLOAT
+#undef FROM_DOUBLE
+#undef IS_NAN
+
+/* ------------------------------------------------------------------------------------
+ * scalar + array entry points
+ * ---------------------------------------------------------------------------------- */
+uint32_t lofo_round_params_bits_f32(uint32_t bits, const lofo_format* f, const lofo_projspec* ps, uint32_t w)
+{
+    return vround_params_f32(bits, f, ps->rounding_mode, ps->stoch_length, w);
+}
+
+uint32_t lofo_round_mantissa_bits_f32(uint32_t bits, int mant_bits, const lofo_projspec* ps, uint32_t w)
+{
+    return vround_mant_f32(bits, mant_bits, ps->rounding_mode, ps->stoch_length, w);
+}
+
+static inline int mode_uses_rng(int mode)
+{
+    return mode == LOFO_SR_A || mode == LOFO_SR_B || mode == LOFO_SR_C || mode == LOFO_SR_D ||
+           mode == LOFO_TRUE_SR || mode == LOFO_PROB;
+}
+
+/* fused pre-scale, Lof_kernel.cu:41,53: v = (scale == From(1)) ? in : From(scale * in),
+ * evaluated in the container's own arithmetic (Half*Half and bf16*bf16 multiply in float
+ * and round back to the container). */
+static inline uint32_t scale_f32(uint32_t b, float s) { return (s == 1.0f) ? b : f2u(s * u2f(b)); }
+static inline uint64_t scale_f64(uint64_t b, double s) { return (s == 1.0) ? b : d2u(s * u2d(b)); }
+static inline uint16_t scale_f16(uint16_t b, uint16_t sb)
+{
+    float s = half_bits_to_float(sb);
+    return (s == 1.0f) ? b : float_to_half_bits(s * half_bits_to_float(b));
+}
+static inline uint16_t scale_bf16(uint16_t b, uint16_t sb)
+{
+    float s = bf16_bits_to_float(sb);
+    return (s == 1.0f) ? b : float_to_bf16_bits(s * bf16_bits_to_float(b));
+}
+
+#define ROUND_LOOP(BITS_T, SCALE_EXPR, CALL)                                              \
+    do {                                                                                  \
+        const BITS_T* src = (const BITS_T*)in;                                            \
+        BITS_T* dst = (BITS_T*)out;                                                       \
+        _Pragma("omp parallel for schedule(static)")                                      \
+        for (int64_t i = 0; i < n; ++i) {                                                 \
+            uint32_t w = need_rng ? lofo_rand_word(rng, first_index + (uint64_t)i, LOFO_STREAM_ELEM) : 0u; \
+            BITS_T v = SCALE_EXPR;                                                        \
+            dst[i] = CALL;                                                                \
+        }                                                                                 \
+    } while (0)
+
+void lofo_round_params(const void* in, void* out, int64_t n, int dtype, const lofo_format* f,
+                       const lofo_projspec* ps, double scale, const lofo_rng* rng, uint64_t first_index)
+{
+    const int mode = ps->rounding_mode, len = ps->stoch_length;
+    const int need_rng = mode_uses_rng(mode) && rng != NULL;
+    switch (dtype) {
+    case LOFO_F32: {
+        const float s = (float)scale;
+        ROUND_LOOP(uint32_t, scale_f32(src[i], s), vround_params_f32(v, f, mode, len, w));
+        break;
+    }
+    case LOFO_F64: {
+        ROUND_LOOP(uint64_t, scale_f64(src[i], scale), vround_params_f64(v, f, mode, len, w));
+        break;
+    }
+    case LOFO_F16: {
+        const uint16_t sb = float_to_half_bits((float)scale);
+        ROUND_LOOP(uint16_t, scale_f16(src[i], sb), vround_params_f16(v, f, mode, len, w));
+        break;
+    }
+    case LOFO_BF16: {
+        const uint16_t sb = float_to_bf16_bits((float)scale);
+        ROUND_LOOP(uint16_t, scale_bf16(src[i], sb), vround_params_bf16(v, f, mode, len, w));
+        break;
+    }
+    default: break;
+    }
+}
+
+void lofo_round_mantissa(const void* in, void* out, int64_t n, int dtype, int mant_bits,
+                         const lofo_projspec* ps, double scale, const lofo_rng* rng, uint64_t first_index)
+{
+    const int mode = ps->rounding_mode, len = ps->stoch_length;
+    const int need_rng = mode_uses_rng(mode) && rng != NULL;
+    switch (dtype) {
+    case LOFO_F32: {
+        const float s = (float)scale;
+        ROUND_LOOP(uint32_t, scale_f32(src[i], s), vround_mant_f32(v, mant_bits, mode, len, w));
+        break;
+    }
+    case LOFO_F64: {
+        ROUND_LOOP(uint64_t, scale_f64(src[i], scale), vround_mant_f64(v, mant_bits, mode, len, w));
+        break;
+    }
+    case LOFO_F16: {
+        const uint16_t sb = float_to_half_bits((float)scale);
+        ROUND_LOOP(uint16_t, scale_f16(src[i], sb), vround_mant_f16(v, mant_bits, mode, len, w));
+        break;
+    }
+    case LOFO_BF16: {
+        const uint16_t sb = float_to_bf16_bits((float)scale);
+        ROUND_LOOP(uint16_t, scale_bf16(src[i], sb), vround_mant_bf16(v, mant_bits, mode, len, w));
+        break;
+    }
+    default: break;
+    }
+}
+
+/* ------------------------------------------------------------------------------------
+ * MX block rounding: LoPy_bind.cpp:197-215 (== lo_float.h:4311-4383 on NaN-free data)
+ * ---------------------------------------------------------------------------------- */
+float lofo_mx_priv_max_normal(const lofo_format* p)
+{
+    const int me = (p->is_signed == LOFO_SIGNED)
+                       ? (1 << (p->bitwidth - p->mantissa_bits - 1)) - 1 - p->bias
+                       : (1 << (p->bitwidth - p->mantissa_bits)) - 1 - p->bias;
+    return ldexpf(1.0f, me) * (2.0f - ldexpf(1.0f, -p->mantissa_bits));   /* LoPy_bind.cpp:202 */
+}
+
+void lofo_mx_round_f32(const float* in, float* out, int64_t n, int block_size,
+                       const lofo_format* pub, const lofo_format* priv,
+                       const lofo_projspec* ps_pub, const lofo_projspec* ps_priv,
+                       const lofo_rng* rng, uint64_t first_index)
+{
+    if (block_size <= 0 || n <= 0) return;
+    const float pmn = lofo_mx_priv_max_normal(priv);
+    const int need_rng_e = mode_uses_rng(ps_priv->rounding_mode) && rng != NULL;
+    const int need_rng_s = mode_uses_rng(ps_pub->rounding_mode) && rng != NULL;
+    const int64_t nblocks = (n + block_size - 1) / block_size;
+#pragma omp parallel for schedule(static)
+    for (int64_t blk = 0; blk < nblocks; ++blk) {
+        const int64_t b = blk * block_size;
+        const int len = (int)((n - b) < block_size ? (n - b) : block_size);
+        float amax = 0.0f;
+        for (int i = 0; i < len; ++i) {                     /* std::max(amax, fabs(x)): NaN is dropped */
+            float v = fabsf(in[b + i]);
+            amax = (amax < v) ? v : amax;
+        }
+        /* scale rounding: ProjSpec{scale_round_mode} -> stoch_len 0 (LoPy_bind.cpp:208) */
+        const uint64_t gblk = (first_index + (uint64_t)b) / (uint64_t)block_size;
+        uint32_t ws = need_rng_s ? lofo_rand_word(rng, gblk, LOFO_STREAM_SCALE) : 0u;
+        const float scale = u2f(vround_params_f32(f2u(amax / pmn), pub, ps_pub->rounding_mode, 0, ws));
+        if (scale > 0.0f) {
+            for (int i = 0; i < len; ++i) {
+                uint32_t w = need_rng_e ? lofo_rand_word(rng, first_index + (uint64_t)(b + i), LOFO_STREAM_ELEM) : 0u;
+                float q = u2f(vround_params_f32(f2u(in[b + i] / scale), priv, ps_priv->rounding_mode,
+                                                ps_priv->stoch_length, w));
+                out[b + i] = q * scale;
+            }
+        } else {
+            for (int i = 0; i < len; ++i) out[b + i] = 0.0f;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------
+ * round-to-odd FMA, blis_lof_gemm.hpp:63-99
+ * ---------------------------------------------------------------------------------- */
+float lofo_round_to_odd_fma(float a, float b, float c)
+{
+    const float rn = fmaf(a, b, c);
+    if (!isfinite(rn)) return rn;
+    const double p = (double)a * (double)b;
+    const double cd = (double)c;
+    const double s = p + cd;
+    const double bb = s - p;
+    const double e = (p - (s - bb)) + (cd - bb);
+    const double res = (s - (double)rn) + e;
+    if (res == 0.0) return rn;
+    uint32_t brn = f2u(rn);
+    if (brn & 1u) return rn;
+    if (rn == 0.0f) {
+        brn = (res > 0.0) ? 0x00000001u : 0x80000001u;
+    } else {
+        const int neg = (int)(brn >> 31);
+        const int toward_pos = res > 0.0;
+        if (toward_pos == neg) --brn; else ++brn;
+    }
+    return u2f(brn);
+}
+
+/* ------------------------------------------------------------------------------------
+ * LoFloat-accumulation GEMM: lof_sgemm_ukr (blis_lof_gemm.hpp:147-262) under BLIS's
+ * K-panelling.  Per output element the result depends only on the panel length kc
+ * (MR/NR/MC/NC only change which elements share a micro-tile, never the k order).
+ * ---------------------------------------------------------------------------------- */
+void lofo_gemm_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                   int accum_mant_bits, const lofo_projspec* ps, int64_t kc,
+                   float alpha, float beta, const lofo_rng* rng)
+{
+    const int mode = ps->rounding_mode, len = ps->stoch_length;
+    const int need_rng = mode_uses_rng(mode) && rng != NULL;
+    if (kc <= 0 || kc > K) kc = K > 0 ? K : 1;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < M; ++i) {
+        for (int64_t j = 0; j < N; ++j) {
+            float cij = C[i * N + j];
+            int first = 1;
+            if (K == 0) { C[i * N + j] = (beta == 0.0f) ? 0.0f : beta * cij; continue; }
+            for (int64_t k0 = 0; k0 < K; k0 += kc) {
+                const int64_t k1 = (k0 + kc < K) ? k0 + kc : K;
+                float acc = 0.0f;
+                if (accum_mant_bits >= 0) {
+                    for (int64_t l = k0; l < k1; ++l) {                                  /* :217-228 */
+                        uint32_t w = need_rng
+                            ? lofo_rand_word(rng, ((uint64_t)i * (uint64_t)N + (uint64_t)j) * (uint64_t)K + (uint64_t)l, LOFO_STREAM_GEMM)
+                            : 0u;
+                        float t = lofo_round_to_odd_fma(A[i * K + l], B[l * N + j], acc);
+                        acc = u2f(vround_mant_f32(f2u(t), accum_mant_bits, mode, len, w));
+                    }
+                } else {
+                    for (int64_t l = k0; l < k1; ++l) {                                  /* :233-239 */
+                        volatile float prod = A[i * K + l] * B[l * N + j];               /* no contraction: ab += a*b */
+                        acc = acc + prod;
+                    }
+                }
+                acc *= alpha;                                                            /* :244-245 */
+                if (first) { cij = (beta == 0.0f) ? acc : beta * cij + acc; first = 0; } /* :248-261 */
+                else       { cij = cij + acc; }                                          /* beta == 1 on later panels */
+            }
+            C[i * N + j] = cij;
+        }
+    }
+}
+
+/* Oracle of OUR tensor-core (tcgen05) chunked mode -- not a reference function.
+ * Each k-chunk's partial dot product is taken as the correctly rounded fp32 value of the
+ * exact sum (the tensor core's internal alignment may differ by a few fp32 ulps; the GPU
+ * test states that tolerance), then acc = round_to_format(acc + partial) with a single
+ * rounding (round-to-odd add in double, then the format rounding). */
+void lofo_gemm_chunked_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                           int accum_mant_bits, const lofo_format* acc_fmt, const lofo_projspec* ps,
+                           int64_t k_chunk, float alpha)
+{
+    const int mode = ps->rounding_mode, len = ps->stoch_length;
+    if (k_chunk <= 0 || k_chunk > K) k_chunk = K > 0 ? K : 1;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < M; ++i) {
+        for (int64_t j = 0; j < N; ++j) {
+            float acc = 0.0f;
+            for (int64_t k0 = 0; k0 < K; k0 += k_chunk) {
+                const int64_t k1 = (k0 + k_chunk < K) ? k0 + k_chunk : K;
+                double part = 0.0;
+                for (int64_t l = k0; l < k1; ++l) part += (double)A[i * K + l] * (double)B[l * N + j];
+                const float partf = (float)part;
+                const float t = lofo_round_to_odd_fma(1.0f, partf, acc);
+                if (acc_fmt) acc = u2f(vround_params_f32(f2u(t), acc_fmt, mode, len, 0u));
+                else         acc = u2f(vround_mant_f32(f2u(t), accum_mant_bits, mode, len, 0u));
+            }
+            C[i * N + j] = acc * alpha;
+        }
+    }
+}
+
+int lofo_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
