@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the LoFloat virtual-rounding hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json configs[1], "C2"): virtual_round of a 1 GiB fp32 tensor (2^28 elements,
+randn * 2^U{-12..12}, seed 2024) over the format x mode sweep
+    formats  E5M2 (8,2,15)  E4M3 (8,3,7)  E3M2 (6,2,3)  E2M1 (4,1,1)  bf16-like (16,7,127,Extended)
+    modes    RNE, RTZ, RoundToOdd, StochasticRoundingA(len 8)
+One STEP = the 20 (format, mode) passes over the tensor = 20 kernel launches, 40 GiB of algorithmic
+traffic (8 B/element: 4 read + 4 written).  With N GPUs the tensor is N GiB, row-sharded, one
+1 GiB shard per rank, no collective (weak scaling).  Metric: aggregate GB/s of algorithmic bytes.
+
+The line also carries: `roofline` for the dominant kernel (CUDA-event time per launch inside the
+timed region), `e2e` (same sweep through the C ABI's HOST-buffer entry point, H2D/D2H inside the
+timed region), `cpu_baseline` (the reference's own scalar CPU path on this box's cores, bounded
+sample) and short side measurements of mx_round and lof_gemm (`other`, outside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_ELEMS = 1 << 28
+FORMATS = [("e5m2", (8, 2, 15, 1, 0)), ("e4m3", (8, 3, 7, 1, 0)), ("e3m2", (6, 2, 3, 1, 0)),
+           ("e2m1", (4, 1, 1, 1, 0)), ("bf16like", (16, 7, 127, 0, 0))]          # (bw, m, bias, ov, signed)
+MODES = [("RNE", 0, 0), ("RTZ", 1, 0), ("RoundToOdd", 12, 0), ("SR_A8", 3, 8)]   # (name, mode, stoch_len)
+KERNEL_OF_MODE = {"RNE": "round_vec_kernel<f32,RoundToNearestEven>", "RTZ": "round_vec_kernel<f32,RoundTowardsZero>",
+                  "RoundToOdd": "round_vec_kernel<f32,RoundToOdd>", "SR_A8": "round_vec_kernel<f32,StochasticRoundingA>"}
+WORKLOAD = "C2: virtual_round fp32 1GiB/GPU, 5 formats x 4 modes (RNE,RTZ,RoundToOdd,SR-A8), row-sharded"
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_structs():
+    from lofloat_b200 import _lib
+    combos = []
+    for fname, (bw, m, bias, ov, sg) in FORMATS:
+        for mname, mode, sl in MODES:
+            combos.append((f"{fname}/{mname}", mname, _lib.CFormat(bw, m, bias, ov, 0, sg, 0), _lib.CProjSpec(mode, 0, sl)))
+    return combos
+
+
+# ----------------------------------------------------------------------------------------- own arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from lofloat_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU; lofloat_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+    combos = make_structs()
+    n = N_ELEMS
+    first_index = rank * n                                   # this rank's row shard of the N GiB tensor
+    g = torch.Generator(device=dev).manual_seed(2024 + rank)
+    x = torch.randn(n, device=dev, generator=g)
+    x *= torch.exp2(torch.randint(-12, 13, (n,), device=dev, generator=g).float())
+    y = torch.empty_like(x)
+    stream = torch.cuda.current_stream().cuda_stream
+    rng = _lib.CRng(2024, 0)
+
+    def one_pass(i, fmt, ps, evs=None):
+        if evs is not None:
+            evs[0].record()
+        st = lib.lof_round_params(x.data_ptr(), y.data_ptr(), n, 0, C.byref(fmt), C.byref(ps), 1.0, C.byref(rng),
+                                  first_index, stream)
+        if evs is not None:
+            evs[1].record()
+        if st != 0:
+            raise RuntimeError(lib.lof_last_error_string().decode())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        for i, (_, _, fmt, ps) in enumerate(combos):
+            one_pass(i, fmt, ps)
+    barrier()
+    per_launch = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in combos]
+                  for _ in range(args.steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.kernel_launch_count()
+    barrier()
+    t0.record()
+    for s in range(args.steps):
+        for i, (_, _, fmt, ps) in enumerate(combos):
+            one_pass(i, fmt, ps, per_launch[s][i])
+    t1.record()
+    barrier()
+    launches = _lib.kernel_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    bytes_per_pass = 8.0 * n
+    value = bytes_per_pass * len(combos) * args.steps * world / (total_ms * 1e-3) / 1e9
+
+    # per-kernel launch durations (CUDA events inside the timed region)
+    by_kernel, by_combo = {}, {}
+    for s in range(args.steps):
+        for i, (cname, mname, _, _) in enumerate(combos):
+            d = per_launch[s][i][0].elapsed_time(per_launch[s][i][1])
+            by_kernel.setdefault(mname, []).append(d)
+            by_combo.setdefault(cname, []).append(d)
+    peak, peak_src = peaks()
+    kernels = {KERNEL_OF_MODE[k]: {"avg_ms": statistics.mean(v), "GBps": bytes_per_pass / (statistics.mean(v) * 1e-3) / 1e9,
+                                   "launches": len(v)} for k, v in by_kernel.items()}
+    dom_mode = max(by_kernel, key=lambda k: sum(by_kernel[k]))
+    dom = kernels[KERNEL_OF_MODE[dom_mode]]
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"                      # dram bytes per launch from the ncu --set full capture
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get(KERNEL_OF_MODE[dom_mode])
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": KERNEL_OF_MODE[dom_mode], "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": dom["GBps"] / peak, "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_pass,
+                "peak_source": peak_src, "share_of_step": sum(by_kernel[dom_mode]) / sum(sum(v) for v in by_kernel.values())}
+
+    # ---- e2e: same sweep through the C ABI's host-buffer entry point (pinned host memory) ----
+    e2e = None
+    try:
+        n_h = n
+        xh = torch.empty(n_h, dtype=torch.float32).pin_memory()
+        xh.copy_(x[:n_h])
+        yh = torch.empty(n_h, dtype=torch.float32).pin_memory()
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+
+        def host_sweep():
+            for _, _, fmt, ps in combos:
+                st = lib.lof_round_params_host(xh.data_ptr(), yh.data_ptr(), n_h, 0, C.byref(fmt), C.byref(ps), 1.0,
+                                               C.byref(rng), first_index, local)
+                if st != 0:
+                    raise RuntimeError(lib.lof_last_error_string().decode())
+        host_sweep()                                             # warm-up (allocates the staging buffers)
+        barrier()
+        l0 = _lib.kernel_launch_count()
+        w0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            host_sweep()
+        torch.cuda.synchronize()
+        w1 = time.perf_counter()
+        e2e_launches = _lib.kernel_launch_count() - l0
+        barrier()
+        el = torch.tensor([w1 - w0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        e2e = {"value": 8.0 * n_h * len(combos) * e2e_steps * world / float(el.item()) / 1e9, "unit": "GB/s",
+               "h2d_bytes_per_step": 4 * n_h * len(combos), "d2h_bytes_per_step": 4 * n_h * len(combos),
+               "steps": e2e_steps, "api": "lof_round_params_host (C ABI, pinned host buffers, chunked 3-stream pipeline)",
+               "gpu_launches": int(e2e_launches)}
+        del xh, yh
+    except Exception as exc:  # pinned allocation can fail on a small host
+        e2e = {"value": None, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(exc)}
+
+    other = {}
+    cpu_baseline = None
+    if rank == 0:
+        other = side_measurements(torch, lib, _lib, dev, x, y, stream)
+        if world == 1:
+            cpu_baseline = cpu_reference_sample(x[: 1 << 24].cpu().numpy(), budget_s=20.0)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": "virtual_round_GBps", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32 bit arithmetic on fp32 containers", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "elements_per_gpu": n, "passes_per_step": len(combos),
+                   "bytes_per_element": 8, "l2": "inputs (1 GiB) larger than L2 (126 MB); no flush needed",
+                   "parallelism": f"row-shard x{world}, no collective"},
+        "roofline": roofline, "kernels": kernels,
+        "sweep_GBps": {k: bytes_per_pass / (statistics.mean(v) * 1e-3) / 1e9 for k, v in by_combo.items()},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu_baseline, "other": other,
+    }
+    print(json.dumps(line))
+
+
+def side_measurements(torch, lib, _lib, dev, x, y, stream):
+    """mx_round (C3 shape) and lof_gemm, outside the timed region: reported next to the headline."""
+    out = {}
+    peak, _ = peaks()
+    try:
+        e8 = _lib.CFormat(8, 0, 127, 0, 0, 1, 0)
+        ps = _lib.CProjSpec(0, 0, 0)
+        n = 16384 * 16384
+        for variant in (0, 1):
+            _lib.set_option("mx.variant", variant)
+            for fname, (bw, m, bias, ov, sg) in (("mxfp8_e4m3", (8, 3, 7, 1, 0)), ("mxfp4_e2m1", (4, 1, 1, 1, 0))):
+                fmt = _lib.CFormat(bw, m, bias, ov, 0, sg, 0)
+                call = lambda: lib.lof_mx_round_f32(x.data_ptr(), y.data_ptr(), n, 32, C.byref(e8), C.byref(fmt),
+                                                    C.byref(ps), C.byref(ps), None, 0, stream)
+                for _ in range(3):
+                    assert call() == 0
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(10):
+                    call()
+                b.record()
+                torch.cuda.synchronize()
+                gbps = 8.0 * n * 10 / (a.elapsed_time(b) * 1e-3) / 1e9
+                out[f"mx_round_{fname}_bs32_16384x16384_variant{variant}"] = {"GBps": gbps, "frac_of_hbm_peak": gbps / peak}
+        _lib.set_option("mx.variant", 0)
+    except Exception as exc:
+        out["mx_round_error"] = str(exc)
+    try:
+        M = N = K = 2048
+        A = torch.rand(M, K, device=dev) * 2 - 1
+        B = torch.rand(K, N, device=dev) * 2 - 1
+        Cm = torch.empty(M, N, device=dev)
+        ps = _lib.CProjSpec(0, 0, 0)
+        call = lambda: lib.lof_gemm_f32(A.data_ptr(), B.data_ptr(), Cm.data_ptr(), M, N, K, 10, C.byref(ps), 256, 1.0, 0.0,
+                                        None, stream)
+        assert call() == 0
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            call()
+        b.record()
+        torch.cuda.synchronize()
+        out["lof_gemm_exact_2048^3_accum10_RNE_kc256"] = {"TFLOPs": 2.0 * M * N * K * 3 / (a.elapsed_time(b) * 1e-3) / 1e12,
+                                                        "note": "per-FMA rounding, SIMT (bit-exact vs BLIS reference)"}
+    except Exception as exc:
+        out["lof_gemm_error"] = str(exc)
+    return out
+
+
+# -------------------------------------------------------------------------------- CPU reference
+def _load_cpu_impl():
+    """The reference's own CPU path (oracle/_ref, compiled from /root/reference) if the prebuilt shim
+    loads and runs on this host, else the oracle port.  Probed in a subprocess so an illegal
+    instruction on a different CPU cannot take the benchmark down."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle_lib as L
+    kind = "port"
+    if L.REF_SO.exists():
+        probe = ("import sys; sys.path.insert(0, %r); import numpy as np, oracle_lib as L; "
+                 "x = np.linspace(-3, 3, 4096, dtype=np.float32); "
+                 "a = L.r_round_params(x, L.FORMATS['e4m3_b7']); b = L.o_round_params(x, L.FORMATS['e4m3_b7']); "
+                 "assert L.bits_equal(a, b)") % str(ROOT / "tests")
+        try:
+            if subprocess.run([sys.executable, "-c", probe], timeout=120, capture_output=True).returncode == 0:
+                kind = "reference"
+        except Exception:
+            pass
+    L.build_oracle()
+    return L, kind
+
+
+def cpu_reference_sample(x_np, budget_s: float):
+    """Time the reference's scalar virtual_round (lo_float.h:2843-2939 looped by oracle/ref_shim.cpp,
+    OpenMP over all host threads) on a bounded sample of the same workload."""
+    import numpy as np
+    L, kind = _load_cpu_impl()
+    threads = os.cpu_count() or 1
+    det_n = x_np.size
+    sto_n = min(x_np.size, 1 << 18)          # the reference re-seeds a std::mt19937 per element in the SR modes
+    total_bytes, total_s = 0.0, 0.0
+    t_start = time.perf_counter()
+    for fname, (bw, m, bias, ov, sg) in FORMATS:
+        f = L.fmt(bw, m, bias, ov, sg)
+        for mname, mode, sl in MODES:
+            xs = x_np[:sto_n] if mname.startswith("SR") else x_np[:det_n]
+            t0 = time.perf_counter()
+            if kind == "reference":
+                L.r_round_params(xs, f, mode, sl, threads=threads)
+            else:
+                L.o_round_params(xs, f, mode, sl, seed=1)
+            dt = time.perf_counter() - t0
+            total_bytes += 8.0 * xs.size
+            total_s += dt
+        if time.perf_counter() - t_start > budget_s:
+            break
+    return {"value": total_bytes / total_s / 1e9, "unit": "GB/s", "cores": threads, "kind": kind,
+            "sample": f"same sweep on the first 2^{int(np.log2(det_n))} elements (SR modes: 2^{int(np.log2(sto_n))}), "
+                      f"scalar virtual_round loop, OpenMP x{threads}, {total_s:.1f} s of CPU work"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation on this box's host cores, same metric/config."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    import numpy as np
+    rng = np.random.default_rng(2024)
+    n = 1 << 24
+    x = (rng.standard_normal(n) * np.exp2(rng.integers(-12, 13, n))).astype(np.float32)
+    L, kind = _load_cpu_impl()
+    threads = os.cpu_count() or 1
+    sto_n = 1 << 18
+
+    def step():
+        nbytes = 0.0
+        for fname, (bw, m, bias, ov, sg) in FORMATS:
+            f = L.fmt(bw, m, bias, ov, sg)
+            for mname, mode, sl in MODES:
+                xs = x[:sto_n] if mname.startswith("SR") else x
+                if kind == "reference":
+                    L.r_round_params(xs, f, mode, sl, threads=threads)
+                else:
+                    L.o_round_params(xs, f, mode, sl, seed=1)
+                nbytes += 8.0 * xs.size
+        return nbytes
+    for _ in range(min(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    total = 0.0
+    for _ in range(args.steps):
+        total += step()
+    dt = time.perf_counter() - t0
+    value = total / dt / 1e9
+    sample = (f"each step = the 20-pass sweep on a 2^24-element sample (SR modes 2^18: the reference re-seeds a "
+              f"std::mt19937 per element), scalar virtual_round loop, OpenMP x{threads}")
+    print(json.dumps({
+        "impl": "reference", "metric": "virtual_round_GBps", "value": value, "unit": "GB/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit arithmetic on fp32 containers", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,206 @@
+/*
+ * lofloat_b200.h -- C ABI of the B200-native LoFloat virtual-rounding hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every entry
+ * point names the reference launcher it replaces (paths relative to /root/reference).
+ * Unless stated otherwise pointers are DEVICE pointers on the current CUDA device, calls
+ * are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ * stream, which is what the reference uses, Lof_kernel.cu:47,59,80) and return a
+ * lof_status_t.  There is no CPU fallback: without a usable CUDA device every compute
+ * entry point returns LOF_ERR_NO_DEVICE / LOF_ERR_CUDA.
+ *
+ * Parameter structs keep the reference's field meaning and enum VALUES
+ * (src/fp_tools.hpp:13-124, 78-88, 187-252), so a binding can copy them field by field.
+ */
+#ifndef LOFLOAT_B200_H
+#define LOFLOAT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LOFLOAT_B200_ABI_VERSION 1
+
+/* the library is built with -fvisibility=hidden; only the entry points below are exported */
+#if defined(__GNUC__)
+#define LOF_API __attribute__((visibility("default")))
+#else
+#define LOF_API
+#endif
+
+/* lo_float::Rounding_Mode, fp_tools.hpp:13-28 (same integer values) */
+typedef enum {
+    LOF_RoundToNearestEven = 0,
+    LOF_RoundTowardsZero = 1,
+    LOF_RoundAwayFromZero = 2,
+    LOF_StochasticRoundingA = 3,
+    LOF_RoundToNearestOdd = 4,
+    LOF_RoundDown = 5,
+    LOF_RoundUp = 6,
+    LOF_RoundTiesToAway = 7,
+    LOF_StochasticRoundingB = 8,
+    LOF_StochasticRoundingC = 9,
+    LOF_True_StochasticRounding = 10,
+    LOF_ProbabilisticRounding = 11,
+    LOF_RoundToOdd = 12,
+    LOF_RoundTiesTowardsZero = 13,
+    LOF_StochasticRoundingD = 14,
+    LOF_NUM_ROUNDING_MODES = 15
+} lof_rounding_mode_t;
+
+typedef enum { LOF_OvfInf = 0, LOF_SatFinite = 1, LOF_SatPropagate = 2 } lof_saturation_mode_t; /* fp_tools.hpp:38-41 */
+typedef enum { LOF_Signed = 0, LOF_Unsigned = 1 } lof_signedness_t;                             /* fp_tools.hpp:30-32 */
+typedef enum { LOF_Extended = 0, LOF_Saturating = 1 } lof_inf_behavior_t;                       /* fp_tools.hpp:34-36 */
+typedef enum { LOF_NaN_3109 = 0, LOF_NaN_754 = 1 } lof_nan_behavior_t;                          /* fp_tools.hpp:44-46 */
+typedef enum { LOF_NegtoZero = 0, LOF_NegtoNaN = 1 } lof_unsigned_behavior_t;                   /* fp_tools.hpp:48-50 */
+
+/* container (storage) type of the tensor being rounded.  The reference dispatches
+ * float/double/c10::Half (LoPy_bind.cpp:83,133); bf16 is new. */
+typedef enum { LOF_F32 = 0, LOF_F16 = 1, LOF_BF16 = 2, LOF_F64 = 3 } lof_dtype_t;
+
+typedef enum {
+    LOF_OK = 0,
+    LOF_ERR_INVALID_ARG = 1,   /* null pointer, negative size, malformed format        */
+    LOF_ERR_UNSUPPORTED = 2,   /* e.g. MX block size not in {16,32,64,128,256}         */
+    LOF_ERR_CUDA = 3,          /* a CUDA call failed; see lof_last_error_string()      */
+    LOF_ERR_NO_DEVICE = 4,     /* no CUDA device: there is NO CPU fallback             */
+    LOF_ERR_ALLOC = 5
+} lof_status_t;
+
+/* lo_float::FloatingPointParams without the Inf/NaN functor objects (they are never read
+ * on this path: lo_float.h:2843-2939), fp_tools.hpp:187-252 */
+typedef struct lof_format_t {
+    int32_t bitwidth;           /* total bits incl. sign                              */
+    int32_t mantissa_bits;      /* explicit fraction bits                             */
+    int32_t bias;               /* exponent bias                                      */
+    int32_t ov_behavior;        /* lof_inf_behavior_t                                 */
+    int32_t na_behavior;        /* lof_nan_behavior_t   (carried, not read)           */
+    int32_t is_signed;          /* lof_signedness_t                                   */
+    int32_t unsigned_behavior;  /* lof_unsigned_behavior_t (carried, not read)        */
+} lof_format_t;
+
+/* lo_float::ProjSpec, fp_tools.hpp:78-88 */
+typedef struct lof_projspec_t {
+    int32_t rounding_mode;      /* lof_rounding_mode_t                                */
+    int32_t saturation_mode;    /* lof_saturation_mode_t (carried, not read)          */
+    int32_t stoch_length;       /* random bits for StochasticRoundingA..D             */
+} lof_projspec_t;
+
+/* Counter-based RNG state for the stochastic modes: Philox4x32-10 keyed by `seed`; the
+ * 32-bit word of element i is word (i & 3) of block (i >> 2) at counter offset `offset`.
+ * Results depend only on (seed, offset, global element index) -- never on launch geometry
+ * or sharding -- unlike the reference's device hash (lo_float.h:83-98).  NULL = {0, 0}. */
+typedef struct lof_rng_t {
+    uint64_t seed;
+    uint64_t offset;
+} lof_rng_t;
+
+/* ---------------------------------------------------------------------------------------
+ * Elementwise virtual rounding.
+ * ------------------------------------------------------------------------------------- */
+
+/* out[i] = virtual_round(scale * in[i], *fmt, *ps)            (out may alias in)
+ * Replaces  lo_float::round_fp_params<T>(T* inout, n, params, ps, scale)
+ *           src/Lof_kernel.cu:49-60 (kernel :50, launcher :58), whose element function is
+ *           lo_float::virtual_round(value, FloatingPointParams, ProjSpec) lo_float.h:2843-2939.
+ * `first_index` is the global index of in[0] (row-sharded tensors pass their shard offset
+ * so stochastic results do not depend on the partition). */
+LOF_API int lof_round_params(const void* in, void* out, int64_t n, int dtype,
+                     const lof_format_t* fmt, const lof_projspec_t* ps, double scale,
+                     const lof_rng_t* rng, uint64_t first_index, void* stream);
+
+/* out[i] = virtual_round(scale * in[i], mantissa_bits, *ps)   (out may alias in)
+ * Replaces  lo_float::round_mantissa<T>(const T* in, T* out, n, mantissa_bits, ps, scale)
+ *           src/Lof_kernel.cu:37-48; element function lo_float.h:2715-2756. */
+LOF_API int lof_round_mantissa(const void* in, void* out, int64_t n, int dtype, int mantissa_bits,
+                       const lof_projspec_t* ps, double scale,
+                       const lof_rng_t* rng, uint64_t first_index, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * MX (microscaling) block rounding, fp32.
+ * ------------------------------------------------------------------------------------- */
+
+/* Per contiguous block of `block_size` elements (16/32/64/128/256; trailing partial block
+ * allowed): amax = max|x|; scale = virtual_round(amax / priv_max_normal, *scale_fmt,
+ * {ps_scale->rounding_mode, -, 0}); out = scale > 0 ? virtual_round(in / scale, *elem_fmt,
+ * *ps_elem) * scale : 0.                                     (out may alias in)
+ * Replaces  lo_float::run_virtual_mx_round(float* inout, n, block_size, params_public,
+ *           params_private, ps_public, ps_private)  src/Lof_kernel.cu:70-94 (kernel
+ *           src/mx_round.cuh:27-214); results follow the reference's CPU definition
+ *           LoPy_bind.cpp:197-215 == lo_float.h:4311-4383 (amax DIVIDED by priv_max_normal).
+ * `first_index` must be a multiple of block_size. */
+LOF_API int lof_mx_round_f32(const float* in, float* out, int64_t n, int block_size,
+                     const lof_format_t* scale_fmt, const lof_format_t* elem_fmt,
+                     const lof_projspec_t* ps_scale, const lof_projspec_t* ps_elem,
+                     const lof_rng_t* rng, uint64_t first_index, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * LoFloat-accumulation GEMM, fp32 row-major contiguous A(MxK), B(KxN), C(MxN).
+ * ------------------------------------------------------------------------------------- */
+
+/* Exact mode: per output element and per kc-panel of K,
+ *     acc = 0; for l in panel: acc = virtual_round(round_to_odd_fma(a_il, b_lj, acc), accum_mant_bits, *ps)
+ *     panel *= alpha; C = first panel ? (beta == 0 ? panel : beta*C + panel) : C + panel
+ * kc = 256 reproduces the reference CPU path bit for bit (bli_sgemm + lof_sgemm_ukr,
+ * src/blis_lof_gemm.hpp:147-262, BLIS generic KC = 256); kc <= 0 = one panel over all K,
+ * the semantics of the reference CUDA leaf (src/cutlass_gemms.cuh:97-168) which, unlike
+ * the CPU path, ignores *ps (always RNE) -- pass ps = RNE to reproduce it.
+ * Replaces  torch::Tensor lo_float::LoF_gemm(A, B, accum_mant_bits, round_mode,
+ *           stochastic_rounding_bits, scale_a, scale_b)  src/Lof_kernel.cu:96-154 with
+ *           alpha = 1/(scale_a*scale_b), beta = 0 (cutlass_gemms.cuh:1777-1787). */
+LOF_API int lof_gemm_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                 int accum_mant_bits, const lof_projspec_t* ps, int64_t kc,
+                 float alpha, float beta, const lof_rng_t* rng, void* stream);
+
+/* Chunked tensor-core mode (tcgen05): C = alpha * sum over k-chunks, where after every
+ * k_chunk columns of K the fp32 partial product from the tensor core is folded into the
+ * running accumulator with ONE rounding into the accumulator format:
+ *     acc = virtual_round(acc + partial_chunk, acc_fmt or accum_mant_bits, *ps)
+ * (acc_fmt == NULL -> mantissa-only rounding like the reference; non-NULL adds the
+ * exponent range, e.g. E5M10).  This is the design intent of src/gemms.hpp:430-552
+ * (KR-chunk micro-accumulator); it has no runnable reference.
+ * A and B must be exactly representable in `operand_dtype` (LOF_BF16 today). k_chunk must
+ * be a multiple of 16; M % 128 == 0, N % 128 == 0, K % k_chunk == 0. */
+LOF_API int lof_gemm_chunked_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                         int accum_mant_bits, const lof_format_t* acc_fmt, const lof_projspec_t* ps,
+                         int64_t k_chunk, float alpha, int operand_dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Host-buffer entry points: what a binding calls when the tensor lives in host memory.
+ * The library stages through device memory in chunks and overlaps H2D, kernel and D2H on
+ * three streams; it blocks until `out_host` is complete.  Pinned host buffers give full
+ * PCIe bandwidth, pageable ones work but are slower.  `device` < 0 = current device.
+ * ------------------------------------------------------------------------------------- */
+LOF_API int lof_round_params_host(const void* in_host, void* out_host, int64_t n, int dtype,
+                          const lof_format_t* fmt, const lof_projspec_t* ps, double scale,
+                          const lof_rng_t* rng, uint64_t first_index, int device);
+LOF_API int lof_round_mantissa_host(const void* in_host, void* out_host, int64_t n, int dtype, int mantissa_bits,
+                            const lof_projspec_t* ps, double scale,
+                            const lof_rng_t* rng, uint64_t first_index, int device);
+LOF_API int lof_mx_round_f32_host(const float* in_host, float* out_host, int64_t n, int block_size,
+                          const lof_format_t* scale_fmt, const lof_format_t* elem_fmt,
+                          const lof_projspec_t* ps_scale, const lof_projspec_t* ps_elem,
+                          const lof_rng_t* rng, uint64_t first_index, int device);
+
+/* ---------------------------------------------------------------------------------------
+ * Introspection / diagnostics.
+ * ------------------------------------------------------------------------------------- */
+LOF_API int         lof_abi_version(void);
+LOF_API const char* lof_status_string(int status);
+LOF_API const char* lof_last_error_string(void);          /* thread-local detail of the last failure  */
+LOF_API uint64_t    lof_kernel_launch_count(void);        /* kernels launched by this library so far  */
+LOF_API float       lof_mx_priv_max_normal(const lof_format_t* elem_fmt);  /* (2 - 2^-m) * 2^max_exp  */
+
+/* Tuning knobs used by bench.py / the profiling scripts to compare kernel variants on the
+ * same inputs.  key: "round.unroll", "round.ctas_per_sm", "mx.variant" (0 = shuffle,
+ * 1 = TMA-staged), "mx.ctas_per_sm", "host.chunk_bytes".  Returns LOF_ERR_INVALID_ARG for
+ * an unknown key. */
+LOF_API int lof_set_option(const char* key, int64_t value);
+LOF_API int lof_get_option(const char* key, int64_t* value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOFLOAT_B200_H */

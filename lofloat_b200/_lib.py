@@ -1,0 +1,117 @@
+"""ctypes loader for liblofloat_b200.so (the C ABI declared in include/lofloat_b200.h).
+
+The library is the product: there is no Python or CPU fallback.  If the shared object is
+missing, or no CUDA device is usable, every op raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "liblofloat_b200.so"
+
+# status codes (include/lofloat_b200.h)
+LOF_OK, LOF_ERR_INVALID_ARG, LOF_ERR_UNSUPPORTED, LOF_ERR_CUDA, LOF_ERR_NO_DEVICE, LOF_ERR_ALLOC = range(6)
+# dtypes
+LOF_F32, LOF_F16, LOF_BF16, LOF_F64 = range(4)
+
+# every symbol include/lofloat_b200.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = (
+    "lof_round_params", "lof_round_mantissa", "lof_mx_round_f32", "lof_gemm_f32", "lof_gemm_chunked_f32",
+    "lof_round_params_host", "lof_round_mantissa_host", "lof_mx_round_f32_host",
+    "lof_abi_version", "lof_status_string", "lof_last_error_string", "lof_kernel_launch_count",
+    "lof_mx_priv_max_normal", "lof_set_option", "lof_get_option",
+)
+
+
+class CFormat(C.Structure):
+    """lof_format_t"""
+    _fields_ = [("bitwidth", C.c_int32), ("mantissa_bits", C.c_int32), ("bias", C.c_int32),
+                ("ov_behavior", C.c_int32), ("na_behavior", C.c_int32), ("is_signed", C.c_int32),
+                ("unsigned_behavior", C.c_int32)]
+
+
+class CProjSpec(C.Structure):
+    """lof_projspec_t"""
+    _fields_ = [("rounding_mode", C.c_int32), ("saturation_mode", C.c_int32), ("stoch_length", C.c_int32)]
+
+
+class CRng(C.Structure):
+    """lof_rng_t"""
+    _fields_ = [("seed", C.c_uint64), ("offset", C.c_uint64)]
+
+
+class LoFloatError(RuntimeError):
+    """A C-ABI call failed (mirrors the reference's TORCH_CHECK -> RuntimeError)."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(message)
+        self.status = status
+
+
+_lib = None
+
+
+def _declare(lib):
+    vp, i64, i32, u64, f64, f32 = C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_double, C.c_float
+    PF, PP, PR = C.POINTER(CFormat), C.POINTER(CProjSpec), C.POINTER(CRng)
+    lib.lof_round_params.argtypes = [vp, vp, i64, i32, PF, PP, f64, PR, u64, vp]
+    lib.lof_round_mantissa.argtypes = [vp, vp, i64, i32, i32, PP, f64, PR, u64, vp]
+    lib.lof_mx_round_f32.argtypes = [vp, vp, i64, i32, PF, PF, PP, PP, PR, u64, vp]
+    lib.lof_gemm_f32.argtypes = [vp, vp, vp, i64, i64, i64, i32, PP, i64, f32, f32, PR, vp]
+    lib.lof_gemm_chunked_f32.argtypes = [vp, vp, vp, i64, i64, i64, i32, PF, PP, i64, f32, i32, vp]
+    lib.lof_round_params_host.argtypes = [vp, vp, i64, i32, PF, PP, f64, PR, u64, i32]
+    lib.lof_round_mantissa_host.argtypes = [vp, vp, i64, i32, i32, PP, f64, PR, u64, i32]
+    lib.lof_mx_round_f32_host.argtypes = [vp, vp, i64, i32, PF, PF, PP, PP, PR, u64, i32]
+    for name in ("lof_round_params", "lof_round_mantissa", "lof_mx_round_f32", "lof_gemm_f32", "lof_gemm_chunked_f32",
+                 "lof_round_params_host", "lof_round_mantissa_host", "lof_mx_round_f32_host", "lof_abi_version"):
+        getattr(lib, name).restype = i32
+    lib.lof_status_string.argtypes = [i32]
+    lib.lof_status_string.restype = C.c_char_p
+    lib.lof_last_error_string.restype = C.c_char_p
+    lib.lof_kernel_launch_count.restype = u64
+    lib.lof_mx_priv_max_normal.argtypes = [PF]
+    lib.lof_mx_priv_max_normal.restype = f32
+    lib.lof_set_option.argtypes = [C.c_char_p, i64]
+    lib.lof_set_option.restype = i32
+    lib.lof_get_option.argtypes = [C.c_char_p, C.POINTER(i64)]
+    lib.lof_get_option.restype = i32
+
+
+def lib():
+    """Load (once) and return the C-ABI library.  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        path = Path(os.environ.get("LOFLOAT_B200_LIB", LIB_PATH))
+        if not path.exists():
+            raise ImportError(
+                f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C lofloat_b200/csrc`). lofloat_b200 has no CPU/Python fallback.")
+        handle = C.CDLL(str(path))
+        _declare(handle)
+        _lib = handle
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != LOF_OK:
+        L = lib()
+        detail = L.lof_last_error_string().decode()
+        kind = L.lof_status_string(status).decode()
+        raise LoFloatError(status, f"{what}: {detail or kind}")
+
+
+def set_option(key: str, value: int) -> None:
+    check(lib().lof_set_option(key.encode(), int(value)), f"lof_set_option({key})")
+
+
+def get_option(key: str) -> int:
+    v = C.c_int64(0)
+    check(lib().lof_get_option(key.encode(), C.byref(v)), f"lof_get_option({key})")
+    return int(v.value)
+
+
+def kernel_launch_count() -> int:
+    return int(lib().lof_kernel_launch_count())

@@ -1,0 +1,490 @@
+// lof_api.cu -- C ABI of liblofloat_b200.so (declared in include/lofloat_b200.h).
+//
+// Host side of the hot path: argument validation (the reference's TORCH_CHECKs,
+// LoPy_bind.cpp:172-173, Lof_kernel.cu:90,106-113 become status codes), folding a
+// (format, source type) pair into a RoundPlan once per call instead of per element
+// (the reference calls std::pow twice per element, lo_float.h:2861), kernel selection, and
+// the host-buffer pipeline (chunked H2D / kernel / D2H on three streams).
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "lof_core.cuh"
+#include "lof_mx_kernels.cuh"
+#include "lof_round_kernels.cuh"
+
+namespace lof {
+cudaError_t launch_gemm_exact(int mode, const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                              int accum_mant_bits, int len, int64_t kc, float alpha, float beta, const RngArgs& rng,
+                              cudaStream_t stream);
+cudaError_t launch_mx_tma(int mode, const float* in, float* out, int64_t n, const MxArgs& a, const RngArgs& rng,
+                          const RngArgs& rng_scale, uint64_t first_index, const MxLaunchCfg& cfg, cudaStream_t stream,
+                          int* launches, bool* handled);
+cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                           int mode, int accum_mant_bits, const RoundPlan* acc_plan, int64_t k_chunk, float alpha,
+                           int operand_dtype, cudaStream_t stream, int* launches, std::string* err);
+}  // namespace lof
+
+using namespace lof;
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+
+struct Options {
+    std::atomic<int64_t> round_unroll{4};
+    std::atomic<int64_t> round_ctas_per_sm{8};
+    std::atomic<int64_t> mx_variant{0};
+    std::atomic<int64_t> mx_ctas_per_sm{8};
+    std::atomic<int64_t> host_chunk_bytes{32ll << 20};
+} g_opt;
+
+int fail(int status, const std::string& msg)
+{
+    g_last_error = msg;
+    return status;
+}
+
+int cuda_fail(cudaError_t e, const char* what)
+{
+    return fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? LOF_ERR_NO_DEVICE : LOF_ERR_CUDA,
+                std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+int num_sms()
+{
+    static int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (dev != cached_dev) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        cached = v;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+struct SrcGeom { int mant, bias; };
+bool src_geom(int dtype, SrcGeom* g)
+{
+    switch (dtype) {
+    case LOF_F32:  *g = {23, 127};  return true;
+    case LOF_F16:  *g = {10, 15};   return true;
+    case LOF_BF16: *g = {7, 127};   return true;
+    case LOF_F64:  *g = {52, 1023}; return true;
+    default: return false;
+    }
+}
+
+uint16_t f32_to_f16_bits(float f) { return __half_as_ushort(__float2half_rn(f)); }
+uint16_t f32_to_bf16_bits(float f) { return __bfloat16_as_ushort(__float2bfloat16_rn(f)); }
+
+// Fold (format, source container) into the per-launch constants.
+int make_plan(const lof_format_t* f, int dtype, int mode, int stoch_len, RoundPlan* p)
+{
+    SrcGeom g;
+    if (!src_geom(dtype, &g)) return fail(LOF_ERR_INVALID_ARG, "unknown dtype");
+    if (!f) return fail(LOF_ERR_INVALID_ARG, "format is NULL");
+    const int ebits = f->bitwidth - f->mantissa_bits - (f->is_signed == LOF_Signed ? 1 : 0);
+    if (f->mantissa_bits < 0 || f->mantissa_bits > 52 || ebits < 0 || ebits > 30)
+        return fail(LOF_ERR_INVALID_ARG, "format: need 0 <= mantissa_bits <= 52 and 0 <= exponent bits <= 30");
+    if (f->is_signed != LOF_Signed && f->is_signed != LOF_Unsigned) return fail(LOF_ERR_INVALID_ARG, "format: bad signedness");
+    if (mode < 0 || mode >= LOF_NUM_ROUNDING_MODES) return fail(LOF_ERR_INVALID_ARG, "unknown rounding mode");
+    const int to_max_exp = (1 << ebits) - 1 - f->bias;          // lo_float.h:2857-2859
+    const int to_min_exp = 1 - f->bias;                          // :2860
+    const float min_val = (float)(std::pow(2.0, (double)to_min_exp) * std::pow(2.0, (double)-f->mantissa_bits));  // :2861
+    p->min_val = min_val;
+    p->half_val = min_val * 0.5f;                                // :2894
+    switch (dtype) {                                             // from_double<From>((double)To_min_val), :2905
+    case LOF_F32: { uint32_t b; std::memcpy(&b, &min_val, 4); p->min_mag_bits = b; break; }
+    case LOF_F64: { double d = (double)min_val; uint64_t b; std::memcpy(&b, &d, 8); p->min_mag_bits = b; break; }
+    case LOF_F16: p->min_mag_bits = f32_to_f16_bits(min_val); break;
+    default:      p->min_mag_bits = f32_to_bf16_bits(min_val); break;
+    }
+    p->min_exp_b = to_min_exp + g.bias;
+    p->max_exp_b = to_max_exp + g.bias;
+    p->shiftN = g.mant - f->mantissa_bits;
+    p->stoch_len = stoch_len;
+    p->saturating = (f->ov_behavior == LOF_Saturating);
+    p->pad_ = 0;
+    // Stochastic bit counts outside [0, r] make the reference shift by a negative amount
+    // (undefined, lo_float.h:664,751,810,833); refuse instead of inventing a result.
+    if (mode == LOF_StochasticRoundingA || mode == LOF_StochasticRoundingB || mode == LOF_StochasticRoundingC ||
+        mode == LOF_StochasticRoundingD) {
+        const int rmin = p->shiftN > 1 ? p->shiftN : 1;
+        if (stoch_len < 0 || stoch_len > rmin || stoch_len > 31)
+            return fail(LOF_ERR_INVALID_ARG, "stoch_length must be in [0, container_mantissa - target_mantissa]");
+    }
+    return LOF_OK;
+}
+
+RngArgs make_rng(const lof_rng_t* rng, uint32_t stream_const)
+{
+    RngArgs r;
+    const uint64_t seed = rng ? rng->seed : 0, off = rng ? rng->offset : 0;
+    r.key0 = (uint32_t)seed; r.key1 = (uint32_t)(seed >> 32);
+    r.off0 = (uint32_t)off;  r.off1 = (uint32_t)(off >> 32) ^ stream_const;
+    return r;
+}
+
+RoundLaunchCfg round_cfg()
+{
+    RoundLaunchCfg c;
+    c.unroll = (int)g_opt.round_unroll.load();
+    c.ctas_per_sm = (int)g_opt.round_ctas_per_sm.load();
+    c.num_sms = num_sms();
+    return c;
+}
+
+int round_common(bool params, const void* in, void* out, int64_t n, int dtype, const lof_format_t* fmt,
+                 int mantissa_bits, const lof_projspec_t* ps, double scale, const lof_rng_t* rng,
+                 uint64_t first_index, void* stream)
+{
+    if (n < 0) return fail(LOF_ERR_INVALID_ARG, "n < 0");
+    if (!ps) return fail(LOF_ERR_INVALID_ARG, "projspec is NULL");
+    SrcGeom g;
+    if (!src_geom(dtype, &g)) return fail(LOF_ERR_INVALID_ARG, "unknown dtype");
+    const int mode = ps->rounding_mode;
+    if (mode < 0 || mode >= LOF_NUM_ROUNDING_MODES) return fail(LOF_ERR_INVALID_ARG, "unknown rounding mode");
+    RoundPlan plan;
+    std::memset(&plan, 0, sizeof plan);
+    int r = 0;
+    if (params) {
+        const int st = make_plan(fmt, dtype, mode, ps->stoch_length, &plan);
+        if (st != LOF_OK) return st;
+    } else {
+        r = g.mant - mantissa_bits;                                           // -kDigitShift, lo_float.h:2722
+        if (mantissa_bits < 0) return fail(LOF_ERR_INVALID_ARG, "mantissa_bits < 0");
+        if (r > 0 && (mode == LOF_StochasticRoundingA || mode == LOF_StochasticRoundingB ||
+                      mode == LOF_StochasticRoundingC || mode == LOF_StochasticRoundingD) &&
+            (ps->stoch_length < 0 || ps->stoch_length > r || ps->stoch_length > 31))
+            return fail(LOF_ERR_INVALID_ARG, "stoch_length must be in [0, container_mantissa - mantissa_bits]");
+    }
+    if (n == 0) return LOF_OK;
+    if (!in || !out) return fail(LOF_ERR_INVALID_ARG, "null tensor pointer");
+    const RoundLaunchCfg cfg = round_cfg();
+    if (cfg.num_sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    const RngArgs ra = make_rng(rng, kStreamElem);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    switch (dtype) {
+    case LOF_F32:  e = launch_round_f32(params, mode, in, out, n, plan, r, ps->stoch_length, scale, ra, first_index, cfg, s); break;
+    case LOF_F16:  e = launch_round_f16(params, mode, in, out, n, plan, r, ps->stoch_length, scale, ra, first_index, cfg, s); break;
+    case LOF_BF16: e = launch_round_bf16(params, mode, in, out, n, plan, r, ps->stoch_length, scale, ra, first_index, cfg, s); break;
+    default:       e = launch_round_f64(params, mode, in, out, n, plan, r, ps->stoch_length, scale, ra, first_index, cfg, s); break;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "virtual_round launch");
+    g_launches.fetch_add(1);
+    return LOF_OK;
+}
+
+size_t dtype_size(int dtype) { return dtype == LOF_F64 ? 8 : dtype == LOF_F32 ? 4 : 2; }
+
+// ---------------------------------------------------------------------------------------
+// host-buffer pipeline: chunk i is copied in on stream A while chunk i-1 runs on stream B
+// and chunk i-2 is copied out on stream C (events order the three stages per buffer).
+// ---------------------------------------------------------------------------------------
+struct HostPipe {
+    static constexpr int kBufs = 3;
+    void* dev[kBufs] = {nullptr, nullptr, nullptr};
+    size_t cap = 0;
+    int device = -1;
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+    cudaEvent_t in_done[kBufs], k_done[kBufs], out_done[kBufs];
+    bool init = false;
+    std::mutex mu;
+
+    int ensure(int dev_id, size_t bytes)
+    {
+        if (init && device == dev_id && cap >= bytes) return LOF_OK;
+        release();
+        cudaError_t e = cudaSetDevice(dev_id);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+        device = dev_id;
+        for (int i = 0; i < kBufs; ++i) {
+            e = cudaMalloc(&dev[i], bytes);
+            if (e != cudaSuccess) { release(); return fail(LOF_ERR_ALLOC, std::string("cudaMalloc staging: ") + cudaGetErrorString(e)); }
+        }
+        cap = bytes;
+        cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking);
+        for (int i = 0; i < kBufs; ++i) {
+            cudaEventCreateWithFlags(&in_done[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&k_done[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&out_done[i], cudaEventDisableTiming);
+        }
+        init = true;
+        return LOF_OK;
+    }
+    void release()
+    {
+        if (init) {
+            for (int i = 0; i < kBufs; ++i) { cudaEventDestroy(in_done[i]); cudaEventDestroy(k_done[i]); cudaEventDestroy(out_done[i]); }
+            cudaStreamDestroy(s_in); cudaStreamDestroy(s_k); cudaStreamDestroy(s_out);
+        }
+        for (int i = 0; i < kBufs; ++i) { if (dev[i]) cudaFree(dev[i]); dev[i] = nullptr; }
+        cap = 0; init = false;
+    }
+};
+HostPipe g_pipe;
+
+// kernel(dev_ptr, elems, first_index_of_chunk, stream) -> status
+template <typename KernelFn>
+int run_host_pipeline(const void* in_host, void* out_host, int64_t n, size_t esize, int64_t granule, int device,
+                      KernelFn&& kernel)
+{
+    if (n < 0) return fail(LOF_ERR_INVALID_ARG, "n < 0");
+    if (n == 0) return LOF_OK;
+    if (!in_host || !out_host) return fail(LOF_ERR_INVALID_ARG, "null host pointer");
+    int dev_id = device;
+    if (dev_id < 0) {
+        cudaError_t e = cudaGetDevice(&dev_id);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    }
+    std::lock_guard<std::mutex> lock(g_pipe.mu);
+    int64_t chunk_elems = (int64_t)(g_opt.host_chunk_bytes.load() / (int64_t)esize);
+    chunk_elems = (chunk_elems / granule) * granule;
+    if (chunk_elems < granule) chunk_elems = granule;
+    if (chunk_elems > n) chunk_elems = ((n + granule - 1) / granule) * granule;
+    int st = g_pipe.ensure(dev_id, (size_t)chunk_elems * esize);
+    if (st != LOF_OK) return st;
+    const int64_t nchunks = (n + chunk_elems - 1) / chunk_elems;
+    const char* src = static_cast<const char*>(in_host);
+    char* dst = static_cast<char*>(out_host);
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int b = (int)(c % HostPipe::kBufs);
+        const int64_t e0 = c * chunk_elems;
+        const int64_t ne = (n - e0) < chunk_elems ? (n - e0) : chunk_elems;
+        if (c >= HostPipe::kBufs) cudaStreamWaitEvent(g_pipe.s_in, g_pipe.out_done[b], 0);   // buffer drained
+        cudaError_t e = cudaMemcpyAsync(g_pipe.dev[b], src + (size_t)e0 * esize, (size_t)ne * esize, cudaMemcpyHostToDevice, g_pipe.s_in);
+        if (e != cudaSuccess) return cuda_fail(e, "H2D copy");
+        cudaEventRecord(g_pipe.in_done[b], g_pipe.s_in);
+        cudaStreamWaitEvent(g_pipe.s_k, g_pipe.in_done[b], 0);
+        st = kernel(g_pipe.dev[b], ne, (uint64_t)e0, (void*)g_pipe.s_k);
+        if (st != LOF_OK) return st;
+        cudaEventRecord(g_pipe.k_done[b], g_pipe.s_k);
+        cudaStreamWaitEvent(g_pipe.s_out, g_pipe.k_done[b], 0);
+        e = cudaMemcpyAsync(dst + (size_t)e0 * esize, g_pipe.dev[b], (size_t)ne * esize, cudaMemcpyDeviceToHost, g_pipe.s_out);
+        if (e != cudaSuccess) return cuda_fail(e, "D2H copy");
+        cudaEventRecord(g_pipe.out_done[b], g_pipe.s_out);
+    }
+    cudaError_t e = cudaStreamSynchronize(g_pipe.s_out);
+    if (e != cudaSuccess) return cuda_fail(e, "host pipeline sync");
+    e = cudaStreamSynchronize(g_pipe.s_k);
+    if (e != cudaSuccess) return cuda_fail(e, "host pipeline sync");
+    return LOF_OK;
+}
+
+int mx_common(const float* in, float* out, int64_t n, int block_size, const lof_format_t* scale_fmt,
+              const lof_format_t* elem_fmt, const lof_projspec_t* ps_scale, const lof_projspec_t* ps_elem,
+              const lof_rng_t* rng, uint64_t first_index, void* stream)
+{
+    if (n < 0) return fail(LOF_ERR_INVALID_ARG, "n < 0");
+    if (!ps_scale || !ps_elem) return fail(LOF_ERR_INVALID_ARG, "projspec is NULL");
+    if (block_size <= 0) return fail(LOF_ERR_INVALID_ARG, "virtual_mx_round: block_size must be positive");        // LoPy_bind.cpp:173
+    if (block_size != 16 && block_size != 32 && block_size != 64 && block_size != 128 && block_size != 256)
+        return fail(LOF_ERR_UNSUPPORTED, "virtual_mx_round: unsupported block_size (use 16/32/64/128/256)");        // Lof_kernel.cu:90
+    if (first_index % (uint64_t)block_size != 0) return fail(LOF_ERR_INVALID_ARG, "first_index must be a multiple of block_size");
+    MxArgs a;
+    std::memset(&a, 0, sizeof a);
+    int st = make_plan(elem_fmt, LOF_F32, ps_elem->rounding_mode, ps_elem->stoch_length, &a.elem);
+    if (st != LOF_OK) return st;
+    st = make_plan(scale_fmt, LOF_F32, ps_scale->rounding_mode, 0, &a.scale);
+    if (st != LOF_OK) return st;
+    a.pmn = lof_mx_priv_max_normal(elem_fmt);
+    a.scale_mode = ps_scale->rounding_mode;
+    a.block_size = block_size;
+    if (n == 0) return LOF_OK;
+    if (!in || !out) return fail(LOF_ERR_INVALID_ARG, "null tensor pointer");
+    MxLaunchCfg cfg;
+    cfg.variant = (int)g_opt.mx_variant.load();
+    cfg.ctas_per_sm = (int)g_opt.mx_ctas_per_sm.load();
+    cfg.num_sms = num_sms();
+    if (cfg.num_sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    const RngArgs re = make_rng(rng, kStreamElem), rs = make_rng(rng, kStreamScale);
+    int launches = 0;
+    cudaError_t e;
+    bool handled = false;
+    if (cfg.variant == 1) {
+        e = launch_mx_tma(ps_elem->rounding_mode, in, out, n, a, re, rs, first_index, cfg, static_cast<cudaStream_t>(stream),
+                          &launches, &handled);
+        if (e != cudaSuccess) return cuda_fail(e, "virtual_mx_round (tma) launch");
+    }
+    if (!handled) {
+        e = launch_mx_shuffle(ps_elem->rounding_mode, in, out, n, a, re, rs, first_index, cfg,
+                              static_cast<cudaStream_t>(stream), &launches);
+        if (e != cudaSuccess) return cuda_fail(e, "virtual_mx_round launch");
+    }
+    g_launches.fetch_add((uint64_t)launches);
+    return LOF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lof_abi_version(void) { return LOFLOAT_B200_ABI_VERSION; }
+
+const char* lof_status_string(int status)
+{
+    switch (status) {
+    case LOF_OK: return "ok";
+    case LOF_ERR_INVALID_ARG: return "invalid argument";
+    case LOF_ERR_UNSUPPORTED: return "unsupported configuration";
+    case LOF_ERR_CUDA: return "CUDA error";
+    case LOF_ERR_NO_DEVICE: return "no CUDA device (no CPU fallback)";
+    case LOF_ERR_ALLOC: return "allocation failed";
+    default: return "unknown status";
+    }
+}
+
+const char* lof_last_error_string(void) { return g_last_error.c_str(); }
+
+uint64_t lof_kernel_launch_count(void) { return g_launches.load(); }
+
+float lof_mx_priv_max_normal(const lof_format_t* p)
+{
+    if (!p) return 0.0f;
+    const int ebits = p->bitwidth - p->mantissa_bits - (p->is_signed == LOF_Signed ? 1 : 0);
+    const int me = (1 << ebits) - 1 - p->bias;
+    return std::ldexp(1.0f, me) * (2.0f - std::ldexp(1.0f, -p->mantissa_bits));     // LoPy_bind.cpp:199-202
+}
+
+int lof_set_option(const char* key, int64_t value)
+{
+    if (!key) return fail(LOF_ERR_INVALID_ARG, "option key is NULL");
+    const std::string k(key);
+    if (k == "round.unroll") { if (value != 1 && value != 2 && value != 4 && value != 8) return fail(LOF_ERR_INVALID_ARG, "round.unroll must be 1/2/4/8"); g_opt.round_unroll = value; }
+    else if (k == "round.ctas_per_sm") { if (value < 1 || value > 64) return fail(LOF_ERR_INVALID_ARG, "round.ctas_per_sm out of range"); g_opt.round_ctas_per_sm = value; }
+    else if (k == "mx.variant") { if (value < 0 || value > 1) return fail(LOF_ERR_INVALID_ARG, "mx.variant must be 0 or 1"); g_opt.mx_variant = value; }
+    else if (k == "mx.ctas_per_sm") { if (value < 1 || value > 64) return fail(LOF_ERR_INVALID_ARG, "mx.ctas_per_sm out of range"); g_opt.mx_ctas_per_sm = value; }
+    else if (k == "host.chunk_bytes") { if (value < (1 << 16)) return fail(LOF_ERR_INVALID_ARG, "host.chunk_bytes too small"); g_opt.host_chunk_bytes = value; }
+    else return fail(LOF_ERR_INVALID_ARG, "unknown option: " + k);
+    return LOF_OK;
+}
+
+int lof_get_option(const char* key, int64_t* value)
+{
+    if (!key || !value) return fail(LOF_ERR_INVALID_ARG, "null argument");
+    const std::string k(key);
+    if (k == "round.unroll") *value = g_opt.round_unroll;
+    else if (k == "round.ctas_per_sm") *value = g_opt.round_ctas_per_sm;
+    else if (k == "mx.variant") *value = g_opt.mx_variant;
+    else if (k == "mx.ctas_per_sm") *value = g_opt.mx_ctas_per_sm;
+    else if (k == "host.chunk_bytes") *value = g_opt.host_chunk_bytes;
+    else return fail(LOF_ERR_INVALID_ARG, "unknown option: " + k);
+    return LOF_OK;
+}
+
+int lof_round_params(const void* in, void* out, int64_t n, int dtype, const lof_format_t* fmt,
+                     const lof_projspec_t* ps, double scale, const lof_rng_t* rng, uint64_t first_index, void* stream)
+{
+    return round_common(true, in, out, n, dtype, fmt, 0, ps, scale, rng, first_index, stream);
+}
+
+int lof_round_mantissa(const void* in, void* out, int64_t n, int dtype, int mantissa_bits, const lof_projspec_t* ps,
+                       double scale, const lof_rng_t* rng, uint64_t first_index, void* stream)
+{
+    return round_common(false, in, out, n, dtype, nullptr, mantissa_bits, ps, scale, rng, first_index, stream);
+}
+
+int lof_mx_round_f32(const float* in, float* out, int64_t n, int block_size, const lof_format_t* scale_fmt,
+                     const lof_format_t* elem_fmt, const lof_projspec_t* ps_scale, const lof_projspec_t* ps_elem,
+                     const lof_rng_t* rng, uint64_t first_index, void* stream)
+{
+    return mx_common(in, out, n, block_size, scale_fmt, elem_fmt, ps_scale, ps_elem, rng, first_index, stream);
+}
+
+int lof_gemm_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int accum_mant_bits,
+                 const lof_projspec_t* ps, int64_t kc, float alpha, float beta, const lof_rng_t* rng, void* stream)
+{
+    if (M < 0 || N < 0 || K < 0) return fail(LOF_ERR_INVALID_ARG, "negative GEMM dimension");
+    if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX) return fail(LOF_ERR_UNSUPPORTED, "GEMM dimension exceeds 2^31-1");
+    if (!ps) return fail(LOF_ERR_INVALID_ARG, "projspec is NULL");
+    const int mode = ps->rounding_mode;
+    if (mode < 0 || mode >= LOF_NUM_ROUNDING_MODES) return fail(LOF_ERR_INVALID_ARG, "unknown rounding mode");
+    if (accum_mant_bits > 23) return fail(LOF_ERR_INVALID_ARG, "accum_mant_bits > 23");
+    if (accum_mant_bits >= 0 && accum_mant_bits < 23 &&
+        (mode == LOF_StochasticRoundingA || mode == LOF_StochasticRoundingB || mode == LOF_StochasticRoundingC ||
+         mode == LOF_StochasticRoundingD) &&
+        (ps->stoch_length < 0 || ps->stoch_length > 23 - accum_mant_bits))
+        return fail(LOF_ERR_INVALID_ARG, "stochastic_rounding_bits must be in [0, 23 - accum_mant_bits]");
+    if (M == 0 || N == 0) return LOF_OK;
+    if (!C || (K > 0 && (!A || !B))) return fail(LOF_ERR_INVALID_ARG, "null matrix pointer");
+    if (num_sms() <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    cudaError_t e = launch_gemm_exact(mode, A, B, C, M, N, K, accum_mant_bits, ps->stoch_length, kc, alpha, beta,
+                                      make_rng(rng, kStreamGemm), static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "lof_gemm launch");
+    g_launches.fetch_add(1);
+    return LOF_OK;
+}
+
+int lof_gemm_chunked_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                         int accum_mant_bits, const lof_format_t* acc_fmt, const lof_projspec_t* ps, int64_t k_chunk,
+                         float alpha, int operand_dtype, void* stream)
+{
+    if (M <= 0 || N <= 0 || K <= 0) return fail(LOF_ERR_INVALID_ARG, "GEMM dimensions must be positive");
+    if (!A || !B || !C || !ps) return fail(LOF_ERR_INVALID_ARG, "null argument");
+    const int mode = ps->rounding_mode;
+    if (mode < 0 || mode >= LOF_NUM_ROUNDING_MODES) return fail(LOF_ERR_INVALID_ARG, "unknown rounding mode");
+    if (mode_uses_rng(mode)) return fail(LOF_ERR_UNSUPPORTED, "chunked GEMM: stochastic accumulator rounding not implemented");
+    RoundPlan plan;
+    std::memset(&plan, 0, sizeof plan);
+    if (acc_fmt) {
+        const int st = make_plan(acc_fmt, LOF_F32, mode, 0, &plan);
+        if (st != LOF_OK) return st;
+    } else if (accum_mant_bits < 0 || accum_mant_bits > 23) {
+        return fail(LOF_ERR_INVALID_ARG, "accum_mant_bits must be in [0, 23]");
+    }
+    if (num_sms() <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    int launches = 0;
+    std::string err;
+    cudaError_t e = launch_gemm_tc(A, B, C, M, N, K, mode, accum_mant_bits, acc_fmt ? &plan : nullptr, k_chunk, alpha,
+                                   operand_dtype, static_cast<cudaStream_t>(stream), &launches, &err);
+    g_launches.fetch_add((uint64_t)launches);
+    if (!err.empty()) return fail(LOF_ERR_UNSUPPORTED, err);
+    if (e != cudaSuccess) return cuda_fail(e, "lof_gemm_chunked launch");
+    return LOF_OK;
+}
+
+int lof_round_params_host(const void* in_host, void* out_host, int64_t n, int dtype, const lof_format_t* fmt,
+                          const lof_projspec_t* ps, double scale, const lof_rng_t* rng, uint64_t first_index, int device)
+{
+    SrcGeom g;
+    if (!src_geom(dtype, &g)) return fail(LOF_ERR_INVALID_ARG, "unknown dtype");
+    return run_host_pipeline(in_host, out_host, n, dtype_size(dtype), 4096, device,
+        [&](void* d, int64_t ne, uint64_t e0, void* s) {
+            return round_common(true, d, d, ne, dtype, fmt, 0, ps, scale, rng, first_index + e0, s);
+        });
+}
+
+int lof_round_mantissa_host(const void* in_host, void* out_host, int64_t n, int dtype, int mantissa_bits,
+                            const lof_projspec_t* ps, double scale, const lof_rng_t* rng, uint64_t first_index, int device)
+{
+    SrcGeom g;
+    if (!src_geom(dtype, &g)) return fail(LOF_ERR_INVALID_ARG, "unknown dtype");
+    return run_host_pipeline(in_host, out_host, n, dtype_size(dtype), 4096, device,
+        [&](void* d, int64_t ne, uint64_t e0, void* s) {
+            return round_common(false, d, d, ne, dtype, nullptr, mantissa_bits, ps, scale, rng, first_index + e0, s);
+        });
+}
+
+int lof_mx_round_f32_host(const float* in_host, float* out_host, int64_t n, int block_size, const lof_format_t* scale_fmt,
+                          const lof_format_t* elem_fmt, const lof_projspec_t* ps_scale, const lof_projspec_t* ps_elem,
+                          const lof_rng_t* rng, uint64_t first_index, int device)
+{
+    if (block_size <= 0) return fail(LOF_ERR_INVALID_ARG, "virtual_mx_round: block_size must be positive");
+    return run_host_pipeline(in_host, out_host, n, 4, 4096, device,      // 4096 is a multiple of every block size
+        [&](void* d, int64_t ne, uint64_t e0, void* s) {
+            return mx_common(static_cast<const float*>(d), static_cast<float*>(d), ne, block_size, scale_fmt, elem_fmt,
+                             ps_scale, ps_elem, rng, first_index + e0, s);
+        });
+}
+
+}  // extern "C"

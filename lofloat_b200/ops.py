@@ -1,0 +1,302 @@
+"""Host-side mirror of the reference's Python extension module `LoFloat.LoFloat`
+(/root/reference/src/LoPy_bind.cpp:281-393): same names, argument meaning and error
+behaviour, implemented as thin calls into the C ABI (include/lofloat_b200.h).
+
+PyTorch is plumbing only: it owns device memory and the current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import threading
+
+import torch
+
+from . import _lib
+from ._lib import CFormat, CProjSpec, CRng, LoFloatError
+
+
+# --------------------------------------------------------------------------------------
+# enums: same names and integer values as the pybind enums (LoPy_bind.cpp:284-313), which
+# are the reference's C++ enums (fp_tools.hpp:13-50).  RoundToNearestOdd and
+# RoundTiesToAway exist in C++ but are missing from the reference binding (:294-308); they
+# are exposed here too.
+# --------------------------------------------------------------------------------------
+class RoundingMode(enum.IntEnum):
+    RoundToNearestEven = 0
+    RoundTowardsZero = 1
+    RoundAwayFromZero = 2
+    StochasticRoundingA = 3
+    RoundToNearestOdd = 4
+    RoundDown = 5
+    RoundUp = 6
+    RoundTiesToAway = 7
+    StochasticRoundingB = 8
+    StochasticRoundingC = 9
+    True_StochasticRounding = 10
+    ProbabilisticRounding = 11
+    RoundToOdd = 12
+    RoundTiesTowardsZero = 13
+    StochasticRoundingD = 14
+
+
+class Signedness(enum.IntEnum):
+    Signed = 0
+    Unsigned = 1
+
+
+class InfBehavior(enum.IntEnum):
+    Extended = 0
+    Saturating = 1
+
+
+class NaNBehavior(enum.IntEnum):
+    _3109 = 0
+    _754 = 1
+
+
+# pybind's .export_values(): the enumerators are also module attributes
+globals().update({m.name: m for e in (RoundingMode, Signedness, InfBehavior) for m in e})
+
+_STOCHASTIC = {RoundingMode.StochasticRoundingA, RoundingMode.StochasticRoundingB, RoundingMode.StochasticRoundingC,
+               RoundingMode.StochasticRoundingD, RoundingMode.True_StochasticRounding,
+               RoundingMode.ProbabilisticRounding}
+
+
+class FloatFormatDescriptor:
+    """Python twin of FloatingPointParamsPy (LoPy_bind.cpp:45-68, 315-327): read-only
+    attributes, checker objects validated the same way (std::invalid_argument -> ValueError)."""
+
+    __slots__ = ("_total_bits", "_mantissa_bits", "_bias", "_inf_behavior", "_nan_behavior", "_signedness",
+                 "_is_inf_checker", "_is_nan_checker")
+
+    def __init__(self, total_bits, mantissa_bits, bias, inf_behavior, nan_behavior, signedness,
+                 is_inf_checker, is_nan_checker):
+        if not callable(is_inf_checker):
+            raise ValueError("inf_checker must be callable")
+        if not hasattr(is_inf_checker, "minNegInf"):
+            raise ValueError("inf_checker must have minNegInf()")
+        if not hasattr(is_inf_checker, "minPosInf"):
+            raise ValueError("inf_checker must have minPosInf()")
+        if not callable(is_nan_checker):
+            raise ValueError("nan_checker must be callable")
+        if not hasattr(is_nan_checker, "qNanBitPattern") and not hasattr(is_nan_checker, "sNanBitPattern"):
+            raise ValueError("nan_checker must have qNanBitPattern() or sNanBitPattern()")
+        self._total_bits = int(total_bits)
+        self._mantissa_bits = int(mantissa_bits)
+        self._bias = int(bias)
+        self._inf_behavior = InfBehavior(int(inf_behavior))
+        self._nan_behavior = NaNBehavior(int(nan_behavior))
+        self._signedness = Signedness(int(signedness))
+        self._is_inf_checker = is_inf_checker
+        self._is_nan_checker = is_nan_checker
+
+    total_bits = property(lambda self: self._total_bits)
+    mantissa_bits = property(lambda self: self._mantissa_bits)
+    bias = property(lambda self: self._bias)
+    inf_behavior = property(lambda self: self._inf_behavior)
+    nan_behavior = property(lambda self: self._nan_behavior)
+    signedness = property(lambda self: self._signedness)
+    is_inf_checker = property(lambda self: self._is_inf_checker)
+    is_nan_checker = property(lambda self: self._is_nan_checker)
+
+    def _c(self) -> CFormat:
+        return CFormat(self._total_bits, self._mantissa_bits, self._bias, int(self._inf_behavior),
+                       int(self._nan_behavior), int(self._signedness), 0)
+
+    def __repr__(self):
+        return (f"FloatFormatDescriptor(total_bits={self._total_bits}, mantissa_bits={self._mantissa_bits}, "
+                f"bias={self._bias}, {self._inf_behavior.name}, {self._signedness.name})")
+
+
+# --------------------------------------------------------------------------------------
+# RNG state for the stochastic modes.  The reference has a thread_local `lof_seed`
+# (lo_float.h:58, not bound to Python); here the seed keys a Philox stream and every
+# stochastic call advances `offset`, so repeated calls draw fresh, reproducible randomness.
+# --------------------------------------------------------------------------------------
+_rng_lock = threading.Lock()
+_rng_seed = 12345          # the reference's default lof_seed
+_rng_offset = 0
+
+
+def manual_seed(seed: int) -> None:
+    """Seed the stochastic-rounding stream and rewind its offset (cf. lo_float::set_seed)."""
+    global _rng_seed, _rng_offset
+    with _rng_lock:
+        _rng_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        _rng_offset = 0
+
+
+set_seed = manual_seed
+
+
+def _next_rng(stochastic: bool, rng) -> CRng:
+    """rng: None -> global stream; (seed, offset) tuple -> explicit, not advanced."""
+    global _rng_offset
+    if rng is not None:
+        return CRng(int(rng[0]) & 0xFFFFFFFFFFFFFFFF, int(rng[1]) & 0xFFFFFFFFFFFFFFFF)
+    with _rng_lock:
+        r = CRng(_rng_seed, _rng_offset)
+        if stochastic:
+            _rng_offset += 1
+    return r
+
+
+_DTYPES = {torch.float32: _lib.LOF_F32, torch.float16: _lib.LOF_F16, torch.bfloat16: _lib.LOF_BF16,
+           torch.float64: _lib.LOF_F64}
+
+
+def _dtype_code(t: torch.Tensor, what: str) -> int:
+    code = _DTYPES.get(t.dtype)
+    if code is None:
+        # AT_DISPATCH_FLOATING_TYPES_AND_HALF error text (LoPy_bind.cpp:83,133)
+        raise RuntimeError(f'"{what}" not implemented for \'{t.dtype}\'')
+    return code
+
+
+def _stream_ptr(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _require_gpu():
+    if not torch.cuda.is_available():
+        raise LoFloatError(_lib.LOF_ERR_NO_DEVICE,
+                           "lofloat_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def _round(input: torch.Tensor, params, to_mantissa_bits, round_mode, stoch_len, scale, rng, first_index):
+    L = _lib.lib()
+    what = "virtual_round_params" if params is not None else "virtual_round_mantissa"
+    code = _dtype_code(input, what)
+    mode = RoundingMode(int(round_mode))
+    ps = CProjSpec(int(mode), 0, int(stoch_len))
+    r = _next_rng(mode in _STOCHASTIC, rng)
+    x = input if input.is_contiguous() else input.contiguous()
+    out = torch.empty_like(x)
+    n = x.numel()
+    _require_gpu()
+    if x.is_cuda:
+        with torch.cuda.device(x.device):
+            if params is not None:
+                fmt = params._c()
+                st = L.lof_round_params(x.data_ptr(), out.data_ptr(), n, code, C.byref(fmt), C.byref(ps), float(scale),
+                                        C.byref(r), int(first_index), _stream_ptr(x))
+            else:
+                st = L.lof_round_mantissa(x.data_ptr(), out.data_ptr(), n, code, int(to_mantissa_bits), C.byref(ps),
+                                          float(scale), C.byref(r), int(first_index), _stream_ptr(x))
+    else:
+        # host tensor: staged through the GPU by the library's host-buffer pipeline (still no CPU compute)
+        if params is not None:
+            fmt = params._c()
+            st = L.lof_round_params_host(x.data_ptr(), out.data_ptr(), n, code, C.byref(fmt), C.byref(ps), float(scale),
+                                         C.byref(r), int(first_index), -1)
+        else:
+            st = L.lof_round_mantissa_host(x.data_ptr(), out.data_ptr(), n, code, int(to_mantissa_bits), C.byref(ps),
+                                           float(scale), C.byref(r), int(first_index), -1)
+    _lib.check(st, what)
+    return out
+
+
+def virtual_round(input: torch.Tensor, params=None, round_mode=RoundingMode.RoundToNearestEven, stoch_len: int = 0,
+                  scale: float = 1.0, *, to_mantissa_bits=None, rng=None, first_index: int = 0) -> torch.Tensor:
+    """Both reference overloads (LoPy_bind.cpp:329-339):
+
+        virtual_round(input, to_mantissa_bits: int, round_mode, stoch_len, scale)
+        virtual_round(input, params: FloatFormatDescriptor, round_mode, stoch_len, scale)
+
+    Returns a new tensor; if scale != 1 computes round(scale * input) in one pass.
+    Extensions (keyword-only): `rng=(seed, offset)` pins the Philox stream, `first_index`
+    is the global index of element 0 (row-sharded tensors).
+    """
+    if to_mantissa_bits is not None and params is None:
+        return _round(input, None, to_mantissa_bits, round_mode, stoch_len, scale, rng, first_index)
+    if isinstance(params, FloatFormatDescriptor):
+        return _round(input, params, None, round_mode, stoch_len, scale, rng, first_index)
+    if isinstance(params, int) and not isinstance(params, bool):
+        return _round(input, None, params, round_mode, stoch_len, scale, rng, first_index)
+    raise TypeError("virtual_round(): incompatible function arguments. The following argument types are supported:\n"
+                    "    1. (input: Tensor, to_mantissa_bits: int, round_mode=RoundToNearestEven, stoch_len=0, scale=1.0)\n"
+                    "    2. (input: Tensor, params: FloatFormatDescriptor, round_mode=RoundToNearestEven, stoch_len=0, scale=1.0)")
+
+
+def virtual_mx_round(input: torch.Tensor, block_size: int, element_format: FloatFormatDescriptor,
+                     scale_format: FloatFormatDescriptor, round_mode=RoundingMode.RoundToNearestEven,
+                     scale_round_mode=RoundingMode.RoundToNearestEven, stoch_len: int = 0, *, rng=None,
+                     first_index: int = 0) -> torch.Tensor:
+    """MX block fake-quantisation, float32 only (LoPy_bind.cpp:165-217, 341-351)."""
+    if input.dtype != torch.float32:
+        raise RuntimeError("virtual_mx_round: float32 tensors only")
+    if block_size <= 0:
+        raise RuntimeError("virtual_mx_round: block_size must be positive")
+    L = _lib.lib()
+    mode, smode = RoundingMode(int(round_mode)), RoundingMode(int(scale_round_mode))
+    ps_e = CProjSpec(int(mode), 0, int(stoch_len))
+    ps_s = CProjSpec(int(smode), 0, 0)
+    r = _next_rng(mode in _STOCHASTIC or smode in _STOCHASTIC, rng)
+    x = input.contiguous()
+    out = torch.empty_like(x)
+    efmt, sfmt = element_format._c(), scale_format._c()
+    _require_gpu()
+    if x.is_cuda:
+        with torch.cuda.device(x.device):
+            st = L.lof_mx_round_f32(x.data_ptr(), out.data_ptr(), x.numel(), int(block_size), C.byref(sfmt),
+                                    C.byref(efmt), C.byref(ps_s), C.byref(ps_e), C.byref(r), int(first_index),
+                                    _stream_ptr(x))
+    else:
+        st = L.lof_mx_round_f32_host(x.data_ptr(), out.data_ptr(), x.numel(), int(block_size), C.byref(sfmt),
+                                     C.byref(efmt), C.byref(ps_s), C.byref(ps_e), C.byref(r), int(first_index), -1)
+    _lib.check(st, "virtual_mx_round")
+    return out.view_as(input)
+
+
+# GEMM semantics switch.  kc = 256 (default) reproduces the reference CPU path
+# (bli_sgemm + lof_sgemm_ukr, blis_lof_gemm.hpp:147-262) bit for bit; kc = 0 is the
+# reference CUDA leaf (cutlass_gemms.cuh:97-168: one accumulator over all of K).
+_gemm_kc = 256
+
+
+def set_gemm_panel(kc: int) -> None:
+    global _gemm_kc
+    _gemm_kc = int(kc)
+
+
+def lof_gemm(A: torch.Tensor, B: torch.Tensor, accum_mant_bits: int, round_mode=RoundingMode.RoundToNearestEven,
+             stochastic_rounding_bits: int = 0, scale_a: float = 1.0, scale_b: float = 1.0, *, kc=None,
+             k_chunk=None, accum_format: FloatFormatDescriptor | None = None, rng=None) -> torch.Tensor:
+    """Low-precision-accumulation GEMM, float32 row-major (Lof_kernel.cu:96-154, LoPy_bind.cpp:361-372).
+    The output is divided by scale_a*scale_b (a zero product counts as 1, cutlass_gemms.cuh:1784-1786).
+
+    Extensions (keyword-only): `kc` panel length of the exact mode; `k_chunk` selects the
+    tensor-core chunked mode (accumulator re-rounded once per k_chunk, optionally into the
+    full `accum_format` incl. its exponent range).
+    """
+    if A.dim() != 2 or B.dim() != 2:
+        raise RuntimeError("LoF_gemm: A and B must be 2-D")
+    if A.size(1) != B.size(0):
+        raise RuntimeError(f"LoF_gemm: A.cols ({A.size(1)}) != B.rows ({B.size(0)})")
+    if A.dtype != torch.float32 or B.dtype != torch.float32:
+        raise RuntimeError("LoF_gemm: only float32 inputs are supported")
+    if not (A.is_cuda and B.is_cuda):
+        raise RuntimeError(f"LoF_gemm requires CUDA tensors (A on {A.device}, B on {B.device})")
+    L = _lib.lib()
+    mode = RoundingMode(int(round_mode))
+    ps = CProjSpec(int(mode), 0, int(stochastic_rounding_bits))
+    denom = float(scale_a) * float(scale_b)
+    alpha = 1.0 if denom == 0.0 else 1.0 / denom
+    A_c, B_c = A.contiguous(), B.contiguous()
+    M, K = A_c.shape
+    N = B_c.shape[1]
+    out = torch.zeros((M, N), dtype=torch.float32, device=A.device)
+    with torch.cuda.device(A.device):
+        if k_chunk is not None:
+            fmt = accum_format._c() if accum_format is not None else None
+            st = L.lof_gemm_chunked_f32(A_c.data_ptr(), B_c.data_ptr(), out.data_ptr(), M, N, K, int(accum_mant_bits),
+                                        C.byref(fmt) if fmt is not None else None, C.byref(ps), int(k_chunk), alpha,
+                                        _lib.LOF_BF16, _stream_ptr(A_c))
+        else:
+            r = _next_rng(mode in _STOCHASTIC, rng)
+            st = L.lof_gemm_f32(A_c.data_ptr(), B_c.data_ptr(), out.data_ptr(), M, N, K, int(accum_mant_bits),
+                                C.byref(ps), int(_gemm_kc if kc is None else kc), alpha, 0.0, C.byref(r),
+                                _stream_ptr(A_c))
+    _lib.check(st, "LoF_gemm")
+    return out

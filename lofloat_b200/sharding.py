@@ -1,0 +1,180 @@
+"""Multi-GPU layer (new: the reference has no distributed code at all).
+
+One process per GPU (`torch.distributed`, NCCL over NVLink on the GPU box, gloo in the CPU
+tests).  The three ops shard like this:
+
+* virtual_round / virtual_mx_round: independent elements / independent 32-element blocks ->
+  contiguous ROW ranges per rank, NO collective on the data path.  Stochastic modes key
+  Philox on the GLOBAL element index, so the result is independent of the partition.
+* lof_gemm: 2-D output partition on an R x C process grid.  Rank (r, c) owns
+  C[r-th row panel, c-th column panel] and needs A's row panel r and B's column panel c; K is
+  never split (that would change the accumulation order).  Operands arrive row-sharded
+  (the layout the rounding ops leave them in) and are exchanged with two collectives:
+  an all-gather of A inside the row group, and an all-gather of B's column slice over
+  the world (the "operand broadcast").
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+
+
+# --------------------------------------------------------------------------------------
+# row sharding (rounding / MX)
+# --------------------------------------------------------------------------------------
+def row_partition(n_rows: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Contiguous, balanced row range [start, end) of `rank` (the first n_rows % world_size
+    ranks get one extra row)."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError(f"bad rank/world_size: {rank}/{world_size}")
+    if n_rows < 0:
+        raise ValueError("n_rows < 0")
+    base, rem = divmod(n_rows, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+@dataclass(frozen=True)
+class RowShard:
+    """A rank's view of a row-sharded 2-D (or flattened N-D) tensor."""
+    n_rows: int          # global
+    row_len: int         # elements per row (product of the trailing dims)
+    row_start: int
+    row_end: int
+
+    @property
+    def first_index(self) -> int:
+        return self.row_start * self.row_len
+
+    @property
+    def local_rows(self) -> int:
+        return self.row_end - self.row_start
+
+    @staticmethod
+    def make(n_rows: int, row_len: int, world_size: int, rank: int) -> "RowShard":
+        s, e = row_partition(n_rows, world_size, rank)
+        return RowShard(n_rows, row_len, s, e)
+
+
+def shard_rows(full: torch.Tensor, world_size: int, rank: int) -> tuple[torch.Tensor, RowShard]:
+    """Slice a full tensor (dim 0 = rows) into this rank's shard."""
+    row_len = 1
+    for d in full.shape[1:]:
+        row_len *= d
+    sh = RowShard.make(full.shape[0], row_len, world_size, rank)
+    return full[sh.row_start:sh.row_end], sh
+
+
+def sharded_virtual_round(local: torch.Tensor, shard: RowShard, params, round_mode=0, stoch_len: int = 0,
+                          scale: float = 1.0, rng=None, round_fn: Optional[Callable] = None) -> torch.Tensor:
+    """Round this rank's rows.  No communication.  `round_fn` defaults to the CUDA op."""
+    if round_fn is None:
+        from .ops import virtual_round as round_fn
+    return round_fn(local, params, round_mode, stoch_len, scale, rng=rng, first_index=shard.first_index)
+
+
+def sharded_virtual_mx_round(local: torch.Tensor, shard: RowShard, block_size: int, element_format, scale_format,
+                             round_mode=0, scale_round_mode=0, stoch_len: int = 0, rng=None,
+                             mx_fn: Optional[Callable] = None) -> torch.Tensor:
+    """MX-round this rank's rows.  Blocks run along the last axis, so a row shard never
+    splits a block as long as block_size divides the row length (layers.py:92,261 enforce
+    the same)."""
+    if shard.row_len % block_size != 0:
+        raise ValueError(f"mx sharding needs the row length ({shard.row_len}) divisible by block_size ({block_size})")
+    if mx_fn is None:
+        from .ops import virtual_mx_round as mx_fn
+    return mx_fn(local, block_size, element_format, scale_format, round_mode, scale_round_mode, stoch_len,
+                 rng=rng, first_index=shard.first_index)
+
+
+def gather_rows(local: torch.Tensor, shard: RowShard, world_size: int, group=None) -> torch.Tensor:
+    """Reassemble the full tensor on every rank (verification / hand-off helper, not on the
+    data path of the rounding ops)."""
+    sizes = [row_partition(shard.n_rows, world_size, r) for r in range(world_size)]
+    max_rows = max(e - s for s, e in sizes)
+    pad = torch.zeros((max_rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world_size)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([b[: e - s] for b, (s, e) in zip(bufs, sizes)], dim=0)
+
+
+# --------------------------------------------------------------------------------------
+# 2-D output-partitioned GEMM
+# --------------------------------------------------------------------------------------
+def process_grid(world_size: int) -> tuple[int, int]:
+    """R x C grid, as square as possible with R <= C (8 -> 2x4, 4 -> 2x2, 2 -> 1x2, 1 -> 1x1)."""
+    r = int(world_size ** 0.5)
+    while world_size % r != 0:
+        r -= 1
+    return r, world_size // r
+
+
+@dataclass
+class GemmGrid:
+    world_size: int
+    rank: int
+    R: int
+    C: int
+    row_group: object = None     # ranks with the same r
+    world_group: object = None
+
+    @property
+    def r(self) -> int:
+        return self.rank // self.C
+
+    @property
+    def c(self) -> int:
+        return self.rank % self.C
+
+    @staticmethod
+    def create(world_size: Optional[int] = None, rank: Optional[int] = None) -> "GemmGrid":
+        """Collective: every rank must call it (new_group is collective)."""
+        if world_size is None:
+            world_size = dist.get_world_size() if dist.is_initialized() else 1
+        if rank is None:
+            rank = dist.get_rank() if dist.is_initialized() else 0
+        R, C = process_grid(world_size)
+        grid = GemmGrid(world_size, rank, R, C)
+        if world_size > 1:
+            for rr in range(R):
+                g = dist.new_group(ranks=[rr * C + cc for cc in range(C)])
+                if rr == grid.r:
+                    grid.row_group = g
+        return grid
+
+
+def gemm_2d(A_local: torch.Tensor, B_local: torch.Tensor, grid: GemmGrid, M: int, N: int, K: int,
+            accum_mant_bits: int, round_mode=0, stochastic_rounding_bits: int = 0, scale_a: float = 1.0,
+            scale_b: float = 1.0, gemm_fn: Optional[Callable] = None, **gemm_kwargs) -> torch.Tensor:
+    """C = A @ B with LoFloat accumulation on an R x C grid.
+
+    A_local: this rank's rows of A under a 1-D row partition over the world, in rank order
+             ([M/W, K]); B_local: this rank's rows of B ([K/W, N]).  M must be divisible by
+             the world size, K by the world size and N by C.
+    Returns this rank's block C[r*M/R:(r+1)*M/R, c*N/C:(c+1)*N/C].
+    """
+    if gemm_fn is None:
+        from .ops import lof_gemm as gemm_fn
+    W, R, Cn = grid.world_size, grid.R, grid.C
+    if M % W or K % W or N % Cn:
+        raise ValueError(f"gemm_2d needs M % world == 0, K % world == 0, N % C == 0 (M={M}, N={N}, K={K}, grid={R}x{Cn})")
+    if tuple(A_local.shape) != (M // W, K) or tuple(B_local.shape) != (K // W, N):
+        raise ValueError("gemm_2d: local operand shapes do not match the 1-D row partition")
+    if W == 1:
+        return gemm_fn(A_local, B_local, accum_mant_bits, round_mode, stochastic_rounding_bits, scale_a, scale_b,
+                       **gemm_kwargs)
+    # A row panel r: the C ranks of row group r hold consecutive row shards -> all-gather in the group
+    A_panel = torch.empty((M // R, K), dtype=A_local.dtype, device=A_local.device)
+    dist.all_gather_into_tensor(A_panel, A_local.contiguous(), group=grid.row_group)
+    # B column panel c: every rank contributes its K/W rows; exchange only the N/C columns each peer needs
+    nc = N // Cn
+    send = torch.stack([B_local[:, (dst % Cn) * nc:(dst % Cn + 1) * nc] for dst in range(W)]).contiguous()
+    recv = torch.empty_like(send)                      # [W, K/W, nc]: slice c of every rank's rows
+    dist.all_to_all_single(recv, send, group=grid.world_group)
+    B_panel = recv.reshape(K, nc)
+    return gemm_fn(A_panel, B_panel, accum_mant_bits, round_mode, stochastic_rounding_bits, scale_a, scale_b,
+                   **gemm_kwargs)

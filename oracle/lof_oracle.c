@@ -104,6 +104,20 @@ static inline uint16_t float_to_bf16_bits(float f)
     return (uint16_t)(x >> 16);
 }
 
+/* per-format constants of virtual_round(value, params): lo_float.h:2857-2861 */
+typedef struct { int ToMax_exp, ToMin_exp; float To_min_val; } lofo_consts;
+
+static lofo_consts lofo_consts_make(const lofo_format* f)
+{
+    lofo_consts k;
+    k.ToMax_exp = (f->is_signed == LOFO_SIGNED)
+                      ? (1 << (f->bitwidth - f->mantissa_bits - 1)) - 1 - f->bias
+                      : (1 << (f->bitwidth - f->mantissa_bits)) - 1 - f->bias;
+    k.ToMin_exp = 1 - f->bias;
+    k.To_min_val = (float)(pow(2.0, (double)k.ToMin_exp) * pow(2.0, (double)(-f->mantissa_bits)));
+    return k;
+}
+
 /* ------------------------------------------------------------------------------------
  * integer rounding core, one instantiation per container width
  * ---------------------------------------------------------------------------------- */
@@ -234,7 +248,8 @@ static inline uint16_t float_to_bf16_bits(float f)
  * ---------------------------------------------------------------------------------- */
 uint32_t lofo_round_params_bits_f32(uint32_t bits, const lofo_format* f, const lofo_projspec* ps, uint32_t w)
 {
-    return vround_params_f32(bits, f, ps->rounding_mode, ps->stoch_length, w);
+    const lofo_consts k = lofo_consts_make(f);
+    return vround_params_f32(bits, f, &k, ps->rounding_mode, ps->stoch_length, w);
 }
 
 uint32_t lofo_round_mantissa_bits_f32(uint32_t bits, int mant_bits, const lofo_projspec* ps, uint32_t w)
@@ -281,24 +296,25 @@ void lofo_round_params(const void* in, void* out, int64_t n, int dtype, const lo
 {
     const int mode = ps->rounding_mode, len = ps->stoch_length;
     const int need_rng = mode_uses_rng(mode) && rng != NULL;
+    const lofo_consts kc = lofo_consts_make(f);
     switch (dtype) {
     case LOFO_F32: {
         const float s = (float)scale;
-        ROUND_LOOP(uint32_t, scale_f32(src[i], s), vround_params_f32(v, f, mode, len, w));
+        ROUND_LOOP(uint32_t, scale_f32(src[i], s), vround_params_f32(v, f, &kc, mode, len, w));
         break;
     }
     case LOFO_F64: {
-        ROUND_LOOP(uint64_t, scale_f64(src[i], scale), vround_params_f64(v, f, mode, len, w));
+        ROUND_LOOP(uint64_t, scale_f64(src[i], scale), vround_params_f64(v, f, &kc, mode, len, w));
         break;
     }
     case LOFO_F16: {
         const uint16_t sb = float_to_half_bits((float)scale);
-        ROUND_LOOP(uint16_t, scale_f16(src[i], sb), vround_params_f16(v, f, mode, len, w));
+        ROUND_LOOP(uint16_t, scale_f16(src[i], sb), vround_params_f16(v, f, &kc, mode, len, w));
         break;
     }
     case LOFO_BF16: {
         const uint16_t sb = float_to_bf16_bits((float)scale);
-        ROUND_LOOP(uint16_t, scale_bf16(src[i], sb), vround_params_bf16(v, f, mode, len, w));
+        ROUND_LOOP(uint16_t, scale_bf16(src[i], sb), vround_params_bf16(v, f, &kc, mode, len, w));
         break;
     }
     default: break;
@@ -352,6 +368,7 @@ void lofo_mx_round_f32(const float* in, float* out, int64_t n, int block_size,
 {
     if (block_size <= 0 || n <= 0) return;
     const float pmn = lofo_mx_priv_max_normal(priv);
+    const lofo_consts kpub = lofo_consts_make(pub), kpriv = lofo_consts_make(priv);
     const int need_rng_e = mode_uses_rng(ps_priv->rounding_mode) && rng != NULL;
     const int need_rng_s = mode_uses_rng(ps_pub->rounding_mode) && rng != NULL;
     const int64_t nblocks = (n + block_size - 1) / block_size;
@@ -367,11 +384,11 @@ void lofo_mx_round_f32(const float* in, float* out, int64_t n, int block_size,
         /* scale rounding: ProjSpec{scale_round_mode} -> stoch_len 0 (LoPy_bind.cpp:208) */
         const uint64_t gblk = (first_index + (uint64_t)b) / (uint64_t)block_size;
         uint32_t ws = need_rng_s ? lofo_rand_word(rng, gblk, LOFO_STREAM_SCALE) : 0u;
-        const float scale = u2f(vround_params_f32(f2u(amax / pmn), pub, ps_pub->rounding_mode, 0, ws));
+        const float scale = u2f(vround_params_f32(f2u(amax / pmn), pub, &kpub, ps_pub->rounding_mode, 0, ws));
         if (scale > 0.0f) {
             for (int i = 0; i < len; ++i) {
                 uint32_t w = need_rng_e ? lofo_rand_word(rng, first_index + (uint64_t)(b + i), LOFO_STREAM_ELEM) : 0u;
-                float q = u2f(vround_params_f32(f2u(in[b + i] / scale), priv, ps_priv->rounding_mode,
+                float q = u2f(vround_params_f32(f2u(in[b + i] / scale), priv, &kpriv, ps_priv->rounding_mode,
                                                 ps_priv->stoch_length, w));
                 out[b + i] = q * scale;
             }
@@ -462,6 +479,8 @@ void lofo_gemm_chunked_f32(const float* A, const float* B, float* C, int64_t M, 
 {
     const int mode = ps->rounding_mode, len = ps->stoch_length;
     if (k_chunk <= 0 || k_chunk > K) k_chunk = K > 0 ? K : 1;
+    lofo_consts kacc = {0, 0, 0.0f};
+    if (acc_fmt) kacc = lofo_consts_make(acc_fmt);
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < M; ++i) {
         for (int64_t j = 0; j < N; ++j) {
@@ -472,7 +491,7 @@ void lofo_gemm_chunked_f32(const float* A, const float* B, float* C, int64_t M, 
                 for (int64_t l = k0; l < k1; ++l) part += (double)A[i * K + l] * (double)B[l * N + j];
                 const float partf = (float)part;
                 const float t = lofo_round_to_odd_fma(1.0f, partf, acc);
-                if (acc_fmt) acc = u2f(vround_params_f32(f2u(t), acc_fmt, mode, len, 0u));
+                if (acc_fmt) acc = u2f(vround_params_f32(f2u(t), acc_fmt, &kacc, mode, len, 0u));
                 else         acc = u2f(vround_mant_f32(f2u(t), accum_mant_bits, mode, len, 0u));
             }
             C[i * N + j] = acc * alpha;

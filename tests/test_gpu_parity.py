@@ -1,0 +1,442 @@
+"""GPU: parity of the CUDA path (through the C ABI, liblofloat_b200.so) against the CPU oracle on
+the same seeded inputs, against the committed golden vectors (generated from the compiled
+reference), and -- at BASELINE.json's full sizes -- through size-independent properties.
+
+Bar: BIT-EXACT for every deterministic mode and for the stochastic modes against the oracle's
+Philox stream (integer/bit work); the chunked tensor-core GEMM states its tolerance inline."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import oracle_lib as L
+
+pytestmark = pytest.mark.gpu
+G = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def lof(cuda_dev):
+    import lofloat_b200
+    return lofloat_b200
+
+
+def _desc(lof, f: L.Format):
+    chk = lof.create_single_params()
+    return lof.FloatFormatDescriptor(f.bitwidth, f.mantissa_bits, f.bias, f.ov_behavior, f.na_behavior, f.is_signed,
+                                     chk.is_inf_checker, chk.is_nan_checker)
+
+
+def _gpu(x, dev):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _bits_t(t):
+    return {2: torch.int16, 4: torch.int32, 8: torch.int64}[t.element_size()]
+
+
+@pytest.fixture(scope="module")
+def xs():
+    return np.concatenate([L.special_values_f32(), L.wide_random_f32(300000, 31)])
+
+
+# ------------------------------------------------------------------------------ virtual_round
+def test_round_params_all_formats_all_modes(lof, cuda_dev, xs):
+    xt = _gpu(xs, cuda_dev)
+    for name, f in L.FORMATS.items():
+        d = _desc(lof, f)
+        r = 23 - f.mantissa_bits
+        for mode in range(15):
+            sl = min(8, max(r, 1)) if mode in (L.SR_A, L.SR_B, L.SR_C, L.SR_D) else 0
+            got = _np(lof.virtual_round(xt, d, mode, sl, rng=(2024, mode)))
+            want = L.o_round_params(xs, f, mode, stoch_len=sl, seed=2024, offset=mode)
+            assert L.bits_equal(got, want), (name, L.MODE_NAMES[mode], L.first_mismatch(xs, got, want))
+
+
+def test_round_params_golden_from_reference(lof, cuda_dev):
+    """GPU output == what the COMPILED REFERENCE produced (tests/golden/round_params_f32.npz)."""
+    g = np.load(G / "round_params_f32.npz")
+    x = g["x"]
+    xt = _gpu(x, cuda_dev)
+    for name, f in L.FORMATS.items():
+        for mode in L.DETERMINISTIC_MODES:
+            got = _np(lof.virtual_round(xt, _desc(lof, f), mode))
+            want = g[f"{name}__{L.MODE_NAMES[mode]}"]
+            assert L.bits_equal(got, want), (name, L.MODE_NAMES[mode], L.first_mismatch(x, got, want))
+
+
+def test_round_mantissa_overload(lof, cuda_dev, xs):
+    xt = _gpu(xs, cuda_dev)
+    g = np.load(G / "round_mantissa_f32.npz")
+    gt = _gpu(g["x"], cuda_dev)
+    for m in (0, 2, 3, 7, 10, 15, 22, 23, 30):
+        for mode in range(15):
+            sl = min(8, 23 - m) if mode in (L.SR_A, L.SR_B, L.SR_C, L.SR_D) and m < 23 else 0
+            got = _np(lof.virtual_round(xt, m, mode, sl, rng=(5, 9)))
+            want = L.o_round_mantissa(xs, m, mode, stoch_len=sl, seed=5, offset=9)
+            assert L.bits_equal(got, want), (m, L.MODE_NAMES[mode], L.first_mismatch(xs, got, want))
+        if m in (0, 2, 3, 7, 10, 15, 22):
+            for mode in L.DETERMINISTIC_MODES:
+                got = _np(lof.virtual_round(gt, m, mode))
+                assert L.bits_equal(got, g[f"m{m}__{L.MODE_NAMES[mode]}"]), (m, mode)
+
+
+def test_round_fused_scale(lof, cuda_dev, xs):
+    xt = _gpu(xs, cuda_dev)
+    f = L.FORMATS["e4m3_b7"]
+    for scale in (0.37, 448.0 / 3.3, 2.0 ** -5):
+        got = _np(lof.virtual_round(xt, _desc(lof, f), 0, 0, scale))
+        want = L.o_round_params(xs, f, L.RNE, scale=scale)
+        assert L.bits_equal(got, want), scale
+        got = _np(lof.virtual_round(xt, 10, 0, 0, scale))
+        assert L.bits_equal(got, L.o_round_mantissa(xs, 10, L.RNE, scale=scale))
+
+
+@pytest.mark.parametrize("dtype,code,tdt", [("f16", L.F16, torch.float16), ("bf16", L.BF16, torch.bfloat16),
+                                            ("f64", L.F64, torch.float64)])
+def test_round_other_containers(lof, cuda_dev, dtype, code, tdt):
+    rng = np.random.default_rng(12)
+    if code == L.F64:
+        x = np.concatenate([L.special_values_f32().astype(np.float64),
+                            rng.standard_normal(100000) * np.exp2(rng.integers(-160, 160, 100000))])
+        xt = _gpu(x, cuda_dev)
+        x_bits = x
+    else:
+        bits = np.concatenate([np.arange(0, 65536, dtype=np.uint32),
+                               rng.integers(0, 65536, 70001, dtype=np.uint32)]).astype(np.uint16)
+        xt = _gpu(bits.view(np.int16), cuda_dev).view(tdt)
+        x_bits = bits.view(np.float16) if code == L.F16 else bits
+    for name in ("e4m3_b7", "e5m2", "e2m1", "e3m2", "half", "bf16_like", "e8m0"):
+        f = L.FORMATS[name]
+        for mode in list(L.DETERMINISTIC_MODES) + [L.TRUE_SR, L.PROB]:
+            got = lof.virtual_round(xt, _desc(lof, f), mode, 0, rng=(3, 4))
+            want = L.o_round_params(x_bits, f, mode, dtype=code, seed=3, offset=4)
+            gb = _np(got.view(_bits_t(got)))
+            wb = want.view({2: np.int16, 8: np.int64}[want.dtype.itemsize])
+            assert np.array_equal(gb, wb), (dtype, name, L.MODE_NAMES[mode], int((gb != wb).sum()))
+    for m in (2, 5, 7):
+        got = lof.virtual_round(xt, m, L.RNE, 0, 0.75)
+        want = L.o_round_mantissa(x_bits, m, L.RNE, scale=0.75, dtype=code)
+        assert np.array_equal(_np(got.view(_bits_t(got))), want.view({2: np.int16, 8: np.int64}[want.dtype.itemsize]))
+
+
+def test_round_edge_shapes_alignment_inplace(lof, cuda_dev):
+    """empty, ragged (n % 4 != 0), unaligned views, in-place through the raw C ABI, shard offsets."""
+    from lofloat_b200 import _lib
+    f = L.FORMATS["e4m3_b7"]
+    d = _desc(lof, f)
+    assert lof.virtual_round(torch.empty(0, device=cuda_dev), d).numel() == 0
+    x = L.wide_random_f32(4103, 77)
+    xt = _gpu(x, cuda_dev)
+    for n in (1, 2, 3, 5, 255, 1023, 1025, 4103):
+        for off in (0, 1, 2, 3):
+            if off + n > x.size:
+                continue
+            view = xt[off:off + n]                               # data_ptr misaligned by 4*off bytes
+            got = _np(lof.virtual_round(view, d, L.SR_A, 6, rng=(1, 2), first_index=1000 + off))
+            want = L.o_round_params(x[off:off + n], f, L.SR_A, stoch_len=6, seed=1, offset=2, first_index=1000 + off)
+            assert L.bits_equal(got, want), (n, off)
+            got = _np(lof.virtual_round(view, d))
+            assert L.bits_equal(got, L.o_round_params(x[off:off + n], f)), (n, off)
+    # non-contiguous input: result is the elementwise op on the logical tensor
+    m2 = xt[:4096].reshape(64, 64).t()
+    got = _np(lof.virtual_round(m2, d))
+    assert L.bits_equal(got, L.o_round_params(x[:4096].reshape(64, 64).T.copy(), f).reshape(64, 64))
+    # raw C ABI, in place (out == in), as the reference's round_fp_params does
+    lib = _lib.lib()
+    buf = xt.clone()
+    fmt = _lib.CFormat(8, 3, 7, 1, 0, 0, 0)
+    ps = _lib.CProjSpec(0, 0, 0)
+    st = lib.lof_round_params(buf.data_ptr(), buf.data_ptr(), buf.numel(), 0, C.byref(fmt), C.byref(ps), 1.0, None, 0,
+                              torch.cuda.current_stream().cuda_stream)
+    assert st == 0
+    assert L.bits_equal(_np(buf), L.o_round_params(x, f))
+    # 2-D shape preserved, new tensor returned, input untouched
+    y = lof.virtual_round(xt[:4096].reshape(64, 64), d)
+    assert y.shape == (64, 64) and y.data_ptr() != xt.data_ptr()
+    assert L.bits_equal(_np(xt), x)
+
+
+def test_host_buffer_entry_points(lof, cuda_dev):
+    """CPU tensors are staged through the GPU by the library's chunked H2D/kernel/D2H pipeline."""
+    from lofloat_b200 import _lib
+    x = L.wide_random_f32(3 * (1 << 20) + 77, 5)
+    f = L.FORMATS["e5m2"]
+    old = _lib.get_option("host.chunk_bytes")
+    _lib.set_option("host.chunk_bytes", 1 << 20)                 # force many chunks
+    try:
+        xt = torch.from_numpy(x).pin_memory()
+        got = lof.virtual_round(xt, _desc(lof, f), L.SR_D, 4, rng=(8, 8)).numpy()
+        assert L.bits_equal(got, L.o_round_params(x, f, L.SR_D, stoch_len=4, seed=8, offset=8))
+        got = lof.virtual_round(torch.from_numpy(x), 7).numpy()  # pageable memory works too
+        assert L.bits_equal(got, L.o_round_mantissa(x, 7))
+        xm = np.nan_to_num(x[: 3 * (1 << 20)], nan=1.0, posinf=2.0, neginf=-2.0)
+        got = lof.virtual_mx_round(torch.from_numpy(xm), 32, _desc(lof, L.FORMATS["e4m3_b7"]),
+                                   lof.create_e8m0_params()).numpy()
+        assert L.bits_equal(got, L.o_mx_round(xm, 32, L.FORMATS["e8m0"], L.FORMATS["e4m3_b7"]))
+    finally:
+        _lib.set_option("host.chunk_bytes", old)
+
+
+def test_round_unroll_and_grid_variants(lof, cuda_dev, xs):
+    from lofloat_b200 import _lib
+    xt = _gpu(xs, cuda_dev)
+    f = L.FORMATS["e4m3_b7"]
+    want = L.o_round_params(xs, f, L.RNE)
+    try:
+        for unroll in (1, 2, 4, 8):
+            for ctas in (1, 4, 16):
+                _lib.set_option("round.unroll", unroll)
+                _lib.set_option("round.ctas_per_sm", ctas)
+                assert L.bits_equal(_np(lof.virtual_round(xt, _desc(lof, f))), want), (unroll, ctas)
+    finally:
+        _lib.set_option("round.unroll", 4)
+        _lib.set_option("round.ctas_per_sm", 8)
+
+
+def test_stochastic_statistics_on_device(lof, cuda_dev):
+    """The reference's probability tests (test_prob_round.cpp:176-236) on the device: 2e5 trials."""
+    n = 200000
+    x = torch.full((n,), 1.0 + 1.3 / 8, device=cuda_dev)
+    lo = 1.125
+    xf = 0.3
+    def p_up(mode, sl):
+        y = lof.virtual_round(x, 3, mode, sl, rng=(99, mode * 16 + sl))
+        return float((y > lo).float().mean())
+    assert abs(p_up(L.PROB, 0) - 0.5) <= 0.02
+    assert abs(p_up(L.TRUE_SR, 0) - xf) <= 0.02
+    for sl in (1, 2, 3, 4):
+        q = 2 ** sl
+        assert abs(p_up(L.SR_D, sl) - 0.5 * (np.floor(q * xf) / q + np.ceil(q * xf) / q)) <= 0.02
+    assert abs(p_up(L.SR_A, 10) - xf) <= 0.02
+    # successive calls on the global stream draw fresh randomness; manual_seed rewinds it
+    lof.manual_seed(123)
+    a = lof.virtual_round(x, 3, L.TRUE_SR)
+    b = lof.virtual_round(x, 3, L.TRUE_SR)
+    lof.manual_seed(123)
+    c = lof.virtual_round(x, 3, L.TRUE_SR)
+    assert not torch.equal(a, b) and torch.equal(a, c)
+
+
+# ---------------------------------------------------------------------------------- MX
+MX_CONFIGS = [("e4m3_b7", "e8m0"), ("p3109_8p4", "e8m0"), ("e5m2", "e8m0"), ("e3m2", "e8m0"), ("e2m3", "e8m0"),
+              ("e2m1", "e8m0"), ("e4m3_b7", "e5m2"), ("e5m2", "e5m2")]
+
+
+def _mx_input(n, seed):
+    rng = np.random.default_rng(seed)
+    x = (rng.standard_normal(n) * np.exp2(rng.integers(-8, 9, n))).astype(np.float32)
+    if n >= 100:
+        x[rng.integers(0, n, max(1, n // 1000))] *= 64
+    return x
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_mx_bit_exact(lof, cuda_dev, variant):
+    """Methodology of test/test_virtual_mx_round_cuda.cu:76-152: GPU vs CPU scalar oracle, bit-exact,
+    block sizes x formats x modes x n in {bs, 3bs, 3bs+1, 1000, 4096, 5003, ...}."""
+    from lofloat_b200 import _lib
+    _lib.set_option("mx.variant", variant)
+    try:
+        for bs in (16, 32, 64, 128, 256):
+            for n in (bs, 3 * bs, 3 * bs + 1, 1000, 4096, 5003, 1 << 17, (1 << 17) + 4 * bs + 3):
+                x = _mx_input(n, 1234 + n)
+                xt = _gpu(x, cuda_dev)
+                for en, sn in MX_CONFIGS:
+                    for mode in (L.RNE, L.RTZ, L.RAZ, L.RTO, L.RNO):
+                        got = _np(lof.virtual_mx_round(xt, bs, _desc(lof, L.FORMATS[en]), _desc(lof, L.FORMATS[sn]), mode))
+                        want = L.o_mx_round(x, bs, L.FORMATS[sn], L.FORMATS[en], mode)
+                        assert L.bits_equal(got, want), (variant, bs, n, en, sn, mode, L.first_mismatch(x, got, want))
+    finally:
+        _lib.set_option("mx.variant", 0)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_mx_modes_scale_modes_and_edge_cases(lof, cuda_dev, variant):
+    from lofloat_b200 import _lib
+    _lib.set_option("mx.variant", variant)
+    try:
+        e4, e8 = L.FORMATS["e4m3_b7"], L.FORMATS["e8m0"]
+        x = _mx_input(1 << 15, 9)
+        x[64:96] = 0.0                                           # all-zero block -> 0, not NaN
+        x[128:160] = 1e-42                                       # amax underflows the scale format -> block = 0
+        x[200] = 3e38                                            # scale overflows E8M0 (Extended -> +inf)
+        xt = _gpu(x, cuda_dev)
+        for mode in range(15):
+            sl = 8 if mode in (L.SR_A, L.SR_B, L.SR_C, L.SR_D) else 0
+            for smode in (L.RNE, L.RU, L.RD, L.RTZ, L.TRUE_SR):
+                got = _np(lof.virtual_mx_round(xt, 32, _desc(lof, e4), _desc(lof, e8), mode, smode, sl, rng=(6, 7)))
+                want = L.o_mx_round(x, 32, e8, e4, mode, smode, sl, seed=6, offset=7)
+                assert L.bits_equal(got, want), (variant, L.MODE_NAMES[mode], smode, L.first_mismatch(x, got, want))
+        z = lof.virtual_mx_round(torch.zeros(4096, device=cuda_dev), 32, _desc(lof, e4), _desc(lof, e8))
+        assert not torch.isnan(z).any() and not z.any()
+        # KAT block of test/test_mx_round_py.py:37-40
+        kat = torch.tensor([448, 224, -112, 1, 0.5, -2, 8, 0] * 4, device=cuda_dev)
+        out = lof.virtual_mx_round(kat, 32, lof.create_p3109_params(8, 4), lof.create_e8m0_params())
+        assert torch.equal(out, kat)
+        # golden vectors generated from the compiled reference
+        g = np.load(G / "mx_round_f32.npz")
+        for n in (32, 96, 97, 1000, 5003):
+            xx = g[f"x_{n}"]
+            xg = _gpu(xx, cuda_dev)
+            for bs in (16, 32, 64, 128, 256):
+                for en in ("e4m3_b7", "e2m1"):
+                    got = _np(lof.virtual_mx_round(xg, bs, _desc(lof, L.FORMATS[en]), _desc(lof, e8)))
+                    assert L.bits_equal(got, g[f"mx_{n}_{bs}_{en}_e8m0_RNE"]), (n, bs, en)
+        # shape is preserved, blocks run over the flattened contiguous tensor (LoPy_bind.cpp:175,216)
+        x2 = xt[:4096].reshape(8, 512)
+        assert lof.virtual_mx_round(x2, 32, _desc(lof, e4), _desc(lof, e8)).shape == (8, 512)
+        # unaligned view falls back to the generic kernel and is still exact
+        view = xt[1:1 + 4096]
+        got = _np(lof.virtual_mx_round(view, 32, _desc(lof, e4), _desc(lof, e8)))
+        assert L.bits_equal(got, L.o_mx_round(x[1:1 + 4096], 32, e8, e4))
+    finally:
+        _lib.set_option("mx.variant", 0)
+
+
+# ---------------------------------------------------------------------------------- GEMM
+def test_gemm_exact_vs_oracle_and_golden(lof, cuda_dev):
+    g = np.load(G / "gemm_f32.npz")
+    for (M, N, K) in ((2, 2, 4), (17, 33, 64), (64, 48, 300), (40, 24, 513)):
+        A, B = g[f"A_{M}_{N}_{K}"], g[f"B_{M}_{N}_{K}"]
+        At, Bt = _gpu(A, cuda_dev), _gpu(B, cuda_dev)
+        for mode in L.DETERMINISTIC_MODES:
+            for bits in (10, 7):
+                got = _np(lof.lof_gemm(At, Bt, bits, mode))
+                assert L.bits_equal(got, g[f"C_{M}_{N}_{K}_{L.MODE_NAMES[mode]}_{bits}"]), (M, N, K, mode, bits)
+    A, B = g["kat_A"], g["kat_B"]                                # exact-representable KAT, every mode == fp64 product
+    for mode in L.DETERMINISTIC_MODES:
+        got = _np(lof.lof_gemm(_gpu(A, cuda_dev), _gpu(B, cuda_dev), 10, mode))
+        assert L.bits_equal(got, g["kat_C"])
+    rng = np.random.default_rng(21)
+    for (M, N, K) in ((1, 1, 1), (65, 63, 129), (128, 192, 512), (200, 72, 1031)):
+        A = rng.uniform(-1, 1, (M, K)).astype(np.float32)
+        B = rng.uniform(-1, 1, (K, N)).astype(np.float32)
+        At, Bt = _gpu(A, cuda_dev), _gpu(B, cuda_dev)
+        for kc in (256, 0, 100):
+            got = _np(lof.lof_gemm(At, Bt, 10, L.RNE, kc=kc))
+            assert L.bits_equal(got, L.o_gemm(A, B, 10, L.RNE, kc=kc)), (M, N, K, kc)
+        got = _np(lof.lof_gemm(At, Bt, 5, L.RAZ, 0, 3.0, 0.25))          # output / (scale_a * scale_b)
+        assert L.bits_equal(got, L.o_gemm(A, B, 5, L.RAZ, kc=256, alpha=np.float32(1.0 / 0.75)))
+        for mode, sl in ((L.SR_A, 6), (L.TRUE_SR, 0), (L.SR_D, 3)):
+            got = _np(lof.lof_gemm(At, Bt, 10, mode, sl, rng=(11, 12)))
+            assert L.bits_equal(got, L.o_gemm(A, B, 10, mode, sl, kc=256, seed=11, offset=12)), (M, N, K, mode)
+    # wide-range operands: cancellation, subnormal and overflowing partial sums exercise round_to_odd_fma
+    A = (rng.standard_normal((48, 96)) * np.exp2(rng.integers(-70, 60, (48, 96)))).astype(np.float32)
+    B = (rng.standard_normal((96, 40)) * np.exp2(rng.integers(-70, 60, (96, 40)))).astype(np.float32)
+    got = _np(lof.lof_gemm(_gpu(A, cuda_dev), _gpu(B, cuda_dev), 10, L.RNE))
+    want = L.o_gemm(A, B, 10, L.RNE, kc=256)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_gemm_via_torch_op_and_linear_composition(lof, cuda_dev):
+    """torch.ops.lofloat.* end to end: the LoF_Linear composition of layers.py:361-398
+    (round activations and weights, transpose, lof_gemm)."""
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((32, 128)).astype(np.float32)
+    w = rng.standard_normal((48, 128)).astype(np.float32)
+    p = lof.create_p3109_params(8, 4, bias=7)
+    fid = lof.register_format(p)
+    xq = torch.ops.lofloat.virtual_round(_gpu(x, cuda_dev), fid, 0, 0, 1.0)
+    wq = torch.ops.lofloat.virtual_round(_gpu(w, cuda_dev), fid, 0, 0, 1.0)
+    out = torch.ops.lofloat.lof_gemm(xq, wq.t().contiguous(), 10, 0, 0, 1.0, 1.0)
+    f = L.FORMATS["e4m3_b7"]
+    xo, wo = L.o_round_params(x, f).reshape(x.shape), L.o_round_params(w, f).reshape(w.shape)
+    want = L.o_gemm(xo, wo.T.copy(), 10, L.RNE, kc=256)
+    assert L.bits_equal(_np(out), want)
+    e8 = lof.register_format(lof.create_e8m0_params())
+    xm = torch.ops.lofloat.virtual_mx_round(_gpu(x, cuda_dev), 32, fid, e8, 0, 0, 0)
+    assert L.bits_equal(_np(xm), L.o_mx_round(x, 32, L.FORMATS["e8m0"], f).reshape(x.shape))
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_full_size_properties_round(lof, cuda_dev):
+    """BASELINE config C2 size (1 GiB fp32 = 2^28 elements): idempotence, sign symmetry, agreement with
+    the oracle on sampled windows, and partition invariance of the stochastic stream."""
+    n = 1 << 28
+    g = torch.Generator(device=cuda_dev).manual_seed(2024)
+    x = torch.randn(n, device=cuda_dev, generator=g)
+    x *= torch.exp2(torch.randint(-12, 13, (n,), device=cuda_dev, generator=g).float())
+    for name in ("e4m3_b7", "e2m1", "bf16_like"):
+        f = L.FORMATS[name]
+        d = _desc(lof, f)
+        for mode in (L.RNE, L.RTZ, L.RTO):
+            y = lof.virtual_round(x, d, mode)
+            if f.ov_behavior == L.SATURATING:
+                # idempotence holds on everything the format can represent (overflowing inputs are
+                # returned unrounded by the reference)
+                y2 = lof.virtual_round(y, d, mode)
+                assert torch.equal(y2.view(torch.int32), y.view(torch.int32))
+            ym = lof.virtual_round(-x, d, mode)
+            if f.ov_behavior == L.SATURATING:
+                assert torch.equal((-ym).view(torch.int32), y.view(torch.int32))      # odd symmetry of these modes
+            for start in (0, 12345678, n - (1 << 16)):
+                w = slice(start, start + (1 << 16))
+                assert L.bits_equal(_np(y[w]), L.o_round_params(_np(x[w]), f, mode)), (name, mode, start)
+            del y, ym
+    # stochastic: rounding two halves separately with their global offsets == rounding the whole
+    d = _desc(lof, L.FORMATS["e4m3_b7"])
+    whole = lof.virtual_round(x, d, L.SR_A, 8, rng=(42, 1))
+    half = n // 2
+    lo = lof.virtual_round(x[:half], d, L.SR_A, 8, rng=(42, 1), first_index=0)
+    hi = lof.virtual_round(x[half:], d, L.SR_A, 8, rng=(42, 1), first_index=half)
+    assert torch.equal(whole[:half], lo) and torch.equal(whole[half:], hi)
+    w = slice(777777, 777777 + 4096)
+    assert L.bits_equal(_np(whole[w]), L.o_round_params(_np(x[w]), L.FORMATS["e4m3_b7"], L.SR_A, stoch_len=8,
+                                                        seed=42, offset=1, first_index=777777))
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_full_size_properties_mx(lof, cuda_dev, variant):
+    """BASELINE config C3 size (16384 x 16384 fp32, block 32): fake-quant is idempotent for power-of-two
+    scales, rows are independent, and sampled rows agree with the oracle bit for bit."""
+    from lofloat_b200 import _lib
+    _lib.set_option("mx.variant", variant)
+    try:
+        R = Ccols = 16384
+        g = torch.Generator(device=cuda_dev).manual_seed(7)
+        x = torch.randn(R, Ccols, device=cuda_dev, generator=g)
+        x *= torch.exp2(torch.randint(-8, 9, (R, 1), device=cuda_dev, generator=g).float())
+        e8 = lof.create_e8m0_params()
+        for en in ("e4m3_b7", "e2m1"):
+            d = _desc(lof, L.FORMATS[en])
+            y = lof.virtual_mx_round(x, 32, d, e8)
+            for r0 in (0, 5000, R - 4):
+                want = L.o_mx_round(_np(x[r0:r0 + 4]).reshape(-1), 32, L.FORMATS["e8m0"], L.FORMATS[en])
+                assert L.bits_equal(_np(y[r0:r0 + 4]).reshape(-1), want), (en, r0)
+            # row shards computed separately (first_index = row offset * row length) == whole-tensor result
+            ys = lof.virtual_mx_round(x[4096:8192], 32, d, e8, first_index=4096 * Ccols)
+            assert torch.equal(ys, y[4096:8192])
+            # |y| never exceeds the block's representable maximum and zero stays zero
+            assert torch.equal(y == 0, (y == 0) | (x == 0))
+            del y, ys
+    finally:
+        _lib.set_option("mx.variant", 0)
+
+
+@pytest.mark.slow
+def test_exhaustive_fp32_sweep_8bit_formats(lof, cuda_dev):
+    """Every fp32 bit pattern (2^32) for the 8-bit benchmark format under RNE, plus every 16th
+    pattern for the other <= 8-bit formats and deterministic modes (north star: exhaustive check for
+    <= 8-bit formats).  The full cross product is run by tests/exhaustive_sweep.py; its log is committed
+    under profiles/."""
+    chunk = 1 << 26
+    def sweep(fname, mode, stride):
+        f = L.FORMATS[fname]
+        d = _desc(lof, f)
+        for base in range(0, 1 << 32, chunk * stride):
+            bits = torch.arange(base, base + chunk * stride, stride, device=cuda_dev, dtype=torch.int64).to(torch.int32)
+            got = _np(lof.virtual_round(bits.view(torch.float32), d, mode))
+            xb = _np(bits).view(np.float32)
+            want = L.o_round_params(xb, f, mode)
+            assert L.bits_equal(got, want), (fname, L.MODE_NAMES[mode], hex(base), L.first_mismatch(xb, got, want))
+    sweep("e4m3_b7", L.RNE, 1)
+    for fname in ("p3109_8p4", "e5m2", "e3m2", "e2m3", "e2m1", "e8m0"):
+        for mode in L.DETERMINISTIC_MODES:
+            sweep(fname, mode, 64)

@@ -1,0 +1,309 @@
+"""CPU: the oracle (oracle/lof_oracle.c) against the committed golden vectors that were generated
+from the COMPILED REFERENCE (tests/golden/make_golden.py), against the known-answer vectors of
+SURVEY.md Appendix C, and against the property checks the reference's own tests make."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle_lib as L
+
+G = Path(__file__).resolve().parent / "golden"
+
+
+def _load(name):
+    return np.load(G / name)
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32-10
+    assert L.o_philox([0, 0, 0, 0], [0, 0]) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert L.o_philox([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert L.o_philox([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]) == \
+        [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_rand_word_layout():
+    # word i of element index: block = index >> 2, lane = index & 3, offset in ctr[2:4], stream xor-ed into ctr[3]
+    seed, off = 0x0123456789ABCDEF, 0x1122334455667788
+    blk = L.o_philox([5, 0, off & 0xFFFFFFFF, off >> 32], [seed & 0xFFFFFFFF, seed >> 32])
+    for lane in range(4):
+        assert L.o_rand_word(seed, off, 20 + lane) == blk[lane]
+    blk_s = L.o_philox([5, 0, off & 0xFFFFFFFF, (off >> 32) ^ L.STREAM_SCALE], [seed & 0xFFFFFFFF, seed >> 32])
+    assert L.o_rand_word(seed, off, 21, L.STREAM_SCALE) == blk_s[1]
+
+
+def test_round_params_golden_f32():
+    g = _load("round_params_f32.npz")
+    x = g["x"]
+    n = 0
+    for name, f in L.FORMATS.items():
+        for mode in L.DETERMINISTIC_MODES:
+            want = g[f"{name}__{L.MODE_NAMES[mode]}"]
+            got = L.o_round_params(x, f, mode)
+            assert L.bits_equal(got, want), (name, L.MODE_NAMES[mode], L.first_mismatch(x, got, want))
+            n += 1
+    assert n == len(L.FORMATS) * 9
+
+
+def test_round_mantissa_golden_f32():
+    g = _load("round_mantissa_f32.npz")
+    x = g["x"]
+    for m in (0, 2, 3, 7, 10, 15, 22):
+        for mode in L.DETERMINISTIC_MODES:
+            want = g[f"m{m}__{L.MODE_NAMES[mode]}"]
+            got = L.o_round_mantissa(x, m, mode)
+            assert L.bits_equal(got, want), (m, L.MODE_NAMES[mode], L.first_mismatch(x, got, want))
+
+
+def test_round_stochastic_golden_f32():
+    """Stochastic bit recipes: the oracle fed the reference's own draw reproduces the reference."""
+    g = _load("round_stochastic_f32.npz")
+    x = g["x"]
+    keys, fmts, modes, lens, words = g["meta_keys"], g["meta_fmt"], g["meta_mode"], g["meta_len"], g["meta_word"]
+    assert len(keys) > 150
+    changed = 0
+    for key, fname, mode, sl, w in zip(keys, fmts, modes, lens, words):
+        want = g[str(key)]
+        got = L.o_round_params(x, L.FORMATS[str(fname)], int(mode), stoch_len=int(sl), fixed_word=int(w))
+        assert L.bits_equal(got, want), (key, L.first_mismatch(x, got, want))
+        trunc = L.o_round_params(x, L.FORMATS[str(fname)], L.RTZ)
+        changed += int(not L.bits_equal(got, trunc))
+    assert changed > 50      # the draws actually moved results away from truncation
+
+
+def test_round_params_golden_f64():
+    g = _load("round_params_f64.npz")
+    x = g["x"]
+    for name in ("e4m3_b7", "e5m2", "bf16_like", "half", "single"):
+        for mode in (L.RNE, L.RTZ, L.RAZ, L.RTO, L.RU, L.RD):
+            want = g[f"{name}__{L.MODE_NAMES[mode]}"]
+            got = L.o_round_params(x, L.FORMATS[name], mode, dtype=L.F64)
+            assert L.bits_equal(got, want), (name, mode)
+
+
+def test_mx_golden():
+    g = _load("mx_round_f32.npz")
+    cnt = 0
+    for n in (32, 96, 97, 1000, 5003):
+        xx = g[f"x_{n}"]
+        for bs in (16, 32, 64, 128, 256):
+            for en in ("e4m3_b7", "p3109_8p4", "e5m2", "e3m2", "e2m3", "e2m1"):
+                for sn in ("e8m0", "e5m2"):
+                    for mode in (L.RNE, L.RTZ, L.RAZ):
+                        want = g[f"mx_{n}_{bs}_{en}_{sn}_{L.MODE_NAMES[mode]}"]
+                        got = L.o_mx_round(xx, bs, L.FORMATS[sn], L.FORMATS[en], mode)
+                        assert L.bits_equal(got, want), (n, bs, en, sn, mode, L.first_mismatch(xx, got, want))
+                        cnt += 1
+    assert cnt == 5 * 5 * 6 * 2 * 3
+    # KAT block of test/test_mx_round_py.py:37-40 round-trips unchanged
+    assert L.bits_equal(g["kat_y"], g["kat_x"])
+    got = L.o_mx_round(g["kat_x"], 32, L.FORMATS["e8m0"], L.FORMATS["p3109_8p4"], L.RNE)
+    assert L.bits_equal(got, g["kat_x"])
+    # all-zero block stays zero, never NaN (test_virtual_mx_round_cuda.cu:156-172)
+    z = L.o_mx_round(np.zeros(64, np.float32), 32, L.FORMATS["e8m0"], L.FORMATS["e4m3_b7"])
+    assert not np.isnan(z).any() and not z.any()
+
+
+def test_gemm_golden():
+    g = _load("gemm_f32.npz")
+    for (M, N, K) in ((2, 2, 4), (17, 33, 64), (64, 48, 300), (40, 24, 513)):
+        A, B = g[f"A_{M}_{N}_{K}"], g[f"B_{M}_{N}_{K}"]
+        for mode in L.DETERMINISTIC_MODES:
+            for bits in (10, 7):
+                want = g[f"C_{M}_{N}_{K}_{L.MODE_NAMES[mode]}_{bits}"]
+                got = L.o_gemm(A, B, bits, mode, kc=256)
+                assert L.bits_equal(got, want), (M, N, K, mode, bits)
+    # exact-representable KAT (test/test_blis_lof_accum.cpp:205-245): equals the fp64 product in every mode
+    A, B = g["kat_A"], g["kat_B"]
+    exact = (A.astype(np.float64) @ B.astype(np.float64)).astype(np.float32)
+    assert L.bits_equal(g["kat_C"], exact)
+    for mode in L.DETERMINISTIC_MODES:
+        assert L.bits_equal(L.o_gemm(A, B, 10, mode), exact)
+    # round-to-odd FMA
+    o = L.oracle()
+    got = np.array([o.lofo_round_to_odd_fma(float(a), float(b), float(c))
+                    for a, b, c in zip(g["fma_a"], g["fma_b"], g["fma_c"])], dtype=np.float32)
+    assert L.bits_equal(got, g["fma_r"])
+
+
+def test_gemm_gamma_bound():
+    """|C - C_exact| <= gamma_K (|A||B|) + 1e-6 with eps = 2^-10 (test_blis_lof_accum.cpp:126-177)."""
+    rng = np.random.default_rng(3)
+    M, N, K = 24, 20, 64
+    A = rng.uniform(-1, 1, (M, K)).astype(np.float32)
+    B = rng.uniform(-1, 1, (K, N)).astype(np.float32)
+    exact = A.astype(np.float64) @ B.astype(np.float64)
+    absab = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64)
+    eps = 2.0 ** -10
+    gamma = K * eps / (1 - K * eps)
+    err32 = np.abs(L.o_gemm(A, B, 23, L.RNE) - exact).max()
+    for mode in L.DETERMINISTIC_MODES:
+        Cq = L.o_gemm(A, B, 10, mode)
+        err = np.abs(Cq - exact)
+        # directed modes accumulate a one-sided error of up to 2 eps per step
+        k = 2.0 if mode in (L.RTZ, L.RAZ, L.RU, L.RD, L.RTO) else 1.0
+        assert (err <= k * gamma * absab + 1e-6).all(), L.MODE_NAMES[mode]
+    assert np.abs(L.o_gemm(A, B, 10, L.RNE) - exact).max() > 50 * err32     # rounding is engaged (:182-198)
+
+
+# ---- known answers extracted from the compiled reference ---------------
+def _r(vals, fname, mode=L.RNE):
+    return L.o_round_params(np.array(vals, np.float32), L.FORMATS[fname], mode)
+
+
+def test_appendix_c_e4m3():
+    x = [1.0625, 1.1875, 447, 464, 480, 0.001, 0.0009765625, 0.00146484375, 1e-30]
+    want = [1.0, 1.25, 448, 448, 480, 0.001953125, 0.0, 0.001953125, 0.0]
+    assert np.array_equal(_r(x, "e4m3_b7"), np.array(want, np.float32))
+    # saturating overflow returns the UNROUNDED input; extended returns +inf even for negatives
+    assert np.array_equal(_r([496, 512, -1e6], "e4m3_b7"), np.array([496, 512, -1e6], np.float32))
+    ext = _r([496, 512, -1e6, -np.inf], "e4m3_b7_ext")
+    assert (ext.view(np.uint32) == 0x7F800000).all()
+    assert _r([-np.inf], "e4m3_b7")[0] == -np.inf
+    assert _r([np.nan], "e4m3_b7").view(np.uint32)[0] == 0x7FC00000
+    assert _r([-0.0], "e4m3_b7").view(np.uint32)[0] == 0x80000000
+
+
+def test_appendix_c_e8m0():
+    x = [1.4, 1.5, 2.9, 3.0, 3.1, 0.75, 1e-38, 1e-39, 3e38]
+    want = [1, 2, 2, 2, 4, 0.5, 2.0 ** -126, 0, np.inf]
+    assert np.array_equal(_r(x, "e8m0"), np.array(want, np.float32))
+    assert _r([3e38], "e8m0", L.RD)[0] == np.float32(2.0 ** 127)
+    assert _r([1e-39], "e8m0", L.RU)[0] == np.float32(2.0 ** -126)
+
+
+def test_appendix_c_e2m1_table():
+    cols = [L.RNE, L.RTZ, L.RAZ, L.RNO, L.RD, L.RU, L.RTA, L.RTO, L.RTTZ]
+    table = {
+        0.1: [0, 0, 0.5, 0, 0, 0.5, 0, 0.5, 0],
+        0.25: [0, 0, 0.5, 0.5, 0, 0.5, 0.5, 0.5, 0],
+        0.3: [0.5, 0, 0.5, 0.5, 0, 0.5, 0.5, 0.5, 0.5],
+        0.75: [1, 0.5, 1, 0.5, 0.5, 1, 1, 0.5, 0.5],
+        1.25: [1, 1, 1.5, 1.5, 1, 1.5, 1.5, 1.5, 1],
+        -1.25: [-1, -1, -1.5, -1.5, -1.5, -1, -1.5, -1.5, -1],
+        2.5: [2, 2, 3, 3, 2, 3, 3, 3, 2],
+        -2.5: [-2, -2, -3, -3, -3, -2, -3, -3, -2],
+        5: [4, 4, 6, 6, 4, 6, 6, 6, 4],
+        6: [6] * 9,
+        6.9: [6, 6, 6.9, 6, 6, 6.9, 6, 6, 6],
+        7: [7, 6, 7, 6, 6, 7, 7, 6, 6],
+        7.5: [7.5, 6, 7.5, 7.5, 6, 7.5, 7.5, 6, 7.5],
+        8: [8] * 9,
+        -0.2: [-0.0, -0.0, -0.5, -0.0, -0.5, -0.0, -0.0, -0.5, -0.0],
+    }
+    for xv, row in table.items():
+        for mode, want in zip(cols, row):
+            got = _r([xv], "e2m1", mode)
+            assert got.view(np.uint32)[0] == np.array([want], np.float32).view(np.uint32)[0], (xv, L.MODE_NAMES[mode], got)
+
+
+def test_bf16_like_bogus_hidden_bit():
+    # fp32-subnormal input to a target with ToMin_exp = -126
+    got = _r([2.0 ** -130], "bf16_like")
+    assert got.view(np.uint32)[0] == 0x00440000
+
+
+# ---- property checks the reference makes (test/test_virtual_round.cpp:95-215) -----------------
+@pytest.mark.parametrize("m", [7, 10, 15])
+def test_mantissa_properties(m):
+    rng = np.random.default_rng(m)
+    x = (rng.standard_normal(20000) * np.exp2(rng.integers(-30, 30, 20000))).astype(np.float32)
+    xd = x.astype(np.float64)
+    rd = L.o_round_mantissa(x, m, L.RD).astype(np.float64)
+    ru = L.o_round_mantissa(x, m, L.RU).astype(np.float64)
+    assert (rd <= xd).all() and (ru >= xd).all()
+    ulp = np.exp2(np.floor(np.log2(np.abs(xd))) - m)
+    for mode in (L.RD, L.RU, L.RTZ, L.RAZ, L.RTO):
+        assert (np.abs(L.o_round_mantissa(x, m, mode).astype(np.float64) - xd) <= ulp * (1 + 1e-12)).all()
+    for mode in (L.RNE, L.RNO, L.RTA, L.RTTZ):
+        assert (np.abs(L.o_round_mantissa(x, m, mode).astype(np.float64) - xd) <= ulp / 2 * (1 + 1e-12)).all()
+    # ties: RNE -> even, RNO -> odd, RTA -> away, RTTZ -> toward zero (:139-184)
+    base = (rng.integers(1 << 23, 1 << 24, 2000).astype(np.uint32) >> (23 - m)) << (23 - m)
+    tie = ((base | (1 << (22 - m))) & 0x7FFFFF) | (120 << 23)
+    t = tie.astype(np.uint32).view(np.float32)
+    lsb = lambda a: (a.view(np.uint32) >> (23 - m)) & 1
+    assert (lsb(L.o_round_mantissa(t, m, L.RNE)) == 0).all()
+    assert (lsb(L.o_round_mantissa(t, m, L.RNO)) == 1).all()
+    assert (L.o_round_mantissa(t, m, L.RTA) > t).all()
+    assert (L.o_round_mantissa(t, m, L.RTTZ) < t).all()
+    # stochastic results are one of the two neighbours (:189-215)
+    for mode, sl in ((L.SR_A, 8), (L.SR_B, 8), (L.SR_C, 8), (L.SR_D, 8), (L.TRUE_SR, 0), (L.PROB, 0)):
+        s = L.o_round_mantissa(x, m, mode, stoch_len=sl, seed=99, offset=1).astype(np.float64)
+        lo, hi = np.minimum(rd, ru), np.maximum(rd, ru)
+        trunc = L.o_round_mantissa(x, m, L.RTZ).astype(np.float64)
+        away = L.o_round_mantissa(x, m, L.RAZ).astype(np.float64)
+        ok = (s == trunc) | (s == away)
+        if mode == L.SR_D:      # SR-D may bump an exactly representable value by one ulp (R + coin == 2^len)
+            ok |= np.abs(s - xd) <= ulp * (1 + 1e-12)
+        assert ok.all(), L.MODE_NAMES[mode]
+        assert (s >= lo - ulp).all() and (s <= hi + ulp).all()
+
+
+def test_stochastic_probabilities():
+    """P(up) model of each SR variant (test/test_prob_round.cpp:176-236, stoch_prob_test.cpp),
+    with Philox draws: |P(up) - ideal| <= 0.02 at 2e5 trials."""
+    n = 200000
+    m = 3
+    frac = 0.3
+    x = np.full(n, 1.0 + (1 + frac) / 8, np.float32)          # between 1.125 and 1.25, fraction 0.3 of the gap
+    lo = np.float32(1.125)
+    xf = float((x[0] - lo) * 8)
+    def p_up(mode, sl):
+        y = L.o_round_mantissa(x, m, mode, stoch_len=sl, seed=2024, offset=mode * 16 + sl)
+        return float((y > lo).mean())
+    assert abs(p_up(L.PROB, 0) - 0.5) <= 0.02
+    assert abs(p_up(L.TRUE_SR, 0) - xf) <= 0.02
+    for sl in (1, 2, 3, 4):
+        q = 2 ** sl
+        ideal_d = 0.5 * (np.floor(q * xf) / q + np.ceil(q * xf) / q)
+        assert abs(p_up(L.SR_D, sl) - ideal_d) <= 0.02, sl
+        assert abs(p_up(L.SR_A, sl) - np.floor(q * xf) / q) <= 0.02, sl
+    assert abs(p_up(L.SR_A, 10) - xf) <= 0.02
+    assert abs(p_up(L.SR_B, 10) - xf) <= 0.02
+    assert abs(p_up(L.SR_C, 10) - xf) <= 0.02
+    # unbiasedness of true SR: mean of rounded == x within 3 sigma
+    y = L.o_round_mantissa(x, m, L.TRUE_SR, seed=5).astype(np.float64)
+    assert abs(y.mean() - float(x[0])) < 3 * (0.125 * 0.5) / np.sqrt(n)
+
+
+def test_mx_properties():
+    """Scale is the RNE E8M0 neighbour of amax/priv_max; every representable value round-trips under all
+    deterministic modes (test/test_virtual_mx_round.cpp:154-193, 234-254)."""
+    for l in range(3, 9):
+        for p in range(1, l):
+            k, m = l, p - 1
+            bias = 1 << (k - p - 1) if k - p - 1 >= 0 else 0
+            f = L.fmt(k, m, bias)
+            ebits = k - m - 1
+            if ebits < 1:
+                continue
+            pmn = float(L.oracle().lofo_mx_priv_max_normal(f))
+            # all representable positive values of the element format
+            vals = []
+            for e in range(0, 1 << ebits):
+                for mm in range(0, 1 << m):
+                    v = (mm / (1 << m)) * 2.0 ** (1 - bias) if e == 0 else (1 + mm / (1 << m)) * 2.0 ** (e - bias)
+                    vals.append(v)
+            vals = np.array(sorted(set(vals)), np.float32)
+            blk = np.zeros(((len(vals) + 30) // 31) * 32, np.float32)
+            # put the max normal into every block so that scale == 1 exactly
+            blk.reshape(-1, 32)[:, 0] = pmn
+            blk.reshape(-1, 32)[:, 1:].flat[: len(vals)] = vals
+            for mode in L.DETERMINISTIC_MODES:
+                y = L.o_mx_round(blk, 32, L.FORMATS["e8m0"], f, mode)
+                assert L.bits_equal(y, blk), (l, p, L.MODE_NAMES[mode])
+    # scale = RNE E8M0 neighbour
+    rng = np.random.default_rng(0)
+    f = L.FORMATS["e4m3_b7"]
+    pmn = 480.0
+    for _ in range(200):
+        amax = float(np.float32(np.exp2(rng.uniform(-20, 20))))
+        blk = np.zeros(32, np.float32)
+        blk[3] = -amax
+        y = L.o_mx_round(blk, 32, L.FORMATS["e8m0"], f)
+        scale = L.o_round_params(np.array([np.float32(amax) / np.float32(pmn)], np.float32), L.FORMATS["e8m0"])[0]
+        lo = 2.0 ** np.floor(np.log2(amax / pmn))
+        assert scale in (np.float32(lo), np.float32(2 * lo))
+        q = L.o_round_params(np.array([-np.float32(amax) / scale], np.float32), f)[0] * scale
+        assert y[3] == q
