@@ -194,8 +194,9 @@ LOF_API uint64_t    lof_kernel_launch_count(void);        /* kernels launched by
 LOF_API float       lof_mx_priv_max_normal(const lof_format_t* elem_fmt);  /* (2 - 2^-m) * 2^max_exp  */
 
 /* Tuning knobs used by bench.py / the profiling scripts to compare kernel variants on the
- * same inputs.  key: "round.unroll", "round.ctas_per_sm", "mx.variant" (0 = shuffle,
- * 1 = TMA-staged), "mx.ctas_per_sm", "host.chunk_bytes".  Returns LOF_ERR_INVALID_ARG for
+ * same inputs.  key: "round.unroll", "round.ctas_per_sm", "round.fast" (0 = always the
+ * exact integer kernel), "mx.variant" (0 = shuffle, 1 = TMA-staged), "mx.ctas_per_sm",
+ * "host.chunk_bytes".  Returns LOF_ERR_INVALID_ARG for
  * an unknown key. */
 LOF_API int lof_set_option(const char* key, int64_t value);
 LOF_API int lof_get_option(const char* key, int64_t* value);

@@ -41,6 +41,7 @@ struct Options {
     std::atomic<int64_t> mx_variant{0};
     std::atomic<int64_t> mx_ctas_per_sm{8};
     std::atomic<int64_t> host_chunk_bytes{32ll << 20};
+    std::atomic<int64_t> round_fast{1};          // 1: use the fp32 fast path when the format is eligible
 } g_opt;
 
 int fail(int status, const std::string& msg)
@@ -123,6 +124,37 @@ int make_plan(const lof_format_t* f, int dtype, int mode, int stoch_len, RoundPl
     return LOF_OK;
 }
 
+// Eligibility + constants of the fp32 fast path (lof_fast_f32.cuh).  plan must come from
+// make_plan(fmt, LOF_F32, ...).
+FastPlan make_fast_plan(const RoundPlan& p, int mode)
+{
+    FastPlan f;
+    std::memset(&f, 0, sizeof f);
+    const int m_exp = p.min_exp_b + p.shiftN;                 // biased exponent of M = denorm_min * 2^23
+    uint32_t mv, hv;
+    std::memcpy(&mv, &p.min_val, 4);
+    std::memcpy(&hv, &p.half_val, 4);
+    bool ok = p.shiftN >= 1 && p.shiftN <= 23 && p.min_exp_b >= 1 && p.min_exp_b <= 254 && m_exp >= 1 && m_exp <= 254 &&
+              mv != 0 && p.max_exp_b >= p.min_exp_b;
+    // RoundToNearestOdd / RoundTiesToAway send an exact ZERO to denorm_min when denorm_min / 2 underflows to 0
+    // (lo_float.h:2894-2899, the tie branch): leave that corner to the exact kernel.
+    if ((mode == LOF_RoundToNearestOdd || mode == LOF_RoundTiesToAway) && hv == 0) ok = false;
+    if (!ok) return f;
+    f.maskN = ~((1u << p.shiftN) - 1u);
+    f.min_normal_bits = (uint32_t)p.min_exp_b << 23;
+    const int64_t thr = (int64_t)p.max_exp_b + 1;
+    f.ovf_thresh = thr > 256 ? 0xFFFFFFFFu : (uint32_t)(thr << 23);
+    const uint32_t mbits = (uint32_t)m_exp << 23;
+    std::memcpy(&f.M, &mbits, 4);
+    f.min_val = p.min_val;
+    f.shiftN = p.shiftN;
+    f.rbase = p.shiftN + p.min_exp_b;
+    f.stoch_len = p.stoch_len;
+    f.check_denorm_in = mv < 0x00800000u;                     // denorm_min is itself an fp32 subnormal
+    f.valid = 1;
+    return f;
+}
+
 RngArgs make_rng(const lof_rng_t* rng, uint32_t stream_const)
 {
     RngArgs r;
@@ -153,10 +185,18 @@ int round_common(bool params, const void* in, void* out, int64_t n, int dtype, c
     if (mode < 0 || mode >= LOF_NUM_ROUNDING_MODES) return fail(LOF_ERR_INVALID_ARG, "unknown rounding mode");
     RoundPlan plan;
     std::memset(&plan, 0, sizeof plan);
+    FastPlan fast;
+    std::memset(&fast, 0, sizeof fast);
+    int kind = params ? kKindParams : kKindMantissa;
     int r = 0;
     if (params) {
         const int st = make_plan(fmt, dtype, mode, ps->stoch_length, &plan);
         if (st != LOF_OK) return st;
+        if (dtype == LOF_F32 && g_opt.round_fast.load()) {
+            fast = make_fast_plan(plan, mode);
+            if (fast.valid) kind = fast.check_denorm_in ? (plan.saturating ? kKindFastSatChk : kKindFastExtChk)
+                                                        : (plan.saturating ? kKindFastSat : kKindFastExt);
+        }
     } else {
         r = g.mant - mantissa_bits;                                           // -kDigitShift, lo_float.h:2722
         if (mantissa_bits < 0) return fail(LOF_ERR_INVALID_ARG, "mantissa_bits < 0");
@@ -173,10 +213,10 @@ int round_common(bool params, const void* in, void* out, int64_t n, int dtype, c
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     cudaError_t e;
     switch (dtype) {
-    case LOF_F32:  e = launch_round_f32(params, mode, in, out, n, plan, r, ps->stoch_length, scale, ra, first_index, cfg, s); break;
-    case LOF_F16:  e = launch_round_f16(params, mode, in, out, n, plan, r, ps->stoch_length, scale, ra, first_index, cfg, s); break;
-    case LOF_BF16: e = launch_round_bf16(params, mode, in, out, n, plan, r, ps->stoch_length, scale, ra, first_index, cfg, s); break;
-    default:       e = launch_round_f64(params, mode, in, out, n, plan, r, ps->stoch_length, scale, ra, first_index, cfg, s); break;
+    case LOF_F32:  e = launch_round_f32(kind, mode, in, out, n, plan, fast, r, ps->stoch_length, scale, ra, first_index, cfg, s); break;
+    case LOF_F16:  e = launch_round_f16(kind, mode, in, out, n, plan, fast, r, ps->stoch_length, scale, ra, first_index, cfg, s); break;
+    case LOF_BF16: e = launch_round_bf16(kind, mode, in, out, n, plan, fast, r, ps->stoch_length, scale, ra, first_index, cfg, s); break;
+    default:       e = launch_round_f64(kind, mode, in, out, n, plan, fast, r, ps->stoch_length, scale, ra, first_index, cfg, s); break;
     }
     if (e != cudaSuccess) return cuda_fail(e, "virtual_round launch");
     g_launches.fetch_add(1);
@@ -297,6 +337,7 @@ int mx_common(const float* in, float* out, int64_t n, int block_size, const lof_
     if (st != LOF_OK) return st;
     st = make_plan(scale_fmt, LOF_F32, ps_scale->rounding_mode, 0, &a.scale);
     if (st != LOF_OK) return st;
+    if (g_opt.round_fast.load()) a.fast = make_fast_plan(a.elem, ps_elem->rounding_mode);
     a.pmn = lof_mx_priv_max_normal(elem_fmt);
     a.scale_mode = ps_scale->rounding_mode;
     a.block_size = block_size;
@@ -364,6 +405,7 @@ int lof_set_option(const char* key, int64_t value)
     else if (k == "round.ctas_per_sm") { if (value < 1 || value > 64) return fail(LOF_ERR_INVALID_ARG, "round.ctas_per_sm out of range"); g_opt.round_ctas_per_sm = value; }
     else if (k == "mx.variant") { if (value < 0 || value > 1) return fail(LOF_ERR_INVALID_ARG, "mx.variant must be 0 or 1"); g_opt.mx_variant = value; }
     else if (k == "mx.ctas_per_sm") { if (value < 1 || value > 64) return fail(LOF_ERR_INVALID_ARG, "mx.ctas_per_sm out of range"); g_opt.mx_ctas_per_sm = value; }
+    else if (k == "round.fast") { g_opt.round_fast = value ? 1 : 0; }
     else if (k == "host.chunk_bytes") { if (value < (1 << 16)) return fail(LOF_ERR_INVALID_ARG, "host.chunk_bytes too small"); g_opt.host_chunk_bytes = value; }
     else return fail(LOF_ERR_INVALID_ARG, "unknown option: " + k);
     return LOF_OK;
@@ -377,6 +419,7 @@ int lof_get_option(const char* key, int64_t* value)
     else if (k == "round.ctas_per_sm") *value = g_opt.round_ctas_per_sm;
     else if (k == "mx.variant") *value = g_opt.mx_variant;
     else if (k == "mx.ctas_per_sm") *value = g_opt.mx_ctas_per_sm;
+    else if (k == "round.fast") *value = g_opt.round_fast;
     else if (k == "host.chunk_bytes") *value = g_opt.host_chunk_bytes;
     else return fail(LOF_ERR_INVALID_ARG, "unknown option: " + k);
     return LOF_OK;

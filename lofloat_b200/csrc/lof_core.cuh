@@ -50,11 +50,11 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 {
 #pragma unroll
     for (int round = 0; round < 10; ++round) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        const uint32_t n0 = hi1 ^ c1 ^ k0;
-        const uint32_t n2 = hi0 ^ c3 ^ k1;
-        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;      // one IMAD.WIDE.U32 each
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
         k0 += 0x9E3779B9u;
         k1 += 0xBB67AE85u;
     }
@@ -171,8 +171,10 @@ template <> struct Src<LOF_F32> {
     { return __float_as_uint(__fmul_rn(__uint2float_rn(k), p.min_val)); }
     __host__ static scale_t make_scale(double s) { return (float)s; }
     __device__ static __forceinline__ bool scale_is_one(scale_t s) { return s == 1.0f; }
+    // NaN operands: the CPU reference (x86 mulss) returns the operand NaN quieted, payload and sign
+    // kept, while FMUL returns the canonical NaN; the mantissa-only overload rounds those bits.
     __device__ static __forceinline__ bits_t apply_scale(bits_t v, scale_t s)
-    { return __float_as_uint(__fmul_rn(s, __uint_as_float(v))); }
+    { return ((v & kAbsMask) > kInf) ? (v | 0x00400000u) : __float_as_uint(__fmul_rn(s, __uint_as_float(v))); }
 };
 
 template <> struct Src<LOF_F64> {
@@ -187,7 +189,10 @@ template <> struct Src<LOF_F64> {
     __host__ static scale_t make_scale(double s) { return s; }
     __device__ static __forceinline__ bool scale_is_one(scale_t s) { return s == 1.0; }
     __device__ static __forceinline__ bits_t apply_scale(bits_t v, scale_t s)
-    { return (bits_t)__double_as_longlong(__dmul_rn(s, __longlong_as_double((long long)v))); }
+    {
+        if ((v & kAbsMask) > kInf) return v | 0x0008000000000000ull;     // quieted operand NaN (x86 mulsd)
+        return (bits_t)__double_as_longlong(__dmul_rn(s, __longlong_as_double((long long)v)));
+    }
 };
 
 template <> struct Src<LOF_F16> {
@@ -201,7 +206,10 @@ template <> struct Src<LOF_F16> {
     __host__ static scale_t make_scale(double s) { return __half2float(__float2half_rn((float)s)); }
     __device__ static __forceinline__ bool scale_is_one(scale_t s) { return s == 1.0f; }
     __device__ static __forceinline__ bits_t apply_scale(bits_t v, scale_t s)   // Half*Half: float multiply, RN to half
-    { return __half_as_ushort(__float2half_rn(__fmul_rn(s, __half2float(__ushort_as_half(v))))); }
+    {
+        if ((v & kAbsMask) > kInf) return (bits_t)((v & 0x8000u) | 0x7E00u);  // c10 float->half: NaN -> sign | 0x7E00
+        return __half_as_ushort(__float2half_rn(__fmul_rn(s, __half2float(__ushort_as_half(v)))));
+    }
 };
 
 template <> struct Src<LOF_BF16> {
@@ -215,7 +223,10 @@ template <> struct Src<LOF_BF16> {
     __host__ static scale_t make_scale(double s) { return __bfloat162float(__float2bfloat16_rn((float)s)); }
     __device__ static __forceinline__ bool scale_is_one(scale_t s) { return s == 1.0f; }
     __device__ static __forceinline__ bits_t apply_scale(bits_t v, scale_t s)
-    { return __bfloat16_as_ushort(__float2bfloat16_rn(__fmul_rn(s, __uint_as_float((uint32_t)v << 16)))); }
+    {
+        if ((v & kAbsMask) > kInf) return (bits_t)(v | 0x0040u);             // quieted operand NaN
+        return __bfloat16_as_ushort(__float2bfloat16_rn(__fmul_rn(s, __uint_as_float((uint32_t)v << 16))));
+    }
 };
 
 // ---------------------------------------------------------------------------------------

@@ -1,0 +1,150 @@
+// lof_fast_f32.cuh -- branch-free fp32 path for virtual_round(value, FloatingPointParams, ps).
+//
+// The streaming kernels are HBM-bound only if the per-element instruction count stays well
+// below ~40 (B200: ~24 B/clk/SM of HBM bandwidth against 128 lanes/clk/SM), and wide-range
+// data puts half of the elements into the target-subnormal / below-denorm_min regimes, so
+// those regimes must not diverge.  Reformulation of lo_float.h:2843-2939 (bit-exactness is
+// established by the exhaustive 2^32 sweeps: tests/test_gpu_parity.py, profiles/):
+//
+//   * normal regime (|x| >= 2^ToMin_exp): RoundMantissa with the launch-constant shift, the
+//     mask, and overflow as ONE unsigned compare of the rounded magnitude against
+//     (ToMax_exp + 1) << 23; all by selects.
+//   * |x| < 2^ToMin_exp, i.e. the target-subnormal AND the below-denorm_min regimes: the
+//     target grid has constant spacing denorm_min there, so
+//         (|x| + M) - M,   M = denorm_min * 2^23
+//     rounds onto it in ONE floating-point add whose IEEE rounding mode is picked per
+//     LoFloat mode (rn / rz / ru / rd; round-to-odd = rz | inexact): the sum lies in
+//     [M, 2M), whose ulp is exactly denorm_min, and the subtraction is exact.  It also
+//     reproduces the reference's below-denorm_min switch (lo_float.h:2872-2908): a tie goes to
+//     0 under RNE, any nonzero value to denorm_min under RAZ / RoundToOdd, by sign under
+//     RoundUp / RoundDown; and it maps +-0 to +-0.
+//   * the modes without such a recipe (ties-to-odd / away / toward-zero and the stochastic
+//     family) use a branch-free integer version of the reference's explicit-leading-one
+//     rounding (lo_float.h:2915-2923) with the shift clamped to 25, which degenerates into
+//     the below-denorm_min switch; the stochastic modes flush below denorm_min (:2902).
+//   * fp32-SUBNORMAL inputs are exact through the add trick whenever denorm_min >= 2^-126;
+//     otherwise (bf16-like targets) the reference gives them a bogus hidden bit (SURVEY.md
+//     Appendix B.6): those lanes, flagged per 4-element vector, call the exact routine.
+//
+// Eligibility is decided on the host (make_fast_plan in lof_api.cu); other formats use the
+// exact integer kernel.
+#pragma once
+
+#include "lof_core.cuh"
+
+namespace lof {
+
+struct FastPlan {
+    uint32_t maskN;            // ~((1u << shiftN) - 1)
+    uint32_t min_normal_bits;  // |x| bits below this -> target-subnormal / tiny regime
+    uint32_t ovf_thresh;       // rounded magnitude bits >= this -> overflow
+    float    M;                // denorm_min * 2^23
+    float    min_val;          // denorm_min
+    int32_t  shiftN;           // 1..23
+    int32_t  rbase;            // shiftN + min_exp_b: shift of the integer sub path = rbase - exponent field
+    int32_t  stoch_len;
+    uint32_t valid;            // host: this (format, mode) is eligible
+    uint32_t check_denorm_in;  // host: fp32-subnormal inputs need the exact routine
+};
+
+template <int MODE>
+struct FastTraits {
+    static constexpr bool kFaddSub =
+        MODE == LOF_RoundToNearestEven || MODE == LOF_RoundTowardsZero || MODE == LOF_RoundAwayFromZero ||
+        MODE == LOF_RoundUp || MODE == LOF_RoundDown || MODE == LOF_RoundToOdd;
+    static constexpr bool kStochastic = ModeTraits<MODE>::kUsesRng;
+};
+
+// RoundMantissa for r >= 1 (no r == 0 special case), magnitude in, unmasked out
+template <int MODE>
+__device__ __forceinline__ uint32_t round_bits_r1(uint32_t a, int r, int len, bool pos, uint32_t w)
+{
+    if constexpr (MODE == LOF_RoundToNearestEven) return a + ((a >> r) & 1u) + ((1u << (r - 1)) - 1u);
+    else if constexpr (MODE == LOF_RoundToNearestOdd) return a + ((~a >> r) & 1u) + ((1u << (r - 1)) - 1u);
+    else if constexpr (MODE == LOF_RoundTiesTowardsZero) return a + ((1u << (r - 1)) - 1u);
+    else if constexpr (MODE == LOF_RoundTiesToAway) return a + (1u << (r - 1));       // == trunc + (bit(r-1) << r) after the mask
+    else if constexpr (MODE == LOF_RoundAwayFromZero) return a + ((1u << r) - 1u);    // == trunc + (tail ? 2^r : 0) after the mask
+    else if constexpr (MODE == LOF_RoundUp) return a + (pos ? ((1u << r) - 1u) : 0u);
+    else if constexpr (MODE == LOF_RoundDown) return a + (pos ? 0u : ((1u << r) - 1u));
+    else return round_bits<MODE, uint32_t>(a, r, len, pos, w);
+}
+
+template <int MODE>
+__device__ __forceinline__ uint32_t sub_regime_fadd(uint32_t a, uint32_t s, float M)
+{
+    const float ax = __uint_as_float(a);
+    float t;
+    if constexpr (MODE == LOF_RoundToNearestEven) t = __fadd_rn(ax, M);
+    else if constexpr (MODE == LOF_RoundTowardsZero) t = __fadd_rz(ax, M);
+    else if constexpr (MODE == LOF_RoundAwayFromZero) t = __fadd_ru(ax, M);
+    else if constexpr (MODE == LOF_RoundUp) t = (s == 0) ? __fadd_ru(ax, M) : __fadd_rz(ax, M);
+    else if constexpr (MODE == LOF_RoundDown) t = (s == 0) ? __fadd_rz(ax, M) : __fadd_ru(ax, M);
+    else {  // RoundToOdd: truncate, then set the grid LSB when anything was dropped
+        const float tz = __fadd_rz(ax, M), tu = __fadd_ru(ax, M);
+        t = __uint_as_float(__float_as_uint(tz) | (tz != tu ? 1u : 0u));
+    }
+    return __float_as_uint(__fsub_rn(t, M)) | s;
+}
+
+// integer sub path for exponent field >= 1 (genuine hidden bit)
+template <int MODE>
+__device__ __forceinline__ uint32_t sub_regime_int(uint32_t a, uint32_t s, const FastPlan& fp, uint32_t w)
+{
+    const int r_true = fp.rbase - (int)(a >> 23);                  // >= shiftN + 1
+    const int r = max(min(r_true, 25), 1);                         // lanes of the normal regime compute garbage that is discarded
+    const uint32_t sig = (a & 0x7FFFFFu) | 0x800000u;
+    const uint32_t t = round_bits_r1<MODE>(sig, r, fp.stoch_len, s == 0, w);
+    uint32_t k = t >> r;
+    if constexpr (FastTraits<MODE>::kStochastic) k = (r_true >= 24) ? 0u : k;   // below denorm_min: flush (lo_float.h:2902)
+    return __float_as_uint(__fmul_rn(__uint2float_rn(k), fp.min_val)) | s;
+}
+
+// one element; *rare is OR-ed with "this lane needs the exact routine"
+template <int MODE, bool SAT, bool CHECK>
+__device__ __forceinline__ uint32_t round_fast_f32(uint32_t x, const FastPlan& fp, uint32_t w, bool& rare)
+{
+    const uint32_t a = x & 0x7FFFFFFFu, s = x & 0x80000000u;
+    const uint32_t tm = round_bits_r1<MODE>(a, fp.shiftN, fp.stoch_len, s == 0, w) & fp.maskN;
+    uint32_t out = (tm >= fp.ovf_thresh) ? (SAT ? x : 0x7F800000u) : (tm | s);
+    if constexpr (FastTraits<MODE>::kFaddSub) {
+        const uint32_t sub = sub_regime_fadd<MODE>(a, s, fp.M);
+        out = (a < fp.min_normal_bits) ? sub : out;
+        if constexpr (CHECK) rare |= (a - 1u) < 0x007FFFFFu;
+    } else {
+        const uint32_t sub = sub_regime_int<MODE>(a, s, fp, w);
+        out = (a < fp.min_normal_bits) ? sub : out;
+        out = (a == 0u) ? x : out;
+        rare |= (a - 1u) < 0x007FFFFFu;
+    }
+    return (a > 0x7F800000u) ? 0x7FC00000u : out;
+}
+
+// Variant with the overflow policy and the subnormal-input check as launch-uniform runtime flags
+// (used by the MX kernels, which are already templated on block size x mode).
+template <int MODE>
+__device__ __forceinline__ uint32_t round_fast_f32_rt(uint32_t x, const FastPlan& fp, bool sat, uint32_t w, bool& rare)
+{
+    const uint32_t a = x & 0x7FFFFFFFu, s = x & 0x80000000u;
+    const uint32_t tm = round_bits_r1<MODE>(a, fp.shiftN, fp.stoch_len, s == 0, w) & fp.maskN;
+    uint32_t out = (tm >= fp.ovf_thresh) ? (sat ? x : 0x7F800000u) : (tm | s);
+    if constexpr (FastTraits<MODE>::kFaddSub) {
+        const uint32_t sub = sub_regime_fadd<MODE>(a, s, fp.M);
+        out = (a < fp.min_normal_bits) ? sub : out;
+        rare |= (fp.check_denorm_in != 0u) && ((a - 1u) < 0x007FFFFFu);
+    } else {
+        const uint32_t sub = sub_regime_int<MODE>(a, s, fp, w);
+        out = (a < fp.min_normal_bits) ? sub : out;
+        out = (a == 0u) ? x : out;
+        rare |= (a - 1u) < 0x007FFFFFu;
+    }
+    return (a > 0x7F800000u) ? 0x7FC00000u : out;
+}
+
+// out-of-line exact routine for the rare lanes of the fast kernels
+template <int MODE>
+__device__ __noinline__ uint32_t exact_params_f32(uint32_t v, const RoundPlan& plan, uint32_t w)
+{
+    return round_params_elem<LOF_F32, MODE>(v, plan, w);
+}
+
+}  // namespace lof

@@ -16,6 +16,7 @@
 #pragma once
 
 #include "lof_core.cuh"
+#include "lof_fast_f32.cuh"
 
 namespace lof {
 
@@ -24,6 +25,7 @@ constexpr int kMxThreads = 256;
 struct MxArgs {
     RoundPlan elem;        // private (element) format plan
     RoundPlan scale;       // public (scale) format plan
+    FastPlan  fast;        // branch-free element rounding when fast.valid (lof_fast_f32.cuh)
     float     inv_pmn_unused;
     float     pmn;         // priv_max_normal (LoPy_bind.cpp:202)
     int32_t   scale_mode;  // rounding mode of the scale (stoch_len forced to 0, LoPy_bind.cpp:208)
@@ -64,12 +66,19 @@ __device__ __forceinline__ MxBlockCtx mx_make_ctx(float scale)
 }
 
 template <int MODE>
-__device__ __forceinline__ float mx_quant(float x, const MxBlockCtx& c, const RoundPlan& ep, uint32_t w)
+__device__ __forceinline__ float mx_quant(float x, const MxBlockCtx& c, const MxArgs& a, uint32_t w)
 {
-    if (!c.live) return 0.0f;
     const float q = c.pow2 ? __fmul_rn(x, c.recip) : __fdiv_rn(x, c.scale);
-    const float r = __uint_as_float(round_params_elem<LOF_F32, MODE>(__float_as_uint(q), ep, w));
-    return __fmul_rn(r, c.scale);
+    uint32_t rb;
+    if (a.fast.valid) {
+        bool rare = false;
+        rb = round_fast_f32_rt<MODE>(__float_as_uint(q), a.fast, a.elem.saturating != 0, w, rare);
+        if (rare) rb = exact_params_f32<MODE>(__float_as_uint(q), a.elem, w);
+    } else {
+        rb = exact_params_f32<MODE>(__float_as_uint(q), a.elem, w);
+    }
+    const float r = __fmul_rn(__uint_as_float(rb), c.scale);
+    return c.live ? r : 0.0f;
 }
 
 __device__ __forceinline__ float amax4(const float4& v)
@@ -137,10 +146,10 @@ mx_shuffle_kernel(const float4* in, float4* out, int64_t nrows, MxArgs a, RngArg
             uint4 w = make_uint4(0, 0, 0, 0);
             if constexpr (ModeTraits<MODE>::kUsesRng) w = philox_block(rng, g0 >> 2);
             float4 o;
-            o.x = mx_quant<MODE>(v[r].x, c, a.elem, w.x);
-            o.y = mx_quant<MODE>(v[r].y, c, a.elem, w.y);
-            o.z = mx_quant<MODE>(v[r].z, c, a.elem, w.z);
-            o.w = mx_quant<MODE>(v[r].w, c, a.elem, w.w);
+            o.x = mx_quant<MODE>(v[r].x, c, a, w.x);
+            o.y = mx_quant<MODE>(v[r].y, c, a, w.y);
+            o.z = mx_quant<MODE>(v[r].z, c, a, w.z);
+            o.w = mx_quant<MODE>(v[r].w, c, a, w.w);
             st_stream_f4(out + (row0 + r) * 32 + lane, o);
         }
     }
@@ -165,7 +174,7 @@ mx_block_per_thread_kernel(const float* in, float* out, int64_t elem0, int64_t n
         for (int i = 0; i < len; ++i) {
             uint32_t w = 0;
             if constexpr (ModeTraits<MODE>::kUsesRng) w = philox_word(rng, first_index + (uint64_t)(s + i));
-            out[s + i] = mx_quant<MODE>(in[s + i], c, a.elem, w);
+            out[s + i] = mx_quant<MODE>(in[s + i], c, a, w);
         }
     }
 }

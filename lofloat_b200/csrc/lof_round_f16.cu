@@ -3,12 +3,13 @@
 
 namespace lof {
 
-cudaError_t launch_round_f16(bool params, int mode, const void* in, void* out, int64_t n, const RoundPlan& plan,
-                            int r, int len, double scale, const RngArgs& rng, uint64_t first_index,
+cudaError_t launch_round_f16(int kind, int mode, const void* in, void* out, int64_t n, const RoundPlan& plan,
+                            const FastPlan& fast, int r, int len, double scale, const RngArgs& rng, uint64_t first_index,
                             const RoundLaunchCfg& cfg, cudaStream_t stream)
 {
-    if (params) return launch_round<LOF_F16, true>(mode, in, out, n, plan, r, len, scale, rng, first_index, cfg, stream);
-    return launch_round<LOF_F16, false>(mode, in, out, n, plan, r, len, scale, rng, first_index, cfg, stream);
+    if (kind != kKindMantissa)
+        return launch_round<LOF_F16, kKindParams>(mode, in, out, n, plan, fast, r, len, scale, rng, first_index, cfg, stream);
+    return launch_round<LOF_F16, kKindMantissa>(mode, in, out, n, plan, fast, r, len, scale, rng, first_index, cfg, stream);
 }
 
 }  // namespace lof

@@ -3,12 +3,20 @@
 
 namespace lof {
 
-cudaError_t launch_round_f32(bool params, int mode, const void* in, void* out, int64_t n, const RoundPlan& plan,
-                            int r, int len, double scale, const RngArgs& rng, uint64_t first_index,
+cudaError_t launch_round_f32(int kind, int mode, const void* in, void* out, int64_t n, const RoundPlan& plan,
+                            const FastPlan& fast, int r, int len, double scale, const RngArgs& rng, uint64_t first_index,
                             const RoundLaunchCfg& cfg, cudaStream_t stream)
 {
-    if (params) return launch_round<LOF_F32, true>(mode, in, out, n, plan, r, len, scale, rng, first_index, cfg, stream);
-    return launch_round<LOF_F32, false>(mode, in, out, n, plan, r, len, scale, rng, first_index, cfg, stream);
+    switch (kind) {
+    case kKindFastSat:    return launch_round<LOF_F32, kKindFastSat>(mode, in, out, n, plan, fast, r, len, scale, rng, first_index, cfg, stream);
+    case kKindFastExt:    return launch_round<LOF_F32, kKindFastExt>(mode, in, out, n, plan, fast, r, len, scale, rng, first_index, cfg, stream);
+    case kKindFastSatChk: return launch_round<LOF_F32, kKindFastSatChk>(mode, in, out, n, plan, fast, r, len, scale, rng, first_index, cfg, stream);
+    case kKindFastExtChk: return launch_round<LOF_F32, kKindFastExtChk>(mode, in, out, n, plan, fast, r, len, scale, rng, first_index, cfg, stream);
+    default: break;
+    }
+    if (kind != kKindMantissa)
+        return launch_round<LOF_F32, kKindParams>(mode, in, out, n, plan, fast, r, len, scale, rng, first_index, cfg, stream);
+    return launch_round<LOF_F32, kKindMantissa>(mode, in, out, n, plan, fast, r, len, scale, rng, first_index, cfg, stream);
 }
 
 }  // namespace lof

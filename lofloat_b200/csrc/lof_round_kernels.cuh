@@ -14,6 +14,7 @@
 #pragma once
 
 #include "lof_core.cuh"
+#include "lof_fast_f32.cuh"
 
 namespace lof {
 
@@ -29,31 +30,68 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p)
 __device__ __forceinline__ void st_stream(uint4* p, const uint4& v)
 {
     asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};"
-                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
 
-// What the kernel does per element: PARAMS = format-params overload, else mantissa-only.
-template <int DTYPE, int MODE, bool PARAMS>
+// What the kernel does per element.
+enum : int {
+    kKindMantissa = 0,      // virtual_round(value, mantissa_bits)
+    kKindParams = 1,        // virtual_round(value, params): exact integer routine, any format / container
+    kKindFastSat = 2,       // fp32 branch-free path (lof_fast_f32.cuh), OV_behavior == Saturating
+    kKindFastExt = 3,       //   "                                      , OV_behavior == Extended
+    kKindFastSatChk = 4,    //   + fp32-subnormal inputs routed to the exact routine (denorm_min < 2^-126)
+    kKindFastExtChk = 5
+};
+constexpr bool kind_is_fast(int k) { return k >= kKindFastSat; }
+
+template <int DTYPE, int MODE, int KIND>
 struct ElemOp {
     using S = Src<DTYPE>;
     using B = typename S::bits_t;
-    RoundPlan plan;                 // PARAMS
-    int r;                          // !PARAMS: bits to drop
+    RoundPlan plan;                 // params overloads
+    FastPlan fast;                  // fast fp32 kinds
+    int r;                          // mantissa overload: bits to drop
     int len;
     typename S::scale_t scale;
     bool scale_one;
 
+    // exact routines (any container)
     __device__ __forceinline__ B operator()(B v, uint32_t w) const
     {
         if (!scale_one) v = S::apply_scale(v, scale);   // Lof_kernel.cu:41,53 fused pre-scale
-        if constexpr (PARAMS) return round_params_elem<DTYPE, MODE>(v, plan, w);
-        else return round_mantissa_elem<DTYPE, MODE>(v, r, len, w);
+        if constexpr (KIND == kKindMantissa) return round_mantissa_elem<DTYPE, MODE>(v, r, len, w);
+        else return round_params_elem<DTYPE, MODE>(v, plan, w);
     }
 };
 
+template <int MODE, int KIND>
+__device__ __forceinline__ uint4 round_vec16_fast(uint4 v, const ElemOp<LOF_F32, MODE, KIND>& op, const uint4& w)
+{
+    constexpr bool SAT = (KIND == kKindFastSat || KIND == kKindFastSatChk);
+    constexpr bool CHK = (KIND == kKindFastSatChk || KIND == kKindFastExtChk);
+    // scale * x unconditionally: x * 1.0f is the identity on every non-NaN bit pattern and NaN ends as +qNaN anyway
+    const uint32_t x0 = __float_as_uint(__fmul_rn(op.scale, __uint_as_float(v.x)));
+    const uint32_t x1 = __float_as_uint(__fmul_rn(op.scale, __uint_as_float(v.y)));
+    const uint32_t x2 = __float_as_uint(__fmul_rn(op.scale, __uint_as_float(v.z)));
+    const uint32_t x3 = __float_as_uint(__fmul_rn(op.scale, __uint_as_float(v.w)));
+    bool rare = false;
+    uint4 o;
+    o.x = round_fast_f32<MODE, SAT, CHK>(x0, op.fast, w.x, rare);
+    o.y = round_fast_f32<MODE, SAT, CHK>(x1, op.fast, w.y, rare);
+    o.z = round_fast_f32<MODE, SAT, CHK>(x2, op.fast, w.z, rare);
+    o.w = round_fast_f32<MODE, SAT, CHK>(x3, op.fast, w.w, rare);
+    if (rare) {     // an fp32-subnormal input in this vector: redo it with the exact routine
+        o.x = exact_params_f32<MODE>(x0, op.plan, w.x);
+        o.y = exact_params_f32<MODE>(x1, op.plan, w.y);
+        o.z = exact_params_f32<MODE>(x2, op.plan, w.z);
+        o.w = exact_params_f32<MODE>(x3, op.plan, w.w);
+    }
+    return o;
+}
+
 // process one 16-byte vector that starts at global element index g0
-template <int DTYPE, int MODE, bool PARAMS>
-__device__ __forceinline__ uint4 round_vec16(uint4 v, const ElemOp<DTYPE, MODE, PARAMS>& op,
+template <int DTYPE, int MODE, int KIND>
+__device__ __forceinline__ uint4 round_vec16(uint4 v, const ElemOp<DTYPE, MODE, KIND>& op,
                                              const RngArgs& rng, uint64_t g0)
 {
     using B = typename Src<DTYPE>::bits_t;
@@ -61,6 +99,7 @@ __device__ __forceinline__ uint4 round_vec16(uint4 v, const ElemOp<DTYPE, MODE, 
     if constexpr (sizeof(B) == 4) {
         uint4 w = make_uint4(0, 0, 0, 0);
         if constexpr (kRng) w = philox_block(rng, g0 >> 2);          // g0 % 4 == 0 (host-checked)
+        if constexpr (kind_is_fast(KIND)) return round_vec16_fast<MODE, KIND>(v, op, w);
         v.x = op(v.x, w.x); v.y = op(v.y, w.y); v.z = op(v.z, w.z); v.w = op(v.w, w.w);
     } else if constexpr (sizeof(B) == 2) {
         uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0;
@@ -87,10 +126,10 @@ __device__ __forceinline__ uint4 round_vec16(uint4 v, const ElemOp<DTYPE, MODE, 
 }
 
 // Vector kernel: in/out 16-byte aligned, nvec full vectors, then `ntail` scalar elements.
-template <int DTYPE, int MODE, bool PARAMS, int UNROLL>
+template <int DTYPE, int MODE, int KIND, int UNROLL>
 __global__ void __launch_bounds__(kRoundThreads)
 round_vec_kernel(const uint4* in, uint4* out, int64_t nvec, int ntail,
-                 ElemOp<DTYPE, MODE, PARAMS> op, RngArgs rng, uint64_t first_index)
+                 ElemOp<DTYPE, MODE, KIND> op, RngArgs rng, uint64_t first_index)
 {
     using B = typename Src<DTYPE>::bits_t;
     constexpr int VEC = 16 / (int)sizeof(B);
@@ -109,7 +148,7 @@ round_vec_kernel(const uint4* in, uint4* out, int64_t nvec, int ntail,
         for (int u = 0; u < UNROLL; ++u) {
             const int64_t idx = base + (int64_t)u * kRoundThreads;
             if (idx < nvec) {
-                const uint4 r = round_vec16<DTYPE, MODE, PARAMS>(v[u], op, rng, first_index + (uint64_t)idx * VEC);
+                const uint4 r = round_vec16<DTYPE, MODE, KIND>(v[u], op, rng, first_index + (uint64_t)idx * VEC);
                 st_stream(out + idx, r);
             }
         }
@@ -127,10 +166,10 @@ round_vec_kernel(const uint4* in, uint4* out, int64_t nvec, int ntail,
 
 // Scalar kernel: any alignment, any first_index (still coalesced; one element per thread
 // per grid-stride step).  Only used for unaligned views / odd shard offsets.
-template <int DTYPE, int MODE, bool PARAMS>
+template <int DTYPE, int MODE, int KIND>
 __global__ void __launch_bounds__(kRoundThreads)
 round_scalar_kernel(const typename Src<DTYPE>::bits_t* in, typename Src<DTYPE>::bits_t* out,
-                    int64_t n, ElemOp<DTYPE, MODE, PARAMS> op, RngArgs rng, uint64_t first_index)
+                    int64_t n, ElemOp<DTYPE, MODE, KIND> op, RngArgs rng, uint64_t first_index)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -146,8 +185,8 @@ struct RoundLaunchCfg {
     int num_sms;
 };
 
-template <int DTYPE, int MODE, bool PARAMS>
-cudaError_t launch_round_mode(const void* in, void* out, int64_t n, const ElemOp<DTYPE, MODE, PARAMS>& op,
+template <int DTYPE, int MODE, int KIND>
+cudaError_t launch_round_mode(const void* in, void* out, int64_t n, const ElemOp<DTYPE, MODE, KIND>& op,
                               const RngArgs& rng, uint64_t first_index, const RoundLaunchCfg& cfg,
                               cudaStream_t stream)
 {
@@ -167,7 +206,7 @@ cudaError_t launch_round_mode(const void* in, void* out, int64_t n, const ElemOp
         uint4* vout = static_cast<uint4*>(out);
         // the unroll depth is tunable for fp32 (the benchmarked container); the other containers
         // use 4 vectors in flight per thread
-#define LOF_LAUNCH_VEC(U) round_vec_kernel<DTYPE, MODE, PARAMS, U><<<(unsigned)grid, kRoundThreads, 0, stream>>>( \
+#define LOF_LAUNCH_VEC(U) round_vec_kernel<DTYPE, MODE, KIND, U><<<(unsigned)grid, kRoundThreads, 0, stream>>>( \
             vin, vout, nvec, ntail, op, rng, first_index)
         if constexpr (DTYPE == LOF_F32) {
             switch (cfg.unroll) {
@@ -184,15 +223,15 @@ cudaError_t launch_round_mode(const void* in, void* out, int64_t n, const ElemOp
         int64_t grid = (n + kRoundThreads - 1) / kRoundThreads;
         if (grid > max_ctas * 2) grid = max_ctas * 2;
         if (grid < 1) grid = 1;
-        round_scalar_kernel<DTYPE, MODE, PARAMS><<<(unsigned)grid, kRoundThreads, 0, stream>>>(
+        round_scalar_kernel<DTYPE, MODE, KIND><<<(unsigned)grid, kRoundThreads, 0, stream>>>(
             static_cast<const B*>(in), static_cast<B*>(out), n, op, rng, first_index);
     }
     return cudaGetLastError();
 }
 
 // mode dispatch for one (dtype, overload); defined once per dtype in lof_round_<dtype>.cu
-template <int DTYPE, bool PARAMS>
-cudaError_t launch_round(int mode, const void* in, void* out, int64_t n, const RoundPlan& plan, int r, int len,
+template <int DTYPE, int KIND>
+cudaError_t launch_round(int mode, const void* in, void* out, int64_t n, const RoundPlan& plan, const FastPlan& fast, int r, int len,
                          double scale, const RngArgs& rng, uint64_t first_index, const RoundLaunchCfg& cfg,
                          cudaStream_t stream)
 {
@@ -201,9 +240,9 @@ cudaError_t launch_round(int mode, const void* in, void* out, int64_t n, const R
     switch (mode) {
 #define LOF_CASE(M)                                                                           \
     case M: {                                                                                 \
-        ElemOp<DTYPE, M, PARAMS> op;                                                          \
-        op.plan = plan; op.r = r; op.len = len; op.scale = sc; op.scale_one = (sc == (typename S::scale_t)1); \
-        return launch_round_mode<DTYPE, M, PARAMS>(in, out, n, op, rng, first_index, cfg, stream); \
+        ElemOp<DTYPE, M, KIND> op;                                                          \
+        op.plan = plan; op.fast = fast; op.r = r; op.len = len; op.scale = sc; op.scale_one = (sc == (typename S::scale_t)1); \
+        return launch_round_mode<DTYPE, M, KIND>(in, out, n, op, rng, first_index, cfg, stream); \
     }
         LOF_CASE(LOF_RoundToNearestEven) LOF_CASE(LOF_RoundTowardsZero) LOF_CASE(LOF_RoundAwayFromZero)
         LOF_CASE(LOF_StochasticRoundingA) LOF_CASE(LOF_RoundToNearestOdd) LOF_CASE(LOF_RoundDown)
@@ -217,17 +256,17 @@ cudaError_t launch_round(int mode, const void* in, void* out, int64_t n, const R
 }
 
 // explicit-instantiation entry points (one translation unit per dtype)
-cudaError_t launch_round_f32(bool params, int mode, const void* in, void* out, int64_t n, const RoundPlan& plan,
-                             int r, int len, double scale, const RngArgs& rng, uint64_t first_index,
+cudaError_t launch_round_f32(int kind, int mode, const void* in, void* out, int64_t n, const RoundPlan& plan,
+                              const FastPlan& fast, int r, int len, double scale, const RngArgs& rng, uint64_t first_index,
                              const RoundLaunchCfg& cfg, cudaStream_t stream);
-cudaError_t launch_round_f16(bool params, int mode, const void* in, void* out, int64_t n, const RoundPlan& plan,
-                             int r, int len, double scale, const RngArgs& rng, uint64_t first_index,
+cudaError_t launch_round_f16(int kind, int mode, const void* in, void* out, int64_t n, const RoundPlan& plan,
+                              const FastPlan& fast, int r, int len, double scale, const RngArgs& rng, uint64_t first_index,
                              const RoundLaunchCfg& cfg, cudaStream_t stream);
-cudaError_t launch_round_bf16(bool params, int mode, const void* in, void* out, int64_t n, const RoundPlan& plan,
-                              int r, int len, double scale, const RngArgs& rng, uint64_t first_index,
+cudaError_t launch_round_bf16(int kind, int mode, const void* in, void* out, int64_t n, const RoundPlan& plan,
+                              const FastPlan& fast, int r, int len, double scale, const RngArgs& rng, uint64_t first_index,
                               const RoundLaunchCfg& cfg, cudaStream_t stream);
-cudaError_t launch_round_f64(bool params, int mode, const void* in, void* out, int64_t n, const RoundPlan& plan,
-                             int r, int len, double scale, const RngArgs& rng, uint64_t first_index,
+cudaError_t launch_round_f64(int kind, int mode, const void* in, void* out, int64_t n, const RoundPlan& plan,
+                              const FastPlan& fast, int r, int len, double scale, const RngArgs& rng, uint64_t first_index,
                              const RoundLaunchCfg& cfg, cudaStream_t stream);
 
 }  // namespace lof

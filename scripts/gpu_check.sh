@@ -26,3 +26,14 @@ echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 1 --e2e-steps 0 > $OUT/ncu_bench.log 2>&1; echo "ncu exit $?"
 tail -3 $OUT/launches.csv
+if [ "${PROFILE:-0}" = 1 ]; then
+  echo "== ncu full captures"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:round_vec_kernel -s 2 -c 1 -f -o $OUT/prof_round_rne \
+      python scripts/prof_target.py round 0 e4m3 > $OUT/ncu_round.log 2>&1; echo "ncu round exit $?"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:round_vec_kernel -s 2 -c 1 -f -o $OUT/prof_round_sra \
+      python scripts/prof_target.py round 3 e4m3 > $OUT/ncu_round_sra.log 2>&1; echo "ncu round sra exit $?"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:mx_shuffle_kernel -s 2 -c 1 -f -o $OUT/prof_mx_shuffle \
+      python scripts/prof_target.py mx 0 e4m3 > $OUT/ncu_mx0.log 2>&1; echo "ncu mx0 exit $?"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:mx_tma_kernel -s 2 -c 1 -f -o $OUT/prof_mx_tma \
+      python scripts/prof_target.py mx 1 e4m3 > $OUT/ncu_mx1.log 2>&1; echo "ncu mx1 exit $?"
+fi

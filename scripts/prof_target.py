@@ -1,0 +1,56 @@
+"""Tiny driver for ncu captures: runs one op a few times on BASELINE-sized inputs.
+
+    python scripts/prof_target.py round [mode] [format]     # 2^28 fp32, randn * 2^U{-12..12}
+    python scripts/prof_target.py mx [variant] [format]     # 16384 x 16384 fp32, block 32
+    python scripts/prof_target.py gemm [M]                  # exact-mode GEMM
+"""
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import lofloat_b200 as lof  # noqa: E402
+
+FMT = {"e4m3": (8, 4, 7), "e5m2": (8, 3, 15), "e3m2": (6, 3, 3), "e2m1": (4, 2, 1)}
+
+
+def fmt(name):
+    if name == "bf16like":
+        return lof.create_bfloat16_params()
+    k, p, b = FMT[name]
+    return lof.create_p3109_params(k, p, bias=b)
+
+
+def main():
+    what = sys.argv[1] if len(sys.argv) > 1 else "round"
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(2024)
+    if what == "round":
+        mode = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+        f = fmt(sys.argv[3] if len(sys.argv) > 3 else "e4m3")
+        n = 1 << 28
+        x = torch.randn(n, device=dev, generator=g)
+        x *= torch.exp2(torch.randint(-12, 13, (n,), device=dev, generator=g).float())
+        for _ in range(4):
+            y = lof.virtual_round(x, f, mode, 8 if mode in (3, 8, 9, 14) else 0)
+    elif what == "mx":
+        variant = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+        f = fmt(sys.argv[3] if len(sys.argv) > 3 else "e4m3")
+        lof.set_option("mx.variant", variant)
+        x = torch.randn(16384, 16384, device=dev, generator=g)
+        x *= torch.exp2(torch.randint(-8, 9, (16384, 1), device=dev, generator=g).float())
+        for _ in range(4):
+            y = lof.virtual_mx_round(x, 32, f, lof.create_e8m0_params())
+    else:
+        M = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
+        A = torch.rand(M, M, device=dev, generator=g) * 2 - 1
+        B = torch.rand(M, M, device=dev, generator=g) * 2 - 1
+        for _ in range(2):
+            y = lof.lof_gemm(A, B, 10)
+    torch.cuda.synchronize()
+    print("done", float(y.flatten()[0]))
+
+
+if __name__ == "__main__":
+    main()

@@ -420,6 +420,52 @@ def test_full_size_properties_mx(lof, cuda_dev, variant):
         _lib.set_option("mx.variant", 0)
 
 
+def test_fast_kernel_equals_exact_kernel_every_fp32_pattern(lof, cuda_dev):
+    """The branch-free fp32 kernels (lof_fast_f32.cuh: float-add trick for the target-subnormal regime,
+    clamped-shift integer path, select-based overflow/NaN) against the exact integer kernel
+    (round.fast = 0) on EVERY fp32 bit pattern, every named format, all 15 modes, with and without the
+    fused scale.  Compared on the device; the exact kernel itself is pinned to the oracle above."""
+    from lofloat_b200 import _lib
+    chunk = 1 << 28
+    checked = 0
+    try:
+        for name, f in L.FORMATS.items():
+            d = _desc(lof, f)
+            r = 23 - f.mantissa_bits
+            for mode in range(15):
+                sl = min(7, max(r, 1)) if mode in (L.SR_A, L.SR_B, L.SR_C, L.SR_D) else 0
+                for base in range(0, 1 << 32, chunk):
+                    bits = torch.arange(base, base + chunk, device=cuda_dev, dtype=torch.int64).to(torch.int32)
+                    x = bits.view(torch.float32)
+                    _lib.set_option("round.fast", 1)
+                    a = lof.virtual_round(x, d, mode, sl, rng=(17, 3), first_index=base)
+                    _lib.set_option("round.fast", 0)
+                    b = lof.virtual_round(x, d, mode, sl, rng=(17, 3), first_index=base)
+                    same = torch.equal(a.view(torch.int32), b.view(torch.int32))
+                    if not same:
+                        idx = int((a.view(torch.int32) != b.view(torch.int32)).nonzero()[0])
+                        raise AssertionError(f"{name} {L.MODE_NAMES[mode]}: in=0x{(base + idx) & 0xFFFFFFFF:08x} "
+                                             f"fast=0x{int(a.view(torch.int32)[idx]) & 0xFFFFFFFF:08x} "
+                                             f"exact=0x{int(b.view(torch.int32)[idx]) & 0xFFFFFFFF:08x}")
+                    checked += chunk
+                    del bits, x, a, b
+        # fused scale (scale * x is formed inside the kernel)
+        for name in ("e4m3_b7", "bf16_like"):
+            d = _desc(lof, L.FORMATS[name])
+            for mode in (L.RNE, L.RAZ, L.RNO, L.SR_A):
+                for base in range(0, 1 << 32, chunk):
+                    x = torch.arange(base, base + chunk, device=cuda_dev, dtype=torch.int64).to(torch.int32).view(torch.float32)
+                    _lib.set_option("round.fast", 1)
+                    a = lof.virtual_round(x, d, mode, 4 if mode == L.SR_A else 0, 0.3, rng=(1, 1))
+                    _lib.set_option("round.fast", 0)
+                    b = lof.virtual_round(x, d, mode, 4 if mode == L.SR_A else 0, 0.3, rng=(1, 1))
+                    assert torch.equal(a.view(torch.int32), b.view(torch.int32)), (name, mode, hex(base))
+                    del x, a, b
+    finally:
+        _lib.set_option("round.fast", 1)
+    assert checked == len(L.FORMATS) * 15 * (1 << 32)
+
+
 @pytest.mark.slow
 def test_exhaustive_fp32_sweep_8bit_formats(lof, cuda_dev):
     """Every fp32 bit pattern (2^32) for the 8-bit benchmark format under RNE, plus every 16th
