@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -71,9 +71,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def mark(self):
+        """Wall-clock marker: rows received after mark_start and before mark_end are 'under load'."""
+        return time.time()
+
+    def stop(self, t_begin=None, t_end=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -83,7 +87,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for (ts, r) in self.rows if (t_begin is None or ts >= t_begin) and (t_end is None or ts <= t_end + 0.05)]
+        if not rows:                                     # region shorter than one sample: take the nearest samples
+            rows = [r for (_, r) in self.rows[-3:]]
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for nm, v in zip(names, r[3:7]):
@@ -146,6 +153,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                                      # nvidia-smi needs a moment to come up: start before warm-up
     for _ in range(args.warmup):
         for i, (_, _, fmt, ps) in enumerate(combos):
             one_pass(i, fmt, ps)
@@ -153,11 +163,9 @@ def run_ours(args):
     per_launch = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in combos]
                   for _ in range(args.steps)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = _lib.kernel_launch_count()
     barrier()
+    w_begin = time.time()
     t0.record()
     for s in range(args.steps):
         for i, (_, _, fmt, ps) in enumerate(combos):
@@ -165,7 +173,7 @@ def run_ours(args):
     t1.record()
     barrier()
     launches = _lib.kernel_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(w_begin, time.time()) if rank == 0 else None
     ms = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -203,7 +211,9 @@ def run_ours(args):
         xh = torch.empty(n_h, dtype=torch.float32).pin_memory()
         xh.copy_(x[:n_h])
         yh = torch.empty(n_h, dtype=torch.float32).pin_memory()
-        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        if args.e2e_steps <= 0:
+            raise RuntimeError("skipped (--e2e-steps 0)")
+        e2e_steps = min(args.steps, args.e2e_steps)
 
         def host_sweep():
             for _, _, fmt, ps in combos:
@@ -234,7 +244,7 @@ def run_ours(args):
 
     other = {}
     cpu_baseline = None
-    if rank == 0:
+    if rank == 0 and not args.no_side:
         other = side_measurements(torch, lib, _lib, dev, x, y, stream)
         if world == 1:
             cpu_baseline = cpu_reference_sample(x[: 1 << 24].cpu().numpy(), budget_s=20.0)
@@ -406,10 +416,11 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-side", action="store_true", help="skip the mx/gemm side measurements and the CPU sample (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -58,7 +58,9 @@ typedef enum { LOF_NegtoZero = 0, LOF_NegtoNaN = 1 } lof_unsigned_behavior_t;   
 
 /* container (storage) type of the tensor being rounded.  The reference dispatches
  * float/double/c10::Half (LoPy_bind.cpp:83,133); bf16 is new. */
-typedef enum { LOF_F32 = 0, LOF_F16 = 1, LOF_BF16 = 2, LOF_F64 = 3 } lof_dtype_t;
+typedef enum { LOF_F32 = 0, LOF_F16 = 1, LOF_BF16 = 2, LOF_F64 = 3,
+               /* tensor-core OPERAND encodings (lof_gemm_chunked_f32 only): OCP e4m3fn / e5m2 */
+               LOF_E4M3 = 4, LOF_E5M2 = 5 } lof_dtype_t;
 
 typedef enum {
     LOF_OK = 0,
@@ -154,18 +156,29 @@ LOF_API int lof_gemm_f32(const float* A, const float* B, float* C, int64_t M, in
                  int accum_mant_bits, const lof_projspec_t* ps, int64_t kc,
                  float alpha, float beta, const lof_rng_t* rng, void* stream);
 
-/* Chunked tensor-core mode (tcgen05): C = alpha * sum over k-chunks, where after every
- * k_chunk columns of K the fp32 partial product from the tensor core is folded into the
- * running accumulator with ONE rounding into the accumulator format:
- *     acc = virtual_round(acc + partial_chunk, acc_fmt or accum_mant_bits, *ps)
- * (acc_fmt == NULL -> mantissa-only rounding like the reference; non-NULL adds the
- * exponent range, e.g. E5M10).  This is the design intent of src/gemms.hpp:430-552
- * (KR-chunk micro-accumulator); it has no runnable reference.
- * A and B must be exactly representable in `operand_dtype` (LOF_BF16 today). k_chunk must
- * be a multiple of 16; M % 128 == 0, N % 128 == 0, K % k_chunk == 0. */
+/* Chunked tensor-core mode (tcgen05 + TMEM): after every k_chunk columns of K the fp32 partial product P of
+ * the chunk (tensor core, fp32 accumulate) is folded into the running accumulator, which lives in the
+ * accumulator format:
+ *     default                      acc = virtual_round(acc + P)                    (ONE rounding of the exact sum)
+ *     LOF_GEMM_PARTIAL_ROUND       acc = virtual_round(acc + virtual_round(P))     (typed micro-accumulator)
+ *     C = alpha * acc
+ * virtual_round = mantissa-only rounding to accum_mant_bits like the reference GEMM leaf (acc_fmt == NULL) or
+ * rounding into the full format *acc_fmt incl. its exponent range (e.g. E5M10), under any deterministic
+ * rounding mode.  This is the design intent of src/gemms.hpp:430-552 (KR-chunk micro-accumulator); it has no
+ * runnable reference -- its CPU statement is oracle/lof_oracle.c.
+ * A and B are fp32 containers whose values must be exactly representable in `operand_dtype` (LOF_E4M3,
+ * LOF_E5M2 or LOF_BF16); otherwise LOF_GEMM_STATUS_{A,B}_INEXACT is OR-ed into *dev_status (a DEVICE int32,
+ * may be NULL) and C is meaningless.  k_chunk must be a multiple of 32 (8-bit operands) / 16 (bf16);
+ * k_chunk <= 0 = one chunk over all K.  K * sizeof(operand) must be a multiple of 16.  Asynchronous on stream. */
+#define LOF_GEMM_PARTIAL_ROUND       1u   /* flags */
+#define LOF_GEMM_NO_PACKED           2u   /* never use the packed half2/bfloat162 rounding epilogue */
+#define LOF_GEMM_STATUS_A_INEXACT    1    /* *dev_status bits */
+#define LOF_GEMM_STATUS_B_INEXACT    2
+#define LOF_GEMM_STATUS_PACKED_RANGE 4    /* informational: packed epilogue left the fp16 range, C was recomputed generically */
 LOF_API int lof_gemm_chunked_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
                          int accum_mant_bits, const lof_format_t* acc_fmt, const lof_projspec_t* ps,
-                         int64_t k_chunk, float alpha, int operand_dtype, void* stream);
+                         int64_t k_chunk, float alpha, int operand_dtype, uint32_t flags, int32_t* dev_status,
+                         void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Host-buffer entry points: what a binding calls when the tensor lives in host memory.

@@ -15,7 +15,10 @@ LIB_PATH = _PKG / "liblofloat_b200.so"
 # status codes (include/lofloat_b200.h)
 LOF_OK, LOF_ERR_INVALID_ARG, LOF_ERR_UNSUPPORTED, LOF_ERR_CUDA, LOF_ERR_NO_DEVICE, LOF_ERR_ALLOC = range(6)
 # dtypes
-LOF_F32, LOF_F16, LOF_BF16, LOF_F64 = range(4)
+LOF_F32, LOF_F16, LOF_BF16, LOF_F64, LOF_E4M3, LOF_E5M2 = range(6)
+# lof_gemm_chunked_f32 flags / status bits
+LOF_GEMM_PARTIAL_ROUND, LOF_GEMM_NO_PACKED = 1, 2
+LOF_GEMM_STATUS_A_INEXACT, LOF_GEMM_STATUS_B_INEXACT, LOF_GEMM_STATUS_PACKED_RANGE = 1, 2, 4
 
 # every symbol include/lofloat_b200.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = (
@@ -61,7 +64,7 @@ def _declare(lib):
     lib.lof_round_mantissa.argtypes = [vp, vp, i64, i32, i32, PP, f64, PR, u64, vp]
     lib.lof_mx_round_f32.argtypes = [vp, vp, i64, i32, PF, PF, PP, PP, PR, u64, vp]
     lib.lof_gemm_f32.argtypes = [vp, vp, vp, i64, i64, i64, i32, PP, i64, f32, f32, PR, vp]
-    lib.lof_gemm_chunked_f32.argtypes = [vp, vp, vp, i64, i64, i64, i32, PF, PP, i64, f32, i32, vp]
+    lib.lof_gemm_chunked_f32.argtypes = [vp, vp, vp, i64, i64, i64, i32, PF, PP, i64, f32, i32, C.c_uint32, vp, vp]
     lib.lof_round_params_host.argtypes = [vp, vp, i64, i32, PF, PP, f64, PR, u64, i32]
     lib.lof_round_mantissa_host.argtypes = [vp, vp, i64, i32, i32, PP, f64, PR, u64, i32]
     lib.lof_mx_round_f32_host.argtypes = [vp, vp, i64, i32, PF, PF, PP, PP, PR, u64, i32]

@@ -23,9 +23,10 @@ cudaError_t launch_gemm_exact(int mode, const float* A, const float* B, float* C
 cudaError_t launch_mx_tma(int mode, const float* in, float* out, int64_t n, const MxArgs& a, const RngArgs& rng,
                           const RngArgs& rng_scale, uint64_t first_index, const MxLaunchCfg& cfg, cudaStream_t stream,
                           int* launches, bool* handled);
-cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
-                           int mode, int accum_mant_bits, const RoundPlan* acc_plan, int64_t k_chunk, float alpha,
-                           int operand_dtype, cudaStream_t stream, int* launches, std::string* err);
+cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int mode,
+                           int accum_mant_bits, const lof_format_t* acc_fmt, const RoundPlan* acc_plan, const FastPlan* acc_fast,
+                           int64_t k_chunk, float alpha, int operand_dtype, uint32_t flags, int* dev_status,
+                           cudaStream_t stream, int* launches, std::string* err);
 }  // namespace lof
 
 using namespace lof;
@@ -470,7 +471,7 @@ int lof_gemm_f32(const float* A, const float* B, float* C, int64_t M, int64_t N,
 
 int lof_gemm_chunked_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
                          int accum_mant_bits, const lof_format_t* acc_fmt, const lof_projspec_t* ps, int64_t k_chunk,
-                         float alpha, int operand_dtype, void* stream)
+                         float alpha, int operand_dtype, uint32_t flags, int32_t* dev_status, void* stream)
 {
     if (M <= 0 || N <= 0 || K <= 0) return fail(LOF_ERR_INVALID_ARG, "GEMM dimensions must be positive");
     if (!A || !B || !C || !ps) return fail(LOF_ERR_INVALID_ARG, "null argument");
@@ -478,18 +479,22 @@ int lof_gemm_chunked_f32(const float* A, const float* B, float* C, int64_t M, in
     if (mode < 0 || mode >= LOF_NUM_ROUNDING_MODES) return fail(LOF_ERR_INVALID_ARG, "unknown rounding mode");
     if (mode_uses_rng(mode)) return fail(LOF_ERR_UNSUPPORTED, "chunked GEMM: stochastic accumulator rounding not implemented");
     RoundPlan plan;
+    FastPlan fast;
     std::memset(&plan, 0, sizeof plan);
+    std::memset(&fast, 0, sizeof fast);
     if (acc_fmt) {
         const int st = make_plan(acc_fmt, LOF_F32, mode, 0, &plan);
         if (st != LOF_OK) return st;
+        if (g_opt.round_fast.load()) fast = make_fast_plan(plan, mode);
     } else if (accum_mant_bits < 0 || accum_mant_bits > 23) {
         return fail(LOF_ERR_INVALID_ARG, "accum_mant_bits must be in [0, 23]");
     }
     if (num_sms() <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
     int launches = 0;
     std::string err;
-    cudaError_t e = launch_gemm_tc(A, B, C, M, N, K, mode, accum_mant_bits, acc_fmt ? &plan : nullptr, k_chunk, alpha,
-                                   operand_dtype, static_cast<cudaStream_t>(stream), &launches, &err);
+    cudaError_t e = launch_gemm_tc(A, B, C, M, N, K, mode, accum_mant_bits, acc_fmt, acc_fmt ? &plan : nullptr,
+                                   acc_fmt ? &fast : nullptr, k_chunk, alpha, operand_dtype, flags, dev_status,
+                                   static_cast<cudaStream_t>(stream), &launches, &err);
     g_launches.fetch_add((uint64_t)launches);
     if (!err.empty()) return fail(LOF_ERR_UNSUPPORTED, err);
     if (e != cudaSuccess) return cuda_fail(e, "lof_gemm_chunked launch");

@@ -11,6 +11,7 @@
 // The kernel is ALU-bound (~14 integer/FMA instructions per MAC); operands are staged in
 // shared memory in 64x16 / 16x64 tiles, each thread owns a 4x4 block of a 64x64 C tile.
 #include "lof_core.cuh"
+#include "lof_gemm_common.cuh"
 
 namespace lof {
 
@@ -18,27 +19,6 @@ namespace {
 
 constexpr int TM = 64, TN = 64, TK = 16;
 constexpr int kGemmThreads = 256;
-
-// round-to-odd fused multiply-add, bit-identical to the host routine
-// lof_round_to_odd_fma (blis_lof_gemm.hpp:63-99): RN result when it is exact or
-// non-finite, otherwise the neighbour (of the exact value) with an odd mantissa LSB.
-__device__ __forceinline__ float rto_fma(float a, float b, float c)
-{
-    const float rd = __fmaf_rd(a, b, c);
-    const float ru = __fmaf_ru(a, b, c);
-    const uint32_t urd = __float_as_uint(rd), uru = __float_as_uint(ru);
-    // any directed result with an all-ones exponent: overflow / inf / NaN operands -> take RN
-    if (((urd & 0x7F800000u) == 0x7F800000u) || ((uru & 0x7F800000u) == 0x7F800000u)) {
-        const float rn = __fmaf_rn(a, b, c);
-        if ((__float_as_uint(rn) & 0x7F800000u) == 0x7F800000u) return rn;   // !isfinite(rn)
-        // RN stayed finite (exact value between FLT_MAX and the overflow threshold): inexact,
-        // the toward-zero neighbour is +-FLT_MAX whose LSB is already odd.
-        return rn;
-    }
-    if (rd == ru) return ru;                         // exact; an exact zero (rd = -0, ru = +0) takes RN's sign = ru
-    const float rz = (rd >= 0.0f) ? rd : ru;         // sign(rd) == sign(exact) when inexact
-    return __uint_as_float(__float_as_uint(rz) | 1u);
-}
 
 template <int MODE>
 __device__ __forceinline__ float accum_round(float t, int r, int len, uint32_t w)

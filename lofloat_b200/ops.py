@@ -260,15 +260,21 @@ def set_gemm_panel(kc: int) -> None:
     _gemm_kc = int(kc)
 
 
+_OPERAND_DTYPES = {"e4m3": _lib.LOF_E4M3, "e5m2": _lib.LOF_E5M2, "bf16": _lib.LOF_BF16}
+
+
 def lof_gemm(A: torch.Tensor, B: torch.Tensor, accum_mant_bits: int, round_mode=RoundingMode.RoundToNearestEven,
              stochastic_rounding_bits: int = 0, scale_a: float = 1.0, scale_b: float = 1.0, *, kc=None,
-             k_chunk=None, accum_format: FloatFormatDescriptor | None = None, rng=None) -> torch.Tensor:
+             k_chunk=None, accum_format: FloatFormatDescriptor | None = None, operand_dtype: str = "e4m3",
+             partial_round: bool = False, allow_packed: bool = True, check: bool = True, rng=None) -> torch.Tensor:
     """Low-precision-accumulation GEMM, float32 row-major (Lof_kernel.cu:96-154, LoPy_bind.cpp:361-372).
     The output is divided by scale_a*scale_b (a zero product counts as 1, cutlass_gemms.cuh:1784-1786).
 
-    Extensions (keyword-only): `kc` panel length of the exact mode; `k_chunk` selects the
-    tensor-core chunked mode (accumulator re-rounded once per k_chunk, optionally into the
-    full `accum_format` incl. its exponent range).
+    Extensions (keyword-only): `kc` panel length of the exact per-FMA mode.  `k_chunk` selects the
+    tensor-core chunked mode (lof_gemm_chunked_f32): the accumulator is re-rounded once per k_chunk,
+    mantissa-only (accum_mant_bits) or into the full `accum_format` incl. its exponent range; A and B must
+    be exactly representable in `operand_dtype` ("e4m3", "e5m2" or "bf16") -- with check=True (default) the
+    call synchronises like the reference (Lof_kernel.cu:149) and raises if they are not.
     """
     if A.dim() != 2 or B.dim() != 2:
         raise RuntimeError("LoF_gemm: A and B must be 2-D")
@@ -287,16 +293,29 @@ def lof_gemm(A: torch.Tensor, B: torch.Tensor, accum_mant_bits: int, round_mode=
     M, K = A_c.shape
     N = B_c.shape[1]
     out = torch.zeros((M, N), dtype=torch.float32, device=A.device)
+    status = None
     with torch.cuda.device(A.device):
         if k_chunk is not None:
             fmt = accum_format._c() if accum_format is not None else None
+            flags = (_lib.LOF_GEMM_PARTIAL_ROUND if partial_round else 0) | (0 if allow_packed else _lib.LOF_GEMM_NO_PACKED)
+            status = torch.zeros(1, dtype=torch.int32, device=A.device)
             st = L.lof_gemm_chunked_f32(A_c.data_ptr(), B_c.data_ptr(), out.data_ptr(), M, N, K, int(accum_mant_bits),
                                         C.byref(fmt) if fmt is not None else None, C.byref(ps), int(k_chunk), alpha,
-                                        _lib.LOF_BF16, _stream_ptr(A_c))
+                                        _OPERAND_DTYPES[operand_dtype], flags, status.data_ptr(), _stream_ptr(A_c))
         else:
             r = _next_rng(mode in _STOCHASTIC, rng)
             st = L.lof_gemm_f32(A_c.data_ptr(), B_c.data_ptr(), out.data_ptr(), M, N, K, int(accum_mant_bits),
                                 C.byref(ps), int(_gemm_kc if kc is None else kc), alpha, 0.0, C.byref(r),
                                 _stream_ptr(A_c))
     _lib.check(st, "LoF_gemm")
+    if status is not None and check:
+        bits = int(status.item())
+        if bits & (_lib.LOF_GEMM_STATUS_A_INEXACT | _lib.LOF_GEMM_STATUS_B_INEXACT):
+            which = [n for b, n in ((1, "A"), (2, "B")) if bits & b]
+            raise LoFloatError(_lib.LOF_ERR_INVALID_ARG,
+                               f"LoF_gemm (chunked): {' and '.join(which)} not exactly representable in {operand_dtype}")
+        lof_gemm.last_status = bits
     return out
+
+
+lof_gemm.last_status = 0

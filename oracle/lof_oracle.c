@@ -469,13 +469,14 @@ void lofo_gemm_f32(const float* A, const float* B, float* C, int64_t M, int64_t 
 }
 
 /* Oracle of OUR tensor-core (tcgen05) chunked mode -- not a reference function.
- * Each k-chunk's partial dot product is taken as the correctly rounded fp32 value of the
- * exact sum (the tensor core's internal alignment may differ by a few fp32 ulps; the GPU
- * test states that tolerance), then acc = round_to_format(acc + partial) with a single
- * rounding (round-to-odd add in double, then the format rounding). */
+ * Each k-chunk's partial dot product P is taken as the correctly rounded fp32 value of the
+ * exact sum (the tensor core's internal alignment may differ by a few fp32 ulps on wide-range
+ * data; the GPU tests state that tolerance and also run exactly-summable data bit for bit), then
+ *     partial_round == 0:  acc = round_to_format(acc + P)            -- single rounding (round-to-odd add, then format rounding)
+ *     partial_round != 0:  acc = round_to_format(acc + round_to_format(P)) */
 void lofo_gemm_chunked_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
                            int accum_mant_bits, const lofo_format* acc_fmt, const lofo_projspec* ps,
-                           int64_t k_chunk, float alpha)
+                           int64_t k_chunk, float alpha, int partial_round)
 {
     const int mode = ps->rounding_mode, len = ps->stoch_length;
     if (k_chunk <= 0 || k_chunk > K) k_chunk = K > 0 ? K : 1;
@@ -489,7 +490,11 @@ void lofo_gemm_chunked_f32(const float* A, const float* B, float* C, int64_t M, 
                 const int64_t k1 = (k0 + k_chunk < K) ? k0 + k_chunk : K;
                 double part = 0.0;
                 for (int64_t l = k0; l < k1; ++l) part += (double)A[i * K + l] * (double)B[l * N + j];
-                const float partf = (float)part;
+                float partf = (float)part;
+                if (partial_round) {
+                    if (acc_fmt) partf = u2f(vround_params_f32(f2u(partf), acc_fmt, &kacc, mode, len, 0u));
+                    else         partf = u2f(vround_mant_f32(f2u(partf), accum_mant_bits, mode, len, 0u));
+                }
                 const float t = lofo_round_to_odd_fma(1.0f, partf, acc);
                 if (acc_fmt) acc = u2f(vround_params_f32(f2u(t), acc_fmt, &kacc, mode, len, 0u));
                 else         acc = u2f(vround_mant_f32(f2u(t), accum_mant_bits, mode, len, 0u));

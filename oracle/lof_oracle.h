@@ -103,12 +103,14 @@ void lofo_gemm_f32(const float* A, const float* B, float* C, int64_t M, int64_t 
                    int accum_mant_bits, const lofo_projspec* ps, int64_t kc,
                    float alpha, float beta, const lofo_rng* rng);
 
-/* chunked tensor-core semantics oracle (our tcgen05 mode, NOT a reference function):
- *   per k-chunk: partial = exact fp32-rounded dot over the chunk (computed in double, RN to fp32)
- *   acc = round(acc + partial) into accum format (mantissa-only if acc_fmt == NULL). */
+/* chunked tensor-core semantics oracle (our tcgen05 mode, NOT a reference function; "parity unpinned" --
+ * there is no runnable reference for chunked accumulation):
+ *   per k-chunk: P = exact dot over the chunk, rounded once to fp32 (computed in double)
+ *   acc = round(acc + P)  or, with partial_round, acc = round(acc + round(P)); round() into the
+ *   accumulator format (mantissa-only if acc_fmt == NULL). */
 void lofo_gemm_chunked_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
                            int accum_mant_bits, const lofo_format* acc_fmt, const lofo_projspec* ps,
-                           int64_t k_chunk, float alpha);
+                           int64_t k_chunk, float alpha, int partial_round);
 
 int lofo_num_threads(void);
 

@@ -116,7 +116,7 @@ def oracle():
         lib.lofo_round_to_odd_fma.argtypes = [C.c_float] * 3
         lib.lofo_round_to_odd_fma.restype = C.c_float
         lib.lofo_gemm_f32.argtypes = [vp, vp, vp, i64, i64, i64, i32, PP, i64, C.c_float, C.c_float, PR]
-        lib.lofo_gemm_chunked_f32.argtypes = [vp, vp, vp, i64, i64, i64, i32, PF, PP, i64, C.c_float]
+        lib.lofo_gemm_chunked_f32.argtypes = [vp, vp, vp, i64, i64, i64, i32, PF, PP, i64, C.c_float, i32]
         lib.lofo_num_threads.restype = i32
         _oracle = lib
     return _oracle
@@ -214,7 +214,8 @@ def o_gemm(A: np.ndarray, B: np.ndarray, accum_mant_bits: int, mode=RNE, stoch_l
     return out
 
 
-def o_gemm_chunked(A, B, accum_mant_bits, k_chunk, mode=RNE, acc_fmt: Format | None = None, alpha=1.0):
+def o_gemm_chunked(A, B, accum_mant_bits, k_chunk, mode=RNE, acc_fmt: Format | None = None, alpha=1.0,
+                   partial_round=False):
     A = np.ascontiguousarray(A, dtype=np.float32)
     B = np.ascontiguousarray(B, dtype=np.float32)
     M, K = A.shape
@@ -222,7 +223,8 @@ def o_gemm_chunked(A, B, accum_mant_bits, k_chunk, mode=RNE, acc_fmt: Format | N
     out = np.zeros((M, N), np.float32)
     ps = ProjSpec(mode, 0, 0)
     oracle().lofo_gemm_chunked_f32(_ptr(A), _ptr(B), _ptr(out), M, N, K, accum_mant_bits,
-                                   C.byref(acc_fmt) if acc_fmt is not None else None, C.byref(ps), k_chunk, alpha)
+                                   C.byref(acc_fmt) if acc_fmt is not None else None, C.byref(ps), k_chunk, alpha,
+                                   1 if partial_round else 0)
     return out
 
 
