@@ -275,9 +275,10 @@ def side_measurements(torch, lib, _lib, dev, x, y, stream):
         e8 = _lib.CFormat(8, 0, 127, 0, 0, 1, 0)
         ps = _lib.CProjSpec(0, 0, 0)
         n = 16384 * 16384
-        for variant in (0, 1):
+        for variant in (0, 1, 2):                                   # 0 fast kernel (default), 1 TMA-staged, 2 first-generation shuffle
             _lib.set_option("mx.variant", variant)
-            for fname, (bw, m, bias, ov, sg) in (("mxfp8_e4m3", (8, 3, 7, 1, 0)), ("mxfp4_e2m1", (4, 1, 1, 1, 0))):
+            for fname, (bw, m, bias, ov, sg) in (("mxfp8_e4m3", (8, 3, 7, 1, 0)), ("mxfp6_e3m2", (6, 2, 3, 1, 0)),
+                                                 ("mxfp4_e2m1", (4, 1, 1, 1, 0))):
                 fmt = _lib.CFormat(bw, m, bias, ov, 0, sg, 0)
                 call = lambda: lib.lof_mx_round_f32(x.data_ptr(), y.data_ptr(), n, 32, C.byref(e8), C.byref(fmt),
                                                     C.byref(ps), C.byref(ps), None, 0, stream)
@@ -313,6 +314,36 @@ def side_measurements(torch, lib, _lib, dev, x, y, stream):
                                                         "note": "per-FMA rounding, SIMT (bit-exact vs BLIS reference)"}
     except Exception as exc:
         out["lof_gemm_error"] = str(exc)
+    try:
+        # C4: tcgen05 chunked GEMM, 8192^3, E4M3 operands (U(-1,1) rounded to E4M3), accumulator re-rounded every k = 32
+        import lofloat_b200 as lof
+        n = 8192
+        g = torch.Generator(device=dev).manual_seed(42)
+        e4m3 = lof.create_p3109_params(8, 4, bias=7)
+        A = lof.virtual_round(torch.rand(n, n, device=dev, generator=g) * 2 - 1, e4m3)
+        B = lof.virtual_round(torch.rand(n, n, device=dev, generator=g) * 2 - 1, e4m3)
+        e5m10 = lof.FloatFormatDescriptor(16, 10, 15, lof.InfBehavior.Saturating, lof.NaNBehavior._3109, lof.Signedness.Signed,
+                                          lof.create_half_params().is_inf_checker, lof.create_half_params().is_nan_checker)
+        cases = (("k32_E5M10_RNE_singleround_hw_fp16_accumulator", dict(k_chunk=32, accum_format=e5m10)),
+                 ("k32_E5M10_RNE_partialround_packed", dict(k_chunk=32, accum_format=e5m10, partial_round=True)),
+                 ("k32_mant10_RNE_singleround_generic", dict(k_chunk=32, allow_hw_accum=False)),
+                 ("k128_mant10_RNE_singleround_generic", dict(k_chunk=128)),
+                 ("k512_mant10_RNE_singleround_generic", dict(k_chunk=512)))
+        for label, kw in cases:
+            lof.lof_gemm(A, B, 10, check=False, **kw)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                lof.lof_gemm(A, B, 10, check=False, **kw)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / 3
+            out[f"lof_gemm_tcgen05_8192^3_e4m3_{label}"] = {
+                "ms": ms, "TFLOPs": 2.0 * n ** 3 / (ms * 1e-3) / 1e12,
+                "note": "includes the fp32 -> e4m3 operand conversion kernels"}
+        del A, B
+    except Exception as exc:
+        out["lof_gemm_tc_error"] = str(exc)
     return out
 
 

@@ -90,10 +90,15 @@ typedef struct lof_projspec_t {
     int32_t stoch_length;       /* random bits for StochasticRoundingA..D             */
 } lof_projspec_t;
 
-/* Counter-based RNG state for the stochastic modes: Philox4x32-10 keyed by `seed`; the
- * 32-bit word of element i is word (i & 3) of block (i >> 2) at counter offset `offset`.
- * Results depend only on (seed, offset, global element index) -- never on launch geometry
- * or sharding -- unlike the reference's device hash (lo_float.h:83-98).  NULL = {0, 0}. */
+/* Counter-based RNG state for the stochastic modes: Philox4x32-10 keyed by `seed`; dense 32-bit word q of the
+ * stream is word (q & 3) of block (q >> 2) at counter offset `offset`.  A rounding event (global element index i)
+ * consumes only the random bits its mode needs (SR-A/B/C: stoch_length, SR-D: stoch_length + 1, Probabilistic: 1,
+ * True_SR: 32), packed so that one Philox block serves up to 16 events:
+ *     > 16 bits: dense word i;   9..16 bits: half (i & 1) of dense word i >> 1;
+ *     <= 8 bits: byte (i & 3) of dense word 4 * (((v >> 10) << 8) | (v & 255)) + ((v >> 8) & 3),  v = i >> 2.
+ * Results depend only on (seed, offset, global element index) -- never on launch geometry or sharding -- unlike
+ * the reference's device hash (lo_float.h:83-98).  The GEMM and the MX block scale draw one dense word per event.
+ * NULL = {0, 0}. */
 typedef struct lof_rng_t {
     uint64_t seed;
     uint64_t offset;
@@ -171,10 +176,11 @@ LOF_API int lof_gemm_f32(const float* A, const float* B, float* C, int64_t M, in
  * may be NULL) and C is meaningless.  k_chunk must be a multiple of 32 (8-bit operands) / 16 (bf16);
  * k_chunk <= 0 = one chunk over all K.  K * sizeof(operand) must be a multiple of 16.  Asynchronous on stream. */
 #define LOF_GEMM_PARTIAL_ROUND       1u   /* flags */
-#define LOF_GEMM_NO_PACKED           2u   /* never use the packed half2/bfloat162 rounding epilogue */
+#define LOF_GEMM_NO_PACKED           2u   /* never use the hardware-format shortcuts (packed half2/bfloat162 fold, fp16 TMEM accumulator) */
+#define LOF_GEMM_NO_HW_ACCUM         4u   /* never let the tensor core keep the accumulator in fp16 (k_chunk == one MMA, E5M10, RNE) */
 #define LOF_GEMM_STATUS_A_INEXACT    1    /* *dev_status bits */
 #define LOF_GEMM_STATUS_B_INEXACT    2
-#define LOF_GEMM_STATUS_PACKED_RANGE 4    /* informational: packed epilogue left the fp16 range, C was recomputed generically */
+#define LOF_GEMM_STATUS_PACKED_RANGE 4    /* informational: a hardware-format shortcut left the fp16 range, C was recomputed generically */
 LOF_API int lof_gemm_chunked_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
                          int accum_mant_bits, const lof_format_t* acc_fmt, const lof_projspec_t* ps,
                          int64_t k_chunk, float alpha, int operand_dtype, uint32_t flags, int32_t* dev_status,
@@ -206,9 +212,14 @@ LOF_API const char* lof_last_error_string(void);          /* thread-local detail
 LOF_API uint64_t    lof_kernel_launch_count(void);        /* kernels launched by this library so far  */
 LOF_API float       lof_mx_priv_max_normal(const lof_format_t* elem_fmt);  /* (2 - 2^-m) * 2^max_exp  */
 
+/* Device self-test of the MX fast kernel's division shortcut: counts the non-negative finite fp32 values a for
+ * which its 3-FMA quotient a / priv_max_normal(elem_fmt) differs from IEEE division (must be 0).  Synchronous. */
+LOF_API int lof_selftest_mx_division(const lof_format_t* elem_fmt, uint64_t* mismatches, void* stream);
+
 /* Tuning knobs used by bench.py / the profiling scripts to compare kernel variants on the
  * same inputs.  key: "round.unroll", "round.ctas_per_sm", "round.fast" (0 = always the
- * exact integer kernel), "mx.variant" (0 = shuffle, 1 = TMA-staged), "mx.ctas_per_sm",
+ * exact integer kernel, 1 = branch-free fast path, 2 = + magic-add path [default]), "mx.variant" (0 = fast kernel
+ * + generic remainder [default], 1 = TMA-staged, 2 = first-generation shuffle kernel), "mx.ctas_per_sm",
  * "host.chunk_bytes".  Returns LOF_ERR_INVALID_ARG for
  * an unknown key. */
 LOF_API int lof_set_option(const char* key, int64_t value);

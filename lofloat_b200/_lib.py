@@ -17,7 +17,7 @@ LOF_OK, LOF_ERR_INVALID_ARG, LOF_ERR_UNSUPPORTED, LOF_ERR_CUDA, LOF_ERR_NO_DEVIC
 # dtypes
 LOF_F32, LOF_F16, LOF_BF16, LOF_F64, LOF_E4M3, LOF_E5M2 = range(6)
 # lof_gemm_chunked_f32 flags / status bits
-LOF_GEMM_PARTIAL_ROUND, LOF_GEMM_NO_PACKED = 1, 2
+LOF_GEMM_PARTIAL_ROUND, LOF_GEMM_NO_PACKED, LOF_GEMM_NO_HW_ACCUM = 1, 2, 4
 LOF_GEMM_STATUS_A_INEXACT, LOF_GEMM_STATUS_B_INEXACT, LOF_GEMM_STATUS_PACKED_RANGE = 1, 2, 4
 
 # every symbol include/lofloat_b200.h declares (tests check the library exports all of them)
@@ -25,7 +25,7 @@ ABI_SYMBOLS = (
     "lof_round_params", "lof_round_mantissa", "lof_mx_round_f32", "lof_gemm_f32", "lof_gemm_chunked_f32",
     "lof_round_params_host", "lof_round_mantissa_host", "lof_mx_round_f32_host",
     "lof_abi_version", "lof_status_string", "lof_last_error_string", "lof_kernel_launch_count",
-    "lof_mx_priv_max_normal", "lof_set_option", "lof_get_option",
+    "lof_mx_priv_max_normal", "lof_set_option", "lof_get_option", "lof_selftest_mx_division",
 )
 
 
@@ -77,6 +77,8 @@ def _declare(lib):
     lib.lof_kernel_launch_count.restype = u64
     lib.lof_mx_priv_max_normal.argtypes = [PF]
     lib.lof_mx_priv_max_normal.restype = f32
+    lib.lof_selftest_mx_division.argtypes = [PF, C.POINTER(u64), vp]
+    lib.lof_selftest_mx_division.restype = i32
     lib.lof_set_option.argtypes = [C.c_char_p, i64]
     lib.lof_set_option.restype = i32
     lib.lof_get_option.argtypes = [C.c_char_p, C.POINTER(i64)]

@@ -23,6 +23,10 @@ cudaError_t launch_gemm_exact(int mode, const float* A, const float* B, float* C
 cudaError_t launch_mx_tma(int mode, const float* in, float* out, int64_t n, const MxArgs& a, const RngArgs& rng,
                           const RngArgs& rng_scale, uint64_t first_index, const MxLaunchCfg& cfg, cudaStream_t stream,
                           int* launches, bool* handled);
+cudaError_t launch_mx_fast(int mode, int scale_mode, const float* in, float* out, int64_t n, const MxArgs& g,
+                           const MagicPlan& elem_magic, const MagicPlan& scale_magic, const FastPlan& scale_fast, int scale_mantissa_bits,
+                           const MxLaunchCfg& cfg, cudaStream_t stream, int64_t* main_elems, int* launches);
+cudaError_t run_mx_div_selftest(float pmn, unsigned long long* host_mismatches, cudaStream_t stream);
 cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int mode,
                            int accum_mant_bits, const lof_format_t* acc_fmt, const RoundPlan* acc_plan, const FastPlan* acc_fast,
                            int64_t k_chunk, float alpha, int operand_dtype, uint32_t flags, int* dev_status,
@@ -42,7 +46,7 @@ struct Options {
     std::atomic<int64_t> mx_variant{0};
     std::atomic<int64_t> mx_ctas_per_sm{8};
     std::atomic<int64_t> host_chunk_bytes{32ll << 20};
-    std::atomic<int64_t> round_fast{1};          // 1: use the fp32 fast path when the format is eligible
+    std::atomic<int64_t> round_fast{2};          // 0: exact kernels; 1: branch-free fast path; 2: + magic-add path (default)
 } g_opt;
 
 int fail(int status, const std::string& msg)
@@ -156,9 +160,45 @@ FastPlan make_fast_plan(const RoundPlan& p, int mode)
     return f;
 }
 
-RngArgs make_rng(const lof_rng_t* rng, uint32_t stream_const)
+// Eligibility + constants of the magic-add path (lof_fast_f32.cuh).  plan from make_plan(fmt, LOF_F32, ...).
+MagicPlan make_magic_plan(const RoundPlan& p, int mode)
+{
+    MagicPlan m;
+    std::memset(&m, 0, sizeof m);
+    const bool sr = mode == LOF_StochasticRoundingA || mode == LOF_StochasticRoundingD;
+    const bool mode_ok = mode == LOF_RoundToNearestEven || mode == LOF_RoundTowardsZero || mode == LOF_RoundAwayFromZero ||
+                         mode == LOF_RoundUp || mode == LOF_RoundDown || mode == LOF_RoundToOdd || sr;
+    // stochastic: 1 <= len <= shiftN (reference precondition), the offset's exponent c - (23 + len) must stay normal
+    if (sr && (p.stoch_len < 1 || p.stoch_len > p.shiftN || p.stoch_len > 22 || p.min_exp_b + p.shiftN < 25 + p.stoch_len)) return m;
+    uint32_t mv;
+    std::memcpy(&mv, &p.min_val, 4);
+    // m = 0 (E8M0-like): the reference's RNE / round-to-odd act on the raw bits, whose "LSB" is then the exponent
+    // field's LSB, not a significand bit -- the value-based magic add would break ties differently
+    if (p.shiftN == 23 && (mode == LOF_RoundToNearestEven || mode == LOF_RoundToOdd)) return m;
+    if (!mode_ok || p.shiftN < 1 || p.shiftN > 23 || p.min_exp_b < 1 || p.min_exp_b > 254 ||
+        p.min_exp_b + p.shiftN > 254 || mv == 0 || p.max_exp_b < p.min_exp_b)
+        return m;
+    m.c_add = (uint32_t)p.shiftN << 23;
+    m.c_floor = (uint32_t)(p.min_exp_b + p.shiftN) << 23;
+    const int64_t thr = (int64_t)p.max_exp_b + 1;
+    m.ovf_thresh = thr > 255 ? 0xFFFFFFFFu : (uint32_t)(thr << 23);
+    // every x whose exponent field e has e + shiftN >= 255 must either be an overflow (then the garbage constant
+    // still yields a magnitude >= ovf_thresh, see lof_fast_f32.cuh) or go to the exact routine
+    m.limit = (p.max_exp_b + p.shiftN <= 254) ? 0xFFFFFFFFu : (uint32_t)(255 - p.shiftN) << 23;
+    m.check_denorm_in = mv < 0x00800000u;
+    m.sr_len = sr ? (uint32_t)p.stoch_len : 0u;
+    m.sr_mask = sr ? ((1u << p.stoch_len) - 1u) : 0u;
+    m.sr_sub = sr ? (uint32_t)(23 + p.stoch_len) << 23 : 0u;
+    m.min_val = p.min_val;
+    m.valid = 1;
+    return m;
+}
+
+RngArgs make_rng(const lof_rng_t* rng, uint32_t stream_const, int mode = LOF_True_StochasticRounding, int len = 0)
 {
     RngArgs r;
+    r.cls = rand_class(mode, len);            // default: one dense 32-bit word per event (GEMM, MX scale)
+    r.pad_ = 0;
     const uint64_t seed = rng ? rng->seed : 0, off = rng ? rng->offset : 0;
     r.key0 = (uint32_t)seed; r.key1 = (uint32_t)(seed >> 32);
     r.off0 = (uint32_t)off;  r.off1 = (uint32_t)(off >> 32) ^ stream_const;
@@ -188,15 +228,26 @@ int round_common(bool params, const void* in, void* out, int64_t n, int dtype, c
     std::memset(&plan, 0, sizeof plan);
     FastPlan fast;
     std::memset(&fast, 0, sizeof fast);
+    MagicPlan magic;
+    std::memset(&magic, 0, sizeof magic);
     int kind = params ? kKindParams : kKindMantissa;
     int r = 0;
     if (params) {
         const int st = make_plan(fmt, dtype, mode, ps->stoch_length, &plan);
         if (st != LOF_OK) return st;
-        if (dtype == LOF_F32 && g_opt.round_fast.load()) {
+        const int64_t fast_opt = g_opt.round_fast.load();        // 0: exact kernel, 1: first-generation fast path, 2: + magic add
+        if (dtype == LOF_F32 && fast_opt) {
             fast = make_fast_plan(plan, mode);
             if (fast.valid) kind = fast.check_denorm_in ? (plan.saturating ? kKindFastSatChk : kKindFastExtChk)
                                                         : (plan.saturating ? kKindFastSat : kKindFastExt);
+            if (fast_opt >= 2) {
+                magic = make_magic_plan(plan, mode);
+                if (magic.valid) {
+                    const bool chk = magic.check_denorm_in || magic.limit != 0xFFFFFFFFu;
+                    kind = chk ? (plan.saturating ? kKindMagicSatChk : kKindMagicExtChk)
+                               : (plan.saturating ? kKindMagicSat : kKindMagicExt);
+                }
+            }
         }
     } else {
         r = g.mant - mantissa_bits;                                           // -kDigitShift, lo_float.h:2722
@@ -210,14 +261,14 @@ int round_common(bool params, const void* in, void* out, int64_t n, int dtype, c
     if (!in || !out) return fail(LOF_ERR_INVALID_ARG, "null tensor pointer");
     const RoundLaunchCfg cfg = round_cfg();
     if (cfg.num_sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
-    const RngArgs ra = make_rng(rng, kStreamElem);
+    const RngArgs ra = make_rng(rng, kStreamElem, mode, ps->stoch_length);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     cudaError_t e;
     switch (dtype) {
-    case LOF_F32:  e = launch_round_f32(kind, mode, in, out, n, plan, fast, r, ps->stoch_length, scale, ra, first_index, cfg, s); break;
-    case LOF_F16:  e = launch_round_f16(kind, mode, in, out, n, plan, fast, r, ps->stoch_length, scale, ra, first_index, cfg, s); break;
-    case LOF_BF16: e = launch_round_bf16(kind, mode, in, out, n, plan, fast, r, ps->stoch_length, scale, ra, first_index, cfg, s); break;
-    default:       e = launch_round_f64(kind, mode, in, out, n, plan, fast, r, ps->stoch_length, scale, ra, first_index, cfg, s); break;
+    case LOF_F32:  e = launch_round_f32(kind, mode, in, out, n, plan, fast, magic, r, ps->stoch_length, scale, ra, first_index, cfg, s); break;
+    case LOF_F16:  e = launch_round_f16(kind, mode, in, out, n, plan, fast, magic, r, ps->stoch_length, scale, ra, first_index, cfg, s); break;
+    case LOF_BF16: e = launch_round_bf16(kind, mode, in, out, n, plan, fast, magic, r, ps->stoch_length, scale, ra, first_index, cfg, s); break;
+    default:       e = launch_round_f64(kind, mode, in, out, n, plan, fast, magic, r, ps->stoch_length, scale, ra, first_index, cfg, s); break;
     }
     if (e != cudaSuccess) return cuda_fail(e, "virtual_round launch");
     g_launches.fetch_add(1);
@@ -349,18 +400,32 @@ int mx_common(const float* in, float* out, int64_t n, int block_size, const lof_
     cfg.ctas_per_sm = (int)g_opt.mx_ctas_per_sm.load();
     cfg.num_sms = num_sms();
     if (cfg.num_sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
-    const RngArgs re = make_rng(rng, kStreamElem), rs = make_rng(rng, kStreamScale);
+    const RngArgs re = make_rng(rng, kStreamElem, ps_elem->rounding_mode, ps_elem->stoch_length), rs = make_rng(rng, kStreamScale);
     int launches = 0;
     cudaError_t e;
     bool handled = false;
-    if (cfg.variant == 1) {
-        e = launch_mx_tma(ps_elem->rounding_mode, in, out, n, a, re, rs, first_index, cfg, static_cast<cudaStream_t>(stream),
-                          &launches, &handled);
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    // variant 0 (default): second-generation fast kernel for the eligible bulk, generic kernels for the rest
+    // variant 1: TMA-staged kernel; variant 2: first-generation shuffle kernel only (comparison / fallback)
+    int64_t done = 0;
+    if (cfg.variant == 0 && g_opt.round_fast.load() >= 2 && !mode_uses_rng(ps_elem->rounding_mode) &&
+        !mode_uses_rng(ps_scale->rounding_mode)) {
+        const MagicPlan em = make_magic_plan(a.elem, ps_elem->rounding_mode);
+        const MagicPlan sm = make_magic_plan(a.scale, ps_scale->rounding_mode);
+        const FastPlan sf = make_fast_plan(a.scale, ps_scale->rounding_mode);
+        e = launch_mx_fast(ps_elem->rounding_mode, ps_scale->rounding_mode, in, out, n, a, em, sm, sf, scale_fmt->mantissa_bits,
+                           cfg, cs, &done, &launches);
+        if (e != cudaSuccess) return cuda_fail(e, "virtual_mx_round (fast) launch");
+        if (done == n) handled = true;
+    }
+    if (!handled && cfg.variant == 1 && done == 0) {
+        e = launch_mx_tma(ps_elem->rounding_mode, in, out, n, a, re, rs, first_index, cfg, cs, &launches, &handled);
         if (e != cudaSuccess) return cuda_fail(e, "virtual_mx_round (tma) launch");
     }
     if (!handled) {
-        e = launch_mx_shuffle(ps_elem->rounding_mode, in, out, n, a, re, rs, first_index, cfg,
-                              static_cast<cudaStream_t>(stream), &launches);
+        // `done` is a multiple of 256 (whole blocks for every supported block size)
+        e = launch_mx_shuffle(ps_elem->rounding_mode, in + done, out + done, n - done, a, re, rs, first_index + (uint64_t)done, cfg,
+                              cs, &launches);
         if (e != cudaSuccess) return cuda_fail(e, "virtual_mx_round launch");
     }
     g_launches.fetch_add((uint64_t)launches);
@@ -398,15 +463,27 @@ float lof_mx_priv_max_normal(const lof_format_t* p)
     return std::ldexp(1.0f, me) * (2.0f - std::ldexp(1.0f, -p->mantissa_bits));     // LoPy_bind.cpp:199-202
 }
 
+int lof_selftest_mx_division(const lof_format_t* elem_fmt, uint64_t* mismatches, void* stream)
+{
+    if (!elem_fmt || !mismatches) return fail(LOF_ERR_INVALID_ARG, "null argument");
+    if (num_sms() <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    unsigned long long bad = 0;
+    cudaError_t e = run_mx_div_selftest(lof_mx_priv_max_normal(elem_fmt), &bad, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "mx division self-test");
+    *mismatches = bad;
+    g_launches.fetch_add(1);
+    return LOF_OK;
+}
+
 int lof_set_option(const char* key, int64_t value)
 {
     if (!key) return fail(LOF_ERR_INVALID_ARG, "option key is NULL");
     const std::string k(key);
     if (k == "round.unroll") { if (value != 1 && value != 2 && value != 4 && value != 8) return fail(LOF_ERR_INVALID_ARG, "round.unroll must be 1/2/4/8"); g_opt.round_unroll = value; }
     else if (k == "round.ctas_per_sm") { if (value < 1 || value > 64) return fail(LOF_ERR_INVALID_ARG, "round.ctas_per_sm out of range"); g_opt.round_ctas_per_sm = value; }
-    else if (k == "mx.variant") { if (value < 0 || value > 1) return fail(LOF_ERR_INVALID_ARG, "mx.variant must be 0 or 1"); g_opt.mx_variant = value; }
+    else if (k == "mx.variant") { if (value < 0 || value > 2) return fail(LOF_ERR_INVALID_ARG, "mx.variant must be 0, 1 or 2"); g_opt.mx_variant = value; }
     else if (k == "mx.ctas_per_sm") { if (value < 1 || value > 64) return fail(LOF_ERR_INVALID_ARG, "mx.ctas_per_sm out of range"); g_opt.mx_ctas_per_sm = value; }
-    else if (k == "round.fast") { g_opt.round_fast = value ? 1 : 0; }
+    else if (k == "round.fast") { if (value < 0 || value > 2) return fail(LOF_ERR_INVALID_ARG, "round.fast must be 0, 1 or 2"); g_opt.round_fast = value; }
     else if (k == "host.chunk_bytes") { if (value < (1 << 16)) return fail(LOF_ERR_INVALID_ARG, "host.chunk_bytes too small"); g_opt.host_chunk_bytes = value; }
     else return fail(LOF_ERR_INVALID_ARG, "unknown option: " + k);
     return LOF_OK;

@@ -36,7 +36,30 @@ struct RoundPlan {
 struct RngArgs {
     uint32_t key0, key1;    // seed
     uint32_t off0, off1;    // counter offset (already xor-ed with the stream constant)
+    uint32_t cls;           // event class: how many random bits one rounding event consumes (rand_class)
+    uint32_t pad_;
 };
+
+// Random bits per rounding event -> packing class of the event stream (include/lofloat_b200.h, lof_rng_t):
+//   class 0 (<= 8 bits):  element i uses byte (i & 3) of the 32-bit word that belongs to its 4-element group
+//                         v = i >> 2:  word (v >> 8) & 3 of Philox block ((v >> 10) << 8) | (v & 255)
+//                         -- inside every aligned run of 4096 elements, the 4 groups v, v + 256, v + 512, v + 768
+//                         share one Philox block, which is exactly what one thread of the vector kernel processes;
+//   class 1 (<= 16 bits): element i uses half (i & 1) of dense word i >> 1;
+//   class 2 (> 16 bits):  element i uses dense word i.
+// Dense word q = word (q & 3) of Philox block (q >> 2).
+__host__ __device__ inline int rand_bits_needed(int mode, int len)
+{
+    if (mode == LOF_True_StochasticRounding) return 32;
+    if (mode == LOF_ProbabilisticRounding) return 1;
+    if (mode == LOF_StochasticRoundingD) return len + 1;
+    return len;            // SR-A / SR-B / SR-C (deterministic modes never draw)
+}
+__host__ __device__ inline uint32_t rand_class(int mode, int len)
+{
+    const int b = rand_bits_needed(mode, len);
+    return b <= 8 ? 0u : b <= 16 ? 1u : 2u;
+}
 
 constexpr uint32_t kStreamElem  = 0u;
 constexpr uint32_t kStreamScale = 0x5ca1e000u;
@@ -72,6 +95,30 @@ __device__ __forceinline__ uint32_t philox_word(const RngArgs& r, uint64_t index
     const uint4 b = philox_block(r, index >> 2);
     const uint32_t lane = (uint32_t)index & 3u;
     return lane == 0 ? b.x : lane == 1 ? b.y : lane == 2 ? b.z : b.w;
+}
+
+// the four per-element event words of the 4-element group v (elements 4v .. 4v + 3)
+__device__ __forceinline__ uint4 philox_group4(const RngArgs& r, uint64_t v)
+{
+    if (r.cls == 2u) return philox_block(r, v);
+    if (r.cls == 1u) {
+        const uint4 b = philox_block(r, v >> 1);
+        const uint32_t w0 = (v & 1u) ? b.z : b.x, w1 = (v & 1u) ? b.w : b.y;
+        return make_uint4(w0 & 0xFFFFu, w0 >> 16, w1 & 0xFFFFu, w1 >> 16);
+    }
+    const uint4 b = philox_block(r, ((v >> 10) << 8) | (v & 255u));
+    const uint32_t u = (uint32_t)(v >> 8) & 3u;
+    const uint32_t w = u == 0 ? b.x : u == 1 ? b.y : u == 2 ? b.z : b.w;
+    return make_uint4(w & 0xFFu, (w >> 8) & 0xFFu, (w >> 16) & 0xFFu, w >> 24);
+}
+__device__ __forceinline__ uint4 bytes_of(uint32_t w) { return make_uint4(w & 0xFFu, (w >> 8) & 0xFFu, (w >> 16) & 0xFFu, w >> 24); }
+
+// event word of one global element index (scalar / tail paths)
+__device__ __forceinline__ uint32_t philox_event(const RngArgs& r, uint64_t index)
+{
+    const uint4 g = philox_group4(r, index >> 2);
+    const uint32_t e = (uint32_t)index & 3u;
+    return e == 0 ? g.x : e == 1 ? g.y : e == 2 ? g.z : g.w;
 }
 
 template <int MODE>

@@ -140,6 +140,110 @@ __device__ __forceinline__ uint32_t round_fast_f32_rt(uint32_t x, const FastPlan
     return (a > 0x7F800000u) ? 0x7FC00000u : out;
 }
 
+// ---------------------------------------------------------------------------------------
+// "Magic add" formulation (second generation of the fast path).
+//
+// For the modes whose tie / direction rule is one of IEEE's (RNE, toward zero, away, up, down) or a sticky
+// variant of it (round-to-odd), BOTH regimes of lo_float.h:2843-2939 collapse into one floating-point add:
+//
+//     c = 2^(max(e, ToMin_exp) + 23 - m)          e = exponent of x, m = target mantissa bits
+//     r = (|x| (+) c) - c                          (+) = add with the rounding mode of the LoFloat mode
+//
+// |x| + c lies in [c, 2c], where one ulp is exactly the target quantum of x's binade (normal regime) or
+// denorm_min (e < ToMin_exp: the uniform target-subnormal grid, which also reproduces the below-denorm_min
+// switch, :2872-2908); the subtraction is exact; a carry into the next binade is the rounded value itself.
+// c's bit pattern is max((x & 0x7F800000) + (shiftN << 23), c_floor): two integer instructions, no shifts,
+// masks or regime selects -- ~10 instructions per element instead of ~19, most of them on the otherwise idle
+// FMA pipe.  If e + shiftN leaves the fp32 exponent range the pattern is garbage; eligibility (host,
+// make_magic_plan) guarantees such an x is an overflow whose r still compares >= ovf_thresh, or routes it
+// (and fp32-subnormal inputs hit by the hidden-bit quirk) to the exact routine via `limit`.
+// Bit-exactness is established by the exhaustive 2^32 sweeps against the exact integer kernel.
+// ---------------------------------------------------------------------------------------
+struct MagicPlan {
+    uint32_t c_add;            // shiftN << 23
+    uint32_t c_floor;          // (min_exp_b + shiftN) << 23: magic constant of the target-subnormal regime
+    uint32_t ovf_thresh;       // rounded magnitude bits >= this -> overflow (0xFFFFFFFF: never)
+    uint32_t limit;            // |x| bits >= limit need the exact routine (0xFFFFFFFF: none)
+    uint32_t check_denorm_in;  // fp32-subnormal inputs need the exact routine
+    uint32_t valid;
+    // stochastic variants (SR-A, SR-D): the random offset R * quantum * 2^-len is added with truncation
+    uint32_t sr_sub;           // (23 + len) << 23: c - sr_sub is the bit pattern of quantum * 2^-len
+    uint32_t sr_mask;          // (1 << len) - 1
+    uint32_t sr_len;
+    float    min_val;          // denorm_min: stochastic modes flush everything below it (lo_float.h:2902)
+};
+
+template <int MODE>
+struct MagicTraits {
+    static constexpr bool kStochastic = MODE == LOF_StochasticRoundingA || MODE == LOF_StochasticRoundingD;
+    static constexpr bool kOk = FastTraits<MODE>::kFaddSub || kStochastic;
+};
+
+// rounded value with x's sign; *mag_bits = bits of |rounded| (for the overflow test)
+template <int MODE>
+__device__ __forceinline__ uint32_t magic_round_core(uint32_t x, uint32_t c_add, uint32_t c_floor, uint32_t& mag_bits)
+{
+    const uint32_t c = max((x & 0x7F800000u) + c_add, c_floor);
+    const uint32_t sign = x & 0x80000000u;
+    if constexpr (MODE == LOF_RoundUp || MODE == LOF_RoundDown) {
+        // directed modes act on the signed value: add the magic constant with x's sign
+        const float cs = __uint_as_float(c | sign);
+        const float xf = __uint_as_float(x);
+        const float t = (MODE == LOF_RoundUp) ? __fadd_ru(xf, cs) : __fadd_rd(xf, cs);
+        const uint32_t r = __float_as_uint(__fsub_rn(t, cs));
+        mag_bits = r & 0x7FFFFFFFu;
+        return r | sign;                                      // keeps -0 for negative inputs that round to zero
+    } else {
+        const float cf = __uint_as_float(c);
+        const float ax = fabsf(__uint_as_float(x));
+        float t;
+        if constexpr (MODE == LOF_RoundToNearestEven) t = __fadd_rn(ax, cf);
+        else if constexpr (MODE == LOF_RoundTowardsZero) t = __fadd_rz(ax, cf);
+        else if constexpr (MODE == LOF_RoundAwayFromZero) t = __fadd_ru(ax, cf);
+        else {                                                // RoundToOdd: truncate, LSB |= inexact
+            const float tz = __fadd_rz(ax, cf), tu = __fadd_ru(ax, cf);
+            t = __uint_as_float(__float_as_uint(tz) | (tz != tu ? 1u : 0u));
+        }
+        mag_bits = __float_as_uint(__fsub_rn(t, cf));
+        return mag_bits | sign;
+    }
+}
+
+// SR-A / SR-D (lo_float.h:653-694, 820-860): bits + (R << (r - len)), then truncate == truncate(|x| + R * q * 2^-len)
+// onto the grid of quantum q; two truncating adds compose to one truncation because the second grid is coarser and
+// aligned.  R = len random bits (+ the next bit as a coin for SR-D).
+template <int MODE>
+__device__ __forceinline__ uint32_t magic_round_sr(uint32_t x, const MagicPlan& p, uint32_t w, uint32_t& mag_bits)
+{
+    const uint32_t c = max((x & 0x7F800000u) + p.c_add, p.c_floor);
+    uint32_t R = w & p.sr_mask;
+    if constexpr (MODE == LOF_StochasticRoundingD) R += (w >> p.sr_len) & 1u;
+    const float off = __fmul_rn(__uint2float_rn(R), __uint_as_float(c - p.sr_sub));       // exact: R < 2^24, power-of-two scale
+    const float cf = __uint_as_float(c);
+    const float ax = fabsf(__uint_as_float(x));
+    const float t = __fadd_rz(__fadd_rz(ax, off), cf);
+    const uint32_t r = __float_as_uint(__fsub_rn(t, cf));
+    mag_bits = (ax < p.min_val) ? 0u : r;                                                  // below denorm_min: flush
+    return mag_bits | (x & 0x80000000u);
+}
+
+// one element of virtual_round(value, FloatingPointParams, ps); `rare` is OR-ed with "needs the exact routine"
+template <int MODE, bool SAT, bool CHECK>
+__device__ __forceinline__ uint32_t round_magic_f32(uint32_t x, const MagicPlan& p, uint32_t w, bool& rare)
+{
+    uint32_t mag, rs;
+    if constexpr (MagicTraits<MODE>::kStochastic) rs = magic_round_sr<MODE>(x, p, w, mag);
+    else rs = magic_round_core<MODE>(x, p.c_add, p.c_floor, mag);
+    uint32_t out = (mag >= p.ovf_thresh) ? (SAT ? x : 0x7F800000u) : rs;
+    const float xf = __uint_as_float(x);
+    out = (xf != xf) ? 0x7FC00000u : out;                     // NaN -> +qNaN (lo_float.h:2869)
+    if constexpr (CHECK) {
+        const uint32_t a = x & 0x7FFFFFFFu;
+        rare |= ((a - 1u) < 0x007FFFFFu && p.check_denorm_in != 0u) || (a >= p.limit);
+    }
+    return out;
+}
+
 // out-of-line exact routine for the rare lanes of the fast kernels
 template <int MODE>
 __device__ __noinline__ uint32_t exact_params_f32(uint32_t v, const RoundPlan& plan, uint32_t w)

@@ -26,4 +26,16 @@ __device__ __forceinline__ float rto_fma(float a, float b, float c)
     return __uint_as_float(__float_as_uint(rz) | 1u);
 }
 
+// Round-to-odd ADD for the chunked GEMM:  RZ(a + b) with the LSB OR-ed with "inexact".  Branch-free: the
+// toward-zero result plus a comparison of the two directed sums (an exact zero gives rd = -0, ru = +0, which
+// compare equal, and RZ returns +0 like RN).  A finite sum beyond FLT_MAX gives +-FLT_MAX (already odd);
+// infinities and NaNs propagate.  CPU statement: oracle/lof_oracle.c lofo_rto_add.
+__device__ __forceinline__ float rto_add(float a, float b)
+{
+    const float rz = __fadd_rz(a, b);
+    const float rd = __fadd_rd(a, b);
+    const float ru = __fadd_ru(a, b);
+    return __uint_as_float(__float_as_uint(rz) | (rd != ru ? 1u : 0u));
+}
+
 }  // namespace lof

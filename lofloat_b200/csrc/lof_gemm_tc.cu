@@ -47,6 +47,7 @@
 #include <algorithm>
 #include <cstring>
 #include <string>
+#include <type_traits>
 
 #include "lof_core.cuh"
 #include "lof_fast_f32.cuh"
@@ -72,7 +73,8 @@ constexpr int kTcThreads = 384;
 constexpr int kEpiWarps = 8;
 constexpr int kColsPerThread = BN / 2;      // 64
 
-enum : int { kEpiMant = 0, kEpiFmt = 1, kEpiHalf2 = 2, kEpiBf162 = 3 };
+enum : int { kEpiMant = 0, kEpiFmt = 1, kEpiHalf2 = 2, kEpiBf162 = 3,
+             kEpiHw16 = 4 };     // the tensor core itself keeps the accumulator in fp16 (c_format = F16): no per-chunk read-back
 
 struct TcArgs {
     int M, N, K;
@@ -114,7 +116,7 @@ template <int MODE, int EPI, bool PARTIAL>
 __device__ __forceinline__ float fold(float acc, float p, const TcArgs& a)
 {
     if constexpr (PARTIAL) p = round_acc<MODE, EPI>(p, a);
-    return round_acc<MODE, EPI>(rto_fma(1.0f, p, acc), a);     // round-to-odd add: the format rounding is the only rounding
+    return round_acc<MODE, EPI>(rto_add(acc, p), a);           // round-to-odd add: the format rounding is the only rounding
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -223,45 +225,74 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int i = 0; i < kColsPerThread; ++i) acc[i] = 0.0f;
         }
 
-        for (int c = 0; c < n_chunks; ++c) {
-            const int ts = c % kTmemStages;
-            mbar_wait(&tmem_full_bar[ts], (uint32_t)((c / kTmemStages) & 1));
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + t_lane + (uint32_t)(ts * BN + h * kColsPerThread);
-            uint32_t p0[32], p1[32];
-            tmem_ld32(taddr, p0);
-            tmem_ld32(taddr + 32, p1);
+        // The partials are pulled out of TMEM in UNITs of columns through two register buffers: the
+        // tcgen05.ld of unit u+1 is in flight while unit u is folded into the accumulators (tcgen05.wait::ld
+        // waits for every outstanding load of the thread, so the prefetch distance is one unit).  The packed
+        // epilogue has few accumulator registers and takes a whole chunk (64 columns) per unit; the generic one
+        // takes half a chunk.
+        constexpr int UNIT = kPacked ? kColsPerThread : kColsPerThread / 2;
+        constexpr int UPC = kColsPerThread / UNIT;               // units per chunk (1 or 2)
+        uint32_t buf0[UNIT], buf1[UNIT];
+        const int total_units = n_chunks * UPC;
+
+        auto issue = [&](int u, uint32_t* buf) {                 // start loading unit u
+            const int c = u / UPC, part = u % UPC, ts = c % kTmemStages;
+            if (part == 0) {
+                mbar_wait(&tmem_full_bar[ts], (uint32_t)((c / kTmemStages) & 1));
+                tc_fence_after();
+            }
+            const uint32_t taddr = tmem_base + t_lane + (uint32_t)(ts * BN + h * kColsPerThread + part * UNIT);
+#pragma unroll
+            for (int k = 0; k < UNIT / 32; ++k) tmem_ld32(taddr + 32 * k, buf + 32 * k);
+        };
+        auto landed = [&](int u, uint32_t* buf) {                // unit u is in registers; release its TMEM stage when it was the chunk's last
             tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[ts]);        // the tensor core may overwrite this stage now
+#pragma unroll
+            for (int i = 0; i < UNIT; ++i) asm volatile("" : "+r"(buf[i]));     // order every later use after the wait
+            if (u % UPC == UPC - 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[(u / UPC) % kTmemStages]);
+            }
+        };
+        auto fold_unit = [&](auto part_tag, const uint32_t* p) {
+            constexpr int PART = decltype(part_tag)::value;
             if constexpr (EPI == kEpiHalf2) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
+                for (int i = 0; i < UNIT / 2; ++i) {
                     const __half2 a0 = *reinterpret_cast<const __half2*>(&accp[i]);
-                    const __half2 a1 = *reinterpret_cast<const __half2*>(&accp[16 + i]);
-                    const __half2 r0 = __hadd2(a0, __floats2half2_rn(__uint_as_float(p0[2 * i]), __uint_as_float(p0[2 * i + 1])));
-                    const __half2 r1 = __hadd2(a1, __floats2half2_rn(__uint_as_float(p1[2 * i]), __uint_as_float(p1[2 * i + 1])));
+                    const __half2 r0 = __hadd2(a0, __floats2half2_rn(__uint_as_float(p[2 * i]), __uint_as_float(p[2 * i + 1])));
                     accp[i] = *reinterpret_cast<const uint32_t*>(&r0);
-                    accp[16 + i] = *reinterpret_cast<const uint32_t*>(&r1);
                 }
             } else if constexpr (EPI == kEpiBf162) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
+                for (int i = 0; i < UNIT / 2; ++i) {
                     const __nv_bfloat162 a0 = *reinterpret_cast<const __nv_bfloat162*>(&accp[i]);
-                    const __nv_bfloat162 a1 = *reinterpret_cast<const __nv_bfloat162*>(&accp[16 + i]);
-                    const __nv_bfloat162 r0 = __hadd2(a0, __floats2bfloat162_rn(__uint_as_float(p0[2 * i]), __uint_as_float(p0[2 * i + 1])));
-                    const __nv_bfloat162 r1 = __hadd2(a1, __floats2bfloat162_rn(__uint_as_float(p1[2 * i]), __uint_as_float(p1[2 * i + 1])));
+                    const __nv_bfloat162 r0 = __hadd2(a0, __floats2bfloat162_rn(__uint_as_float(p[2 * i]), __uint_as_float(p[2 * i + 1])));
                     accp[i] = *reinterpret_cast<const uint32_t*>(&r0);
-                    accp[16 + i] = *reinterpret_cast<const uint32_t*>(&r1);
                 }
+            } else if constexpr (EPI == kEpiHw16) {
+#pragma unroll
+                for (int i = 0; i < UNIT; ++i)                    // fp16 accumulator: one element per 32-bit TMEM column, low half
+                    acc[PART * UNIT + i] = __half2float(__ushort_as_half((unsigned short)(p[i] & 0xFFFFu)));
             } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    acc[i] = fold<MODE, EPI, PARTIAL>(acc[i], __uint_as_float(p0[i]), args);
-                    acc[32 + i] = fold<MODE, EPI, PARTIAL>(acc[32 + i], __uint_as_float(p1[i]), args);
-                }
+                for (int i = 0; i < UNIT; ++i)
+                    acc[PART * UNIT + i] = fold<MODE, EPI, PARTIAL>(acc[PART * UNIT + i], __uint_as_float(p[i]), args);
             }
+        };
+        using Part0 = std::integral_constant<int, 0>;
+        using Part1 = std::integral_constant<int, UPC - 1>;      // second half-chunk (== Part0 when a unit is a whole chunk)
+
+        issue(0, buf0);
+        for (int u = 0; u < total_units; u += 2) {
+            landed(u, buf0);
+            if (u + 1 < total_units) issue(u + 1, buf1);
+            fold_unit(Part0{}, buf0);
+            if (u + 1 >= total_units) break;
+            landed(u + 1, buf1);
+            if (u + 2 < total_units) issue(u + 2, buf0);
+            fold_unit(Part1{}, buf1);
         }
 
         // C = alpha * acc
@@ -280,6 +311,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < kColsPerThread / 2; ++i)          // inf / NaN: an accumulator left the finite fp16 range
                 bad |= ((accp[i] & 0x7C00u) == 0x7C00u) || ((accp[i] & 0x7C000000u) == 0x7C000000u);
+            if (bad) atomicOr(args.status, LOF_GEMM_STATUS_PACKED_RANGE);
+        }
+        if constexpr (EPI == kEpiHw16) {
+            bool bad = false;
+#pragma unroll
+            for (int i = 0; i < kColsPerThread; ++i) bad |= (__float_as_uint(acc[i]) & 0x7F800000u) == 0x7F800000u;
             if (bad) atomicOr(args.status, LOF_GEMM_STATUS_PACKED_RANGE);
         }
         if (row < args.M) {
@@ -436,12 +473,12 @@ bool make_operand_map(CUtensorMap* map, const void* base, int64_t rows, int64_t 
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-uint32_t make_idesc(int op)
+uint32_t make_idesc(int op, bool f16_accum = false)
 {
     // tcgen05 instruction descriptor: c_format F32 (bits 4-5 = 1), a/b format (bits 7-9 / 10-12), K-major A and B
     // (bits 15, 16 = 0), N >> 3 (bits 17-22), M >> 4 (bits 24-28)
     const uint32_t fmt = (op == kOpE4M3) ? 0u : (op == kOpE5M2) ? 1u : 1u /* kind::f16: 1 = BF16 */;
-    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    return ((f16_accum ? 0u : 1u) << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 template <int MODE, int EPI, bool PARTIAL>
@@ -493,6 +530,20 @@ int packed_epi(int op, int mode, bool partial, bool allow, int accum_mant_bits, 
     return -1;
 }
 
+// Can the tensor core keep the accumulator itself?  With c_format = F16 every tcgen05.mma performs
+//     D_fp16 <- RNE_fp16( D_fp16 + sum_k a_k * b_k )          (one rounding of the exact sum; scripts/probe_tmem_f16.cu,
+//                                                              profiles/r01_probe_tmem_f16.txt; fp16 incl. subnormals)
+// which IS the single-rounding fold with an E5M10 accumulator under RNE when the k-chunk is exactly one MMA
+// (K = 32 for 8-bit operands, 16 for bf16).  Valid while the accumulator stays finite (checked, generic recompute
+// otherwise).  Mantissa-only 10-bit accumulators qualify for e4m3 operands only (see packed_epi).
+bool hw_f16_accum_ok(int op, int mode, bool partial, bool allow, int accum_mant_bits, const lof_format_t* fmt, int64_t k_chunk, int kstep)
+{
+    if (!allow || partial || mode != LOF_RoundToNearestEven || k_chunk != kstep) return false;
+    if (!fmt) return accum_mant_bits == 10 && op == kOpE4M3;
+    const int ebits = fmt->bitwidth - fmt->mantissa_bits - (fmt->is_signed == LOF_Signed ? 1 : 0);
+    return fmt->mantissa_bits == 10 && ebits == 5 && fmt->bias == 15;
+}
+
 }  // namespace
 
 // operand_dtype: LOF_BF16, LOF_E4M3 or LOF_E5M2.  *err is set for unsupported requests (no launch happened).
@@ -515,6 +566,20 @@ cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, 
     const size_t bytes_a = (size_t)M * K * esize, bytes_b = (size_t)N * K * esize;
     const size_t off_b = (bytes_a + 1023) & ~size_t(1023), off_s = off_b + ((bytes_b + 1023) & ~size_t(1023));
     uint8_t* ws = nullptr;
+    {   // keep freed workspace blocks cached in the device's default pool (the default threshold of 0 returns them
+        // to the driver at every synchronisation, which costs a real cudaMalloc per call)
+        static bool pool_ready[64] = {false};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                uint64_t keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            pool_ready[dev] = true;
+        }
+    }
     cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&ws), off_s + 256, stream);
     if (e != cudaSuccess) return e;
     int* status = reinterpret_cast<int*>(ws + off_s);
@@ -569,7 +634,19 @@ cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, 
 
     const bool partial = (flags & LOF_GEMM_PARTIAL_ROUND) != 0;
     const int packed = packed_epi(op, mode, partial, (flags & LOF_GEMM_NO_PACKED) == 0, accum_mant_bits, acc_fmt);
-    if (packed >= 0) {
+    const bool hw16 = hw_f16_accum_ok(op, mode, partial, (flags & (LOF_GEMM_NO_PACKED | LOF_GEMM_NO_HW_ACCUM)) == 0,
+                                      accum_mant_bits, acc_fmt, k_chunk, kstep);
+    if (hw16) {
+        // fp16 accumulation inside the tensor core: one "chunk" as far as the kernel's pipeline is concerned
+        TcArgs h = a;
+        h.idesc = make_idesc(op, true);
+        h.steps_per_chunk = h.k_steps;
+        h.run_mask = 0; h.run_value = 0;
+        e = launch_one<LOF_RoundToNearestEven, kEpiHw16, false>(ma, mb, C, h, stream);
+        ++*launches;
+        if (e != cudaSuccess) return fail(e);
+        a.run_mask = LOF_GEMM_STATUS_PACKED_RANGE; a.run_value = LOF_GEMM_STATUS_PACKED_RANGE;
+    } else if (packed >= 0) {
         // packed epilogue; if it reports LOF_GEMM_STATUS_PACKED_RANGE the generic kernel below recomputes C
         a.run_mask = 0; a.run_value = 0;
         e = (packed == kEpiHalf2) ? launch_one<LOF_RoundToNearestEven, kEpiHalf2, true>(ma, mb, C, a, stream)

@@ -77,7 +77,10 @@ __device__ __forceinline__ float mx_quant(float x, const MxBlockCtx& c, const Mx
     } else {
         rb = exact_params_f32<MODE>(__float_as_uint(q), a.elem, w);
     }
-    const float r = __fmul_rn(__uint_as_float(rb), c.scale);
+    float r = __fmul_rn(__uint_as_float(rb), c.scale);
+    // NaN bit patterns of the reference's CPU arithmetic (x86 SSE): a NaN operand propagates quieted (virtual_round
+    // only ever produces +qNaN), an invalid operation (0 * inf with an infinite scale) yields the negative "indefinite"
+    if (r != r) r = __uint_as_float((rb & 0x7FFFFFFFu) > 0x7F800000u ? 0x7FC00000u : 0xFFC00000u);
     return c.live ? r : 0.0f;
 }
 
@@ -144,7 +147,7 @@ mx_shuffle_kernel(const float4* in, float4* out, int64_t nrows, MxArgs a, RngArg
             const float scale = mx_block_scale(m[r], a, rng_scale, g0 / (uint64_t)BS);
             const MxBlockCtx c = mx_make_ctx(scale);
             uint4 w = make_uint4(0, 0, 0, 0);
-            if constexpr (ModeTraits<MODE>::kUsesRng) w = philox_block(rng, g0 >> 2);
+            if constexpr (ModeTraits<MODE>::kUsesRng) w = philox_group4(rng, g0 >> 2);
             float4 o;
             o.x = mx_quant<MODE>(v[r].x, c, a, w.x);
             o.y = mx_quant<MODE>(v[r].y, c, a, w.y);
@@ -173,7 +176,7 @@ mx_block_per_thread_kernel(const float* in, float* out, int64_t elem0, int64_t n
         const MxBlockCtx c = mx_make_ctx(scale);
         for (int i = 0; i < len; ++i) {
             uint32_t w = 0;
-            if constexpr (ModeTraits<MODE>::kUsesRng) w = philox_word(rng, first_index + (uint64_t)(s + i));
+            if constexpr (ModeTraits<MODE>::kUsesRng) w = philox_event(rng, first_index + (uint64_t)(s + i));
             out[s + i] = mx_quant<MODE>(in[s + i], c, a, w);
         }
     }

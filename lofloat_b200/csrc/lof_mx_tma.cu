@@ -118,7 +118,7 @@ mx_tma_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant_
             for (int j = 0; j < 8; ++j) {
                 const MxBlockCtx& c = (j < 4) ? c0 : c1;
                 uint4 w = make_uint4(0, 0, 0, 0);
-                if constexpr (ModeTraits<MODE>::kUsesRng) w = philox_block(rng, (g0 >> 2) + j);
+                if constexpr (ModeTraits<MODE>::kUsesRng) w = philox_group4(rng, (g0 >> 2) + j);
                 v[j].x = mx_quant<MODE>(v[j].x, c, a, w.x);
                 v[j].y = mx_quant<MODE>(v[j].y, c, a, w.y);
                 v[j].z = mx_quant<MODE>(v[j].z, c, a, w.z);
@@ -134,7 +134,7 @@ mx_tma_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 uint4 w = make_uint4(0, 0, 0, 0);
-                if constexpr (ModeTraits<MODE>::kUsesRng) w = philox_block(rng, (g0 >> 2) + j);
+                if constexpr (ModeTraits<MODE>::kUsesRng) w = philox_group4(rng, (g0 >> 2) + j);
                 v[j].x = mx_quant<MODE>(v[j].x, c, a, w.x);
                 v[j].y = mx_quant<MODE>(v[j].y, c, a, w.y);
                 v[j].z = mx_quant<MODE>(v[j].z, c, a, w.z);

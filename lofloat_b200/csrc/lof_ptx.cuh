@@ -94,7 +94,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar)
 }
 
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive 32-bit columns (thread i gets lane i's columns)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v)     // v[0..31]: compile-time indexed registers
 {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "

@@ -4,12 +4,12 @@
 namespace lof {
 
 cudaError_t launch_round_f64(int kind, int mode, const void* in, void* out, int64_t n, const RoundPlan& plan,
-                            const FastPlan& fast, int r, int len, double scale, const RngArgs& rng, uint64_t first_index,
+                            const FastPlan& fast, const MagicPlan& magic, int r, int len, double scale, const RngArgs& rng, uint64_t first_index,
                             const RoundLaunchCfg& cfg, cudaStream_t stream)
 {
     if (kind != kKindMantissa)
-        return launch_round<LOF_F64, kKindParams>(mode, in, out, n, plan, fast, r, len, scale, rng, first_index, cfg, stream);
-    return launch_round<LOF_F64, kKindMantissa>(mode, in, out, n, plan, fast, r, len, scale, rng, first_index, cfg, stream);
+        return launch_round<LOF_F64, kKindParams>(mode, in, out, n, plan, fast, magic, r, len, scale, rng, first_index, cfg, stream);
+    return launch_round<LOF_F64, kKindMantissa>(mode, in, out, n, plan, fast, magic, r, len, scale, rng, first_index, cfg, stream);
 }
 
 }  // namespace lof

@@ -40,9 +40,14 @@ enum : int {
     kKindFastSat = 2,       // fp32 branch-free path (lof_fast_f32.cuh), OV_behavior == Saturating
     kKindFastExt = 3,       //   "                                      , OV_behavior == Extended
     kKindFastSatChk = 4,    //   + fp32-subnormal inputs routed to the exact routine (denorm_min < 2^-126)
-    kKindFastExtChk = 5
+    kKindFastExtChk = 5,
+    kKindMagicSat = 6,      // fp32 "magic add" path (lof_fast_f32.cuh, second generation): 6 IEEE-like modes only
+    kKindMagicExt = 7,
+    kKindMagicSatChk = 8,   //   + exact routine for fp32-subnormal / out-of-range-constant inputs
+    kKindMagicExtChk = 9
 };
-constexpr bool kind_is_fast(int k) { return k >= kKindFastSat; }
+constexpr bool kind_is_fast(int k) { return k >= kKindFastSat && k <= kKindFastExtChk; }
+constexpr bool kind_is_magic(int k) { return k >= kKindMagicSat; }
 
 template <int DTYPE, int MODE, int KIND>
 struct ElemOp {
@@ -50,6 +55,7 @@ struct ElemOp {
     using B = typename S::bits_t;
     RoundPlan plan;                 // params overloads
     FastPlan fast;                  // fast fp32 kinds
+    MagicPlan magic;                // magic-add fp32 kinds
     int r;                          // mantissa overload: bits to drop
     int len;
     typename S::scale_t scale;
@@ -89,6 +95,44 @@ __device__ __forceinline__ uint4 round_vec16_fast(uint4 v, const ElemOp<LOF_F32,
     return o;
 }
 
+template <int MODE, int KIND>
+__device__ __forceinline__ uint4 round_vec16_magic(uint4 v, const ElemOp<LOF_F32, MODE, KIND>& op, const uint4& w)
+{
+    constexpr bool SAT = (KIND == kKindMagicSat || KIND == kKindMagicSatChk);
+    constexpr bool CHK = (KIND == kKindMagicSatChk || KIND == kKindMagicExtChk);
+    const uint32_t x0 = __float_as_uint(__fmul_rn(op.scale, __uint_as_float(v.x)));
+    const uint32_t x1 = __float_as_uint(__fmul_rn(op.scale, __uint_as_float(v.y)));
+    const uint32_t x2 = __float_as_uint(__fmul_rn(op.scale, __uint_as_float(v.z)));
+    const uint32_t x3 = __float_as_uint(__fmul_rn(op.scale, __uint_as_float(v.w)));
+    bool rare = false;
+    uint4 o;
+    o.x = round_magic_f32<MODE, SAT, CHK>(x0, op.magic, w.x, rare);
+    o.y = round_magic_f32<MODE, SAT, CHK>(x1, op.magic, w.y, rare);
+    o.z = round_magic_f32<MODE, SAT, CHK>(x2, op.magic, w.z, rare);
+    o.w = round_magic_f32<MODE, SAT, CHK>(x3, op.magic, w.w, rare);
+    if constexpr (CHK) {
+        if (rare) {
+            o.x = exact_params_f32<MODE>(x0, op.plan, w.x);
+            o.y = exact_params_f32<MODE>(x1, op.plan, w.y);
+            o.z = exact_params_f32<MODE>(x2, op.plan, w.z);
+            o.w = exact_params_f32<MODE>(x3, op.plan, w.w);
+        }
+    }
+    return o;
+}
+
+// 4-byte containers: one 16-byte vector with its four event words already drawn
+template <int DTYPE, int MODE, int KIND>
+__device__ __forceinline__ uint4 round_vec16_w(uint4 v, const ElemOp<DTYPE, MODE, KIND>& op, const uint4& w)
+{
+    if constexpr (kind_is_fast(KIND)) return round_vec16_fast<MODE, KIND>(v, op, w);
+    else if constexpr (kind_is_magic(KIND)) return round_vec16_magic<MODE, KIND>(v, op, w);
+    else {
+        v.x = op(v.x, w.x); v.y = op(v.y, w.y); v.z = op(v.z, w.z); v.w = op(v.w, w.w);
+        return v;
+    }
+}
+
 // process one 16-byte vector that starts at global element index g0
 template <int DTYPE, int MODE, int KIND>
 __device__ __forceinline__ uint4 round_vec16(uint4 v, const ElemOp<DTYPE, MODE, KIND>& op,
@@ -98,12 +142,11 @@ __device__ __forceinline__ uint4 round_vec16(uint4 v, const ElemOp<DTYPE, MODE, 
     constexpr bool kRng = ModeTraits<MODE>::kUsesRng;
     if constexpr (sizeof(B) == 4) {
         uint4 w = make_uint4(0, 0, 0, 0);
-        if constexpr (kRng) w = philox_block(rng, g0 >> 2);          // g0 % 4 == 0 (host-checked)
-        if constexpr (kind_is_fast(KIND)) return round_vec16_fast<MODE, KIND>(v, op, w);
-        v.x = op(v.x, w.x); v.y = op(v.y, w.y); v.z = op(v.z, w.z); v.w = op(v.w, w.w);
+        if constexpr (kRng) w = philox_group4(rng, g0 >> 2);         // g0 % 4 == 0 (host-checked)
+        return round_vec16_w<DTYPE, MODE, KIND>(v, op, w);
     } else if constexpr (sizeof(B) == 2) {
         uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0;
-        if constexpr (kRng) { w0 = philox_block(rng, g0 >> 2); w1 = philox_block(rng, (g0 >> 2) + 1); }
+        if constexpr (kRng) { w0 = philox_group4(rng, g0 >> 2); w1 = philox_group4(rng, (g0 >> 2) + 1); }
         auto two = [&](uint32_t packed, uint32_t wa, uint32_t wb) -> uint32_t {
             const uint16_t lo = op((uint16_t)(packed & 0xFFFFu), wa);
             const uint16_t hi = op((uint16_t)(packed >> 16), wb);
@@ -114,7 +157,7 @@ __device__ __forceinline__ uint4 round_vec16(uint4 v, const ElemOp<DTYPE, MODE, 
     } else {
         uint32_t wa = 0, wb = 0;
         if constexpr (kRng) {                                         // g0 % 2 == 0
-            const uint4 w = philox_block(rng, g0 >> 2);
+            const uint4 w = philox_group4(rng, g0 >> 2);
             const bool hi = (g0 & 2u) != 0;
             wa = hi ? w.z : w.x; wb = hi ? w.w : w.y;
         }
@@ -144,6 +187,20 @@ round_vec_kernel(const uint4* in, uint4* out, int64_t nvec, int ntail,
             const int64_t idx = base + (int64_t)u * kRoundThreads;
             if (idx < nvec) v[u] = ld_stream(in + idx);
         }
+        if constexpr (ModeTraits<MODE>::kUsesRng && sizeof(B) == 4 && UNROLL == 4) {
+            // class-0 events (<= 8 random bits): the 4 vectors of this thread in this 4096-element tile share ONE
+            // Philox block by construction of the event stream (lof_core.cuh) when the tile grid is aligned with it
+            if (rng.cls == 0u && (first_index & 4095u) == 0u) {
+                const uint4 b = philox_block(rng, ((first_index >> 12) + (uint64_t)tile) * 256u + threadIdx.x);
+                const uint32_t wu[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    const int64_t idx = base + (int64_t)u * kRoundThreads;
+                    if (idx < nvec) st_stream(out + idx, round_vec16_w<DTYPE, MODE, KIND>(v[u], op, bytes_of(wu[u])));
+                }
+                continue;
+            }
+        }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const int64_t idx = base + (int64_t)u * kRoundThreads;
@@ -159,7 +216,7 @@ round_vec_kernel(const uint4* in, uint4* out, int64_t nvec, int ntail,
         const B* sin = reinterpret_cast<const B*>(in);
         B* sout = reinterpret_cast<B*>(out);
         uint32_t w = 0;
-        if constexpr (ModeTraits<MODE>::kUsesRng) w = philox_word(rng, first_index + (uint64_t)i);
+        if constexpr (ModeTraits<MODE>::kUsesRng) w = philox_event(rng, first_index + (uint64_t)i);
         sout[i] = op(sin[i], w);
     }
 }
@@ -174,7 +231,7 @@ round_scalar_kernel(const typename Src<DTYPE>::bits_t* in, typename Src<DTYPE>::
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         uint32_t w = 0;
-        if constexpr (ModeTraits<MODE>::kUsesRng) w = philox_word(rng, first_index + (uint64_t)i);
+        if constexpr (ModeTraits<MODE>::kUsesRng) w = philox_event(rng, first_index + (uint64_t)i);
         out[i] = op(in[i], w);
     }
 }
@@ -200,7 +257,15 @@ cudaError_t launch_round_mode(const void* in, void* out, int64_t n, const ElemOp
         const int ntail = (int)(n - nvec * VEC);
         const int64_t tile = (int64_t)kRoundThreads * cfg.unroll;
         int64_t grid = (nvec + tile - 1) / tile;
-        if (grid > max_ctas) grid = max_ctas;
+        // persistent grid: never more CTAs than are resident at once (a partial second wave would run alone)
+        static int resident = 0;
+        if (resident == 0) {
+            int nb = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, round_vec_kernel<DTYPE, MODE, KIND, 4>, kRoundThreads, 0) != cudaSuccess || nb < 1) nb = 1;
+            resident = nb;
+        }
+        const int64_t cap = (int64_t)cfg.num_sms * (resident < cfg.ctas_per_sm ? resident : cfg.ctas_per_sm);
+        if (grid > cap) grid = cap;
         if (grid < 1) grid = 1;
         const uint4* vin = static_cast<const uint4*>(in);
         uint4* vout = static_cast<uint4*>(out);
@@ -231,7 +296,7 @@ cudaError_t launch_round_mode(const void* in, void* out, int64_t n, const ElemOp
 
 // mode dispatch for one (dtype, overload); defined once per dtype in lof_round_<dtype>.cu
 template <int DTYPE, int KIND>
-cudaError_t launch_round(int mode, const void* in, void* out, int64_t n, const RoundPlan& plan, const FastPlan& fast, int r, int len,
+cudaError_t launch_round(int mode, const void* in, void* out, int64_t n, const RoundPlan& plan, const FastPlan& fast, const MagicPlan& magic, int r, int len,
                          double scale, const RngArgs& rng, uint64_t first_index, const RoundLaunchCfg& cfg,
                          cudaStream_t stream)
 {
@@ -240,9 +305,10 @@ cudaError_t launch_round(int mode, const void* in, void* out, int64_t n, const R
     switch (mode) {
 #define LOF_CASE(M)                                                                           \
     case M: {                                                                                 \
+        if constexpr (kind_is_magic(KIND) && !MagicTraits<M>::kOk) return cudaErrorInvalidValue; else { \
         ElemOp<DTYPE, M, KIND> op;                                                          \
-        op.plan = plan; op.fast = fast; op.r = r; op.len = len; op.scale = sc; op.scale_one = (sc == (typename S::scale_t)1); \
-        return launch_round_mode<DTYPE, M, KIND>(in, out, n, op, rng, first_index, cfg, stream); \
+        op.plan = plan; op.fast = fast; op.magic = magic; op.r = r; op.len = len; op.scale = sc; op.scale_one = (sc == (typename S::scale_t)1); \
+        return launch_round_mode<DTYPE, M, KIND>(in, out, n, op, rng, first_index, cfg, stream); } \
     }
         LOF_CASE(LOF_RoundToNearestEven) LOF_CASE(LOF_RoundTowardsZero) LOF_CASE(LOF_RoundAwayFromZero)
         LOF_CASE(LOF_StochasticRoundingA) LOF_CASE(LOF_RoundToNearestOdd) LOF_CASE(LOF_RoundDown)
@@ -257,16 +323,16 @@ cudaError_t launch_round(int mode, const void* in, void* out, int64_t n, const R
 
 // explicit-instantiation entry points (one translation unit per dtype)
 cudaError_t launch_round_f32(int kind, int mode, const void* in, void* out, int64_t n, const RoundPlan& plan,
-                              const FastPlan& fast, int r, int len, double scale, const RngArgs& rng, uint64_t first_index,
+                              const FastPlan& fast, const MagicPlan& magic, int r, int len, double scale, const RngArgs& rng, uint64_t first_index,
                              const RoundLaunchCfg& cfg, cudaStream_t stream);
 cudaError_t launch_round_f16(int kind, int mode, const void* in, void* out, int64_t n, const RoundPlan& plan,
-                              const FastPlan& fast, int r, int len, double scale, const RngArgs& rng, uint64_t first_index,
+                              const FastPlan& fast, const MagicPlan& magic, int r, int len, double scale, const RngArgs& rng, uint64_t first_index,
                              const RoundLaunchCfg& cfg, cudaStream_t stream);
 cudaError_t launch_round_bf16(int kind, int mode, const void* in, void* out, int64_t n, const RoundPlan& plan,
-                              const FastPlan& fast, int r, int len, double scale, const RngArgs& rng, uint64_t first_index,
+                              const FastPlan& fast, const MagicPlan& magic, int r, int len, double scale, const RngArgs& rng, uint64_t first_index,
                               const RoundLaunchCfg& cfg, cudaStream_t stream);
 cudaError_t launch_round_f64(int kind, int mode, const void* in, void* out, int64_t n, const RoundPlan& plan,
-                              const FastPlan& fast, int r, int len, double scale, const RngArgs& rng, uint64_t first_index,
+                              const FastPlan& fast, const MagicPlan& magic, int r, int len, double scale, const RngArgs& rng, uint64_t first_index,
                              const RoundLaunchCfg& cfg, cudaStream_t stream);
 
 }  // namespace lof

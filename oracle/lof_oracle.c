@@ -6,6 +6,7 @@
  */
 #include "lof_oracle.h"
 
+#include <float.h>
 #include <math.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -48,6 +49,31 @@ uint32_t lofo_rand_word(const lofo_rng* rng, uint64_t index, uint32_t stream)
     lofo_philox4x32_10(ctr, key, out);
     return out[index & 3u];
 }
+
+/* Random bits one rounding event consumes, and the event word of global element `index`:
+ *   <= 8 bits : byte (index & 3) of the word owned by the 4-element group v = index >> 2, namely dense word
+ *               4 * (((v >> 10) << 8) | (v & 255)) + ((v >> 8) & 3)   (4 groups 256 apart share one Philox block)
+ *   <= 16 bits: half (index & 1) of dense word index >> 1
+ *   else      : dense word index                                     (lofloat_b200/csrc/lof_core.cuh rand_class) */
+int lofo_rand_bits_needed(int mode, int len)
+{
+    if (mode == LOFO_TRUE_SR) return 32;
+    if (mode == LOFO_PROB) return 1;
+    if (mode == LOFO_SR_D) return len + 1;
+    return len;
+}
+
+uint32_t lofo_rand_event(const lofo_rng* rng, uint64_t index, uint32_t stream, int nbits)
+{
+    if (!rng) return 0u;
+    if (rng->fixed) return rng->fixed_word;
+    if (nbits > 16) return lofo_rand_word(rng, index, stream);
+    if (nbits > 8) return (lofo_rand_word(rng, index >> 1, stream) >> (16u * (uint32_t)(index & 1u))) & 0xFFFFu;
+    const uint64_t v = index >> 2;
+    const uint64_t q = 4u * (((v >> 10) << 8) | (v & 255u)) + ((v >> 8) & 3u);
+    return (lofo_rand_word(rng, q, stream) >> (8u * (uint32_t)(index & 3u))) & 0xFFu;
+}
+
 
 /* ------------------------------------------------------------------------------------
  * container conversions
@@ -285,7 +311,7 @@ static inline uint16_t scale_bf16(uint16_t b, uint16_t sb)
         BITS_T* dst = (BITS_T*)out;                                                       \
         _Pragma("omp parallel for schedule(static)")                                      \
         for (int64_t i = 0; i < n; ++i) {                                                 \
-            uint32_t w = need_rng ? lofo_rand_word(rng, first_index + (uint64_t)i, LOFO_STREAM_ELEM) : 0u; \
+            uint32_t w = need_rng ? lofo_rand_event(rng, first_index + (uint64_t)i, LOFO_STREAM_ELEM, nbits) : 0u; \
             BITS_T v = SCALE_EXPR;                                                        \
             dst[i] = CALL;                                                                \
         }                                                                                 \
@@ -296,6 +322,7 @@ void lofo_round_params(const void* in, void* out, int64_t n, int dtype, const lo
 {
     const int mode = ps->rounding_mode, len = ps->stoch_length;
     const int need_rng = mode_uses_rng(mode) && rng != NULL;
+    const int nbits = lofo_rand_bits_needed(mode, len);
     const lofo_consts kc = lofo_consts_make(f);
     switch (dtype) {
     case LOFO_F32: {
@@ -326,6 +353,7 @@ void lofo_round_mantissa(const void* in, void* out, int64_t n, int dtype, int ma
 {
     const int mode = ps->rounding_mode, len = ps->stoch_length;
     const int need_rng = mode_uses_rng(mode) && rng != NULL;
+    const int nbits = lofo_rand_bits_needed(mode, len);
     switch (dtype) {
     case LOFO_F32: {
         const float s = (float)scale;
@@ -371,6 +399,7 @@ void lofo_mx_round_f32(const float* in, float* out, int64_t n, int block_size,
     const lofo_consts kpub = lofo_consts_make(pub), kpriv = lofo_consts_make(priv);
     const int need_rng_e = mode_uses_rng(ps_priv->rounding_mode) && rng != NULL;
     const int need_rng_s = mode_uses_rng(ps_pub->rounding_mode) && rng != NULL;
+    const int nbits_e = lofo_rand_bits_needed(ps_priv->rounding_mode, ps_priv->stoch_length);
     const int64_t nblocks = (n + block_size - 1) / block_size;
 #pragma omp parallel for schedule(static)
     for (int64_t blk = 0; blk < nblocks; ++blk) {
@@ -387,7 +416,7 @@ void lofo_mx_round_f32(const float* in, float* out, int64_t n, int block_size,
         const float scale = u2f(vround_params_f32(f2u(amax / pmn), pub, &kpub, ps_pub->rounding_mode, 0, ws));
         if (scale > 0.0f) {
             for (int i = 0; i < len; ++i) {
-                uint32_t w = need_rng_e ? lofo_rand_word(rng, first_index + (uint64_t)(b + i), LOFO_STREAM_ELEM) : 0u;
+                uint32_t w = need_rng_e ? lofo_rand_event(rng, first_index + (uint64_t)(b + i), LOFO_STREAM_ELEM, nbits_e) : 0u;
                 float q = u2f(vround_params_f32(f2u(in[b + i] / scale), priv, &kpriv, ps_priv->rounding_mode,
                                                 ps_priv->stoch_length, w));
                 out[b + i] = q * scale;
@@ -468,6 +497,28 @@ void lofo_gemm_f32(const float* A, const float* B, float* C, int64_t M, int64_t 
     }
 }
 
+/* Round-to-odd add used by the chunked mode: RZ(a + b) with the LSB OR-ed with "inexact".  Computed from
+ * the RN sum and its exact TwoSum error term (Knuth), no rounding-mode switching. */
+float lofo_rto_add(float a, float b)
+{
+    const float s = a + b;
+    if (isnan(s)) return u2f(f2u(s) | 1u);                    /* NaN stays NaN (device: RZ NaN | sticky) */
+    if (isinf(s)) {
+        if (isinf(a) || isinf(b)) return s;                    /* genuine infinity: exact */
+        return copysignf(FLT_MAX, s);                          /* finite sum beyond FLT_MAX: RZ = FLT_MAX, LSB already 1 */
+    }
+    const float bb = s - a;
+    const float err = (a - (s - bb)) + (b - bb);               /* exact: a + b == s + err */
+    if (err == 0.0f) return s;
+    float rz = s;
+    if (s == 0.0f) {
+        /* cannot happen with err != 0 (a sum that rounds to zero is exact) */
+        return s;
+    }
+    if ((err > 0.0f) != (s > 0.0f)) rz = nextafterf(s, 0.0f);  /* the exact value lies between s and zero */
+    return u2f(f2u(rz) | 1u);
+}
+
 /* Oracle of OUR tensor-core (tcgen05) chunked mode -- not a reference function.
  * Each k-chunk's partial dot product P is taken as the correctly rounded fp32 value of the
  * exact sum (the tensor core's internal alignment may differ by a few fp32 ulps on wide-range
@@ -495,7 +546,7 @@ void lofo_gemm_chunked_f32(const float* A, const float* B, float* C, int64_t M, 
                     if (acc_fmt) partf = u2f(vround_params_f32(f2u(partf), acc_fmt, &kacc, mode, len, 0u));
                     else         partf = u2f(vround_mant_f32(f2u(partf), accum_mant_bits, mode, len, 0u));
                 }
-                const float t = lofo_round_to_odd_fma(1.0f, partf, acc);
+                const float t = lofo_rto_add(acc, partf);
                 if (acc_fmt) acc = u2f(vround_params_f32(f2u(t), acc_fmt, &kacc, mode, len, 0u));
                 else         acc = u2f(vround_mant_f32(f2u(t), accum_mant_bits, mode, len, 0u));
             }

@@ -69,7 +69,9 @@ typedef struct {
 } lofo_rng;
 
 void     lofo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
-uint32_t lofo_rand_word(const lofo_rng* rng, uint64_t index, uint32_t stream);
+uint32_t lofo_rand_word(const lofo_rng* rng, uint64_t index, uint32_t stream);      /* dense 32-bit word */
+int      lofo_rand_bits_needed(int mode, int stoch_len);
+uint32_t lofo_rand_event(const lofo_rng* rng, uint64_t index, uint32_t stream, int nbits); /* per-event word, see lof_oracle.c */
 
 /* scalar entry points (bit patterns in / out, container = fp32) */
 uint32_t lofo_round_params_bits_f32(uint32_t bits, const lofo_format* f, const lofo_projspec* ps, uint32_t w);
@@ -102,6 +104,9 @@ float lofo_round_to_odd_fma(float a, float b, float c);
 void lofo_gemm_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
                    int accum_mant_bits, const lofo_projspec* ps, int64_t kc,
                    float alpha, float beta, const lofo_rng* rng);
+
+/* round-to-odd add of the chunked mode: RZ(a + b) | inexact */
+float lofo_rto_add(float a, float b);
 
 /* chunked tensor-core semantics oracle (our tcgen05 mode, NOT a reference function; "parity unpinned" --
  * there is no runnable reference for chunked accumulation):

@@ -31,7 +31,7 @@ for t in $TARGETS; do
       timeout 600 $NCU_FULL -k regex:round_vec_kernel -s 2 -c 1 -o $OUT/round_sra python scripts/prof_target.py round 3 e4m3 > $OUT/round_sra.log 2>&1
       echo "round_sra exit $?"; export_rep round_sra ;;
     mx0)
-      timeout 600 $NCU_FULL -k regex:mx_shuffle_kernel -s 2 -c 1 -o $OUT/mx_shuffle python scripts/prof_target.py mx 0 e4m3 > $OUT/mx0.log 2>&1
+      timeout 600 $NCU_FULL -k regex:"mx_fast_kernel|mx_shuffle_kernel" -s 2 -c 1 -o $OUT/mx_shuffle python scripts/prof_target.py mx 0 e4m3 > $OUT/mx0.log 2>&1
       echo "mx0 exit $?"; export_rep mx_shuffle ;;
     mx1)
       timeout 600 $NCU_FULL -k regex:mx_tma_kernel -s 2 -c 1 -o $OUT/mx_tma python scripts/prof_target.py mx 1 e4m3 > $OUT/mx1.log 2>&1
@@ -39,8 +39,11 @@ for t in $TARGETS; do
     gemm_exact)
       timeout 600 $NCU_FULL -k regex:gemm_exact_kernel -s 1 -c 1 -o $OUT/gemm_exact python scripts/prof_target.py gemm 2048 > $OUT/gemm_exact.log 2>&1
       echo "gemm_exact exit $?"; export_rep gemm_exact ;;
+    gemm_tc_hw)
+      timeout 600 $NCU_FULL -k regex:gemm_tc_kernel -s 1 -c 1 -o $OUT/gemm_tc_hw python scripts/prof_target.py gemm_tc 8192 hw > $OUT/gemm_tc_hw.log 2>&1
+      echo "gemm_tc_hw exit $?"; export_rep gemm_tc_hw ;;
     gemm_tc)
-      timeout 600 $NCU_FULL -k regex:gemm_tc_kernel -s 1 -c 1 -o $OUT/gemm_tc python scripts/prof_target.py gemm_tc 4096 > $OUT/gemm_tc.log 2>&1
+      timeout 600 $NCU_FULL -k regex:gemm_tc_kernel -s 1 -c 1 -o $OUT/gemm_tc python scripts/prof_target.py gemm_tc 8192 packed > $OUT/gemm_tc.log 2>&1
       echo "gemm_tc exit $?"; export_rep gemm_tc ;;
   esac
 done

@@ -3,6 +3,7 @@
     python scripts/prof_target.py round [mode] [format]     # 2^28 fp32, randn * 2^U{-12..12}
     python scripts/prof_target.py mx [variant] [format]     # 16384 x 16384 fp32, block 32
     python scripts/prof_target.py gemm [M]                  # exact-mode GEMM
+    python scripts/prof_target.py gemm_tc [M] [packed|generic]   # tcgen05 chunked GEMM, k_chunk 32, accum mant 10
 """
 import sys
 from pathlib import Path
@@ -42,6 +43,17 @@ def main():
         x *= torch.exp2(torch.randint(-8, 9, (16384, 1), device=dev, generator=g).float())
         for _ in range(4):
             y = lof.virtual_mx_round(x, 32, f, lof.create_e8m0_params())
+    elif what == "gemm_tc":
+        import numpy as np
+        M = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+        variant = sys.argv[3] if len(sys.argv) > 3 else "packed"
+        kw = {"packed": dict(k_chunk=32, partial_round=True), "hw": dict(k_chunk=32),
+              "generic": dict(k_chunk=32, allow_hw_accum=False)}[variant]
+        e4m3 = fmt("e4m3")
+        A = lof.virtual_round(torch.rand(M, M, device=dev, generator=g) * 2 - 1, e4m3)
+        B = lof.virtual_round(torch.rand(M, M, device=dev, generator=g) * 2 - 1, e4m3)
+        for _ in range(3):
+            y = lof.lof_gemm(A, B, 10, check=False, **kw)
     else:
         M = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
         A = torch.rand(M, M, device=dev, generator=g) * 2 - 1

@@ -139,6 +139,40 @@ def step_packed():
     print("INFO status bits after overflow case:", lof.lof_gemm.last_status, flush=True)
 
 
+def step_hw16():
+    """fp16 accumulation inside the tensor core (c_format = F16) vs the oracle's single-rounding fold, E5M10 / RNE / k = 32."""
+    import numpy as np
+    import oracle_lib as L
+    import lofloat_b200 as lof
+    e5m10 = L.fmt(16, 10, 15, L.SATURATING, L.SIGNED)
+    d = lof.FloatFormatDescriptor(16, 10, 15, lof.InfBehavior.Saturating, lof.NaNBehavior._3109, lof.Signedness.Signed,
+                                  lof.create_half_params().is_inf_checker, lof.create_half_params().is_nan_checker)
+    A, B = ints((256, 1024), -8, 8, 5), ints((1024, 384), -8, 8, 6)
+    compare("hw16: integer data, E5M10", run_gemm(A, B, 0, 32, accum_format=d), L.o_gemm_chunked(A, B, 0, 32, acc_fmt=e5m10))
+    A, B = e4m3_uniform((512, 2048), 13), e4m3_uniform((2048, 256), 14)
+    want = L.o_gemm_chunked(A, B, 0, 32, acc_fmt=e5m10)
+    compare("hw16: U(-1,1) e4m3, E5M10 vs oracle (bit-exact?)", run_gemm(A, B, 0, 32, accum_format=d), want)
+    compare("hw16: mantissa-only 10 vs oracle (bit-exact?)", run_gemm(A, B, 10, 32), L.o_gemm_chunked(A, B, 10, 32))
+    compare("generic (no hw) E5M10 vs oracle", run_gemm(A, B, 0, 32, accum_format=d, allow_hw_accum=False, allow_packed=False), want)
+    # wide-range operands: every e4m3 magnitude class, random signs -> partial sums with large exponent spread
+    rng = np.random.default_rng(99)
+    def wide(shape):
+        e = rng.integers(-6, 5, shape)
+        m = rng.integers(8, 16, shape) / 8.0
+        return (np.where(rng.random(shape) < 0.5, -1, 1) * m * np.exp2(e)).astype(np.float32)
+    A, B = wide((256, 4096)), wide((4096, 256))
+    want = L.o_gemm_chunked(A, B, 0, 32, acc_fmt=e5m10)
+    compare("hw16: wide-range e4m3 operands, K = 4096 (bit-exact?)", run_gemm(A, B, 0, 32, accum_format=d), want)
+    compare("hw16: wide-range, tolerance view", run_gemm(A, B, 0, 32, accum_format=d), want, exact=False, tol_ulps=4.0)
+    compare("generic: wide-range (bit-exact?)", run_gemm(A, B, 0, 32, accum_format=d, allow_hw_accum=False, allow_packed=False), want)
+    Ab, Bb = ints((128, 512), -60, 60, 7), ints((512, 128), -60, 60, 8)
+    compare("hw16: bf16 operands, k_chunk 16", run_gemm(Ab, Bb, 0, 16, accum_format=d, operand_dtype="bf16"),
+            L.o_gemm_chunked(Ab, Bb, 0, 16, acc_fmt=e5m10))
+    Ao, Bo = (ints((128, 512), 200, 448, 15) // 32) * 32, (ints((512, 128), 200, 448, 16) // 32) * 32
+    compare("hw16: overflow -> generic recompute", run_gemm(Ao, Bo, 0, 32, accum_format=d), L.o_gemm_chunked(Ao, Bo, 0, 32, acc_fmt=e5m10))
+    print("INFO status after overflow:", lof.lof_gemm.last_status, flush=True)
+
+
 def step_inexact():
     import numpy as np
     import lofloat_b200 as lof
@@ -158,8 +192,9 @@ def step_perf():
     for n in (4096, 8192):
         A = torch.from_numpy(e4m3_uniform((n, n), 21)).to(dev)
         B = torch.from_numpy(e4m3_uniform((n, n), 22)).to(dev)
-        for label, kw in (("k32 mant10 S2 packed", dict(k_chunk=32, partial_round=True)),
-                          ("k32 mant10 S1 generic", dict(k_chunk=32)),
+        for label, kw in (("k32 mant10 S1 hw fp16 accumulate", dict(k_chunk=32)),
+                          ("k32 mant10 S2 packed", dict(k_chunk=32, partial_round=True)),
+                          ("k32 mant10 S1 generic", dict(k_chunk=32, allow_hw_accum=False)),
                           ("k128 mant10 S1 generic", dict(k_chunk=128)),
                           ("k512 mant10 S1 generic", dict(k_chunk=512)),
                           ("k512 mant10 S2 packed", dict(k_chunk=512, partial_round=True)),
@@ -189,7 +224,7 @@ def step_perf():
 
 
 STEPS = {"plain_1tile": step_plain_1tile, "plain_k512": step_plain_k512, "multitile": step_multitile, "bf16": step_bf16,
-         "tails": step_tails, "packed": step_packed, "inexact": step_inexact, "perf": step_perf}
+         "tails": step_tails, "packed": step_packed, "hw16": step_hw16, "inexact": step_inexact, "perf": step_perf}
 
 
 def main():

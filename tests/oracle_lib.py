@@ -104,6 +104,10 @@ def oracle():
         lib.lofo_philox4x32_10.argtypes = [C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
         lib.lofo_rand_word.argtypes = [PR, u64, u32]
         lib.lofo_rand_word.restype = u32
+        lib.lofo_rand_event.argtypes = [PR, u64, u32, i32]
+        lib.lofo_rand_event.restype = u32
+        lib.lofo_rand_bits_needed.argtypes = [i32, i32]
+        lib.lofo_rand_bits_needed.restype = i32
         lib.lofo_round_params_bits_f32.argtypes = [u32, PF, PP, u32]
         lib.lofo_round_params_bits_f32.restype = u32
         lib.lofo_round_mantissa_bits_f32.argtypes = [u32, i32, PP, u32]
@@ -234,6 +238,11 @@ def o_philox(ctr, key):
     o = (C.c_uint32 * 4)()
     oracle().lofo_philox4x32_10(c, k, o)
     return [int(v) for v in o]
+
+
+def o_rand_event(seed, offset, index, nbits, stream=STREAM_ELEM) -> int:
+    r = _rng(seed, offset)
+    return int(oracle().lofo_rand_event(C.byref(r), index, stream, nbits))
 
 
 def o_rand_word(seed, offset, index, stream=STREAM_ELEM) -> int:

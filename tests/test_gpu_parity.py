@@ -237,7 +237,7 @@ def _mx_input(n, seed):
     return x
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_mx_bit_exact(lof, cuda_dev, variant):
     """Methodology of test/test_virtual_mx_round_cuda.cu:76-152: GPU vs CPU scalar oracle, bit-exact,
     block sizes x formats x modes x n in {bs, 3bs, 3bs+1, 1000, 4096, 5003, ...}."""
@@ -257,7 +257,7 @@ def test_mx_bit_exact(lof, cuda_dev, variant):
         _lib.set_option("mx.variant", 0)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_mx_modes_scale_modes_and_edge_cases(lof, cuda_dev, variant):
     from lofloat_b200 import _lib
     _lib.set_option("mx.variant", variant)
@@ -267,6 +267,13 @@ def test_mx_modes_scale_modes_and_edge_cases(lof, cuda_dev, variant):
         x[64:96] = 0.0                                           # all-zero block -> 0, not NaN
         x[128:160] = 1e-42                                       # amax underflows the scale format -> block = 0
         x[200] = 3e38                                            # scale overflows E8M0 (Extended -> +inf)
+        x[300] = np.nan                                          # NaN element: dropped from the amax, +qNaN in the output
+        x[420] = np.inf                                          # infinite amax -> infinite scale
+        x[520] = -np.inf
+        x[640:672] = np.float32(2.0 ** 127)                      # scale 2^127 / 2^126 boundary of the reciprocal shortcut
+        x[700] = np.float32(1.7e38)
+        x[800:832] = np.float32(1e-38) * np.arange(32, dtype=np.float32)   # subnormal-ish block: tiny scales
+        x[900:932] = np.float32(3e-36)
         xt = _gpu(x, cuda_dev)
         for mode in range(15):
             sl = 8 if mode in (L.SR_A, L.SR_B, L.SR_C, L.SR_D) else 0
@@ -301,6 +308,124 @@ def test_mx_modes_scale_modes_and_edge_cases(lof, cuda_dev, variant):
 
 
 # ---------------------------------------------------------------------------------- GEMM
+def test_mx_division_shortcut_exhaustive(lof, cuda_dev):
+    """The fast MX kernel forms amax / priv_max_normal with a 3-FMA sequence instead of an IEEE division:
+    checked on the device against __fdiv_rn for EVERY non-negative finite fp32 amax, for every MX element format."""
+    from lofloat_b200 import _lib
+    lib = _lib.lib()
+    for name in ("e4m3_b7", "p3109_8p4", "e5m2", "e3m2", "e2m3", "e2m1"):
+        f = L.FORMATS[name]
+        cf = _lib.CFormat(f.bitwidth, f.mantissa_bits, f.bias, f.ov_behavior, f.na_behavior, f.is_signed, 0)
+        bad = C.c_uint64(123)
+        _lib.check(lib.lof_selftest_mx_division(C.byref(cf), C.byref(bad), None), "selftest")
+        assert bad.value == 0, (name, bad.value)
+
+
+# --------------------------------------------------------------------------- chunked tensor-core GEMM
+def _ints(shape, lo, hi, seed):
+    return np.random.default_rng(seed).integers(lo, hi + 1, shape).astype(np.float32)
+
+
+def _e4m3_uniform(shape, seed):
+    """U(-1,1) rounded to OCP e4m3 -- the C4 operand distribution (test/gemm_test.cpp:82-86)."""
+    x = np.random.default_rng(seed).uniform(-1, 1, shape).astype(np.float32)
+    return L.o_round_params(x.ravel(), L.FORMATS["e4m3_b7"], L.RNE).reshape(shape)
+
+
+def _tc(lof, dev, A, B, mant, k_chunk, **kw):
+    return _np(lof.lof_gemm(_gpu(A, dev), _gpu(B, dev), mant, k_chunk=k_chunk, **kw))
+
+
+def test_gemm_chunked_tcgen05_exactly_summable_data(lof, cuda_dev):
+    """tcgen05 chunked GEMM vs the CPU statement of its semantics (oracle/lof_oracle.c lofo_gemm_chunked_f32) on
+    small-integer operands, where every k-chunk partial is exact in any accumulator: BIT-EXACT for every
+    deterministic mode, both fold semantics, mantissa-only and full-format accumulators, e4m3 / e5m2 / bf16
+    operands, ragged shapes and the alpha scaling."""
+    A, B = _ints((256, 1024), -8, 8, 5), _ints((1024, 384), -8, 8, 6)
+    assert L.bits_equal(_tc(lof, cuda_dev, A, B, 23, 1024), A @ B)                       # plain GEMM, one chunk, no rounding
+    for mant in (10, 7, 4):
+        assert L.bits_equal(_tc(lof, cuda_dev, A, B, mant, 32, allow_packed=False), L.o_gemm_chunked(A, B, mant, 32)), mant
+    for mode in L.DETERMINISTIC_MODES:
+        got = _tc(lof, cuda_dev, A, B, 6, 32, round_mode=mode, allow_packed=False)
+        assert L.bits_equal(got, L.o_gemm_chunked(A, B, 6, 32, mode=mode)), L.MODE_NAMES[mode]
+        got = _tc(lof, cuda_dev, A, B, 5, 64, round_mode=mode, partial_round=True)
+        assert L.bits_equal(got, L.o_gemm_chunked(A, B, 5, 64, mode=mode, partial_round=True)), L.MODE_NAMES[mode]
+    e5m10 = L.fmt(16, 10, 15, L.SATURATING, L.SIGNED)
+    got = _tc(lof, cuda_dev, A, B, 0, 32, accum_format=_desc(lof, e5m10), allow_packed=False)
+    assert L.bits_equal(got, L.o_gemm_chunked(A, B, 0, 32, acc_fmt=e5m10))
+    e4m3acc = L.FORMATS["e4m3_b7"]                                                          # tiny accumulator: saturates / overflows
+    got = _tc(lof, cuda_dev, A, B, 0, 32, accum_format=_desc(lof, e4m3acc), round_mode=L.RTZ)
+    assert L.bits_equal(got, L.o_gemm_chunked(A, B, 0, 32, acc_fmt=e4m3acc, mode=L.RTZ))
+    # bf16 and e5m2 operands
+    Ab, Bb = _ints((256, 512), -100, 100, 7), _ints((512, 256), -100, 100, 8)
+    assert L.bits_equal(_tc(lof, cuda_dev, Ab, Bb, 8, 16, operand_dtype="bf16"), L.o_gemm_chunked(Ab, Bb, 8, 16))
+    got = _tc(lof, cuda_dev, Ab, Bb, 7, 32, operand_dtype="bf16", partial_round=True)               # packed bfloat162 epilogue
+    assert L.bits_equal(got, L.o_gemm_chunked(Ab, Bb, 7, 32, partial_round=True))
+    A5, B5 = _ints((128, 256), -3, 3, 9) * np.float32(0.25), _ints((256, 128), -3, 3, 10) * np.float32(4.0)
+    assert L.bits_equal(_tc(lof, cuda_dev, A5, B5, 10, 32, operand_dtype="e5m2"), L.o_gemm_chunked(A5, B5, 10, 32))
+    # ragged M, N, K (K % 128 != 0, last chunk short), alpha
+    Ar, Br = _ints((200, 400), -6, 6, 11), _ints((400, 136), -6, 6, 12)
+    assert L.bits_equal(_tc(lof, cuda_dev, Ar, Br, 10, 32, allow_packed=False), L.o_gemm_chunked(Ar, Br, 10, 32))
+    assert L.bits_equal(_tc(lof, cuda_dev, Ar, Br, 10, 96, allow_packed=False), L.o_gemm_chunked(Ar, Br, 10, 96))
+    got = _tc(lof, cuda_dev, Ar, Br, 10, 32, scale_a=2.0, scale_b=4.0, allow_packed=False)
+    assert L.bits_equal(got, L.o_gemm_chunked(Ar, Br, 10, 32, alpha=0.125))
+
+
+def test_gemm_chunked_tcgen05_c4_distribution_and_packed_epilogue(lof, cuda_dev):
+    """C4 operand distribution (U(-1,1) rounded to E4M3), k_chunk 32, accumulator mantissa 10 / E5M10.
+    Tolerance vs the oracle: the tensor core may form a chunk's fp32 partial with a different internal alignment
+    than the oracle's exactly rounded sum, which can move an accumulator by one unit of the ACCUMULATOR format per
+    disagreement; stated bound: |C - C_oracle| <= 4 ulp of the accumulator format (2^-10 relative) at the result's
+    magnitude (in practice the two agree bit for bit on this data).  The packed half2 epilogue must equal the
+    generic epilogue BIT FOR BIT (same tensor-core partials)."""
+    A, B = _e4m3_uniform((512, 2048), 13), _e4m3_uniform((2048, 256), 14)
+
+    def ulp_err(got, want, mant=10):
+        ulp = np.exp2(np.floor(np.log2(np.maximum(np.abs(want), 1e-30))) - mant)
+        return float((np.abs(got.astype(np.float64) - want) / ulp).max())
+    want2 = L.o_gemm_chunked(A, B, 10, 32, partial_round=True)
+    gen2 = _tc(lof, cuda_dev, A, B, 10, 32, partial_round=True, allow_packed=False)
+    assert ulp_err(gen2, want2) <= 4.0
+    assert L.bits_equal(_tc(lof, cuda_dev, A, B, 10, 32, partial_round=True), gen2)           # packed half2 == generic
+    assert lof.lof_gemm.last_status == 0
+    e5m10 = L.fmt(16, 10, 15, L.SATURATING, L.SIGNED)
+    assert L.bits_equal(_tc(lof, cuda_dev, A, B, 0, 32, accum_format=_desc(lof, e5m10), partial_round=True), gen2)
+    assert ulp_err(_tc(lof, cuda_dev, A, B, 10, 32), L.o_gemm_chunked(A, B, 10, 32)) <= 4.0  # single-rounding fold
+    # leaving the fp16 range: the packed kernel must flag it and the generic kernel recompute
+    Ab, Bb = (_ints((128, 512), 200, 448, 15) // 32) * 32, (_ints((512, 128), 200, 448, 16) // 32) * 32
+    got = _tc(lof, cuda_dev, Ab, Bb, 10, 32, partial_round=True)
+    assert L.bits_equal(got, L.o_gemm_chunked(Ab, Bb, 10, 32, partial_round=True))
+    assert lof.lof_gemm.last_status & 4
+    # operands that are not exactly representable are reported, not silently rounded
+    with pytest.raises(lof.LoFloatError):
+        _tc(lof, cuda_dev, np.full((128, 128), 0.3, np.float32), np.ones((128, 128), np.float32), 10, 32)
+    with pytest.raises(lof.LoFloatError):
+        lof.lof_gemm(_gpu(A, cuda_dev), _gpu(B, cuda_dev), 10, k_chunk=48)                          # k_chunk % 32 != 0
+
+
+def test_gemm_chunked_full_size_properties(lof, cuda_dev):
+    """C4 at full size (8192^3, E4M3 operands, k_chunk 32, accumulator mantissa 10): size-independent properties.
+    (1) sampled rows x columns against the oracle, (2) rows of A that are zero give zero rows, (3) scaling A by 2
+    (exact in every format involved) scales C by exactly 2, (4) packed == generic on a sampled band."""
+    n = 8192
+    g = torch.Generator(device=cuda_dev).manual_seed(42)
+    e4m3 = lof.create_p3109_params(8, 4, bias=7)
+    A = lof.virtual_round(torch.rand(n, n, device=cuda_dev, generator=g) * 2 - 1, e4m3)
+    B = lof.virtual_round(torch.rand(n, n, device=cuda_dev, generator=g) * 2 - 1, e4m3)
+    A[100:164] = 0
+    Cm = lof.lof_gemm(A, B, 10, k_chunk=32, partial_round=True)
+    assert not Cm[100:164].any()
+    rows, cols = [0, 1, 777, 4095, 8191], slice(4000, 4128)
+    want = L.o_gemm_chunked(_np(A[rows]), _np(B[:, cols]), 10, 32, partial_round=True)
+    got = _np(Cm[rows][:, cols])
+    ulp = np.exp2(np.floor(np.log2(np.maximum(np.abs(want), 1e-30))) - 10)
+    assert float((np.abs(got.astype(np.float64) - want) / ulp).max()) <= 4.0
+    C2 = lof.lof_gemm(A * 2, B, 10, k_chunk=32, partial_round=True)
+    assert torch.equal(C2, Cm * 2)
+    Cg = lof.lof_gemm(A[:256], B, 10, k_chunk=32, partial_round=True, allow_packed=False)
+    assert torch.equal(Cg, Cm[:256])
+
+
 def test_gemm_exact_vs_oracle_and_golden(lof, cuda_dev):
     g = np.load(G / "gemm_f32.npz")
     for (M, N, K) in ((2, 2, 4), (17, 33, 64), (64, 48, 300), (40, 24, 513)):
@@ -421,13 +546,26 @@ def test_full_size_properties_mx(lof, cuda_dev, variant):
 
 
 def test_fast_kernel_equals_exact_kernel_every_fp32_pattern(lof, cuda_dev):
-    """The branch-free fp32 kernels (lof_fast_f32.cuh: float-add trick for the target-subnormal regime,
-    clamped-shift integer path, select-based overflow/NaN) against the exact integer kernel
-    (round.fast = 0) on EVERY fp32 bit pattern, every named format, all 15 modes, with and without the
-    fused scale.  Compared on the device; the exact kernel itself is pinned to the oracle above."""
+    """The branch-free fp32 kernels (lof_fast_f32.cuh) against the exact integer kernel (round.fast = 0) on EVERY
+    fp32 bit pattern, every named format, all 15 modes, with and without the fused scale: round.fast = 2 (the
+    default: magic-add path for the six IEEE-like modes, first-generation fast path for the others) and, for
+    those six modes, also round.fast = 1.  Compared on the device; the exact kernel itself is pinned to the
+    oracle above."""
     from lofloat_b200 import _lib
     chunk = 1 << 28
     checked = 0
+    magic_modes = (L.RNE, L.RTZ, L.RAZ, L.RU, L.RD, L.RTO)
+
+    def run(x, d, mode, sl, scale, base, fast):
+        _lib.set_option("round.fast", fast)
+        return lof.virtual_round(x, d, mode, sl, scale, rng=(17, 3), first_index=base)
+
+    def check(a, b, what, base):
+        if not torch.equal(a.view(torch.int32), b.view(torch.int32)):
+            idx = int((a.view(torch.int32) != b.view(torch.int32)).nonzero()[0])
+            raise AssertionError(f"{what}: in=0x{(base + idx) & 0xFFFFFFFF:08x} "
+                                 f"fast=0x{int(a.view(torch.int32)[idx]) & 0xFFFFFFFF:08x} "
+                                 f"exact=0x{int(b.view(torch.int32)[idx]) & 0xFFFFFFFF:08x}")
     try:
         for name, f in L.FORMATS.items():
             d = _desc(lof, f)
@@ -437,32 +575,25 @@ def test_fast_kernel_equals_exact_kernel_every_fp32_pattern(lof, cuda_dev):
                 for base in range(0, 1 << 32, chunk):
                     bits = torch.arange(base, base + chunk, device=cuda_dev, dtype=torch.int64).to(torch.int32)
                     x = bits.view(torch.float32)
-                    _lib.set_option("round.fast", 1)
-                    a = lof.virtual_round(x, d, mode, sl, rng=(17, 3), first_index=base)
-                    _lib.set_option("round.fast", 0)
-                    b = lof.virtual_round(x, d, mode, sl, rng=(17, 3), first_index=base)
-                    same = torch.equal(a.view(torch.int32), b.view(torch.int32))
-                    if not same:
-                        idx = int((a.view(torch.int32) != b.view(torch.int32)).nonzero()[0])
-                        raise AssertionError(f"{name} {L.MODE_NAMES[mode]}: in=0x{(base + idx) & 0xFFFFFFFF:08x} "
-                                             f"fast=0x{int(a.view(torch.int32)[idx]) & 0xFFFFFFFF:08x} "
-                                             f"exact=0x{int(b.view(torch.int32)[idx]) & 0xFFFFFFFF:08x}")
+                    b = run(x, d, mode, sl, 1.0, base, 0)
+                    check(run(x, d, mode, sl, 1.0, base, 2), b, f"{name} {L.MODE_NAMES[mode]} fast=2", base)
+                    if mode in magic_modes:
+                        check(run(x, d, mode, sl, 1.0, base, 1), b, f"{name} {L.MODE_NAMES[mode]} fast=1", base)
                     checked += chunk
-                    del bits, x, a, b
+                    del bits, x, b
         # fused scale (scale * x is formed inside the kernel)
         for name in ("e4m3_b7", "bf16_like"):
             d = _desc(lof, L.FORMATS[name])
-            for mode in (L.RNE, L.RAZ, L.RNO, L.SR_A):
+            for mode in (L.RNE, L.RAZ, L.RNO, L.SR_A, L.RD):
+                sl = 4 if mode == L.SR_A else 0
                 for base in range(0, 1 << 32, chunk):
                     x = torch.arange(base, base + chunk, device=cuda_dev, dtype=torch.int64).to(torch.int32).view(torch.float32)
-                    _lib.set_option("round.fast", 1)
-                    a = lof.virtual_round(x, d, mode, 4 if mode == L.SR_A else 0, 0.3, rng=(1, 1))
-                    _lib.set_option("round.fast", 0)
-                    b = lof.virtual_round(x, d, mode, 4 if mode == L.SR_A else 0, 0.3, rng=(1, 1))
-                    assert torch.equal(a.view(torch.int32), b.view(torch.int32)), (name, mode, hex(base))
-                    del x, a, b
+                    b = run(x, d, mode, sl, 0.3, 0, 0)
+                    check(run(x, d, mode, sl, 0.3, 0, 2), b, f"{name} {mode} scaled fast=2", base)
+                    check(run(x, d, mode, sl, 0.3, 0, 1), b, f"{name} {mode} scaled fast=1", base)
+                    del x, b
     finally:
-        _lib.set_option("round.fast", 1)
+        _lib.set_option("round.fast", 2)
     assert checked == len(L.FORMATS) * 15 * (1 << 32)
 
 

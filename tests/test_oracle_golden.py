@@ -33,6 +33,30 @@ def test_rand_word_layout():
     assert L.o_rand_word(seed, off, 21, L.STREAM_SCALE) == blk_s[1]
 
 
+def test_rand_event_packing():
+    """Per-event random words (oracle/lof_oracle.c lofo_rand_event == lofloat_b200/csrc/lof_core.cuh philox_group4):
+    > 16 bits -> dense word i; <= 16 bits -> half of dense word i >> 1; <= 8 bits -> byte (i & 3) of the word owned by
+    the 4-element group, where the groups v, v + 256, v + 512, v + 768 of an aligned 4096-element run share a block."""
+    seed, off = 77, 5
+    for i in (0, 1, 5, 1023, 1024, 4095, 4096, 4097 + 3 * 1024, 10 ** 7 + 3):
+        assert L.o_rand_event(seed, off, i, 32) == L.o_rand_word(seed, off, i)
+        assert L.o_rand_event(seed, off, i, 17) == L.o_rand_word(seed, off, i)
+        assert L.o_rand_event(seed, off, i, 16) == (L.o_rand_word(seed, off, i >> 1) >> (16 * (i & 1))) & 0xFFFF
+        v = i >> 2
+        q = 4 * (((v >> 10) << 8) | (v & 255)) + ((v >> 8) & 3)
+        assert L.o_rand_event(seed, off, i, 8) == (L.o_rand_word(seed, off, q) >> (8 * (i & 3))) & 0xFF
+        assert L.o_rand_event(seed, off, i, 1) == L.o_rand_event(seed, off, i, 8)
+    # every byte of every word of a block is used exactly once inside an aligned 4096-element run
+    owners = {}
+    for i in range(4096):
+        v = i >> 2
+        q = 4 * (((v >> 10) << 8) | (v & 255)) + ((v >> 8) & 3)
+        owners.setdefault((q, i & 3), []).append(i)
+    assert len(owners) == 4096 and all(len(o) == 1 for o in owners.values())
+    assert L.oracle().lofo_rand_bits_needed(L.SR_A, 8) == 8 and L.oracle().lofo_rand_bits_needed(L.SR_D, 8) == 9
+    assert L.oracle().lofo_rand_bits_needed(L.TRUE_SR, 0) == 32 and L.oracle().lofo_rand_bits_needed(L.PROB, 0) == 1
+
+
 def test_round_params_golden_f32():
     g = _load("round_params_f32.npz")
     x = g["x"]
