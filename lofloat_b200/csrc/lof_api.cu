@@ -169,7 +169,7 @@ MagicPlan make_magic_plan(const RoundPlan& p, int mode)
     const bool mode_ok = mode == LOF_RoundToNearestEven || mode == LOF_RoundTowardsZero || mode == LOF_RoundAwayFromZero ||
                          mode == LOF_RoundUp || mode == LOF_RoundDown || mode == LOF_RoundToOdd || sr;
     // stochastic: 1 <= len <= shiftN (reference precondition), the offset's exponent c - (23 + len) must stay normal
-    if (sr && (p.stoch_len < 1 || p.stoch_len > p.shiftN || p.stoch_len > 22 || p.min_exp_b + p.shiftN < 25 + p.stoch_len)) return m;
+    if (sr && (p.stoch_len < 1 || p.stoch_len > p.shiftN || p.stoch_len > 22)) return m;
     uint32_t mv;
     std::memcpy(&mv, &p.min_val, 4);
     // m = 0 (E8M0-like): the reference's RNE / round-to-odd act on the raw bits, whose "LSB" is then the exponent
@@ -186,6 +186,14 @@ MagicPlan make_magic_plan(const RoundPlan& p, int mode)
     // still yields a magnitude >= ovf_thresh, see lof_fast_f32.cuh) or go to the exact routine
     m.limit = (p.max_exp_b + p.shiftN <= 254) ? 0xFFFFFFFFu : (uint32_t)(255 - p.shiftN) << 23;
     m.check_denorm_in = mv < 0x00800000u;
+    m.lo_rare = m.check_denorm_in ? 0x007FFFFFu : 0u;
+    // SR: the offset's bit pattern is c - sr_sub with c >= (e + shiftN) << 23; it is a normal fp32 number iff
+    // e + shiftN >= 24 + len.  Formats whose subnormal floor already guarantees that need no check; for wide
+    // formats (bf16-like) the few binades below go to the exact routine.
+    if (sr && p.min_exp_b + p.shiftN < 24 + p.stoch_len) {
+        const uint32_t lo_limit = (uint32_t)(24 + p.stoch_len - p.shiftN) << 23;
+        if (lo_limit - 1u > m.lo_rare) m.lo_rare = lo_limit - 1u;
+    }
     m.sr_len = sr ? (uint32_t)p.stoch_len : 0u;
     m.sr_mask = sr ? ((1u << p.stoch_len) - 1u) : 0u;
     m.sr_sub = sr ? (uint32_t)(23 + p.stoch_len) << 23 : 0u;
@@ -243,7 +251,7 @@ int round_common(bool params, const void* in, void* out, int64_t n, int dtype, c
             if (fast_opt >= 2) {
                 magic = make_magic_plan(plan, mode);
                 if (magic.valid) {
-                    const bool chk = magic.check_denorm_in || magic.limit != 0xFFFFFFFFu;
+                    const bool chk = magic.lo_rare != 0u || magic.limit != 0xFFFFFFFFu;
                     kind = chk ? (plan.saturating ? kKindMagicSatChk : kKindMagicExtChk)
                                : (plan.saturating ? kKindMagicSat : kKindMagicExt);
                 }

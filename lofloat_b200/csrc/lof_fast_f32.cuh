@@ -165,6 +165,9 @@ struct MagicPlan {
     uint32_t ovf_thresh;       // rounded magnitude bits >= this -> overflow (0xFFFFFFFF: never)
     uint32_t limit;            // |x| bits >= limit need the exact routine (0xFFFFFFFF: none)
     uint32_t check_denorm_in;  // fp32-subnormal inputs need the exact routine
+    uint32_t lo_rare;          // nonzero |x| bits with (bits - 1) < lo_rare need the exact routine: the fp32 subnormals when
+                               // check_denorm_in, and for SR into wide formats every x whose offset quantum * 2^-len would
+                               // itself be an fp32 subnormal (0: none)
     uint32_t valid;
     // stochastic variants (SR-A, SR-D): the random offset R * quantum * 2^-len is added with truncation
     uint32_t sr_sub;           // (23 + len) << 23: c - sr_sub is the bit pattern of quantum * 2^-len
@@ -239,7 +242,7 @@ __device__ __forceinline__ uint32_t round_magic_f32(uint32_t x, const MagicPlan&
     out = (xf != xf) ? 0x7FC00000u : out;                     // NaN -> +qNaN (lo_float.h:2869)
     if constexpr (CHECK) {
         const uint32_t a = x & 0x7FFFFFFFu;
-        rare |= ((a - 1u) < 0x007FFFFFu && p.check_denorm_in != 0u) || (a >= p.limit);
+        rare |= ((a - 1u) < p.lo_rare) || (a >= p.limit);
     }
     return out;
 }

@@ -40,7 +40,7 @@ for t in $TARGETS; do
       timeout 600 $NCU_FULL -k regex:gemm_exact_kernel -s 1 -c 1 -o $OUT/gemm_exact python scripts/prof_target.py gemm 2048 > $OUT/gemm_exact.log 2>&1
       echo "gemm_exact exit $?"; export_rep gemm_exact ;;
     gemm_tc_hw)
-      timeout 600 $NCU_FULL -k regex:gemm_tc_kernel -s 1 -c 1 -o $OUT/gemm_tc_hw python scripts/prof_target.py gemm_tc 8192 hw > $OUT/gemm_tc_hw.log 2>&1
+      timeout 600 $NCU_FULL -k regex:gemm_tc_kernel -s 2 -c 1 -o $OUT/gemm_tc_hw python scripts/prof_target.py gemm_tc 8192 hw > $OUT/gemm_tc_hw.log 2>&1
       echo "gemm_tc_hw exit $?"; export_rep gemm_tc_hw ;;
     gemm_tc)
       timeout 600 $NCU_FULL -k regex:gemm_tc_kernel -s 1 -c 1 -o $OUT/gemm_tc python scripts/prof_target.py gemm_tc 8192 packed > $OUT/gemm_tc.log 2>&1
