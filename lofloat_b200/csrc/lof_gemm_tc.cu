@@ -173,7 +173,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
-        if (lane == 0) {
+        if (elect_one()) {
             for (int it = 0; it < n_stage_iters; ++it) {
                 const int s = it % kStages;
                 mbar_wait(&empty_bar[s], (uint32_t)(((it / kStages) & 1) ^ 1));
@@ -184,7 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else if (warp == 1) {
         // ====================================== MMA issuer ======================================
-        if (lane == 0) {
+        if (elect_one()) {
             int step = 0;
             for (int c = 0; c < n_chunks; ++c) {
                 const int ts = c % kTmemStages;
@@ -539,6 +539,7 @@ int packed_epi(int op, int mode, bool partial, bool allow, int accum_mant_bits, 
 bool hw_f16_accum_ok(int op, int mode, bool partial, bool allow, int accum_mant_bits, const lof_format_t* fmt, int64_t k_chunk, int kstep)
 {
     if (!allow || partial || mode != LOF_RoundToNearestEven || k_chunk != kstep) return false;
+    if (op == kOpBF16) return false;        // kind::f16 with bf16 operands has no F16 accumulator (illegal instruction on sm_100a)
     if (!fmt) return accum_mant_bits == 10 && op == kOpE4M3;
     const int ebits = fmt->bitwidth - fmt->mantissa_bits - (fmt->is_signed == LOF_Signed ? 1 : 0);
     return fmt->mantissa_bits == 10 && ebits == 5 && fmt->bias == 15;

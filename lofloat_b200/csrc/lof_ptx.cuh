@@ -12,6 +12,20 @@ namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a fully active warp.  The compiler's divergence analysis knows elect.sync leaves exactly one
+// thread active, so everything issued under this predicate keeps its operands in uniform registers; an
+// `if (lane == 0)` guard instead makes ptxas wrap every TMA / tcgen05 instruction in a uniformisation loop
+// (ELECT + BRA.U.ANY, ~50 clk each: profiles/r01e, the MMA issue loop ran at ~470 clk per instruction).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n.reg .b32 rx;\n.reg .pred px;\n"
+        "elect.sync rx|px, 0xFFFFFFFF;\n"
+        "@px mov.s32 %0, 1;\n}\n" : "+r"(pred));
+    return pred != 0;
+}
+
 // ---------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
