@@ -343,6 +343,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 2) tmem_dealloc(tmem_base, kTmemStages * BN);
 }
 
+#include "lof_gemm_tc2.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // operand preparation: fp32 -> tensor-core operand bytes (+ exact-representability check)
 // ------------------------------------------------------------------------------------------------
@@ -473,12 +475,12 @@ bool make_operand_map(CUtensorMap* map, const void* base, int64_t rows, int64_t 
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-uint32_t make_idesc(int op, bool f16_accum = false)
+uint32_t make_idesc(int op, bool f16_accum = false, int mma_m = BM, int mma_n = BN)
 {
     // tcgen05 instruction descriptor: c_format F32 (bits 4-5 = 1), a/b format (bits 7-9 / 10-12), K-major A and B
     // (bits 15, 16 = 0), N >> 3 (bits 17-22), M >> 4 (bits 24-28)
     const uint32_t fmt = (op == kOpE4M3) ? 0u : (op == kOpE5M2) ? 1u : 1u /* kind::f16: 1 = BF16 */;
-    return ((f16_accum ? 0u : 1u) << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    return ((f16_accum ? 0u : 1u) << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(mma_n >> 3) << 17) | ((uint32_t)(mma_m >> 4) << 24);
 }
 
 template <int MODE, int EPI, bool PARTIAL>
@@ -637,6 +639,39 @@ cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, 
     const int packed = packed_epi(op, mode, partial, (flags & LOF_GEMM_NO_PACKED) == 0, accum_mant_bits, acc_fmt);
     const bool hw16 = hw_f16_accum_ok(op, mode, partial, (flags & (LOF_GEMM_NO_PACKED | LOF_GEMM_NO_HW_ACCUM)) == 0,
                                       accum_mant_bits, acc_fmt, k_chunk, kstep);
+    // second-generation main loop (persistent CTA pairs, lof_gemm_tc2.cuh) for the accumulator semantics it serves
+    const bool one_chunk = a.steps_per_chunk >= a.k_steps;
+    int sms = 0, dev_id = 0;
+    cudaGetDevice(&dev_id);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
+    const bool pair_ok = (flags & LOF_GEMM_NO_PAIR) == 0 && sms >= 2 &&
+                         (hw16 || (one_chunk && mode == LOF_RoundToNearestEven));
+    if (pair_ok) {
+        PairArgs pa;
+        memset(&pa, 0, sizeof pa);
+        pa.t = a;
+        pa.t.idesc = make_idesc(op, hw16, 256, P_BN);
+        pa.tiles_m2 = (int)((M + 255) / 256);
+        pa.tiles_n2 = (int)((N + P_BN - 1) / P_BN);
+        pa.n_iters = (int)((K * esize + kRowBytes - 1) / kRowBytes);
+        const bool f8 = op != kOpBF16;
+        if (hw16) e = launch_pair<kEpiHw16, true>(ma, mb, C, pa, sms, stream);
+        else if (acc_fmt) e = f8 ? launch_pair<kEpiFmt, true>(ma, mb, C, pa, sms, stream) : launch_pair<kEpiFmt, false>(ma, mb, C, pa, sms, stream);
+        else e = f8 ? launch_pair<kEpiMant, true>(ma, mb, C, pa, sms, stream) : launch_pair<kEpiMant, false>(ma, mb, C, pa, sms, stream);
+        ++*launches;
+        if (e != cudaSuccess) return fail(e);
+        if (hw16) {         // left the fp16 range somewhere: the generic kernel recomputes C (device-side conditional launch)
+            a.run_mask = LOF_GEMM_STATUS_PACKED_RANGE; a.run_value = LOF_GEMM_STATUS_PACKED_RANGE;
+            e = launch_generic(mode, acc_fmt != nullptr, partial, ma, mb, C, a, stream);
+            ++*launches;
+            if (e != cudaSuccess) return fail(e);
+        }
+        if (dev_status) {
+            tc_or_status_kernel<<<1, 1, 0, stream>>>(dev_status, status);
+            ++*launches;
+        }
+        return cudaFreeAsync(ws, stream);
+    }
     if (hw16) {
         // fp16 accumulation inside the tensor core: one "chunk" as far as the kernel's pipeline is concerned
         TcArgs h = a;

@@ -266,7 +266,7 @@ _OPERAND_DTYPES = {"e4m3": _lib.LOF_E4M3, "e5m2": _lib.LOF_E5M2, "bf16": _lib.LO
 def lof_gemm(A: torch.Tensor, B: torch.Tensor, accum_mant_bits: int, round_mode=RoundingMode.RoundToNearestEven,
              stochastic_rounding_bits: int = 0, scale_a: float = 1.0, scale_b: float = 1.0, *, kc=None,
              k_chunk=None, accum_format: FloatFormatDescriptor | None = None, operand_dtype: str = "e4m3",
-             partial_round: bool = False, allow_packed: bool = True, allow_hw_accum: bool = True, check: bool = True,
+             partial_round: bool = False, allow_packed: bool = True, allow_hw_accum: bool = True, allow_pair: bool = True, check: bool = True,
              rng=None) -> torch.Tensor:
     """Low-precision-accumulation GEMM, float32 row-major (Lof_kernel.cu:96-154, LoPy_bind.cpp:361-372).
     The output is divided by scale_a*scale_b (a zero product counts as 1, cutlass_gemms.cuh:1784-1786).
@@ -299,7 +299,7 @@ def lof_gemm(A: torch.Tensor, B: torch.Tensor, accum_mant_bits: int, round_mode=
         if k_chunk is not None:
             fmt = accum_format._c() if accum_format is not None else None
             flags = ((_lib.LOF_GEMM_PARTIAL_ROUND if partial_round else 0) | (0 if allow_packed else _lib.LOF_GEMM_NO_PACKED) |
-                     (0 if allow_hw_accum else _lib.LOF_GEMM_NO_HW_ACCUM))
+                     (0 if allow_hw_accum else _lib.LOF_GEMM_NO_HW_ACCUM) | (0 if allow_pair else _lib.LOF_GEMM_NO_PAIR))
             status = torch.zeros(1, dtype=torch.int32, device=A.device)
             st = L.lof_gemm_chunked_f32(A_c.data_ptr(), B_c.data_ptr(), out.data_ptr(), M, N, K, int(accum_mant_bits),
                                         C.byref(fmt) if fmt is not None else None, C.byref(ps), int(k_chunk), alpha,

@@ -223,7 +223,46 @@ def step_perf():
         print(f"INFO perf {n}^3 cuBLAS bf16 (context): {2.0 * n ** 3 / (a.elapsed_time(b) / 5) / 1e9:.1f} TFLOP/s", flush=True)
 
 
-STEPS = {"plain_1tile": step_plain_1tile, "plain_k512": step_plain_k512, "multitile": step_multitile, "bf16": step_bf16,
+def step_pair():
+    """Persistent CTA-pair kernel (lof_gemm_tc2.cuh) against the first-generation kernel: same tensor-core arithmetic
+    -> bit-identical C, on aligned, ragged and tiny shapes; then its speed."""
+    import numpy as np
+    import torch
+    import lofloat_b200 as lof
+    d = lof.FloatFormatDescriptor(16, 10, 15, lof.InfBehavior.Saturating, lof.NaNBehavior._3109, lof.Signedness.Signed,
+                                  lof.create_half_params().is_inf_checker, lof.create_half_params().is_nan_checker)
+    for (M, N, K) in ((256, 256, 512), (512, 768, 2048), (200, 136, 400), (1000, 520, 4096 + 32), (128, 64, 128), (1536, 2048, 1024)):
+        A, B = e4m3_uniform((M, K), M + K), e4m3_uniform((K, N), N + K + 1)
+        for label, kw in (("hw16 E5M10 k32", dict(k_chunk=32, accum_format=d)), ("hw16 mant10 k32", dict(k_chunk=32)),
+                          ("one chunk mant10", dict(k_chunk=0)), ("one chunk E5M10", dict(k_chunk=0, accum_format=d)),
+                          ("one chunk mant23", dict(k_chunk=0, mant=23))):
+            kw = dict(kw)
+            mant = kw.pop("mant", 0 if "accum_format" in kw else 10)
+            got = run_gemm(A, B, mant, allow_pair=True, **kw)
+            want = run_gemm(A, B, mant, allow_pair=False, **kw)
+            compare(f"pair vs single-CTA kernel {M}x{N}x{K} {label}", got, want)
+    Ab, Bb = ints((384, 640), -60, 60, 7), ints((640, 300), -60, 60, 8)
+    compare("pair vs single-CTA, bf16 operands one chunk mant 8", run_gemm(Ab, Bb, 8, 640, operand_dtype="bf16"),
+            run_gemm(Ab, Bb, 8, 640, operand_dtype="bf16", allow_pair=False))
+    dev = torch.device("cuda:0")
+    for n in (4096, 8192):
+        A = torch.from_numpy(e4m3_uniform((n, n), 21)).to(dev)
+        B = torch.from_numpy(e4m3_uniform((n, n), 22)).to(dev)
+        for label, kw in (("pair hw16 k32", dict(k_chunk=32)), ("single-CTA hw16 k32", dict(k_chunk=32, allow_pair=False)),
+                          ("pair one chunk", dict(k_chunk=n)), ("single-CTA one chunk", dict(k_chunk=n, allow_pair=False))):
+            lof.lof_gemm(A, B, 10, check=False, **kw)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                lof.lof_gemm(A, B, 10, check=False, **kw)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / 5
+            print(f"INFO perf {n}^3 {label}: {ms:.3f} ms  {2.0 * n ** 3 / ms / 1e9:.1f} TFLOP/s (incl. operand conversion)", flush=True)
+
+
+STEPS = {"pair": step_pair, "plain_1tile": step_plain_1tile, "plain_k512": step_plain_k512, "multitile": step_multitile, "bf16": step_bf16,
          "tails": step_tails, "packed": step_packed, "hw16": step_hw16, "inexact": step_inexact, "perf": step_perf}
 
 
