@@ -42,6 +42,12 @@ for t in $TARGETS; do
     gemm_tc_hw)
       timeout 600 $NCU_FULL -k regex:gemm_tc_kernel -s 2 -c 1 -o $OUT/gemm_tc_hw python scripts/prof_target.py gemm_tc 8192 hw > $OUT/gemm_tc_hw.log 2>&1
       echo "gemm_tc_hw exit $?"; export_rep gemm_tc_hw ;;
+    gemm_pair)
+      timeout 600 $NCU_FULL -k regex:gemm_tc_pair_kernel -s 1 -c 1 -o $OUT/gemm_pair python scripts/prof_target.py gemm_tc 8192 hw > $OUT/gemm_pair.log 2>&1
+      echo "gemm_pair exit $?"; export_rep gemm_pair ;;
+    gemm_launches)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/gemm_launches.csv \
+          python scripts/prof_target.py gemm_tc 8192 hw > $OUT/gemm_launches.log 2>&1; echo "gemm_launches exit $?" ;;
     gemm_tc)
       timeout 600 $NCU_FULL -k regex:gemm_tc_kernel -s 1 -c 1 -o $OUT/gemm_tc python scripts/prof_target.py gemm_tc 8192 packed > $OUT/gemm_tc.log 2>&1
       echo "gemm_tc exit $?"; export_rep gemm_tc ;;

@@ -426,6 +426,59 @@ def test_gemm_chunked_full_size_properties(lof, cuda_dev):
     assert torch.equal(Cg, Cm[:256])
 
 
+def test_gemm_pair_kernel_equals_single_cta_kernel_and_oracle(lof, cuda_dev):
+    """Persistent CTA-pair main loop (tcgen05 cta_group::2, 256 x 256 tiles, lof_gemm_tc2.cuh): the accumulator
+    semantics it serves -- fp16 accumulation inside the tensor core (k_chunk 32, E5M10 / mantissa 10, RNE) and
+    one-chunk fp32 accumulation with a final rounding -- must be BIT-IDENTICAL to the single-CTA kernel (same
+    tensor-core arithmetic, different tiling) on aligned, ragged and tiny shapes, and bit-exact against the oracle on
+    exactly summable data."""
+    e5m10 = _desc(lof, L.fmt(16, 10, 15, L.SATURATING, L.SIGNED))
+    for (M, N, K) in ((256, 256, 512), (200, 136, 400), (1000, 520, 4096 + 32), (128, 64, 128), (768, 1280, 1024)):
+        A, B = _e4m3_uniform((M, K), M + K), _e4m3_uniform((K, N), N + K + 1)
+        for kw, mant in ((dict(k_chunk=32, accum_format=e5m10), 0), (dict(k_chunk=32), 10), (dict(k_chunk=0), 10),
+                         (dict(k_chunk=0, accum_format=e5m10), 0), (dict(k_chunk=0), 23)):
+            got = _np(lof.lof_gemm(_gpu(A, cuda_dev), _gpu(B, cuda_dev), mant, **kw))
+            ref = _np(lof.lof_gemm(_gpu(A, cuda_dev), _gpu(B, cuda_dev), mant, allow_pair=False, **kw))
+            assert L.bits_equal(got, ref), (M, N, K, kw)
+    A, B = _ints((300, 1024), -8, 8, 5), _ints((1024, 520), -8, 8, 6)
+    assert L.bits_equal(_tc(lof, cuda_dev, A, B, 23, 0), A @ B)
+    assert L.bits_equal(_tc(lof, cuda_dev, A, B, 10, 32), L.o_gemm_chunked(A, B, 10, 32))
+    assert L.bits_equal(_tc(lof, cuda_dev, A, B, 0, 32, accum_format=e5m10),
+                        L.o_gemm_chunked(A, B, 0, 32, acc_fmt=L.fmt(16, 10, 15, L.SATURATING, L.SIGNED)))
+    assert L.bits_equal(_tc(lof, cuda_dev, A, B, 4, 0), L.o_gemm_chunked(A, B, 4, 1024))
+    Ab, Bb = _ints((384, 640), -60, 60, 7), _ints((640, 300), -60, 60, 8)
+    assert L.bits_equal(_tc(lof, cuda_dev, Ab, Bb, 8, 0, operand_dtype="bf16"), L.o_gemm_chunked(Ab, Bb, 8, 640))
+    # leaving the fp16 range: flagged, and the generic kernel recomputes C
+    Ao, Bo = (_ints((128, 512), 200, 448, 15) // 32) * 32, (_ints((512, 128), 200, 448, 16) // 32) * 32
+    assert L.bits_equal(_tc(lof, cuda_dev, Ao, Bo, 10, 32), L.o_gemm_chunked(Ao, Bo, 10, 32))
+    assert lof.lof_gemm.last_status & 4
+
+
+def test_gemm_pair_kernel_c4_full_size_properties(lof, cuda_dev):
+    """C4 at full size through the CTA-pair kernel (8192^3, E4M3 operands, E5M10 accumulator re-rounded every k = 32
+    by the tensor core): sampled rows against the oracle within the stated 4 ulp-of-accumulator tolerance, zero rows,
+    exact power-of-two scaling, and pair == single-CTA kernel on a band."""
+    n = 8192
+    g = torch.Generator(device=cuda_dev).manual_seed(42)
+    e4m3 = lof.create_p3109_params(8, 4, bias=7)
+    A = lof.virtual_round(torch.rand(n, n, device=cuda_dev, generator=g) * 2 - 1, e4m3)
+    B = lof.virtual_round(torch.rand(n, n, device=cuda_dev, generator=g) * 2 - 1, e4m3)
+    A[300:364] = 0
+    e5m10_o = L.fmt(16, 10, 15, L.SATURATING, L.SIGNED)
+    Cm = lof.lof_gemm(A, B, 0, k_chunk=32, accum_format=_desc(lof, e5m10_o))
+    assert lof.lof_gemm.last_status == 0
+    assert not Cm[300:364].any()
+    rows, cols = [0, 1, 255, 256, 4097, 8191], slice(3968, 4224)
+    want = L.o_gemm_chunked(_np(A[rows]), _np(B[:, cols]), 0, 32, acc_fmt=e5m10_o)
+    got = _np(Cm[rows][:, cols])
+    ulp = np.exp2(np.floor(np.log2(np.maximum(np.abs(want), 2.0 ** -14))) - 10)
+    assert float((np.abs(got.astype(np.float64) - want) / ulp).max()) <= 4.0
+    C2 = lof.lof_gemm(A * 2, B, 0, k_chunk=32, accum_format=_desc(lof, e5m10_o))
+    assert torch.equal(C2, Cm * 2)
+    Cs = lof.lof_gemm(A[:512], B, 0, k_chunk=32, accum_format=_desc(lof, e5m10_o), allow_pair=False)
+    assert torch.equal(Cs, Cm[:512])
+
+
 def test_gemm_exact_vs_oracle_and_golden(lof, cuda_dev):
     g = np.load(G / "gemm_f32.npz")
     for (M, N, K) in ((2, 2, 4), (17, 33, 64), (64, 48, 300), (40, 24, 513)):
