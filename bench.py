@@ -125,6 +125,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly ONE JSON line (NCCL prints its version banner there otherwise)
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
     combos = make_structs()

@@ -644,7 +644,7 @@ cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, 
     int sms = 0, dev_id = 0;
     cudaGetDevice(&dev_id);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
-    const bool pair_ok = (flags & LOF_GEMM_NO_PAIR) == 0 && sms >= 2 &&
+    const bool pair_ok = (flags & LOF_GEMM_NO_PAIR) == 0 && sms >= 2 && K > 0 &&
                          (hw16 || (one_chunk && mode == LOF_RoundToNearestEven));
     if (pair_ok) {
         PairArgs pa;

@@ -293,7 +293,7 @@ def lof_gemm(A: torch.Tensor, B: torch.Tensor, accum_mant_bits: int, round_mode=
     A_c, B_c = A.contiguous(), B.contiguous()
     M, K = A_c.shape
     N = B_c.shape[1]
-    out = torch.zeros((M, N), dtype=torch.float32, device=A.device)
+    out = torch.empty((M, N), dtype=torch.float32, device=A.device)      # every element is written (beta = 0); the reference zero-fills first (Lof_kernel.cu:119)
     status = None
     with torch.cuda.device(A.device):
         if k_chunk is not None:
