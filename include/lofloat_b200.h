@@ -188,6 +188,49 @@ LOF_API int lof_gemm_chunked_f32(const float* A, const float* B, float* C, int64
                          void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Low-bit storage codec: fp32 -> packed n-bit representations and back.
+ * Replaces LoF_encode_cuda / LoF_decode_cuda (src/lo_pack.hpp:499-529; CPU twins LoF_encode / LoF_decode
+ * :419-465) with the conversion semantics of convert_float_to_rep / convert_rep_to_float (:109-319): the strict
+ * typed conversion (Saturation_Mode, Inf / NaN checkers, signedness), NOT virtual_round's container semantics.
+ * The Inf / NaN functor objects of FloatingPointParams (fp_tools.hpp:187-252) travel as data:
+ *     IsInf(rep) := (rep & inf_mask) == inf_value
+ *     IsNaN(rep) := (rep & nan_mask) == nan_value  &&  (nan_mant_mask == 0 || (rep & nan_mant_mask) != 0)
+ * ("never" = mask 0, value 1); this form covers every checker the reference defines.
+ * bitwidth must be in [1, 16] (lo_pack.hpp:4-9).  Packed layout: groups of lcm(n, 8 or 16) bits, LSB-first inside
+ * a byte, element i of a group in slot i (LOF_PACK_FORWARD) or slot G-1-i (LOF_PACK_REVERSE); a trailing partial
+ * group is zero-padded.  For n = 8 / 16 the packed buffer is simply the array of representations.
+ * ------------------------------------------------------------------------------------- */
+typedef struct lof_codec_format_t {
+    lof_format_t fmt;
+    uint32_t inf_mask, inf_value;
+    uint32_t nan_mask, nan_value, nan_mant_mask;
+    uint32_t min_pos_inf;           /* IsInf.minPosInf()                              */
+    uint32_t qnan, snan;            /* IsNaN.qNanBitPattern() / sNanBitPattern()      */
+} lof_codec_format_t;
+typedef enum { LOF_PACK_FORWARD = 0, LOF_PACK_REVERSE = 1 } lof_pack_endian_t;            /* lo_pack.hpp:52 */
+
+/* LoF_packed_size (lo_pack.hpp:399): bytes of the packed buffer for `count` elements of an n-bit format; 0 if n is
+ * outside [1, 16].  Host-only helper. */
+LOF_API uint64_t lof_packed_size(int bitwidth, uint64_t count);
+/* replaces LoF_encode_cuda<E>(d_dst, d_src, params, count, ps, stream) (lo_pack.hpp:499-513).  Stochastic modes draw
+ * the event word of global element first_index + i (same stream definition as lof_round_params). */
+LOF_API int lof_encode_f32(const float* src, uint8_t* dst, int64_t count, const lof_codec_format_t* fmt,
+                           const lof_projspec_t* ps, int endian, const lof_rng_t* rng, uint64_t first_index, void* stream);
+/* replaces LoF_decode_cuda<E>(d_dst, d_src, params, count, stream) (lo_pack.hpp:516-529) */
+LOF_API int lof_decode_f32(const uint8_t* src, float* dst, int64_t count, const lof_codec_format_t* fmt, int endian,
+                           void* stream);
+
+/* Chunked tensor-core GEMM on operands that are ALREADY stored as 8-bit representations (what lof_encode_f32
+ * produces for e4m3fn / e5m2): A is M x K bytes row-major, Bt is N x K bytes row-major (B transposed, K-major --
+ * the [out_features, in_features] weight layout of LoF_Linear, LoFloat/layers.py:160-161).  operand_dtype is
+ * LOF_E4M3 or LOF_E5M2.  Same accumulator semantics, flags and status word as lof_gemm_chunked_f32; no conversion
+ * pass and no workspace for the operands.  K must be a multiple of 16. */
+LOF_API int lof_gemm_chunked_packed(const uint8_t* A, const uint8_t* Bt, float* C, int64_t M, int64_t N, int64_t K,
+                                    int accum_mant_bits, const lof_format_t* acc_fmt, const lof_projspec_t* ps,
+                                    int64_t k_chunk, float alpha, int operand_dtype, uint32_t flags, int32_t* dev_status,
+                                    void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Host-buffer entry points: what a binding calls when the tensor lives in host memory.
  * The library stages through device memory in chunks and overlaps H2D, kernel and D2H on
  * three streams; it blocks until `out_host` is complete.  Pinned host buffers give full

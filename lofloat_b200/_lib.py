@@ -26,7 +26,9 @@ ABI_SYMBOLS = (
     "lof_round_params_host", "lof_round_mantissa_host", "lof_mx_round_f32_host",
     "lof_abi_version", "lof_status_string", "lof_last_error_string", "lof_kernel_launch_count",
     "lof_mx_priv_max_normal", "lof_set_option", "lof_get_option", "lof_selftest_mx_division",
+    "lof_packed_size", "lof_encode_f32", "lof_decode_f32", "lof_gemm_chunked_packed",
 )
+LOF_PACK_FORWARD, LOF_PACK_REVERSE = 0, 1
 
 
 class CFormat(C.Structure):
@@ -34,6 +36,13 @@ class CFormat(C.Structure):
     _fields_ = [("bitwidth", C.c_int32), ("mantissa_bits", C.c_int32), ("bias", C.c_int32),
                 ("ov_behavior", C.c_int32), ("na_behavior", C.c_int32), ("is_signed", C.c_int32),
                 ("unsigned_behavior", C.c_int32)]
+
+
+class CCodecFormat(C.Structure):
+    """lof_codec_format_t"""
+    _fields_ = [("fmt", CFormat), ("inf_mask", C.c_uint32), ("inf_value", C.c_uint32), ("nan_mask", C.c_uint32),
+                ("nan_value", C.c_uint32), ("nan_mant_mask", C.c_uint32), ("min_pos_inf", C.c_uint32),
+                ("qnan", C.c_uint32), ("snan", C.c_uint32)]
 
 
 class CProjSpec(C.Structure):
@@ -79,6 +88,15 @@ def _declare(lib):
     lib.lof_mx_priv_max_normal.restype = f32
     lib.lof_selftest_mx_division.argtypes = [PF, C.POINTER(u64), vp]
     lib.lof_selftest_mx_division.restype = i32
+    PC = C.POINTER(CCodecFormat)
+    lib.lof_packed_size.argtypes = [i32, u64]
+    lib.lof_packed_size.restype = u64
+    lib.lof_encode_f32.argtypes = [vp, vp, i64, PC, PP, i32, PR, u64, vp]
+    lib.lof_encode_f32.restype = i32
+    lib.lof_decode_f32.argtypes = [vp, vp, i64, PC, i32, vp]
+    lib.lof_decode_f32.restype = i32
+    lib.lof_gemm_chunked_packed.argtypes = [vp, vp, vp, i64, i64, i64, i32, PF, PP, i64, f32, i32, C.c_uint32, vp, vp]
+    lib.lof_gemm_chunked_packed.restype = i32
     lib.lof_set_option.argtypes = [C.c_char_p, i64]
     lib.lof_set_option.restype = i32
     lib.lof_get_option.argtypes = [C.c_char_p, C.POINTER(i64)]

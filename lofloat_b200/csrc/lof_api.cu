@@ -13,7 +13,9 @@
 #include <string>
 
 #include "lof_core.cuh"
+#include "lof_gemm_common.cuh"
 #include "lof_mx_kernels.cuh"
+#include "lof_pack.cuh"
 #include "lof_round_kernels.cuh"
 
 namespace lof {
@@ -583,6 +585,113 @@ int lof_gemm_chunked_f32(const float* A, const float* B, float* C, int64_t M, in
     g_launches.fetch_add((uint64_t)launches);
     if (!err.empty()) return fail(LOF_ERR_UNSUPPORTED, err);
     if (e != cudaSuccess) return cuda_fail(e, "lof_gemm_chunked launch");
+    return LOF_OK;
+}
+
+int lof_gemm_chunked_packed(const uint8_t* A, const uint8_t* Bt, float* C, int64_t M, int64_t N, int64_t K,
+                            int accum_mant_bits, const lof_format_t* acc_fmt, const lof_projspec_t* ps, int64_t k_chunk,
+                            float alpha, int operand_dtype, uint32_t flags, int32_t* dev_status, void* stream)
+{
+    if (operand_dtype != LOF_E4M3 && operand_dtype != LOF_E5M2)
+        return fail(LOF_ERR_INVALID_ARG, "lof_gemm_chunked_packed: operand_dtype must be LOF_E4M3 or LOF_E5M2");
+    if (flags & LOF_GEMM_INTERNAL_PACKED_OPERANDS) return fail(LOF_ERR_INVALID_ARG, "unknown flag");
+    return lof_gemm_chunked_f32(reinterpret_cast<const float*>(A), reinterpret_cast<const float*>(Bt), C, M, N, K, accum_mant_bits,
+                                acc_fmt, ps, k_chunk, alpha, operand_dtype, flags | LOF_GEMM_INTERNAL_PACKED_OPERANDS, dev_status, stream);
+}
+
+// ---------------------------------------------------------------------------------------
+// storage codec (lo_pack.hpp)
+// ---------------------------------------------------------------------------------------
+namespace {
+int pack_gcd(int a, int b) { return b == 0 ? a : pack_gcd(b, a % b); }
+int pack_group_bits(int n) { const int al = n <= 8 ? 8 : 16; return (n / pack_gcd(n, al)) * al; }     // lo_pack.hpp:58-67
+
+int make_codec_plan(const lof_codec_format_t* cf, const lof_projspec_t* ps, int endian, CodecPlan* p)
+{
+    if (!cf) return fail(LOF_ERR_INVALID_ARG, "codec format is NULL");
+    const lof_format_t& f = cf->fmt;
+    if (f.bitwidth < 1 || f.bitwidth > 16) return fail(LOF_ERR_INVALID_ARG, "codec: bitwidth must be in [1, 16] (lo_pack.hpp)");
+    if (f.is_signed != LOF_Signed && f.is_signed != LOF_Unsigned) return fail(LOF_ERR_INVALID_ARG, "codec: bad signedness");
+    const int to_signed = f.is_signed == LOF_Signed;
+    const int ebits = f.bitwidth - f.mantissa_bits - (to_signed ? 1 : 0);
+    if (f.mantissa_bits < 0 || ebits < 0 || ebits > 30) return fail(LOF_ERR_INVALID_ARG, "codec: malformed format");
+    if (endian != LOF_PACK_FORWARD && endian != LOF_PACK_REVERSE) return fail(LOF_ERR_INVALID_ARG, "codec: bad endian");
+    std::memset(p, 0, sizeof *p);
+    const int n = f.bitwidth;
+    p->n = n; p->mant = f.mantissa_bits; p->bias = f.bias; p->to_signed = to_signed;
+    p->exp_offset = f.bias - 127;
+    p->digit_drop = 23 - f.mantissa_bits;
+    p->to_min_exp = 1 - f.bias;
+    const int to_max_exp = (1 << ebits) - 1 - f.bias, to_digits = f.mantissa_bits + 1;
+    p->narrower = (to_max_exp < 128) || (to_max_exp == 128 && to_digits < 24);
+    p->has_inf = f.ov_behavior != LOF_Saturating;
+    p->signmask = to_signed ? (1u << (n - 1)) : 0u;
+    p->rep_mask = (1u << n) - 1u;
+    p->inf_mask = cf->inf_mask; p->inf_value = cf->inf_value;
+    p->nan_mask = cf->nan_mask; p->nan_value = cf->nan_value; p->nan_mant_mask = cf->nan_mant_mask;
+    p->sign_is_nan = (p->signmask & cf->nan_mask) == cf->nan_value && (cf->nan_mant_mask == 0u || (p->signmask & cf->nan_mant_mask) != 0u);
+    p->max_finite_rep = p->has_inf ? (cf->min_pos_inf - 1u) : (to_signed ? (((1u << n) - 1u) >> 1) : ((1u << n) - 1u));
+    const uint32_t inf_rep = p->has_inf ? cf->min_pos_inf : p->max_finite_rep;
+    const int sat = ps ? ps->saturation_mode : LOF_OvfInf;
+    p->inf_in_rep = (sat != LOF_SatFinite && p->has_inf) ? inf_rep : p->max_finite_rep;
+    p->ovf_rep = (sat == LOF_OvfInf && p->has_inf) ? inf_rep : p->max_finite_rep;
+    p->neg_unsigned_rep = (f.unsigned_behavior == LOF_NegtoZero) ? 0u : (f.na_behavior == LOF_NaN_3109 ? cf->qnan : cf->snan);
+    p->qnan = cf->qnan;
+    p->len = ps ? ps->stoch_length : 0;
+    p->gc = pack_group_bits(n) / n;
+    p->reverse = endian == LOF_PACK_REVERSE;
+    return LOF_OK;
+}
+}  // namespace
+
+uint64_t lof_packed_size(int bitwidth, uint64_t count)
+{
+    if (bitwidth < 1 || bitwidth > 16) return 0;
+    const uint64_t gc = (uint64_t)(pack_group_bits(bitwidth) / bitwidth), gb = (uint64_t)(pack_group_bits(bitwidth) / 8);
+    return ((count + gc - 1) / gc) * gb;
+}
+
+int lof_encode_f32(const float* src, uint8_t* dst, int64_t count, const lof_codec_format_t* fmt, const lof_projspec_t* ps,
+                   int endian, const lof_rng_t* rng, uint64_t first_index, void* stream)
+{
+    if (count < 0) return fail(LOF_ERR_INVALID_ARG, "count < 0");
+    if (!ps) return fail(LOF_ERR_INVALID_ARG, "projspec is NULL");
+    const int mode = ps->rounding_mode;
+    if (mode < 0 || mode >= LOF_NUM_ROUNDING_MODES) return fail(LOF_ERR_INVALID_ARG, "unknown rounding mode");
+    CodecPlan p;
+    const int st = make_codec_plan(fmt, ps, endian, &p);
+    if (st != LOF_OK) return st;
+    if (mode == LOF_StochasticRoundingA || mode == LOF_StochasticRoundingB || mode == LOF_StochasticRoundingC ||
+        mode == LOF_StochasticRoundingD) {
+        // the reference shifts by (roundoff - len); roundoff >= 23 - mantissa_bits on every path
+        if (ps->stoch_length < 0 || ps->stoch_length > p.digit_drop || ps->stoch_length > 31)
+            return fail(LOF_ERR_INVALID_ARG, "stoch_length must be in [0, 23 - mantissa_bits]");
+    }
+    if (count == 0) return LOF_OK;
+    if (!src || !dst) return fail(LOF_ERR_INVALID_ARG, "null tensor pointer");
+    const int sms = num_sms();
+    if (sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    const RngArgs ra = make_rng(rng, kStreamElem, mode, ps->stoch_length);
+    cudaError_t e = launch_encode(mode, src, dst, count, lof_packed_size(p.n, (uint64_t)count), p, ra, first_index, sms,
+                                  static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "lof_encode launch");
+    g_launches.fetch_add(1);
+    return LOF_OK;
+}
+
+int lof_decode_f32(const uint8_t* src, float* dst, int64_t count, const lof_codec_format_t* fmt, int endian, void* stream)
+{
+    if (count < 0) return fail(LOF_ERR_INVALID_ARG, "count < 0");
+    CodecPlan p;
+    const int st = make_codec_plan(fmt, nullptr, endian, &p);
+    if (st != LOF_OK) return st;
+    if (count == 0) return LOF_OK;
+    if (!src || !dst) return fail(LOF_ERR_INVALID_ARG, "null tensor pointer");
+    const int sms = num_sms();
+    if (sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    cudaError_t e = launch_decode(src, dst, count, lof_packed_size(p.n, (uint64_t)count), p, sms, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "lof_decode launch");
+    g_launches.fetch_add(1);
     return LOF_OK;
 }
 

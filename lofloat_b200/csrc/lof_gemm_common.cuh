@@ -5,6 +5,9 @@
 
 namespace lof {
 
+// internal flag of launch_gemm_tc (not part of the public flag set): A / B are 8-bit representations, B is K-major
+constexpr uint32_t LOF_GEMM_INTERNAL_PACKED_OPERANDS = 0x80000000u;
+
 // round-to-odd fused multiply-add, bit-identical to the host routine
 // lof_round_to_odd_fma (blis_lof_gemm.hpp:63-99): RN result when it is exact or
 // non-finite, otherwise the neighbour (of the exact value) with an odd mantissa LSB.

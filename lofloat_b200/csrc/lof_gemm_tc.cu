@@ -565,8 +565,16 @@ cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, 
     if (M > (1 << 24) || N > (1 << 24) || K > (1ll << 30)) { *err = "chunked GEMM: dimension too large"; return cudaSuccess; }
     if (mode_uses_rng(mode)) { *err = "chunked GEMM: stochastic accumulator rounding is not implemented"; return cudaSuccess; }
 
+    // operands already stored as 8-bit representations (lof_gemm_chunked_packed): A = M x K bytes, B = Bt = N x K bytes
+    const bool packed_in = (flags & LOF_GEMM_INTERNAL_PACKED_OPERANDS) != 0;
+    if (packed_in) {
+        if (op == kOpBF16) { *err = "chunked GEMM (packed operands): operand_dtype must be LOF_E4M3 or LOF_E5M2"; return cudaSuccess; }
+        if (((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15u) != 0) {
+            *err = "chunked GEMM (packed operands): A and Bt must be 16-byte aligned (TMA)"; return cudaSuccess;
+        }
+    }
     // workspace: operand copies + status word, stream-ordered
-    const size_t bytes_a = (size_t)M * K * esize, bytes_b = (size_t)N * K * esize;
+    const size_t bytes_a = packed_in ? 0 : (size_t)M * K * esize, bytes_b = packed_in ? 0 : (size_t)N * K * esize;
     const size_t off_b = (bytes_a + 1023) & ~size_t(1023), off_s = off_b + ((bytes_b + 1023) & ~size_t(1023));
     uint8_t* ws = nullptr;
     {   // keep freed workspace blocks cached in the device's default pool (the default threshold of 0 returns them
@@ -590,7 +598,7 @@ cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, 
 
     tc_clear_status_kernel<<<1, 1, 0, stream>>>(status);
     ++*launches;
-    {
+    if (!packed_in) {
         const int64_t na = M * K;
         const unsigned ga = (unsigned)std::min<int64_t>((na / 4 + 255) / 256 + 1, 148 * 16);
         const dim3 gb((unsigned)((N + 63) / 64), (unsigned)((K + (128 / esize) - 1) / (128 / esize)));
@@ -614,7 +622,9 @@ cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, 
     }
 
     CUtensorMap ma, mb;
-    if (!make_operand_map(&ma, ws, M, K * esize) || !make_operand_map(&mb, ws + off_b, N, K * esize)) {
+    const void* opa = packed_in ? static_cast<const void*>(A) : static_cast<const void*>(ws);
+    const void* opb = packed_in ? static_cast<const void*>(B) : static_cast<const void*>(ws + off_b);
+    if (!make_operand_map(&ma, opa, M, K * esize) || !make_operand_map(&mb, opb, N, K * esize)) {
         cudaFreeAsync(ws, stream);
         *err = "chunked GEMM: cuTensorMapEncodeTiled failed";
         return cudaSuccess;

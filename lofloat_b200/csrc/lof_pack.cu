@@ -1,0 +1,265 @@
+// lof_pack.cu -- low-bit storage codec for sm_100a: fp32 -> packed n-bit representations and back.
+//
+// Replaces the reference's one-thread-per-group kernels (/root/reference/src/lo_pack.hpp:474-529,
+// encode_float_kernel / decode_float_kernel: 64-float local arrays, bit-at-a-time put_bits / get_bits, scalar
+// uncoalesced loads).  Semantics are those of lo_pack.hpp:
+//   convert_float_to_rep   (:109-267)  runtime twin of ConvertImpl<float, Templated_Float<Fp>>::run(): strict typed
+//                                       conversion honouring Saturation_Mode, the Inf / NaN checkers, signedness;
+//   convert_rep_to_float   (:277-319)
+//   group packing          (:58-102)   n in [1,16]; a group of lcm(n, 8 or 16) bits, LSB-first, Forward / Reverse slots.
+// HBM-bound streaming op: 4 B read + n/8 B written per element (encode), the reverse for decode.  Data path per CTA
+// tile of 4096 elements: coalesced 128-bit loads -> rep per element in registers -> 16-bit reps staged in shared
+// memory -> every thread assembles whole 32-bit words of the packed stream (any n, either slot order) -> coalesced
+// 32-bit stores.  The bit position of slot s is s * n in BOTH slot orders (groups tile the stream exactly), so the
+// packed stream is a plain LSB-first bit stream and only the slot -> element map depends on the order.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lof_core.cuh"
+#include "lof_pack.cuh"
+
+namespace lof {
+
+namespace {
+
+constexpr int kPackThreads = 256;
+constexpr int kPackPerThread = 16;
+constexpr int kPackTile = kPackThreads * kPackPerThread;     // 4096 elements: a multiple of every group count (1..16)
+
+__device__ __forceinline__ bool codec_is_nan(const CodecPlan& p, uint32_t rep)
+{
+    return (rep & p.nan_mask) == p.nan_value && (p.nan_mant_mask == 0u || (rep & p.nan_mant_mask) != 0u);
+}
+__device__ __forceinline__ uint32_t with_sign(const CodecPlan& p, uint32_t mag, bool neg)     // lo_pack.hpp:147-152
+{
+    if (!neg || !p.to_signed) return mag;
+    if (mag == 0u && p.sign_is_nan) return 0u;
+    return mag | p.signmask;
+}
+
+// lo_pack.hpp:109-267.  Every RoundMantissa call there leaves `pos` at its default (false), lo_float.h:1232.
+template <int MODE>
+__device__ __forceinline__ uint32_t float_to_rep(uint32_t fb, const CodecPlan& p, uint32_t w)
+{
+    const bool neg = (fb >> 31) != 0;
+    if (!p.to_signed && neg) return p.neg_unsigned_rep;                                        // :156-161
+    const uint32_t from_bits = fb & 0x7FFFFFFFu;
+    if (from_bits >= 0x7F800000u) {
+        if (from_bits > 0x7F800000u) return p.qnan;                                            // :170
+        return with_sign(p, p.inf_in_rep, neg);                                                // :165-169
+    }
+    if (from_bits == 0u) return with_sign(p, 0u, neg);
+    const int biased_from = (int)(from_bits >> 23);
+    const int ds = p.digit_drop;                                                               // -kDigitShift = 23 - m > 0
+
+    if (p.to_min_exp < -125 && biased_from == 0) {                                             // branch 1, :176-196
+        uint64_t bits = from_bits;
+        const int nf = __clz((int)from_bits) - (32 - 23) + 1;
+        const int be = p.exp_offset - nf + 1;
+        if (be <= 0) {
+            if (p.exp_offset < 64) bits <<= p.exp_offset;
+        } else {
+            bits <<= nf;
+            bits &= ~(1ull << 23);
+            bits |= (uint64_t)be << 23;
+        }
+        bits = round_bits<MODE, uint64_t>(bits, ds, p.len, false, w) >> ds;
+        return with_sign(p, (uint32_t)bits, neg);
+    }
+    if (p.to_min_exp > -125) {                                                                 // branch 2, :199-243
+        const int biased_to = biased_from - 127 + p.bias;
+        if (biased_to <= 0) {
+            const uint32_t lead = biased_from > 0 ? 1u : 0u;
+            const int sh = ds - biased_to + (int)lead;
+            const uint32_t sig = (from_bits & 0x007FFFFFu) | (lead << 23);
+            uint32_t bits;
+            if (sh <= 24) {
+                bits = round_bits<MODE, uint32_t>(sig, sh, p.len, false, w) >> sh;
+            } else if constexpr (MODE == LOF_RoundToOdd || MODE == LOF_RoundAwayFromZero) {
+                bits = sig > 0u ? 1u : 0u;
+            } else if constexpr (MODE == LOF_RoundUp) {
+                bits = (sig != 0u && !neg) ? 1u : 0u;
+            } else if constexpr (MODE == LOF_RoundDown) {
+                bits = (sig != 0u && neg) ? 1u : 0u;
+            } else if constexpr (ModeTraits<MODE>::kUsesRng) {
+                bits = sh < 64 ? (uint32_t)(round_bits<MODE, uint64_t>((uint64_t)sig, sh, p.len, false, w) >> sh) : 0u;
+            } else {
+                bits = 0u;
+            }
+            return with_sign(p, bits, neg);
+        }
+    }
+    // normal path, :246-266
+    uint64_t rounded = round_bits<MODE, uint64_t>((uint64_t)from_bits, ds, p.len, false, w);
+    rounded &= ~((1ull << ds) - 1ull);
+    rounded += (uint64_t)(int64_t)p.exp_offset << 23;
+    if (p.narrower && rounded > ((uint64_t)p.max_finite_rep << ds)) return with_sign(p, p.ovf_rep, neg);
+    return with_sign(p, (uint32_t)(rounded >> ds), neg);
+}
+
+// lo_pack.hpp:277-319
+__device__ __forceinline__ float rep_to_float(uint32_t rep, const CodecPlan& p)
+{
+    rep &= p.rep_mask;
+    const bool sign = p.to_signed && ((rep >> (p.n - 1)) & 1u);
+    const uint32_t mag = p.to_signed ? (rep & (p.signmask - 1u)) : rep;
+    if (p.has_inf && (rep & p.inf_mask) == p.inf_value) return __uint_as_float(sign ? 0xFF800000u : 0x7F800000u);
+    if (codec_is_nan(p, rep)) return __uint_as_float(0x7FC00000u);
+    const uint32_t ef = mag >> p.mant, mf = mag & ((1u << p.mant) - 1u);
+    const uint32_t s = sign ? 0x80000000u : 0u;
+    if (ef == 0u) {
+        const int e = 1 - p.bias - p.mant;                    // value = mf * 2^e
+        if (e >= -126 && e <= 100) return __uint_as_float(__float_as_uint(__fmul_rn(__uint2float_rn(mf), __uint_as_float((uint32_t)(e + 127) << 23))) | s);
+        return (float)(sign ? -ldexp((double)mf, e) : ldexp((double)mf, e));
+    }
+    const int E = (int)ef - p.bias + 127;
+    if (E >= 1 && E <= 254) return __uint_as_float(s | ((uint32_t)E << 23) | (mf << (23 - p.mant)));
+    const double v = ldexp(1.0 + (double)mf / (double)(1u << p.mant), (int)ef - p.bias);
+    return (float)(sign ? -v : v);
+}
+
+__device__ __forceinline__ int slot_to_elem(int slot, int gc, int reverse)
+{
+    if (!reverse) return slot;
+    const int g = slot / gc, j = slot - g * gc;
+    return g * gc + (gc - 1 - j);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kPackThreads)
+encode_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int64_t count, uint64_t packed_bytes,
+              const CodecPlan p, const RngArgs rng, uint64_t first_index, int vec_ok, int word_ok)
+{
+    __shared__ uint16_t reps[kPackTile];
+    const int64_t ntiles = (count + kPackTile - 1) / kPackTile;
+    const int words_per_tile = kPackTile / 32 * p.n;          // 128 n
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t base = tile * kPackTile;
+        // ---- phase 1: one rep per element ----
+#pragma unroll
+        for (int u = 0; u < kPackPerThread / 4; ++u) {
+            const int local = (u * kPackThreads + (int)threadIdx.x) * 4;
+            const int64_t i = base + local;
+            uint32_t x[4] = {0u, 0u, 0u, 0u};
+            if (vec_ok && i + 3 < count) {
+                const uint4 v = __ldcs(reinterpret_cast<const uint4*>(src + i));
+                x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (i + e < count) x[e] = __float_as_uint(src[i + e]);
+            }
+            uint32_t r[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                uint32_t w = 0u;
+                if constexpr (ModeTraits<MODE>::kUsesRng) w = philox_event(rng, first_index + (uint64_t)(i + e));
+                r[e] = (i + e < count) ? float_to_rep<MODE>(x[e], p, w) : 0u;        // partial group: encode(0.0f) == 0 (:425-429)
+            }
+            *reinterpret_cast<uint2*>(&reps[local]) = make_uint2((r[0] & 0xFFFFu) | (r[1] << 16), (r[2] & 0xFFFFu) | (r[3] << 16));
+        }
+        __syncthreads();
+        // ---- phase 2: whole 32-bit words of the packed stream ----
+        const uint64_t tile_byte = (uint64_t)tile * (uint64_t)words_per_tile * 4u;
+        for (int k = threadIdx.x; k < words_per_tile; k += kPackThreads) {
+            const uint64_t byte = tile_byte + (uint64_t)k * 4u;
+            if (byte >= packed_bytes) break;
+            const int bit0 = k * 32;
+            uint32_t word = 0u;
+            for (int slot = bit0 / p.n; slot * p.n < bit0 + 32; ++slot) {
+                const uint32_t rep = reps[slot_to_elem(slot, p.gc, p.reverse)] & p.rep_mask;
+                const int sh = slot * p.n - bit0;
+                word |= sh >= 0 ? (rep << sh) : (rep >> (-sh));
+            }
+            if (word_ok && byte + 4u <= packed_bytes) {
+                __stcs(reinterpret_cast<uint32_t*>(dst + byte), word);
+            } else {
+                for (int b = 0; b < 4 && byte + (uint64_t)b < packed_bytes; ++b) dst[byte + b] = (uint8_t)(word >> (8 * b));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kPackThreads)
+decode_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int64_t count, uint64_t packed_bytes,
+              const CodecPlan p, int vec_ok, int word_ok)
+{
+    __shared__ uint32_t words[kPackTile / 32 * 16 + 1];
+    const int64_t ntiles = (count + kPackTile - 1) / kPackTile;
+    const int words_per_tile = kPackTile / 32 * p.n;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t base = tile * kPackTile;
+        const uint64_t tile_byte = (uint64_t)tile * (uint64_t)words_per_tile * 4u;
+        for (int k = threadIdx.x; k <= words_per_tile; k += kPackThreads) {
+            const uint64_t byte = tile_byte + (uint64_t)k * 4u;
+            uint32_t wv = 0u;
+            if (k < words_per_tile && byte < packed_bytes) {
+                if (word_ok && byte + 4u <= packed_bytes) wv = __ldcs(reinterpret_cast<const uint32_t*>(src + byte));
+                else for (int b = 0; b < 4 && byte + (uint64_t)b < packed_bytes; ++b) wv |= (uint32_t)src[byte + b] << (8 * b);
+            }
+            words[k] = wv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < kPackPerThread / 4; ++u) {
+            const int local = (u * kPackThreads + (int)threadIdx.x) * 4;
+            const int64_t i = base + local;
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int el = local + e;
+                const int slot = slot_to_elem(el, p.gc, p.reverse);          // the slot <-> element map is an involution
+                const int bit = slot * p.n;
+                const uint64_t two = (uint64_t)words[bit >> 5] | ((uint64_t)words[(bit >> 5) + 1] << 32);
+                o[e] = rep_to_float((uint32_t)(two >> (bit & 31)) & p.rep_mask, p);
+            }
+            if (vec_ok && i + 3 < count) {
+                __stcs(reinterpret_cast<float4*>(dst + i), make_float4(o[0], o[1], o[2], o[3]));
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (i + e < count) dst[i + e] = o[e];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+unsigned pack_grid(int64_t count, int num_sms)
+{
+    const int64_t ntiles = (count + kPackTile - 1) / kPackTile;
+    const int64_t cap = (int64_t)num_sms * 8;
+    return (unsigned)(ntiles < 1 ? 1 : ntiles < cap ? ntiles : cap);
+}
+
+}  // namespace
+
+cudaError_t launch_encode(int mode, const float* src, uint8_t* dst, int64_t count, uint64_t packed_bytes, const CodecPlan& p,
+                          const RngArgs& rng, uint64_t first_index, int num_sms, cudaStream_t stream)
+{
+    const int vec_ok = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+    const int word_ok = (reinterpret_cast<uintptr_t>(dst) & 3u) == 0;
+    const unsigned grid = pack_grid(count, num_sms);
+    switch (mode) {
+#define LOF_CASE(M) case M: encode_kernel<M><<<grid, kPackThreads, 0, stream>>>(src, dst, count, packed_bytes, p, rng, first_index, vec_ok, word_ok); break;
+        LOF_CASE(LOF_RoundToNearestEven) LOF_CASE(LOF_RoundTowardsZero) LOF_CASE(LOF_RoundAwayFromZero)
+        LOF_CASE(LOF_StochasticRoundingA) LOF_CASE(LOF_RoundToNearestOdd) LOF_CASE(LOF_RoundDown)
+        LOF_CASE(LOF_RoundUp) LOF_CASE(LOF_RoundTiesToAway) LOF_CASE(LOF_StochasticRoundingB)
+        LOF_CASE(LOF_StochasticRoundingC) LOF_CASE(LOF_True_StochasticRounding)
+        LOF_CASE(LOF_ProbabilisticRounding) LOF_CASE(LOF_RoundToOdd) LOF_CASE(LOF_RoundTiesTowardsZero)
+        LOF_CASE(LOF_StochasticRoundingD)
+#undef LOF_CASE
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decode(const uint8_t* src, float* dst, int64_t count, uint64_t packed_bytes, const CodecPlan& p, int num_sms,
+                          cudaStream_t stream)
+{
+    const int vec_ok = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
+    const int word_ok = (reinterpret_cast<uintptr_t>(src) & 3u) == 0;
+    decode_kernel<<<pack_grid(count, num_sms), kPackThreads, 0, stream>>>(src, dst, count, packed_bytes, p, vec_ok, word_ok);
+    return cudaGetLastError();
+}
+
+}  // namespace lof

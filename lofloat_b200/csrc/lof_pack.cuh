@@ -1,0 +1,37 @@
+// lof_pack.cuh -- per-launch constants of the storage codec (lof_pack.cu) and its launchers.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lof_core.cuh"
+
+namespace lof {
+
+// FloatingPointParams + ProjSpec folded once per call (lo_pack.hpp:121-145 evaluates these per element)
+struct CodecPlan {
+    int32_t n, mant, bias;          // bitwidth, mantissa bits, exponent bias
+    int32_t to_signed;
+    int32_t exp_offset;             // kExponentOffset = bias - 127
+    int32_t digit_drop;             // -kDigitShift = 23 - mant  (> 0: formats of <= 16 bits)
+    int32_t to_min_exp;             // 1 - bias
+    int32_t narrower;               // pair(toMaxExp, toDigits) < pair(128, 24)
+    int32_t has_inf;                // OV_behavior != Saturating
+    int32_t sign_is_nan;            // IsNaN(sign bit only): the format has no -0
+    int32_t len;                    // stoch_length
+    int32_t gc, reverse;            // group count, PackEndian::Reverse
+    uint32_t signmask, rep_mask;
+    uint32_t max_finite_rep;
+    uint32_t inf_in_rep;            // what +-inf encodes to   (lo_pack.hpp:165-169)
+    uint32_t ovf_rep;               // what an overflow encodes to (:261-264)
+    uint32_t neg_unsigned_rep;      // negative input, unsigned format (:156-161)
+    uint32_t qnan;
+    uint32_t inf_mask, inf_value, nan_mask, nan_value, nan_mant_mask;
+};
+
+cudaError_t launch_encode(int mode, const float* src, uint8_t* dst, int64_t count, uint64_t packed_bytes, const CodecPlan& p,
+                          const RngArgs& rng, uint64_t first_index, int num_sms, cudaStream_t stream);
+cudaError_t launch_decode(const uint8_t* src, float* dst, int64_t count, uint64_t packed_bytes, const CodecPlan& p, int num_sms,
+                          cudaStream_t stream);
+
+}  // namespace lof

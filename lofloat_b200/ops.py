@@ -55,6 +55,17 @@ class NaNBehavior(enum.IntEnum):
     _754 = 1
 
 
+class SaturationMode(enum.IntEnum):      # lo_float::Saturation_Mode (fp_tools.hpp:38-41); read by the storage codec only
+    OvfInf = 0
+    SatFinite = 1
+    SatPropagate = 2
+
+
+class PackEndian(enum.IntEnum):          # lo_float::PackEndian (lo_pack.hpp:52)
+    Forward = 0
+    Reverse = 1
+
+
 # pybind's .export_values(): the enumerators are also module attributes
 globals().update({m.name: m for e in (RoundingMode, Signedness, InfBehavior) for m in e})
 
@@ -321,3 +332,144 @@ def lof_gemm(A: torch.Tensor, B: torch.Tensor, accum_mant_bits: int, round_mode=
 
 
 lof_gemm.last_status = 0
+
+
+# --------------------------------------------------------------------------------------
+# Low-bit storage codec: host mirror of LoF_encode_cuda / LoF_decode_cuda (lo_pack.hpp:499-529; the reference
+# has no Python binding for them yet -- "trivial to bind to Python later", lo_pack.hpp:17 -- so the names
+# follow the C++ API).
+# --------------------------------------------------------------------------------------
+def _fit_checker(pred, n: int, what: str):
+    """Express a checker callable over n-bit representations as (mask, value, mant_mask):
+    pred(rep) == ((rep & mask) == value and (mant_mask == 0 or (rep & mant_mask) != 0))."""
+    full = (1 << n) - 1
+    S = [r for r in range(1 << n) if pred(r)]
+    if not S:
+        return 0, 1, 0
+    and_all, or_all = full, 0
+    for r in S:
+        and_all &= r
+        or_all |= r
+    mask = ~(and_all ^ or_all) & full
+    value = and_all & mask
+    free = full & ~mask
+    if len(S) == 1 << bin(free).count("1"):
+        return mask, value, 0
+    Sset = set(S)
+    excluded_or = 0
+    for r in range(1 << n):
+        if (r & mask) == value and r not in Sset:
+            excluded_or |= r
+    mant_mask = free & ~excluded_or
+    ok = mant_mask != 0 and all(((r & mask) == value and (r & mant_mask) != 0) == (r in Sset) for r in range(1 << n))
+    if not ok:
+        raise ValueError(f"{what} is not expressible as (rep & mask) == value [and (rep & mant_mask) != 0]")
+    return mask, value, mant_mask
+
+
+_codec_cache: dict = {}
+
+
+def codec_format(params: FloatFormatDescriptor, unsigned_behavior: int = 0) -> "_lib.CCodecFormat":
+    """lof_codec_format_t of a descriptor: the Inf / NaN checker callables are evaluated over every n-bit
+    representation once (n <= 16) and folded into masks."""
+    key = (id(params), int(unsigned_behavior))
+    hit = _codec_cache.get(key)
+    if hit is not None and hit[0] is params:
+        return hit[1]
+    n = params.total_bits
+    if not 1 <= n <= 16:
+        raise ValueError("storage codec: total_bits must be in [1, 16]")
+    inf_m, inf_v, inf_mm = _fit_checker(params.is_inf_checker, n, "is_inf_checker")
+    if inf_mm:
+        raise ValueError("is_inf_checker is not expressible as (rep & mask) == value")
+    nan_m, nan_v, nan_mm = _fit_checker(params.is_nan_checker, n, "is_nan_checker")
+    q = params.is_nan_checker.qNanBitPattern() if hasattr(params.is_nan_checker, "qNanBitPattern") else params.is_nan_checker.sNanBitPattern()
+    s_ = params.is_nan_checker.sNanBitPattern() if hasattr(params.is_nan_checker, "sNanBitPattern") else q
+    f = params._c()
+    f.unsigned_behavior = int(unsigned_behavior)
+    cf = _lib.CCodecFormat(f, inf_m, inf_v, nan_m, nan_v, nan_mm, int(params.is_inf_checker.minPosInf()) & 0xFFFFFFFF,
+                           int(q) & 0xFFFFFFFF, int(s_) & 0xFFFFFFFF)
+    _codec_cache[key] = (params, cf)
+    return cf
+
+
+def packed_size(total_bits: int, count: int) -> int:
+    """LoF_packed_size (lo_pack.hpp:399)."""
+    return int(_lib.lib().lof_packed_size(int(total_bits), int(count)))
+
+
+def lof_encode(input: torch.Tensor, params: FloatFormatDescriptor, round_mode=RoundingMode.RoundToNearestEven,
+               stoch_len: int = 0, saturation_mode=SaturationMode.OvfInf, endian=PackEndian.Forward, *,
+               unsigned_behavior: int = 0, rng=None, first_index: int = 0) -> torch.Tensor:
+    """float32 CUDA tensor -> packed uint8 tensor of packed_size(bits, numel) bytes (LoF_encode_cuda, lo_pack.hpp:499)."""
+    if input.dtype != torch.float32:
+        raise RuntimeError("lof_encode: float32 tensors only")
+    if not input.is_cuda:
+        raise RuntimeError("lof_encode requires a CUDA tensor")
+    L = _lib.lib()
+    mode = RoundingMode(int(round_mode))
+    ps = CProjSpec(int(mode), int(saturation_mode), int(stoch_len))
+    r = _next_rng(mode in _STOCHASTIC, rng)
+    cf = codec_format(params, unsigned_behavior)
+    x = input.contiguous()
+    out = torch.empty(packed_size(params.total_bits, x.numel()), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        st = L.lof_encode_f32(x.data_ptr(), out.data_ptr(), x.numel(), C.byref(cf), C.byref(ps), int(endian), C.byref(r),
+                              int(first_index), _stream_ptr(x))
+    _lib.check(st, "lof_encode")
+    return out
+
+
+def lof_decode(packed: torch.Tensor, count: int, params: FloatFormatDescriptor, endian=PackEndian.Forward, *,
+               unsigned_behavior: int = 0) -> torch.Tensor:
+    """packed uint8 CUDA tensor -> `count` float32 values (LoF_decode_cuda, lo_pack.hpp:516)."""
+    if packed.dtype != torch.uint8:
+        raise RuntimeError("lof_decode: uint8 tensors only")
+    if not packed.is_cuda:
+        raise RuntimeError("lof_decode requires a CUDA tensor")
+    need = packed_size(params.total_bits, count)
+    if packed.numel() < need:
+        raise RuntimeError(f"lof_decode: packed buffer has {packed.numel()} bytes, {need} needed for {count} elements")
+    L = _lib.lib()
+    cf = codec_format(params, unsigned_behavior)
+    src = packed.contiguous()
+    out = torch.empty(int(count), dtype=torch.float32, device=packed.device)
+    with torch.cuda.device(packed.device):
+        st = L.lof_decode_f32(src.data_ptr(), out.data_ptr(), int(count), C.byref(cf), int(endian), _stream_ptr(src))
+    _lib.check(st, "lof_decode")
+    return out
+
+
+def lof_gemm_packed(A: torch.Tensor, Bt: torch.Tensor, accum_mant_bits: int, round_mode=RoundingMode.RoundToNearestEven,
+                    scale_a: float = 1.0, scale_b: float = 1.0, *, k_chunk: int = 32,
+                    accum_format: FloatFormatDescriptor | None = None, operand_dtype: str = "e4m3",
+                    partial_round: bool = False, allow_packed: bool = True, allow_hw_accum: bool = True,
+                    allow_pair: bool = True) -> torch.Tensor:
+    """Chunked tensor-core GEMM on operands already stored as OCP 8-bit representations (uint8): A is [M, K], Bt is
+    [N, K] (the [out_features, in_features] weight layout).  C = A @ Bt^T / (scale_a * scale_b), float32 [M, N]."""
+    if A.dtype != torch.uint8 or Bt.dtype != torch.uint8 or A.dim() != 2 or Bt.dim() != 2:
+        raise RuntimeError("lof_gemm_packed: A and Bt must be 2-D uint8 tensors")
+    if A.size(1) != Bt.size(1):
+        raise RuntimeError(f"lof_gemm_packed: A.cols ({A.size(1)}) != Bt.cols ({Bt.size(1)})")
+    if not (A.is_cuda and Bt.is_cuda):
+        raise RuntimeError("lof_gemm_packed requires CUDA tensors")
+    L = _lib.lib()
+    ps = CProjSpec(int(RoundingMode(int(round_mode))), 0, 0)
+    denom = float(scale_a) * float(scale_b)
+    alpha = 1.0 if denom == 0.0 else 1.0 / denom
+    A_c, B_c = A.contiguous(), Bt.contiguous()
+    M, K = A_c.shape
+    N = B_c.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    status = torch.zeros(1, dtype=torch.int32, device=A.device)
+    fmt = accum_format._c() if accum_format is not None else None
+    flags = ((_lib.LOF_GEMM_PARTIAL_ROUND if partial_round else 0) | (0 if allow_packed else _lib.LOF_GEMM_NO_PACKED) |
+             (0 if allow_hw_accum else _lib.LOF_GEMM_NO_HW_ACCUM) | (0 if allow_pair else _lib.LOF_GEMM_NO_PAIR))
+    with torch.cuda.device(A.device):
+        st = L.lof_gemm_chunked_packed(A_c.data_ptr(), B_c.data_ptr(), out.data_ptr(), M, N, K, int(accum_mant_bits),
+                                       C.byref(fmt) if fmt is not None else None, C.byref(ps), int(k_chunk), alpha,
+                                       _OPERAND_DTYPES[operand_dtype], flags, status.data_ptr(), _stream_ptr(A_c))
+    _lib.check(st, "lof_gemm_packed")
+    lof_gemm_packed.status = status
+    return out

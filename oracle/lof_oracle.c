@@ -555,6 +555,250 @@ void lofo_gemm_chunked_f32(const float* A, const float* B, float* C, int64_t M, 
     }
 }
 
+/* ------------------------------------------------------------------------------------
+ * Low-bit storage codec: lo_pack.hpp (runtime twin of ConvertImpl<float, Templated_Float<Fp>>::run()).
+ * ---------------------------------------------------------------------------------- */
+static inline int codec_is_inf(const lofo_codec_format* f, uint32_t rep) { return (rep & f->inf_mask) == f->inf_value; }
+static inline int codec_is_nan(const lofo_codec_format* f, uint32_t rep)
+{
+    return (rep & f->nan_mask) == f->nan_value && (f->nan_mant_mask == 0u || (rep & f->nan_mant_mask) != 0u);
+}
+
+/* lo_pack.hpp:147-152 with_sign(): the negate operator's guard (no representable -0 when sign-bit-only is NaN) */
+static inline uint32_t codec_with_sign(const lofo_codec_format* f, uint32_t mag, int neg, int to_signed, uint32_t signmask)
+{
+    if (!neg || !to_signed) return mag;
+    if (mag == 0u && codec_is_nan(f, signmask)) return 0u;
+    return mag | signmask;
+}
+
+/* lo_pack.hpp:109-267 convert_float_to_rep.  Every RoundMantissa call there omits `pos`, i.e. pos = false
+ * (lo_float.h:1232): RoundUp / RoundDown treat every value as negative -- reproduced. */
+uint32_t lofo_float_to_rep(float from, const lofo_codec_format* f, const lofo_projspec* ps, uint32_t w)
+{
+    const int mode = ps->rounding_mode, len = ps->stoch_length, sat_mode = ps->saturation_mode;
+    const int n = f->fmt.bitwidth, toMant = f->fmt.mantissa_bits;
+    const int to_signed = (f->fmt.is_signed == LOFO_SIGNED);
+    const int toExpBits = to_signed ? n - toMant - 1 : n - toMant;
+    const int toBias = f->fmt.bias;
+    const int kExponentOffset = toBias - 127;
+    const int kDigitShift = toMant - 23;
+    const int toMinExp = 1 - toBias;
+    const int toMaxExp = (1 << toExpBits) - 1 - toBias;
+    const int toDigits = toMant + 1;
+    const int has_inf = (f->fmt.ov_behavior != LOFO_SATURATING);
+    const uint32_t signmask = to_signed ? (1u << (n - 1)) : 0u;
+    const uint32_t maxFiniteRep = has_inf ? (f->min_pos_inf - 1u)
+                                          : (to_signed ? (((1u << n) - 1u) >> 1) : ((1u << n) - 1u));
+    const uint32_t infRep = has_inf ? f->min_pos_inf : maxFiniteRep;
+    const uint32_t fb = f2u(from);
+    const int neg = (fb >> 31) != 0;
+
+    if (!to_signed && neg) {                                       /* :156-161 */
+        if (f->fmt.unsigned_behavior == 0 /* NegtoZero */) return 0u;
+        if (f->fmt.na_behavior == 0 /* _3109 */) return f->qnan;
+        return f->snan;
+    }
+    const uint32_t from_bits = fb & 0x7FFFFFFFu;
+    if (from_bits == 0x7F800000u) {                                /* :165-169 */
+        if (sat_mode != LOFO_SAT_FINITE && has_inf) return codec_with_sign(f, infRep, neg, to_signed, signmask);
+        return codec_with_sign(f, maxFiniteRep, neg, to_signed, signmask);
+    }
+    if (from_bits > 0x7F800000u) return f->qnan;                   /* :170 */
+    if (from_bits == 0u) return codec_with_sign(f, 0u, neg, to_signed, signmask);
+    const int biased_from_exponent = (int)(from_bits >> 23);
+
+    if (toMinExp < -125) {                                         /* branch 1, :176-196 */
+        if (biased_from_exponent == 0) {
+            uint64_t bits = from_bits;
+            const int normalization_factor = __builtin_clz(from_bits) - (32 - 23) + 1;
+            const int biased_exponent = kExponentOffset - normalization_factor + 1;
+            if (biased_exponent <= 0) {
+                if (kExponentOffset < 64) bits <<= kExponentOffset;
+            } else {
+                bits <<= normalization_factor;
+                bits &= ~((uint64_t)1 << 23);
+                bits |= (uint64_t)biased_exponent << 23;
+            }
+            if (kDigitShift > 0) bits <<= kDigitShift;
+            else { bits = round_mantissa_b64(bits, -kDigitShift, mode, len, 0, w); bits >>= -kDigitShift; }
+            return codec_with_sign(f, (uint32_t)bits, neg, to_signed, signmask);
+        }
+    }
+    if (toMinExp > -125) {                                         /* branch 2, :199-243 */
+        const int unbiased_exponent = biased_from_exponent - 127;
+        const int biased_to_exponent = unbiased_exponent + toBias;
+        if (biased_to_exponent <= 0) {
+            const uint32_t lead = (biased_from_exponent > 0) ? 1u : 0u;
+            const int exponent_shift = -kDigitShift - biased_to_exponent + (int)lead;
+            uint32_t rounded = (from_bits & 0x007FFFFFu) | (lead << 23);
+            uint32_t bits = 0;
+            if (exponent_shift <= 23 + 1) {
+                rounded = round_mantissa_b32(rounded, exponent_shift, mode, len, 0, w);
+                bits = (exponent_shift >= 32) ? 0u : (rounded >> exponent_shift);
+            } else {
+                uint64_t wide = rounded;
+                switch (mode) {
+                case LOFO_RTO: case LOFO_RAZ: bits = rounded > 0u ? 1u : 0u; break;
+                case LOFO_RTZ: bits = 0u; break;
+                case LOFO_RU: bits = (rounded && !neg) ? 1u : 0u; break;      /* `rounded && !sign > 0` */
+                case LOFO_RD: bits = (rounded && neg) ? 1u : 0u; break;
+                case LOFO_SR_A: case LOFO_SR_B: case LOFO_SR_C: case LOFO_SR_D: case LOFO_TRUE_SR: case LOFO_PROB:
+                    /* the reference shifts a 64-bit word by exponent_shift, undefined for >= 64; defined here as 0 */
+                    if (exponent_shift < 64) { wide = round_mantissa_b64(wide, exponent_shift, mode, len, 0, w); bits = (uint32_t)(wide >> exponent_shift); }
+                    else bits = 0u;
+                    break;
+                default: bits = 0u; break;
+                }
+            }
+            return codec_with_sign(f, bits, neg, to_signed, signmask);
+        }
+    }
+    /* normal path, :246-266 */
+    uint64_t rounded = from_bits;
+    if (kDigitShift < 0) {
+        rounded = round_mantissa_b64(rounded, -kDigitShift, mode, len, 0, w);
+        rounded &= ~(((uint64_t)1 << (-kDigitShift)) - 1u);
+    }
+    rounded += (uint64_t)(int64_t)kExponentOffset << 23;          /* static_cast<WideBits>(int) sign-extends, then wraps */
+    uint32_t bits;
+    uint64_t aligned_highest = maxFiniteRep;
+    if (kDigitShift < 0) {
+        aligned_highest <<= -kDigitShift;
+        bits = (uint32_t)(rounded >> -kDigitShift);
+    } else {
+        rounded <<= kDigitShift;
+        bits = (uint32_t)rounded;
+    }
+    const int to_is_narrower = (toMaxExp < 128) || (toMaxExp == 128 && toDigits < 24);
+    if (to_is_narrower && rounded > aligned_highest) {
+        const int emit_inf = (sat_mode == LOFO_OVF_INF) && has_inf;
+        return codec_with_sign(f, emit_inf ? infRep : maxFiniteRep, neg, to_signed, signmask);
+    }
+    return codec_with_sign(f, bits, neg, to_signed, signmask);
+}
+
+/* lo_pack.hpp:277-319 convert_rep_to_float */
+float lofo_rep_to_float(uint32_t rep, const lofo_codec_format* f)
+{
+    const int n = f->fmt.bitwidth, mant = f->fmt.mantissa_bits, bias = f->fmt.bias;
+    const int is_signed = (f->fmt.is_signed == LOFO_SIGNED);
+    const int has_inf = (f->fmt.ov_behavior != LOFO_SATURATING);
+    rep &= (n >= 32) ? 0xFFFFFFFFu : ((1u << n) - 1u);
+    const int sign = is_signed ? (int)((rep >> (n - 1)) & 1u) : 0;
+    const uint32_t mag = is_signed ? (rep & ((1u << (n - 1)) - 1u)) : rep;
+    if (has_inf && codec_is_inf(f, rep)) return sign ? -INFINITY : INFINITY;
+    if (codec_is_nan(f, rep)) return u2f(0x7FC00000u);
+    const uint32_t exp_field = mag >> mant;
+    const uint32_t mant_field = mag & ((1u << mant) - 1u);
+    double val;
+    if (exp_field == 0) val = ldexp((double)mant_field, 1 - bias - mant);
+    else val = ldexp(1.0 + (double)mant_field / (double)(1u << mant), (int)exp_field - bias);
+    return (float)(sign ? -val : val);
+}
+
+void lofo_float_to_rep_array(const float* in, uint32_t* out, int64_t n, const lofo_codec_format* f, const lofo_projspec* ps,
+                             const lofo_rng* rng, uint64_t first_index)
+{
+    const int nbits = lofo_rand_bits_needed(ps->rounding_mode, ps->stoch_length);
+    for (int64_t i = 0; i < n; ++i) {
+        const uint32_t w = nbits ? lofo_rand_event(rng, first_index + (uint64_t)i, LOFO_STREAM_ELEM, nbits) : 0u;
+        out[i] = lofo_float_to_rep(in[i], f, ps, w);
+    }
+}
+void lofo_rep_to_float_array(const uint32_t* in, float* out, int64_t n, const lofo_codec_format* f)
+{
+    for (int64_t i = 0; i < n; ++i) out[i] = lofo_rep_to_float(in[i], f);
+}
+
+/* lo_pack.hpp:58-73 group geometry */
+static int pk_gcd(int a, int b) { return b == 0 ? a : pk_gcd(b, a % b); }
+static int pk_group_bits(int n) { const int al = n <= 8 ? 8 : 16; return (n / pk_gcd(n, al)) * al; }
+int lofo_pack_group_count(int n) { return pk_group_bits(n) / n; }
+int lofo_pack_group_bytes(int n) { return pk_group_bits(n) / 8; }
+uint64_t lofo_packed_size(int n, uint64_t count)
+{
+    const uint64_t gc = (uint64_t)lofo_pack_group_count(n);
+    return ((count + gc - 1) / gc) * (uint64_t)lofo_pack_group_bytes(n);
+}
+
+/* lo_pack.hpp:76-102 bit_offset / put_bits / get_bits (LSB-first within a byte) */
+static void pk_put(uint8_t* dst, int off, uint32_t v, int n)
+{
+    for (int b = 0; b < n; ++b) { const int pos = off + b; dst[pos >> 3] |= (uint8_t)(((v >> b) & 1u) << (pos & 7)); }
+}
+static uint32_t pk_get(const uint8_t* src, int off, int n)
+{
+    uint32_t v = 0;
+    for (int b = 0; b < n; ++b) { const int pos = off + b; v |= (uint32_t)((src[pos >> 3] >> (pos & 7)) & 1u) << b; }
+    return v;
+}
+static int pk_off(int i, int n, int gc, int endian) { return ((endian == LOFO_PACK_FORWARD) ? i : (gc - 1 - i)) * n; }
+
+uint64_t lofo_pack_reps(uint8_t* dst, const uint32_t* reps, uint64_t count, int n, int endian)
+{
+    const int gc = lofo_pack_group_count(n), gb = lofo_pack_group_bytes(n);
+    const uint32_t mask = (n >= 32) ? 0xFFFFFFFFu : ((1u << n) - 1u);
+    uint64_t written = 0;
+    for (uint64_t i = 0; i < count; i += (uint64_t)gc) {
+        uint8_t* d = dst + written;
+        memset(d, 0, (size_t)gb);
+        for (int j = 0; j < gc; ++j) {
+            const uint32_t r = (i + (uint64_t)j < count) ? (reps[i + j] & mask) : 0u;      /* partial group: zero padded (:409-411) */
+            pk_put(d, pk_off(j, n, gc, endian), r, n);
+        }
+        written += (uint64_t)gb;
+    }
+    return written;
+}
+
+uint64_t lofo_unpack_reps(uint32_t* reps, const uint8_t* src, uint64_t count, int n, int endian)
+{
+    const int gc = lofo_pack_group_count(n), gb = lofo_pack_group_bytes(n);
+    uint64_t consumed = 0;
+    for (uint64_t i = 0; i < count; i += (uint64_t)gc) {
+        for (int j = 0; j < gc && i + (uint64_t)j < count; ++j) reps[i + j] = pk_get(src + consumed, pk_off(j, n, gc, endian), n);
+        consumed += (uint64_t)gb;
+    }
+    return consumed;
+}
+
+uint64_t lofo_encode_f32(uint8_t* dst, const float* src, uint64_t count, const lofo_codec_format* f,
+                         const lofo_projspec* ps, int endian, const lofo_rng* rng, uint64_t first_index)
+{
+    const int n = f->fmt.bitwidth;
+    const int gc = lofo_pack_group_count(n), gb = lofo_pack_group_bytes(n);
+    const int nbits = lofo_rand_bits_needed(ps->rounding_mode, ps->stoch_length);
+    const int64_t groups = (int64_t)((count + (uint64_t)gc - 1) / (uint64_t)gc);
+#pragma omp parallel for schedule(static)
+    for (int64_t g = 0; g < groups; ++g) {
+        uint8_t* d = dst + (uint64_t)g * (uint64_t)gb;
+        memset(d, 0, (size_t)gb);
+        for (int j = 0; j < gc; ++j) {
+            const uint64_t i = (uint64_t)g * (uint64_t)gc + (uint64_t)j;
+            const float x = (i < count) ? src[i] : 0.0f;                                    /* :425-429 */
+            const uint32_t w = nbits ? lofo_rand_event(rng, first_index + i, LOFO_STREAM_ELEM, nbits) : 0u;
+            pk_put(d, pk_off(j, n, gc, endian), lofo_float_to_rep(x, f, ps, w), n);
+        }
+    }
+    return (uint64_t)groups * (uint64_t)gb;
+}
+
+uint64_t lofo_decode_f32(float* dst, const uint8_t* src, uint64_t count, const lofo_codec_format* f, int endian)
+{
+    const int n = f->fmt.bitwidth;
+    const int gc = lofo_pack_group_count(n), gb = lofo_pack_group_bytes(n);
+    const int64_t groups = (int64_t)((count + (uint64_t)gc - 1) / (uint64_t)gc);
+#pragma omp parallel for schedule(static)
+    for (int64_t g = 0; g < groups; ++g) {
+        for (int j = 0; j < gc; ++j) {
+            const uint64_t i = (uint64_t)g * (uint64_t)gc + (uint64_t)j;
+            if (i < count) dst[i] = lofo_rep_to_float(pk_get(src + (uint64_t)g * (uint64_t)gb, pk_off(j, n, gc, endian), n), f);
+        }
+    }
+    return (uint64_t)groups * (uint64_t)gb;
+}
+
 int lofo_num_threads(void)
 {
 #ifdef _OPENMP

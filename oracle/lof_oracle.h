@@ -117,6 +117,42 @@ void lofo_gemm_chunked_f32(const float* A, const float* B, float* C, int64_t M, 
                            int accum_mant_bits, const lofo_format* acc_fmt, const lofo_projspec* ps,
                            int64_t k_chunk, float alpha, int partial_round);
 
+/* ------------------------------------------------------------------------------------
+ * Low-bit storage codec ("next" row f-1): /root/reference/src/lo_pack.hpp.
+ * The Inf / NaN functor objects of FloatingPointParams (fp_tools.hpp:187-252) travel as data:
+ *     IsInf(rep) := (rep & inf_mask) == inf_value
+ *     IsNaN(rep) := (rep & nan_mask) == nan_value  &&  (nan_mant_mask == 0 || (rep & nan_mant_mask) != 0)
+ * ("never" = mask 0, value 1), which covers every checker the reference defines (lo_float.h:1411-1830,
+ * fp_tools.hpp:257-440, LoFloat/formats.py).
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+    lofo_format fmt;
+    uint32_t inf_mask, inf_value;
+    uint32_t nan_mask, nan_value, nan_mant_mask;
+    uint32_t min_pos_inf;          /* IsInf.minPosInf()       */
+    uint32_t qnan, snan;           /* IsNaN.qNanBitPattern() / sNanBitPattern() */
+} lofo_codec_format;
+
+enum { LOFO_PACK_FORWARD = 0, LOFO_PACK_REVERSE = 1 };      /* lo_pack.hpp:52 PackEndian */
+enum { LOFO_OVF_INF = 0, LOFO_SAT_FINITE = 1, LOFO_SAT_PROPAGATE = 2 };   /* fp_tools.hpp:38-41 */
+
+uint32_t lofo_float_to_rep(float from, const lofo_codec_format* f, const lofo_projspec* ps, uint32_t w);   /* lo_pack.hpp:109-267 */
+float    lofo_rep_to_float(uint32_t rep, const lofo_codec_format* f);                                     /* lo_pack.hpp:277-319 */
+void     lofo_float_to_rep_array(const float* in, uint32_t* out, int64_t n, const lofo_codec_format* f, const lofo_projspec* ps,
+                                 const lofo_rng* rng, uint64_t first_index);
+void     lofo_rep_to_float_array(const uint32_t* in, float* out, int64_t n, const lofo_codec_format* f);
+int      lofo_pack_group_count(int n);                                                                    /* lo_pack.hpp:65-68 */
+int      lofo_pack_group_bytes(int n);
+uint64_t lofo_packed_size(int n, uint64_t count);                                                         /* lo_pack.hpp:70-73, 399 */
+/* raw n-bit reps <-> packed bytes (the typed API 2 of lo_pack.hpp:329-341, 359-371); reps as uint32 */
+uint64_t lofo_pack_reps(uint8_t* dst, const uint32_t* reps, uint64_t count, int n, int endian);
+uint64_t lofo_unpack_reps(uint32_t* reps, const uint8_t* src, uint64_t count, int n, int endian);
+/* float arrays <-> packed bytes (LoF_encode / LoF_decode, lo_pack.hpp:419-432, 452-465); stochastic modes draw the
+ * event word of global element first_index + i like lofo_round_params.  Return bytes written / consumed. */
+uint64_t lofo_encode_f32(uint8_t* dst, const float* src, uint64_t count, const lofo_codec_format* f,
+                         const lofo_projspec* ps, int endian, const lofo_rng* rng, uint64_t first_index);
+uint64_t lofo_decode_f32(float* dst, const uint8_t* src, uint64_t count, const lofo_codec_format* f, int endian);
+
 int lofo_num_threads(void);
 
 #ifdef __cplusplus

@@ -11,11 +11,14 @@
 //   lo_float::virtual_round(float*, float*, n, params, ps)  [xsimd array]  lo_float.h:4278 -> 2942
 //   lo_float::virtual_mx_round(float*, n, block, pub, priv, ps, ps)        lo_float.h:4311
 //   lof_round_to_odd_fma / lof_sgemm_ukr via bli_sgemm                     blis_lof_gemm.hpp:63,147,280
+//   lo_pack_internal::convert_float_to_rep / convert_rep_to_float          lo_pack.hpp:109, 277
+//   LoF_encode<E>(uint8_t*, const float*, params, count, ps) / LoF_decode  lo_pack.hpp:419, 452
 #include <cstdint>
 #include <cstring>
 #include <random>
 
 #include "lo_float.h"
+#include "lo_pack.hpp"
 #ifdef LOF_SHIM_WITH_BLIS
 #include "blis_lof_gemm.hpp"
 #endif
@@ -175,4 +178,74 @@ int ref_has_blis() { return 1; }
 int ref_has_blis() { return 0; }
 #endif
 
+
+// ---- low-bit storage codec (lo_pack.hpp) with the Inf / NaN functors as data ---------------
+struct ShimCodecFormat {                    // == lofo_codec_format (oracle/lof_oracle.h)
+    int32_t bitwidth, mantissa_bits, bias, ov_behavior, na_behavior, is_signed, unsigned_behavior;
+    uint32_t inf_mask, inf_value, nan_mask, nan_value, nan_mant_mask, min_pos_inf, qnan, snan;
+};
+struct ShimInf {
+    uint32_t mask, value, min_pos, sign;
+    constexpr bool operator()(uint64_t bits) const { return ((uint32_t)bits & mask) == value; }
+    constexpr uint64_t minNegInf() const { return min_pos | sign; }
+    constexpr uint64_t minPosInf() const { return min_pos; }
+};
+struct ShimNaN {
+    uint32_t mask, value, mant_mask, q, s;
+    constexpr bool operator()(uint64_t bits) const { return ((uint32_t)bits & mask) == value && (mant_mask == 0u || ((uint32_t)bits & mant_mask) != 0u); }
+    constexpr uint64_t qNanBitPattern() const { return q; }
+    constexpr uint64_t sNanBitPattern() const { return s; }
+};
+using CodecParams = FloatingPointParams<ShimInf, ShimNaN>;
+static CodecParams make_codec(const ShimCodecFormat* f)
+{
+    const uint32_t sign = (f->is_signed == 0) ? (1u << (f->bitwidth - 1)) : 0u;
+    return CodecParams(f->bitwidth, f->mantissa_bits, f->bias, static_cast<Inf_Behaviors>(f->ov_behavior),
+                       static_cast<NaN_Behaviors>(f->na_behavior), static_cast<Signedness>(f->is_signed),
+                       ShimInf{f->inf_mask, f->inf_value, f->min_pos_inf, sign},
+                       ShimNaN{f->nan_mask, f->nan_value, f->nan_mant_mask, f->qnan, f->snan},
+                       static_cast<Unsigned_behavior>(f->unsigned_behavior));
+}
+static ProjSpec make_ps3(int mode, int sat, int stoch_len)
+{
+    return ProjSpec{static_cast<Rounding_Mode>(mode), static_cast<Saturation_Mode>(sat), stoch_len};
+}
+
+void ref_float_to_rep(const float* in, uint32_t* out, int64_t n, const ShimCodecFormat* f, int mode, int sat, int stoch_len, unsigned seed)
+{
+    const CodecParams p = make_codec(f);
+    const ProjSpec ps = make_ps3(mode, sat, stoch_len);
+    for (int64_t i = 0; i < n; ++i) {
+        lo_float::lof_seed = seed;
+        out[i] = lo_pack_internal::convert_float_to_rep(in[i], p, ps);
+    }
+}
+void ref_rep_to_float(const uint32_t* in, float* out, int64_t n, const ShimCodecFormat* f)
+{
+    const CodecParams p = make_codec(f);
+    for (int64_t i = 0; i < n; ++i) out[i] = lo_pack_internal::convert_rep_to_float(in[i], p);
+}
+uint64_t ref_packed_size(int n, uint64_t count) { return LoF_packed_size(n, count); }
+int64_t ref_encode_f32(uint8_t* dst, const float* src, uint64_t count, const ShimCodecFormat* f, int mode, int sat, int stoch_len, int endian)
+{
+    const CodecParams p = make_codec(f);
+    const ProjSpec ps = make_ps3(mode, sat, stoch_len);
+    return endian == 0 ? LoF_encode<PackEndian::Forward>(dst, src, p, count, ps) : LoF_encode<PackEndian::Reverse>(dst, src, p, count, ps);
+}
+int64_t ref_decode_f32(float* dst, const uint8_t* src, uint64_t count, const ShimCodecFormat* f, int endian)
+{
+    const CodecParams p = make_codec(f);
+    return endian == 0 ? LoF_decode<PackEndian::Forward>(dst, src, p, count) : LoF_decode<PackEndian::Reverse>(dst, src, p, count);
+}
+// typed ground truth of test/test_pack.cpp for two named presets: rep of Templated_Float<Fp>(x) and (float)FromRep(rep)
+void ref_typed_e4m3fn(const float* in, uint32_t* rep, float* back, int64_t n)
+{
+    using TF = lo_float_internal::Templated_Float<lo_float_internal::param_float8_e4m3fn>;
+    for (int64_t i = 0; i < n; ++i) { TF t(in[i]); rep[i] = (uint32_t)t.rep(); back[i] = (float)t; }
+}
+void ref_typed_p3109_8_4(const float* in, uint32_t* rep, float* back, int64_t n)
+{
+    using TF = lo_float_internal::Templated_Float<lo_float_internal::param_float_p_3109<8, 4>>;
+    for (int64_t i = 0; i < n; ++i) { TF t(in[i]); rep[i] = (uint32_t)t.rep(); back[i] = (float)t; }
+}
 }  // extern "C"

@@ -109,6 +109,34 @@ def main():
     out["fma_r"] = np.array([lib.ref_round_to_odd_fma(float(p), float(q), float(s)) for p, q, s in zip(a, b, c)],
                             dtype=np.float32)
     np.savez_compressed(HERE / "gemm_f32.npz", **out)
+    # 7) storage codec (lo_pack.hpp): reps of the probe set of test/test_pack.cpp under every deterministic mode
+    #    (OvfInf) and under RNE for the other two saturation modes, the full decode table, packed bytes for both
+    #    slot orders, and the typed ground truth (Templated_Float<Fp>) for the two presets the shim instantiates.
+    out = {}
+    for name, f in L.CODEC_FORMATS.items():
+        x = L.codec_probe_floats(f)
+        x = x[:: max(1, x.size // 3000)]
+        out[f"{name}__x"] = x
+        for mode in L.DETERMINISTIC_MODES:
+            out[f"{name}__rep__{L.MODE_NAMES[mode]}__sat0"] = L.r_float_to_rep(x, f, mode, 0).astype(np.uint16)
+        for sat in (1, 2):
+            out[f"{name}__rep__RNE__sat{sat}"] = L.r_float_to_rep(x, f, L.RNE, sat).astype(np.uint16)
+        n = f.fmt.bitwidth
+        reps = np.arange(1 << n, dtype=np.uint32) if n <= 12 else np.arange(0, 1 << n, 7, dtype=np.uint32)
+        out[f"{name}__dec_reps"] = reps.astype(np.uint16)
+        out[f"{name}__dec"] = L.r_rep_to_float(reps, f)
+        xs = x[:1001]
+        for endian in (0, 1):
+            out[f"{name}__packed{endian}"] = L.r_encode(xs, f, L.RNE, 0, 0, endian)
+            out[f"{name}__unpacked{endian}"] = L.r_decode(out[f"{name}__packed{endian}"], xs.size, f, endian)
+    lib = L.ref()
+    for tag, fn, f in (("typed_e4m3fn", lib.ref_typed_e4m3fn, L.CODEC_FORMATS["e4m3fn"]),
+                       ("typed_p3109_8p4", lib.ref_typed_p3109_8_4, L.CODEC_FORMATS["p3109_8p4"])):
+        x = L.codec_probe_floats(f)
+        rep, back = np.empty(x.size, np.uint32), np.empty(x.size, np.float32)
+        fn(L._ptr(x), L._ptr(rep), L._ptr(back), x.size)
+        out[f"{tag}__x"], out[f"{tag}__rep"], out[f"{tag}__back"] = x, rep.astype(np.uint16), back
+    np.savez_compressed(HERE / "pack_codec.npz", **out)
     print("golden vectors written to", HERE)
 
 

@@ -69,6 +69,62 @@ FORMATS = {
     "e4m3_b7_ext": fmt(8, 3, 7, ov=EXTENDED),
 }
 
+
+
+# ------------------------------------------------------------------------------ storage codec formats
+class CodecFormat(C.Structure):
+    """lofo_codec_format / lof_codec_format_t: FloatingPointParams with the Inf / NaN functors as data."""
+    _fields_ = [("fmt", Format), ("inf_mask", C.c_uint32), ("inf_value", C.c_uint32), ("nan_mask", C.c_uint32),
+                ("nan_value", C.c_uint32), ("nan_mant_mask", C.c_uint32), ("min_pos_inf", C.c_uint32),
+                ("qnan", C.c_uint32), ("snan", C.c_uint32)]
+
+
+NEVER = (0, 1)      # (mask, value): (rep & 0) == 1 is never true
+ALL = 0xFFFFFFFF
+
+
+def codec_p3109(k, p, signed=True, saturating=True, bias=None, unsigned_behavior=0) -> CodecFormat:
+    """param_float_p_3109<k, p, signedness, has_inf> (lo_float.h:1679-1768) == LoFloat/formats.py create_p3109_params."""
+    bias = (1 << (k - p - 1)) if bias is None else bias
+    f = Format(k, p - 1, bias, SATURATING if saturating else EXTENDED, 0, SIGNED if signed else UNSIGNED, unsigned_behavior)
+    nan = (1 << (k - 1)) if signed else (1 << k) - 1
+    if saturating:
+        inf_m, inf_v = NEVER
+    else:   # (bits | 1 << (k-1)) == (signed ? 2^k - 1 : 2^k - 2)
+        inf_m, inf_v = (1 << (k - 1)) - 1, ((1 << k) - 1 if signed else (1 << k) - 2) & ((1 << (k - 1)) - 1)
+    min_pos = ((1 << (k - 1)) - 1) if signed else (1 << k) - 2
+    return CodecFormat(f, inf_m, inf_v, ALL, nan, 0, min_pos, nan, nan)
+
+
+def codec_ocp(k, m, bias, signed=True) -> CodecFormat:
+    """The OCP-style presets (e4m3fn, e5m2, e3m2, e2m3, e2m1: lo_float.h:1448-1660): no infinities, NaN == 0xFF
+    (OCP_F8E4M3_{Inf,NaN}Checker -- the reference uses these two functors for ALL of them)."""
+    f = Format(k, m, bias, SATURATING, 0, SIGNED if signed else UNSIGNED, 0)
+    return CodecFormat(f, NEVER[0], NEVER[1], ALL, 0xFF, 0, 0, 0xFF, 0xFF)
+
+
+def codec_half() -> CodecFormat:
+    """halfPrecisionParams (fp_tools.hpp:334-370): IEEE binary16."""
+    f = Format(16, 10, 15, EXTENDED, 1, SIGNED, 0)
+    return CodecFormat(f, 0x7FFF, 0x7C00, 0x7C00, 0x7C00, 0x03FF, 0x7C00, 0x7E00, 0x7D00)
+
+
+def codec_e8m0() -> CodecFormat:
+    """param_ocp_e8m0 (lo_float.h:1777-1795): unsigned, NaN == 0xFF, saturating."""
+    f = Format(8, 0, 127, SATURATING, 0, UNSIGNED, 0)
+    return CodecFormat(f, NEVER[0], NEVER[1], ALL, 0xFF, 0, 0, 0xFF, 0xFF)
+
+
+# the formats test/test_pack.cpp:230-244 runs plus the MX element / scale formats
+CODEC_FORMATS = {
+    "p3109_3p2": codec_p3109(3, 2), "e2m1": codec_ocp(4, 1, 1), "p3109_5p2": codec_p3109(5, 2), "e3m2": codec_ocp(6, 2, 3),
+    "e2m3": codec_ocp(6, 3, 1), "p3109_7p3": codec_p3109(7, 3), "e5m2": codec_ocp(8, 2, 15), "e4m3fn": codec_ocp(8, 3, 7),
+    "p3109_8p4": codec_p3109(8, 4), "p3109_8p4_ext": codec_p3109(8, 4, saturating=False),
+    "p3109_8p3_unsigned": codec_p3109(8, 3, signed=False), "p3109_8p3_unsigned_ext_nan": codec_p3109(8, 3, signed=False, saturating=False, unsigned_behavior=1),
+    "p3109_9p3": codec_p3109(9, 3), "p3109_11p5": codec_p3109(11, 5), "p3109_12p8": codec_p3109(12, 8), "half": codec_half(),
+    "e8m0": codec_e8m0(),
+}
+
 _NP_OF = {F32: np.float32, F16: np.float16, F64: np.float64, BF16: np.uint16}
 
 
@@ -122,6 +178,25 @@ def oracle():
         lib.lofo_gemm_f32.argtypes = [vp, vp, vp, i64, i64, i64, i32, PP, i64, C.c_float, C.c_float, PR]
         lib.lofo_gemm_chunked_f32.argtypes = [vp, vp, vp, i64, i64, i64, i32, PF, PP, i64, C.c_float, i32]
         lib.lofo_num_threads.restype = i32
+        PC, u8p = C.POINTER(CodecFormat), C.c_void_p
+        lib.lofo_float_to_rep.argtypes = [C.c_float, PC, PP, u32]
+        lib.lofo_float_to_rep.restype = u32
+        lib.lofo_rep_to_float.argtypes = [u32, PC]
+        lib.lofo_rep_to_float.restype = C.c_float
+        lib.lofo_float_to_rep_array.argtypes = [vp, vp, i64, PC, PP, PR, u64]
+        lib.lofo_rep_to_float_array.argtypes = [vp, vp, i64, PC]
+        lib.lofo_pack_group_count.argtypes = [i32]
+        lib.lofo_pack_group_bytes.argtypes = [i32]
+        lib.lofo_packed_size.argtypes = [i32, u64]
+        lib.lofo_packed_size.restype = u64
+        lib.lofo_pack_reps.argtypes = [u8p, vp, u64, i32, i32]
+        lib.lofo_pack_reps.restype = u64
+        lib.lofo_unpack_reps.argtypes = [vp, u8p, u64, i32, i32]
+        lib.lofo_unpack_reps.restype = u64
+        lib.lofo_encode_f32.argtypes = [u8p, vp, u64, PC, PP, i32, PR, u64]
+        lib.lofo_encode_f32.restype = u64
+        lib.lofo_decode_f32.argtypes = [vp, u8p, u64, PC, i32]
+        lib.lofo_decode_f32.restype = u64
         _oracle = lib
     return _oracle
 
@@ -151,6 +226,17 @@ def ref():
         lib.ref_draw_real.restype = C.c_double
         lib.ref_shim_threads.restype = i32
         lib.ref_has_blis.restype = i32
+        PC = C.POINTER(CodecFormat)
+        lib.ref_float_to_rep.argtypes = [vp, vp, i64, PC, i32, i32, i32, u32]
+        lib.ref_rep_to_float.argtypes = [vp, vp, i64, PC]
+        lib.ref_packed_size.argtypes = [i32, C.c_uint64]
+        lib.ref_packed_size.restype = C.c_uint64
+        lib.ref_encode_f32.argtypes = [vp, vp, C.c_uint64, PC, i32, i32, i32, i32]
+        lib.ref_encode_f32.restype = i64
+        lib.ref_decode_f32.argtypes = [vp, vp, C.c_uint64, PC, i32]
+        lib.ref_decode_f32.restype = i64
+        lib.ref_typed_e4m3fn.argtypes = [vp, vp, vp, i64]
+        lib.ref_typed_p3109_8_4.argtypes = [vp, vp, vp, i64]
         if lib.ref_has_blis():
             lib.ref_round_to_odd_fma.argtypes = [C.c_float] * 3
             lib.ref_round_to_odd_fma.restype = C.c_float
@@ -346,3 +432,98 @@ def first_mismatch(x, a, b):
         return None
     i = int(idx[0])
     return f"{idx.size} mismatches; first at {i}: in=0x{int(ux[i]):08x} got=0x{int(ua[i]):08x} want=0x{int(ub[i]):08x}"
+
+
+# ------------------------------------------------------------------------------ storage codec (lo_pack.hpp)
+def packed_size(n: int, count: int) -> int:
+    return int(oracle().lofo_packed_size(n, count))
+
+
+def o_float_to_rep(x: np.ndarray, f: CodecFormat, mode=RNE, sat=0, stoch_len=0, seed=0, offset=0, first_index=0, fixed_word=None) -> np.ndarray:
+    """convert_float_to_rep element by element (no packing)."""
+    x = np.ascontiguousarray(x, np.float32).ravel()
+    ps, r = ProjSpec(mode, sat, stoch_len), _rng(seed, offset, fixed_word)
+    out = np.empty(x.size, np.uint32)
+    oracle().lofo_float_to_rep_array(_ptr(x), _ptr(out), x.size, C.byref(f), C.byref(ps), C.byref(r), first_index)
+    return out
+
+
+def o_rep_to_float(reps: np.ndarray, f: CodecFormat) -> np.ndarray:
+    reps = np.ascontiguousarray(reps, np.uint32).ravel()
+    out = np.empty(reps.size, np.float32)
+    oracle().lofo_rep_to_float_array(_ptr(reps), _ptr(out), reps.size, C.byref(f))
+    return out
+
+
+def o_encode(x: np.ndarray, f: CodecFormat, mode=RNE, sat=0, stoch_len=0, endian=0, seed=0, offset=0, first_index=0) -> np.ndarray:
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.full(packed_size(f.fmt.bitwidth, x.size), 0xAB, np.uint8)
+    ps, r = ProjSpec(mode, sat, stoch_len), _rng(seed, offset)
+    n = oracle().lofo_encode_f32(_ptr(out), _ptr(x), x.size, C.byref(f), C.byref(ps), endian, C.byref(r), first_index)
+    assert n == out.size
+    return out
+
+
+def o_decode(buf: np.ndarray, count: int, f: CodecFormat, endian=0) -> np.ndarray:
+    buf = np.ascontiguousarray(buf, np.uint8)
+    out = np.empty(count, np.float32)
+    oracle().lofo_decode_f32(_ptr(out), _ptr(buf), count, C.byref(f), endian)
+    return out
+
+
+def o_pack_reps(reps: np.ndarray, n: int, endian=0) -> np.ndarray:
+    reps = np.ascontiguousarray(reps, np.uint32)
+    out = np.full(packed_size(n, reps.size), 0xAB, np.uint8)
+    oracle().lofo_pack_reps(_ptr(out), _ptr(reps), reps.size, n, endian)
+    return out
+
+
+def o_unpack_reps(buf: np.ndarray, count: int, n: int, endian=0) -> np.ndarray:
+    buf = np.ascontiguousarray(buf, np.uint8)
+    out = np.empty(count, np.uint32)
+    oracle().lofo_unpack_reps(_ptr(out), _ptr(buf), count, n, endian)
+    return out
+
+
+def r_float_to_rep(x: np.ndarray, f: CodecFormat, mode=RNE, sat=0, stoch_len=0, seed=12345) -> np.ndarray:
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.empty(x.size, np.uint32)
+    ref().ref_float_to_rep(_ptr(x), _ptr(out), x.size, C.byref(f), mode, sat, stoch_len, seed)
+    return out
+
+
+def r_rep_to_float(reps: np.ndarray, f: CodecFormat) -> np.ndarray:
+    reps = np.ascontiguousarray(reps, np.uint32)
+    out = np.empty(reps.size, np.float32)
+    ref().ref_rep_to_float(_ptr(reps), _ptr(out), reps.size, C.byref(f))
+    return out
+
+
+def r_encode(x: np.ndarray, f: CodecFormat, mode=RNE, sat=0, stoch_len=0, endian=0) -> np.ndarray:
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.full(int(ref().ref_packed_size(f.fmt.bitwidth, x.size)), 0xAB, np.uint8)
+    n = ref().ref_encode_f32(_ptr(out), _ptr(x), x.size, C.byref(f), mode, sat, stoch_len, endian)
+    assert n == out.size
+    return out
+
+
+def r_decode(buf: np.ndarray, count: int, f: CodecFormat, endian=0) -> np.ndarray:
+    buf = np.ascontiguousarray(buf, np.uint8)
+    out = np.empty(count, np.float32)
+    ref().ref_decode_f32(_ptr(out), _ptr(buf), count, C.byref(f), endian)
+    return out
+
+
+def codec_probe_floats(f: CodecFormat) -> np.ndarray:
+    """The probe set of test/test_pack.cpp:77-115: every representable value and its two fp32 neighbours, the exact
+    midpoints between adjacent values, zeros, overflow, infinities, fp32 subnormals -- plus NaN and wide random data."""
+    n = f.fmt.bitwidth
+    grid = o_rep_to_float(np.arange(1 << n, dtype=np.uint32), f) if n <= 12 else \
+        o_rep_to_float(np.arange(0, 1 << n, 37, dtype=np.uint32), f)
+    fin = np.unique(grid[np.isfinite(grid)])
+    mids = (0.5 * (fin[1:].astype(np.float64) + fin[:-1])).astype(np.float32)
+    extras = np.array([0.0, -0.0, 1e30, -1e30, np.inf, -np.inf, 1e-40, -1e-40, 1.4e-45, np.nan, 3.4e38, -3.4e38], np.float32)
+    with np.errstate(over="ignore", invalid="ignore"):
+        return np.concatenate([fin, np.nextafter(fin, np.float32(np.inf)), np.nextafter(fin, np.float32(-np.inf)), mids,
+                               np.nextafter(mids, np.float32(np.inf)), np.nextafter(mids, np.float32(-np.inf)), extras,
+                               wide_random_f32(4096, 77 + n)]).astype(np.float32)

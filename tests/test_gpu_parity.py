@@ -670,3 +670,114 @@ def test_exhaustive_fp32_sweep_8bit_formats(lof, cuda_dev):
     for fname in ("p3109_8p4", "e5m2", "e3m2", "e2m3", "e2m1", "e8m0"):
         for mode in L.DETERMINISTIC_MODES:
             sweep(fname, mode, 64)
+
+
+# ------------------------------------------------------------------------------ storage codec (lo_pack.hpp), row f-1
+def _abi_encode(cuda_dev, x, f, mode=0, sat=0, stoch_len=0, endian=0, seed=0, offset=0, first_index=0, misalign=0):
+    from lofloat_b200 import _lib
+    lib = _lib.lib()
+    xt = _gpu(x, cuda_dev)
+    nbytes = L.packed_size(f.fmt.bitwidth, x.size)
+    buf = torch.full((nbytes + 8,), 0xAB, dtype=torch.uint8, device=cuda_dev)
+    ps, rng = _lib.CProjSpec(mode, sat, stoch_len), _lib.CRng(seed, offset)
+    st = lib.lof_encode_f32(xt.data_ptr(), buf.data_ptr() + misalign, x.size, C.cast(C.byref(f), C.POINTER(_lib.CCodecFormat)),
+                            C.byref(ps), endian, C.byref(rng), first_index, torch.cuda.current_stream().cuda_stream)
+    assert st == 0, lib.lof_last_error_string().decode()
+    out = _np(buf)
+    assert np.all(out[:misalign] == 0xAB) and np.all(out[misalign + nbytes:] == 0xAB)        # nothing written outside the packed range
+    return out[misalign:misalign + nbytes]
+
+
+def _abi_decode(cuda_dev, packed, count, f, endian=0):
+    from lofloat_b200 import _lib
+    lib = _lib.lib()
+    pt = _gpu(packed, cuda_dev)
+    out = torch.empty(count, dtype=torch.float32, device=cuda_dev)
+    st = lib.lof_decode_f32(pt.data_ptr(), out.data_ptr(), count, C.cast(C.byref(f), C.POINTER(_lib.CCodecFormat)), endian,
+                            torch.cuda.current_stream().cuda_stream)
+    assert st == 0, lib.lof_last_error_string().decode()
+    return _np(out)
+
+
+def test_pack_codec_bit_exact_all_formats_modes(lof, cuda_dev):
+    """lof_encode_f32 / lof_decode_f32 through the C ABI against the oracle (itself pinned to the compiled reference's
+    lo_pack.hpp): every codec format of test/test_pack.cpp (+ MX element / scale formats) x every deterministic mode
+    x every saturation mode x both slot orders on the probe set; decode over every representation; ragged counts
+    (partial groups, partial 32-bit words, tiles), misaligned destination; committed golden bytes."""
+    g = np.load(G / "pack_codec.npz")
+    for name, f in L.CODEC_FORMATS.items():
+        x = L.codec_probe_floats(f)
+        n = f.fmt.bitwidth
+        for mode in L.DETERMINISTIC_MODES:
+            for sat in ((0, 1, 2) if mode == L.RNE else (0,)):
+                for endian in (0, 1):
+                    got = _abi_encode(cuda_dev, x, f, mode, sat, 0, endian)
+                    assert np.array_equal(got, L.o_encode(x, f, mode, sat, 0, endian)), (name, L.MODE_NAMES[mode], sat, endian)
+        reps = np.arange(1 << n, dtype=np.uint32)
+        for endian in (0, 1):
+            packed = L.o_pack_reps(reps, n, endian)
+            assert L.bits_equal(_abi_decode(cuda_dev, packed, reps.size, f, endian), L.o_rep_to_float(reps, f)), (name, endian)
+        for count in (1, 3, 15, 16, 17, 1001, 4095, 4096, 4097, 3 * 4096 + 5):
+            xs_ = np.resize(x, count)
+            want = L.o_encode(xs_, f, endian=count & 1)
+            assert np.array_equal(_abi_encode(cuda_dev, xs_, f, endian=count & 1), want), (name, count)
+            assert np.array_equal(_abi_encode(cuda_dev, xs_, f, endian=count & 1, misalign=1), want), (name, count, "misaligned")
+            assert L.bits_equal(_abi_decode(cuda_dev, want, count, f, count & 1), L.o_decode(want, count, f, count & 1)), (name, count)
+        assert np.array_equal(_abi_encode(cuda_dev, g[f"{name}__x"][:1001], f, endian=1), g[f"{name}__packed1"]), name
+    # stochastic modes draw the same Philox event words as the oracle (global element index keyed)
+    f = L.CODEC_FORMATS["e4m3fn"]
+    x = L.wide_random_f32(50000, 3) * np.float32(2.0 ** -3)
+    for mode, sl in ((L.SR_A, 4), (L.SR_B, 3), (L.SR_C, 5), (L.SR_D, 6), (L.TRUE_SR, 0), (L.PROB, 0)):
+        got = _abi_encode(cuda_dev, x, f, mode, 0, sl, 0, seed=9, offset=2, first_index=4096)
+        assert np.array_equal(got, L.o_encode(x, f, mode, 0, sl, 0, seed=9, offset=2, first_index=4096)), L.MODE_NAMES[mode]
+
+
+def test_pack_python_surface_and_full_size_properties(lof, cuda_dev):
+    """lof.lof_encode / lof.lof_decode (checker callables folded into masks) == oracle for the factory formats; at
+    2^26 elements: decode(encode(x)) is idempotent under re-encoding (the codec is a projection), equals the oracle on
+    a sampled window, and the packed size is exact."""
+    pairs = ((lof.create_p3109_params(8, 4), L.CODEC_FORMATS["p3109_8p4"]),
+             (lof.create_p3109_params(8, 4, saturating=False), L.CODEC_FORMATS["p3109_8p4_ext"]),
+             (lof.create_p3109_params(5, 2), L.CODEC_FORMATS["p3109_5p2"]),
+             (lof.create_p3109_params(11, 5), L.CODEC_FORMATS["p3109_11p5"]),
+             (lof.create_half_params(), L.codec_half()))
+    for d, f in pairs:
+        x = L.codec_probe_floats(f)
+        for endian in (lof.PackEndian.Forward, lof.PackEndian.Reverse):
+            packed = lof.lof_encode(_gpu(x, cuda_dev), d, endian=endian)
+            assert np.array_equal(_np(packed), L.o_encode(x, f, endian=int(endian))), (d, endian)
+            back = lof.lof_decode(packed, x.size, d, endian)
+            assert L.bits_equal(_np(back), L.o_decode(_np(packed), x.size, f, int(endian))), (d, endian)
+    n = 1 << 26
+    g = torch.Generator(device=cuda_dev).manual_seed(3)
+    x = torch.randn(n, device=cuda_dev, generator=g) * torch.exp2(torch.randint(-10, 9, (n,), device=cuda_dev, generator=g).float())
+    for d, f in ((lof.create_p3109_params(8, 4), L.CODEC_FORMATS["p3109_8p4"]), (lof.create_p3109_params(6, 3, bias=3), None),
+                 (lof.create_p3109_params(4, 2, bias=1), None)):
+        packed = lof.lof_encode(x, d)
+        assert packed.numel() == lof.packed_size(d.total_bits, n)
+        y = lof.lof_decode(packed, n, d)
+        assert torch.equal(lof.lof_encode(y, d), packed)                                   # projection: re-encoding is the identity
+        if f is not None:
+            lo = 12345 * 16
+            assert np.array_equal(_np(packed[lo:lo + 4096]), L.o_encode(_np(x[lo:lo + 4096]), f))
+    with pytest.raises(RuntimeError):
+        lof.lof_encode(x.double(), lof.create_p3109_params(8, 4))
+    with pytest.raises(ValueError):
+        lof.lof_encode(x, lof.create_single_params())                                       # 32-bit formats cannot be packed (lo_pack.hpp:4-9)
+
+
+def test_gemm_on_packed_operands_equals_fp32_container_path(lof, cuda_dev):
+    """lof_gemm_chunked_packed: A and B^T stored as e4m3 bytes by lof_encode -> the same C, bit for bit, as the
+    fp32-container entry point (which converts inside the call)."""
+    from lofloat_b200 import formats
+    A, B = _e4m3_uniform((512, 2048), 13), _e4m3_uniform((2048, 384), 14)
+    ocp = lof.FloatFormatDescriptor(8, 3, 7, lof.InfBehavior.Saturating, lof.NaNBehavior._3109, lof.Signedness.Signed,
+                                    formats._P3109Inf(8, True, True), formats._BitPatternNaN(0xFF))   # param_float8_e4m3fn
+    Ap = lof.lof_encode(_gpu(A, cuda_dev), ocp).view(512, 2048)
+    Btp = lof.lof_encode(_gpu(np.ascontiguousarray(B.T), cuda_dev), ocp).view(384, 2048)
+    e5m10 = _desc(lof, L.fmt(16, 10, 15, L.SATURATING, L.SIGNED))
+    for kw, mant in ((dict(k_chunk=32, accum_format=e5m10), 0), (dict(k_chunk=32), 10), (dict(k_chunk=0), 10),
+                     (dict(k_chunk=128), 7), (dict(k_chunk=32, partial_round=True), 10)):
+        want = lof.lof_gemm(_gpu(A, cuda_dev), _gpu(B, cuda_dev), mant, **kw)
+        got = lof.lof_gemm_packed(Ap, Btp, mant, **kw)
+        assert torch.equal(got, want), kw

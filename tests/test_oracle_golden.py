@@ -331,3 +331,74 @@ def test_mx_properties():
         assert scale in (np.float32(lo), np.float32(2 * lo))
         q = L.o_round_params(np.array([-np.float32(amax) / scale], np.float32), f)[0] * scale
         assert y[3] == q
+
+
+# ------------------------------------------------------------------------------ storage codec (lo_pack.hpp)
+def test_pack_geometry_against_independent_lcm_oracle():
+    """test/test_pack.cpp:30-38: group bytes / counts / packed sizes for every width, via an independent lcm."""
+    from math import gcd
+    lib = L.oracle()
+    for n in range(1, 17):
+        al = 8 if n <= 8 else 16
+        lcm = n * al // gcd(n, al)
+        assert lib.lofo_pack_group_count(n) == lcm // n and lib.lofo_pack_group_bytes(n) == lcm // 8
+        for count in (0, 1, lcm // n - 1, lcm // n, lcm // n + 1, 1000, 4097):
+            assert L.packed_size(n, count) == -(-count // (lcm // n)) * (lcm // 8)
+
+
+def test_pack_codec_golden_from_reference():
+    """Oracle codec == the compiled reference's convert_float_to_rep / convert_rep_to_float / LoF_encode / LoF_decode
+    on the probe set of test/test_pack.cpp (grid values, fp32 neighbours, midpoints, overflow, fp32 subnormals) for
+    every format that test runs (+ MX element / scale formats), every deterministic mode and saturation mode."""
+    g = _load("pack_codec.npz")
+    for name, f in L.CODEC_FORMATS.items():
+        x = g[f"{name}__x"]
+        for mode in L.DETERMINISTIC_MODES:
+            assert np.array_equal(L.o_float_to_rep(x, f, mode, 0), g[f"{name}__rep__{L.MODE_NAMES[mode]}__sat0"]), (name, mode)
+        for sat in (1, 2):
+            assert np.array_equal(L.o_float_to_rep(x, f, L.RNE, sat), g[f"{name}__rep__RNE__sat{sat}"]), (name, sat)
+        assert L.bits_equal(L.o_rep_to_float(g[f"{name}__dec_reps"].astype(np.uint32), f), g[f"{name}__dec"]), name
+        xs = x[:1001]
+        for endian in (0, 1):
+            packed = L.o_encode(xs, f, endian=endian)
+            assert np.array_equal(packed, g[f"{name}__packed{endian}"]), (name, endian)
+            assert L.bits_equal(L.o_decode(packed, xs.size, f, endian), g[f"{name}__unpacked{endian}"]), (name, endian)
+
+
+def test_pack_codec_against_typed_ground_truth():
+    """test/test_pack.cpp:64-115: the runtime codec must agree with the compile-time Templated_Float<Fp> path
+    (rep of TF(x), and (float)TF(x) after a round trip); NaN reps only need to be NaN."""
+    g = _load("pack_codec.npz")
+    for tag, key in (("typed_e4m3fn", "e4m3fn"), ("typed_p3109_8p4", "p3109_8p4")):
+        f = L.CODEC_FORMATS[key]
+        x, rep, back = g[f"{tag}__x"], g[f"{tag}__rep"].astype(np.uint32), g[f"{tag}__back"]
+        got = L.o_float_to_rep(x, f)
+        is_nan = np.isnan(back)
+        assert np.array_equal(got[~is_nan], rep[~is_nan]), tag
+        assert np.all(np.isnan(L.o_rep_to_float(got[is_nan], f))), tag
+        assert L.bits_equal(L.o_rep_to_float(got, f)[~is_nan], back[~is_nan]), tag
+
+
+def test_pack_roundtrip_properties():
+    """test/test_pack.cpp:118-227: packing is a lossless bijection on reps for every width and both slot orders
+    (incl. a partial trailing group), the two orders differ iff a group holds more than one element, and encoding
+    a decoded value reproduces its rep (idempotence) for every non-NaN rep of the small formats."""
+    rng = np.random.default_rng(5)
+    lib = L.oracle()
+    for n in range(1, 17):
+        gc = lib.lofo_pack_group_count(n)
+        for count in (2 * gc + 1 if gc > 1 else 5, 1 << min(n, 10)):
+            reps = rng.integers(0, 1 << n, count, dtype=np.uint32)
+            fwd, rev = L.o_pack_reps(reps, n, 0), L.o_pack_reps(reps, n, 1)
+            assert fwd.size == L.packed_size(n, count)
+            assert np.array_equal(L.o_unpack_reps(fwd, count, n, 0), reps)
+            assert np.array_equal(L.o_unpack_reps(rev, count, n, 1), reps)
+            if count > gc:
+                assert (gc > 1) == (not np.array_equal(fwd, rev)) or gc == 1
+    for name in ("p3109_3p2", "e2m1", "p3109_5p2", "e3m2", "e2m3", "p3109_7p3", "e5m2", "e4m3fn", "p3109_8p4", "p3109_8p4_ext"):
+        f = L.CODEC_FORMATS[name]
+        reps = np.arange(1 << f.fmt.bitwidth, dtype=np.uint32)
+        vals = L.o_rep_to_float(reps, f)
+        keep = ~np.isnan(vals)
+        again = L.o_float_to_rep(vals[keep], f)
+        assert np.array_equal(again, reps[keep]), name

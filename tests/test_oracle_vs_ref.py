@@ -103,3 +103,22 @@ def test_gemm_and_rto_fma():
         u = np.float32(o.lofo_round_to_odd_fma(p, q, s)).view(np.uint32)
         v = np.float32(r.ref_round_to_odd_fma(p, q, s)).view(np.uint32)
         assert u == v, (p, q, s)
+
+
+def test_pack_codec_vs_reference():
+    """Storage codec: oracle == compiled reference (lo_pack.hpp) for every codec format x deterministic mode x
+    saturation mode on the full probe set, the exhaustive decode table, and packed bytes in both slot orders."""
+    for name, f in L.CODEC_FORMATS.items():
+        x = L.codec_probe_floats(f)
+        n = f.fmt.bitwidth
+        for mode in L.DETERMINISTIC_MODES:
+            for sat in (0, 1, 2):
+                assert np.array_equal(L.o_float_to_rep(x, f, mode, sat), L.r_float_to_rep(x, f, mode, sat)), (name, mode, sat)
+        reps = np.arange(1 << n, dtype=np.uint32)
+        assert L.bits_equal(L.o_rep_to_float(reps, f), L.r_rep_to_float(reps, f)), name
+        for endian in (0, 1):
+            for count in (1, 7, 1001, 4096 + 17):
+                xs = x[:count]
+                ea, eb = L.o_encode(xs, f, endian=endian), L.r_encode(xs, f, endian=endian)
+                assert np.array_equal(ea, eb), (name, endian, count)
+                assert L.bits_equal(L.o_decode(ea, xs.size, f, endian), L.r_decode(eb, xs.size, f, endian))
