@@ -48,6 +48,7 @@ struct Options {
     std::atomic<int64_t> mx_variant{0};
     std::atomic<int64_t> mx_ctas_per_sm{8};
     std::atomic<int64_t> host_chunk_bytes{32ll << 20};
+    std::atomic<int64_t> pack_fast{1};           // storage codec: 0 = exact integer routine only, 1 = magic-add fast path where eligible
     std::atomic<int64_t> round_fast{2};          // 0: exact kernels; 1: branch-free fast path; 2: + magic-add path (default)
 } g_opt;
 
@@ -494,6 +495,7 @@ int lof_set_option(const char* key, int64_t value)
     else if (k == "mx.variant") { if (value < 0 || value > 2) return fail(LOF_ERR_INVALID_ARG, "mx.variant must be 0, 1 or 2"); g_opt.mx_variant = value; }
     else if (k == "mx.ctas_per_sm") { if (value < 1 || value > 64) return fail(LOF_ERR_INVALID_ARG, "mx.ctas_per_sm out of range"); g_opt.mx_ctas_per_sm = value; }
     else if (k == "round.fast") { if (value < 0 || value > 2) return fail(LOF_ERR_INVALID_ARG, "round.fast must be 0, 1 or 2"); g_opt.round_fast = value; }
+    else if (k == "pack.fast") { if (value < 0 || value > 1) return fail(LOF_ERR_INVALID_ARG, "pack.fast must be 0 or 1"); g_opt.pack_fast = value; }
     else if (k == "host.chunk_bytes") { if (value < (1 << 16)) return fail(LOF_ERR_INVALID_ARG, "host.chunk_bytes too small"); g_opt.host_chunk_bytes = value; }
     else return fail(LOF_ERR_INVALID_ARG, "unknown option: " + k);
     return LOF_OK;
@@ -508,6 +510,7 @@ int lof_get_option(const char* key, int64_t* value)
     else if (k == "mx.variant") *value = g_opt.mx_variant;
     else if (k == "mx.ctas_per_sm") *value = g_opt.mx_ctas_per_sm;
     else if (k == "round.fast") *value = g_opt.round_fast;
+    else if (k == "pack.fast") *value = g_opt.pack_fast;
     else if (k == "host.chunk_bytes") *value = g_opt.host_chunk_bytes;
     else return fail(LOF_ERR_INVALID_ARG, "unknown option: " + k);
     return LOF_OK;
@@ -640,6 +643,21 @@ int make_codec_plan(const lof_codec_format_t* cf, const lof_projspec_t* ps, int 
     p->len = ps ? ps->stoch_length : 0;
     p->gc = pack_group_bits(n) / n;
     p->reverse = endian == LOF_PACK_REVERSE;
+    p->rev_xor = p->reverse ? (uint32_t)(p->gc - 1) : 0u;                   // gc = 8 / gcd(n, 8) or 16 / gcd(n, 16): a power of two
+    p->recip_n = n > 1 ? (uint32_t)(((1ull << 32) + (uint64_t)n - 1) / (uint64_t)n) : 0u;
+    // magic-add fast path: IEEE-like modes, >= 1 mantissa bit (with m = 0 the reference's RNE / round-to-odd break ties
+    // on the fp32 EXPONENT's LSB), target range inside fp32's normal range (bias <= 125 keeps lo_pack.hpp's branch 2 in
+    // charge of fp32 subnormals), every magic constant a normal fp32 number
+    const int mode = ps ? ps->rounding_mode : LOF_RoundToNearestEven;
+    const int emin_b = 128 - f.bias;                                        // biased fp32 exponent of 2^(1 - bias)
+    const int ds = p->digit_drop;
+    const bool mode_ok = mode == LOF_RoundToNearestEven || mode == LOF_RoundTowardsZero || mode == LOF_RoundAwayFromZero ||
+                         mode == LOF_RoundToOdd;
+    p->fast_ok = g_opt.pack_fast.load() && mode_ok && f.mantissa_bits >= 1 && f.bias <= 125 && emin_b >= 1 && emin_b + ds <= 254 &&
+                 to_max_exp + 127 + ds <= 254 && to_max_exp + 128 <= 254 && p->narrower && p->max_finite_rep < (1u << 16);
+    p->f_cadd = (uint32_t)ds << 23;
+    p->f_cfloor = (uint32_t)(emin_b + ds) << 23;
+    p->f_big = (uint32_t)(to_max_exp + 128) << 23;
     return LOF_OK;
 }
 }  // namespace

@@ -24,6 +24,7 @@ namespace {
 
 constexpr int kPackThreads = 256;
 constexpr int kPackPerThread = 16;
+constexpr int kLutBits = 12;
 constexpr int kPackTile = kPackThreads * kPackPerThread;     // 4096 elements: a multiple of every group count (1..16)
 
 __device__ __forceinline__ bool codec_is_nan(const CodecPlan& p, uint32_t rep)
@@ -97,6 +98,47 @@ __device__ __forceinline__ uint32_t float_to_rep(uint32_t fb, const CodecPlan& p
     return with_sign(p, (uint32_t)(rounded >> ds), neg);
 }
 
+// Magic-add formulation of the same conversion for the IEEE-like modes (see lof_fast_f32.cuh for the idea): with
+// c = 2^(max(e, emin) + 23 - m) the sum |x| (+) c lands in c's binade, whose ulp is exactly the target quantum of x
+// (2^(e - m), or denorm_min below the smallest normal), so (bits(|x| (+) c) - bits(c)) is the rounded significand in
+// quanta -- including a carry into the next binade -- and the exponent field is max(e, emin) - emin.  Eligibility is
+// decided on the host (make_codec_plan); equality with the integer routine above is established exhaustively over
+// all 2^32 inputs on the device (tests/test_gpu_parity.py::test_pack_fast_path_equals_exact_every_fp32_pattern).
+template <int MODE>
+__device__ __forceinline__ uint32_t float_to_rep_fast(uint32_t x, const CodecPlan& p)
+{
+    const uint32_t a = x & 0x7FFFFFFFu;
+    const bool neg = (x >> 31) != 0;
+    const uint32_t c = max((a & 0x7F800000u) + p.f_cadd, p.f_cfloor);
+    const float cf = __uint_as_float(c), ax = __uint_as_float(a);
+    float t;
+    if constexpr (MODE == LOF_RoundToNearestEven) t = __fadd_rn(ax, cf);
+    else if constexpr (MODE == LOF_RoundTowardsZero) t = __fadd_rz(ax, cf);
+    else if constexpr (MODE == LOF_RoundAwayFromZero) t = __fadd_ru(ax, cf);
+    else {                                                    // RoundToOdd: truncate, LSB |= inexact
+        const float tz = __fadd_rz(ax, cf), tu = __fadd_ru(ax, cf);
+        t = __uint_as_float(__float_as_uint(tz) | (tz != tu ? 1u : 0u));
+    }
+    uint32_t mag = (__float_as_uint(t) - c) + (((c - p.f_cfloor) >> 23) << p.mant);
+    mag = mag > p.max_finite_rep ? p.ovf_rep : mag;
+    if (a >= p.f_big) {
+        if (a > 0x7F800000u) return (!p.to_signed && neg) ? p.neg_unsigned_rep : p.qnan;
+        mag = (a == 0x7F800000u) ? p.inf_in_rep : p.ovf_rep;
+    }
+    if (neg) {
+        if (!p.to_signed) return p.neg_unsigned_rep;
+        if (!(mag == 0u && p.sign_is_nan)) mag |= p.signmask;
+    }
+    return mag;
+}
+
+__device__ __noinline__ float rep_to_float_wide(uint32_t ef, uint32_t mf, bool sign, int mant, int bias)
+{
+    const double v = ef == 0u ? ldexp((double)mf, 1 - bias - mant)
+                              : ldexp(1.0 + (double)mf / (double)(1u << mant), (int)ef - bias);
+    return (float)(sign ? -v : v);
+}
+
 // lo_pack.hpp:277-319
 __device__ __forceinline__ float rep_to_float(uint32_t rep, const CodecPlan& p)
 {
@@ -110,22 +152,15 @@ __device__ __forceinline__ float rep_to_float(uint32_t rep, const CodecPlan& p)
     if (ef == 0u) {
         const int e = 1 - p.bias - p.mant;                    // value = mf * 2^e
         if (e >= -126 && e <= 100) return __uint_as_float(__float_as_uint(__fmul_rn(__uint2float_rn(mf), __uint_as_float((uint32_t)(e + 127) << 23))) | s);
-        return (float)(sign ? -ldexp((double)mf, e) : ldexp((double)mf, e));
+        return rep_to_float_wide(ef, mf, sign, p.mant, p.bias);
     }
     const int E = (int)ef - p.bias + 127;
     if (E >= 1 && E <= 254) return __uint_as_float(s | ((uint32_t)E << 23) | (mf << (23 - p.mant)));
-    const double v = ldexp(1.0 + (double)mf / (double)(1u << p.mant), (int)ef - p.bias);
-    return (float)(sign ? -v : v);
+    return rep_to_float_wide(ef, mf, sign, p.mant, p.bias);
 }
 
-__device__ __forceinline__ int slot_to_elem(int slot, int gc, int reverse)
-{
-    if (!reverse) return slot;
-    const int g = slot / gc, j = slot - g * gc;
-    return g * gc + (gc - 1 - j);
-}
 
-template <int MODE>
+template <int MODE, bool FAST>
 __global__ void __launch_bounds__(kPackThreads)
 encode_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int64_t count, uint64_t packed_bytes,
               const CodecPlan p, const RngArgs rng, uint64_t first_index, int vec_ok, int word_ok)
@@ -133,30 +168,76 @@ encode_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int64_t 
     __shared__ uint16_t reps[kPackTile];
     const int64_t ntiles = (count + kPackTile - 1) / kPackTile;
     const int words_per_tile = kPackTile / 32 * p.n;          // 128 n
+    const bool direct = word_ok && (p.n == 8 || p.n == 16 || p.n == 4);
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t base = tile * kPackTile;
-        // ---- phase 1: one rep per element ----
+        // ---- phase 1: one rep per element (all four 16-byte loads of the thread are issued before the first use) ----
+        uint4 v[kPackPerThread / 4];
+#pragma unroll
+        for (int u = 0; u < kPackPerThread / 4; ++u) {
+            const int64_t i = base + (u * kPackThreads + (int)threadIdx.x) * 4;
+            v[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (vec_ok && i + 3 < count) {
+                v[u] = __ldcs(reinterpret_cast<const uint4*>(src + i));
+            } else {
+                if (i < count) v[u].x = __float_as_uint(src[i]);
+                if (i + 1 < count) v[u].y = __float_as_uint(src[i + 1]);
+                if (i + 2 < count) v[u].z = __float_as_uint(src[i + 2]);
+                if (i + 3 < count) v[u].w = __float_as_uint(src[i + 3]);
+            }
+        }
 #pragma unroll
         for (int u = 0; u < kPackPerThread / 4; ++u) {
             const int local = (u * kPackThreads + (int)threadIdx.x) * 4;
             const int64_t i = base + local;
-            uint32_t x[4] = {0u, 0u, 0u, 0u};
-            if (vec_ok && i + 3 < count) {
-                const uint4 v = __ldcs(reinterpret_cast<const uint4*>(src + i));
-                x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-            } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) if (i + e < count) x[e] = __float_as_uint(src[i + e]);
-            }
+            const uint32_t x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
             uint32_t r[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                uint32_t w = 0u;
-                if constexpr (ModeTraits<MODE>::kUsesRng) w = philox_event(rng, first_index + (uint64_t)(i + e));
-                r[e] = (i + e < count) ? float_to_rep<MODE>(x[e], p, w) : 0u;        // partial group: encode(0.0f) == 0 (:425-429)
+                if constexpr (FAST) {
+                    r[e] = float_to_rep_fast<MODE>(x[e], p);       // elements past `count` were loaded as +0.0 -> rep 0
+                } else {
+                    uint32_t w = 0u;
+                    if constexpr (ModeTraits<MODE>::kUsesRng) w = philox_event(rng, first_index + (uint64_t)(i + e));
+                    r[e] = (i + e < count) ? float_to_rep<MODE>(x[e], p, w) : 0u;    // partial group: encode(0.0f) == 0 (:425-429)
+                }
             }
-            *reinterpret_cast<uint2*>(&reps[local]) = make_uint2((r[0] & 0xFFFFu) | (r[1] << 16), (r[2] & 0xFFFFu) | (r[3] << 16));
+            if (direct) {
+                // n = 8 / 16 / 4: the thread's four consecutive elements are whole groups and land on byte boundaries of
+                // their own -> packed straight from registers (no staging, no barrier); slot order only swaps nibbles
+                if (p.n == 8) {
+                    const uint32_t word = (r[0] & 0xFFu) | ((r[1] & 0xFFu) << 8) | ((r[2] & 0xFFu) << 16) | (r[3] << 24);
+                    if (i + 3 < count) __stcs(reinterpret_cast<uint32_t*>(dst + i), word);
+                    else for (int b = 0; b < 4 && i + b < count; ++b) dst[i + b] = (uint8_t)(word >> (8 * b));
+                } else if (p.n == 16) {
+                    const uint32_t w0 = (r[0] & 0xFFFFu) | (r[1] << 16), w1 = (r[2] & 0xFFFFu) | (r[3] << 16);
+                    if (i + 3 < count) {
+                        __stcs(reinterpret_cast<uint32_t*>(dst + 2 * i), w0);
+                        __stcs(reinterpret_cast<uint32_t*>(dst + 2 * i + 4), w1);
+                    } else {
+                        const uint32_t ww[2] = {w0, w1};
+                        for (int e = 0; e < 4 && i + e < count; ++e) reinterpret_cast<uint16_t*>(dst)[i + e] = (uint16_t)(ww[e >> 1] >> (16 * (e & 1)));
+                    }
+                } else {    // n == 4, two elements per byte
+                    const uint32_t lo0 = p.reverse ? r[1] : r[0], hi0 = p.reverse ? r[0] : r[1];
+                    const uint32_t lo1 = p.reverse ? r[3] : r[2], hi1 = p.reverse ? r[2] : r[3];
+                    const uint32_t half = (lo0 & 0xFu) | ((hi0 & 0xFu) << 4) | ((lo1 & 0xFu) << 8) | ((hi1 & 0xFu) << 12);
+                    const uint64_t byte = (uint64_t)i >> 1;
+                    const uint32_t pair = half | (__shfl_down_sync(0xFFFFFFFFu, half, 1) << 16);       // even lane: 8 elements = one word
+                    const uint64_t wbyte = byte & ~(uint64_t)3;
+                    if (wbyte + 4u <= packed_bytes) {
+                        if ((threadIdx.x & 1) == 0) __stcs(reinterpret_cast<uint32_t*>(dst + byte), pair);
+                    } else if (byte + 2u <= packed_bytes) {
+                        __stcs(reinterpret_cast<uint16_t*>(dst + byte), (uint16_t)half);
+                    } else if (byte < packed_bytes) {
+                        dst[byte] = (uint8_t)half;
+                    }
+                }
+            } else {
+                *reinterpret_cast<uint2*>(&reps[local]) = make_uint2((r[0] & 0xFFFFu) | (r[1] << 16), (r[2] & 0xFFFFu) | (r[3] << 16));
+            }
         }
+        if (direct) continue;
         __syncthreads();
         // ---- phase 2: whole 32-bit words of the packed stream ----
         const uint64_t tile_byte = (uint64_t)tile * (uint64_t)words_per_tile * 4u;
@@ -165,9 +246,10 @@ encode_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int64_t 
             if (byte >= packed_bytes) break;
             const int bit0 = k * 32;
             uint32_t word = 0u;
-            for (int slot = bit0 / p.n; slot * p.n < bit0 + 32; ++slot) {
-                const uint32_t rep = reps[slot_to_elem(slot, p.gc, p.reverse)] & p.rep_mask;
-                const int sh = slot * p.n - bit0;
+            int slot = p.n == 1 ? bit0 : (int)__umulhi((uint32_t)bit0, p.recip_n);
+            for (int sb = slot * p.n; sb < bit0 + 32; ++slot, sb += p.n) {
+                const uint32_t rep = reps[slot ^ p.rev_xor] & p.rep_mask;
+                const int sh = sb - bit0;
                 word |= sh >= 0 ? (rep << sh) : (rep >> (-sh));
             }
             if (word_ok && byte + 4u <= packed_bytes) {
@@ -185,10 +267,63 @@ decode_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int64_t 
               const CodecPlan p, int vec_ok, int word_ok)
 {
     __shared__ uint32_t words[kPackTile / 32 * 16 + 1];
+    __shared__ float lut[1 << kLutBits];                      // n <= 12: every representation decoded once per CTA
+    const bool use_lut = p.n <= kLutBits;
+    if (use_lut) {
+        for (int r = threadIdx.x; r < (1 << p.n); r += kPackThreads) lut[r] = rep_to_float((uint32_t)r, p);
+        __syncthreads();
+    }
     const int64_t ntiles = (count + kPackTile - 1) / kPackTile;
     const int words_per_tile = kPackTile / 32 * p.n;
+    const bool direct = word_ok && (p.n == 8 || p.n == 16 || p.n == 4);
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t base = tile * kPackTile;
+        if (direct) {
+            // n = 8 / 16 / 4: each thread reads the bytes of its own four elements (mirror of the encode fast lane)
+            uint32_t raw[kPackPerThread / 4][2];
+#pragma unroll
+            for (int u = 0; u < kPackPerThread / 4; ++u) {
+                const int64_t i = base + (u * kPackThreads + (int)threadIdx.x) * 4;
+                raw[u][0] = raw[u][1] = 0u;
+                if (i >= count) continue;
+                if (p.n == 8) {
+                    if (i + 3 < count) raw[u][0] = __ldcs(reinterpret_cast<const uint32_t*>(src + i));
+                    else for (int b = 0; b < 4 && i + b < count; ++b) raw[u][0] |= (uint32_t)src[i + b] << (8 * b);
+                } else if (p.n == 16) {
+                    if (i + 3 < count) {
+                        raw[u][0] = __ldcs(reinterpret_cast<const uint32_t*>(src + 2 * i));
+                        raw[u][1] = __ldcs(reinterpret_cast<const uint32_t*>(src + 2 * i + 4));
+                    } else {
+                        for (int e = 0; e < 4 && i + e < count; ++e)
+                            raw[u][e >> 1] |= (uint32_t)reinterpret_cast<const uint16_t*>(src)[i + e] << (16 * (e & 1));
+                    }
+                } else {
+                    const uint64_t byte = (uint64_t)i >> 1;
+                    if (byte + 2u <= packed_bytes) raw[u][0] = __ldcs(reinterpret_cast<const uint16_t*>(src + byte));
+                    else if (byte < packed_bytes) raw[u][0] = src[byte];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kPackPerThread / 4; ++u) {
+                const int64_t i = base + (u * kPackThreads + (int)threadIdx.x) * 4;
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    uint32_t rep;
+                    if (p.n == 8) rep = (raw[u][0] >> (8 * e)) & 0xFFu;
+                    else if (p.n == 16) rep = (raw[u][e >> 1] >> (16 * (e & 1))) & 0xFFFFu;
+                    else rep = (raw[u][0] >> (4 * (e ^ (int)p.rev_xor))) & 0xFu;
+                    o[e] = use_lut ? lut[rep] : rep_to_float(rep, p);
+                }
+                if (vec_ok && i + 3 < count) {
+                    __stcs(reinterpret_cast<float4*>(dst + i), make_float4(o[0], o[1], o[2], o[3]));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) if (i + e < count) dst[i + e] = o[e];
+                }
+            }
+            continue;
+        }
         const uint64_t tile_byte = (uint64_t)tile * (uint64_t)words_per_tile * 4u;
         for (int k = threadIdx.x; k <= words_per_tile; k += kPackThreads) {
             const uint64_t byte = tile_byte + (uint64_t)k * 4u;
@@ -208,10 +343,11 @@ decode_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int64_t 
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int el = local + e;
-                const int slot = slot_to_elem(el, p.gc, p.reverse);          // the slot <-> element map is an involution
+                const int slot = el ^ (int)p.rev_xor;                          // the slot <-> element map is an involution
                 const int bit = slot * p.n;
                 const uint64_t two = (uint64_t)words[bit >> 5] | ((uint64_t)words[(bit >> 5) + 1] << 32);
-                o[e] = rep_to_float((uint32_t)(two >> (bit & 31)) & p.rep_mask, p);
+                const uint32_t rep = (uint32_t)(two >> (bit & 31)) & p.rep_mask;
+                o[e] = use_lut ? lut[rep] : rep_to_float(rep, p);
             }
             if (vec_ok && i + 3 < count) {
                 __stcs(reinterpret_cast<float4*>(dst + i), make_float4(o[0], o[1], o[2], o[3]));
@@ -239,8 +375,16 @@ cudaError_t launch_encode(int mode, const float* src, uint8_t* dst, int64_t coun
     const int vec_ok = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
     const int word_ok = (reinterpret_cast<uintptr_t>(dst) & 3u) == 0;
     const unsigned grid = pack_grid(count, num_sms);
+    if (p.fast_ok) {
+        switch (mode) {
+#define LOF_CASE(M) case M: encode_kernel<M, true><<<grid, kPackThreads, 0, stream>>>(src, dst, count, packed_bytes, p, rng, first_index, vec_ok, word_ok); return cudaGetLastError();
+            LOF_CASE(LOF_RoundToNearestEven) LOF_CASE(LOF_RoundTowardsZero) LOF_CASE(LOF_RoundAwayFromZero) LOF_CASE(LOF_RoundToOdd)
+#undef LOF_CASE
+        default: break;
+        }
+    }
     switch (mode) {
-#define LOF_CASE(M) case M: encode_kernel<M><<<grid, kPackThreads, 0, stream>>>(src, dst, count, packed_bytes, p, rng, first_index, vec_ok, word_ok); break;
+#define LOF_CASE(M) case M: encode_kernel<M, false><<<grid, kPackThreads, 0, stream>>>(src, dst, count, packed_bytes, p, rng, first_index, vec_ok, word_ok); break;
         LOF_CASE(LOF_RoundToNearestEven) LOF_CASE(LOF_RoundTowardsZero) LOF_CASE(LOF_RoundAwayFromZero)
         LOF_CASE(LOF_StochasticRoundingA) LOF_CASE(LOF_RoundToNearestOdd) LOF_CASE(LOF_RoundDown)
         LOF_CASE(LOF_RoundUp) LOF_CASE(LOF_RoundTiesToAway) LOF_CASE(LOF_StochasticRoundingB)

@@ -27,6 +27,13 @@ struct CodecPlan {
     uint32_t neg_unsigned_rep;      // negative input, unsigned format (:156-161)
     uint32_t qnan;
     uint32_t inf_mask, inf_value, nan_mask, nan_value, nan_mant_mask;
+    uint32_t rev_xor;               // slot <-> element map inside a group: index ^ rev_xor (group counts are powers of two)
+    uint32_t recip_n;               // ceil(2^32 / n) for n > 1: floor(x / n) == __umulhi(x, recip_n) for x < 2^16
+    // magic-add fast path (RNE, toward zero, away, round-to-odd on formats whose whole range sits inside fp32's normal
+    // range): rep = ((max(e, emin) - emin) << m) + ((|x| (+) c) - c), c = 2^(max(e, emin) + 23 - m)   (lof_pack.cu)
+    uint32_t fast_ok;
+    uint32_t f_cadd, f_cfloor;      // (23 - m) << 23, (emin_biased + 23 - m) << 23
+    uint32_t f_big;                 // |x| bits >= f_big: certain overflow, infinity or NaN
 };
 
 cudaError_t launch_encode(int mode, const float* src, uint8_t* dst, int64_t count, uint64_t packed_bytes, const CodecPlan& p,

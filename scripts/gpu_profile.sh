@@ -42,6 +42,12 @@ for t in $TARGETS; do
     gemm_tc_hw)
       timeout 600 $NCU_FULL -k regex:gemm_tc_kernel -s 2 -c 1 -o $OUT/gemm_tc_hw python scripts/prof_target.py gemm_tc 8192 hw > $OUT/gemm_tc_hw.log 2>&1
       echo "gemm_tc_hw exit $?"; export_rep gemm_tc_hw ;;
+    pack8)
+      timeout 600 $NCU_FULL -k regex:"encode_kernel|decode_kernel" -s 2 -c 2 -o $OUT/pack8 python scripts/prof_target.py pack e4m3 > $OUT/pack8.log 2>&1
+      echo "pack8 exit $?"; export_rep pack8 ;;
+    pack4)
+      timeout 600 $NCU_FULL -k regex:"encode_kernel|decode_kernel" -s 2 -c 2 -o $OUT/pack4 python scripts/prof_target.py pack e2m1 > $OUT/pack4.log 2>&1
+      echo "pack4 exit $?"; export_rep pack4 ;;
     gemm_pair)
       timeout 600 $NCU_FULL -k regex:gemm_tc_pair_kernel -s 1 -c 1 -o $OUT/gemm_pair python scripts/prof_target.py gemm_tc 8192 hw > $OUT/gemm_pair.log 2>&1
       echo "gemm_pair exit $?"; export_rep gemm_pair ;;

@@ -43,6 +43,14 @@ def main():
         x *= torch.exp2(torch.randint(-8, 9, (16384, 1), device=dev, generator=g).float())
         for _ in range(4):
             y = lof.virtual_mx_round(x, 32, f, lof.create_e8m0_params())
+    elif what == "pack":
+        f = fmt(sys.argv[2] if len(sys.argv) > 2 else "e4m3")
+        n = 1 << 28
+        x = torch.randn(n, device=dev, generator=g)
+        x *= torch.exp2(torch.randint(-6, 7, (n,), device=dev, generator=g).float())
+        for _ in range(3):
+            p = lof.lof_encode(x, f)
+            y = lof.lof_decode(p, n, f)
     elif what == "gemm_tc":
         import numpy as np
         M = int(sys.argv[2]) if len(sys.argv) > 2 else 4096

@@ -781,3 +781,44 @@ def test_gemm_on_packed_operands_equals_fp32_container_path(lof, cuda_dev):
         want = lof.lof_gemm(_gpu(A, cuda_dev), _gpu(B, cuda_dev), mant, **kw)
         got = lof.lof_gemm_packed(Ap, Btp, mant, **kw)
         assert torch.equal(got, want), kw
+
+
+def test_pack_fast_path_equals_exact_every_fp32_pattern(lof, cuda_dev):
+    """The magic-add encode path (pack.fast = 1, default) against the exact integer routine (pack.fast = 0, pinned to
+    the oracle / compiled reference above) on EVERY fp32 bit pattern, for every eligible codec format, the four
+    IEEE-like modes and all three saturation modes under RNE.  Compared on the device."""
+    from lofloat_b200 import _lib
+    lib = _lib.lib()
+    chunk = 1 << 28
+    stream = torch.cuda.current_stream().cuda_stream
+    checked = 0
+
+    def enc(x, f, mode, sat, out):
+        ps = _lib.CProjSpec(mode, sat, 0)
+        st = lib.lof_encode_f32(x.data_ptr(), out.data_ptr(), x.numel(), C.cast(C.byref(f), C.POINTER(_lib.CCodecFormat)),
+                                C.byref(ps), 0, None, 0, stream)
+        assert st == 0, lib.lof_last_error_string().decode()
+    try:
+        for name in ("e2m1", "e3m2", "e2m3", "p3109_5p2", "e5m2", "e4m3fn", "p3109_8p4", "p3109_8p4_ext", "p3109_8p3_unsigned",
+                     "p3109_8p3_unsigned_ext_nan", "p3109_11p5", "half"):
+            f = L.CODEC_FORMATS[name]
+            nbytes = L.packed_size(f.fmt.bitwidth, chunk)
+            a = torch.empty(nbytes, dtype=torch.uint8, device=cuda_dev)
+            b = torch.empty(nbytes, dtype=torch.uint8, device=cuda_dev)
+            for mode, sat in ((L.RNE, 0), (L.RNE, 1), (L.RNE, 2), (L.RTZ, 0), (L.RAZ, 0), (L.RTO, 0)):
+                for base in range(0, 1 << 32, chunk):
+                    x = torch.arange(base, base + chunk, device=cuda_dev, dtype=torch.int64).to(torch.int32).view(torch.float32)
+                    _lib.set_option("pack.fast", 0)
+                    enc(x, f, mode, sat, b)
+                    _lib.set_option("pack.fast", 1)
+                    enc(x, f, mode, sat, a)
+                    if not torch.equal(a, b):
+                        idx = int((a != b).nonzero()[0])
+                        raise AssertionError(f"{name} {L.MODE_NAMES[mode]} sat{sat}: packed byte {idx} of chunk 0x{base:08x} "
+                                             f"fast=0x{int(a[idx]):02x} exact=0x{int(b[idx]):02x}")
+                    checked += chunk
+                    del x
+            del a, b
+    finally:
+        _lib.set_option("pack.fast", 1)
+    assert checked == 12 * 6 * (1 << 32)
