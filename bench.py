@@ -249,6 +249,10 @@ def run_ours(args):
         other = side_measurements(torch, lib, _lib, dev, x, y, stream)
         if world == 1:
             cpu_baseline = cpu_reference_sample(x[: 1 << 24].cpu().numpy(), budget_s=20.0)
+            try:
+                other.update(c1_and_cpu_side(torch, dev))
+            except Exception as exc:
+                other["cpu_side_error"] = str(exc)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -395,6 +399,83 @@ def side_measurements(torch, lib, _lib, dev, x, y, stream):
             del packed, back
     except Exception as exc:
         out["lof_gemm_tc_error"] = str(exc)
+    return out
+
+
+def c1_and_cpu_side(torch, dev):
+    """C1 (BASELINE.json configs[0]: fp32 -> E4M3 RNE saturating on 2^24 elements, the reference's own CPU-runnable
+    case, benchmark/vec_round.cpp) on the GPU next to the reference's xsimd array loop and scalar loop on this box's
+    cores, plus bounded CPU samples of C3 (mx_round) and C4 (BLIS lof GEMM) so every GPU number above has its CPU
+    counterpart measured in the same run.  Reported baselines, not targets."""
+    import numpy as np
+    import lofloat_b200 as lof
+    L, kind = _load_cpu_impl()
+    threads = os.cpu_count() or 1
+    out = {}
+    n = 1 << 24
+    g = torch.Generator(device=dev).manual_seed(12345)
+    x = torch.randn(n, device=dev, generator=g) * 4
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)               # > L2 (126 MB): C1's 64 MiB input would otherwise stay cached
+    xn = x.cpu().numpy()
+    for label, d, f in (("e4m3_bias7", lof.create_p3109_params(8, 4, bias=7), L.FORMATS["e4m3_b7"]),
+                        ("p3109_8p4_bias8", lof.create_p3109_params(8, 4), L.FORMATS["p3109_8p4"])):
+        lof.virtual_round(x, d)
+        best = 1e9
+        for _ in range(20):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            lof.virtual_round(x, d)
+            b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        entry = {"gpu_GBps": 8.0 * n / (best * 1e-3) / 1e9, "gpu_ms_best_of_20": best, "l2": "flushed between launches (256 MiB fill)"}
+        if kind == "reference":
+            lib = L.ref()
+            buf_in, buf_out = xn.copy(), np.empty_like(xn)
+            bt = 1e9
+            for _ in range(7):
+                t0 = time.perf_counter()
+                lib.ref_round_params_array_f32(L._ptr(buf_in), L._ptr(buf_out), n, f.bitwidth, f.mantissa_bits, f.bias, f.ov_behavior,
+                                               f.na_behavior, f.is_signed, 0, 0)
+                bt = min(bt, time.perf_counter() - t0)
+            entry["cpu_xsimd_array_GBps"] = 8.0 * n / bt / 1e9
+            entry["cpu_xsimd_note"] = (f"lo_float.h:2942 xsimd loop, -O3 -march=x86-64-v3 -fopenmp -D_LOFOPENMP, {threads} threads, best of 7 "
+                                       "(not an oracle: drops signs / flushes subnormals, SURVEY B.10)")
+            bt = 1e9
+            for _ in range(3):
+                t0 = time.perf_counter()
+                L.r_round_params(xn, f, 0, 0, threads=threads)
+                bt = min(bt, time.perf_counter() - t0)
+            entry["cpu_scalar_loop_GBps"] = 8.0 * n / bt / 1e9
+        out[f"C1_virtual_round_2^24_{label}"] = entry
+    del flush
+    # C3 on the CPU: the reference's virtual_mx_round is a serial loop (lo_float.h:4311-4383)
+    m = 1 << 22
+    xm = (np.random.default_rng(7).standard_normal(m)).astype(np.float32)
+    t0 = time.perf_counter()
+    if kind == "reference":
+        L.r_mx_round(xm, 32, L.FORMATS["e8m0"], L.FORMATS["e4m3_b7"])
+    else:
+        L.o_mx_round(xm, 32, L.FORMATS["e8m0"], L.FORMATS["e4m3_b7"])
+    dt = time.perf_counter() - t0
+    out["C3_cpu_mx_round_mxfp8"] = {"GBps": 8.0 * m / dt / 1e9, "cores": 1 if kind == "reference" else threads, "kind": kind,
+                                    "sample": f"2^22 elements, block 32, {dt:.2f} s"}
+    # C4 on the CPU: BLIS generic + lof_sgemm_ukr (per-FMA rounding to 10 mantissa bits), bounded size
+    k = 1536
+    rng = np.random.default_rng(42)
+    A = L.o_round_params(rng.uniform(-1, 1, (k * k)).astype(np.float32), L.FORMATS["e4m3_b7"]).reshape(k, k)
+    B = L.o_round_params(rng.uniform(-1, 1, (k * k)).astype(np.float32), L.FORMATS["e4m3_b7"]).reshape(k, k)
+    t0 = time.perf_counter()
+    if kind == "reference" and L.ref().ref_has_blis():
+        L.r_gemm(A, B, 10, threads=threads)
+        gk = "reference"
+    else:
+        L.o_gemm(A, B, 10)
+        gk = "port"
+    dt = time.perf_counter() - t0
+    out["C4_cpu_lof_gemm_accum10"] = {"GFLOPs": 2.0 * k ** 3 / dt / 1e9, "cores": threads, "kind": gk,
+                                      "sample": f"{k}^3, bli_sgemm + lof_sgemm_ukr (BLIS generic, KC = 256), {dt:.1f} s"}
     return out
 
 

@@ -220,6 +220,15 @@ LOF_API int lof_encode_f32(const float* src, uint8_t* dst, int64_t count, const 
 LOF_API int lof_decode_f32(const uint8_t* src, float* dst, int64_t count, const lof_codec_format_t* fmt, int endian,
                            void* stream);
 
+/* Strict typed-semantics rounding as an elementwise op: out[i] = decode(encode(in[i]))
+ * in one pass = (float)Templated_Float<Fp>(in[i]), the typed conversion ConvertImpl::run (src/lo_float.h:3057-3364,
+ * runtime twin src/lo_pack.hpp:109-319; behaviour spec test/test_sat_mode.cpp:11-18, test/test_unsigned.cpp): overflow
+ * goes to +-inf or +-max by Saturation_Mode and OV_behavior, NaN to the format's NaN (read back as +qNaN), negatives into
+ * unsigned formats to zero or NaN.  virtual_round (lof_round_params) keeps the reference's container semantics instead.
+ * fp32 only, bitwidth in [1, 16], out may alias in. */
+LOF_API int lof_round_strict_f32(const float* in, float* out, int64_t n, const lof_codec_format_t* fmt,
+                                 const lof_projspec_t* ps, const lof_rng_t* rng, uint64_t first_index, void* stream);
+
 /* Chunked tensor-core GEMM on operands that are ALREADY stored as 8-bit representations (what lof_encode_f32
  * produces for e4m3fn / e5m2): A is M x K bytes row-major, Bt is N x K bytes row-major (B transposed, K-major --
  * the [out_features, in_features] weight layout of LoF_Linear, LoFloat/layers.py:160-161).  operand_dtype is

@@ -697,6 +697,30 @@ int lof_encode_f32(const float* src, uint8_t* dst, int64_t count, const lof_code
     return LOF_OK;
 }
 
+int lof_round_strict_f32(const float* in, float* out, int64_t n, const lof_codec_format_t* fmt, const lof_projspec_t* ps,
+                         const lof_rng_t* rng, uint64_t first_index, void* stream)
+{
+    if (n < 0) return fail(LOF_ERR_INVALID_ARG, "n < 0");
+    if (!ps) return fail(LOF_ERR_INVALID_ARG, "projspec is NULL");
+    const int mode = ps->rounding_mode;
+    if (mode < 0 || mode >= LOF_NUM_ROUNDING_MODES) return fail(LOF_ERR_INVALID_ARG, "unknown rounding mode");
+    CodecPlan p;
+    const int st = make_codec_plan(fmt, ps, LOF_PACK_FORWARD, &p);
+    if (st != LOF_OK) return st;
+    if ((mode == LOF_StochasticRoundingA || mode == LOF_StochasticRoundingB || mode == LOF_StochasticRoundingC ||
+         mode == LOF_StochasticRoundingD) && (ps->stoch_length < 0 || ps->stoch_length > p.digit_drop || ps->stoch_length > 31))
+        return fail(LOF_ERR_INVALID_ARG, "stoch_length must be in [0, 23 - mantissa_bits]");
+    if (n == 0) return LOF_OK;
+    if (!in || !out) return fail(LOF_ERR_INVALID_ARG, "null tensor pointer");
+    const int sms = num_sms();
+    if (sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    const RngArgs ra = make_rng(rng, kStreamElem, mode, ps->stoch_length);
+    cudaError_t e = launch_round_strict(mode, in, out, n, p, ra, first_index, sms, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "lof_round_strict launch");
+    g_launches.fetch_add(1);
+    return LOF_OK;
+}
+
 int lof_decode_f32(const uint8_t* src, float* dst, int64_t count, const lof_codec_format_t* fmt, int endian, void* stream)
 {
     if (count < 0) return fail(LOF_ERR_INVALID_ARG, "count < 0");

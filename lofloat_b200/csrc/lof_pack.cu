@@ -360,6 +360,66 @@ decode_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int64_t 
     }
 }
 
+// Strict typed-semantics rounding as an elementwise op: out = decode(encode(x)) in one
+// pass, i.e. (float)Templated_Float<Fp>(x) -- ConvertImpl::run (lo_float.h:3057-3364) through its runtime twin in
+// lo_pack.hpp -- with Saturation_Mode (OvfInf / SatFinite / SatPropagate), signed infinities, clamp-to-max and the
+// NegtoZero / NegtoNaN policies, unlike virtual_round's container semantics.  8 B / element, HBM-bound.
+template <int MODE, bool FAST>
+__global__ void __launch_bounds__(kPackThreads)
+round_strict_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t count, const CodecPlan p, const RngArgs rng,
+                    uint64_t first_index, int vec_ok)
+{
+    __shared__ float lut[1 << kLutBits];
+    const bool use_lut = p.n <= kLutBits;
+    if (use_lut) {
+        for (int r = threadIdx.x; r < (1 << p.n); r += kPackThreads) lut[r] = rep_to_float((uint32_t)r, p);
+        __syncthreads();
+    }
+    const int64_t ntiles = (count + kPackTile - 1) / kPackTile;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t base = tile * kPackTile;
+        uint4 v[kPackPerThread / 4];
+#pragma unroll
+        for (int u = 0; u < kPackPerThread / 4; ++u) {
+            const int64_t i = base + (u * kPackThreads + (int)threadIdx.x) * 4;
+            v[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (vec_ok && i + 3 < count) {
+                v[u] = __ldcs(reinterpret_cast<const uint4*>(src + i));
+            } else {
+                if (i < count) v[u].x = __float_as_uint(src[i]);
+                if (i + 1 < count) v[u].y = __float_as_uint(src[i + 1]);
+                if (i + 2 < count) v[u].z = __float_as_uint(src[i + 2]);
+                if (i + 3 < count) v[u].w = __float_as_uint(src[i + 3]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kPackPerThread / 4; ++u) {
+            const int64_t i = base + (u * kPackThreads + (int)threadIdx.x) * 4;
+            const uint32_t x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                uint32_t rep;
+                if constexpr (FAST) {
+                    rep = float_to_rep_fast<MODE>(x[e], p);
+                } else {
+                    uint32_t w = 0u;
+                    if constexpr (ModeTraits<MODE>::kUsesRng) w = philox_event(rng, first_index + (uint64_t)(i + e));
+                    rep = float_to_rep<MODE>(x[e], p, w);
+                }
+                rep &= p.rep_mask;
+                o[e] = use_lut ? lut[rep] : rep_to_float(rep, p);
+            }
+            if (vec_ok && i + 3 < count) {
+                __stcs(reinterpret_cast<float4*>(dst + i), make_float4(o[0], o[1], o[2], o[3]));
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (i + e < count) dst[i + e] = o[e];
+            }
+        }
+    }
+}
+
 unsigned pack_grid(int64_t count, int num_sms)
 {
     const int64_t ntiles = (count + kPackTile - 1) / kPackTile;
@@ -385,6 +445,33 @@ cudaError_t launch_encode(int mode, const float* src, uint8_t* dst, int64_t coun
     }
     switch (mode) {
 #define LOF_CASE(M) case M: encode_kernel<M, false><<<grid, kPackThreads, 0, stream>>>(src, dst, count, packed_bytes, p, rng, first_index, vec_ok, word_ok); break;
+        LOF_CASE(LOF_RoundToNearestEven) LOF_CASE(LOF_RoundTowardsZero) LOF_CASE(LOF_RoundAwayFromZero)
+        LOF_CASE(LOF_StochasticRoundingA) LOF_CASE(LOF_RoundToNearestOdd) LOF_CASE(LOF_RoundDown)
+        LOF_CASE(LOF_RoundUp) LOF_CASE(LOF_RoundTiesToAway) LOF_CASE(LOF_StochasticRoundingB)
+        LOF_CASE(LOF_StochasticRoundingC) LOF_CASE(LOF_True_StochasticRounding)
+        LOF_CASE(LOF_ProbabilisticRounding) LOF_CASE(LOF_RoundToOdd) LOF_CASE(LOF_RoundTiesTowardsZero)
+        LOF_CASE(LOF_StochasticRoundingD)
+#undef LOF_CASE
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_round_strict(int mode, const float* src, float* dst, int64_t count, const CodecPlan& p, const RngArgs& rng,
+                                uint64_t first_index, int num_sms, cudaStream_t stream)
+{
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
+    const unsigned grid = pack_grid(count, num_sms);
+    if (p.fast_ok) {
+        switch (mode) {
+#define LOF_CASE(M) case M: round_strict_kernel<M, true><<<grid, kPackThreads, 0, stream>>>(src, dst, count, p, rng, first_index, vec_ok); return cudaGetLastError();
+            LOF_CASE(LOF_RoundToNearestEven) LOF_CASE(LOF_RoundTowardsZero) LOF_CASE(LOF_RoundAwayFromZero) LOF_CASE(LOF_RoundToOdd)
+#undef LOF_CASE
+        default: break;
+        }
+    }
+    switch (mode) {
+#define LOF_CASE(M) case M: round_strict_kernel<M, false><<<grid, kPackThreads, 0, stream>>>(src, dst, count, p, rng, first_index, vec_ok); break;
         LOF_CASE(LOF_RoundToNearestEven) LOF_CASE(LOF_RoundTowardsZero) LOF_CASE(LOF_RoundAwayFromZero)
         LOF_CASE(LOF_StochasticRoundingA) LOF_CASE(LOF_RoundToNearestOdd) LOF_CASE(LOF_RoundDown)
         LOF_CASE(LOF_RoundUp) LOF_CASE(LOF_RoundTiesToAway) LOF_CASE(LOF_StochasticRoundingB)

@@ -38,6 +38,8 @@ struct CodecPlan {
 
 cudaError_t launch_encode(int mode, const float* src, uint8_t* dst, int64_t count, uint64_t packed_bytes, const CodecPlan& p,
                           const RngArgs& rng, uint64_t first_index, int num_sms, cudaStream_t stream);
+cudaError_t launch_round_strict(int mode, const float* src, float* dst, int64_t count, const CodecPlan& p, const RngArgs& rng,
+                                uint64_t first_index, int num_sms, cudaStream_t stream);
 cudaError_t launch_decode(const uint8_t* src, float* dst, int64_t count, uint64_t packed_bytes, const CodecPlan& p, int num_sms,
                           cudaStream_t stream);
 

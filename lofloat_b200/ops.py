@@ -441,6 +441,29 @@ def lof_decode(packed: torch.Tensor, count: int, params: FloatFormatDescriptor, 
     return out
 
 
+def virtual_round_strict(input: torch.Tensor, params: FloatFormatDescriptor, round_mode=RoundingMode.RoundToNearestEven,
+                         stoch_len: int = 0, saturation_mode=SaturationMode.OvfInf, *, unsigned_behavior: int = 0, rng=None,
+                         first_index: int = 0) -> torch.Tensor:
+    """Strict typed-semantics rounding: (float)Templated_Float<Fp>(x) elementwise (ConvertImpl::run, lo_float.h:3057-3364)
+    -- overflow to +-inf / +-max by `saturation_mode`, NaN propagation, NegtoZero / NegtoNaN -- as one fused pass."""
+    if input.dtype != torch.float32:
+        raise RuntimeError("virtual_round_strict: float32 tensors only")
+    if not input.is_cuda:
+        raise RuntimeError("virtual_round_strict requires a CUDA tensor")
+    L = _lib.lib()
+    mode = RoundingMode(int(round_mode))
+    ps = CProjSpec(int(mode), int(saturation_mode), int(stoch_len))
+    r = _next_rng(mode in _STOCHASTIC, rng)
+    cf = codec_format(params, unsigned_behavior)
+    x = input.contiguous()
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        st = L.lof_round_strict_f32(x.data_ptr(), out.data_ptr(), x.numel(), C.byref(cf), C.byref(ps), C.byref(r), int(first_index),
+                                    _stream_ptr(x))
+    _lib.check(st, "virtual_round_strict")
+    return out
+
+
 def lof_gemm_packed(A: torch.Tensor, Bt: torch.Tensor, accum_mant_bits: int, round_mode=RoundingMode.RoundToNearestEven,
                     scale_a: float = 1.0, scale_b: float = 1.0, *, k_chunk: int = 32,
                     accum_format: FloatFormatDescriptor | None = None, operand_dtype: str = "e4m3",

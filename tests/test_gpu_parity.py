@@ -822,3 +822,62 @@ def test_pack_fast_path_equals_exact_every_fp32_pattern(lof, cuda_dev):
     finally:
         _lib.set_option("pack.fast", 1)
     assert checked == 12 * 6 * (1 << 32)
+
+
+def test_strict_typed_rounding_op(lof, cuda_dev):
+    """Row f-2: lof_round_strict_f32 == decode(encode(x)) of the oracle codec (pinned to the compiled reference's lo_pack.hpp,
+    itself validated against Templated_Float<Fp> by test/test_pack.cpp) for every codec format x deterministic mode x
+    saturation mode, stochastic modes on the oracle's Philox stream, the behaviours test/test_sat_mode.cpp:11-18 spells
+    out, and agreement with the committed typed ground truth."""
+    from lofloat_b200 import _lib
+    lib = _lib.lib()
+
+    def strict(x, f, mode=0, sat=0, sl=0, seed=0, offset=0, first_index=0):
+        xt = _gpu(x, cuda_dev)
+        out = torch.empty_like(xt)
+        ps, rng = _lib.CProjSpec(mode, sat, sl), _lib.CRng(seed, offset)
+        st = lib.lof_round_strict_f32(xt.data_ptr(), out.data_ptr(), x.size, C.cast(C.byref(f), C.POINTER(_lib.CCodecFormat)),
+                                      C.byref(ps), C.byref(rng), first_index, torch.cuda.current_stream().cuda_stream)
+        assert st == 0, lib.lof_last_error_string().decode()
+        return _np(out)
+    for name, f in L.CODEC_FORMATS.items():
+        x = L.codec_probe_floats(f)
+        for mode in L.DETERMINISTIC_MODES:
+            for sat in ((0, 1, 2) if mode in (L.RNE, L.RTZ) else (0,)):
+                want = L.o_rep_to_float(L.o_float_to_rep(x, f, mode, sat), f)
+                assert L.bits_equal(strict(x, f, mode, sat), want), (name, L.MODE_NAMES[mode], sat)
+    f = L.CODEC_FORMATS["e5m2"]
+    x = L.wide_random_f32(40001, 8)[:40001]
+    for mode, sl in ((L.SR_A, 7), (L.SR_D, 5), (L.TRUE_SR, 0), (L.PROB, 0)):
+        want = L.o_rep_to_float(L.o_float_to_rep(x, f, mode, 0, sl, seed=4, offset=1, first_index=64), f)
+        assert L.bits_equal(strict(x, f, mode, 0, sl, seed=4, offset=1, first_index=64), want), L.MODE_NAMES[mode]
+    # test_sat_mode.cpp:11-18: finite overflow -> inf under OvfInf, max finite under SatFinite / SatPropagate; inf input -> inf
+    # under OvfInf / SatPropagate, max finite under SatFinite (formats with infinities); saturating formats always clamp
+    ext, sat8 = L.CODEC_FORMATS["p3109_8p4_ext"], L.CODEC_FORMATS["p3109_8p4"]
+    big = np.array([1e30, -1e30, np.inf, -np.inf], np.float32)
+    mx = float(L.o_rep_to_float(np.array([0x7E], np.uint32), ext)[0])
+    assert np.array_equal(strict(big, ext, 0, 0), np.array([np.inf, -np.inf, np.inf, -np.inf], np.float32))
+    assert np.array_equal(strict(big, ext, 0, 1), np.array([mx, -mx, mx, -mx], np.float32))
+    assert np.array_equal(strict(big, ext, 0, 2), np.array([mx, -mx, np.inf, -np.inf], np.float32))
+    smx = float(L.o_rep_to_float(np.array([0x7F], np.uint32), sat8)[0])
+    for sat in (0, 1, 2):
+        assert np.array_equal(strict(big, sat8, 0, sat), np.array([smx, -smx, smx, -smx], np.float32))
+    # negatives into unsigned formats: NegtoZero / NegtoNaN (test/test_unsigned.cpp)
+    neg = np.array([-1.0, -0.0, -np.inf, 2.0], np.float32)
+    got = strict(neg, L.CODEC_FORMATS["p3109_8p3_unsigned"])
+    assert np.array_equal(got[:3], np.zeros(3, np.float32)) and got[3] == 2.0
+    got = strict(neg, L.CODEC_FORMATS["p3109_8p3_unsigned_ext_nan"])
+    assert np.all(np.isnan(got[:3])) and got[3] == 2.0
+    # typed ground truth (Templated_Float<Fp>) committed with the golden vectors
+    g = np.load(G / "pack_codec.npz")
+    for tag, key in (("typed_e4m3fn", "e4m3fn"), ("typed_p3109_8p4", "p3109_8p4")):
+        x, back = g[f"{tag}__x"], g[f"{tag}__back"]
+        got = strict(x, L.CODEC_FORMATS[key])
+        keep = ~np.isnan(back)
+        assert L.bits_equal(got[keep], back[keep]) and np.all(np.isnan(got[~keep])), tag
+    # Python surface + full size: idempotent projection at 2^28 elements
+    d = lof.create_p3109_params(8, 4, saturating=False)
+    xt = torch.randn(1 << 28, device=cuda_dev) * 37.0
+    y = lof.virtual_round_strict(xt, d, saturation_mode=lof.SaturationMode.SatFinite)
+    assert torch.equal(lof.virtual_round_strict(y, d, saturation_mode=lof.SaturationMode.SatFinite), y)
+    assert float(y.abs().max()) == mx
