@@ -220,6 +220,20 @@ LOF_API int lof_encode_f32(const float* src, uint8_t* dst, int64_t count, const 
 LOF_API int lof_decode_f32(const uint8_t* src, float* dst, int64_t count, const lof_codec_format_t* fmt, int endian,
                            void* stream);
 
+/* MX quantisation with MATERIALISED scales (real MXFP8 / MXFP6 / MXFP4 storage; containers src/Matrix.h:79-176
+ * MX_Matrix = element array + shared_exps array): the blocks, amax, scale and element rounding of virtual_mx_round
+ * (src/lo_float.h:4311-4383) composed with the storage codec (src/lo_pack.hpp):
+ *     scales[b] = convert_float_to_rep(scale_b, scale format)                       one byte per block
+ *     elems     = packed convert_float_to_rep(virtual_round(x / scale_b, element format))   4-, 6- or 8-bit elements
+ * decode(elems) * decode(scales) == lof_mx_round_f32's output wherever that value is representable (virtual_round returns
+ * an overflowing x / scale unchanged for Saturating formats; storage clamps it).  block_size in {16, 32, 64, 128},
+ * n % block_size == 0, `in` / `out` 16-byte and `elems` 4-byte aligned.  elems holds lof_packed_size(bits, n) bytes. */
+LOF_API int lof_mx_encode_f32(const float* in, int64_t n, int block_size, const lof_codec_format_t* scale_fmt,
+                              const lof_codec_format_t* elem_fmt, const lof_projspec_t* ps_scale, const lof_projspec_t* ps_elem,
+                              int endian, const lof_rng_t* rng, uint64_t first_index, uint8_t* scales, uint8_t* elems, void* stream);
+LOF_API int lof_mx_decode_f32(const uint8_t* scales, const uint8_t* elems, float* out, int64_t n, int block_size,
+                              const lof_codec_format_t* scale_fmt, const lof_codec_format_t* elem_fmt, int endian, void* stream);
+
 /* Strict typed-semantics rounding as an elementwise op: out[i] = decode(encode(in[i]))
  * in one pass = (float)Templated_Float<Fp>(in[i]), the typed conversion ConvertImpl::run (src/lo_float.h:3057-3364,
  * runtime twin src/lo_pack.hpp:109-319; behaviour spec test/test_sat_mode.cpp:11-18, test/test_unsigned.cpp): overflow

@@ -721,6 +721,90 @@ int lof_round_strict_f32(const float* in, float* out, int64_t n, const lof_codec
     return LOF_OK;
 }
 
+namespace {
+int mx_storage_check(int64_t n, int block_size, const lof_codec_format_t* scale_fmt, const lof_codec_format_t* elem_fmt)
+{
+    if (n < 0) return fail(LOF_ERR_INVALID_ARG, "n < 0");
+    if (!scale_fmt || !elem_fmt) return fail(LOF_ERR_INVALID_ARG, "codec format is NULL");
+    if (block_size != 16 && block_size != 32 && block_size != 64 && block_size != 128)
+        return fail(LOF_ERR_UNSUPPORTED, "mx storage: block_size must be 16, 32, 64 or 128");
+    if (n % block_size != 0) return fail(LOF_ERR_INVALID_ARG, "mx storage: n must be a multiple of block_size");
+    if (elem_fmt->fmt.bitwidth != 4 && elem_fmt->fmt.bitwidth != 6 && elem_fmt->fmt.bitwidth != 8)
+        return fail(LOF_ERR_UNSUPPORTED, "mx storage: element formats of 4, 6 or 8 bits (MXFP4 / MXFP6 / MXFP8)");
+    if (scale_fmt->fmt.bitwidth < 1 || scale_fmt->fmt.bitwidth > 8)
+        return fail(LOF_ERR_UNSUPPORTED, "mx storage: the scale format must fit one byte");
+    return LOF_OK;
+}
+}  // namespace
+
+int lof_mx_encode_f32(const float* in, int64_t n, int block_size, const lof_codec_format_t* scale_fmt,
+                      const lof_codec_format_t* elem_fmt, const lof_projspec_t* ps_scale, const lof_projspec_t* ps_elem, int endian,
+                      const lof_rng_t* rng, uint64_t first_index, uint8_t* scales, uint8_t* elems, void* stream)
+{
+    int st = mx_storage_check(n, block_size, scale_fmt, elem_fmt);
+    if (st != LOF_OK) return st;
+    if (!ps_scale || !ps_elem) return fail(LOF_ERR_INVALID_ARG, "projspec is NULL");
+    if (first_index % (uint64_t)block_size != 0) return fail(LOF_ERR_INVALID_ARG, "first_index must be a multiple of block_size");
+    MxArgs a;
+    std::memset(&a, 0, sizeof a);
+    st = make_plan(&elem_fmt->fmt, LOF_F32, ps_elem->rounding_mode, ps_elem->stoch_length, &a.elem);
+    if (st != LOF_OK) return st;
+    st = make_plan(&scale_fmt->fmt, LOF_F32, ps_scale->rounding_mode, 0, &a.scale);
+    if (st != LOF_OK) return st;
+    a.pmn = lof_mx_priv_max_normal(&elem_fmt->fmt);
+    a.scale_mode = ps_scale->rounding_mode;
+    a.block_size = block_size;
+    lof_projspec_t exact = {LOF_RoundTowardsZero, LOF_OvfInf, 0};
+    CodecPlan cs, ce;
+    st = make_codec_plan(scale_fmt, &exact, LOF_PACK_FORWARD, &cs);
+    if (st != LOF_OK) return st;
+    st = make_codec_plan(elem_fmt, &exact, endian, &ce);
+    if (st != LOF_OK) return st;
+    // the element rounding + conversion collapse into the codec's magic-add path when that path is eligible for the
+    // ELEMENT rounding mode and the two overflow policies agree (virtual_round: unchanged -> clamped by the conversion,
+    // or +inf for Extended formats; codec under OvfInf: max finite for Saturating formats, inf for Extended ones)
+    lof_projspec_t elem_ps = {ps_elem->rounding_mode, LOF_OvfInf, 0};
+    CodecPlan probe;
+    st = make_codec_plan(elem_fmt, &elem_ps, endian, &probe);
+    if (st != LOF_OK) return st;
+    const bool fast = probe.fast_ok != 0 && !probe.has_inf;     // Extended formats: virtual_round sends every overflow to +inf (sign dropped)
+    if (fast) ce = probe;
+    if (n == 0) return LOF_OK;
+    if (!in || !scales || !elems) return fail(LOF_ERR_INVALID_ARG, "null tensor pointer");
+    if ((reinterpret_cast<uintptr_t>(in) & 15u) || (reinterpret_cast<uintptr_t>(elems) & 3u))
+        return fail(LOF_ERR_INVALID_ARG, "mx storage: `in` must be 16-byte and `elems` 4-byte aligned");
+    const int sms = num_sms();
+    if (sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    const RngArgs re = make_rng(rng, kStreamElem, ps_elem->rounding_mode, ps_elem->stoch_length), rs = make_rng(rng, kStreamScale);
+    cudaError_t e = launch_mx_encode(ps_elem->rounding_mode, in, n, a, cs, ce, re, rs, first_index, scales, elems, sms, fast,
+                                     static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "lof_mx_encode launch");
+    g_launches.fetch_add(1);
+    return LOF_OK;
+}
+
+int lof_mx_decode_f32(const uint8_t* scales, const uint8_t* elems, float* out, int64_t n, int block_size,
+                      const lof_codec_format_t* scale_fmt, const lof_codec_format_t* elem_fmt, int endian, void* stream)
+{
+    int st = mx_storage_check(n, block_size, scale_fmt, elem_fmt);
+    if (st != LOF_OK) return st;
+    CodecPlan cs, ce;
+    st = make_codec_plan(scale_fmt, nullptr, LOF_PACK_FORWARD, &cs);
+    if (st != LOF_OK) return st;
+    st = make_codec_plan(elem_fmt, nullptr, endian, &ce);
+    if (st != LOF_OK) return st;
+    if (n == 0) return LOF_OK;
+    if (!out || !scales || !elems) return fail(LOF_ERR_INVALID_ARG, "null tensor pointer");
+    if ((reinterpret_cast<uintptr_t>(out) & 15u) || (reinterpret_cast<uintptr_t>(elems) & 3u))
+        return fail(LOF_ERR_INVALID_ARG, "mx storage: `out` must be 16-byte and `elems` 4-byte aligned");
+    const int sms = num_sms();
+    if (sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    cudaError_t e = launch_mx_decode(scales, elems, out, n, block_size, cs, ce, sms, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "lof_mx_decode launch");
+    g_launches.fetch_add(1);
+    return LOF_OK;
+}
+
 int lof_decode_f32(const uint8_t* src, float* dst, int64_t count, const lof_codec_format_t* fmt, int endian, void* stream)
 {
     if (count < 0) return fail(LOF_ERR_INVALID_ARG, "count < 0");

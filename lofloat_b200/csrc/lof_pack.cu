@@ -16,6 +16,7 @@
 #include <stdint.h>
 
 #include "lof_core.cuh"
+#include "lof_mx_kernels.cuh"
 #include "lof_pack.cuh"
 
 namespace lof {
@@ -104,12 +105,23 @@ __device__ __forceinline__ uint32_t float_to_rep(uint32_t fb, const CodecPlan& p
 // quanta -- including a carry into the next binade -- and the exponent field is max(e, emin) - emin.  Eligibility is
 // decided on the host (make_codec_plan); equality with the integer routine above is established exhaustively over
 // all 2^32 inputs on the device (tests/test_gpu_parity.py::test_pack_fast_path_equals_exact_every_fp32_pattern).
+// launch-uniform constants of the fast path, copied out of the parameter bank once per thread
+struct FastConsts {
+    uint32_t cadd, cfloor, big, max_finite, ovf, inf_in, qnan, signmask, neg_unsigned;
+    int ds, sign_shift;
+    bool to_signed, sign_is_nan;
+    __device__ __forceinline__ explicit FastConsts(const CodecPlan& p)
+        : cadd(p.f_cadd), cfloor(p.f_cfloor), big(p.f_big), max_finite(p.max_finite_rep), ovf(p.ovf_rep), inf_in(p.inf_in_rep),
+          qnan(p.qnan), signmask(p.signmask), neg_unsigned(p.neg_unsigned_rep), ds(p.digit_drop), sign_shift(32 - p.n),
+          to_signed(p.to_signed != 0), sign_is_nan(p.sign_is_nan != 0) {}
+};
+
+// ~15 instructions per element: the stream has to stay under ~20 to be HBM- rather than ALU-bound (ncu r01g).
 template <int MODE>
-__device__ __forceinline__ uint32_t float_to_rep_fast(uint32_t x, const CodecPlan& p)
+__device__ __forceinline__ uint32_t float_to_rep_fast(uint32_t x, const FastConsts& k)
 {
     const uint32_t a = x & 0x7FFFFFFFu;
-    const bool neg = (x >> 31) != 0;
-    const uint32_t c = max((a & 0x7F800000u) + p.f_cadd, p.f_cfloor);
+    const uint32_t c = max((a & 0x7F800000u) + k.cadd, k.cfloor);
     const float cf = __uint_as_float(c), ax = __uint_as_float(a);
     float t;
     if constexpr (MODE == LOF_RoundToNearestEven) t = __fadd_rn(ax, cf);
@@ -119,17 +131,20 @@ __device__ __forceinline__ uint32_t float_to_rep_fast(uint32_t x, const CodecPla
         const float tz = __fadd_rz(ax, cf), tu = __fadd_ru(ax, cf);
         t = __uint_as_float(__float_as_uint(tz) | (tz != tu ? 1u : 0u));
     }
-    uint32_t mag = (__float_as_uint(t) - c) + (((c - p.f_cfloor) >> 23) << p.mant);
-    mag = mag > p.max_finite_rep ? p.ovf_rep : mag;
-    if (a >= p.f_big) {
-        if (a > 0x7F800000u) return (!p.to_signed && neg) ? p.neg_unsigned_rep : p.qnan;
-        mag = (a == 0x7F800000u) ? p.inf_in_rep : p.ovf_rep;
+    // (c - cfloor) has 23 zero low bits, so >> ds places max(e, emin) - emin directly above the m mantissa bits
+    uint32_t mag = (__float_as_uint(t) + ((c - k.cfloor) >> k.ds)) - c;
+    mag = mag > k.max_finite ? k.ovf : mag;
+    uint32_t xs = x;                                          // carries the sign that is attached to the result
+    if (a >= k.big) {                                         // certain overflow, infinity or NaN: rare
+        mag = a > 0x7F800000u ? k.qnan : (a == 0x7F800000u ? k.inf_in : k.ovf);
+        if (a > 0x7F800000u) xs = a;                          // a NaN result carries no sign (lo_pack.hpp:170)
     }
-    if (neg) {
-        if (!p.to_signed) return p.neg_unsigned_rep;
-        if (!(mag == 0u && p.sign_is_nan)) mag |= p.signmask;
+    if (k.to_signed) {                                        // launch-uniform
+        uint32_t sbit = (xs >> k.sign_shift) & k.signmask;
+        if (k.sign_is_nan) sbit = mag == 0u ? 0u : sbit;      // no -0 when the sign-bit-only pattern is the NaN (:147-152)
+        return mag | sbit;
     }
-    return mag;
+    return (int32_t)x < 0 ? k.neg_unsigned : mag;             // any negative input incl. -0, -inf, -NaN (:156-161)
 }
 
 __device__ __noinline__ float rep_to_float_wide(uint32_t ef, uint32_t mf, bool sign, int mant, int bias)
@@ -166,6 +181,7 @@ encode_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int64_t 
               const CodecPlan p, const RngArgs rng, uint64_t first_index, int vec_ok, int word_ok)
 {
     __shared__ uint16_t reps[kPackTile];
+    const FastConsts fk(p);
     const int64_t ntiles = (count + kPackTile - 1) / kPackTile;
     const int words_per_tile = kPackTile / 32 * p.n;          // 128 n
     const bool direct = word_ok && (p.n == 8 || p.n == 16 || p.n == 4);
@@ -195,7 +211,7 @@ encode_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int64_t 
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 if constexpr (FAST) {
-                    r[e] = float_to_rep_fast<MODE>(x[e], p);       // elements past `count` were loaded as +0.0 -> rep 0
+                    r[e] = float_to_rep_fast<MODE>(x[e], fk);      // elements past `count` were loaded as +0.0 -> rep 0
                 } else {
                     uint32_t w = 0u;
                     if constexpr (ModeTraits<MODE>::kUsesRng) w = philox_event(rng, first_index + (uint64_t)(i + e));
@@ -375,6 +391,7 @@ round_strict_kernel(const float* __restrict__ src, float* __restrict__ dst, int6
         for (int r = threadIdx.x; r < (1 << p.n); r += kPackThreads) lut[r] = rep_to_float((uint32_t)r, p);
         __syncthreads();
     }
+    const FastConsts fk(p);
     const int64_t ntiles = (count + kPackTile - 1) / kPackTile;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t base = tile * kPackTile;
@@ -401,7 +418,7 @@ round_strict_kernel(const float* __restrict__ src, float* __restrict__ dst, int6
             for (int e = 0; e < 4; ++e) {
                 uint32_t rep;
                 if constexpr (FAST) {
-                    rep = float_to_rep_fast<MODE>(x[e], p);
+                    rep = float_to_rep_fast<MODE>(x[e], fk);
                 } else {
                     uint32_t w = 0u;
                     if constexpr (ModeTraits<MODE>::kUsesRng) w = philox_event(rng, first_index + (uint64_t)(i + e));
@@ -417,6 +434,108 @@ round_strict_kernel(const float* __restrict__ src, float* __restrict__ dst, int6
                 for (int e = 0; e < 4; ++e) if (i + e < count) dst[i + e] = o[e];
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MX quantisation with MATERIALISED scales: virtual_mx_round's block / amax / scale / element rounding
+// (lo_float.h:4311-4383, same device routines as lof_mx_kernels.cuh) composed with the codec above:
+// one scale byte per block + packed element representations (4-, 6- or 8-bit) instead of fp32 fake-quant values.
+// A lane owns 4 consecutive elements (one 128-bit load), a block is BS / 4 lanes of one warp (amax by shfl.xor).
+// 4 B read + (n/8 + 1/BS) B written per element.
+// ------------------------------------------------------------------------------------------------
+template <int MODE, bool FAST>
+__global__ void __launch_bounds__(kPackThreads)
+mx_encode_kernel(const float4* __restrict__ in, int64_t nvec, MxArgs a, CodecPlan scale_codec, CodecPlan elem_codec, RngArgs rng,
+                 RngArgs rng_scale, uint64_t first_index, uint8_t* __restrict__ scales, uint8_t* __restrict__ elems)
+{
+    const int lanes = a.block_size >> 2;                         // lanes per block: 4 .. 32
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * kPackThreads;
+    const int64_t nvec_pad = (nvec + 31) & ~(int64_t)31;         // whole warps stay converged for the shuffles
+    const FastConsts fk(elem_codec);
+    for (int64_t v = (int64_t)blockIdx.x * kPackThreads + threadIdx.x; v < nvec_pad; v += stride) {
+        const bool live_lane = v < nvec;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live_lane) x = __ldcs(in + v);
+        float amax = fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w)));       // NaN-dropping like std::max(amax, |x|)
+        for (int o = lanes >> 1; o >= 1; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, o));
+        const uint64_t g0 = first_index + (uint64_t)v * 4u;
+        // the block's scale and its stored byte: computed by the block's first lane only, then broadcast
+        const bool head = (lane & (lanes - 1)) == 0;
+        float scale = 0.0f;
+        if (head && live_lane) {
+            scale = mx_block_scale(amax, a, rng_scale, g0 / (uint64_t)a.block_size);
+            scales[(v * 4) / a.block_size] = (uint8_t)float_to_rep<LOF_RoundTowardsZero>(__float_as_uint(scale), scale_codec, 0u);
+        }
+        scale = __shfl_sync(0xFFFFFFFFu, scale, lane & ~(lanes - 1));
+        if (!live_lane) continue;
+        const MxBlockCtx ctx = mx_make_ctx(scale);
+        uint32_t r[4] = {0u, 0u, 0u, 0u};
+        if (ctx.live) {
+            const float xs[4] = {x.x, x.y, x.z, x.w};
+            uint4 w4 = make_uint4(0u, 0u, 0u, 0u);
+            if constexpr (ModeTraits<MODE>::kUsesRng) w4 = philox_group4(rng, g0 >> 2);         // g0 % 4 == 0 (host-checked)
+            const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float y = ctx.pow2 ? __fmul_rn(xs[e], ctx.recip) : __fdiv_rn(xs[e], ctx.scale);   // == x / scale bit for bit
+                if constexpr (FAST) {
+                    // rep(virtual_round(y)) == the codec's own rounding of y for the IEEE-like modes on eligible formats
+                    // (both are the correctly rounded grid value; overflow clamps to the same code): one magic add
+                    r[e] = float_to_rep_fast<MODE>(__float_as_uint(y), fk) & elem_codec.rep_mask;
+                } else {
+                    const uint32_t q = round_params_elem<LOF_F32, MODE>(__float_as_uint(y), a.elem, w[e]);
+                    r[e] = float_to_rep<LOF_RoundTowardsZero>(q, elem_codec, 0u) & elem_codec.rep_mask;   // q is on the grid: exact
+                }
+            }
+        }
+        if (elem_codec.reverse && elem_codec.gc > 1) {           // slot order inside a group (gc = 2 for 4-bit, 4 for 6-bit)
+            if (elem_codec.gc == 2) { uint32_t t = r[0]; r[0] = r[1]; r[1] = t; t = r[2]; r[2] = r[3]; r[3] = t; }
+            else { uint32_t t = r[0]; r[0] = r[3]; r[3] = t; t = r[1]; r[1] = r[2]; r[2] = t; }
+        }
+        if (elem_codec.n == 8) {
+            __stcs(reinterpret_cast<uint32_t*>(elems) + v, r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24));
+        } else if (elem_codec.n == 4) {
+            __stcs(reinterpret_cast<uint16_t*>(elems) + v, (uint16_t)(r[0] | (r[1] << 4) | (r[2] << 8) | (r[3] << 12)));
+        } else {                                                 // 6-bit: four elements = one 3-byte group
+            const uint32_t g = r[0] | (r[1] << 6) | (r[2] << 12) | (r[3] << 18);
+            uint8_t* d = elems + v * 3;
+            d[0] = (uint8_t)g; d[1] = (uint8_t)(g >> 8); d[2] = (uint8_t)(g >> 16);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kPackThreads)
+mx_decode_kernel(const uint8_t* __restrict__ scales, const uint8_t* __restrict__ elems, float4* __restrict__ out, int64_t nvec,
+                 int block_size, CodecPlan scale_codec, CodecPlan elem_codec)
+{
+    __shared__ float lut_e[256], lut_s[256];
+    for (int r = threadIdx.x; r < 256; r += kPackThreads) {
+        lut_e[r] = rep_to_float((uint32_t)r & elem_codec.rep_mask, elem_codec);
+        lut_s[r] = rep_to_float((uint32_t)r & scale_codec.rep_mask, scale_codec);
+    }
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * kPackThreads;
+    for (int64_t v = (int64_t)blockIdx.x * kPackThreads + threadIdx.x; v < nvec; v += stride) {
+        uint32_t r[4];
+        if (elem_codec.n == 8) {
+            const uint32_t w = __ldcs(reinterpret_cast<const uint32_t*>(elems) + v);
+            r[0] = w & 0xFFu; r[1] = (w >> 8) & 0xFFu; r[2] = (w >> 16) & 0xFFu; r[3] = w >> 24;
+        } else if (elem_codec.n == 4) {
+            const uint32_t w = __ldcs(reinterpret_cast<const uint16_t*>(elems) + v);
+            r[0] = w & 0xFu; r[1] = (w >> 4) & 0xFu; r[2] = (w >> 8) & 0xFu; r[3] = (w >> 12) & 0xFu;
+        } else {
+            const uint8_t* d = elems + v * 3;
+            const uint32_t g = (uint32_t)d[0] | ((uint32_t)d[1] << 8) | ((uint32_t)d[2] << 16);
+            r[0] = g & 0x3Fu; r[1] = (g >> 6) & 0x3Fu; r[2] = (g >> 12) & 0x3Fu; r[3] = (g >> 18) & 0x3Fu;
+        }
+        if (elem_codec.reverse && elem_codec.gc > 1) {
+            if (elem_codec.gc == 2) { uint32_t t = r[0]; r[0] = r[1]; r[1] = t; t = r[2]; r[2] = r[3]; r[3] = t; }
+            else { uint32_t t = r[0]; r[0] = r[3]; r[3] = t; t = r[1]; r[1] = r[2]; r[2] = t; }
+        }
+        const float s = lut_s[scales[(v * 4) / block_size]];
+        __stcs(out + v, make_float4(__fmul_rn(lut_e[r[0]], s), __fmul_rn(lut_e[r[1]], s), __fmul_rn(lut_e[r[2]], s), __fmul_rn(lut_e[r[3]], s)));
     }
 }
 
@@ -481,6 +600,46 @@ cudaError_t launch_round_strict(int mode, const float* src, float* dst, int64_t 
 #undef LOF_CASE
     default: return cudaErrorInvalidValue;
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mx_encode(int mode, const float* in, int64_t n, const MxArgs& a, const CodecPlan& scale_codec, const CodecPlan& elem_codec,
+                             const RngArgs& rng, const RngArgs& rng_scale, uint64_t first_index, uint8_t* scales, uint8_t* elems, int num_sms,
+                             bool fast, cudaStream_t stream)
+{
+    const int64_t nvec = n / 4;
+    const int64_t want = (nvec + kPackThreads - 1) / kPackThreads, cap = (int64_t)num_sms * 8;
+    const unsigned grid = (unsigned)(want < 1 ? 1 : want < cap ? want : cap);
+    const float4* vin = reinterpret_cast<const float4*>(in);
+    if (fast) {
+        switch (mode) {
+#define LOF_CASE(M) case M: mx_encode_kernel<M, true><<<grid, kPackThreads, 0, stream>>>(vin, nvec, a, scale_codec, elem_codec, rng, rng_scale, first_index, scales, elems); return cudaGetLastError();
+            LOF_CASE(LOF_RoundToNearestEven) LOF_CASE(LOF_RoundTowardsZero) LOF_CASE(LOF_RoundAwayFromZero) LOF_CASE(LOF_RoundToOdd)
+#undef LOF_CASE
+        default: break;
+        }
+    }
+    switch (mode) {
+#define LOF_CASE(M) case M: mx_encode_kernel<M, false><<<grid, kPackThreads, 0, stream>>>(vin, nvec, a, scale_codec, elem_codec, rng, rng_scale, first_index, scales, elems); break;
+        LOF_CASE(LOF_RoundToNearestEven) LOF_CASE(LOF_RoundTowardsZero) LOF_CASE(LOF_RoundAwayFromZero)
+        LOF_CASE(LOF_StochasticRoundingA) LOF_CASE(LOF_RoundToNearestOdd) LOF_CASE(LOF_RoundDown)
+        LOF_CASE(LOF_RoundUp) LOF_CASE(LOF_RoundTiesToAway) LOF_CASE(LOF_StochasticRoundingB)
+        LOF_CASE(LOF_StochasticRoundingC) LOF_CASE(LOF_True_StochasticRounding)
+        LOF_CASE(LOF_ProbabilisticRounding) LOF_CASE(LOF_RoundToOdd) LOF_CASE(LOF_RoundTiesTowardsZero)
+        LOF_CASE(LOF_StochasticRoundingD)
+#undef LOF_CASE
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mx_decode(const uint8_t* scales, const uint8_t* elems, float* out, int64_t n, int block_size, const CodecPlan& scale_codec,
+                             const CodecPlan& elem_codec, int num_sms, cudaStream_t stream)
+{
+    const int64_t nvec = n / 4;
+    const int64_t want = (nvec + kPackThreads - 1) / kPackThreads, cap = (int64_t)num_sms * 8;
+    const unsigned grid = (unsigned)(want < 1 ? 1 : want < cap ? want : cap);
+    mx_decode_kernel<<<grid, kPackThreads, 0, stream>>>(scales, elems, reinterpret_cast<float4*>(out), nvec, block_size, scale_codec, elem_codec);
     return cudaGetLastError();
 }
 

@@ -464,6 +464,44 @@ def virtual_round_strict(input: torch.Tensor, params: FloatFormatDescriptor, rou
     return out
 
 
+def mx_encode(input: torch.Tensor, block_size: int, element_format: FloatFormatDescriptor, scale_format: FloatFormatDescriptor,
+              round_mode=RoundingMode.RoundToNearestEven, scale_round_mode=RoundingMode.RoundToNearestEven, stoch_len: int = 0,
+              endian=PackEndian.Forward, *, rng=None, first_index: int = 0):
+    """MX quantisation to real storage: returns (scales uint8 [numel / block_size], packed elements uint8).  Blocks run
+    along the flattened tensor (keep K last), same scale / element rounding as virtual_mx_round."""
+    if input.dtype != torch.float32 or not input.is_cuda:
+        raise RuntimeError("mx_encode: float32 CUDA tensors only")
+    L = _lib.lib()
+    mode, smode = RoundingMode(int(round_mode)), RoundingMode(int(scale_round_mode))
+    ps_e, ps_s = CProjSpec(int(mode), 0, int(stoch_len)), CProjSpec(int(smode), 0, 0)
+    r = _next_rng(mode in _STOCHASTIC or smode in _STOCHASTIC, rng)
+    x = input.contiguous()
+    n = x.numel()
+    cfe, cfs = codec_format(element_format), codec_format(scale_format)
+    scales = torch.empty(max(n // max(int(block_size), 1), 0), dtype=torch.uint8, device=x.device)
+    elems = torch.empty(packed_size(element_format.total_bits, n), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        st = L.lof_mx_encode_f32(x.data_ptr(), n, int(block_size), C.byref(cfs), C.byref(cfe), C.byref(ps_s), C.byref(ps_e), int(endian),
+                                 C.byref(r), int(first_index), scales.data_ptr(), elems.data_ptr(), _stream_ptr(x))
+    _lib.check(st, "mx_encode")
+    return scales, elems
+
+
+def mx_decode(scales: torch.Tensor, elems: torch.Tensor, count: int, block_size: int, element_format: FloatFormatDescriptor,
+              scale_format: FloatFormatDescriptor, endian=PackEndian.Forward) -> torch.Tensor:
+    """Inverse of mx_encode: float32 values element * scale."""
+    if scales.dtype != torch.uint8 or elems.dtype != torch.uint8 or not elems.is_cuda:
+        raise RuntimeError("mx_decode: uint8 CUDA tensors only")
+    L = _lib.lib()
+    cfe, cfs = codec_format(element_format), codec_format(scale_format)
+    out = torch.empty(int(count), dtype=torch.float32, device=elems.device)
+    with torch.cuda.device(elems.device):
+        st = L.lof_mx_decode_f32(scales.contiguous().data_ptr(), elems.contiguous().data_ptr(), out.data_ptr(), int(count), int(block_size),
+                                 C.byref(cfs), C.byref(cfe), int(endian), _stream_ptr(elems))
+    _lib.check(st, "mx_decode")
+    return out
+
+
 def lof_gemm_packed(A: torch.Tensor, Bt: torch.Tensor, accum_mant_bits: int, round_mode=RoundingMode.RoundToNearestEven,
                     scale_a: float = 1.0, scale_b: float = 1.0, *, k_chunk: int = 32,
                     accum_format: FloatFormatDescriptor | None = None, operand_dtype: str = "e4m3",

@@ -8,6 +8,7 @@
 
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
 #include <omp.h>
@@ -797,6 +798,51 @@ uint64_t lofo_decode_f32(float* dst, const uint8_t* src, uint64_t count, const l
         }
     }
     return (uint64_t)groups * (uint64_t)gb;
+}
+
+void lofo_mx_encode_f32(const float* in, int64_t n, int block_size, const lofo_codec_format* scale_fmt,
+                        const lofo_codec_format* elem_fmt, const lofo_projspec* ps_scale, const lofo_projspec* ps_elem, int endian,
+                        const lofo_rng* rng, uint64_t first_index, uint8_t* scales, uint8_t* elems)
+{
+    if (block_size <= 0 || n <= 0) return;
+    const lofo_format* pub = &scale_fmt->fmt;
+    const lofo_format* priv = &elem_fmt->fmt;
+    const float pmn = lofo_mx_priv_max_normal(priv);
+    const lofo_consts kpub = lofo_consts_make(pub), kpriv = lofo_consts_make(priv);
+    const int need_rng_e = mode_uses_rng(ps_elem->rounding_mode) && rng != NULL;
+    const int need_rng_s = mode_uses_rng(ps_scale->rounding_mode) && rng != NULL;
+    const int nbits_e = lofo_rand_bits_needed(ps_elem->rounding_mode, ps_elem->stoch_length);
+    const lofo_projspec exact = { LOFO_RTZ, LOFO_OVF_INF, 0 };          /* on-grid values convert exactly under any mode */
+    const int64_t nblocks = n / block_size;
+    uint32_t* reps = (uint32_t*)malloc((size_t)n * sizeof(uint32_t));
+#pragma omp parallel for schedule(static)
+    for (int64_t blk = 0; blk < nblocks; ++blk) {
+        const int64_t b = blk * block_size;
+        float amax = 0.0f;
+        for (int i = 0; i < block_size; ++i) { const float v = fabsf(in[b + i]); amax = (amax < v) ? v : amax; }
+        const uint64_t gblk = (first_index + (uint64_t)b) / (uint64_t)block_size;
+        const uint32_t ws = need_rng_s ? lofo_rand_word(rng, gblk, LOFO_STREAM_SCALE) : 0u;
+        const float scale = u2f(vround_params_f32(f2u(amax / pmn), pub, &kpub, ps_scale->rounding_mode, 0, ws));
+        scales[blk] = (uint8_t)lofo_float_to_rep(scale, scale_fmt, &exact, 0u);
+        for (int i = 0; i < block_size; ++i) {
+            float q = 0.0f;
+            if (scale > 0.0f) {
+                const uint32_t w = need_rng_e ? lofo_rand_event(rng, first_index + (uint64_t)(b + i), LOFO_STREAM_ELEM, nbits_e) : 0u;
+                q = u2f(vround_params_f32(f2u(in[b + i] / scale), priv, &kpriv, ps_elem->rounding_mode, ps_elem->stoch_length, w));
+            }
+            reps[b + i] = lofo_float_to_rep(q, elem_fmt, &exact, 0u);
+        }
+    }
+    lofo_pack_reps(elems, reps, (uint64_t)n, elem_fmt->fmt.bitwidth, endian);
+    free(reps);
+}
+
+void lofo_mx_decode_f32(const uint8_t* scales, const uint8_t* elems, float* out, int64_t n, int block_size,
+                        const lofo_codec_format* scale_fmt, const lofo_codec_format* elem_fmt, int endian)
+{
+    if (block_size <= 0 || n <= 0) return;
+    lofo_decode_f32(out, elems, (uint64_t)n, elem_fmt, endian);
+    for (int64_t i = 0; i < n; ++i) out[i] = out[i] * lofo_rep_to_float(scales[i / block_size], scale_fmt);
 }
 
 int lofo_num_threads(void)

@@ -153,6 +153,19 @@ uint64_t lofo_encode_f32(uint8_t* dst, const float* src, uint64_t count, const l
                          const lofo_projspec* ps, int endian, const lofo_rng* rng, uint64_t first_index);
 uint64_t lofo_decode_f32(float* dst, const uint8_t* src, uint64_t count, const lofo_codec_format* f, int endian);
 
+/* MX quantisation with MATERIALISED scales (row f-1, second half): the blocks, amax, scale and element rounding of
+ * virtual_mx_round (lo_float.h:4311-4383) composed with the storage codec (lo_pack.hpp):
+ *     scales[b] = convert_float_to_rep(scale_b, scale codec format)                      one byte per block (bitwidth <= 8)
+ *     elems     = packed convert_float_to_rep(virtual_round(x / scale_b, element format), element codec format)
+ * (a zero / non-positive scale gives an all-zero block).  decode(elems) * decode(scale) reproduces virtual_mx_round
+ * wherever the fake-quant value is representable (virtual_round returns an overflowing input unchanged for
+ * Saturating formats; storage necessarily clamps it).  n % block_size == 0. */
+void lofo_mx_encode_f32(const float* in, int64_t n, int block_size, const lofo_codec_format* scale_fmt,
+                        const lofo_codec_format* elem_fmt, const lofo_projspec* ps_scale, const lofo_projspec* ps_elem, int endian,
+                        const lofo_rng* rng, uint64_t first_index, uint8_t* scales, uint8_t* elems);
+void lofo_mx_decode_f32(const uint8_t* scales, const uint8_t* elems, float* out, int64_t n, int block_size,
+                        const lofo_codec_format* scale_fmt, const lofo_codec_format* elem_fmt, int endian);
+
 int lofo_num_threads(void);
 
 #ifdef __cplusplus

@@ -197,6 +197,8 @@ def oracle():
         lib.lofo_encode_f32.restype = u64
         lib.lofo_decode_f32.argtypes = [vp, u8p, u64, PC, i32]
         lib.lofo_decode_f32.restype = u64
+        lib.lofo_mx_encode_f32.argtypes = [vp, i64, i32, PC, PC, PP, PP, i32, PR, u64, vp, vp]
+        lib.lofo_mx_decode_f32.argtypes = [vp, vp, vp, i64, i32, PC, PC, i32]
         _oracle = lib
     return _oracle
 
@@ -527,3 +529,22 @@ def codec_probe_floats(f: CodecFormat) -> np.ndarray:
         return np.concatenate([fin, np.nextafter(fin, np.float32(np.inf)), np.nextafter(fin, np.float32(-np.inf)), mids,
                                np.nextafter(mids, np.float32(np.inf)), np.nextafter(mids, np.float32(-np.inf)), extras,
                                wide_random_f32(4096, 77 + n)]).astype(np.float32)
+
+
+def o_mx_encode(x: np.ndarray, block: int, scale_f: CodecFormat, elem_f: CodecFormat, mode=RNE, scale_mode=RNE, stoch_len=0, endian=0,
+                seed=0, offset=0, first_index=0):
+    """-> (scales uint8 [n / block], packed elements uint8)"""
+    x = np.ascontiguousarray(x, np.float32).ravel()
+    scales = np.full(x.size // block, 0xAB, np.uint8)
+    elems = np.full(packed_size(elem_f.fmt.bitwidth, x.size), 0xAB, np.uint8)
+    ps_s, ps_e, r = ProjSpec(scale_mode, 0, 0), ProjSpec(mode, 0, stoch_len), _rng(seed, offset)
+    oracle().lofo_mx_encode_f32(_ptr(x), x.size, block, C.byref(scale_f), C.byref(elem_f), C.byref(ps_s), C.byref(ps_e), endian,
+                                C.byref(r), first_index, _ptr(scales), _ptr(elems))
+    return scales, elems
+
+
+def o_mx_decode(scales: np.ndarray, elems: np.ndarray, n: int, block: int, scale_f: CodecFormat, elem_f: CodecFormat, endian=0):
+    out = np.empty(n, np.float32)
+    oracle().lofo_mx_decode_f32(_ptr(np.ascontiguousarray(scales, np.uint8)), _ptr(np.ascontiguousarray(elems, np.uint8)), _ptr(out), n,
+                                block, C.byref(scale_f), C.byref(elem_f), endian)
+    return out

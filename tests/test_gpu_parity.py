@@ -881,3 +881,119 @@ def test_strict_typed_rounding_op(lof, cuda_dev):
     y = lof.virtual_round_strict(xt, d, saturation_mode=lof.SaturationMode.SatFinite)
     assert torch.equal(lof.virtual_round_strict(y, d, saturation_mode=lof.SaturationMode.SatFinite), y)
     assert float(y.abs().max()) == mx
+
+
+def test_ste_backward_and_cuda_graph_capture(lof, cuda_dev):
+    """Row f-4: the straight-through wrappers (layers.py:8-57) -- forward == the op, backward = grad * scale / identity --
+    and CUDA-graph safety: rounding, MX, strict rounding and the storage codec captured once and replayed on new data
+    give the eager result bit for bit (single async launches on the capturing stream, no allocation, no sync)."""
+    from lofloat_b200 import _lib
+    e4m3, e8m0 = lof.create_p3109_params(8, 4, bias=7), lof.create_e8m0_params()
+    x = torch.randn(64, 256, device=cuda_dev, requires_grad=True)
+    y = lof.STERound.apply(x, e4m3, lof.RoundingMode.RoundToNearestEven, 4.0)
+    assert torch.equal(y, lof.virtual_round(x.detach(), e4m3, scale=4.0))
+    g = torch.randn_like(y)
+    y.backward(g)
+    assert torch.equal(x.grad, g * 4.0)
+    x.grad = None
+    fid = lof.register_format(e4m3)
+    y = lof.STERound.apply(x, fid)
+    assert torch.equal(y, lof.virtual_round(x.detach(), e4m3))
+    y.sum().backward()
+    assert torch.equal(x.grad, torch.ones_like(x))
+    x.grad = None
+    y = lof.STEMXRound.apply(x, e4m3, e8m0, 32)
+    assert torch.equal(y, lof.virtual_mx_round(x.detach(), 32, e4m3, e8m0))
+    y.backward(g)
+    assert torch.equal(x.grad, g)
+    # CUDA graph: raw C-ABI launches on the capturing stream into static buffers
+    lib = _lib.lib()
+    n = 1 << 20
+    xin = torch.randn(n, device=cuda_dev)
+    out_r, out_m, out_s = torch.empty_like(xin), torch.empty_like(xin), torch.empty_like(xin)
+    out_p = torch.empty(n, dtype=torch.uint8, device=cuda_dev)
+    fmt, fe8 = e4m3._c(), e8m0._c()
+    cf = lof.codec_format(e4m3)
+    ps = _lib.CProjSpec(0, 0, 0)
+
+    def launch_all(stream):
+        assert lib.lof_round_params(xin.data_ptr(), out_r.data_ptr(), n, 0, C.byref(fmt), C.byref(ps), 1.0, None, 0, stream) == 0
+        assert lib.lof_mx_round_f32(xin.data_ptr(), out_m.data_ptr(), n, 32, C.byref(fe8), C.byref(fmt), C.byref(ps), C.byref(ps), None, 0, stream) == 0
+        assert lib.lof_round_strict_f32(xin.data_ptr(), out_s.data_ptr(), n, C.byref(cf), C.byref(ps), None, 0, stream) == 0
+        assert lib.lof_encode_f32(xin.data_ptr(), out_p.data_ptr(), n, C.byref(cf), C.byref(ps), 0, None, 0, stream) == 0
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        launch_all(s.cuda_stream)                                                # warm-up outside capture
+    s.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=s):
+        launch_all(torch.cuda.current_stream().cuda_stream)
+    for seed in (1, 2):
+        xin.copy_(torch.randn(n, device=cuda_dev, generator=torch.Generator(device=cuda_dev).manual_seed(seed)) * 3)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out_r, lof.virtual_round(xin, e4m3))
+        assert torch.equal(out_m, lof.virtual_mx_round(xin, 32, e4m3, e8m0))
+        assert torch.equal(out_s, lof.virtual_round_strict(xin, e4m3))
+        assert torch.equal(out_p, lof.lof_encode(xin, e4m3))
+
+
+def test_mx_storage_encode_decode(lof, cuda_dev):
+    """MX quantisation with materialised E8M0 scale bytes + packed MXFP8 / MXFP6 / MXFP4 elements (row f-1, second half):
+    bit-exact against the oracle composition (virtual_mx_round's scale / element rounding + lo_pack.hpp codec, both pinned
+    to the compiled reference) for every block size, element format, slot order, deterministic element / scale modes and
+    stochastic element rounding; decode(encode(x)) == virtual_mx_round(x) wherever the fake-quant value is representable;
+    16384 x 16384 (C3 shape) round trip."""
+    e8 = L.codec_e8m0()
+    elem = {"mxfp8_e4m3": (L.codec_p3109(8, 4, bias=7), lof.create_p3109_params(8, 4, bias=7), L.FORMATS["e4m3_b7"]),
+            "mxfp8_e5m2": (L.codec_p3109(8, 3, bias=15), lof.create_p3109_params(8, 3, bias=15), L.FORMATS["e5m2"]),
+            "mxfp6_e3m2": (L.codec_p3109(6, 3, bias=3), lof.create_p3109_params(6, 3, bias=3), L.FORMATS["e3m2"]),
+            "mxfp6_e2m3": (L.codec_p3109(6, 4, bias=1), lof.create_p3109_params(6, 4, bias=1), L.FORMATS["e2m3"]),
+            "mxfp4_e2m1": (L.codec_p3109(4, 2, bias=1), lof.create_p3109_params(4, 2, bias=1), L.FORMATS["e2m1"])}
+    from lofloat_b200 import formats
+    d8 = lof.FloatFormatDescriptor(8, 0, 127, lof.InfBehavior.Saturating, lof.NaNBehavior._3109, lof.Signedness.Unsigned,
+                                   formats._P3109Inf(8, False, True), formats._BitPatternNaN(0xFF))          # param_ocp_e8m0
+    rng = np.random.default_rng(21)
+    n = 128 * 300
+    x = (rng.standard_normal(n) * np.exp2(rng.integers(-20, 21, n))).astype(np.float32)
+    x[:128] = 0.0
+    x[128:256] = 2.0 ** -140                                                              # fp32-subnormal block
+    x[300] = np.float32(3e38)
+    xt = _gpu(x, cuda_dev)
+    for name, (cf, d, ff) in elem.items():
+        for bs in (16, 32, 64, 128):
+            for endian in (0, 1):
+                sc, el = lof.mx_encode(xt, bs, d, d8, endian=endian)
+                wsc, wel = L.o_mx_encode(x, bs, e8, cf, endian=endian)
+                assert np.array_equal(_np(sc), wsc), (name, bs, endian, "scales")
+                assert np.array_equal(_np(el), wel), (name, bs, endian, "elements")
+                back = _np(lof.mx_decode(sc, el, n, bs, d, d8, endian))
+                assert L.bits_equal(back, L.o_mx_decode(wsc, wel, n, bs, e8, cf, endian)), (name, bs, endian, "decode")
+        for mode, smode, sl in ((L.RTZ, L.RNE, 0), (L.RAZ, L.RU, 0), (L.RTO, L.RD, 0), (L.RNE, L.RAZ, 0), (L.SR_A, L.RNE, 6), (L.TRUE_SR, L.RNE, 0)):
+            sc, el = lof.mx_encode(xt, 32, d, d8, mode, smode, sl, rng=(5, 7))
+            wsc, wel = L.o_mx_encode(x, 32, e8, cf, mode, smode, sl, seed=5, offset=7)
+            assert np.array_equal(_np(sc), wsc) and np.array_equal(_np(el), wel), (name, L.MODE_NAMES[mode], L.MODE_NAMES[smode])
+        # against the fake-quant op: identical wherever virtual_mx_round's value is representable in the element format
+        xr = x.copy()
+        xr[128:256] = 1.5                                  # (a 2^-127 scale has no nonzero E8M0 code in lo_pack.hpp's decoder: exp field 0 reads as 0)
+        xrt = _gpu(xr, cuda_dev)
+        sc, el = lof.mx_encode(xrt, 32, d, d8, scale_round_mode=lof.RoundingMode.RoundUp)
+        fake = _np(lof.virtual_mx_round(xrt, 32, d, d8, scale_round_mode=lof.RoundingMode.RoundUp))
+        back = _np(lof.mx_decode(sc, el, n, 32, d, d8))
+        assert np.array_equal(back, fake), name            # a scale rounded UP never lets x / scale overflow -> always representable
+                                                           # (value compare: the P3109-style element formats have no -0, the fake-quant op keeps it)
+    # C3 shape: 16384 x 16384, MXFP8 and MXFP4
+    g = torch.Generator(device=cuda_dev).manual_seed(7)
+    big = torch.randn(16384, 16384, device=cuda_dev, generator=g) * torch.exp2(torch.randint(-8, 9, (16384, 1), device=cuda_dev, generator=g).float())
+    for name in ("mxfp8_e4m3", "mxfp4_e2m1"):
+        cf, d, ff = elem[name]
+        sc, el = lof.mx_encode(big, 32, d, d8, scale_round_mode=lof.RoundingMode.RoundUp)
+        assert sc.numel() == big.numel() // 32 and el.numel() == lof.packed_size(d.total_bits, big.numel())
+        back = lof.mx_decode(sc, el, big.numel(), 32, d, d8).view_as(big)
+        assert torch.equal(back, lof.virtual_mx_round(big, 32, d, d8, scale_round_mode=lof.RoundingMode.RoundUp)), name
+        rows = slice(5000, 5002)
+        wsc, wel = L.o_mx_encode(_np(big[rows]).ravel(), 32, e8, cf, scale_mode=L.RU)
+        lo = 5000 * 16384
+        assert np.array_equal(_np(sc[lo // 32:(lo + 2 * 16384) // 32]), wsc), name
+    with pytest.raises(lof.LoFloatError):
+        lof.mx_encode(xt[:100], 32, elem["mxfp8_e4m3"][1], d8)                            # n % block_size != 0
