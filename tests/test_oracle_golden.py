@@ -402,3 +402,35 @@ def test_pack_roundtrip_properties():
         keep = ~np.isnan(vals)
         again = L.o_float_to_rep(vals[keep], f)
         assert np.array_equal(again, reps[keep]), name
+
+
+def test_mx_storage_oracle_consistent_with_virtual_mx_round():
+    """The MX storage oracle (scale bytes + packed elements) is a composition of two pinned pieces; tie it to them:
+    decode(encode(x)) equals the (reference-pinned) virtual_mx_round oracle wherever the fake-quant value is
+    representable -- always when the scale is rounded UP -- the scale byte of an E8M0 scale is its biased exponent, and
+    the element codes are the codec's codes of the unscaled quantised values."""
+    rng = np.random.default_rng(8)
+    n = 64 * 400
+    x = (rng.standard_normal(n) * np.exp2(rng.integers(-15, 16, n))).astype(np.float32)
+    x[:64] = 0
+    e8c, e8f = L.codec_e8m0(), L.fmt(8, 0, 127, L.SATURATING, L.UNSIGNED)
+    for cf, ff in ((L.codec_p3109(8, 4, bias=7), L.FORMATS["e4m3_b7"]), (L.codec_p3109(6, 3, bias=3), L.FORMATS["e3m2"]),
+                   (L.codec_p3109(4, 2, bias=1), L.FORMATS["e2m1"])):
+        for bs in (16, 32, 64):
+            sc, el = L.o_mx_encode(x, bs, e8c, cf, scale_mode=L.RU)
+            back = L.o_mx_decode(sc, el, n, bs, e8c, cf)
+            fake = L.o_mx_round(x, bs, e8f, ff, scale_mode=L.RU)
+            assert np.array_equal(back, fake), (cf.fmt.bitwidth, bs)                 # value compare: these formats have no -0
+            scale = np.abs(x).reshape(-1, bs).max(axis=1) / L.oracle().lofo_mx_priv_max_normal(C_byref(ff))
+            live = scale > 0
+            want_exp = np.ceil(np.log2(scale[live])).astype(np.int64) + 127              # RoundUp to a power of two
+            assert np.array_equal(sc[live].astype(np.int64), want_exp), (cf.fmt.bitwidth, bs)
+            assert not sc[~live].any()
+            reps = L.o_unpack_reps(el, n, cf.fmt.bitwidth)
+            q = (x.reshape(-1, bs) / np.exp2(sc.astype(np.float64) - 127)[:, None].astype(np.float32)).astype(np.float32)
+            assert np.array_equal(reps.reshape(-1, bs)[live], L.o_float_to_rep(q[live].ravel(), cf).reshape(-1, bs))
+
+
+def C_byref(obj):
+    import ctypes
+    return ctypes.byref(obj)
