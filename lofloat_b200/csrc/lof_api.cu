@@ -777,6 +777,7 @@ int lof_mx_encode_f32(const float* in, int64_t n, int block_size, const lof_code
     if (sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
     const RngArgs re = make_rng(rng, kStreamElem, ps_elem->rounding_mode, ps_elem->stoch_length), rs = make_rng(rng, kStreamScale);
     cudaError_t e = launch_mx_encode(ps_elem->rounding_mode, in, n, a, cs, ce, re, rs, first_index, scales, elems, sms, fast,
+                                     make_magic_plan(a.scale, ps_scale->rounding_mode), make_fast_plan(a.scale, ps_scale->rounding_mode),
                                      static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "lof_mx_encode launch");
     g_launches.fetch_add(1);

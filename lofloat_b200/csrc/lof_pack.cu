@@ -113,7 +113,12 @@ struct FastConsts {
     __device__ __forceinline__ explicit FastConsts(const CodecPlan& p)
         : cadd(p.f_cadd), cfloor(p.f_cfloor), big(p.f_big), max_finite(p.max_finite_rep), ovf(p.ovf_rep), inf_in(p.inf_in_rep),
           qnan(p.qnan), signmask(p.signmask), neg_unsigned(p.neg_unsigned_rep), ds(p.digit_drop), sign_shift(32 - p.n),
-          to_signed(p.to_signed != 0), sign_is_nan(p.sign_is_nan != 0) {}
+          to_signed(p.to_signed != 0), sign_is_nan(p.sign_is_nan != 0)
+    {
+        // keep the per-element constants in registers: ptxas otherwise re-loads them from the parameter bank for every element
+        // (7 LDC / LDCU per conversion in the first build, ncu r01i)
+        asm volatile("" : "+r"(cadd), "+r"(cfloor), "+r"(big), "+r"(max_finite), "+r"(ovf), "+r"(signmask), "+r"(ds), "+r"(sign_shift));
+    }
 };
 
 // ~15 instructions per element: the stream has to stay under ~20 to be HBM- rather than ALU-bound (ncu r01g).
@@ -444,64 +449,138 @@ round_strict_kernel(const float* __restrict__ src, float* __restrict__ dst, int6
 // A lane owns 4 consecutive elements (one 128-bit load), a block is BS / 4 lanes of one warp (amax by shfl.xor).
 // 4 B read + (n/8 + 1/BS) B written per element.
 // ------------------------------------------------------------------------------------------------
+// virtual_round(amax / pmn, scale format) on the branch-free routines of lof_fast_f32.cuh where they apply (the same
+// selection lof_mx_fast.cu makes; every one of them is proven equal to the exact routine by the exhaustive sweeps),
+// the generic 15-mode routine otherwise
+struct MxScaleQuick {
+    MagicPlan magic;
+    FastPlan fast;
+    int32_t quick_mode_ok;          // scale mode in {RNE, RTZ, RAZ, RU, RD, RoundToOdd}
+};
+
+__device__ __forceinline__ float mx_scale_quick(float amax, const MxArgs& a, const MxScaleQuick& q, const RngArgs& rng_scale, uint64_t gblock)
+{
+    if (q.quick_mode_ok) {
+        const uint32_t x = __float_as_uint(__fdiv_rn(amax, a.pmn));          // >= 0, never NaN (fmaxf drops NaNs)
+        const MagicPlan& p = q.magic;
+        if (p.valid && !(x >= p.limit) && !((x - 1u) < p.lo_rare)) {
+            uint32_t mag, rs;
+            switch (a.scale_mode) {
+            case LOF_RoundToNearestEven: rs = magic_round_core<LOF_RoundToNearestEven>(x, p.c_add, p.c_floor, mag); break;
+            case LOF_RoundTowardsZero:   rs = magic_round_core<LOF_RoundTowardsZero>(x, p.c_add, p.c_floor, mag); break;
+            case LOF_RoundAwayFromZero:  rs = magic_round_core<LOF_RoundAwayFromZero>(x, p.c_add, p.c_floor, mag); break;
+            case LOF_RoundUp:            rs = magic_round_core<LOF_RoundUp>(x, p.c_add, p.c_floor, mag); break;
+            case LOF_RoundDown:          rs = magic_round_core<LOF_RoundDown>(x, p.c_add, p.c_floor, mag); break;
+            default:                     rs = magic_round_core<LOF_RoundToOdd>(x, p.c_add, p.c_floor, mag); break;
+            }
+            return __uint_as_float((mag >= p.ovf_thresh) ? (a.scale.saturating ? x : 0x7F800000u) : rs);
+        }
+        if (q.fast.valid) {
+            bool rare = false;
+            uint32_t rb;
+            const bool sat = a.scale.saturating != 0;
+            switch (a.scale_mode) {
+            case LOF_RoundToNearestEven: rb = round_fast_f32_rt<LOF_RoundToNearestEven>(x, q.fast, sat, 0u, rare); break;
+            case LOF_RoundTowardsZero:   rb = round_fast_f32_rt<LOF_RoundTowardsZero>(x, q.fast, sat, 0u, rare); break;
+            case LOF_RoundAwayFromZero:  rb = round_fast_f32_rt<LOF_RoundAwayFromZero>(x, q.fast, sat, 0u, rare); break;
+            case LOF_RoundUp:            rb = round_fast_f32_rt<LOF_RoundUp>(x, q.fast, sat, 0u, rare); break;
+            case LOF_RoundDown:          rb = round_fast_f32_rt<LOF_RoundDown>(x, q.fast, sat, 0u, rare); break;
+            default:                     rb = round_fast_f32_rt<LOF_RoundToOdd>(x, q.fast, sat, 0u, rare); break;
+            }
+            if (!rare) return __uint_as_float(rb);
+        }
+    }
+    return mx_block_scale(amax, a, rng_scale, gblock);
+}
+
 template <int MODE, bool FAST>
 __global__ void __launch_bounds__(kPackThreads)
-mx_encode_kernel(const float4* __restrict__ in, int64_t nvec, MxArgs a, CodecPlan scale_codec, CodecPlan elem_codec, RngArgs rng,
-                 RngArgs rng_scale, uint64_t first_index, uint8_t* __restrict__ scales, uint8_t* __restrict__ elems)
+mx_encode_kernel(const float4* __restrict__ in, int64_t nvec, MxArgs a, MxScaleQuick sq, CodecPlan scale_codec, CodecPlan elem_codec,
+                 RngArgs rng, RngArgs rng_scale, uint64_t first_index, uint8_t* __restrict__ scales, uint8_t* __restrict__ elems)
 {
+    constexpr int U = 2;                                         // vectors in flight per thread
     const int lanes = a.block_size >> 2;                         // lanes per block: 4 .. 32
+    const int log2_bs = 31 - __clz(a.block_size);                // block sizes are powers of two: no 64-bit divisions in the loop
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * kPackThreads;
     const int64_t nvec_pad = (nvec + 31) & ~(int64_t)31;         // whole warps stay converged for the shuffles
     const FastConsts fk(elem_codec);
-    for (int64_t v = (int64_t)blockIdx.x * kPackThreads + threadIdx.x; v < nvec_pad; v += stride) {
-        const bool live_lane = v < nvec;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live_lane) x = __ldcs(in + v);
-        float amax = fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w)));       // NaN-dropping like std::max(amax, |x|)
-        for (int o = lanes >> 1; o >= 1; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, o));
-        const uint64_t g0 = first_index + (uint64_t)v * 4u;
-        // the block's scale and its stored byte: computed by the block's first lane only, then broadcast
-        const bool head = (lane & (lanes - 1)) == 0;
-        float scale = 0.0f;
-        if (head && live_lane) {
-            scale = mx_block_scale(amax, a, rng_scale, g0 / (uint64_t)a.block_size);
-            scales[(v * 4) / a.block_size] = (uint8_t)float_to_rep<LOF_RoundTowardsZero>(__float_as_uint(scale), scale_codec, 0u);
-        }
-        scale = __shfl_sync(0xFFFFFFFFu, scale, lane & ~(lanes - 1));
-        if (!live_lane) continue;
-        const MxBlockCtx ctx = mx_make_ctx(scale);
-        uint32_t r[4] = {0u, 0u, 0u, 0u};
-        if (ctx.live) {
-            const float xs[4] = {x.x, x.y, x.z, x.w};
-            uint4 w4 = make_uint4(0u, 0u, 0u, 0u);
-            if constexpr (ModeTraits<MODE>::kUsesRng) w4 = philox_group4(rng, g0 >> 2);         // g0 % 4 == 0 (host-checked)
-            const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+    for (int64_t v0 = (int64_t)blockIdx.x * kPackThreads + threadIdx.x; v0 < nvec_pad; v0 += U * stride) {
+        float4 xv[U];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float y = ctx.pow2 ? __fmul_rn(xs[e], ctx.recip) : __fdiv_rn(xs[e], ctx.scale);   // == x / scale bit for bit
-                if constexpr (FAST) {
-                    // rep(virtual_round(y)) == the codec's own rounding of y for the IEEE-like modes on eligible formats
-                    // (both are the correctly rounded grid value; overflow clamps to the same code): one magic add
-                    r[e] = float_to_rep_fast<MODE>(__float_as_uint(y), fk) & elem_codec.rep_mask;
+        for (int u = 0; u < U; ++u) {
+            const int64_t v = v0 + u * stride;
+            xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (v < nvec) xv[u] = __ldcs(in + v);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t v = v0 + u * stride;
+            if (v >= nvec_pad) break;                            // warp-uniform
+            const bool live_lane = v < nvec;
+            const float4 x = xv[u];
+            float amax = fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w)));       // NaN-dropping like std::max(amax, |x|)
+            for (int o = lanes >> 1; o >= 1; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, o));
+            const uint64_t g0 = first_index + (uint64_t)v * 4u;
+            // the block's scale and its stored byte: computed by the block's first lane only, then broadcast
+            const bool head = (lane & (lanes - 1)) == 0;
+            float scale = 0.0f;
+            if (head && live_lane) {
+                scale = mx_scale_quick(amax, a, sq, rng_scale, g0 >> log2_bs);
+                // stored scale byte: for exponent-only unsigned formats (E8M0) a normal power-of-two scale encodes as its
+                // re-biased exponent field (lo_pack.hpp's normal path with nothing to round); anything else: exact routine
+                const uint32_t sb = __float_as_uint(scale);
+                const int code = (int)(sb >> 23) + scale_codec.exp_offset;
+                uint32_t byte;
+                if (scale_codec.mant == 0 && !scale_codec.to_signed && (sb & 0x807FFFFFu) == 0u && (sb >> 23) >= 1u && (sb >> 23) <= 254u &&
+                    code >= 1 && code <= (int)scale_codec.max_finite_rep)
+                    byte = (uint32_t)code;
+                else
+                    byte = float_to_rep<LOF_RoundTowardsZero>(sb, scale_codec, 0u);
+                scales[(v * 4) >> log2_bs] = (uint8_t)byte;
+            }
+            scale = __shfl_sync(0xFFFFFFFFu, scale, lane & ~(lanes - 1));
+            if (!live_lane) continue;
+            const MxBlockCtx ctx = mx_make_ctx(scale);
+            uint32_t r[4] = {0u, 0u, 0u, 0u};
+            if (ctx.live) {
+                const float xs[4] = {x.x, x.y, x.z, x.w};
+                uint4 w4 = make_uint4(0u, 0u, 0u, 0u);
+                if constexpr (ModeTraits<MODE>::kUsesRng) w4 = philox_group4(rng, g0 >> 2);         // g0 % 4 == 0 (host-checked)
+                const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+                float y[4];
+                if (ctx.pow2) {                                  // E8M0-like scale: x / scale == x * 2^-k exactly
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) y[e] = __fmul_rn(xs[e], ctx.recip);
                 } else {
-                    const uint32_t q = round_params_elem<LOF_F32, MODE>(__float_as_uint(y), a.elem, w[e]);
-                    r[e] = float_to_rep<LOF_RoundTowardsZero>(q, elem_codec, 0u) & elem_codec.rep_mask;   // q is on the grid: exact
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) y[e] = __fdiv_rn(xs[e], ctx.scale);
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if constexpr (FAST) {
+                        // rep(virtual_round(y)) == the codec's own rounding of y for the IEEE-like modes on eligible formats
+                        // (both are the correctly rounded grid value; overflow clamps to the same code): one magic add
+                        r[e] = float_to_rep_fast<MODE>(__float_as_uint(y[e]), fk) & elem_codec.rep_mask;
+                    } else {
+                        const uint32_t q = round_params_elem<LOF_F32, MODE>(__float_as_uint(y[e]), a.elem, w[e]);
+                        r[e] = float_to_rep<LOF_RoundTowardsZero>(q, elem_codec, 0u) & elem_codec.rep_mask;   // q is on the grid: exact
+                    }
                 }
             }
-        }
-        if (elem_codec.reverse && elem_codec.gc > 1) {           // slot order inside a group (gc = 2 for 4-bit, 4 for 6-bit)
-            if (elem_codec.gc == 2) { uint32_t t = r[0]; r[0] = r[1]; r[1] = t; t = r[2]; r[2] = r[3]; r[3] = t; }
-            else { uint32_t t = r[0]; r[0] = r[3]; r[3] = t; t = r[1]; r[1] = r[2]; r[2] = t; }
-        }
-        if (elem_codec.n == 8) {
-            __stcs(reinterpret_cast<uint32_t*>(elems) + v, r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24));
-        } else if (elem_codec.n == 4) {
-            __stcs(reinterpret_cast<uint16_t*>(elems) + v, (uint16_t)(r[0] | (r[1] << 4) | (r[2] << 8) | (r[3] << 12)));
-        } else {                                                 // 6-bit: four elements = one 3-byte group
-            const uint32_t g = r[0] | (r[1] << 6) | (r[2] << 12) | (r[3] << 18);
-            uint8_t* d = elems + v * 3;
-            d[0] = (uint8_t)g; d[1] = (uint8_t)(g >> 8); d[2] = (uint8_t)(g >> 16);
+            if (elem_codec.reverse && elem_codec.gc > 1) {           // slot order inside a group (gc = 2 for 4-bit, 4 for 6-bit)
+                if (elem_codec.gc == 2) { uint32_t t = r[0]; r[0] = r[1]; r[1] = t; t = r[2]; r[2] = r[3]; r[3] = t; }
+                else { uint32_t t = r[0]; r[0] = r[3]; r[3] = t; t = r[1]; r[1] = r[2]; r[2] = t; }
+            }
+            if (elem_codec.n == 8) {
+                __stcs(reinterpret_cast<uint32_t*>(elems) + v, r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24));
+            } else if (elem_codec.n == 4) {
+                __stcs(reinterpret_cast<uint16_t*>(elems) + v, (uint16_t)(r[0] | (r[1] << 4) | (r[2] << 8) | (r[3] << 12)));
+            } else {                                                 // 6-bit: four elements = one 3-byte group
+                const uint32_t g = r[0] | (r[1] << 6) | (r[2] << 12) | (r[3] << 18);
+                uint8_t* d = elems + v * 3;
+                d[0] = (uint8_t)g; d[1] = (uint8_t)(g >> 8); d[2] = (uint8_t)(g >> 16);
+            }
         }
     }
 }
@@ -605,22 +684,27 @@ cudaError_t launch_round_strict(int mode, const float* src, float* dst, int64_t 
 
 cudaError_t launch_mx_encode(int mode, const float* in, int64_t n, const MxArgs& a, const CodecPlan& scale_codec, const CodecPlan& elem_codec,
                              const RngArgs& rng, const RngArgs& rng_scale, uint64_t first_index, uint8_t* scales, uint8_t* elems, int num_sms,
-                             bool fast, cudaStream_t stream)
+                             bool fast, const MagicPlan& scale_magic, const FastPlan& scale_fast, cudaStream_t stream)
 {
+    MxScaleQuick sq;
+    sq.magic = scale_magic;
+    sq.fast = scale_fast;
+    sq.quick_mode_ok = a.scale_mode == LOF_RoundToNearestEven || a.scale_mode == LOF_RoundTowardsZero || a.scale_mode == LOF_RoundAwayFromZero ||
+                       a.scale_mode == LOF_RoundUp || a.scale_mode == LOF_RoundDown || a.scale_mode == LOF_RoundToOdd;
     const int64_t nvec = n / 4;
     const int64_t want = (nvec + kPackThreads - 1) / kPackThreads, cap = (int64_t)num_sms * 8;
     const unsigned grid = (unsigned)(want < 1 ? 1 : want < cap ? want : cap);
     const float4* vin = reinterpret_cast<const float4*>(in);
     if (fast) {
         switch (mode) {
-#define LOF_CASE(M) case M: mx_encode_kernel<M, true><<<grid, kPackThreads, 0, stream>>>(vin, nvec, a, scale_codec, elem_codec, rng, rng_scale, first_index, scales, elems); return cudaGetLastError();
+#define LOF_CASE(M) case M: mx_encode_kernel<M, true><<<grid, kPackThreads, 0, stream>>>(vin, nvec, a, sq, scale_codec, elem_codec, rng, rng_scale, first_index, scales, elems); return cudaGetLastError();
             LOF_CASE(LOF_RoundToNearestEven) LOF_CASE(LOF_RoundTowardsZero) LOF_CASE(LOF_RoundAwayFromZero) LOF_CASE(LOF_RoundToOdd)
 #undef LOF_CASE
         default: break;
         }
     }
     switch (mode) {
-#define LOF_CASE(M) case M: mx_encode_kernel<M, false><<<grid, kPackThreads, 0, stream>>>(vin, nvec, a, scale_codec, elem_codec, rng, rng_scale, first_index, scales, elems); break;
+#define LOF_CASE(M) case M: mx_encode_kernel<M, false><<<grid, kPackThreads, 0, stream>>>(vin, nvec, a, sq, scale_codec, elem_codec, rng, rng_scale, first_index, scales, elems); break;
         LOF_CASE(LOF_RoundToNearestEven) LOF_CASE(LOF_RoundTowardsZero) LOF_CASE(LOF_RoundAwayFromZero)
         LOF_CASE(LOF_StochasticRoundingA) LOF_CASE(LOF_RoundToNearestOdd) LOF_CASE(LOF_RoundDown)
         LOF_CASE(LOF_RoundUp) LOF_CASE(LOF_RoundTiesToAway) LOF_CASE(LOF_StochasticRoundingB)

@@ -46,7 +46,7 @@ cudaError_t launch_decode(const uint8_t* src, float* dst, int64_t count, uint64_
 
 cudaError_t launch_mx_encode(int mode, const float* in, int64_t n, const MxArgs& a, const CodecPlan& scale_codec, const CodecPlan& elem_codec,
                              const RngArgs& rng, const RngArgs& rng_scale, uint64_t first_index, uint8_t* scales, uint8_t* elems, int num_sms,
-                             bool fast, cudaStream_t stream);
+                             bool fast, const MagicPlan& scale_magic, const FastPlan& scale_fast, cudaStream_t stream);
 cudaError_t launch_mx_decode(const uint8_t* scales, const uint8_t* elems, float* out, int64_t n, int block_size, const CodecPlan& scale_codec,
                              const CodecPlan& elem_codec, int num_sms, cudaStream_t stream);
 

@@ -43,6 +43,15 @@ def main():
         x *= torch.exp2(torch.randint(-8, 9, (16384, 1), device=dev, generator=g).float())
         for _ in range(4):
             y = lof.virtual_mx_round(x, 32, f, lof.create_e8m0_params())
+    elif what == "mxenc":
+        from lofloat_b200 import formats
+        d8 = lof.FloatFormatDescriptor(8, 0, 127, lof.InfBehavior.Saturating, lof.NaNBehavior._3109, lof.Signedness.Unsigned,
+                                       formats._P3109Inf(8, False, True), formats._BitPatternNaN(0xFF))
+        x = torch.randn(16384, 16384, device=dev, generator=g)
+        x *= torch.exp2(torch.randint(-8, 9, (16384, 1), device=dev, generator=g).float())
+        for _ in range(3):
+            sc, el = lof.mx_encode(x, 32, fmt("e4m3"), d8)
+            y = lof.mx_decode(sc, el, x.numel(), 32, fmt("e4m3"), d8)
     elif what == "pack":
         f = fmt(sys.argv[2] if len(sys.argv) > 2 else "e4m3")
         n = 1 << 28
