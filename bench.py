@@ -301,6 +301,25 @@ def side_measurements(torch, lib, _lib, dev, x, y, stream):
     except Exception as exc:
         out["mx_round_error"] = str(exc)
     try:
+        # C2's bf16-in / bf16-out variant: 2^29 bf16 containers (1 GiB), 4 B / element of algorithmic traffic
+        import lofloat_b200 as lof
+        nb = 1 << 29
+        xb = x.to(torch.bfloat16).repeat(2)[:nb].contiguous()
+        for label, d, mode, sl in (("e4m3_RNE", lof.create_p3109_params(8, 4, bias=7), 0, 0), ("e2m1_RNE", lof.create_p3109_params(4, 2, bias=1), 0, 0),
+                                   ("e4m3_SR_A4", lof.create_p3109_params(8, 4, bias=7), 3, 4)):
+            lof.virtual_round(xb, d, mode, sl)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                lof.virtual_round(xb, d, mode, sl)
+            b.record()
+            torch.cuda.synchronize()
+            gbps = 4.0 * nb * 5 / (a.elapsed_time(b) * 1e-3) / 1e9
+            out[f"C2_virtual_round_bf16_container_{label}_2^29"] = {"GBps": gbps, "frac_of_hbm_peak": gbps / peak}
+        del xb
+    except Exception as exc:
+        out["bf16_container_error"] = str(exc)
+    try:
         M = N = K = 2048
         A = torch.rand(M, K, device=dev) * 2 - 1
         B = torch.rand(K, N, device=dev) * 2 - 1

@@ -7,6 +7,14 @@ cudaError_t launch_round_bf16(int kind, int mode, const void* in, void* out, int
                             const FastPlan& fast, const MagicPlan& magic, int r, int len, double scale, const RngArgs& rng, uint64_t first_index,
                             const RoundLaunchCfg& cfg, cudaStream_t stream)
 {
+    // fp32 branch-free routines on (bits << 16): deterministic modes, no fused scale (lof_api.cu decides)
+    switch (kind) {
+    case kKindFastSatChk:  return launch_round<LOF_BF16, kKindFastSatChk>(mode, in, out, n, plan, fast, magic, r, len, scale, rng, first_index, cfg, stream);
+    case kKindFastExtChk:  return launch_round<LOF_BF16, kKindFastExtChk>(mode, in, out, n, plan, fast, magic, r, len, scale, rng, first_index, cfg, stream);
+    case kKindMagicSatChk: return launch_round<LOF_BF16, kKindMagicSatChk>(mode, in, out, n, plan, fast, magic, r, len, scale, rng, first_index, cfg, stream);
+    case kKindMagicExtChk: return launch_round<LOF_BF16, kKindMagicExtChk>(mode, in, out, n, plan, fast, magic, r, len, scale, rng, first_index, cfg, stream);
+    default: break;
+    }
     if (kind != kKindMantissa)
         return launch_round<LOF_BF16, kKindParams>(mode, in, out, n, plan, fast, magic, r, len, scale, rng, first_index, cfg, stream);
     return launch_round<LOF_BF16, kKindMantissa>(mode, in, out, n, plan, fast, magic, r, len, scale, rng, first_index, cfg, stream);

@@ -997,3 +997,24 @@ def test_mx_storage_encode_decode(lof, cuda_dev):
         assert np.array_equal(_np(sc[lo // 32:(lo + 2 * 16384) // 32]), wsc), name
     with pytest.raises(lof.LoFloatError):
         lof.mx_encode(xt[:100], 32, elem["mxfp8_e4m3"][1], d8)                            # n % block_size != 0
+
+
+def test_bf16_container_fast_path_equals_exact_all_patterns(lof, cuda_dev):
+    """bf16 containers run on the fp32 branch-free routines applied to (bits << 16) (round.fast = 1 / 2); they must equal
+    the exact bf16-container routine (round.fast = 0, pinned to the oracle by test_round_other_containers) on ALL 65536
+    bf16 bit patterns for every named format and deterministic mode, at every vector alignment."""
+    from lofloat_b200 import _lib
+    allbits = torch.arange(0, 65536, device=cuda_dev, dtype=torch.int32).to(torch.int16).view(torch.bfloat16).repeat(9)[3:]
+    try:
+        for name, f in L.FORMATS.items():
+            if f.bitwidth > 16:
+                continue
+            d = _desc(lof, f)
+            for mode in L.DETERMINISTIC_MODES:
+                _lib.set_option("round.fast", 0)
+                want = lof.virtual_round(allbits, d, mode).view(torch.int16)
+                for fast in (1, 2):
+                    _lib.set_option("round.fast", fast)
+                    assert torch.equal(lof.virtual_round(allbits, d, mode).view(torch.int16), want), (name, L.MODE_NAMES[mode], fast)
+    finally:
+        _lib.set_option("round.fast", 2)
