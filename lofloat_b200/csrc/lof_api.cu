@@ -247,7 +247,8 @@ int round_common(bool params, const void* in, void* out, int64_t n, int dtype, c
         const int st = make_plan(fmt, dtype, mode, ps->stoch_length, &plan);
         if (st != LOF_OK) return st;
         const int64_t fast_opt = g_opt.round_fast.load();        // 0: exact kernel, 1: first-generation fast path, 2: + magic add
-        if (dtype == LOF_BF16 && fast_opt && !mode_uses_rng(mode) && scale == 1.0 && fmt->mantissa_bits <= 7) {
+        const bool bf16_sr = (mode == LOF_StochasticRoundingA || mode == LOF_StochasticRoundingD) && fast_opt >= 2;
+        if (dtype == LOF_BF16 && fast_opt && (!mode_uses_rng(mode) || bf16_sr) && scale == 1.0 && fmt->mantissa_bits <= 7) {
             // bf16 container: the fp32 branch-free routines applied to (bits << 16) (lof_round_kernels.cuh); always the checked
             // variants.  `plan` stays the exact bf16-container plan for the rare lanes and the scalar tail.
             RoundPlan p32;
@@ -255,6 +256,7 @@ int round_common(bool params, const void* in, void* out, int64_t n, int dtype, c
             if (make_plan(fmt, LOF_F32, mode, ps->stoch_length, &p32) == LOF_OK) {
                 fast = make_fast_plan(p32, mode);
                 if (fast.valid) kind = p32.saturating ? kKindFastSatChk : kKindFastExtChk;
+                if (mode_uses_rng(mode)) { kind = kKindParams; std::memset(&fast, 0, sizeof fast); }     // stochastic: magic path or nothing
                 if (fast_opt >= 2) {
                     magic = make_magic_plan(p32, mode);
                     if (magic.valid) kind = p32.saturating ? kKindMagicSatChk : kKindMagicExtChk;

@@ -1016,5 +1016,15 @@ def test_bf16_container_fast_path_equals_exact_all_patterns(lof, cuda_dev):
                 for fast in (1, 2):
                     _lib.set_option("round.fast", fast)
                     assert torch.equal(lof.virtual_round(allbits, d, mode).view(torch.int16), want), (name, L.MODE_NAMES[mode], fast)
+            r16 = 7 - f.mantissa_bits
+            for mode in (L.SR_A, L.SR_D):                      # stochastic: same Philox events, same offsets in both containers
+                for sl in {1, max(1, min(r16, 4)), max(1, r16 - (1 if mode == L.SR_D else 0))}:
+                    if r16 < 1 or sl > r16:
+                        continue
+                    _lib.set_option("round.fast", 0)
+                    want = lof.virtual_round(allbits, d, mode, sl, rng=(77, 5), first_index=8).view(torch.int16)
+                    _lib.set_option("round.fast", 2)
+                    got = lof.virtual_round(allbits, d, mode, sl, rng=(77, 5), first_index=8).view(torch.int16)
+                    assert torch.equal(got, want), (name, L.MODE_NAMES[mode], sl)
     finally:
         _lib.set_option("round.fast", 2)
