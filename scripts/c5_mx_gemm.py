@@ -45,7 +45,9 @@ def main():
         return float(t.item())
 
     def timed(fn, reps):
-        fn()
+        for _ in range(3):                      # warm-up: kernels, and the caching allocator's blocks for the outputs
+            keep = fn()
+        del keep
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
