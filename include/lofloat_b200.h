@@ -188,6 +188,20 @@ LOF_API int lof_gemm_chunked_f32(const float* A, const float* B, float* C, int64
                          void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Callers fused around the path: the orthonormal block-diagonal Walsh-Hadamard rotation
+ * LoF_Linear applies to its activations (LoFloat/layers.py:182-216 `_fwht`, used at :363-365) fused with the rounding
+ * that follows it -- STERound (:378, with its fused pre-scale) or STEMXRound (:366-369).  One pass over HBM; bit-identical
+ * to `_fwht` followed by the separate op (same butterflies in the same stage order, then * fl32(1 / sqrt(block_size))).
+ * block_size: a power of two up to 1024 that divides the last dimension; n % 128 == 0; 16-byte aligned; out may alias in.
+ * ------------------------------------------------------------------------------------- */
+LOF_API int lof_fwht_f32(const float* in, float* out, int64_t n, int block_size, void* stream);
+LOF_API int lof_fwht_round_f32(const float* in, float* out, int64_t n, int block_size, const lof_format_t* fmt,
+                               const lof_projspec_t* ps, double scale, const lof_rng_t* rng, uint64_t first_index, void* stream);
+LOF_API int lof_fwht_mx_round_f32(const float* in, float* out, int64_t n, int block_size, int mx_block_size,
+                                  const lof_format_t* scale_fmt, const lof_format_t* elem_fmt, const lof_projspec_t* ps_scale,
+                                  const lof_projspec_t* ps_elem, const lof_rng_t* rng, uint64_t first_index, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Low-bit storage codec: fp32 -> packed n-bit representations and back.
  * Replaces LoF_encode_cuda / LoF_decode_cuda (src/lo_pack.hpp:499-529; CPU twins LoF_encode / LoF_decode
  * :419-465) with the conversion semantics of convert_float_to_rep / convert_rep_to_float (:109-319): the strict

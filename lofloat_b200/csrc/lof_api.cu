@@ -28,6 +28,9 @@ cudaError_t launch_mx_tma(int mode, const float* in, float* out, int64_t n, cons
 cudaError_t launch_mx_fast(int mode, int scale_mode, const float* in, float* out, int64_t n, const MxArgs& g,
                            const MagicPlan& elem_magic, const MagicPlan& scale_magic, const FastPlan& scale_fast, int scale_mantissa_bits,
                            const MxLaunchCfg& cfg, cudaStream_t stream, int64_t* main_elems, int* launches);
+cudaError_t launch_fwht(int op, int mode, const float* in, float* out, int64_t n, int hadamard_block, const RoundPlan* plan,
+                        float pre_scale, const MxArgs* mx, const MagicPlan* scale_magic, const FastPlan* scale_fast, const RngArgs& rng,
+                        const RngArgs& rng_scale, uint64_t first_index, int num_sms, cudaStream_t stream);
 cudaError_t run_mx_div_selftest(float pmn, unsigned long long* host_mismatches, cudaStream_t stream);
 cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int mode,
                            int accum_mant_bits, const lof_format_t* acc_fmt, const RoundPlan* acc_plan, const FastPlan* acc_fast,
@@ -616,6 +619,95 @@ int lof_gemm_chunked_packed(const uint8_t* A, const uint8_t* Bt, float* C, int64
     if (flags & LOF_GEMM_INTERNAL_PACKED_OPERANDS) return fail(LOF_ERR_INVALID_ARG, "unknown flag");
     return lof_gemm_chunked_f32(reinterpret_cast<const float*>(A), reinterpret_cast<const float*>(Bt), C, M, N, K, accum_mant_bits,
                                 acc_fmt, ps, k_chunk, alpha, operand_dtype, flags | LOF_GEMM_INTERNAL_PACKED_OPERANDS, dev_status, stream);
+}
+
+// ---------------------------------------------------------------------------------------
+// fused callers: Hadamard rotation + rounding (LoFloat/layers.py:182-216, 363-378)
+// ---------------------------------------------------------------------------------------
+namespace {
+int fwht_check(const float* in, float* out, int64_t n, int block)
+{
+    if (n < 0) return fail(LOF_ERR_INVALID_ARG, "n < 0");
+    if (block <= 0 || (block & (block - 1)) != 0) return fail(LOF_ERR_INVALID_ARG, "fwht: block_size must be a power of 2");   // layers.py:196-197
+    if (block > 1024) return fail(LOF_ERR_UNSUPPORTED, "fwht: fused kernel handles block sizes up to 1024");
+    if (n % block != 0) return fail(LOF_ERR_INVALID_ARG, "fwht: block_size must divide the tensor's last dimension");          // layers.py:198-199
+    if (n % 128 != 0) return fail(LOF_ERR_UNSUPPORTED, "fwht: fused kernel needs the element count to be a multiple of 128");
+    if (n > 0 && (!in || !out)) return fail(LOF_ERR_INVALID_ARG, "null tensor pointer");
+    if (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) != 0)
+        return fail(LOF_ERR_INVALID_ARG, "fwht: pointers must be 16-byte aligned");
+    return LOF_OK;
+}
+}  // namespace
+
+int lof_fwht_f32(const float* in, float* out, int64_t n, int block_size, void* stream)
+{
+    const int st = fwht_check(in, out, n, block_size);
+    if (st != LOF_OK) return st;
+    if (n == 0) return LOF_OK;
+    const int sms = num_sms();
+    if (sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    const RngArgs none = make_rng(nullptr, kStreamElem);
+    cudaError_t e = launch_fwht(0, 0, in, out, n, block_size, nullptr, 1.0f, nullptr, nullptr, nullptr, none, none, 0, sms, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "lof_fwht launch");
+    g_launches.fetch_add(1);
+    return LOF_OK;
+}
+
+int lof_fwht_round_f32(const float* in, float* out, int64_t n, int block_size, const lof_format_t* fmt, const lof_projspec_t* ps,
+                       double scale, const lof_rng_t* rng, uint64_t first_index, void* stream)
+{
+    int st = fwht_check(in, out, n, block_size);
+    if (st != LOF_OK) return st;
+    if (!ps) return fail(LOF_ERR_INVALID_ARG, "projspec is NULL");
+    const int mode = ps->rounding_mode;
+    if (mode < 0 || mode >= LOF_NUM_ROUNDING_MODES) return fail(LOF_ERR_INVALID_ARG, "unknown rounding mode");
+    if (first_index % 4 != 0) return fail(LOF_ERR_INVALID_ARG, "first_index must be a multiple of 4");
+    RoundPlan plan;
+    std::memset(&plan, 0, sizeof plan);
+    st = make_plan(fmt, LOF_F32, mode, ps->stoch_length, &plan);
+    if (st != LOF_OK) return st;
+    if (n == 0) return LOF_OK;
+    const int sms = num_sms();
+    if (sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    const RngArgs ra = make_rng(rng, kStreamElem, mode, ps->stoch_length);
+    cudaError_t e = launch_fwht(1, mode, in, out, n, block_size, &plan, (float)scale, nullptr, nullptr, nullptr, ra, ra, first_index, sms,
+                                static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "lof_fwht_round launch");
+    g_launches.fetch_add(1);
+    return LOF_OK;
+}
+
+int lof_fwht_mx_round_f32(const float* in, float* out, int64_t n, int block_size, int mx_block_size, const lof_format_t* scale_fmt,
+                          const lof_format_t* elem_fmt, const lof_projspec_t* ps_scale, const lof_projspec_t* ps_elem,
+                          const lof_rng_t* rng, uint64_t first_index, void* stream)
+{
+    int st = fwht_check(in, out, n, block_size);
+    if (st != LOF_OK) return st;
+    if (!ps_scale || !ps_elem) return fail(LOF_ERR_INVALID_ARG, "projspec is NULL");
+    if (mx_block_size != 16 && mx_block_size != 32 && mx_block_size != 64 && mx_block_size != 128)
+        return fail(LOF_ERR_UNSUPPORTED, "fwht + mx: mx block_size must be 16, 32, 64 or 128");
+    if (first_index % (uint64_t)mx_block_size != 0) return fail(LOF_ERR_INVALID_ARG, "first_index must be a multiple of the mx block_size");
+    MxArgs a;
+    std::memset(&a, 0, sizeof a);
+    st = make_plan(elem_fmt, LOF_F32, ps_elem->rounding_mode, ps_elem->stoch_length, &a.elem);
+    if (st != LOF_OK) return st;
+    st = make_plan(scale_fmt, LOF_F32, ps_scale->rounding_mode, 0, &a.scale);
+    if (st != LOF_OK) return st;
+    if (g_opt.round_fast.load()) a.fast = make_fast_plan(a.elem, ps_elem->rounding_mode);
+    a.pmn = lof_mx_priv_max_normal(elem_fmt);
+    a.scale_mode = ps_scale->rounding_mode;
+    a.block_size = mx_block_size;
+    if (n == 0) return LOF_OK;
+    const int sms = num_sms();
+    if (sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    const RngArgs re = make_rng(rng, kStreamElem, ps_elem->rounding_mode, ps_elem->stoch_length), rs = make_rng(rng, kStreamScale);
+    const MagicPlan smg = make_magic_plan(a.scale, ps_scale->rounding_mode);
+    const FastPlan sfp = make_fast_plan(a.scale, ps_scale->rounding_mode);
+    cudaError_t e = launch_fwht(2, ps_elem->rounding_mode, in, out, n, block_size, nullptr, 1.0f, &a, &smg, &sfp, re, rs, first_index, sms,
+                                static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "lof_fwht_mx_round launch");
+    g_launches.fetch_add(1);
+    return LOF_OK;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -1,0 +1,218 @@
+// lof_fwht.cu -- callers fused around the path: the block-diagonal orthonormal
+// Walsh-Hadamard rotation LoF_Linear applies to its activations (/root/reference/LoFloat/layers.py:182-216, 363-365)
+// fused with the rounding that follows it (STEMXRound :366-369 or STERound :378), one pass over HBM instead of the
+// reference's log2(B) + 2 passes (its _fwht materialises a new tensor per butterfly stage).
+//
+//     y = FWHT_B(x) * fl32(1 / sqrt(B))          per contiguous block of B elements (B a power of two, 4 .. 1024)
+//     out = y | virtual_round(scale * y, fmt) | virtual_mx_round(y, mx_block, ...)
+//
+// Bit-exactness with the reference's PyTorch formulation: its stages run h = 1, 2, 4, ... with new[i] = a + b,
+// new[i + h] = a - b for the pair (a, b) = (x[i], x[i + h]); every add / subtract here is the same fp32 operation on the
+// same operands in the same stage order (in-lane for h = 1, 2; shfl.xor across lanes for h = 4 .. 64; across the rows a
+// lane holds for h = 128 .. 512), then one fp32 multiply by the rounded constant.
+// Layout: a warp owns rows of 128 consecutive floats, lane l holds elements 4l .. 4l + 3 of each row (one 128-bit load).
+#include <cuda_runtime.h>
+
+#include "lof_core.cuh"
+#include "lof_mx_kernels.cuh"
+
+namespace lof {
+
+namespace {
+
+constexpr int kFwhtThreads = 256;
+enum : int { kFwhtPlain = 0, kFwhtRound = 1, kFwhtMx = 2 };
+
+struct FwhtArgs {
+    int log2_b;             // Hadamard block = 2^log2_b elements
+    float inv_sqrt_b;
+    RoundPlan plan;         // kFwhtRound
+    float pre_scale;        // kFwhtRound: fused scale-then-round (Lof_kernel.cu:41,53); 1 = none
+    MxArgs mx;              // kFwhtMx
+    MxScaleQuick sq;        // kFwhtMx: branch-free scale rounding where eligible
+};
+
+__device__ __forceinline__ void butterfly(float& a, float& b)
+{
+    const float s = __fadd_rn(a, b), d = __fsub_rn(a, b);
+    a = s; b = d;
+}
+
+// ROWS = rows (of 128 floats) one warp step holds per lane; a Hadamard block spans max(1, B / 128) of them
+template <int ROWS, int OP, int MODE>
+__global__ void __launch_bounds__(kFwhtThreads)
+fwht_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t nrows, FwhtArgs a, RngArgs rng, RngArgs rng_scale,
+            uint64_t first_index)
+{
+    constexpr int kWarps = kFwhtThreads / 32;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int64_t nsteps = (nrows + ROWS - 1) / ROWS;
+    const int lane_stages = min(a.log2_b, 7) - 2;            // shuffle stages h = 4 .. min(B, 128) / 2
+    const int row_stages = max(a.log2_b - 7, 0);             // register stages across rows, h = 128 ..
+
+    for (int64_t step = (int64_t)blockIdx.x * kWarps + warp; step < nsteps; step += (int64_t)gridDim.x * kWarps) {
+        const int64_t row0 = step * ROWS;
+        float4 v[ROWS];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            if (row0 + r < nrows) v[r] = ld_stream_f4(in + (row0 + r) * 32 + lane);
+            else v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // h = 1, 2: inside the lane's four elements
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            if (a.log2_b >= 1) { butterfly(v[r].x, v[r].y); butterfly(v[r].z, v[r].w); }
+            if (a.log2_b >= 2) { butterfly(v[r].x, v[r].z); butterfly(v[r].y, v[r].w); }
+        }
+        // h = 4 .. 64: across lanes
+        for (int s = 0; s < lane_stages; ++s) {
+            const int m = 1 << s;
+            const bool upper = (lane & m) != 0;
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                const float px = __shfl_xor_sync(0xFFFFFFFFu, v[r].x, m), py = __shfl_xor_sync(0xFFFFFFFFu, v[r].y, m);
+                const float pz = __shfl_xor_sync(0xFFFFFFFFu, v[r].z, m), pw = __shfl_xor_sync(0xFFFFFFFFu, v[r].w, m);
+                v[r].x = upper ? __fsub_rn(px, v[r].x) : __fadd_rn(v[r].x, px);
+                v[r].y = upper ? __fsub_rn(py, v[r].y) : __fadd_rn(v[r].y, py);
+                v[r].z = upper ? __fsub_rn(pz, v[r].z) : __fadd_rn(v[r].z, pz);
+                v[r].w = upper ? __fsub_rn(pw, v[r].w) : __fadd_rn(v[r].w, pw);
+            }
+        }
+        // h = 128 ..: across the rows this lane holds (rows of one block are consecutive and aligned: nrows-tail rows are zero)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            if (s < row_stages) {
+                const int hr = 1 << s;
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+                    if ((r & hr) == 0 && r + hr < ROWS) {
+                        butterfly(v[r].x, v[r + hr].x); butterfly(v[r].y, v[r + hr].y);
+                        butterfly(v[r].z, v[r + hr].z); butterfly(v[r].w, v[r + hr].w);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            v[r].x = __fmul_rn(v[r].x, a.inv_sqrt_b); v[r].y = __fmul_rn(v[r].y, a.inv_sqrt_b);
+            v[r].z = __fmul_rn(v[r].z, a.inv_sqrt_b); v[r].w = __fmul_rn(v[r].w, a.inv_sqrt_b);
+        }
+        if constexpr (OP == kFwhtMx) {
+            const int group = a.mx.block_size >> 2;               // lanes per MX block (4 .. 32)
+            const int log2_mx = 31 - __clz(a.mx.block_size);
+            float m[ROWS];
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                float t = amax4(v[r]);
+                for (int off = group >> 1; off > 0; off >>= 1) t = fmaxf(t, __shfl_xor_sync(0xFFFFFFFFu, t, off));
+                m[r] = t;
+            }
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                if (row0 + r >= nrows) continue;
+                const uint64_t g0 = first_index + (uint64_t)(row0 + r) * 128u + (uint64_t)lane * 4u;
+                float scale = 0.0f;                                   // computed by the block's first lane, then broadcast
+                if ((lane & (group - 1)) == 0) scale = mx_scale_quick(m[r], a.mx, a.sq, rng_scale, g0 >> log2_mx);
+                scale = __shfl_sync(0xFFFFFFFFu, scale, lane & ~(group - 1));
+                const MxBlockCtx c = mx_make_ctx(scale);
+                uint4 w = make_uint4(0, 0, 0, 0);
+                if constexpr (ModeTraits<MODE>::kUsesRng) w = philox_group4(rng, g0 >> 2);
+                float4 o;
+                o.x = mx_quant<MODE>(v[r].x, c, a.mx, w.x); o.y = mx_quant<MODE>(v[r].y, c, a.mx, w.y);
+                o.z = mx_quant<MODE>(v[r].z, c, a.mx, w.z); o.w = mx_quant<MODE>(v[r].w, c, a.mx, w.w);
+                st_stream_f4(out + (row0 + r) * 32 + lane, o);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                if (row0 + r >= nrows) continue;
+                float4 o = v[r];
+                if constexpr (OP == kFwhtRound) {
+                    const uint64_t g0 = first_index + (uint64_t)(row0 + r) * 128u + (uint64_t)lane * 4u;
+                    uint4 w = make_uint4(0, 0, 0, 0);
+                    if constexpr (ModeTraits<MODE>::kUsesRng) w = philox_group4(rng, g0 >> 2);
+                    if (a.pre_scale != 1.0f) {
+                        o.x = __fmul_rn(a.pre_scale, o.x); o.y = __fmul_rn(a.pre_scale, o.y);
+                        o.z = __fmul_rn(a.pre_scale, o.z); o.w = __fmul_rn(a.pre_scale, o.w);
+                    }
+                    o.x = __uint_as_float(round_params_elem<LOF_F32, MODE>(__float_as_uint(o.x), a.plan, w.x));
+                    o.y = __uint_as_float(round_params_elem<LOF_F32, MODE>(__float_as_uint(o.y), a.plan, w.y));
+                    o.z = __uint_as_float(round_params_elem<LOF_F32, MODE>(__float_as_uint(o.z), a.plan, w.z));
+                    o.w = __uint_as_float(round_params_elem<LOF_F32, MODE>(__float_as_uint(o.w), a.plan, w.w));
+                }
+                st_stream_f4(out + (row0 + r) * 32 + lane, o);
+            }
+        }
+    }
+}
+
+template <int OP, int MODE>
+cudaError_t launch_rows(int rows_per_block, const float* in, float* out, int64_t nrows, const FwhtArgs& a, const RngArgs& rng,
+                        const RngArgs& rng_scale, uint64_t first_index, int num_sms, cudaStream_t stream)
+{
+    const float4* vin = reinterpret_cast<const float4*>(in);
+    float4* vout = reinterpret_cast<float4*>(out);
+    constexpr int kWarps = kFwhtThreads / 32;
+    auto grid_for = [&](int rows) {
+        const int64_t nsteps = (nrows + rows - 1) / rows;
+        const int64_t want = (nsteps + kWarps - 1) / kWarps, cap = (int64_t)num_sms * 8;
+        return (unsigned)(want < 1 ? 1 : want < cap ? want : cap);
+    };
+    switch (rows_per_block) {
+    case 8: fwht_kernel<8, OP, MODE><<<grid_for(8), kFwhtThreads, 0, stream>>>(vin, vout, nrows, a, rng, rng_scale, first_index); break;
+    default: fwht_kernel<4, OP, MODE><<<grid_for(4), kFwhtThreads, 0, stream>>>(vin, vout, nrows, a, rng, rng_scale, first_index); break;   // B <= 512
+    }
+    return cudaGetLastError();
+}
+
+template <int OP>
+cudaError_t launch_mode(int mode, int rows_per_block, const float* in, float* out, int64_t nrows, const FwhtArgs& a, const RngArgs& rng,
+                        const RngArgs& rng_scale, uint64_t first_index, int num_sms, cudaStream_t stream)
+{
+    switch (mode) {
+#define LOF_CASE(M) case M: return launch_rows<OP, M>(rows_per_block, in, out, nrows, a, rng, rng_scale, first_index, num_sms, stream);
+        LOF_CASE(LOF_RoundToNearestEven) LOF_CASE(LOF_RoundTowardsZero) LOF_CASE(LOF_RoundAwayFromZero)
+        LOF_CASE(LOF_StochasticRoundingA) LOF_CASE(LOF_RoundToNearestOdd) LOF_CASE(LOF_RoundDown)
+        LOF_CASE(LOF_RoundUp) LOF_CASE(LOF_RoundTiesToAway) LOF_CASE(LOF_StochasticRoundingB)
+        LOF_CASE(LOF_StochasticRoundingC) LOF_CASE(LOF_True_StochasticRounding)
+        LOF_CASE(LOF_ProbabilisticRounding) LOF_CASE(LOF_RoundToOdd) LOF_CASE(LOF_RoundTiesTowardsZero)
+        LOF_CASE(LOF_StochasticRoundingD)
+#undef LOF_CASE
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace
+
+// op: 0 plain FWHT, 1 + virtual_round(params), 2 + virtual_mx_round.  n % 128 == 0, block in {4 .. 1024}, 16-byte aligned.
+cudaError_t launch_fwht(int op, int mode, const float* in, float* out, int64_t n, int hadamard_block, const RoundPlan* plan,
+                        float pre_scale, const MxArgs* mx, const MagicPlan* scale_magic, const FastPlan* scale_fast, const RngArgs& rng,
+                        const RngArgs& rng_scale, uint64_t first_index, int num_sms, cudaStream_t stream)
+{
+    FwhtArgs a;
+    memset(&a, 0, sizeof a);
+    int lg = 0;
+    while ((1 << lg) < hadamard_block) ++lg;
+    a.log2_b = lg;
+    a.inv_sqrt_b = (float)(1.0 / sqrt((double)hadamard_block));       // layers.py:215: flat * (1.0 / math.sqrt(block_size))
+    if (plan) a.plan = *plan;
+    a.pre_scale = pre_scale;
+    if (mx) {
+        a.mx = *mx;
+        if (scale_magic) a.sq.magic = *scale_magic;
+        if (scale_fast) a.sq.fast = *scale_fast;
+        const int sm = mx->scale_mode;
+        a.sq.quick_mode_ok = sm == LOF_RoundToNearestEven || sm == LOF_RoundTowardsZero || sm == LOF_RoundAwayFromZero ||
+                             sm == LOF_RoundUp || sm == LOF_RoundDown || sm == LOF_RoundToOdd;
+    }
+    const int rows_per_block = hadamard_block > 512 ? 8 : 4;
+    const int64_t nrows = n / 128;
+    switch (op) {
+    case kFwhtRound: return launch_mode<kFwhtRound>(mode, rows_per_block, in, out, nrows, a, rng, rng_scale, first_index, num_sms, stream);
+    case kFwhtMx:    return launch_mode<kFwhtMx>(mode, rows_per_block, in, out, nrows, a, rng, rng_scale, first_index, num_sms, stream);
+    default:         return launch_rows<kFwhtPlain, LOF_RoundToNearestEven>(rows_per_block, in, out, nrows, a, rng, rng_scale, first_index, num_sms, stream);
+    }
+}
+
+}  // namespace lof

@@ -43,6 +43,50 @@ __device__ __forceinline__ float mx_block_scale(float amax, const MxArgs& a, con
     return __uint_as_float(round_params_elem_rt<LOF_F32>(a.scale_mode, __float_as_uint(ratio), sp, w));
 }
 
+// virtual_round(amax / pmn, scale format) on the branch-free routines of lof_fast_f32.cuh where they apply (the same
+// selection lof_mx_fast.cu makes; every one of them is proven equal to the exact routine by the exhaustive sweeps),
+// the generic 15-mode routine otherwise
+struct MxScaleQuick {
+    MagicPlan magic;
+    FastPlan fast;
+    int32_t quick_mode_ok;          // scale mode in {RNE, RTZ, RAZ, RU, RD, RoundToOdd}
+};
+
+__device__ __forceinline__ float mx_scale_quick(float amax, const MxArgs& a, const MxScaleQuick& q, const RngArgs& rng_scale, uint64_t gblock)
+{
+    if (q.quick_mode_ok) {
+        const uint32_t x = __float_as_uint(__fdiv_rn(amax, a.pmn));          // >= 0, never NaN (fmaxf drops NaNs)
+        const MagicPlan& p = q.magic;
+        if (p.valid && !(x >= p.limit) && !((x - 1u) < p.lo_rare)) {
+            uint32_t mag, rs;
+            switch (a.scale_mode) {
+            case LOF_RoundToNearestEven: rs = magic_round_core<LOF_RoundToNearestEven>(x, p.c_add, p.c_floor, mag); break;
+            case LOF_RoundTowardsZero:   rs = magic_round_core<LOF_RoundTowardsZero>(x, p.c_add, p.c_floor, mag); break;
+            case LOF_RoundAwayFromZero:  rs = magic_round_core<LOF_RoundAwayFromZero>(x, p.c_add, p.c_floor, mag); break;
+            case LOF_RoundUp:            rs = magic_round_core<LOF_RoundUp>(x, p.c_add, p.c_floor, mag); break;
+            case LOF_RoundDown:          rs = magic_round_core<LOF_RoundDown>(x, p.c_add, p.c_floor, mag); break;
+            default:                     rs = magic_round_core<LOF_RoundToOdd>(x, p.c_add, p.c_floor, mag); break;
+            }
+            return __uint_as_float((mag >= p.ovf_thresh) ? (a.scale.saturating ? x : 0x7F800000u) : rs);
+        }
+        if (q.fast.valid) {
+            bool rare = false;
+            uint32_t rb;
+            const bool sat = a.scale.saturating != 0;
+            switch (a.scale_mode) {
+            case LOF_RoundToNearestEven: rb = round_fast_f32_rt<LOF_RoundToNearestEven>(x, q.fast, sat, 0u, rare); break;
+            case LOF_RoundTowardsZero:   rb = round_fast_f32_rt<LOF_RoundTowardsZero>(x, q.fast, sat, 0u, rare); break;
+            case LOF_RoundAwayFromZero:  rb = round_fast_f32_rt<LOF_RoundAwayFromZero>(x, q.fast, sat, 0u, rare); break;
+            case LOF_RoundUp:            rb = round_fast_f32_rt<LOF_RoundUp>(x, q.fast, sat, 0u, rare); break;
+            case LOF_RoundDown:          rb = round_fast_f32_rt<LOF_RoundDown>(x, q.fast, sat, 0u, rare); break;
+            default:                     rb = round_fast_f32_rt<LOF_RoundToOdd>(x, q.fast, sat, 0u, rare); break;
+            }
+            if (!rare) return __uint_as_float(rb);
+        }
+    }
+    return mx_block_scale(amax, a, rng_scale, gblock);
+}
+
 // Per-block constants for the element pass.  x / scale is evaluated as x * (1/scale) when
 // scale is a power of two whose reciprocal is representable: both are the correctly
 // rounded value of the same real number, so the result is bit-identical to the division.

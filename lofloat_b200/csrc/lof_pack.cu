@@ -449,50 +449,6 @@ round_strict_kernel(const float* __restrict__ src, float* __restrict__ dst, int6
 // A lane owns 4 consecutive elements (one 128-bit load), a block is BS / 4 lanes of one warp (amax by shfl.xor).
 // 4 B read + (n/8 + 1/BS) B written per element.
 // ------------------------------------------------------------------------------------------------
-// virtual_round(amax / pmn, scale format) on the branch-free routines of lof_fast_f32.cuh where they apply (the same
-// selection lof_mx_fast.cu makes; every one of them is proven equal to the exact routine by the exhaustive sweeps),
-// the generic 15-mode routine otherwise
-struct MxScaleQuick {
-    MagicPlan magic;
-    FastPlan fast;
-    int32_t quick_mode_ok;          // scale mode in {RNE, RTZ, RAZ, RU, RD, RoundToOdd}
-};
-
-__device__ __forceinline__ float mx_scale_quick(float amax, const MxArgs& a, const MxScaleQuick& q, const RngArgs& rng_scale, uint64_t gblock)
-{
-    if (q.quick_mode_ok) {
-        const uint32_t x = __float_as_uint(__fdiv_rn(amax, a.pmn));          // >= 0, never NaN (fmaxf drops NaNs)
-        const MagicPlan& p = q.magic;
-        if (p.valid && !(x >= p.limit) && !((x - 1u) < p.lo_rare)) {
-            uint32_t mag, rs;
-            switch (a.scale_mode) {
-            case LOF_RoundToNearestEven: rs = magic_round_core<LOF_RoundToNearestEven>(x, p.c_add, p.c_floor, mag); break;
-            case LOF_RoundTowardsZero:   rs = magic_round_core<LOF_RoundTowardsZero>(x, p.c_add, p.c_floor, mag); break;
-            case LOF_RoundAwayFromZero:  rs = magic_round_core<LOF_RoundAwayFromZero>(x, p.c_add, p.c_floor, mag); break;
-            case LOF_RoundUp:            rs = magic_round_core<LOF_RoundUp>(x, p.c_add, p.c_floor, mag); break;
-            case LOF_RoundDown:          rs = magic_round_core<LOF_RoundDown>(x, p.c_add, p.c_floor, mag); break;
-            default:                     rs = magic_round_core<LOF_RoundToOdd>(x, p.c_add, p.c_floor, mag); break;
-            }
-            return __uint_as_float((mag >= p.ovf_thresh) ? (a.scale.saturating ? x : 0x7F800000u) : rs);
-        }
-        if (q.fast.valid) {
-            bool rare = false;
-            uint32_t rb;
-            const bool sat = a.scale.saturating != 0;
-            switch (a.scale_mode) {
-            case LOF_RoundToNearestEven: rb = round_fast_f32_rt<LOF_RoundToNearestEven>(x, q.fast, sat, 0u, rare); break;
-            case LOF_RoundTowardsZero:   rb = round_fast_f32_rt<LOF_RoundTowardsZero>(x, q.fast, sat, 0u, rare); break;
-            case LOF_RoundAwayFromZero:  rb = round_fast_f32_rt<LOF_RoundAwayFromZero>(x, q.fast, sat, 0u, rare); break;
-            case LOF_RoundUp:            rb = round_fast_f32_rt<LOF_RoundUp>(x, q.fast, sat, 0u, rare); break;
-            case LOF_RoundDown:          rb = round_fast_f32_rt<LOF_RoundDown>(x, q.fast, sat, 0u, rare); break;
-            default:                     rb = round_fast_f32_rt<LOF_RoundToOdd>(x, q.fast, sat, 0u, rare); break;
-            }
-            if (!rare) return __uint_as_float(rb);
-        }
-    }
-    return mx_block_scale(amax, a, rng_scale, gblock);
-}
-
 template <int MODE, bool FAST>
 __global__ void __launch_bounds__(kPackThreads)
 mx_encode_kernel(const float4* __restrict__ in, int64_t nvec, MxArgs a, MxScaleQuick sq, CodecPlan scale_codec, CodecPlan elem_codec,

@@ -464,6 +464,54 @@ def virtual_round_strict(input: torch.Tensor, params: FloatFormatDescriptor, rou
     return out
 
 
+def fwht(input: torch.Tensor, block_size=None, *, params: FloatFormatDescriptor | None = None, round_mode=RoundingMode.RoundToNearestEven,
+         stoch_len: int = 0, scale: float = 1.0, mx_block_size: int | None = None, scale_format: FloatFormatDescriptor | None = None,
+         scale_round_mode=RoundingMode.RoundToNearestEven, rng=None, first_index: int = 0) -> torch.Tensor:
+    """Orthonormal Walsh-Hadamard transform along the last dim in blocks of `block_size` (None = the whole last dim), the
+    `_fwht` of LoFloat/layers.py:182-216, optionally FUSED with the rounding LoF_Linear applies next: `params` alone ->
+    virtual_round(scale * y, params); `params` + `mx_block_size` (+ `scale_format`) -> virtual_mx_round(y, ...)."""
+    if input.dtype != torch.float32 or not input.is_cuda:
+        raise RuntimeError("fwht: float32 CUDA tensors only")
+    n_last = input.shape[-1]
+    if block_size is None:
+        block_size = n_last
+    if block_size <= 0 or (block_size & (block_size - 1)) != 0:
+        raise ValueError(f"block_size must be a power of 2, got {block_size}")
+    if n_last % block_size != 0:
+        raise ValueError(f"block_size {block_size} must divide last dim {n_last}")
+    L = _lib.lib()
+    x = input.contiguous()
+    out = torch.empty_like(x)
+    n = x.numel()
+    mode = RoundingMode(int(round_mode))
+    with torch.cuda.device(x.device):
+        if params is None:
+            st = L.lof_fwht_f32(x.data_ptr(), out.data_ptr(), n, int(block_size), _stream_ptr(x))
+        elif mx_block_size is None:
+            ps = CProjSpec(int(mode), 0, int(stoch_len))
+            r = _next_rng(mode in _STOCHASTIC, rng)
+            f = params._c()
+            st = L.lof_fwht_round_f32(x.data_ptr(), out.data_ptr(), n, int(block_size), C.byref(f), C.byref(ps), float(scale), C.byref(r),
+                                      int(first_index), _stream_ptr(x))
+        else:
+            if n_last % int(mx_block_size) != 0:
+                raise ValueError(f"mx scaling needs the last dim ({n_last}) divisible by mx_block_size ({mx_block_size})")
+            sf = scale_format if scale_format is not None else _default_e8m0()
+            smode = RoundingMode(int(scale_round_mode))
+            ps_e, ps_s = CProjSpec(int(mode), 0, int(stoch_len)), CProjSpec(int(smode), 0, 0)
+            r = _next_rng(mode in _STOCHASTIC or smode in _STOCHASTIC, rng)
+            fe, fs = params._c(), sf._c()
+            st = L.lof_fwht_mx_round_f32(x.data_ptr(), out.data_ptr(), n, int(block_size), int(mx_block_size), C.byref(fs), C.byref(fe),
+                                         C.byref(ps_s), C.byref(ps_e), C.byref(r), int(first_index), _stream_ptr(x))
+    _lib.check(st, "fwht")
+    return out
+
+
+def _default_e8m0():
+    from .formats import create_e8m0_params
+    return create_e8m0_params()
+
+
 def mx_encode(input: torch.Tensor, block_size: int, element_format: FloatFormatDescriptor, scale_format: FloatFormatDescriptor,
               round_mode=RoundingMode.RoundToNearestEven, scale_round_mode=RoundingMode.RoundToNearestEven, stoch_len: int = 0,
               endian=PackEndian.Forward, *, rng=None, first_index: int = 0):

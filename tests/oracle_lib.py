@@ -548,3 +548,18 @@ def o_mx_decode(scales: np.ndarray, elems: np.ndarray, n: int, block: int, scale
     oracle().lofo_mx_decode_f32(_ptr(np.ascontiguousarray(scales, np.uint8)), _ptr(np.ascontiguousarray(elems, np.uint8)), _ptr(out), n,
                                 block, C.byref(scale_f), C.byref(elem_f), endian)
     return out
+
+
+def o_fwht(x: np.ndarray, block: int) -> np.ndarray:
+    """Orthonormal block Walsh-Hadamard transform along the last axis, restating LoFloat/layers.py:182-216 (`_fwht`):
+    stages h = 1, 2, 4, ...: (a, b) = (x[i], x[i + h]) -> (a + b, a - b), all in float32, then * float32(1 / sqrt(block))."""
+    x = np.ascontiguousarray(x, np.float32)
+    flat = x.reshape(-1, block)
+    M = flat.shape[0]
+    h = 1
+    while h < block:
+        v = flat.reshape(M, block // (2 * h), 2, h)
+        a, b = v[:, :, 0, :], v[:, :, 1, :]
+        flat = np.stack([a + b, a - b], axis=2).reshape(M, block)
+        h *= 2
+    return (flat * np.float32(1.0 / np.sqrt(float(block)))).reshape(x.shape)

@@ -1028,3 +1028,46 @@ def test_bf16_container_fast_path_equals_exact_all_patterns(lof, cuda_dev):
                     assert torch.equal(got, want), (name, L.MODE_NAMES[mode], sl)
     finally:
         _lib.set_option("round.fast", 2)
+
+
+def test_fused_hadamard_rounding(lof, cuda_dev):
+    """Row f-3: the block Walsh-Hadamard rotation of LoF_Linear (layers.py:182-216) fused with the rounding that follows it.
+    Plain transform == the oracle's restatement of `_fwht` and == the same formula evaluated with torch ops on the device
+    (what the reference computes), bit for bit, for every block size 2 .. 1024; the fused variants == the separate ops."""
+    def torch_fwht(x, block):                      # same dataflow as layers.py:182-216, torch float32 ops on the device
+        flat = x.reshape(-1, block)
+        M, h = flat.shape[0], 1
+        while h < block:
+            v = flat.view(M, block // (2 * h), 2, h)
+            flat = torch.stack([v[:, :, 0, :] + v[:, :, 1, :], v[:, :, 0, :] - v[:, :, 1, :]], dim=2).reshape(M, block)
+            h *= 2
+        return (flat * (1.0 / float(np.sqrt(block)))).view(x.shape)
+    rng = np.random.default_rng(4)
+    e4m3, e8m0 = lof.create_p3109_params(8, 4, bias=7), lof.create_e8m0_params()
+    for block in (2, 4, 8, 16, 32, 64, 128, 256, 512, 1024):
+        cols = max(block, 128) * 3
+        x = (rng.standard_normal((37, cols)) * np.exp2(rng.integers(-6, 7, (37, 1)))).astype(np.float32)
+        if (37 * cols) % 128:
+            x = x[:32]
+        xt = _gpu(x, cuda_dev)
+        y = lof.fwht(xt, block)
+        assert L.bits_equal(_np(y), L.o_fwht(x, block)), block
+        assert torch.equal(y, torch_fwht(xt, block)), block
+        for mode, sl, scale in ((L.RNE, 0, 1.0), (L.RTO, 0, 0.5), (L.SR_A, 5, 3.0), (L.RD, 0, 1.0)):
+            got = lof.fwht(xt, block, params=e4m3, round_mode=mode, stoch_len=sl, scale=scale, rng=(3, 1))
+            assert torch.equal(got, lof.virtual_round(y, e4m3, mode, sl, scale, rng=(3, 1))), (block, mode)
+        for mxb in (16, 32, 128):
+            if cols % mxb:
+                continue
+            for mode in (L.RNE, L.RTZ, L.TRUE_SR):
+                got = lof.fwht(xt, block, params=e4m3, round_mode=mode, mx_block_size=mxb, scale_format=e8m0, rng=(9, 2))
+                want = lof.virtual_mx_round(y, mxb, e4m3, e8m0, mode, rng=(9, 2))
+                assert torch.equal(got.view(torch.int32), want.view(torch.int32)), (block, mxb, mode)
+    # involution (H_B / sqrt(B) is orthonormal and symmetric) up to rounding, on the C3 shape with the whole-row default
+    big = torch.randn(4096, 1024, device=cuda_dev)
+    back = lof.fwht(lof.fwht(big), None)
+    assert float((back - big).abs().max()) < 1e-5
+    with pytest.raises(ValueError):
+        lof.fwht(big, 48)
+    with pytest.raises(lof.LoFloatError):
+        lof.fwht(torch.randn(8, 4096, device=cuda_dev), 2048)                               # > 1024: not handled by the fused kernel
