@@ -15,12 +15,20 @@
  *   - lof_round_to_odd_fma .............. /root/reference/src/blis_lof_gemm.hpp:63-99
  *   - lof_sgemm_ukr accumulation ........ /root/reference/src/blis_lof_gemm.hpp:147-262
  *     (+ BLIS generic KC=256 panelling, third_party/blis/ref_kernels/bli_cntx_ref.c:383)
+ *   - storage codec ..................... /root/reference/src/lo_pack.hpp:58-319 (group geometry, put/get bits,
+ *                                         convert_float_to_rep, convert_rep_to_float, LoF_encode / LoF_decode)
+ * plus three statements that have NO reference function of their own ("parity unpinned" for these as a whole; each is a
+ * composition of pinned pieces and is tied back to them by tests/test_oracle_golden.py):
+ *   - lofo_gemm_chunked_f32 (k-chunk accumulation: the design intent of gemms.hpp:430-552, which is not runnable)
+ *   - lofo_mx_encode_f32 / lofo_mx_decode_f32 (virtual_mx_round's rounding composed with the codec)
+ *   - o_fwht in tests/oracle_lib.py (numpy restatement of LoFloat/layers.py:182-216)
  *
  * PARITY PINNING: the restatement is pinned against the reference itself, compiled from
  * /root/reference by oracle/Makefile into oracle/_ref/libref_shim.so (tests/test_oracle_vs_ref.py,
  * runs wherever /root/reference exists) and against golden vectors generated from that
  * shim and committed under tests/golden/ (tests/test_oracle_golden.py, runs everywhere).
- * float and double sources are pinned that way; the fp16 / bf16 source types go through
+ * float and double sources and the storage codec (17 formats x 9 deterministic modes x 3 saturation modes, decode tables,
+ * packed bytes in both slot orders, the typed Templated_Float<Fp> ground truth) are pinned that way; the fp16 / bf16 source types go through
  * the same macro-expanded core but the reference's host build has no 16-bit source type
  * (c10::Half exists only under USE_CUDA), so for those two "parity unpinned" applies to
  * the container type handling (conversions), not to the rounding core.

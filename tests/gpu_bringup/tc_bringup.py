@@ -1,7 +1,8 @@
-"""Bring-up / characterisation driver for the tcgen05 chunked GEMM (runs on the GPU box).
+"""Bring-up / characterisation driver for the tcgen05 chunked GEMM (runs on the GPU box).  TEST INFRASTRUCTURE: it checks
+against the CPU oracle, which is why it lives under tests/.
 
-    python scripts/tc_bringup.py            # every step, each in its own subprocess with a timeout
-    python scripts/tc_bringup.py <step>     # one step in this process
+    python tests/gpu_bringup/tc_bringup.py            # every step, each in its own subprocess with a timeout
+    python tests/gpu_bringup/tc_bringup.py <step>     # one step in this process
 
 Each step prints one line starting with PASS / FAIL / INFO so the gpurun tail stays readable.
 """
@@ -10,7 +11,7 @@ import sys
 import time
 from pathlib import Path
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
