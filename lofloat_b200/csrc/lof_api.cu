@@ -29,8 +29,9 @@ cudaError_t launch_mx_fast(int mode, int scale_mode, const float* in, float* out
                            const MagicPlan& elem_magic, const MagicPlan& scale_magic, const FastPlan& scale_fast, int scale_mantissa_bits,
                            const MxLaunchCfg& cfg, cudaStream_t stream, int64_t* main_elems, int* launches);
 cudaError_t launch_fwht(int op, int mode, const float* in, float* out, int64_t n, int hadamard_block, const RoundPlan* plan,
-                        float pre_scale, const MxArgs* mx, const MagicPlan* scale_magic, const FastPlan* scale_fast, const RngArgs& rng,
-                        const RngArgs& rng_scale, uint64_t first_index, int num_sms, cudaStream_t stream);
+                        float pre_scale, const MxArgs* mx, const MagicPlan* scale_magic, const FastPlan* scale_fast,
+                        const MagicPlan* elem_magic, const RngArgs& rng, const RngArgs& rng_scale, uint64_t first_index, int num_sms,
+                        cudaStream_t stream);
 cudaError_t run_mx_div_selftest(float pmn, unsigned long long* host_mismatches, cudaStream_t stream);
 cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int mode,
                            int accum_mant_bits, const lof_format_t* acc_fmt, const RoundPlan* acc_plan, const FastPlan* acc_fast,
@@ -647,7 +648,7 @@ int lof_fwht_f32(const float* in, float* out, int64_t n, int block_size, void* s
     const int sms = num_sms();
     if (sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
     const RngArgs none = make_rng(nullptr, kStreamElem);
-    cudaError_t e = launch_fwht(0, 0, in, out, n, block_size, nullptr, 1.0f, nullptr, nullptr, nullptr, none, none, 0, sms, static_cast<cudaStream_t>(stream));
+    cudaError_t e = launch_fwht(0, 0, in, out, n, block_size, nullptr, 1.0f, nullptr, nullptr, nullptr, nullptr, none, none, 0, sms, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "lof_fwht launch");
     g_launches.fetch_add(1);
     return LOF_OK;
@@ -670,7 +671,7 @@ int lof_fwht_round_f32(const float* in, float* out, int64_t n, int block_size, c
     const int sms = num_sms();
     if (sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
     const RngArgs ra = make_rng(rng, kStreamElem, mode, ps->stoch_length);
-    cudaError_t e = launch_fwht(1, mode, in, out, n, block_size, &plan, (float)scale, nullptr, nullptr, nullptr, ra, ra, first_index, sms,
+    cudaError_t e = launch_fwht(1, mode, in, out, n, block_size, &plan, (float)scale, nullptr, nullptr, nullptr, nullptr, ra, ra, first_index, sms,
                                 static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "lof_fwht_round launch");
     g_launches.fetch_add(1);
@@ -703,7 +704,11 @@ int lof_fwht_mx_round_f32(const float* in, float* out, int64_t n, int block_size
     const RngArgs re = make_rng(rng, kStreamElem, ps_elem->rounding_mode, ps_elem->stoch_length), rs = make_rng(rng, kStreamScale);
     const MagicPlan smg = make_magic_plan(a.scale, ps_scale->rounding_mode);
     const FastPlan sfp = make_fast_plan(a.scale, ps_scale->rounding_mode);
-    cudaError_t e = launch_fwht(2, ps_elem->rounding_mode, in, out, n, block_size, nullptr, 1.0f, &a, &smg, &sfp, re, rs, first_index, sms,
+    // magic-add element rounding for power-of-two scales: same eligibility as the second-generation MX kernel (lof_mx_fast.cu)
+    const MagicPlan emg = make_magic_plan(a.elem, ps_elem->rounding_mode);
+    const bool elem_fast = g_opt.round_fast.load() >= 2 && emg.valid && emg.limit == 0xFFFFFFFFu && !emg.check_denorm_in &&
+                           scale_fmt->mantissa_bits == 0 && !mode_uses_rng(ps_elem->rounding_mode);
+    cudaError_t e = launch_fwht(2, ps_elem->rounding_mode, in, out, n, block_size, nullptr, 1.0f, &a, &smg, &sfp, elem_fast ? &emg : nullptr, re, rs, first_index, sms,
                                 static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "lof_fwht_mx_round launch");
     g_launches.fetch_add(1);

@@ -30,6 +30,8 @@ struct FwhtArgs {
     float pre_scale;        // kFwhtRound: fused scale-then-round (Lof_kernel.cu:41,53); 1 = none
     MxArgs mx;              // kFwhtMx
     MxScaleQuick sq;        // kFwhtMx: branch-free scale rounding where eligible
+    MagicPlan elem_magic;   // kFwhtMx: magic-add element rounding for power-of-two scales when elem_fast_ok
+    int elem_fast_ok;
 };
 
 __device__ __forceinline__ void butterfly(float& a, float& b)
@@ -115,12 +117,25 @@ fwht_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t nro
                 float scale = 0.0f;                                   // computed by the block's first lane, then broadcast
                 if ((lane & (group - 1)) == 0) scale = mx_scale_quick(m[r], a.mx, a.sq, rng_scale, g0 >> log2_mx);
                 scale = __shfl_sync(0xFFFFFFFFu, scale, lane & ~(group - 1));
-                const MxBlockCtx c = mx_make_ctx(scale);
                 uint4 w = make_uint4(0, 0, 0, 0);
                 if constexpr (ModeTraits<MODE>::kUsesRng) w = philox_group4(rng, g0 >> 2);
                 float4 o;
-                o.x = mx_quant<MODE>(v[r].x, c, a.mx, w.x); o.y = mx_quant<MODE>(v[r].y, c, a.mx, w.y);
-                o.z = mx_quant<MODE>(v[r].z, c, a.mx, w.z); o.w = mx_quant<MODE>(v[r].w, c, a.mx, w.w);
+                const uint32_t sb = __float_as_uint(scale);
+                bool done = false;
+                if constexpr (FastTraits<MODE>::kFaddSub) {
+                    if (a.elem_fast_ok && (sb & 0x007FFFFFu) == 0u && (sb - 0x00800000u) < 0x7E800000u) {   // normal power of two, 2^-126 .. 2^126
+                        const float recip = __uint_as_float(0x7F000000u - sb);                               // 2^-k, exact
+                        const bool sat = a.mx.elem.saturating != 0;
+                        o.x = mx_quant_magic<MODE>(v[r].x, recip, scale, a.elem_magic, sat); o.y = mx_quant_magic<MODE>(v[r].y, recip, scale, a.elem_magic, sat);
+                        o.z = mx_quant_magic<MODE>(v[r].z, recip, scale, a.elem_magic, sat); o.w = mx_quant_magic<MODE>(v[r].w, recip, scale, a.elem_magic, sat);
+                        done = true;
+                    }
+                }
+                if (!done) {
+                    const MxBlockCtx c = mx_make_ctx(scale);
+                    o.x = mx_quant<MODE>(v[r].x, c, a.mx, w.x); o.y = mx_quant<MODE>(v[r].y, c, a.mx, w.y);
+                    o.z = mx_quant<MODE>(v[r].z, c, a.mx, w.z); o.w = mx_quant<MODE>(v[r].w, c, a.mx, w.w);
+                }
                 st_stream_f4(out + (row0 + r) * 32 + lane, o);
             }
         } else {
@@ -187,8 +202,9 @@ cudaError_t launch_mode(int mode, int rows_per_block, const float* in, float* ou
 
 // op: 0 plain FWHT, 1 + virtual_round(params), 2 + virtual_mx_round.  n % 128 == 0, block in {4 .. 1024}, 16-byte aligned.
 cudaError_t launch_fwht(int op, int mode, const float* in, float* out, int64_t n, int hadamard_block, const RoundPlan* plan,
-                        float pre_scale, const MxArgs* mx, const MagicPlan* scale_magic, const FastPlan* scale_fast, const RngArgs& rng,
-                        const RngArgs& rng_scale, uint64_t first_index, int num_sms, cudaStream_t stream)
+                        float pre_scale, const MxArgs* mx, const MagicPlan* scale_magic, const FastPlan* scale_fast,
+                        const MagicPlan* elem_magic, const RngArgs& rng, const RngArgs& rng_scale, uint64_t first_index, int num_sms,
+                        cudaStream_t stream)
 {
     FwhtArgs a;
     memset(&a, 0, sizeof a);
@@ -202,6 +218,7 @@ cudaError_t launch_fwht(int op, int mode, const float* in, float* out, int64_t n
         a.mx = *mx;
         if (scale_magic) a.sq.magic = *scale_magic;
         if (scale_fast) a.sq.fast = *scale_fast;
+        if (elem_magic) { a.elem_magic = *elem_magic; a.elem_fast_ok = 1; }
         const int sm = mx->scale_mode;
         a.sq.quick_mode_ok = sm == LOF_RoundToNearestEven || sm == LOF_RoundTowardsZero || sm == LOF_RoundAwayFromZero ||
                              sm == LOF_RoundUp || sm == LOF_RoundDown || sm == LOF_RoundToOdd;

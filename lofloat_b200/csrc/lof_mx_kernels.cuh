@@ -128,6 +128,21 @@ __device__ __forceinline__ float mx_quant(float x, const MxBlockCtx& c, const Mx
     return c.live ? r : 0.0f;
 }
 
+// Element quantisation on the magic-add routine (lof_fast_f32.cuh) for a block whose scale is a normal power of two
+// 2^k: x / scale is the exact product x * 2^-k, the rounding is one magic add, the result is scaled back exactly.
+// Same sequence as lof_mx_fast.cu's quant_fast (pinned there by the bit-exact MX tests); the caller guarantees that the
+// element (format, mode) is magic-eligible without the checked variants.
+template <int MODE>
+__device__ __forceinline__ float mx_quant_magic(float x, float recip, float scale, const MagicPlan& em, bool sat)
+{
+    const float q = __fmul_rn(x, recip);
+    uint32_t mag;
+    const uint32_t rs = magic_round_core<MODE>(__float_as_uint(q), em.c_add, em.c_floor, mag);
+    const uint32_t rb = (mag >= em.ovf_thresh) ? (sat ? __float_as_uint(q) : 0x7F800000u) : rs;
+    const float o = __fmul_rn(__uint_as_float(rb), scale);
+    return (x != x) ? __uint_as_float(0x7FC00000u) : o;                     // NaN element -> +qNaN
+}
+
 __device__ __forceinline__ float amax4(const float4& v)
 {
     return fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
