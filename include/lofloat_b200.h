@@ -161,6 +161,14 @@ LOF_API int lof_gemm_f32(const float* A, const float* B, float* C, int64_t M, in
                  int accum_mant_bits, const lof_projspec_t* ps, int64_t kc,
                  float alpha, float beta, const lof_rng_t* rng, void* stream);
 
+/* Batched form of lof_gemm_f32: `batch` independent GEMMs C_b = A_b * B_b in ONE launch (matrix b starts at
+ * A + b * stride_a etc., row-major, contiguous rows), replacing the Python per-(batch, head) loop of `_lof_gemm_2d`
+ * (LoFloat/layers.py:142-149).  Each C_b is bit-identical to the single call on (A_b, B_b); for the stochastic modes the
+ * rounding-event index continues across the batch. */
+LOF_API int lof_gemm_batched_f32(const float* A, const float* B, float* C, int64_t batch, int64_t M, int64_t N, int64_t K,
+                                 int64_t stride_a, int64_t stride_b, int64_t stride_c, int accum_mant_bits,
+                                 const lof_projspec_t* ps, int64_t kc, float alpha, float beta, const lof_rng_t* rng, void* stream);
+
 /* Chunked tensor-core mode (tcgen05 + TMEM): after every k_chunk columns of K the fp32 partial product P of
  * the chunk (tensor core, fp32 accumulate) is folded into the running accumulator, which lives in the
  * accumulator format:

@@ -26,7 +26,7 @@ ABI_SYMBOLS = (
     "lof_round_params_host", "lof_round_mantissa_host", "lof_mx_round_f32_host",
     "lof_abi_version", "lof_status_string", "lof_last_error_string", "lof_kernel_launch_count",
     "lof_mx_priv_max_normal", "lof_set_option", "lof_get_option", "lof_selftest_mx_division",
-    "lof_packed_size", "lof_encode_f32", "lof_decode_f32", "lof_gemm_chunked_packed", "lof_round_strict_f32", "lof_mx_encode_f32", "lof_mx_decode_f32", "lof_fwht_f32", "lof_fwht_round_f32", "lof_fwht_mx_round_f32",
+    "lof_packed_size", "lof_encode_f32", "lof_decode_f32", "lof_gemm_chunked_packed", "lof_round_strict_f32", "lof_mx_encode_f32", "lof_mx_decode_f32", "lof_gemm_batched_f32", "lof_fwht_f32", "lof_fwht_round_f32", "lof_fwht_mx_round_f32",
 )
 LOF_PACK_FORWARD, LOF_PACK_REVERSE = 0, 1
 
@@ -95,10 +95,12 @@ def _declare(lib):
     lib.lof_encode_f32.restype = i32
     lib.lof_decode_f32.argtypes = [vp, vp, i64, PC, i32, vp]
     lib.lof_decode_f32.restype = i32
+    lib.lof_gemm_batched_f32.argtypes = [vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, i32, PP, i64, f32, f32, PR, vp]
+    lib.lof_gemm_batched_f32.restype = i32
     lib.lof_fwht_f32.argtypes = [vp, vp, i64, i32, vp]
     lib.lof_fwht_round_f32.argtypes = [vp, vp, i64, i32, PF, PP, f64, PR, u64, vp]
     lib.lof_fwht_mx_round_f32.argtypes = [vp, vp, i64, i32, i32, PF, PF, PP, PP, PR, u64, vp]
-    for _n in ("lof_fwht_f32", "lof_fwht_round_f32", "lof_fwht_mx_round_f32"):
+    for _n in ("lof_gemm_batched_f32", "lof_fwht_f32", "lof_fwht_round_f32", "lof_fwht_mx_round_f32"):
         getattr(lib, _n).restype = i32
     lib.lof_mx_encode_f32.argtypes = [vp, i64, i32, PC, PC, PP, PP, i32, PR, u64, vp, vp, vp]
     lib.lof_mx_encode_f32.restype = i32

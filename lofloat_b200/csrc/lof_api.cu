@@ -21,7 +21,7 @@
 namespace lof {
 cudaError_t launch_gemm_exact(int mode, const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
                               int accum_mant_bits, int len, int64_t kc, float alpha, float beta, const RngArgs& rng,
-                              cudaStream_t stream);
+                              cudaStream_t stream, int64_t batch = 1, int64_t stride_a = 0, int64_t stride_b = 0, int64_t stride_c = 0);
 cudaError_t launch_mx_tma(int mode, const float* in, float* out, int64_t n, const MxArgs& a, const RngArgs& rng,
                           const RngArgs& rng_scale, uint64_t first_index, const MxLaunchCfg& cfg, cudaStream_t stream,
                           int* launches, bool* handled);
@@ -553,6 +553,32 @@ int lof_mx_round_f32(const float* in, float* out, int64_t n, int block_size, con
                      const lof_rng_t* rng, uint64_t first_index, void* stream)
 {
     return mx_common(in, out, n, block_size, scale_fmt, elem_fmt, ps_scale, ps_elem, rng, first_index, stream);
+}
+
+int lof_gemm_batched_f32(const float* A, const float* B, float* C, int64_t batch, int64_t M, int64_t N, int64_t K,
+                         int64_t stride_a, int64_t stride_b, int64_t stride_c, int accum_mant_bits, const lof_projspec_t* ps,
+                         int64_t kc, float alpha, float beta, const lof_rng_t* rng, void* stream)
+{
+    if (batch < 0 || M < 0 || N < 0 || K < 0) return fail(LOF_ERR_INVALID_ARG, "negative GEMM dimension");
+    if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX) return fail(LOF_ERR_UNSUPPORTED, "GEMM dimension exceeds 2^31-1");
+    if (batch > 65535) return fail(LOF_ERR_UNSUPPORTED, "batched GEMM: at most 65535 matrices per call");
+    if (!ps) return fail(LOF_ERR_INVALID_ARG, "projspec is NULL");
+    const int mode = ps->rounding_mode;
+    if (mode < 0 || mode >= LOF_NUM_ROUNDING_MODES) return fail(LOF_ERR_INVALID_ARG, "unknown rounding mode");
+    if (accum_mant_bits > 23) return fail(LOF_ERR_INVALID_ARG, "accum_mant_bits > 23");
+    if (accum_mant_bits >= 0 && accum_mant_bits < 23 &&
+        (mode == LOF_StochasticRoundingA || mode == LOF_StochasticRoundingB || mode == LOF_StochasticRoundingC ||
+         mode == LOF_StochasticRoundingD) &&
+        (ps->stoch_length < 0 || ps->stoch_length > 23 - accum_mant_bits))
+        return fail(LOF_ERR_INVALID_ARG, "stochastic_rounding_bits must be in [0, 23 - accum_mant_bits]");
+    if (batch == 0 || M == 0 || N == 0) return LOF_OK;
+    if (!C || (K > 0 && (!A || !B))) return fail(LOF_ERR_INVALID_ARG, "null matrix pointer");
+    if (num_sms() <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    cudaError_t e = launch_gemm_exact(mode, A, B, C, M, N, K, accum_mant_bits, ps->stoch_length, kc, alpha, beta,
+                                      make_rng(rng, kStreamGemm), static_cast<cudaStream_t>(stream), batch, stride_a, stride_b, stride_c);
+    if (e != cudaSuccess) return cuda_fail(e, "lof_gemm_batched launch");
+    g_launches.fetch_add(1);
+    return LOF_OK;
 }
 
 int lof_gemm_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int accum_mant_bits,

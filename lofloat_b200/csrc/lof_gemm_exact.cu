@@ -29,8 +29,15 @@ __device__ __forceinline__ float accum_round(float t, int r, int len, uint32_t w
 template <int MODE>
 __global__ void __launch_bounds__(kGemmThreads)
 gemm_exact_kernel(const float* __restrict__ A, const float* __restrict__ B, float* C, int M, int N, int K,
-                  int r, int len, int kc, float alpha, float beta, bool custom, RngArgs rng)
+                  int r, int len, int kc, float alpha, float beta, bool custom, RngArgs rng,
+                  int64_t stride_a, int64_t stride_b, int64_t stride_c)
 {
+    // batched call (blockIdx.z = batch index): the (b, h) loop of LoFloat/layers.py:142-149 as one launch; the stochastic
+    // event index continues across the batch ((batch * M + i) * N + j) * K + k
+    A += (int64_t)blockIdx.z * stride_a;
+    B += (int64_t)blockIdx.z * stride_b;
+    C += (int64_t)blockIdx.z * stride_c;
+    const uint64_t rng_base = (uint64_t)blockIdx.z * (uint64_t)M * (uint64_t)N * (uint64_t)K;
     __shared__ float As[TK][TM + 4];
     __shared__ float Bs[TK][TN + 4];
 
@@ -88,7 +95,7 @@ gemm_exact_kernel(const float* __restrict__ A, const float* __restrict__ B, floa
                             uint32_t w = 0;
                             if constexpr (ModeTraits<MODE>::kUsesRng) {
                                 const uint64_t gi = (uint64_t)(m0 + ty * 4 + i), gj = (uint64_t)(n0 + tx * 4 + j);
-                                w = philox_word(rng, (gi * (uint64_t)N + gj) * (uint64_t)K + (uint64_t)(k0 + k));
+                                w = philox_word(rng, rng_base + (gi * (uint64_t)N + gj) * (uint64_t)K + (uint64_t)(k0 + k));
                             }
                             acc[i][j] = accum_round<MODE>(rto_fma(a4[i], b4[j], acc[i][j]), r, len, w);
                         } else {
@@ -145,15 +152,15 @@ gemm_exact_kernel(const float* __restrict__ A, const float* __restrict__ B, floa
 
 cudaError_t launch_gemm_exact(int mode, const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
                               int accum_mant_bits, int len, int64_t kc, float alpha, float beta, const RngArgs& rng,
-                              cudaStream_t stream)
+                              cudaStream_t stream, int64_t batch, int64_t stride_a, int64_t stride_b, int64_t stride_c)
 {
-    if (M <= 0 || N <= 0) return cudaSuccess;
+    if (M <= 0 || N <= 0 || batch <= 0) return cudaSuccess;
     const bool custom = accum_mant_bits >= 0;
     const int r = custom ? 23 - accum_mant_bits : 0;
     int kci = (kc <= 0 || kc > K) ? (int)(K > 0 ? K : 1) : (int)kc;
-    dim3 grid((unsigned)((N + TN - 1) / TN), (unsigned)((M + TM - 1) / TM));
+    dim3 grid((unsigned)((N + TN - 1) / TN), (unsigned)((M + TM - 1) / TM), (unsigned)batch);
     switch (mode) {
-#define LOF_CASE(Mo) case Mo: gemm_exact_kernel<Mo><<<grid, kGemmThreads, 0, stream>>>(A, B, C, (int)M, (int)N, (int)K, r, len, kci, alpha, beta, custom, rng); break;
+#define LOF_CASE(Mo) case Mo: gemm_exact_kernel<Mo><<<grid, kGemmThreads, 0, stream>>>(A, B, C, (int)M, (int)N, (int)K, r, len, kci, alpha, beta, custom, rng, stride_a, stride_b, stride_c); break;
         LOF_CASE(LOF_RoundToNearestEven) LOF_CASE(LOF_RoundTowardsZero) LOF_CASE(LOF_RoundAwayFromZero)
         LOF_CASE(LOF_StochasticRoundingA) LOF_CASE(LOF_RoundToNearestOdd) LOF_CASE(LOF_RoundDown)
         LOF_CASE(LOF_RoundUp) LOF_CASE(LOF_RoundTiesToAway) LOF_CASE(LOF_StochasticRoundingB)

@@ -464,6 +464,37 @@ def virtual_round_strict(input: torch.Tensor, params: FloatFormatDescriptor, rou
     return out
 
 
+def lof_gemm_batched(A: torch.Tensor, B: torch.Tensor, accum_mant_bits: int, round_mode=RoundingMode.RoundToNearestEven,
+                     stochastic_rounding_bits: int = 0, scale_a: float = 1.0, scale_b: float = 1.0, *, kc=None, rng=None) -> torch.Tensor:
+    """(..., M, K) x (..., K, N) -> (..., M, N) with LoFloat accumulation, the `_lof_gemm_2d` of LoFloat/layers.py:121-150,
+    as ONE launch over the flattened batch instead of a Python loop; every slice equals lof_gemm on that slice."""
+    if A.dim() < 2 or B.dim() < 2 or A.shape[:-2] != B.shape[:-2] or A.shape[-1] != B.shape[-2]:
+        raise RuntimeError(f"lof_gemm_batched: incompatible shapes {tuple(A.shape)} x {tuple(B.shape)}")
+    if A.dtype != torch.float32 or B.dtype != torch.float32:
+        raise RuntimeError("LoF_gemm: only float32 inputs are supported")
+    if not (A.is_cuda and B.is_cuda):
+        raise RuntimeError("LoF_gemm requires CUDA tensors")
+    L = _lib.lib()
+    mode = RoundingMode(int(round_mode))
+    ps = CProjSpec(int(mode), 0, int(stochastic_rounding_bits))
+    denom = float(scale_a) * float(scale_b)
+    alpha = 1.0 if denom == 0.0 else 1.0 / denom
+    batch_shape = A.shape[:-2]
+    M, K, N = A.shape[-2], A.shape[-1], B.shape[-1]
+    A_f, B_f = A.reshape(-1, M, K).contiguous(), B.reshape(-1, K, N).contiguous()
+    nb = A_f.shape[0]
+    out = torch.empty((nb, M, N), dtype=torch.float32, device=A.device)
+    r = _next_rng(mode in _STOCHASTIC, rng)
+    with torch.cuda.device(A.device):
+        for b0 in range(0, nb, 65535):                       # grid.z limit
+            cnt = min(65535, nb - b0)
+            st = L.lof_gemm_batched_f32(A_f[b0].data_ptr(), B_f[b0].data_ptr(), out[b0].data_ptr(), cnt, M, N, K, M * K, K * N, M * N,
+                                        int(accum_mant_bits), C.byref(ps), int(_gemm_kc if kc is None else kc), alpha, 0.0, C.byref(r),
+                                        _stream_ptr(A_f))
+            _lib.check(st, "LoF_gemm (batched)")
+    return out.reshape(*batch_shape, M, N)
+
+
 def fwht(input: torch.Tensor, block_size=None, *, params: FloatFormatDescriptor | None = None, round_mode=RoundingMode.RoundToNearestEven,
          stoch_len: int = 0, scale: float = 1.0, mx_block_size: int | None = None, scale_format: FloatFormatDescriptor | None = None,
          scale_round_mode=RoundingMode.RoundToNearestEven, rng=None, first_index: int = 0) -> torch.Tensor:

@@ -1071,3 +1071,20 @@ def test_fused_hadamard_rounding(lof, cuda_dev):
         lof.fwht(big, 48)
     with pytest.raises(lof.LoFloatError):
         lof.fwht(torch.randn(8, 4096, device=cuda_dev), 2048)                               # > 1024: not handled by the fused kernel
+
+
+def test_batched_gemm_equals_per_slice_calls(lof, cuda_dev):
+    """Row f-3: lof_gemm_batched (one launch, grid.z = batch) == lof_gemm on every (batch, head) slice, which is what the
+    reference's Python loop computes (layers.py:142-149), bit for bit; attention-like shapes, ragged sizes, the BLIS-panel
+    and single-panel accumulation modes, a non-RNE mode."""
+    g = torch.Generator(device=cuda_dev).manual_seed(12)
+    for (bh, M, K, N) in (((2, 3), 64, 96, 64), ((5,), 100, 300, 36), ((4, 2), 17, 33, 129)):
+        A = torch.rand(*bh, M, K, device=cuda_dev, generator=g) * 2 - 1
+        B = torch.rand(*bh, K, N, device=cuda_dev, generator=g) * 2 - 1
+        for mant, mode, kc in ((10, L.RNE, None), (7, L.RTZ, 0), (4, L.RTO, 64)):
+            got = lof.lof_gemm_batched(A, B, mant, mode, kc=kc)
+            Af, Bf = A.reshape(-1, M, K), B.reshape(-1, K, N)
+            want = torch.stack([lof.lof_gemm(Af[i], Bf[i], mant, mode, kc=kc) for i in range(Af.shape[0])]).reshape(*bh, M, N)
+            assert torch.equal(got, want), (bh, M, K, N, mant)
+    A0, B0 = _np(A.reshape(-1, M, K)[3]), _np(B.reshape(-1, K, N)[3])
+    assert L.bits_equal(_np(lof.lof_gemm_batched(A, B, 10).reshape(-1, M, N)[3]), L.o_gemm(A0, B0, 10, L.RNE, kc=256))
