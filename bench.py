@@ -416,6 +416,29 @@ def side_measurements(torch, lib, _lib, dev, x, y, stream):
                 out[f"pack_{what}_{fname}_2^28"] = {"GBps": gbps, "frac_of_hbm_peak": gbps / peak,
                                                     "algorithmic_bytes_per_element": 4.0 + d.total_bits / 8.0}
             del packed, back
+        # strict typed-semantics rounding (row f-2), fused Hadamard (+ MX) (row f-3), MX storage (row f-1): 2^28 elements
+        from lofloat_b200 import formats as _f
+        d8 = lof.FloatFormatDescriptor(8, 0, 127, lof.InfBehavior.Saturating, lof.NaNBehavior._3109, lof.Signedness.Unsigned,
+                                       _f._P3109Inf(8, False, True), _f._BitPatternNaN(0xFF))
+        e4 = lof.create_p3109_params(8, 4, bias=7)
+        x2 = x.view(16384, 16384)
+        sc, el = lof.mx_encode(x2, 32, e4, d8)
+        extra = (("strict_round_e4m3_RNE", lambda: lof.virtual_round_strict(x, e4), 8.0),
+                 ("fwht128", lambda: lof.fwht(x2, 128), 8.0),
+                 ("fwht128_fused_mx_round_mxfp8", lambda: lof.fwht(x2, 128, params=e4, mx_block_size=32, scale_format=lof.create_e8m0_params()), 8.0),
+                 ("mx_encode_mxfp8_scale_bytes_plus_packed", lambda: lof.mx_encode(x2, 32, e4, d8), 4.0 + 1.0 + 1.0 / 32),
+                 ("mx_decode_mxfp8", lambda: lof.mx_decode(sc, el, x.numel(), 32, e4, d8), 4.0 + 1.0 + 1.0 / 32))
+        for label, fn, bpe in extra:
+            fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            gbps = bpe * x.numel() * 5 / (a.elapsed_time(b) * 1e-3) / 1e9
+            out[f"{label}_2^28"] = {"GBps": gbps, "frac_of_hbm_peak": gbps / peak, "algorithmic_bytes_per_element": bpe}
+        del sc, el
     except Exception as exc:
         out["lof_gemm_tc_error"] = str(exc)
     return out

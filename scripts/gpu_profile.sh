@@ -42,6 +42,9 @@ for t in $TARGETS; do
     gemm_tc_hw)
       timeout 600 $NCU_FULL -k regex:gemm_tc_kernel -s 2 -c 1 -o $OUT/gemm_tc_hw python scripts/prof_target.py gemm_tc 8192 hw > $OUT/gemm_tc_hw.log 2>&1
       echo "gemm_tc_hw exit $?"; export_rep gemm_tc_hw ;;
+    newops)
+      timeout 900 $NCU_FULL -k regex:"round_strict_kernel|encode_kernel|decode_kernel|fwht_kernel|round_vec_kernel" -s 8 -c 8 -o $OUT/newops python scripts/prof_target.py newops > $OUT/newops.log 2>&1
+      echo "newops exit $?"; export_rep newops ;;
     mxenc)
       timeout 600 $NCU_FULL -k regex:"mx_encode_kernel" -s 1 -c 1 -o $OUT/mxenc python scripts/prof_target.py mxenc > $OUT/mxenc.log 2>&1
       echo "mxenc exit $?"; export_rep mxenc ;;

@@ -43,6 +43,24 @@ def main():
         x *= torch.exp2(torch.randint(-8, 9, (16384, 1), device=dev, generator=g).float())
         for _ in range(4):
             y = lof.virtual_mx_round(x, 32, f, lof.create_e8m0_params())
+    elif what == "newops":
+        from lofloat_b200 import formats
+        e4m3, e8m0 = fmt("e4m3"), lof.create_e8m0_params()
+        d8 = lof.FloatFormatDescriptor(8, 0, 127, lof.InfBehavior.Saturating, lof.NaNBehavior._3109, lof.Signedness.Unsigned,
+                                       formats._P3109Inf(8, False, True), formats._BitPatternNaN(0xFF))
+        x = torch.randn(16384, 16384, device=dev, generator=g)
+        x *= torch.exp2(torch.randint(-8, 9, (16384, 1), device=dev, generator=g).float())
+        xb = x.to(torch.bfloat16)
+        for _ in range(2):
+            y = lof.virtual_round_strict(x, e4m3)                                   # round_strict_kernel
+            p = lof.lof_encode(x, e4m3)                                             # encode_kernel
+            y = lof.lof_decode(p, x.numel(), e4m3)                                  # decode_kernel
+            y = lof.fwht(x, 128)                                                    # fwht_kernel (plain)
+            y = lof.fwht(x, 128, params=e4m3, mx_block_size=32, scale_format=e8m0)  # fwht_kernel (fused MX)
+            sc, el = lof.mx_encode(x, 32, e4m3, d8)                                 # mx_encode_kernel
+            y = lof.mx_decode(sc, el, x.numel(), 32, e4m3, d8)                      # mx_decode_kernel
+            yb = lof.virtual_round(xb, e4m3)                                        # round_vec_kernel<bf16>
+            y = yb.float()
     elif what == "mxenc":
         from lofloat_b200 import formats
         d8 = lof.FloatFormatDescriptor(8, 0, 127, lof.InfBehavior.Saturating, lof.NaNBehavior._3109, lof.Signedness.Unsigned,
