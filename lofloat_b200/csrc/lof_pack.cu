@@ -541,6 +541,96 @@ mx_encode_kernel(const float4* __restrict__ in, int64_t nvec, MxArgs a, MxScaleQ
     }
 }
 
+// Second-generation MX encode for the eligible bulk (fast element path, block sizes 16 / 32 / 64): ncu of the kernel above
+// (profiles/r01j) shows ~300 warp instructions per 128 elements, a third of them the block-scale path, which only the
+// first lane of each block executes but the whole warp pays for.  Here a warp step covers exactly 32 MX blocks
+// (LANES = BS / 4 vectors per lane); the 32 block maxima are transposed onto the 32 lanes by shuffles, EVERY lane rounds
+// one scale (no divergence, 32 scale bytes stored as one coalesced row), and scale / reciprocal travel back by shuffle.
+template <int MODE, int LANES>
+__global__ void __launch_bounds__(kPackThreads)
+mx_encode_fast_kernel(const float4* __restrict__ in, int64_t nvec, MxArgs a, MxScaleQuick sq, CodecPlan scale_codec, CodecPlan elem_codec,
+                      RngArgs rng_scale, uint64_t first_index, uint8_t* __restrict__ scales, uint8_t* __restrict__ elems)
+{
+    constexpr int V = LANES;                         // vectors (rows of 128 floats) per lane and warp step
+    constexpr int BPR = 32 / LANES;                  // blocks per row
+    constexpr int kWarps = kPackThreads / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t nsteps = (nvec + 32 * V - 1) / (32 * V);
+    const int64_t nblocks = (nvec * 4) / a.block_size;
+    const int log2_bs = 31 - __clz(a.block_size);
+    const FastConsts fk(elem_codec);
+    for (int64_t step = (int64_t)blockIdx.x * kWarps + warp; step < nsteps; step += (int64_t)gridDim.x * kWarps) {
+        const int64_t v0 = step * (32 * V) + lane;
+        float4 x[V];
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            const int64_t v = v0 + u * 32;
+            x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (v < nvec) x[u] = __ldcs(in + v);
+        }
+        // block maxima (all LANES lanes of a block end up with it), then lane j takes block j = (row j / BPR, group j % BPR)
+        float mine = 0.0f;
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            float m = fmaxf(fmaxf(fabsf(x[u].x), fabsf(x[u].y)), fmaxf(fabsf(x[u].z), fabsf(x[u].w)));
+#pragma unroll
+            for (int o = LANES / 2; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+            const float t = __shfl_sync(0xFFFFFFFFu, m, (lane % BPR) * LANES);
+            if (lane / BPR == u) mine = t;
+        }
+        const int64_t gblock_local = step * 32 + lane;
+        const uint64_t gblock = (first_index >> log2_bs) + (uint64_t)gblock_local;
+        const float scale = mx_scale_quick(mine, a, sq, rng_scale, gblock);
+        const uint32_t sb = __float_as_uint(scale);
+        // reciprocal for the consumers: exact 2^-k when the scale is a normal power of two, 0 = "use the division"
+        const bool pow2 = (sb & 0x807FFFFFu) == 0u && (sb - 0x00800000u) < 0x7E800000u;
+        const float recip = pow2 ? __uint_as_float(0x7F000000u - sb) : 0.0f;
+        if (gblock_local < nblocks) {
+            const int code = (int)(sb >> 23) + scale_codec.exp_offset;
+            uint32_t byte;
+            if (scale_codec.mant == 0 && !scale_codec.to_signed && pow2 && (sb >> 23) <= 254u && code >= 1 && code <= (int)scale_codec.max_finite_rep)
+                byte = (uint32_t)code;
+            else
+                byte = float_to_rep<LOF_RoundTowardsZero>(sb, scale_codec, 0u);
+            scales[gblock_local] = (uint8_t)byte;
+        }
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            const int owner = u * BPR + lane / LANES;
+            const float sc = __shfl_sync(0xFFFFFFFFu, scale, owner), rc = __shfl_sync(0xFFFFFFFFu, recip, owner);
+            const int64_t v = v0 + u * 32;
+            if (v >= nvec) continue;
+            uint32_t r[4] = {0u, 0u, 0u, 0u};
+            if (sc > 0.0f) {
+                const float xs[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+                float y[4];
+                if (rc != 0.0f) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) y[e] = __fmul_rn(xs[e], rc);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) y[e] = __fdiv_rn(xs[e], sc);
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) r[e] = float_to_rep_fast<MODE>(__float_as_uint(y[e]), fk) & elem_codec.rep_mask;
+            }
+            if (elem_codec.reverse && elem_codec.gc > 1) {
+                if (elem_codec.gc == 2) { uint32_t t = r[0]; r[0] = r[1]; r[1] = t; t = r[2]; r[2] = r[3]; r[3] = t; }
+                else { uint32_t t = r[0]; r[0] = r[3]; r[3] = t; t = r[1]; r[1] = r[2]; r[2] = t; }
+            }
+            if (elem_codec.n == 8) {
+                __stcs(reinterpret_cast<uint32_t*>(elems) + v, r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24));
+            } else if (elem_codec.n == 4) {
+                __stcs(reinterpret_cast<uint16_t*>(elems) + v, (uint16_t)(r[0] | (r[1] << 4) | (r[2] << 8) | (r[3] << 12)));
+            } else {
+                const uint32_t g = r[0] | (r[1] << 6) | (r[2] << 12) | (r[3] << 18);
+                uint8_t* d = elems + v * 3;
+                d[0] = (uint8_t)g; d[1] = (uint8_t)(g >> 8); d[2] = (uint8_t)(g >> 16);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kPackThreads)
 mx_decode_kernel(const uint8_t* __restrict__ scales, const uint8_t* __restrict__ elems, float4* __restrict__ out, int64_t nvec,
                  int block_size, CodecPlan scale_codec, CodecPlan elem_codec)
@@ -651,6 +741,22 @@ cudaError_t launch_mx_encode(int mode, const float* in, int64_t n, const MxArgs&
     const int64_t want = (nvec + kPackThreads - 1) / kPackThreads, cap = (int64_t)num_sms * 8;
     const unsigned grid = (unsigned)(want < 1 ? 1 : want < cap ? want : cap);
     const float4* vin = reinterpret_cast<const float4*>(in);
+    // eligible bulk: fast element path, deterministic scale mode, 32 whole blocks per warp step
+    if (fast && !mode_uses_rng(a.scale_mode) && (a.block_size == 16 || a.block_size == 32 || a.block_size == 64)) {
+        constexpr int kWarps = kPackThreads / 32;
+        const int lanes = a.block_size / 4;
+        const int64_t nsteps = (nvec + 32 * lanes - 1) / (32 * lanes);
+        const int64_t want2 = (nsteps + kWarps - 1) / kWarps;
+        const unsigned grid2 = (unsigned)(want2 < 1 ? 1 : want2 < cap ? want2 : cap);
+#define LOF_CASE2(M, L) mx_encode_fast_kernel<M, L><<<grid2, kPackThreads, 0, stream>>>(vin, nvec, a, sq, scale_codec, elem_codec, rng_scale, first_index, scales, elems)
+#define LOF_CASE(M) case M: if (lanes == 4) LOF_CASE2(M, 4); else if (lanes == 8) LOF_CASE2(M, 8); else LOF_CASE2(M, 16); return cudaGetLastError();
+        switch (mode) {
+            LOF_CASE(LOF_RoundToNearestEven) LOF_CASE(LOF_RoundTowardsZero) LOF_CASE(LOF_RoundAwayFromZero) LOF_CASE(LOF_RoundToOdd)
+        default: break;
+        }
+#undef LOF_CASE
+#undef LOF_CASE2
+    }
     if (fast) {
         switch (mode) {
 #define LOF_CASE(M) case M: mx_encode_kernel<M, true><<<grid, kPackThreads, 0, stream>>>(vin, nvec, a, sq, scale_codec, elem_codec, rng, rng_scale, first_index, scales, elems); return cudaGetLastError();
