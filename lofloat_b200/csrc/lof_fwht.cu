@@ -110,13 +110,37 @@ fwht_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t nro
                 for (int off = group >> 1; off > 0; off >>= 1) t = fmaxf(t, __shfl_xor_sync(0xFFFFFFFFu, t, off));
                 m[r] = t;
             }
+            // scales: the ROWS * (32 / group) block maxima are transposed onto the lanes so that every lane rounds ONE scale
+            // (no divergent per-block path); when that is more than 32 blocks the first lane of each block does it
+            const int bpr = 32 / group;                               // blocks per row
+            const bool transposed = ROWS * bpr <= 32;
+            float scales_r[ROWS];
+            if (transposed) {
+                float mine = 0.0f;
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+                    const float t = __shfl_sync(0xFFFFFFFFu, m[r], (lane % bpr) * group);
+                    if (lane / bpr == r) mine = t;
+                }
+                const uint64_t gb0 = (first_index + (uint64_t)row0 * 128u) >> log2_mx;
+                float sc = 0.0f;
+                if (lane < ROWS * bpr) sc = mx_scale_quick(mine, a.mx, a.sq, rng_scale, gb0 + (uint64_t)lane);
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) scales_r[r] = __shfl_sync(0xFFFFFFFFu, sc, r * bpr + lane / group);
+            } else {
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+                    const uint64_t g0 = first_index + (uint64_t)(row0 + r) * 128u + (uint64_t)lane * 4u;
+                    float sc = 0.0f;
+                    if ((lane & (group - 1)) == 0) sc = mx_scale_quick(m[r], a.mx, a.sq, rng_scale, g0 >> log2_mx);
+                    scales_r[r] = __shfl_sync(0xFFFFFFFFu, sc, lane & ~(group - 1));
+                }
+            }
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) {
                 if (row0 + r >= nrows) continue;
                 const uint64_t g0 = first_index + (uint64_t)(row0 + r) * 128u + (uint64_t)lane * 4u;
-                float scale = 0.0f;                                   // computed by the block's first lane, then broadcast
-                if ((lane & (group - 1)) == 0) scale = mx_scale_quick(m[r], a.mx, a.sq, rng_scale, g0 >> log2_mx);
-                scale = __shfl_sync(0xFFFFFFFFu, scale, lane & ~(group - 1));
+                const float scale = scales_r[r];
                 uint4 w = make_uint4(0, 0, 0, 0);
                 if constexpr (ModeTraits<MODE>::kUsesRng) w = philox_group4(rng, g0 >> 2);
                 float4 o;
