@@ -47,8 +47,8 @@ thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launches{0};
 
 struct Options {
-    std::atomic<int64_t> round_unroll{4};
-    std::atomic<int64_t> round_ctas_per_sm{8};
+    std::atomic<int64_t> round_unroll{0};        // 0 = auto (B200 sweep, scripts/round_tune.py): 8 for deterministic modes, 4 for stochastic ones
+    std::atomic<int64_t> round_ctas_per_sm{0};   // 0 = auto: 8 CTAs per SM, 4 for the stochastic modes
     std::atomic<int64_t> mx_variant{0};
     std::atomic<int64_t> mx_ctas_per_sm{8};
     std::atomic<int64_t> host_chunk_bytes{32ll << 20};
@@ -220,11 +220,14 @@ RngArgs make_rng(const lof_rng_t* rng, uint32_t stream_const, int mode = LOF_Tru
     return r;
 }
 
-RoundLaunchCfg round_cfg()
+RoundLaunchCfg round_cfg(int mode = LOF_RoundToNearestEven, bool checked_kind = false)
 {
     RoundLaunchCfg c;
     c.unroll = (int)g_opt.round_unroll.load();
     c.ctas_per_sm = (int)g_opt.round_ctas_per_sm.load();
+    const bool rng_mode = mode_uses_rng(mode);      // the shared-Philox-block tile layout needs 4 vectors per thread
+    if (c.unroll == 0) c.unroll = (rng_mode || checked_kind) ? 4 : 8;     // the checked kinds (wide targets) carry more live registers
+    if (c.ctas_per_sm == 0) c.ctas_per_sm = rng_mode ? 4 : 8;
     c.num_sms = num_sms();
     return c;
 }
@@ -290,7 +293,7 @@ int round_common(bool params, const void* in, void* out, int64_t n, int dtype, c
     }
     if (n == 0) return LOF_OK;
     if (!in || !out) return fail(LOF_ERR_INVALID_ARG, "null tensor pointer");
-    const RoundLaunchCfg cfg = round_cfg();
+    const RoundLaunchCfg cfg = round_cfg(mode, kind == kKindFastSatChk || kind == kKindFastExtChk || kind == kKindMagicSatChk || kind == kKindMagicExtChk);
     if (cfg.num_sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
     const RngArgs ra = make_rng(rng, kStreamElem, mode, ps->stoch_length);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -510,8 +513,8 @@ int lof_set_option(const char* key, int64_t value)
 {
     if (!key) return fail(LOF_ERR_INVALID_ARG, "option key is NULL");
     const std::string k(key);
-    if (k == "round.unroll") { if (value != 1 && value != 2 && value != 4 && value != 8) return fail(LOF_ERR_INVALID_ARG, "round.unroll must be 1/2/4/8"); g_opt.round_unroll = value; }
-    else if (k == "round.ctas_per_sm") { if (value < 1 || value > 64) return fail(LOF_ERR_INVALID_ARG, "round.ctas_per_sm out of range"); g_opt.round_ctas_per_sm = value; }
+    if (k == "round.unroll") { if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return fail(LOF_ERR_INVALID_ARG, "round.unroll must be 0 (auto) or 1/2/4/8"); g_opt.round_unroll = value; }
+    else if (k == "round.ctas_per_sm") { if (value < 0 || value > 64) return fail(LOF_ERR_INVALID_ARG, "round.ctas_per_sm out of range"); g_opt.round_ctas_per_sm = value; }
     else if (k == "mx.variant") { if (value < 0 || value > 2) return fail(LOF_ERR_INVALID_ARG, "mx.variant must be 0, 1 or 2"); g_opt.mx_variant = value; }
     else if (k == "mx.ctas_per_sm") { if (value < 1 || value > 64) return fail(LOF_ERR_INVALID_ARG, "mx.ctas_per_sm out of range"); g_opt.mx_ctas_per_sm = value; }
     else if (k == "round.fast") { if (value < 0 || value > 2) return fail(LOF_ERR_INVALID_ARG, "round.fast must be 0, 1 or 2"); g_opt.round_fast = value; }

@@ -196,8 +196,8 @@ def test_round_unroll_and_grid_variants(lof, cuda_dev, xs):
                 _lib.set_option("round.ctas_per_sm", ctas)
                 assert L.bits_equal(_np(lof.virtual_round(xt, _desc(lof, f))), want), (unroll, ctas)
     finally:
-        _lib.set_option("round.unroll", 4)
-        _lib.set_option("round.ctas_per_sm", 8)
+        _lib.set_option("round.unroll", 0)
+        _lib.set_option("round.ctas_per_sm", 0)
 
 
 def test_stochastic_statistics_on_device(lof, cuda_dev):
