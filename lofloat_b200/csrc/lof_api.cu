@@ -47,10 +47,13 @@ thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launches{0};
 
 struct Options {
-    std::atomic<int64_t> round_unroll{0};        // 0 = auto (B200 sweep, scripts/round_tune.py): 8 for deterministic modes, 4 for stochastic ones
-    std::atomic<int64_t> round_ctas_per_sm{0};   // 0 = auto: 8 CTAs per SM, 4 for the stochastic modes
+    // B200 sweeps (scripts/round_tune.py, scripts/geom_tune2.py): the streaming kernels peak with ~48 KB of loads in flight per
+    // SM -- 3 resident CTAs x 256 threads x 4 x 16 B -- (6.1-6.3 TB/s); more residency costs 5-10 % (DRAM read/write turnarounds)
+    std::atomic<int64_t> round_unroll{0};        // 0 = auto: 4 vectors in flight per thread
+    std::atomic<int64_t> round_ctas_per_sm{0};   // 0 = auto: 3 CTAs per SM
     std::atomic<int64_t> mx_variant{0};
-    std::atomic<int64_t> mx_ctas_per_sm{8};
+    std::atomic<int64_t> mx_ctas_per_sm{3};
+    std::atomic<int64_t> stream_ctas_per_sm{8};  // codec / strict rounding / MX storage / fused Hadamard kernels: ALU-heavier, they want full residency (scripts/stream_tune.py)
     std::atomic<int64_t> host_chunk_bytes{32ll << 20};
     std::atomic<int64_t> pack_fast{1};           // storage codec: 0 = exact integer routine only, 1 = magic-add fast path where eligible
     std::atomic<int64_t> round_fast{2};          // 0: exact kernels; 1: branch-free fast path; 2: + magic-add path (default)
@@ -226,8 +229,9 @@ RoundLaunchCfg round_cfg(int mode = LOF_RoundToNearestEven, bool checked_kind = 
     c.unroll = (int)g_opt.round_unroll.load();
     c.ctas_per_sm = (int)g_opt.round_ctas_per_sm.load();
     const bool rng_mode = mode_uses_rng(mode);      // the shared-Philox-block tile layout needs 4 vectors per thread
-    if (c.unroll == 0) c.unroll = (rng_mode || checked_kind) ? 4 : 8;     // the checked kinds (wide targets) carry more live registers
-    if (c.ctas_per_sm == 0) c.ctas_per_sm = rng_mode ? 4 : 8;
+    (void)rng_mode; (void)checked_kind;
+    if (c.unroll == 0) c.unroll = 4;
+    if (c.ctas_per_sm == 0) c.ctas_per_sm = 3;
     c.num_sms = num_sms();
     return c;
 }
@@ -518,6 +522,7 @@ int lof_set_option(const char* key, int64_t value)
     else if (k == "mx.variant") { if (value < 0 || value > 2) return fail(LOF_ERR_INVALID_ARG, "mx.variant must be 0, 1 or 2"); g_opt.mx_variant = value; }
     else if (k == "mx.ctas_per_sm") { if (value < 1 || value > 64) return fail(LOF_ERR_INVALID_ARG, "mx.ctas_per_sm out of range"); g_opt.mx_ctas_per_sm = value; }
     else if (k == "round.fast") { if (value < 0 || value > 2) return fail(LOF_ERR_INVALID_ARG, "round.fast must be 0, 1 or 2"); g_opt.round_fast = value; }
+    else if (k == "stream.ctas_per_sm") { if (value < 1 || value > 64) return fail(LOF_ERR_INVALID_ARG, "stream.ctas_per_sm out of range"); g_opt.stream_ctas_per_sm = value; }
     else if (k == "pack.fast") { if (value < 0 || value > 1) return fail(LOF_ERR_INVALID_ARG, "pack.fast must be 0 or 1"); g_opt.pack_fast = value; }
     else if (k == "host.chunk_bytes") { if (value < (1 << 16)) return fail(LOF_ERR_INVALID_ARG, "host.chunk_bytes too small"); g_opt.host_chunk_bytes = value; }
     else return fail(LOF_ERR_INVALID_ARG, "unknown option: " + k);
@@ -533,6 +538,7 @@ int lof_get_option(const char* key, int64_t* value)
     else if (k == "mx.variant") *value = g_opt.mx_variant;
     else if (k == "mx.ctas_per_sm") *value = g_opt.mx_ctas_per_sm;
     else if (k == "round.fast") *value = g_opt.round_fast;
+    else if (k == "stream.ctas_per_sm") *value = g_opt.stream_ctas_per_sm;
     else if (k == "pack.fast") *value = g_opt.pack_fast;
     else if (k == "host.chunk_bytes") *value = g_opt.host_chunk_bytes;
     else return fail(LOF_ERR_INVALID_ARG, "unknown option: " + k);
@@ -677,7 +683,7 @@ int lof_fwht_f32(const float* in, float* out, int64_t n, int block_size, void* s
     const int sms = num_sms();
     if (sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
     const RngArgs none = make_rng(nullptr, kStreamElem);
-    cudaError_t e = launch_fwht(0, 0, in, out, n, block_size, nullptr, 1.0f, nullptr, nullptr, nullptr, nullptr, none, none, 0, sms, static_cast<cudaStream_t>(stream));
+    cudaError_t e = launch_fwht(0, 0, in, out, n, block_size, nullptr, 1.0f, nullptr, nullptr, nullptr, nullptr, none, none, 0, sms * (int)g_opt.stream_ctas_per_sm.load(), static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "lof_fwht launch");
     g_launches.fetch_add(1);
     return LOF_OK;
@@ -700,7 +706,7 @@ int lof_fwht_round_f32(const float* in, float* out, int64_t n, int block_size, c
     const int sms = num_sms();
     if (sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
     const RngArgs ra = make_rng(rng, kStreamElem, mode, ps->stoch_length);
-    cudaError_t e = launch_fwht(1, mode, in, out, n, block_size, &plan, (float)scale, nullptr, nullptr, nullptr, nullptr, ra, ra, first_index, sms,
+    cudaError_t e = launch_fwht(1, mode, in, out, n, block_size, &plan, (float)scale, nullptr, nullptr, nullptr, nullptr, ra, ra, first_index, sms * (int)g_opt.stream_ctas_per_sm.load(),
                                 static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "lof_fwht_round launch");
     g_launches.fetch_add(1);
@@ -737,7 +743,7 @@ int lof_fwht_mx_round_f32(const float* in, float* out, int64_t n, int block_size
     const MagicPlan emg = make_magic_plan(a.elem, ps_elem->rounding_mode);
     const bool elem_fast = g_opt.round_fast.load() >= 2 && emg.valid && emg.limit == 0xFFFFFFFFu && !emg.check_denorm_in &&
                            scale_fmt->mantissa_bits == 0 && !mode_uses_rng(ps_elem->rounding_mode);
-    cudaError_t e = launch_fwht(2, ps_elem->rounding_mode, in, out, n, block_size, nullptr, 1.0f, &a, &smg, &sfp, elem_fast ? &emg : nullptr, re, rs, first_index, sms,
+    cudaError_t e = launch_fwht(2, ps_elem->rounding_mode, in, out, n, block_size, nullptr, 1.0f, &a, &smg, &sfp, elem_fast ? &emg : nullptr, re, rs, first_index, sms * (int)g_opt.stream_ctas_per_sm.load(),
                                 static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "lof_fwht_mx_round launch");
     g_launches.fetch_add(1);
@@ -832,7 +838,7 @@ int lof_encode_f32(const float* src, uint8_t* dst, int64_t count, const lof_code
     const int sms = num_sms();
     if (sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
     const RngArgs ra = make_rng(rng, kStreamElem, mode, ps->stoch_length);
-    cudaError_t e = launch_encode(mode, src, dst, count, lof_packed_size(p.n, (uint64_t)count), p, ra, first_index, sms,
+    cudaError_t e = launch_encode(mode, src, dst, count, lof_packed_size(p.n, (uint64_t)count), p, ra, first_index, sms * (int)g_opt.stream_ctas_per_sm.load(),
                                   static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "lof_encode launch");
     g_launches.fetch_add(1);
@@ -857,7 +863,7 @@ int lof_round_strict_f32(const float* in, float* out, int64_t n, const lof_codec
     const int sms = num_sms();
     if (sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
     const RngArgs ra = make_rng(rng, kStreamElem, mode, ps->stoch_length);
-    cudaError_t e = launch_round_strict(mode, in, out, n, p, ra, first_index, sms, static_cast<cudaStream_t>(stream));
+    cudaError_t e = launch_round_strict(mode, in, out, n, p, ra, first_index, sms * (int)g_opt.stream_ctas_per_sm.load(), static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "lof_round_strict launch");
     g_launches.fetch_add(1);
     return LOF_OK;
@@ -918,7 +924,7 @@ int lof_mx_encode_f32(const float* in, int64_t n, int block_size, const lof_code
     const int sms = num_sms();
     if (sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
     const RngArgs re = make_rng(rng, kStreamElem, ps_elem->rounding_mode, ps_elem->stoch_length), rs = make_rng(rng, kStreamScale);
-    cudaError_t e = launch_mx_encode(ps_elem->rounding_mode, in, n, a, cs, ce, re, rs, first_index, scales, elems, sms, fast,
+    cudaError_t e = launch_mx_encode(ps_elem->rounding_mode, in, n, a, cs, ce, re, rs, first_index, scales, elems, sms * (int)g_opt.stream_ctas_per_sm.load(), fast,
                                      make_magic_plan(a.scale, ps_scale->rounding_mode), make_fast_plan(a.scale, ps_scale->rounding_mode),
                                      static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "lof_mx_encode launch");
@@ -942,7 +948,7 @@ int lof_mx_decode_f32(const uint8_t* scales, const uint8_t* elems, float* out, i
         return fail(LOF_ERR_INVALID_ARG, "mx storage: `out` must be 16-byte and `elems` 4-byte aligned");
     const int sms = num_sms();
     if (sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
-    cudaError_t e = launch_mx_decode(scales, elems, out, n, block_size, cs, ce, sms, static_cast<cudaStream_t>(stream));
+    cudaError_t e = launch_mx_decode(scales, elems, out, n, block_size, cs, ce, sms * (int)g_opt.stream_ctas_per_sm.load(), static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "lof_mx_decode launch");
     g_launches.fetch_add(1);
     return LOF_OK;
@@ -958,7 +964,7 @@ int lof_decode_f32(const uint8_t* src, float* dst, int64_t count, const lof_code
     if (!src || !dst) return fail(LOF_ERR_INVALID_ARG, "null tensor pointer");
     const int sms = num_sms();
     if (sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
-    cudaError_t e = launch_decode(src, dst, count, lof_packed_size(p.n, (uint64_t)count), p, sms, static_cast<cudaStream_t>(stream));
+    cudaError_t e = launch_decode(src, dst, count, lof_packed_size(p.n, (uint64_t)count), p, sms * (int)g_opt.stream_ctas_per_sm.load(), static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "lof_decode launch");
     g_launches.fetch_add(1);
     return LOF_OK;

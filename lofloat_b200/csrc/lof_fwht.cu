@@ -195,7 +195,7 @@ cudaError_t launch_rows(int rows_per_block, const float* in, float* out, int64_t
     constexpr int kWarps = kFwhtThreads / 32;
     auto grid_for = [&](int rows) {
         const int64_t nsteps = (nrows + rows - 1) / rows;
-        const int64_t want = (nsteps + kWarps - 1) / kWarps, cap = (int64_t)num_sms * 8;
+        const int64_t want = (nsteps + kWarps - 1) / kWarps, cap = (int64_t)num_sms /* = SMs x resident CTAs per SM, chosen by the caller */;
         return (unsigned)(want < 1 ? 1 : want < cap ? want : cap);
     };
     switch (rows_per_block) {

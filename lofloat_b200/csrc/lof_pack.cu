@@ -667,7 +667,7 @@ mx_decode_kernel(const uint8_t* __restrict__ scales, const uint8_t* __restrict__
 unsigned pack_grid(int64_t count, int num_sms)
 {
     const int64_t ntiles = (count + kPackTile - 1) / kPackTile;
-    const int64_t cap = (int64_t)num_sms * 8;
+    const int64_t cap = (int64_t)num_sms /* = SMs x resident CTAs per SM, chosen by the caller */;
     return (unsigned)(ntiles < 1 ? 1 : ntiles < cap ? ntiles : cap);
 }
 
@@ -738,7 +738,7 @@ cudaError_t launch_mx_encode(int mode, const float* in, int64_t n, const MxArgs&
     sq.quick_mode_ok = a.scale_mode == LOF_RoundToNearestEven || a.scale_mode == LOF_RoundTowardsZero || a.scale_mode == LOF_RoundAwayFromZero ||
                        a.scale_mode == LOF_RoundUp || a.scale_mode == LOF_RoundDown || a.scale_mode == LOF_RoundToOdd;
     const int64_t nvec = n / 4;
-    const int64_t want = (nvec + kPackThreads - 1) / kPackThreads, cap = (int64_t)num_sms * 8;
+    const int64_t want = (nvec + kPackThreads - 1) / kPackThreads, cap = (int64_t)num_sms /* = SMs x resident CTAs per SM, chosen by the caller */;
     const unsigned grid = (unsigned)(want < 1 ? 1 : want < cap ? want : cap);
     const float4* vin = reinterpret_cast<const float4*>(in);
     // eligible bulk: fast element path, deterministic scale mode, 32 whole blocks per warp step
@@ -783,7 +783,7 @@ cudaError_t launch_mx_decode(const uint8_t* scales, const uint8_t* elems, float*
                              const CodecPlan& elem_codec, int num_sms, cudaStream_t stream)
 {
     const int64_t nvec = n / 4;
-    const int64_t want = (nvec + kPackThreads - 1) / kPackThreads, cap = (int64_t)num_sms * 8;
+    const int64_t want = (nvec + kPackThreads - 1) / kPackThreads, cap = (int64_t)num_sms /* = SMs x resident CTAs per SM, chosen by the caller */;
     const unsigned grid = (unsigned)(want < 1 ? 1 : want < cap ? want : cap);
     mx_decode_kernel<<<grid, kPackThreads, 0, stream>>>(scales, elems, reinterpret_cast<float4*>(out), nvec, block_size, scale_codec, elem_codec);
     return cudaGetLastError();
