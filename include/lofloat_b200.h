@@ -169,6 +169,39 @@ LOF_API int lof_gemm_batched_f32(const float* A, const float* B, float* C, int64
                                  int64_t stride_a, int64_t stride_b, int64_t stride_c, int accum_mant_bits,
                                  const lof_projspec_t* ps, int64_t kc, float alpha, float beta, const lof_rng_t* rng, void* stream);
 
+/* x(M x K) times an nn.Linear weight stored (N x K) row-major, plus an optional (already quantised) bias of N values
+ * added to alpha * acc in plain fp32: `_lof_linear` of LoFloat/layers.py:152-168 without the `weight.t().contiguous()`
+ * copy and without the extra pass of `out + b_q` (layers.py:392-398).  Bit-identical to lof_gemm_f32 on the transposed
+ * weight followed by the addition. */
+LOF_API int lof_linear_f32(const float* x, const float* weight, const float* bias, float* out, int64_t M, int64_t N, int64_t K,
+                           int accum_mant_bits, const lof_projspec_t* ps, int64_t kc, float alpha, const lof_rng_t* rng, void* stream);
+
+/* Conv2d forward as an implicit GEMM with LoFloat accumulation (no im2col matrix in HBM): input NCHW, weight OIHW
+ * (C_out, C_in / groups, R, S), out NCHW (batch, C_out, P, Q), all fp32 contiguous.  Every output element is the chain
+ *     acc = virtual_round(round_to_odd_fma(w[co, k], x_col[k, (p, q)], acc), accum_mant_bits, *ps)   for k ascending
+ * over the reduction axis in `k_order`:
+ *   LOF_CONV_K_CRS  k = (c, r, s): F.unfold order == LoF_Conv2d(backend="im2col"), LoFloat/layers.py:710-745 (one
+ *                   lof_gemm(w_col, x_col[b]) per image and group); kc = 256 matches that path on the reference CPU GEMM
+ *   LOF_CONV_K_RSC  k = (r, s, c): the NHWC / KRSC order of lo_float::LoF_conv2d, src/Lof_kernel.cu:156-228
+ *                   (CUTLASS implicit GEMM, one accumulator over all of K: kc <= 0), which this entry point replaces
+ * Zero padding contributes fma(w, 0, acc) = acc, already on the accumulator grid.  out = alpha * acc (+ bias[co]),
+ * alpha = 1 / (weight_scale * input_scale) (Lof_kernel.cu:209-212); `bias` may be NULL. */
+enum { LOF_CONV_K_CRS = 0, LOF_CONV_K_RSC = 1 };
+typedef struct lof_conv2d_t {
+    int64_t batch, c_in, h, w;            /* input  (batch, c_in, h, w) */
+    int64_t c_out, r, s;                  /* weight (c_out, c_in / groups, r, s) */
+    int64_t pad_h, pad_w, stride_h, stride_w, dilation_h, dilation_w, groups;
+    int32_t k_order;
+} lof_conv2d_t;
+LOF_API int lof_conv2d_f32(const float* input, const float* weight, const float* bias, float* out, const lof_conv2d_t* geometry,
+                           int accum_mant_bits, const lof_projspec_t* ps, int64_t kc, float alpha, const lof_rng_t* rng, void* stream);
+/* floor((in + 2 pad - dilation (kernel - 1) - 1) / stride) + 1, 0 if the window does not fit (Lof_kernel.cu:194-195) */
+LOF_API int lof_conv2d_out_size(int64_t in, int64_t kernel, int64_t pad, int64_t stride, int64_t dilation, int64_t* out);
+
+/* Device self-test of the exact GEMM's float-domain RNE step ((t + K) - K, lof_gemm_exact.cu): every fp32 pattern x every
+ * accumulator width against the integer routine; adds the number of mismatches to *dev_mismatches (device memory, uint64). */
+LOF_API int lof_selftest_gemm_rne_round(uint64_t* dev_mismatches, void* stream);
+
 /* Chunked tensor-core mode (tcgen05 + TMEM): after every k_chunk columns of K the fp32 partial product P of
  * the chunk (tensor core, fp32 accumulate) is folded into the running accumulator, which lives in the
  * accumulator format:

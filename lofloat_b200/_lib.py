@@ -27,8 +27,10 @@ ABI_SYMBOLS = (
     "lof_abi_version", "lof_status_string", "lof_last_error_string", "lof_kernel_launch_count",
     "lof_mx_priv_max_normal", "lof_set_option", "lof_get_option", "lof_selftest_mx_division",
     "lof_packed_size", "lof_encode_f32", "lof_decode_f32", "lof_gemm_chunked_packed", "lof_round_strict_f32", "lof_mx_encode_f32", "lof_mx_decode_f32", "lof_gemm_batched_f32", "lof_fwht_f32", "lof_fwht_round_f32", "lof_fwht_mx_round_f32",
+    "lof_linear_f32", "lof_conv2d_f32", "lof_conv2d_out_size", "lof_selftest_gemm_rne_round",
 )
 LOF_PACK_FORWARD, LOF_PACK_REVERSE = 0, 1
+LOF_CONV_K_CRS, LOF_CONV_K_RSC = 0, 1
 
 
 class CFormat(C.Structure):
@@ -48,6 +50,12 @@ class CCodecFormat(C.Structure):
 class CProjSpec(C.Structure):
     """lof_projspec_t"""
     _fields_ = [("rounding_mode", C.c_int32), ("saturation_mode", C.c_int32), ("stoch_length", C.c_int32)]
+
+
+class CConv2d(C.Structure):
+    """lof_conv2d_t"""
+    _fields_ = [(n, C.c_int64) for n in ("batch", "c_in", "h", "w", "c_out", "r", "s", "pad_h", "pad_w", "stride_h", "stride_w",
+                                         "dilation_h", "dilation_w", "groups")] + [("k_order", C.c_int32)]
 
 
 class CRng(C.Structure):
@@ -110,6 +118,14 @@ def _declare(lib):
     lib.lof_round_strict_f32.restype = i32
     lib.lof_gemm_chunked_packed.argtypes = [vp, vp, vp, i64, i64, i64, i32, PF, PP, i64, f32, i32, C.c_uint32, vp, vp]
     lib.lof_gemm_chunked_packed.restype = i32
+    lib.lof_linear_f32.argtypes = [vp, vp, vp, vp, i64, i64, i64, i32, PP, i64, f32, PR, vp]
+    lib.lof_linear_f32.restype = i32
+    lib.lof_conv2d_f32.argtypes = [vp, vp, vp, vp, C.POINTER(CConv2d), i32, PP, i64, f32, PR, vp]
+    lib.lof_conv2d_f32.restype = i32
+    lib.lof_conv2d_out_size.argtypes = [i64, i64, i64, i64, i64, C.POINTER(i64)]
+    lib.lof_conv2d_out_size.restype = i32
+    lib.lof_selftest_gemm_rne_round.argtypes = [vp, vp]
+    lib.lof_selftest_gemm_rne_round.restype = i32
     lib.lof_set_option.argtypes = [C.c_char_p, i64]
     lib.lof_set_option.restype = i32
     lib.lof_get_option.argtypes = [C.c_char_p, C.POINTER(i64)]

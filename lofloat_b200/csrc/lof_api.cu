@@ -21,7 +21,9 @@
 namespace lof {
 cudaError_t launch_gemm_exact(int mode, const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
                               int accum_mant_bits, int len, int64_t kc, float alpha, float beta, const RngArgs& rng,
-                              cudaStream_t stream, int64_t batch = 1, int64_t stride_a = 0, int64_t stride_b = 0, int64_t stride_c = 0);
+                              cudaStream_t stream, int64_t batch = 1, int64_t stride_a = 0, int64_t stride_b = 0, int64_t stride_c = 0,
+                              const ExactView* view = nullptr, int fast = 1);
+cudaError_t launch_selftest_rne_round(unsigned long long* mismatches, int num_sms, cudaStream_t stream);
 cudaError_t launch_mx_tma(int mode, const float* in, float* out, int64_t n, const MxArgs& a, const RngArgs& rng,
                           const RngArgs& rng_scale, uint64_t first_index, const MxLaunchCfg& cfg, cudaStream_t stream,
                           int* launches, bool* handled);
@@ -56,6 +58,7 @@ struct Options {
     std::atomic<int64_t> stream_ctas_per_sm{8};  // codec / strict rounding / MX storage / fused Hadamard kernels: ALU-heavier, they want full residency (scripts/stream_tune.py)
     std::atomic<int64_t> host_chunk_bytes{32ll << 20};
     std::atomic<int64_t> pack_fast{1};           // storage codec: 0 = exact integer routine only, 1 = magic-add fast path where eligible
+    std::atomic<int64_t> gemm_fast{1};           // exact GEMM: 1 = optimistic branch-free chain with a per-tile fallback, 0 = exact routines only
     std::atomic<int64_t> round_fast{2};          // 0: exact kernels; 1: branch-free fast path; 2: + magic-add path (default)
 } g_opt;
 
@@ -524,6 +527,7 @@ int lof_set_option(const char* key, int64_t value)
     else if (k == "round.fast") { if (value < 0 || value > 2) return fail(LOF_ERR_INVALID_ARG, "round.fast must be 0, 1 or 2"); g_opt.round_fast = value; }
     else if (k == "stream.ctas_per_sm") { if (value < 1 || value > 64) return fail(LOF_ERR_INVALID_ARG, "stream.ctas_per_sm out of range"); g_opt.stream_ctas_per_sm = value; }
     else if (k == "pack.fast") { if (value < 0 || value > 1) return fail(LOF_ERR_INVALID_ARG, "pack.fast must be 0 or 1"); g_opt.pack_fast = value; }
+    else if (k == "gemm.fast") { if (value < 0 || value > 2) return fail(LOF_ERR_INVALID_ARG, "gemm.fast must be 0, 1 or 2"); g_opt.gemm_fast = value; }
     else if (k == "host.chunk_bytes") { if (value < (1 << 16)) return fail(LOF_ERR_INVALID_ARG, "host.chunk_bytes too small"); g_opt.host_chunk_bytes = value; }
     else return fail(LOF_ERR_INVALID_ARG, "unknown option: " + k);
     return LOF_OK;
@@ -540,6 +544,7 @@ int lof_get_option(const char* key, int64_t* value)
     else if (k == "round.fast") *value = g_opt.round_fast;
     else if (k == "stream.ctas_per_sm") *value = g_opt.stream_ctas_per_sm;
     else if (k == "pack.fast") *value = g_opt.pack_fast;
+    else if (k == "gemm.fast") *value = g_opt.gemm_fast;
     else if (k == "host.chunk_bytes") *value = g_opt.host_chunk_bytes;
     else return fail(LOF_ERR_INVALID_ARG, "unknown option: " + k);
     return LOF_OK;
@@ -584,7 +589,8 @@ int lof_gemm_batched_f32(const float* A, const float* B, float* C, int64_t batch
     if (!C || (K > 0 && (!A || !B))) return fail(LOF_ERR_INVALID_ARG, "null matrix pointer");
     if (num_sms() <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
     cudaError_t e = launch_gemm_exact(mode, A, B, C, M, N, K, accum_mant_bits, ps->stoch_length, kc, alpha, beta,
-                                      make_rng(rng, kStreamGemm), static_cast<cudaStream_t>(stream), batch, stride_a, stride_b, stride_c);
+                                      make_rng(rng, kStreamGemm), static_cast<cudaStream_t>(stream), batch, stride_a, stride_b, stride_c, nullptr,
+                                      (int)g_opt.gemm_fast.load());
     if (e != cudaSuccess) return cuda_fail(e, "lof_gemm_batched launch");
     g_launches.fetch_add(1);
     return LOF_OK;
@@ -608,8 +614,102 @@ int lof_gemm_f32(const float* A, const float* B, float* C, int64_t M, int64_t N,
     if (!C || (K > 0 && (!A || !B))) return fail(LOF_ERR_INVALID_ARG, "null matrix pointer");
     if (num_sms() <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
     cudaError_t e = launch_gemm_exact(mode, A, B, C, M, N, K, accum_mant_bits, ps->stoch_length, kc, alpha, beta,
-                                      make_rng(rng, kStreamGemm), static_cast<cudaStream_t>(stream));
+                                      make_rng(rng, kStreamGemm), static_cast<cudaStream_t>(stream), 1, 0, 0, 0, nullptr, (int)g_opt.gemm_fast.load());
     if (e != cudaSuccess) return cuda_fail(e, "lof_gemm launch");
+    g_launches.fetch_add(1);
+    return LOF_OK;
+}
+
+namespace {
+// argument checks shared by the exact-GEMM entry points
+int check_exact_args(int accum_mant_bits, const lof_projspec_t* ps)
+{
+    if (!ps) return fail(LOF_ERR_INVALID_ARG, "projspec is NULL");
+    const int mode = ps->rounding_mode;
+    if (mode < 0 || mode >= LOF_NUM_ROUNDING_MODES) return fail(LOF_ERR_INVALID_ARG, "unknown rounding mode");
+    if (accum_mant_bits > 23) return fail(LOF_ERR_INVALID_ARG, "accum_mant_bits > 23");
+    if (accum_mant_bits >= 0 && accum_mant_bits < 23 &&
+        (mode == LOF_StochasticRoundingA || mode == LOF_StochasticRoundingB || mode == LOF_StochasticRoundingC ||
+         mode == LOF_StochasticRoundingD) &&
+        (ps->stoch_length < 0 || ps->stoch_length > 23 - accum_mant_bits))
+        return fail(LOF_ERR_INVALID_ARG, "stochastic_rounding_bits must be in [0, 23 - accum_mant_bits]");
+    return LOF_OK;
+}
+}  // namespace
+
+int lof_linear_f32(const float* x, const float* weight, const float* bias, float* out, int64_t M, int64_t N, int64_t K,
+                   int accum_mant_bits, const lof_projspec_t* ps, int64_t kc, float alpha, const lof_rng_t* rng, void* stream)
+{
+    if (M < 0 || N < 0 || K < 0) return fail(LOF_ERR_INVALID_ARG, "negative GEMM dimension");
+    if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX) return fail(LOF_ERR_UNSUPPORTED, "GEMM dimension exceeds 2^31-1");
+    if (const int st = check_exact_args(accum_mant_bits, ps)) return st;
+    if (M == 0 || N == 0) return LOF_OK;
+    if (!out || (K > 0 && (!x || !weight))) return fail(LOF_ERR_INVALID_ARG, "null matrix pointer");
+    if (num_sms() <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    ExactView v;
+    v.b_kind = 1;
+    v.bias = bias;
+    v.bias_axis = 1;
+    cudaError_t e = launch_gemm_exact(ps->rounding_mode, x, weight, out, M, N, K, accum_mant_bits, ps->stoch_length, kc, alpha, 0.0f,
+                                      make_rng(rng, kStreamGemm), static_cast<cudaStream_t>(stream), 1, 0, 0, 0, &v, (int)g_opt.gemm_fast.load());
+    if (e != cudaSuccess) return cuda_fail(e, "lof_linear launch");
+    g_launches.fetch_add(1);
+    return LOF_OK;
+}
+
+int lof_selftest_gemm_rne_round(uint64_t* dev_mismatches, void* stream)
+{
+    if (!dev_mismatches) return fail(LOF_ERR_INVALID_ARG, "dev_mismatches is NULL");
+    const int sms = num_sms();
+    if (sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    cudaError_t e = launch_selftest_rne_round(reinterpret_cast<unsigned long long*>(dev_mismatches), sms, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "lof_selftest_gemm_rne_round launch");
+    g_launches.fetch_add(1);
+    return LOF_OK;
+}
+
+int lof_conv2d_out_size(int64_t in, int64_t kernel, int64_t pad, int64_t stride, int64_t dilation, int64_t* out)
+{
+    if (!out) return fail(LOF_ERR_INVALID_ARG, "out is NULL");
+    if (in <= 0 || kernel <= 0 || pad < 0 || stride <= 0 || dilation <= 0) return fail(LOF_ERR_INVALID_ARG, "conv2d: bad geometry");
+    const int64_t span = in + 2 * pad - dilation * (kernel - 1) - 1;
+    *out = span < 0 ? 0 : span / stride + 1;
+    return LOF_OK;
+}
+
+int lof_conv2d_f32(const float* input, const float* weight, const float* bias, float* out, const lof_conv2d_t* g,
+                   int accum_mant_bits, const lof_projspec_t* ps, int64_t kc, float alpha, const lof_rng_t* rng, void* stream)
+{
+    if (!g) return fail(LOF_ERR_INVALID_ARG, "conv2d geometry is NULL");
+    if (g->batch < 0 || g->c_in <= 0 || g->c_out <= 0 || g->h <= 0 || g->w <= 0 || g->r <= 0 || g->s <= 0 || g->groups <= 0 ||
+        g->pad_h < 0 || g->pad_w < 0 || g->stride_h <= 0 || g->stride_w <= 0 || g->dilation_h <= 0 || g->dilation_w <= 0)
+        return fail(LOF_ERR_INVALID_ARG, "conv2d: bad geometry");
+    if (g->c_in % g->groups || g->c_out % g->groups) return fail(LOF_ERR_INVALID_ARG, "conv2d: groups must divide C_in and C_out");
+    if (g->k_order != LOF_CONV_K_CRS && g->k_order != LOF_CONV_K_RSC) return fail(LOF_ERR_INVALID_ARG, "conv2d: unknown k_order");
+    if (const int st = check_exact_args(accum_mant_bits, ps)) return st;
+    int64_t P = 0, Q = 0;
+    lof_conv2d_out_size(g->h, g->r, g->pad_h, g->stride_h, g->dilation_h, &P);
+    lof_conv2d_out_size(g->w, g->s, g->pad_w, g->stride_w, g->dilation_w, &Q);
+    if (P <= 0 || Q <= 0) return fail(LOF_ERR_INVALID_ARG, "LoF_conv2d: non-positive output spatial size");   // Lof_kernel.cu:196
+    const int64_t Cg = g->c_in / g->groups, Mg = g->c_out / g->groups, K = Cg * g->r * g->s, L = P * Q;
+    if (K > INT32_MAX || L > INT32_MAX || g->c_in * g->h * g->w > INT32_MAX || g->pad_h > (1 << 20) || g->pad_w > (1 << 20))
+        return fail(LOF_ERR_UNSUPPORTED, "conv2d: image or reduction extent exceeds 2^31-1");
+    if (g->batch * g->groups > 65535) return fail(LOF_ERR_UNSUPPORTED, "conv2d: at most 65535 (image, group) pairs per call");
+    if (g->batch == 0) return LOF_OK;
+    if (!input || !weight || !out) return fail(LOF_ERR_INVALID_ARG, "null tensor pointer");
+    if (num_sms() <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    ExactView v;
+    v.b_kind = 2;
+    v.k_order = g->k_order;
+    v.bias = bias;
+    v.bias_axis = 0;
+    v.C = (int)g->c_in; v.H = (int)g->h; v.W = (int)g->w; v.Cg = (int)Cg; v.R = (int)g->r; v.S = (int)g->s; v.Q = (int)Q;
+    v.ph = (int)g->pad_h; v.pw = (int)g->pad_w; v.sh = (int)g->stride_h; v.sw = (int)g->stride_w;
+    v.dh = (int)g->dilation_h; v.dw = (int)g->dilation_w; v.groups = (int)g->groups;
+    cudaError_t e = launch_gemm_exact(ps->rounding_mode, weight, input, out, Mg, L, K, accum_mant_bits, ps->stoch_length, kc, alpha, 0.0f,
+                                      make_rng(rng, kStreamGemm), static_cast<cudaStream_t>(stream), g->batch * g->groups, 0, 0, 0, &v,
+                                      (int)g_opt.gemm_fast.load());
+    if (e != cudaSuccess) return cuda_fail(e, "lof_conv2d launch");
     g_launches.fetch_add(1);
     return LOF_OK;
 }

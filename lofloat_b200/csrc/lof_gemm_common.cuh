@@ -8,6 +8,21 @@ namespace lof {
 // internal flag of launch_gemm_tc (not part of the public flag set): A / B are 8-bit representations, B is K-major
 constexpr uint32_t LOF_GEMM_INTERNAL_PACKED_OPERANDS = 0x80000000u;
 
+// Operand addressing of the exact GEMM beyond plain row-major: the callers fused around lof_gemm.
+//   b_kind 0  B is K x N row-major (lof_gemm_f32 / lof_gemm_batched_f32)
+//   b_kind 1  B is N x K row-major -- an nn.Linear weight used as stored, replacing `weight.t().contiguous()` of
+//             _lof_linear (LoFloat/layers.py:152-168)
+//   b_kind 2  implicit im2col: B(k, n) is gathered from an NCHW image, A is the OIHW filter bank; grid.z = image x group.
+//             k_order 0 = (c, r, s) ascending, the F.unfold order of LoF_Conv2d's im2col backend (layers.py:710-745);
+//             k_order 1 = (r, s, c), the NHWC / KRSC order of the implicit-GEMM backend (Lof_kernel.cu:156-228).
+// `bias` (already quantised) is added to alpha * acc in plain fp32 like `out + b_q` (layers.py:392-398, 747-751):
+// bias_axis 0 = one value per row of C (conv: output channel), 1 = per column (linear: output feature).
+struct ExactView {
+    int b_kind = 0, k_order = 0, bias_axis = 0;
+    const float* bias = nullptr;
+    int C = 0, H = 0, W = 0, Cg = 0, R = 0, S = 0, Q = 0, ph = 0, pw = 0, sh = 1, sw = 1, dh = 1, dw = 1, groups = 1;
+};
+
 // round-to-odd fused multiply-add, bit-identical to the host routine
 // lof_round_to_odd_fma (blis_lof_gemm.hpp:63-99): RN result when it is exact or
 // non-finite, otherwise the neighbour (of the exact value) with an odd mantissa LSB.

@@ -26,30 +26,82 @@ __device__ __forceinline__ float accum_round(float t, int r, int len, uint32_t w
     return __uint_as_float(round_mantissa_elem<LOF_F32, MODE>(__float_as_uint(t), r, len, w));
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kGemmThreads)
-gemm_exact_kernel(const float* __restrict__ A, const float* __restrict__ B, float* C, int M, int N, int K,
-                  int r, int len, int kc, float alpha, float beta, bool custom, RngArgs rng,
-                  int64_t stride_a, int64_t stride_b, int64_t stride_c)
+// Optimistic round-to-odd FMA: RZ(a*b + c) with the LSB OR-ed with "inexact" (the two directed results differ), no branch.
+// Equal to rto_fma whenever |result| < 2^127: an exact sum gives rd == ru == rz (an exact zero: rd = -0 == ru = +0, and
+// RZ returns +0 like the reference's `ru`); an inexact one gives the toward-zero neighbour, which is `rd` for a positive and
+// `ru` for a negative exact value.  Overflow, infinities and NaNs (where the reference switches to RN) all land at
+// |result| >= 2^127 or NaN, which the caller flags and recomputes with the exact routine.
+__device__ __forceinline__ float rto_fma_optimistic(float a, float b, float c)
 {
-    // batched call (blockIdx.z = batch index): the (b, h) loop of LoFloat/layers.py:142-149 as one launch; the stochastic
-    // event index continues across the batch ((batch * M + i) * N + j) * K + k
-    A += (int64_t)blockIdx.z * stride_a;
-    B += (int64_t)blockIdx.z * stride_b;
-    C += (int64_t)blockIdx.z * stride_c;
-    const uint64_t rng_base = (uint64_t)blockIdx.z * (uint64_t)M * (uint64_t)N * (uint64_t)K;
-    __shared__ float As[TK][TM + 4];
-    __shared__ float Bs[TK][TN + 4];
+    const float rd = __fmaf_rd(a, b, c), ru = __fmaf_ru(a, b, c), rz = __fmaf_rz(a, b, c);
+    return __uint_as_float(__float_as_uint(rz) | (rd != ru ? 1u : 0u));
+}
+
+// The same with two FMAs: the toward-zero result is picked by the sign of rd (an exact zero has rd = -0 and takes ru = +0).
+__device__ __forceinline__ float rto_fma_optimistic2(float a, float b, float c)
+{
+    const float rd = __fmaf_rd(a, b, c), ru = __fmaf_ru(a, b, c);
+    const uint32_t rz = (int32_t)__float_as_uint(rd) >= 0 ? __float_as_uint(rd) : __float_as_uint(ru);
+    return __uint_as_float(rz | (rd != ru ? 1u : 0u));
+}
+
+// Mantissa-only rounding on the signed bit pattern (no |x| / sign re-attach): the increments of every mode only look at the
+// low r bits (+ the sign for RoundUp / RoundDown), and for |t| < 2^127 the carry cannot reach the sign bit.
+template <int MODE>
+__device__ __forceinline__ float accum_round_signed(float t, int r, uint32_t keep, int len, uint32_t w)
+{
+    const uint32_t b = __float_as_uint(t);
+    return __uint_as_float(round_bits<MODE, uint32_t>(b, r, len, (int32_t)b >= 0, w) & keep);
+}
+
+// RNE to (23 - r) mantissa bits in the float domain:  K = sign(t) * 2^(e + r)  (e = exponent of t), y = (t + K) - K.
+// t + K lies in [2^(e+r) + 2^e, 2^(e+r) + 2^(e+1)), one binade whose ulp is 2^(e + r - 23) -- the target grid -- so the
+// hardware's RNE add performs the rounding (ties to even on that grid, i.e. on bit r of t's pattern) and the subtraction is
+// exact.  Equal to round_bits<RNE> + mask for every NORMAL t with e + r < 127 and r <= 22 (lof_selftest_gemm_rne_round checks
+// all 2^32 patterns x 22 widths on the device; at r = 23 the integer routine's "even" is the exponent's low bit, ours is not); larger t, infinities and NaNs give a non-finite y (K = inf -> NaN; at e + r = 127 the
+// sum can round up to inf), which sticks to the accumulator until the panel ends, where the caller looks for it.  One alu-pipe and three fma-pipe instructions instead of
+// four alu-pipe ones: the chain is bound by the (half-rate) alu pipe, see profiles/r01k_gemm_exact_summary.txt.
+__device__ __forceinline__ float accum_round_rne_float(float t, float two_r)
+{
+    const float k = __fmul_rn(__uint_as_float(__float_as_uint(t) & 0xFF800000u), two_r);
+    return __fsub_rn(__fadd_rn(t, k), k);
+}
+
+// One 64 x 64 tile of C into `crun` (not stored).  VARIANT 0: the exact routines (rto_fma with its non-finite branch,
+// round_mantissa_elem); VARIANT 1 / 2: the optimistic chain (r > 0 / r == 0) -- returns true if any intermediate left
+// the range where it is proven equal, in which case the caller discards `crun` and runs VARIANT 0.  VARIANT 3 (RNE, r > 0):
+// the same chain with the rounding in the float domain; its range conditions are checked outside the MAC loop -- operands
+// are 0 or >= 2^-40 in magnitude (then every product and every accumulator is a multiple of 2^-126: no subnormal
+// intermediate can occur), and no accumulator is NaN / inf at the end of a panel.
+template <int MODE, int VARIANT>
+__device__ __forceinline__ bool
+gemm_exact_tile(const float* __restrict__ A, const float* __restrict__ B, const float* C, int M, int N, int K,
+                int r, int len, int kc, float alpha, float beta, bool custom, const RngArgs& rng, uint64_t rng_base,
+                int bias_off, const ExactView& v, float (*As)[TM + 4], float (*Bs)[TN + 4], float (&crun)[4][4])
+{
+    bool flagged = false;
+    const uint32_t keep = r > 0 ? ~((1u << r) - 1u) : 0xFFFFFFFFu;
+    const float two_r = __uint_as_float((uint32_t)(127 + r) << 23);
+    constexpr float kTinyOperand = 9.094947017729282e-13f;      // 2^-40
 
     const int tx = threadIdx.x & 15;     // n direction
     const int ty = threadIdx.x >> 4;     // m direction
     const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
 
-    float crun[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) crun[i][j] = 0.0f;
+
+    // conv: the output position this thread stages (column n0 + (tid & 63) of the im2col matrix) never changes
+    int ih0 = 0, iw0 = 0;
+    const int RS = v.R * v.S;
+    if (v.b_kind == 2) {
+        const int n = n0 + (threadIdx.x & 63);
+        const int p = n / v.Q, q = n - p * v.Q;
+        ih0 = p * v.sh - v.ph;
+        iw0 = q * v.sw - v.pw;
+    }
 
     bool first = true;
     for (int p0 = 0; p0 < K; p0 += kc) {
@@ -68,40 +120,107 @@ gemm_exact_kernel(const float* __restrict__ A, const float* __restrict__ B, floa
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int m = am + 16 * i;
-                    float v = 0.0f;
-                    if (ak < kt && m0 + m < M) v = A[(int64_t)(m0 + m) * K + k0 + ak];
-                    As[ak][m] = v;
+                    float x = 0.0f;
+                    if (ak < kt && m0 + m < M) {
+                        int kp = k0 + ak;                       // physical column of the filter row (stored (c, r, s))
+                        if (v.b_kind == 2 && v.k_order == 1) { const int rs = kp / v.Cg, c = kp - rs * v.Cg; kp = c * RS + rs; }
+                        x = A[(int64_t)(m0 + m) * K + kp];
+                    }
+                    if constexpr (VARIANT >= 3) flagged |= (x != 0.0f) & (fabsf(x) < kTinyOperand);
+                    As[ak][m] = x;
                 }
-                const int bn = threadIdx.x & 63, bk = threadIdx.x >> 6;
+                if (v.b_kind == 1) {                            // B stored N x K: same access pattern as A
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int k = bk + 4 * i;
-                    float v = 0.0f;
-                    if (k < kt && n0 + bn < N) v = B[(int64_t)(k0 + k) * N + n0 + bn];
-                    Bs[k][bn] = v;
+                    for (int i = 0; i < 4; ++i) {
+                        const int n = am + 16 * i;
+                        float x = 0.0f;
+                        if (ak < kt && n0 + n < N) x = B[(int64_t)(n0 + n) * K + k0 + ak];
+                        if constexpr (VARIANT >= 3) flagged |= (x != 0.0f) & (fabsf(x) < kTinyOperand);
+                        Bs[ak][n] = x;
+                    }
+                } else {
+                    const int bn = threadIdx.x & 63, bk = threadIdx.x >> 6;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int k = bk + 4 * i;
+                        float x = 0.0f;
+                        if (k < kt && n0 + bn < N) {
+                            if (v.b_kind == 0) {
+                                x = B[(int64_t)(k0 + k) * N + n0 + bn];
+                            } else {
+                                const int kk = k0 + k;
+                                int c, r, s2;
+                                if (v.k_order == 0) { c = kk / RS; const int rs = kk - c * RS; r = rs / v.S; s2 = rs - r * v.S; }
+                                else { const int rs = kk / v.Cg; c = kk - rs * v.Cg; r = rs / v.S; s2 = rs - r * v.S; }
+                                const int ih = ih0 + r * v.dh, iw = iw0 + s2 * v.dw;
+                                if (ih >= 0 && ih < v.H && iw >= 0 && iw < v.W) x = B[((int64_t)c * v.H + ih) * v.W + iw];   // zero padding otherwise
+                            }
+                        }
+                        if constexpr (VARIANT >= 3) flagged |= (x != 0.0f) & (fabsf(x) < kTinyOperand);
+                        Bs[k][bn] = x;
+                    }
                 }
             }
             __syncthreads();
-            for (int k = 0; k < kt; ++k) {
-                const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-                const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-                const float a4[4] = {av.x, av.y, av.z, av.w};
-                const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if (custom) {
-                            uint32_t w = 0;
-                            if constexpr (ModeTraits<MODE>::kUsesRng) {
-                                const uint64_t gi = (uint64_t)(m0 + ty * 4 + i), gj = (uint64_t)(n0 + tx * 4 + j);
-                                w = philox_word(rng, rng_base + (gi * (uint64_t)N + gj) * (uint64_t)K + (uint64_t)(k0 + k));
-                            }
-                            acc[i][j] = accum_round<MODE>(rto_fma(a4[i], b4[j], acc[i][j]), r, len, w);
-                        } else {
-                            acc[i][j] = __fadd_rn(acc[i][j], __fmul_rn(a4[i], b4[j]));   // blis_lof_gemm.hpp:233-239
-                        }
+            // one multiply-accumulate of chain (i, j): w = the rounding event's random word (stochastic modes)
+            auto mac = [&](float a, float b, float& c, uint32_t w) {
+                if constexpr (VARIANT != 0) {
+                    const float t = VARIANT == 4 ? rto_fma_optimistic2(a, b, c) : rto_fma_optimistic(a, b, c);
+                    if constexpr (VARIANT >= 3) {
+                        c = accum_round_rne_float(t, two_r);
+                    } else {
+                        flagged |= !(fabsf(t) < 1.7014118346046923e38f);   // 2^127: also inf / NaN
+                        if constexpr (VARIANT == 1) c = accum_round_signed<MODE>(t, r, keep, len, w);
+                        else c = t;
                     }
+                } else if (custom) {
+                    c = accum_round<MODE>(rto_fma(a, b, c), r, len, w);
+                } else {
+                    c = __fadd_rn(c, __fmul_rn(a, b));   // blis_lof_gemm.hpp:233-239
+                }
+            };
+            if constexpr (ModeTraits<MODE>::kUsesRng) {
+                // stochastic modes: event index = ((row * N + col) * K + k); four consecutive k of one chain share a Philox
+                // block when that index is a multiple of 4 -- one generator call per 4 MACs instead of 4 (same words)
+                for (int kq = 0; kq < kt; kq += 4) {
+                    float a4[4][4], b4[4][4];
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const float4 av = *reinterpret_cast<const float4*>(&As[kq + kk][ty * 4]);   // rows >= kt hold stale data, unused
+                        const float4 bv = *reinterpret_cast<const float4*>(&Bs[kq + kk][tx * 4]);
+                        a4[kk][0] = av.x; a4[kk][1] = av.y; a4[kk][2] = av.z; a4[kk][3] = av.w;
+                        b4[kk][0] = bv.x; b4[kk][1] = bv.y; b4[kk][2] = bv.z; b4[kk][3] = bv.w;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint64_t gi = (uint64_t)(m0 + ty * 4 + i), gj = (uint64_t)(n0 + tx * 4 + j);
+                            const uint64_t e0 = rng_base + (gi * (uint64_t)N + gj) * (uint64_t)K + (uint64_t)(k0 + kq);
+                            uint32_t w[4];
+                            if ((e0 & 3u) == 0) {
+                                const uint4 blk = philox_block(rng, e0 >> 2);
+                                w[0] = blk.x; w[1] = blk.y; w[2] = blk.z; w[3] = blk.w;
+                            } else {
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk) w[kk] = philox_word(rng, e0 + kk);
+                            }
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                if (kq + kk < kt) mac(a4[kk][i], b4[kk][j], acc[i][j], w[kk]);
+                        }
+                }
+            } else {
+                for (int k = 0; k < kt; ++k) {
+                    const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+                    const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+                    const float a4[4] = {av.x, av.y, av.z, av.w};
+                    const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) mac(a4[i], b4[j], acc[i][j], 0u);
+                }
             }
             __syncthreads();
         }
@@ -110,6 +229,7 @@ gemm_exact_kernel(const float* __restrict__ A, const float* __restrict__ B, floa
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
+                if constexpr (VARIANT >= 3) flagged |= !(fabsf(acc[i][j]) < __int_as_float(0x7F800000));
                 const float ab = __fmul_rn(acc[i][j], alpha);
                 if (first) {
                     if (beta == 0.0f) crun[i][j] = ab;
@@ -133,6 +253,59 @@ gemm_exact_kernel(const float* __restrict__ A, const float* __restrict__ B, floa
                 crun[i][j] = (beta == 0.0f || gm >= M || gn >= N) ? 0.0f : __fmul_rn(beta, C[(int64_t)gm * N + gn]);
             }
     }
+    return flagged;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kGemmThreads)
+gemm_exact_kernel(const float* __restrict__ A, const float* __restrict__ B, float* C, int M, int N, int K,
+                  int r, int len, int kc, float alpha, float beta, bool custom, int fast, RngArgs rng,
+                  int64_t stride_a, int64_t stride_b, int64_t stride_c, ExactView v)
+{
+    // batched call (blockIdx.z = batch index): the (b, h) loop of LoFloat/layers.py:142-149 as one launch; the stochastic
+    // event index continues across the batch ((batch * M + i) * N + j) * K + k
+    int bias_off = 0;
+    if (v.b_kind == 2) {                                  // conv: z = image * groups + group; M = output channels per group, N = P * Q
+        const int img = blockIdx.z / v.groups, grp = blockIdx.z - img * v.groups;
+        A += (int64_t)grp * M * K;
+        B += ((int64_t)img * v.C + (int64_t)grp * v.Cg) * v.H * v.W;
+        C += (int64_t)blockIdx.z * M * N;
+        bias_off = grp * M;
+    } else {
+        A += (int64_t)blockIdx.z * stride_a;
+        B += (int64_t)blockIdx.z * stride_b;
+        C += (int64_t)blockIdx.z * stride_c;
+    }
+    const uint64_t rng_base = (uint64_t)blockIdx.z * (uint64_t)M * (uint64_t)N * (uint64_t)K;
+    __shared__ float As[TK][TM + 4];
+    __shared__ float Bs[TK][TN + 4];
+    const int tx = threadIdx.x & 15;     // n direction
+    const int ty = threadIdx.x >> 4;     // m direction
+    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+
+    float crun[4][4];
+    bool redo = true;
+    if (fast && custom) {
+        constexpr int kRounding = MODE == LOF_RoundToNearestEven ? 3 : 1;
+        constexpr int kRounding2 = MODE == LOF_RoundToNearestEven ? 4 : 1;
+        // r = 23 (no mantissa bit kept) stays on the integer rounding: there "even" refers to the exponent's low bit
+        const bool f = (r > 0 && r < 23 && fast == 2) ? gemm_exact_tile<MODE, kRounding2>(A, B, C, M, N, K, r, len, kc, alpha, beta, custom, rng, rng_base, bias_off, v, As, Bs, crun)
+                     : (r > 0 && r < 23) ? gemm_exact_tile<MODE, kRounding>(A, B, C, M, N, K, r, len, kc, alpha, beta, custom, rng, rng_base, bias_off, v, As, Bs, crun)
+                     : r > 0 ? gemm_exact_tile<MODE, 1>(A, B, C, M, N, K, r, len, kc, alpha, beta, custom, rng, rng_base, bias_off, v, As, Bs, crun)
+                             : gemm_exact_tile<MODE, 2>(A, B, C, M, N, K, r, len, kc, alpha, beta, custom, rng, rng_base, bias_off, v, As, Bs, crun);
+        redo = __syncthreads_or(f) != 0;
+    }
+    if (redo) gemm_exact_tile<MODE, 0>(A, B, C, M, N, K, r, len, kc, alpha, beta, custom, rng, rng_base, bias_off, v, As, Bs, crun);
+
+    if (v.bias != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
+                if (gm < M && gn < N) crun[i][j] = __fadd_rn(crun[i][j], v.bias[v.bias_axis == 0 ? bias_off + gm : gn]);
+            }
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int gm = m0 + ty * 4 + i;
@@ -148,19 +321,45 @@ gemm_exact_kernel(const float* __restrict__ A, const float* __restrict__ B, floa
     }
 }
 
+// every fp32 pattern x every width: the float-domain RNE of the optimistic chain against round_bits<RNE> + mask
+__global__ void selftest_rne_round_kernel(unsigned long long* mismatches)
+{
+    unsigned long long bad = 0;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < (1ull << 32); p += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t b = (uint32_t)p, field = (b >> 23) & 0xFFu;
+        if (field == 0) continue;                                              // zeros / subnormals: excluded by the operand check
+        for (int r = 1; r <= 22; ++r) {
+            const float y = accum_round_rne_float(__uint_as_float(b), __uint_as_float((uint32_t)(127 + r) << 23));
+            const bool nonfinite = !(fabsf(y) < __int_as_float(0x7F800000));
+            if (field == 255 || (int)field + r > 254) { bad += !nonfinite; continue; }     // out of range must surface as inf / NaN
+            const uint32_t want = round_bits<LOF_RoundToNearestEven, uint32_t>(b, r, 0, true, 0) & ~((1u << r) - 1u);
+            bad += __float_as_uint(y) != want && !((int)field + r == 254 && nonfinite);    // top binade: t + K may round up to 2^128
+        }
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 }  // namespace
+
+cudaError_t launch_selftest_rne_round(unsigned long long* mismatches, int num_sms, cudaStream_t stream)
+{
+    selftest_rne_round_kernel<<<num_sms * 8, 256, 0, stream>>>(mismatches);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_gemm_exact(int mode, const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
                               int accum_mant_bits, int len, int64_t kc, float alpha, float beta, const RngArgs& rng,
-                              cudaStream_t stream, int64_t batch, int64_t stride_a, int64_t stride_b, int64_t stride_c)
+                              cudaStream_t stream, int64_t batch, int64_t stride_a, int64_t stride_b, int64_t stride_c, const ExactView* view,
+                              int fast)
 {
+    const ExactView v = view ? *view : ExactView{};
     if (M <= 0 || N <= 0 || batch <= 0) return cudaSuccess;
     const bool custom = accum_mant_bits >= 0;
     const int r = custom ? 23 - accum_mant_bits : 0;
     int kci = (kc <= 0 || kc > K) ? (int)(K > 0 ? K : 1) : (int)kc;
     dim3 grid((unsigned)((N + TN - 1) / TN), (unsigned)((M + TM - 1) / TM), (unsigned)batch);
     switch (mode) {
-#define LOF_CASE(Mo) case Mo: gemm_exact_kernel<Mo><<<grid, kGemmThreads, 0, stream>>>(A, B, C, (int)M, (int)N, (int)K, r, len, kci, alpha, beta, custom, rng, stride_a, stride_b, stride_c); break;
+#define LOF_CASE(Mo) case Mo: gemm_exact_kernel<Mo><<<grid, kGemmThreads, 0, stream>>>(A, B, C, (int)M, (int)N, (int)K, r, len, kci, alpha, beta, custom, fast, rng, stride_a, stride_b, stride_c, v); break;
         LOF_CASE(LOF_RoundToNearestEven) LOF_CASE(LOF_RoundTowardsZero) LOF_CASE(LOF_RoundAwayFromZero)
         LOF_CASE(LOF_StochasticRoundingA) LOF_CASE(LOF_RoundToNearestOdd) LOF_CASE(LOF_RoundDown)
         LOF_CASE(LOF_RoundUp) LOF_CASE(LOF_RoundTiesToAway) LOF_CASE(LOF_StochasticRoundingB)

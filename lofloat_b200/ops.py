@@ -495,6 +495,91 @@ def lof_gemm_batched(A: torch.Tensor, B: torch.Tensor, accum_mant_bits: int, rou
     return out.reshape(*batch_shape, M, N)
 
 
+def lof_linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, accum_mant_bits: int,
+               round_mode=RoundingMode.RoundToNearestEven, stochastic_rounding_bits: int = 0, scale_a: float = 1.0, scale_b: float = 1.0,
+               *, kc=None, rng=None) -> torch.Tensor:
+    """F.linear with LoFloat accumulation: x (..., K), weight (N, K) -> (..., N) -- `_lof_linear` of LoFloat/layers.py:152-168
+    as ONE kernel: the weight is read as stored (no `weight.t().contiguous()` copy) and the already quantised `bias` is added in
+    the epilogue (plain fp32 add, `out + bias`).  Bit-identical to lof_gemm(x_2d, weight.t().contiguous(), ...) + bias."""
+    if weight.dim() != 2 or x.dim() < 1 or x.shape[-1] != weight.shape[1]:
+        raise RuntimeError(f"lof_linear: incompatible shapes {tuple(x.shape)} x {tuple(weight.shape)}")
+    if x.dtype != torch.float32 or weight.dtype != torch.float32 or (bias is not None and bias.dtype != torch.float32):
+        raise RuntimeError("LoF_gemm: only float32 inputs are supported")
+    if not (x.is_cuda and weight.is_cuda and (bias is None or bias.is_cuda)):
+        raise RuntimeError("LoF_gemm requires CUDA tensors")
+    N, K = weight.shape
+    if bias is not None and bias.numel() != N:
+        raise RuntimeError(f"lof_linear: bias has {bias.numel()} values, expected {N}")
+    mode = RoundingMode(int(round_mode))
+    ps = CProjSpec(int(mode), 0, int(stochastic_rounding_bits))
+    denom = float(scale_a) * float(scale_b)
+    alpha = 1.0 if denom == 0.0 else 1.0 / denom
+    x2, w_c = x.reshape(-1, K).contiguous(), weight.contiguous()
+    b_c = bias.contiguous() if bias is not None else None
+    out = torch.empty((x2.shape[0], N), dtype=torch.float32, device=x.device)
+    r = _next_rng(mode in _STOCHASTIC, rng)
+    with torch.cuda.device(x.device):
+        st = _lib.lib().lof_linear_f32(x2.data_ptr(), w_c.data_ptr(), b_c.data_ptr() if b_c is not None else None, out.data_ptr(),
+                                       x2.shape[0], N, K, int(accum_mant_bits), C.byref(ps), int(_gemm_kc if kc is None else kc), alpha,
+                                       C.byref(r), _stream_ptr(x2))
+    _lib.check(st, "lof_linear")
+    return out.reshape(*x.shape[:-1], N)
+
+
+def lof_conv2d(input: torch.Tensor, weight: torch.Tensor, pad_h: int, pad_w: int, stride_h: int, stride_w: int, dilation_h: int,
+               dilation_w: int, accum_mant_bits: int, round_mode=RoundingMode.RoundToNearestEven, stochastic_rounding_bits: int = 0,
+               weight_scale: float = 1.0, input_scale: float = 1.0, *, groups: int = 1, bias: torch.Tensor | None = None,
+               k_order: str = "rsc", kc=None, rng=None) -> torch.Tensor:
+    """Low-precision Conv2d forward, float32 NCHW input x OIHW weight -> NCHW output, divided by weight_scale * input_scale
+    (LoPy_bind.cpp:374-392, Lof_kernel.cu:156-228).  Implicit GEMM: no im2col matrix is written.
+
+    Defaults reproduce the reference entry point: reduction order (r, s, c) and one accumulator over all of K.  Keyword
+    extensions: `k_order="crs"` (+ `kc=256` for the CPU GEMM's panels) is LoF_Conv2d's im2col backend -- F.unfold followed
+    by one lof_gemm per image and group (LoFloat/layers.py:710-745) -- as one launch, `groups`, and a fused `bias` epilogue
+    (`out + b_q.view(1, -1, 1, 1)`, layers.py:747-751)."""
+    if input.dim() != 4 or weight.dim() != 4:
+        raise RuntimeError("LoF_conv2d: input and weight must be 4-D (NCHW / OIHW)")
+    if input.dtype != torch.float32 or weight.dtype != torch.float32 or (bias is not None and bias.dtype != torch.float32):
+        raise RuntimeError("LoF_conv2d: only float32 inputs are supported")
+    if not (input.is_cuda and weight.is_cuda and (bias is None or bias.is_cuda)):
+        raise RuntimeError(f"LoF_conv2d requires CUDA tensors (input on {input.device}, weight on {weight.device})")
+    if groups < 1 or input.size(1) % groups or weight.size(0) % groups:
+        raise RuntimeError("LoF_conv2d: groups must divide C_in and C_out")
+    if input.size(1) != weight.size(1) * groups:
+        raise RuntimeError(f"LoF_conv2d: input C_in ({input.size(1)}) != weight C_in ({weight.size(1) * groups})")
+    if k_order not in ("rsc", "crs"):
+        raise ValueError("k_order must be 'rsc' or 'crs'")
+    L = _lib.lib()
+    B, C_in, H, W = input.shape
+    C_out, _, R, S = weight.shape
+    if bias is not None and bias.numel() != C_out:
+        raise RuntimeError(f"LoF_conv2d: bias has {bias.numel()} values, expected {C_out}")
+    P, Q = C.c_int64(0), C.c_int64(0)
+    _lib.check(L.lof_conv2d_out_size(H, R, pad_h, stride_h, dilation_h, C.byref(P)), "LoF_conv2d")
+    _lib.check(L.lof_conv2d_out_size(W, S, pad_w, stride_w, dilation_w, C.byref(Q)), "LoF_conv2d")
+    if P.value <= 0 or Q.value <= 0:
+        raise RuntimeError(f"LoF_conv2d: non-positive output spatial size (P={P.value}, Q={Q.value})")
+    mode = RoundingMode(int(round_mode))
+    ps = CProjSpec(int(mode), 0, int(stochastic_rounding_bits))
+    denom = float(weight_scale) * float(input_scale)
+    alpha = 1.0 if denom == 0.0 else 1.0 / denom
+    x_c, w_c = input.contiguous(), weight.contiguous()
+    b_c = bias.contiguous() if bias is not None else None
+    out = torch.empty((B, C_out, P.value, Q.value), dtype=torch.float32, device=input.device)
+    r = _next_rng(mode in _STOCHASTIC, rng)
+    per_call = max(1, 65535 // groups)
+    with torch.cuda.device(input.device):
+        for b0 in range(0, B, per_call):
+            cnt = min(per_call, B - b0)
+            geo = _lib.CConv2d(cnt, C_in, H, W, C_out, R, S, pad_h, pad_w, stride_h, stride_w, dilation_h, dilation_w, groups,
+                               _lib.LOF_CONV_K_RSC if k_order == "rsc" else _lib.LOF_CONV_K_CRS)
+            st = L.lof_conv2d_f32(x_c[b0].data_ptr(), w_c.data_ptr(), b_c.data_ptr() if b_c is not None else None, out[b0].data_ptr(),
+                                  C.byref(geo), int(accum_mant_bits), C.byref(ps), int(0 if kc is None else kc), alpha, C.byref(r),
+                                  _stream_ptr(x_c))
+            _lib.check(st, "LoF_conv2d")
+    return out
+
+
 def fwht(input: torch.Tensor, block_size=None, *, params: FloatFormatDescriptor | None = None, round_mode=RoundingMode.RoundToNearestEven,
          stoch_len: int = 0, scale: float = 1.0, mx_block_size: int | None = None, scale_format: FloatFormatDescriptor | None = None,
          scale_round_mode=RoundingMode.RoundToNearestEven, rng=None, first_index: int = 0) -> torch.Tensor:

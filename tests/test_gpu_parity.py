@@ -1088,3 +1088,124 @@ def test_batched_gemm_equals_per_slice_calls(lof, cuda_dev):
             assert torch.equal(got, want), (bh, M, K, N, mant)
     A0, B0 = _np(A.reshape(-1, M, K)[3]), _np(B.reshape(-1, K, N)[3])
     assert L.bits_equal(_np(lof.lof_gemm_batched(A, B, 10).reshape(-1, M, N)[3]), L.o_gemm(A0, B0, 10, L.RNE, kc=256))
+
+
+def test_conv2d_implicit_gemm_and_fused_linear(lof, cuda_dev):
+    """Row f-3: lof_conv2d (implicit GEMM, no im2col matrix) == F.unfold + one lof_gemm per image and group, which is what
+    LoF_Conv2d's im2col backend computes (layers.py:710-745), bit for bit -- strides, dilation, padding, groups, ragged
+    tiles, both reduction orders (the (r, s, c) order is the same GEMM on the permuted K axis), the fused bias epilogue,
+    the output rescale; one image also against the CPU oracle's GEMM.  lof_linear (weight read as stored, bias fused)
+    == lof_gemm on the transposed copy + bias (layers.py:152-168)."""
+    import torch.nn.functional as F
+    g = torch.Generator(device=cuda_dev).manual_seed(31)
+    e4m3 = lof.create_p3109_params(8, 4, bias=7)
+    cases = (  # B, C_in, H, W, C_out, R, S, pad, stride, dil, groups
+        (2, 8, 12, 12, 16, 3, 3, (1, 1), (1, 1), (1, 1), 1),
+        (3, 6, 17, 13, 10, 3, 2, (2, 0), (2, 1), (1, 2), 2),
+        (1, 32, 20, 20, 70, 1, 1, (0, 0), (1, 1), (1, 1), 1),
+        (2, 4, 9, 31, 5, 5, 3, (3, 4), (3, 2), (2, 1), 1),
+    )
+    for (B, Ci, H, W, Co, R, S, pad, st, dil, grp) in cases:
+        x = lof.virtual_round(torch.randn(B, Ci, H, W, device=cuda_dev, generator=g), e4m3)
+        w = lof.virtual_round(torch.randn(Co, Ci // grp, R, S, device=cuda_dev, generator=g) * 0.5, e4m3)
+        bias = lof.virtual_round(torch.randn(Co, device=cuda_dev, generator=g), e4m3)
+        cols = F.unfold(x, (R, S), dilation=dil, padding=pad, stride=st)                      # (B, Ci*R*S, L), k = (c, r, s)
+        Lout = cols.shape[-1]
+        Cg, Mg = Ci // grp, Co // grp
+        cols = cols.view(B, grp, Cg * R * S, Lout)
+        wcol = w.view(grp, Mg, Cg * R * S)
+        for mant, mode, kc, ws, xs_ in ((10, L.RNE, 0, 1.0, 1.0), (7, L.RTZ, 256, 2.0, 4.0), (4, L.RTO, 16, 1.0, 1.0)):
+            for order in ("crs", "rsc"):
+                if order == "crs":
+                    wc, xc = wcol, cols
+                else:                                                                         # same chains with k = (r, s, c)
+                    wc = wcol.view(grp, Mg, Cg, R * S).transpose(2, 3).reshape(grp, Mg, -1)
+                    xc = cols.view(B, grp, Cg, R * S, Lout).transpose(2, 3).reshape(B, grp, -1, Lout)
+                want = torch.stack([torch.cat([lof.lof_gemm(wc[gi].contiguous(), xc[b, gi].contiguous(), mant, mode, 0, ws, xs_, kc=kc)
+                                               for gi in range(grp)], 0) for b in range(B)])
+                want = want.view(B, Co, *[(d + 2 * p - dl * (k - 1) - 1) // s_ + 1 for d, p, dl, k, s_ in zip((H, W), pad, dil, (R, S), st)])
+                got = lof.lof_conv2d(x, w, pad[0], pad[1], st[0], st[1], dil[0], dil[1], mant, mode, 0, ws, xs_, groups=grp, k_order=order, kc=kc)
+                assert got.shape == want.shape and torch.equal(got, want), (B, Ci, H, W, Co, R, S, order, mant)
+                got_b = lof.lof_conv2d(x, w, pad[0], pad[1], st[0], st[1], dil[0], dil[1], mant, mode, 0, ws, xs_, groups=grp, k_order=order,
+                                       kc=kc, bias=bias)
+                assert torch.equal(got_b, want + bias.view(1, -1, 1, 1))
+    # against the CPU oracle (pinned to bli_sgemm + lof_sgemm_ukr): last case, image 0
+    w0, x0 = _np(wcol[0]), _np(cols[0, 0])
+    got = lof.lof_conv2d(x, w, pad[0], pad[1], st[0], st[1], dil[0], dil[1], 10, k_order="crs", kc=256)
+    assert L.bits_equal(_np(got[0].reshape(Co, -1)), L.o_gemm(w0, x0, 10, L.RNE, kc=256))
+    # accum_mant_bits = 23 on exactly summable data == torch's conv
+    xi = torch.randint(-4, 5, (2, 8, 10, 10), device=cuda_dev, generator=g).float()
+    wi = torch.randint(-4, 5, (12, 8, 3, 3), device=cuda_dev, generator=g).float()
+    assert torch.equal(lof.lof_conv2d(xi, wi, 1, 1, 1, 1, 1, 1, 23), F.conv2d(xi.double(), wi.double(), padding=1).float())
+    with pytest.raises(RuntimeError):
+        lof.lof_conv2d(xi, wi[:, :4], 1, 1, 1, 1, 1, 1, 10)                                   # C_in mismatch (Lof_kernel.cu:175)
+    with pytest.raises(RuntimeError):
+        lof.lof_conv2d(xi[:, :, :2, :2], wi, 0, 0, 1, 1, 1, 1, 10)                            # window does not fit (Lof_kernel.cu:196)
+
+    # fused linear
+    for (lead, K, N) in (((4, 9), 96, 50), ((130,), 257, 64), ((1,), 16, 3)):
+        x = torch.rand(*lead, K, device=cuda_dev, generator=g) * 2 - 1
+        wt = torch.rand(N, K, device=cuda_dev, generator=g) * 2 - 1
+        bias = torch.randn(N, device=cuda_dev, generator=g)
+        for mant, mode, kc in ((10, L.RNE, None), (5, L.RTZ, 0)):
+            want = lof.lof_gemm(x.reshape(-1, K), wt.t().contiguous(), mant, mode, 0, 2.0, 0.5, kc=kc).reshape(*lead, N)
+            assert torch.equal(lof.lof_linear(x, wt, None, mant, mode, 0, 2.0, 0.5, kc=kc), want)
+            assert torch.equal(lof.lof_linear(x, wt, bias, mant, mode, 0, 2.0, 0.5, kc=kc), want + bias)
+
+
+def test_exact_gemm_optimistic_chain_equals_exact_routines(lof, cuda_dev):
+    """The per-FMA GEMM's default kernel runs a branch-free chain (RZ FMA | inexact, rounding on the signed pattern) and
+    falls back per tile to the exact routines when an intermediate reaches 2^127 / inf / NaN.  It must equal the exact
+    routines (gemm.fast = 0, the kernel pinned to bli_sgemm + lof_sgemm_ukr) bit for bit: all 15 modes, accumulator widths
+    incl. r = 0, panels, data with exact cancellations, subnormal products, overflowing sums, infinities and NaNs."""
+    g = torch.Generator(device=cuda_dev).manual_seed(77)
+    M, K, N = 96, 200, 130
+
+    def operands(kind):
+        A = torch.randn(M, K, device=cuda_dev, generator=g)
+        B = torch.randn(K, N, device=cuda_dev, generator=g)
+        if kind == "cancel":                                  # small integers: exact sums, exact zeros of both signs
+            A, B = torch.round(A * 2), torch.round(B * 2)
+            A[::7] = -0.0
+        elif kind == "tiny":                                  # products in the fp32 subnormal range
+            A, B = A * 1e-22, B * 1e-22
+        elif kind == "tiny_some":                             # a few operands below 2^-40: only their tiles fall back
+            A[5, ::3] *= 1e-30
+            B[::5, 77] *= 1e-25
+        elif kind == "huge":                                  # sums beyond FLT_MAX in some tiles only
+            A[:10] *= 1e19
+            B[:, :10] *= 1e19
+        elif kind == "special":
+            A[3, 5], A[40, 7], B[9, 100] = float("inf"), float("nan"), float("-inf")
+            A[70, :] *= 3e19
+            B[:, 64:70] *= 3e19
+        return A, B
+
+    try:
+        for kind in ("plain", "cancel", "tiny", "tiny_some", "huge", "special"):
+            A, B = operands(kind)
+            for mode in range(15):
+                sl = 3 if mode in (L.SR_A, L.SR_B, L.SR_C, L.SR_D) else 0
+                for mant, kc in ((10, 256), (23, 0), (2, 64), (0, 0), (1, 32)) if mode in (L.RNE, L.RTZ, L.SR_A, L.RU) else ((7, 0),):
+                    lof.manual_seed(5)
+                    lof.set_option("gemm.fast", 1)
+                    fast = lof.lof_gemm(A, B, mant, mode, sl, kc=kc)
+                    lof.manual_seed(5)
+                    lof.set_option("gemm.fast", 0)
+                    exact = lof.lof_gemm(A, B, mant, mode, sl, kc=kc)
+                    assert L.bits_equal(_np(fast), _np(exact)), (kind, mode, mant, kc)
+                    if mode == L.RNE:                                              # the two-FMA flavour of the RNE chain
+                        lof.set_option("gemm.fast", 2)
+                        assert L.bits_equal(_np(lof.lof_gemm(A, B, mant, mode, sl, kc=kc)), _np(exact)), (kind, mant, kc, "fast=2")
+    finally:
+        lof.set_option("gemm.fast", 1)
+
+
+def test_exact_gemm_float_domain_rne_selftest(lof, cuda_dev):
+    """(t + K) - K == round_bits<RNE> + mask for every normal fp32 pattern x every accumulator width, and every out-of-range
+    pattern surfaces as NaN (the fallback trigger): device self-test over 2^32 x 22 cases (the chain is not used for a 0-bit mantissa, where it differs)."""
+    from lofloat_b200 import _lib
+    bad = torch.zeros(1, dtype=torch.int64, device=cuda_dev)
+    _lib.check(_lib.lib().lof_selftest_gemm_rne_round(bad.data_ptr(), None), "selftest")
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0
