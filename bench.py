@@ -335,7 +335,36 @@ def side_measurements(torch, lib, _lib, dev, x, y, stream):
         b.record()
         torch.cuda.synchronize()
         out["lof_gemm_exact_2048^3_accum10_RNE_kc256"] = {"TFLOPs": 2.0 * M * N * K * 3 / (a.elapsed_time(b) * 1e-3) / 1e12,
-                                                        "note": "per-FMA rounding, SIMT (bit-exact vs BLIS reference)"}
+                                                        "note": "per-FMA rounding, SIMT (bit-exact vs BLIS reference); bound of the chain: "
+                                                                "12 clk per warp-MAC and SMSP = 6.06 TFLOP/s at 1.92 GHz"}
+        # row f-3: Conv2d as an implicit GEMM on the same kernel (ResNet-style 3x3 layer) vs the reference's composition
+        import lofloat_b200 as lof
+        import torch.nn.functional as F
+        Bn, Ci, Hh, Co = 32, 64, 56, 64
+        e4m3 = lof.create_p3109_params(8, 4, bias=7)
+        cx = lof.virtual_round(torch.randn(Bn, Ci, Hh, Hh, device=dev), e4m3)
+        cw = lof.virtual_round(torch.randn(Co, Ci, 3, 3, device=dev) * 0.1, e4m3)
+        cbias = torch.randn(Co, device=dev)
+
+        def composed():                                  # LoF_Conv2d im2col backend, LoFloat/layers.py:710-751
+            cols = F.unfold(cx, (3, 3), padding=1)
+            wc = cw.view(Co, -1)
+            o = torch.stack([lof.lof_gemm(wc, cols[i].contiguous(), 10, kc=0) for i in range(Bn)]).view(Bn, Co, Hh, Hh)
+            return o + cbias.view(1, -1, 1, 1)
+
+        fused = lambda: lof.lof_conv2d(cx, cw, 1, 1, 1, 1, 1, 1, 10, k_order="crs", bias=cbias)
+        same = bool(torch.equal(composed(), fused()))
+        for name, fn in (("unfold_plus_per_image_lof_gemm", composed), ("lof_conv2d_implicit_gemm", fused)):
+            fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / 3
+            out[f"conv3x3_32x64x56x56_to_64_accum10_{name}"] = {"ms": ms, "TFLOPs": 2.0 * Bn * Co * Hh * Hh * Ci * 9 / ms / 1e9,
+                                                                "bit_identical": same}
     except Exception as exc:
         out["lof_gemm_error"] = str(exc)
     try:

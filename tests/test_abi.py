@@ -86,6 +86,43 @@ def test_validation_without_gpu(lib):
     assert lib.lof_round_params(None, None, 0, 0, C.byref(f), C.byref(ps), 1.0, None, 0, None) == 0
 
 
+def test_conv2d_geometry_and_validation_without_gpu(lib):
+    """lof_conv2d_out_size == the reference's P / Q formula (Lof_kernel.cu:194-195) == torch's conv output shape; the conv /
+    linear entry points validate their arguments before touching a device."""
+    import torch.nn.functional as F
+    from lofloat_b200._lib import CConv2d, CProjSpec, LOF_ERR_INVALID_ARG, LOF_ERR_UNSUPPORTED, LOF_CONV_K_CRS
+    out = C.c_int64(0)
+    for (h, k, p, s, d) in ((12, 3, 1, 1, 1), (17, 3, 2, 2, 1), (9, 5, 3, 3, 2), (31, 3, 4, 2, 1), (224, 7, 3, 2, 1), (5, 1, 0, 1, 1)):
+        assert lib.lof_conv2d_out_size(h, k, p, s, d, C.byref(out)) == 0
+        want = F.conv2d(torch.zeros(1, 1, h, h), torch.zeros(1, 1, k, k), padding=p, stride=s, dilation=d).shape[-1]
+        assert out.value == want == (h + 2 * p - d * (k - 1) - 1) // s + 1
+    assert lib.lof_conv2d_out_size(2, 3, 0, 1, 1, C.byref(out)) == 0 and out.value == 0          # window does not fit
+    assert lib.lof_conv2d_out_size(8, 3, 0, 0, 1, C.byref(out)) == LOF_ERR_INVALID_ARG
+    ps = CProjSpec(0, 0, 0)
+    geo = CConv2d(1, 8, 10, 10, 16, 3, 3, 1, 1, 1, 1, 1, 1, 1, LOF_CONV_K_CRS)
+    assert lib.lof_conv2d_f32(None, None, None, None, None, 10, C.byref(ps), 0, 1.0, None, None) == LOF_ERR_INVALID_ARG
+    bad = CConv2d(1, 8, 10, 10, 16, 3, 3, 1, 1, 1, 1, 1, 1, 3, LOF_CONV_K_CRS)                    # groups must divide C_in / C_out
+    assert lib.lof_conv2d_f32(None, None, None, None, C.byref(bad), 10, C.byref(ps), 0, 1.0, None, None) == LOF_ERR_INVALID_ARG
+    bad = CConv2d(1, 8, 2, 2, 16, 3, 3, 0, 0, 1, 1, 1, 1, 1, LOF_CONV_K_CRS)
+    assert lib.lof_conv2d_f32(None, None, None, None, C.byref(bad), 10, C.byref(ps), 0, 1.0, None, None) == LOF_ERR_INVALID_ARG
+    assert b"non-positive output spatial size" in lib.lof_last_error_string()
+    bad = CConv2d(1, 8, 10, 10, 16, 3, 3, 1, 1, 1, 1, 1, 1, 1, 7)                                 # unknown reduction order
+    assert lib.lof_conv2d_f32(None, None, None, None, C.byref(bad), 10, C.byref(ps), 0, 1.0, None, None) == LOF_ERR_INVALID_ARG
+    assert lib.lof_conv2d_f32(None, None, None, None, C.byref(geo), 24, C.byref(ps), 0, 1.0, None, None) == LOF_ERR_INVALID_ARG
+    geo0 = CConv2d(0, 8, 10, 10, 16, 3, 3, 1, 1, 1, 1, 1, 1, 1, LOF_CONV_K_CRS)                   # empty batch: no-op, no device needed
+    assert lib.lof_conv2d_f32(None, None, None, None, C.byref(geo0), 10, C.byref(ps), 0, 1.0, None, None) == 0
+    assert lib.lof_linear_f32(None, None, None, None, -1, 4, 4, 10, C.byref(ps), 0, 1.0, None, None) == LOF_ERR_INVALID_ARG
+    assert lib.lof_linear_f32(None, None, None, None, 0, 4, 4, 10, C.byref(ps), 0, 1.0, None, None) == 0
+    assert lib.lof_linear_f32(None, None, None, None, 1 << 31, 4, 4, 10, C.byref(ps), 0, 1.0, None, None) == LOF_ERR_UNSUPPORTED
+    import lofloat_b200 as lof
+    with pytest.raises(RuntimeError, match="CUDA tensors"):
+        lof.lof_conv2d(torch.zeros(1, 8, 10, 10), torch.zeros(16, 8, 3, 3), 1, 1, 1, 1, 1, 1, 10)
+    with pytest.raises(RuntimeError, match="4-D"):
+        lof.lof_conv2d(torch.zeros(8, 10, 10), torch.zeros(16, 8, 3, 3), 1, 1, 1, 1, 1, 1, 10)
+    with pytest.raises(RuntimeError, match="incompatible shapes"):
+        lof.lof_linear(torch.zeros(4, 7), torch.zeros(5, 8), None, 10)
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_compute_without_gpu_fails_loudly(lib):
     import lofloat_b200 as lof
