@@ -301,8 +301,11 @@ LOF_API int lof_round_strict_f32(const float* in, float* out, int64_t n, const l
 /* Chunked tensor-core GEMM on operands that are ALREADY stored as 8-bit representations (what lof_encode_f32
  * produces for e4m3fn / e5m2): A is M x K bytes row-major, Bt is N x K bytes row-major (B transposed, K-major --
  * the [out_features, in_features] weight layout of LoF_Linear, LoFloat/layers.py:160-161).  operand_dtype is
- * LOF_E4M3 or LOF_E5M2.  Same accumulator semantics, flags and status word as lof_gemm_chunked_f32; no conversion
- * pass and no workspace for the operands.  K must be a multiple of 16. */
+ * LOF_E4M3 or LOF_E5M2 -- or LOF_BF16, in which case A and Bt hold bf16 words (M x K and N x K, 2 bytes each): the
+ * form in which MX-rounded operands (an e4m3 / e5m2 / e3m2 / e2m1 value times a power-of-two block scale is exact in
+ * bf16) travel between GPUs at half the fp32 volume (sharding.gemm_2d_packed).  Same accumulator semantics, flags and
+ * status word as lof_gemm_chunked_f32; no conversion pass and no workspace for the operands.  K * sizeof(operand) must be
+ * a multiple of 16. */
 LOF_API int lof_gemm_chunked_packed(const uint8_t* A, const uint8_t* Bt, float* C, int64_t M, int64_t N, int64_t K,
                                     int accum_mant_bits, const lof_format_t* acc_fmt, const lof_projspec_t* ps,
                                     int64_t k_chunk, float alpha, int operand_dtype, uint32_t flags, int32_t* dev_status,

@@ -750,8 +750,8 @@ int lof_gemm_chunked_packed(const uint8_t* A, const uint8_t* Bt, float* C, int64
                             int accum_mant_bits, const lof_format_t* acc_fmt, const lof_projspec_t* ps, int64_t k_chunk,
                             float alpha, int operand_dtype, uint32_t flags, int32_t* dev_status, void* stream)
 {
-    if (operand_dtype != LOF_E4M3 && operand_dtype != LOF_E5M2)
-        return fail(LOF_ERR_INVALID_ARG, "lof_gemm_chunked_packed: operand_dtype must be LOF_E4M3 or LOF_E5M2");
+    if (operand_dtype != LOF_E4M3 && operand_dtype != LOF_E5M2 && operand_dtype != LOF_BF16)
+        return fail(LOF_ERR_INVALID_ARG, "lof_gemm_chunked_packed: operand_dtype must be LOF_E4M3, LOF_E5M2 or LOF_BF16");
     if (flags & LOF_GEMM_INTERNAL_PACKED_OPERANDS) return fail(LOF_ERR_INVALID_ARG, "unknown flag");
     return lof_gemm_chunked_f32(reinterpret_cast<const float*>(A), reinterpret_cast<const float*>(Bt), C, M, N, K, accum_mant_bits,
                                 acc_fmt, ps, k_chunk, alpha, operand_dtype, flags | LOF_GEMM_INTERNAL_PACKED_OPERANDS, dev_status, stream);

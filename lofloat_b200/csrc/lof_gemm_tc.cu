@@ -565,10 +565,10 @@ cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, 
     if (M > (1 << 24) || N > (1 << 24) || K > (1ll << 30)) { *err = "chunked GEMM: dimension too large"; return cudaSuccess; }
     if (mode_uses_rng(mode)) { *err = "chunked GEMM: stochastic accumulator rounding is not implemented"; return cudaSuccess; }
 
-    // operands already stored as 8-bit representations (lof_gemm_chunked_packed): A = M x K bytes, B = Bt = N x K bytes
+    // operands already stored in the tensor core's operand type (lof_gemm_chunked_packed): A = M x K, B = Bt = N x K, e4m3 / e5m2
+    // bytes or bf16 words
     const bool packed_in = (flags & LOF_GEMM_INTERNAL_PACKED_OPERANDS) != 0;
     if (packed_in) {
-        if (op == kOpBF16) { *err = "chunked GEMM (packed operands): operand_dtype must be LOF_E4M3 or LOF_E5M2"; return cudaSuccess; }
         if (((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15u) != 0) {
             *err = "chunked GEMM (packed operands): A and Bt must be 16-byte aligned (TMA)"; return cudaSuccess;
         }

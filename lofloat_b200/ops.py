@@ -671,10 +671,17 @@ def lof_gemm_packed(A: torch.Tensor, Bt: torch.Tensor, accum_mant_bits: int, rou
                     accum_format: FloatFormatDescriptor | None = None, operand_dtype: str = "e4m3",
                     partial_round: bool = False, allow_packed: bool = True, allow_hw_accum: bool = True,
                     allow_pair: bool = True) -> torch.Tensor:
-    """Chunked tensor-core GEMM on operands already stored as OCP 8-bit representations (uint8): A is [M, K], Bt is
+    """Chunked tensor-core GEMM on operands already stored in the tensor core's operand type: OCP 8-bit representations
+    (uint8, operand_dtype "e4m3" / "e5m2") or bfloat16 tensors (operand_dtype is then "bf16").  A is [M, K], Bt is
     [N, K] (the [out_features, in_features] weight layout).  C = A @ Bt^T / (scale_a * scale_b), float32 [M, N]."""
-    if A.dtype != torch.uint8 or Bt.dtype != torch.uint8 or A.dim() != 2 or Bt.dim() != 2:
-        raise RuntimeError("lof_gemm_packed: A and Bt must be 2-D uint8 tensors")
+    if A.dtype == torch.bfloat16 and Bt.dtype == torch.bfloat16:
+        operand_dtype = "bf16"
+    elif A.dtype != torch.uint8 or Bt.dtype != torch.uint8:
+        raise RuntimeError("lof_gemm_packed: A and Bt must both be uint8 (8-bit representations) or both bfloat16")
+    elif operand_dtype == "bf16":
+        raise RuntimeError("lof_gemm_packed: operand_dtype 'bf16' needs bfloat16 tensors")
+    if A.dim() != 2 or Bt.dim() != 2:
+        raise RuntimeError("lof_gemm_packed: A and Bt must be 2-D")
     if A.size(1) != Bt.size(1):
         raise RuntimeError(f"lof_gemm_packed: A.cols ({A.size(1)}) != Bt.cols ({Bt.size(1)})")
     if not (A.is_cuda and Bt.is_cuda):

@@ -178,3 +178,35 @@ def gemm_2d(A_local: torch.Tensor, B_local: torch.Tensor, grid: GemmGrid, M: int
     B_panel = recv.reshape(K, nc)
     return gemm_fn(A_panel, B_panel, accum_mant_bits, round_mode, stochastic_rounding_bits, scale_a, scale_b,
                    **gemm_kwargs)
+
+
+def gemm_2d_packed(A_local: torch.Tensor, Bt_local: torch.Tensor, grid: GemmGrid, M: int, N: int, K: int,
+                   accum_mant_bits: int, round_mode=0, scale_a: float = 1.0, scale_b: float = 1.0,
+                   gemm_fn: Optional[Callable] = None, **gemm_kwargs) -> torch.Tensor:
+    """gemm_2d for operands that already are in the tensor core's operand type (bf16, or uint8 e4m3 / e5m2
+    representations) with the second operand in the weight layout: A_local = this rank's rows of A ([M/W, K]), Bt_local =
+    this rank's rows of B^T ([N/W, K]) under 1-D row partitions over the world.  Half (bf16) or a quarter (8-bit) of the
+    fp32 exchange volume, no transposes, and both panels are unions of whole row shards:
+      A row panel r    = shards of ranks r*C .. r*C + C - 1      -> all-gather inside the row group
+      Bt column panel c = shards of ranks c*R .. c*R + R - 1      -> one all-to-all in which shard s goes to column s // R
+    Returns this rank's block C[r*M/R:(r+1)*M/R, c*N/C:(c+1)*N/C] (fp32)."""
+    if gemm_fn is None:
+        from .ops import lof_gemm_packed as gemm_fn
+    W, R, Cn = grid.world_size, grid.R, grid.C
+    if M % W or N % W:
+        raise ValueError(f"gemm_2d_packed needs M % world == 0 and N % world == 0 (M={M}, N={N}, grid={R}x{Cn})")
+    if tuple(A_local.shape) != (M // W, K) or tuple(Bt_local.shape) != (N // W, K):
+        raise ValueError("gemm_2d_packed: local operand shapes do not match the 1-D row partitions")
+    if W == 1:
+        return gemm_fn(A_local, Bt_local, accum_mant_bits, round_mode, scale_a, scale_b, **gemm_kwargs)
+    A_panel = torch.empty((M // R, K), dtype=A_local.dtype, device=A_local.device)
+    dist.all_gather_into_tensor(A_panel, A_local.contiguous(), group=grid.row_group)
+    rows = N // W
+    my_col = grid.rank // R                                    # the column panel this rank's Bt shard belongs to
+    dsts = [d for d in range(W) if d % Cn == my_col]            # the R ranks that own a block in that column
+    send = Bt_local.contiguous().unsqueeze(0).expand(len(dsts), rows, K).reshape(len(dsts) * rows, K)
+    in_split = [rows if d % Cn == my_col else 0 for d in range(W)]
+    out_split = [rows if s // R == grid.c else 0 for s in range(W)]
+    Bt_panel = torch.empty((N // Cn, K), dtype=Bt_local.dtype, device=Bt_local.device)
+    dist.all_to_all_single(Bt_panel, send.contiguous(), out_split, in_split, group=grid.world_group)
+    return gemm_fn(A_panel, Bt_panel, accum_mant_bits, round_mode, scale_a, scale_b, **gemm_kwargs)

@@ -66,6 +66,20 @@ def main():
                      B[:512, :m2][rank * (512 // world):(rank + 1) * (512 // world)].contiguous(), grid, m2, m2, 512, 10)
     r0, c0 = grid.r * (m2 // grid.R), grid.c * (m2 // grid.C)
     report(f"gemm_2d {grid.R}x{grid.C} exact per-FMA mode == single GPU", torch.equal(Cblk, Cfull[r0:r0 + m2 // grid.R, c0:c0 + m2 // grid.C]))
+    # packed-operand exchange: MX-rounded operands travel as bf16 (exact), second operand in the weight layout [N, K]
+    e4m3, e8m0 = lof.create_p3109_params(8, 4, bias=7), lof.create_e8m0_params()
+    # (.bfloat16().float(): the reference's saturating virtual_round leaves a block's overflowing maxima UNROUNDED, SURVEY
+    #  Appendix B, so a few MX-rounded elements are arbitrary fp32 values; both paths get the same bf16-exact operands)
+    Aq = lof.virtual_mx_round(torch.randn(M, K, device=dev, generator=g), 32, e4m3, e8m0).bfloat16().float()
+    Wq = lof.virtual_mx_round(torch.randn(N, K, device=dev, generator=g), 32, e4m3, e8m0).bfloat16().float()
+    exact_bf16 = torch.equal(Aq.bfloat16().float(), Aq) and torch.equal(Wq.bfloat16().float(), Wq)
+    Cfull = lof.lof_gemm(Aq, Wq.t().contiguous(), 7, k_chunk=32, operand_dtype="bf16", partial_round=True)
+    Cblk = S.gemm_2d_packed(Aq[rank * (M // world):(rank + 1) * (M // world)].bfloat16().contiguous(),
+                            Wq[rank * (N // world):(rank + 1) * (N // world)].bfloat16().contiguous(), grid, M, N, K, 7,
+                            k_chunk=32, partial_round=True)
+    r0, c0 = grid.r * (M // grid.R), grid.c * (N // grid.C)
+    report(f"gemm_2d_packed {grid.R}x{grid.C} (bf16 exchange of MX-rounded operands, exact: {exact_bf16}) == single GPU fp32-container GEMM",
+           exact_bf16 and torch.equal(Cblk, Cfull[r0:r0 + M // grid.R, c0:c0 + N // grid.C]))
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:

@@ -781,6 +781,13 @@ def test_gemm_on_packed_operands_equals_fp32_container_path(lof, cuda_dev):
         want = lof.lof_gemm(_gpu(A, cuda_dev), _gpu(B, cuda_dev), mant, **kw)
         got = lof.lof_gemm_packed(Ap, Btp, mant, **kw)
         assert torch.equal(got, want), kw
+    # bf16 words as the packed operand type (how MX-rounded operands travel between GPUs, sharding.gemm_2d_packed)
+    Ab, Btb = _gpu(A, cuda_dev).bfloat16(), _gpu(np.ascontiguousarray(B.T), cuda_dev).bfloat16()
+    for kw, mant in ((dict(k_chunk=32, partial_round=True), 7), (dict(k_chunk=64), 7), (dict(k_chunk=0), 10)):
+        want = lof.lof_gemm(_gpu(A, cuda_dev), _gpu(B, cuda_dev), mant, operand_dtype="bf16", **kw)
+        assert torch.equal(lof.lof_gemm_packed(Ab, Btb, mant, **kw), want), ("bf16", kw)
+    with pytest.raises(RuntimeError):
+        lof.lof_gemm_packed(Ab, Btp, 7)
 
 
 def test_pack_fast_path_equals_exact_every_fp32_pattern(lof, cuda_dev):

@@ -175,7 +175,7 @@ def _worker(rank, world, port, q):
         m_loc = sh.sharded_virtual_mx_round(local, shard, 32, p, e8, mx_fn=_np_mx)
         m = sh.gather_rows(m_loc, shard, world)
         ok_mx = torch.equal(m.view(torch.int32), _np_mx(full, 32, p, e8, 0, 0, 0).view(torch.int32))
-        # 2-D GEMM: 1x2 grid at world 2
+        # 2-D GEMM: 1x2 grid at world 2, 2x2 at world 4
         M, N, K = 8, 12, 300
         A = torch.rand(M, K, generator=g) * 2 - 1
         B = torch.rand(K, N, generator=g) * 2 - 1
@@ -187,23 +187,34 @@ def _worker(rank, world, port, q):
         r, c = grid.r, grid.c
         want = C_full[r * (M // grid.R):(r + 1) * (M // grid.R), c * (N // grid.C):(c + 1) * (N // grid.C)]
         ok_gemm = torch.equal(C_blk.view(torch.int32), want.contiguous().view(torch.int32))
+        # the same product through the packed-operand exchange (operands row-sharded as A [M/W, K] and B^T [N/W, K])
+        M2, N2 = 4 * world, 6 * world
+        A2 = torch.rand(M2, K, generator=g) * 2 - 1
+        Bt2 = torch.rand(N2, K, generator=g) * 2 - 1
+        C2_blk = sh.gemm_2d_packed(A2[rank * 4:(rank + 1) * 4].contiguous(), Bt2[rank * 6:(rank + 1) * 6].contiguous(), grid, M2, N2, K, 10,
+                                   gemm_fn=lambda a, bt, bits, mode, sa, sb, **kw: _np_gemm(a, bt.t().contiguous(), bits, mode, 0, sa, sb))
+        C2_full = _np_gemm(A2, Bt2.t().contiguous(), 10, 0, 0, 1.0, 1.0)
+        want2 = C2_full[r * (M2 // grid.R):(r + 1) * (M2 // grid.R), c * (N2 // grid.C):(c + 1) * (N2 // grid.C)]
+        ok_gemm = ok_gemm and torch.equal(C2_blk.view(torch.int32), want2.contiguous().view(torch.int32))
         q.put((rank, ok_round, ok_mx, ok_gemm, (grid.R, grid.C)))
     finally:
         dist.destroy_process_group()
 
 
-def test_sharding_world2_gloo(lof):
+@pytest.mark.parametrize("world,want_grid", [(2, (1, 2)), (4, (2, 2))])
+def test_sharding_gloo(lof, world, want_grid):
+    """world 2 (1 x 2 grid) and world 4 (2 x 2: row AND column panels are real unions of shards)."""
     L.build_oracle()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=180) for _ in range(2)]
+    res = [q.get(timeout=240) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     for rank, ok_round, ok_mx, ok_gemm, grid in res:
         assert ok_round and ok_mx and ok_gemm, (rank, ok_round, ok_mx, ok_gemm)
-        assert grid == (1, 2)
+        assert grid == want_grid
