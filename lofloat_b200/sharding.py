@@ -182,14 +182,15 @@ def gemm_2d(A_local: torch.Tensor, B_local: torch.Tensor, grid: GemmGrid, M: int
 
 def gemm_2d_packed(A_local: torch.Tensor, Bt_local: torch.Tensor, grid: GemmGrid, M: int, N: int, K: int,
                    accum_mant_bits: int, round_mode=0, scale_a: float = 1.0, scale_b: float = 1.0,
-                   gemm_fn: Optional[Callable] = None, **gemm_kwargs) -> torch.Tensor:
+                   gemm_fn: Optional[Callable] = None, overlap: bool = True, **gemm_kwargs) -> torch.Tensor:
     """gemm_2d for operands that already are in the tensor core's operand type (bf16, or uint8 e4m3 / e5m2
     representations) with the second operand in the weight layout: A_local = this rank's rows of A ([M/W, K]), Bt_local =
     this rank's rows of B^T ([N/W, K]) under 1-D row partitions over the world.  Half (bf16) or a quarter (8-bit) of the
     fp32 exchange volume, no transposes, and both panels are unions of whole row shards:
       A row panel r    = shards of ranks r*C .. r*C + C - 1      -> all-gather inside the row group
       Bt column panel c = shards of ranks c*R .. c*R + R - 1      -> one all-to-all in which shard s goes to column s // R
-    Returns this rank's block C[r*M/R:(r+1)*M/R, c*N/C:(c+1)*N/C] (fp32)."""
+    With overlap=True (default) the all-gather of A runs while the rows of C that need only this rank's own A shard are
+    being computed.  Returns this rank's block C[r*M/R:(r+1)*M/R, c*N/C:(c+1)*N/C] (fp32)."""
     if gemm_fn is None:
         from .ops import lof_gemm_packed as gemm_fn
     W, R, Cn = grid.world_size, grid.R, grid.C
@@ -199,8 +200,6 @@ def gemm_2d_packed(A_local: torch.Tensor, Bt_local: torch.Tensor, grid: GemmGrid
         raise ValueError("gemm_2d_packed: local operand shapes do not match the 1-D row partitions")
     if W == 1:
         return gemm_fn(A_local, Bt_local, accum_mant_bits, round_mode, scale_a, scale_b, **gemm_kwargs)
-    A_panel = torch.empty((M // R, K), dtype=A_local.dtype, device=A_local.device)
-    dist.all_gather_into_tensor(A_panel, A_local.contiguous(), group=grid.row_group)
     rows = N // W
     my_col = grid.rank // R                                    # the column panel this rank's Bt shard belongs to
     dsts = [d for d in range(W) if d % Cn == my_col]            # the R ranks that own a block in that column
@@ -208,5 +207,22 @@ def gemm_2d_packed(A_local: torch.Tensor, Bt_local: torch.Tensor, grid: GemmGrid
     in_split = [rows if d % Cn == my_col else 0 for d in range(W)]
     out_split = [rows if s // R == grid.c else 0 for s in range(W)]
     Bt_panel = torch.empty((N // Cn, K), dtype=Bt_local.dtype, device=Bt_local.device)
-    dist.all_to_all_single(Bt_panel, send.contiguous(), out_split, in_split, group=grid.world_group)
-    return gemm_fn(A_panel, Bt_panel, accum_mant_bits, round_mode, scale_a, scale_b, **gemm_kwargs)
+    A_panel = torch.empty((M // R, K), dtype=A_local.dtype, device=A_local.device)
+    A_own = A_local.contiguous()
+    if not overlap:
+        dist.all_gather_into_tensor(A_panel, A_own, group=grid.row_group)
+        dist.all_to_all_single(Bt_panel, send.contiguous(), out_split, in_split, group=grid.world_group)
+        return gemm_fn(A_panel, Bt_panel, accum_mant_bits, round_mode, scale_a, scale_b, **gemm_kwargs)
+    # overlapped: B^T first (every output needs all of it), then the rows of C that come from this rank's OWN A shard are
+    # computed while the other A shards of the row panel are still in flight (output rows are independent)
+    w_b = dist.all_to_all_single(Bt_panel, send.contiguous(), out_split, in_split, group=grid.world_group, async_op=True)
+    w_a = dist.all_gather_into_tensor(A_panel, A_own, group=grid.row_group, async_op=True)
+    mw = M // W
+    parts = [None] * Cn
+    w_b.wait()
+    parts[grid.c] = gemm_fn(A_own, Bt_panel, accum_mant_bits, round_mode, scale_a, scale_b, **gemm_kwargs)
+    w_a.wait()
+    for j in range(Cn):
+        if j != grid.c:
+            parts[j] = gemm_fn(A_panel[j * mw:(j + 1) * mw], Bt_panel, accum_mant_bits, round_mode, scale_a, scale_b, **gemm_kwargs)
+    return torch.cat(parts, dim=0)

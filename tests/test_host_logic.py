@@ -196,6 +196,10 @@ def _worker(rank, world, port, q):
         C2_full = _np_gemm(A2, Bt2.t().contiguous(), 10, 0, 0, 1.0, 1.0)
         want2 = C2_full[r * (M2 // grid.R):(r + 1) * (M2 // grid.R), c * (N2 // grid.C):(c + 1) * (N2 // grid.C)]
         ok_gemm = ok_gemm and torch.equal(C2_blk.view(torch.int32), want2.contiguous().view(torch.int32))
+        C2_seq = sh.gemm_2d_packed(A2[rank * 4:(rank + 1) * 4].contiguous(), Bt2[rank * 6:(rank + 1) * 6].contiguous(), grid, M2, N2, K, 10,
+                                   overlap=False,
+                                   gemm_fn=lambda a, bt, bits, mode, sa, sb, **kw: _np_gemm(a, bt.t().contiguous(), bits, mode, 0, sa, sb))
+        ok_gemm = ok_gemm and torch.equal(C2_seq.view(torch.int32), C2_blk.view(torch.int32))
         q.put((rank, ok_round, ok_mx, ok_gemm, (grid.R, grid.C)))
     finally:
         dist.destroy_process_group()
