@@ -58,6 +58,7 @@ struct Options {
     std::atomic<int64_t> stream_ctas_per_sm{8};  // codec / strict rounding / MX storage / fused Hadamard kernels: ALU-heavier, they want full residency (scripts/stream_tune.py)
     std::atomic<int64_t> host_chunk_bytes{32ll << 20};
     std::atomic<int64_t> pack_fast{1};           // storage codec: 0 = exact integer routine only, 1 = magic-add fast path where eligible
+    std::atomic<int64_t> bf16_fast{2};           // bf16 containers on the magic path: 2 = unchecked kinds where the fp32 path is unchecked, 1 = always checked
     std::atomic<int64_t> gemm_fast{1};           // exact GEMM: 1 = optimistic branch-free chain with a per-tile fallback, 0 = exact routines only
     std::atomic<int64_t> round_fast{2};          // 0: exact kernels; 1: branch-free fast path; 2: + magic-add path (default)
 } g_opt;
@@ -273,7 +274,11 @@ int round_common(bool params, const void* in, void* out, int64_t n, int dtype, c
                 if (mode_uses_rng(mode)) { kind = kKindParams; std::memset(&fast, 0, sizeof fast); }     // stochastic: magic path or nothing
                 if (fast_opt >= 2) {
                     magic = make_magic_plan(p32, mode);
-                    if (magic.valid) kind = p32.saturating ? kKindMagicSatChk : kKindMagicExtChk;
+                    if (magic.valid) {
+                        // checked kinds only where the fp32 path itself needs them (wide targets, stochastic offsets) or bf16.fast = 1
+                        const bool chk = magic.lo_rare != 0u || magic.limit != 0xFFFFFFFFu || mode_uses_rng(mode) || g_opt.bf16_fast.load() < 2;
+                        kind = chk ? (p32.saturating ? kKindMagicSatChk : kKindMagicExtChk) : (p32.saturating ? kKindMagicSat : kKindMagicExt);
+                    }
                 }
             }
         }
@@ -527,6 +532,7 @@ int lof_set_option(const char* key, int64_t value)
     else if (k == "round.fast") { if (value < 0 || value > 2) return fail(LOF_ERR_INVALID_ARG, "round.fast must be 0, 1 or 2"); g_opt.round_fast = value; }
     else if (k == "stream.ctas_per_sm") { if (value < 1 || value > 64) return fail(LOF_ERR_INVALID_ARG, "stream.ctas_per_sm out of range"); g_opt.stream_ctas_per_sm = value; }
     else if (k == "pack.fast") { if (value < 0 || value > 1) return fail(LOF_ERR_INVALID_ARG, "pack.fast must be 0 or 1"); g_opt.pack_fast = value; }
+    else if (k == "bf16.fast") { if (value < 1 || value > 2) return fail(LOF_ERR_INVALID_ARG, "bf16.fast must be 1 or 2"); g_opt.bf16_fast = value; }
     else if (k == "gemm.fast") { if (value < 0 || value > 2) return fail(LOF_ERR_INVALID_ARG, "gemm.fast must be 0, 1 or 2"); g_opt.gemm_fast = value; }
     else if (k == "host.chunk_bytes") { if (value < (1 << 16)) return fail(LOF_ERR_INVALID_ARG, "host.chunk_bytes too small"); g_opt.host_chunk_bytes = value; }
     else return fail(LOF_ERR_INVALID_ARG, "unknown option: " + k);
@@ -545,6 +551,7 @@ int lof_get_option(const char* key, int64_t* value)
     else if (k == "stream.ctas_per_sm") *value = g_opt.stream_ctas_per_sm;
     else if (k == "pack.fast") *value = g_opt.pack_fast;
     else if (k == "gemm.fast") *value = g_opt.gemm_fast;
+    else if (k == "bf16.fast") *value = g_opt.bf16_fast;
     else if (k == "host.chunk_bytes") *value = g_opt.host_chunk_bytes;
     else return fail(LOF_ERR_INVALID_ARG, "unknown option: " + k);
     return LOF_OK;

@@ -11,6 +11,8 @@ cudaError_t launch_round_bf16(int kind, int mode, const void* in, void* out, int
     switch (kind) {
     case kKindFastSatChk:  return launch_round<LOF_BF16, kKindFastSatChk>(mode, in, out, n, plan, fast, magic, r, len, scale, rng, first_index, cfg, stream);
     case kKindFastExtChk:  return launch_round<LOF_BF16, kKindFastExtChk>(mode, in, out, n, plan, fast, magic, r, len, scale, rng, first_index, cfg, stream);
+    case kKindMagicSat:    return launch_round<LOF_BF16, kKindMagicSat>(mode, in, out, n, plan, fast, magic, r, len, scale, rng, first_index, cfg, stream);
+    case kKindMagicExt:    return launch_round<LOF_BF16, kKindMagicExt>(mode, in, out, n, plan, fast, magic, r, len, scale, rng, first_index, cfg, stream);
     case kKindMagicSatChk: return launch_round<LOF_BF16, kKindMagicSatChk>(mode, in, out, n, plan, fast, magic, r, len, scale, rng, first_index, cfg, stream);
     case kKindMagicExtChk: return launch_round<LOF_BF16, kKindMagicExtChk>(mode, in, out, n, plan, fast, magic, r, len, scale, rng, first_index, cfg, stream);
     default: break;
