@@ -282,6 +282,21 @@ int round_common(bool params, const void* in, void* out, int64_t n, int dtype, c
                 }
             }
         }
+        if (dtype == LOF_F16 && fast_opt >= 2 && !mode_uses_rng(mode) && scale == 1.0 && fmt->mantissa_bits <= 10) {
+            // fp16 container: widen (exact), round with the fp32 magic add, narrow (exact).  Only where every result is an fp16
+            // value again and fp16-subnormal inputs sit below denorm_min: largest target exponent <= 15, denorm_min >= 2^-14,
+            // and the fp32 path itself needs no per-lane checks.  `plan` stays the container plan for the scalar tail.
+            RoundPlan p32;
+            std::memset(&p32, 0, sizeof p32);
+            if (make_plan(fmt, LOF_F32, mode, ps->stoch_length, &p32) == LOF_OK) {
+                const MagicPlan m16 = make_magic_plan(p32, mode);
+                if (m16.valid && m16.lo_rare == 0u && m16.limit == 0xFFFFFFFFu && p32.max_exp_b <= 127 + 15 &&
+                    p32.min_val >= 6.103515625e-05f) {
+                    magic = m16;
+                    kind = p32.saturating ? kKindMagicSat : kKindMagicExt;
+                }
+            }
+        }
         if (dtype == LOF_F32 && fast_opt) {
             fast = make_fast_plan(plan, mode);
             if (fast.valid) kind = fast.check_denorm_in ? (plan.saturating ? kKindFastSatChk : kKindFastExtChk)

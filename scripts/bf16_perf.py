@@ -40,3 +40,18 @@ for name, d, mode, sl in (("e4m3 RNE", lof.create_p3109_params(8, 4, bias=7), 0,
     b.record()
     torch.cuda.synchronize()
     print(f"bf16 container {name:28s} {4.0 * n * 5 / (a.elapsed_time(b) * 1e-3) / 1e9:7.0f} GB/s")
+xh = (torch.randn(n // 2, device=dev, generator=g) * torch.exp2(torch.randint(-10, 6, (n // 2,), device=dev, generator=g).float())).to(torch.float16).repeat(2)
+for name, d, mode in (("e4m3 RNE", lof.create_p3109_params(8, 4, bias=7), 0), ("e2m1 RNE", lof.create_p3109_params(4, 2, bias=1), 0),
+                      ("e5m2 RNE (exact kernel: denorm_min < 2^-14)", lof.create_p3109_params(8, 3, bias=15), 0)):
+    for fast in (0, 2):
+        lof.set_option("round.fast", fast)
+        fn = lambda: lof.virtual_round(xh, d, mode)
+        fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        print(f"fp16 container {name:44s} round.fast={fast} {4.0 * n * 5 / (a.elapsed_time(b) * 1e-3) / 1e9:7.0f} GB/s")
+lof.set_option("round.fast", 2)

@@ -1037,6 +1037,27 @@ def test_bf16_container_fast_path_equals_exact_all_patterns(lof, cuda_dev):
         _lib.set_option("round.fast", 2)
 
 
+def test_fp16_container_fast_path_equals_exact_all_patterns(lof, cuda_dev):
+    """fp16 containers (a reference dtype: AT_DISPATCH_FLOATING_TYPES_AND_HALF, LoPy_bind.cpp:83,133) take the fp32 magic-add
+    routine on the widened values where the host proves every result is an fp16 value again; it must equal the exact
+    fp16-container routine (round.fast = 0, pinned to the oracle by test_round_other_containers) on ALL 65536 patterns for
+    every named format (eligible or not) and deterministic mode, at every vector alignment."""
+    from lofloat_b200 import _lib
+    allbits = torch.arange(0, 65536, device=cuda_dev, dtype=torch.int32).to(torch.int16).view(torch.float16).repeat(9)[5:]
+    try:
+        for name, f in L.FORMATS.items():
+            if f.bitwidth > 16:
+                continue
+            d = _desc(lof, f)
+            for mode in L.DETERMINISTIC_MODES:
+                _lib.set_option("round.fast", 0)
+                want = lof.virtual_round(allbits, d, mode).view(torch.int16)
+                _lib.set_option("round.fast", 2)
+                assert torch.equal(lof.virtual_round(allbits, d, mode).view(torch.int16), want), (name, L.MODE_NAMES[mode])
+    finally:
+        _lib.set_option("round.fast", 2)
+
+
 def test_fused_hadamard_rounding(lof, cuda_dev):
     """Row f-3: the block Walsh-Hadamard rotation of LoF_Linear (layers.py:182-216) fused with the rounding that follows it.
     Plain transform == the oracle's restatement of `_fwht` and == the same formula evaluated with torch ops on the device
