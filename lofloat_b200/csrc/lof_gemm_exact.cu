@@ -26,15 +26,16 @@ __device__ __forceinline__ float accum_round(float t, int r, int len, uint32_t w
     return __uint_as_float(round_mantissa_elem<LOF_F32, MODE>(__float_as_uint(t), r, len, w));
 }
 
-// Optimistic round-to-odd FMA: RZ(a*b + c) with the LSB OR-ed with "inexact" (the two directed results differ), no branch.
-// Equal to rto_fma whenever |result| < 2^127: an exact sum gives rd == ru == rz (an exact zero: rd = -0 == ru = +0, and
-// RZ returns +0 like the reference's `ru`); an inexact one gives the toward-zero neighbour, which is `rd` for a positive and
-// `ru` for a negative exact value.  Overflow, infinities and NaNs (where the reference switches to RN) all land at
-// |result| >= 2^127 or NaN, which the caller flags and recomputes with the exact routine.
+// Optimistic round-to-odd FMA, no branch: of the two directed results rd <= exact <= ru, take the one whose LSB is odd.
+// Inexact: rd and ru are adjacent floats, exactly one is odd, and it is the reference's "toward-zero neighbour with the LSB
+// set" (rz itself if odd, else rz | 1 = the other neighbour).  Exact: rd == ru, either will do -- except the exact zero, where
+// rd = -0 (even) selects ru = +0 like the reference.  Equal to rto_fma whenever |result| < 2^127; overflow, infinities and
+// NaNs (where the reference switches to RN) land at |result| >= 2^127 or NaN, which the caller detects and recomputes with
+// the exact routine.  Two FFMAs + LOP3 (-> predicate) + SEL.
 __device__ __forceinline__ float rto_fma_optimistic(float a, float b, float c)
 {
-    const float rd = __fmaf_rd(a, b, c), ru = __fmaf_ru(a, b, c), rz = __fmaf_rz(a, b, c);
-    return __uint_as_float(__float_as_uint(rz) | (rd != ru ? 1u : 0u));
+    const float rd = __fmaf_rd(a, b, c), ru = __fmaf_ru(a, b, c);
+    return (__float_as_uint(rd) & 1u) ? rd : ru;
 }
 
 // The same with two FMAs: the toward-zero result is picked by the sign of rd (an exact zero has rd = -0 and takes ru = +0).
@@ -165,7 +166,9 @@ gemm_exact_tile(const float* __restrict__ A, const float* __restrict__ B, const 
             // one multiply-accumulate of chain (i, j): w = the rounding event's random word (stochastic modes)
             auto mac = [&](float a, float b, float& c, uint32_t w) {
                 if constexpr (VARIANT != 0) {
-                    const float t = VARIANT == 4 ? rto_fma_optimistic2(a, b, c) : rto_fma_optimistic(a, b, c);
+                    // truncation composes: RTZ to 23 - r bits (r > 0) of the exact sum == mask(RZ fma); no sticky bit needed
+                    const float t = (MODE == LOF_RoundTowardsZero && VARIANT == 1) ? __fmaf_rz(a, b, c)
+                                  : VARIANT == 4 ? rto_fma_optimistic2(a, b, c) : rto_fma_optimistic(a, b, c);
                     if constexpr (VARIANT >= 3) {
                         c = accum_round_rne_float(t, two_r);
                     } else {

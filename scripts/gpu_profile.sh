@@ -27,6 +27,9 @@ for t in $TARGETS; do
     round_rne)
       timeout 600 $NCU_FULL -k regex:round_vec_kernel -s 2 -c 1 -o $OUT/round_rne python scripts/prof_target.py round 0 e4m3 > $OUT/round_rne.log 2>&1
       echo "round_rne exit $?"; export_rep round_rne ;;
+    round_bf16)
+      timeout 600 $NCU_FULL -k regex:round_vec_kernel -s 2 -c 1 -o $OUT/round_bf16 python scripts/prof_target.py round16 bf16 > $OUT/round_bf16.log 2>&1
+      echo "round_bf16 exit $?"; export_rep round_bf16 ;;
     round_sra)
       timeout 600 $NCU_FULL -k regex:round_vec_kernel -s 2 -c 1 -o $OUT/round_sra python scripts/prof_target.py round 3 e4m3 > $OUT/round_sra.log 2>&1
       echo "round_sra exit $?"; export_rep round_sra ;;

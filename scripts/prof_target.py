@@ -35,6 +35,13 @@ def main():
         x *= torch.exp2(torch.randint(-12, 13, (n,), device=dev, generator=g).float())
         for _ in range(4):
             y = lof.virtual_round(x, f, mode, 8 if mode in (3, 8, 9, 14) else 0)
+    elif what == "round16":                          # 16-bit containers: python scripts/prof_target.py round16 [bf16|f16]
+        dt = torch.bfloat16 if (len(sys.argv) < 3 or sys.argv[2] == "bf16") else torch.float16
+        n = 1 << 29
+        x = (torch.randn(n, device=dev, generator=g) * torch.exp2(torch.randint(-8, 6, (n,), device=dev, generator=g).float())).to(dt)
+        for _ in range(4):
+            y = lof.virtual_round(x, fmt("e4m3"), 0)
+        y = y.float()
     elif what == "mx":
         variant = int(sys.argv[2]) if len(sys.argv) > 2 else 0
         f = fmt(sys.argv[3] if len(sys.argv) > 3 else "e4m3")
