@@ -44,16 +44,15 @@ __device__ __forceinline__ float rto_fma(float a, float b, float c)
     return __uint_as_float(__float_as_uint(rz) | 1u);
 }
 
-// Round-to-odd ADD for the chunked GEMM:  RZ(a + b) with the LSB OR-ed with "inexact".  Branch-free: the
-// toward-zero result plus a comparison of the two directed sums (an exact zero gives rd = -0, ru = +0, which
-// compare equal, and RZ returns +0 like RN).  A finite sum beyond FLT_MAX gives +-FLT_MAX (already odd);
-// infinities and NaNs propagate.  CPU statement: oracle/lof_oracle.c lofo_rto_add.
+// Round-to-odd ADD for the chunked GEMM:  RZ(a + b) with the LSB OR-ed with "inexact".  Branch-free: of the two directed
+// sums rd <= exact <= ru take the one whose LSB is odd -- inexact: they are adjacent floats, exactly one is odd, and it is
+// RZ | 1; exact: they are equal (an exact zero gives rd = -0, even, and takes ru = +0 like RZ and RN do).  A finite sum beyond
+// FLT_MAX gives +-FLT_MAX (odd); infinities and NaNs propagate.  CPU statement: oracle/lof_oracle.c lofo_rto_add.
 __device__ __forceinline__ float rto_add(float a, float b)
 {
-    const float rz = __fadd_rz(a, b);
     const float rd = __fadd_rd(a, b);
     const float ru = __fadd_ru(a, b);
-    return __uint_as_float(__float_as_uint(rz) | (rd != ru ? 1u : 0u));
+    return (__float_as_uint(rd) & 1u) ? rd : ru;
 }
 
 }  // namespace lof
