@@ -60,12 +60,13 @@ __device__ __forceinline__ float accum_round_signed(float t, int r, uint32_t kee
 // hardware's RNE add performs the rounding (ties to even on that grid, i.e. on bit r of t's pattern) and the subtraction is
 // exact.  Equal to round_bits<RNE> + mask for every NORMAL t with e + r < 127 and r <= 22 (lof_selftest_gemm_rne_round checks
 // all 2^32 patterns x 22 widths on the device; at r = 23 the integer routine's "even" is the exponent's low bit, ours is not); larger t, infinities and NaNs give a non-finite y (K = inf -> NaN; at e + r = 127 the
-// sum can round up to inf), which sticks to the accumulator until the panel ends, where the caller looks for it.  One alu-pipe and three fma-pipe instructions instead of
+// sum can round up to inf), which sticks to the accumulator until the panel ends, where the caller looks for it.  One alu-pipe and two fma-pipe instructions instead of
 // four alu-pipe ones: the chain is bound by the (half-rate) alu pipe, see profiles/r01k_gemm_exact_summary.txt.
 __device__ __forceinline__ float accum_round_rne_float(float t, float two_r)
 {
-    const float k = __fmul_rn(__uint_as_float(__float_as_uint(t) & 0xFF800000u), two_r);
-    return __fsub_rn(__fadd_rn(t, k), k);
+    // K = m * 2^r is an exact product, so both steps are single FMAs: s = fma(m, 2^r, t) = RN(t + K), y = fma(m, -2^r, s) = s - K
+    const float m = __uint_as_float(__float_as_uint(t) & 0xFF800000u);
+    return __fmaf_rn(m, -two_r, __fmaf_rn(m, two_r, t));
 }
 
 // One 64 x 64 tile of C into `crun` (not stored).  VARIANT 0: the exact routines (rto_fma with its non-finite branch,
