@@ -234,6 +234,8 @@ LOF_API int lof_gemm_chunked_f32(const float* A, const float* B, float* C, int64
  * that follows it -- STERound (:378, with its fused pre-scale) or STEMXRound (:366-369).  One pass over HBM; bit-identical
  * to `_fwht` followed by the separate op (same butterflies in the same stage order, then * fl32(1 / sqrt(block_size))).
  * block_size: a power of two up to 1024 that divides the last dimension; n % 128 == 0; 16-byte aligned; out may alias in.
+ * lof_fwht_f32 (the plain transform) also takes block sizes 2048, 4096 and 8192 -- `hadamard_block_size=None` on an LLM-sized
+ * in_features -- as two passes (inside the 1024-element chunks, then across them), still bit-identical to `_fwht`.
  * ------------------------------------------------------------------------------------- */
 LOF_API int lof_fwht_f32(const float* in, float* out, int64_t n, int block_size, void* stream);
 LOF_API int lof_fwht_round_f32(const float* in, float* out, int64_t n, int block_size, const lof_format_t* fmt,

@@ -23,6 +23,7 @@ cudaError_t launch_gemm_exact(int mode, const float* A, const float* B, float* C
                               int accum_mant_bits, int len, int64_t kc, float alpha, float beta, const RngArgs& rng,
                               cudaStream_t stream, int64_t batch = 1, int64_t stride_a = 0, int64_t stride_b = 0, int64_t stride_c = 0,
                               const ExactView* view = nullptr, int fast = 1);
+cudaError_t launch_fwht_large(const float* in, float* out, int64_t n, int hadamard_block, int num_sms, cudaStream_t stream);
 cudaError_t launch_selftest_rne_round(unsigned long long* mismatches, int num_sms, cudaStream_t stream);
 cudaError_t launch_mx_tma(int mode, const float* in, float* out, int64_t n, const MxArgs& a, const RngArgs& rng,
                           const RngArgs& rng_scale, uint64_t first_index, const MxLaunchCfg& cfg, cudaStream_t stream,
@@ -783,11 +784,13 @@ int lof_gemm_chunked_packed(const uint8_t* A, const uint8_t* Bt, float* C, int64
 // fused callers: Hadamard rotation + rounding (LoFloat/layers.py:182-216, 363-378)
 // ---------------------------------------------------------------------------------------
 namespace {
-int fwht_check(const float* in, float* out, int64_t n, int block)
+int fwht_check(const float* in, float* out, int64_t n, int block, int max_block = 1024)
 {
     if (n < 0) return fail(LOF_ERR_INVALID_ARG, "n < 0");
     if (block <= 0 || (block & (block - 1)) != 0) return fail(LOF_ERR_INVALID_ARG, "fwht: block_size must be a power of 2");   // layers.py:196-197
-    if (block > 1024) return fail(LOF_ERR_UNSUPPORTED, "fwht: fused kernel handles block sizes up to 1024");
+    if (block > max_block)
+        return fail(LOF_ERR_UNSUPPORTED, max_block > 1024 ? "fwht: block sizes up to 8192 are handled" : "fwht: the fused kernels handle block sizes up to 1024 "
+                                                            "(transform with lof_fwht_f32, then round)");
     if (n % block != 0) return fail(LOF_ERR_INVALID_ARG, "fwht: block_size must divide the tensor's last dimension");          // layers.py:198-199
     if (n % 128 != 0) return fail(LOF_ERR_UNSUPPORTED, "fwht: fused kernel needs the element count to be a multiple of 128");
     if (n > 0 && (!in || !out)) return fail(LOF_ERR_INVALID_ARG, "null tensor pointer");
@@ -799,11 +802,17 @@ int fwht_check(const float* in, float* out, int64_t n, int block)
 
 int lof_fwht_f32(const float* in, float* out, int64_t n, int block_size, void* stream)
 {
-    const int st = fwht_check(in, out, n, block_size);
+    const int st = fwht_check(in, out, n, block_size, 8192);
     if (st != LOF_OK) return st;
     if (n == 0) return LOF_OK;
     const int sms = num_sms();
     if (sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    if (block_size > 1024) {                                   // two passes: inside the 1024-element chunks, then across them
+        cudaError_t e2 = launch_fwht_large(in, out, n, block_size, sms * (int)g_opt.stream_ctas_per_sm.load(), static_cast<cudaStream_t>(stream));
+        if (e2 != cudaSuccess) return cuda_fail(e2, "lof_fwht (large block) launch");
+        g_launches.fetch_add(2);
+        return LOF_OK;
+    }
     const RngArgs none = make_rng(nullptr, kStreamElem);
     cudaError_t e = launch_fwht(0, 0, in, out, n, block_size, nullptr, 1.0f, nullptr, nullptr, nullptr, nullptr, none, none, 0, sms * (int)g_opt.stream_ctas_per_sm.load(), static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "lof_fwht launch");

@@ -222,7 +222,65 @@ cudaError_t launch_mode(int mode, int rows_per_block, const float* in, float* ou
     }
 }
 
+// Hadamard blocks of G x 1024 elements (G = 2, 4, 8): the stages h = 1 .. 512 run inside the 1024-element chunks (fwht_kernel,
+// unnormalised), this kernel runs the remaining log2(G) stages h = 1024 .. B / 2 ACROSS the chunks -- a thread owns one float4
+// column of the G chunks, so every pair (i, i + h) sits in its registers -- and applies fl32(1 / sqrt(B)) once at the end.
+// Same adds and subtracts on the same operands in the same stage order as the reference's formulation: bit-identical.
+// In place (every thread reads and writes the same addresses).
+template <int G>
+__global__ void __launch_bounds__(256)
+fwht_cross_kernel(float4* __restrict__ data, int64_t nblocks, float inv_sqrt_b)
+{
+    const int64_t total = nblocks * 256;                       // 256 float4 columns per block
+    for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (int64_t)gridDim.x * blockDim.x) {
+        float4* base = data + (id >> 8) * (int64_t)(G * 256) + (id & 255);
+        float4 v[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) v[g] = __ldcs(base + g * 256);
+#pragma unroll
+        for (int h = 1; h < G; h <<= 1)
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+                if ((g & h) == 0) {
+                    butterfly(v[g].x, v[g + h].x); butterfly(v[g].y, v[g + h].y);
+                    butterfly(v[g].z, v[g + h].z); butterfly(v[g].w, v[g + h].w);
+                }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            v[g].x = __fmul_rn(v[g].x, inv_sqrt_b); v[g].y = __fmul_rn(v[g].y, inv_sqrt_b);
+            v[g].z = __fmul_rn(v[g].z, inv_sqrt_b); v[g].w = __fmul_rn(v[g].w, inv_sqrt_b);
+            __stcs(base + g * 256, v[g]);
+        }
+    }
+}
+
 }  // namespace
+
+// Plain transform for Hadamard blocks of 2048, 4096 or 8192 elements: two passes (16 B / element) instead of the reference's
+// log2(B) stage tensors.
+cudaError_t launch_fwht_large(const float* in, float* out, int64_t n, int hadamard_block, int num_sms, cudaStream_t stream)
+{
+    FwhtArgs a;
+    memset(&a, 0, sizeof a);
+    a.log2_b = 10;
+    a.inv_sqrt_b = 1.0f;                                        // x * 1.0f is the identity: normalisation happens after the last stage
+    const RngArgs none{};
+    cudaError_t e = launch_rows<kFwhtPlain, LOF_RoundToNearestEven>(8, in, out, n / 128, a, none, none, 0, num_sms, stream);
+    if (e != cudaSuccess) return e;
+    const int G = hadamard_block / 1024;
+    const int64_t nblocks = n / hadamard_block;
+    const float norm = (float)(1.0 / sqrt((double)hadamard_block));
+    const int64_t want = (nblocks * 256 + 255) / 256;
+    const unsigned grid = (unsigned)(want < 1 ? 1 : want < num_sms ? want : num_sms);
+    float4* v = reinterpret_cast<float4*>(out);
+    switch (G) {
+    case 2: fwht_cross_kernel<2><<<grid, 256, 0, stream>>>(v, nblocks, norm); break;
+    case 4: fwht_cross_kernel<4><<<grid, 256, 0, stream>>>(v, nblocks, norm); break;
+    case 8: fwht_cross_kernel<8><<<grid, 256, 0, stream>>>(v, nblocks, norm); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
 
 // op: 0 plain FWHT, 1 + virtual_round(params), 2 + virtual_mx_round.  n % 128 == 0, block in {4 .. 1024}, 16-byte aligned.
 cudaError_t launch_fwht(int op, int mode, const float* in, float* out, int64_t n, int hadamard_block, const RoundPlan* plan,

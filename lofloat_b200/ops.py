@@ -600,6 +600,15 @@ def fwht(input: torch.Tensor, block_size=None, *, params: FloatFormatDescriptor 
     out = torch.empty_like(x)
     n = x.numel()
     mode = RoundingMode(int(round_mode))
+    if block_size > 1024 and params is not None:
+        # blocks of 2048 .. 8192 (block_size=None on an LLM-sized in_features): two-pass transform, then the rounding op (the
+        # single-pass fused kernels hold a whole Hadamard block in one warp's registers, up to 1024 elements)
+        y = fwht(x, block_size)
+        if mx_block_size is None:
+            return virtual_round(y, params, mode, stoch_len, scale, rng=rng, first_index=first_index)
+        sf = scale_format if scale_format is not None else _default_e8m0()
+        return virtual_mx_round(y, int(mx_block_size), params, sf, mode, RoundingMode(int(scale_round_mode)), stoch_len, rng=rng,
+                                first_index=first_index)
     with torch.cuda.device(x.device):
         if params is None:
             st = L.lof_fwht_f32(x.data_ptr(), out.data_ptr(), n, int(block_size), _stream_ptr(x))

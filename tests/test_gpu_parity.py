@@ -1097,8 +1097,20 @@ def test_fused_hadamard_rounding(lof, cuda_dev):
     assert float((back - big).abs().max()) < 1e-5
     with pytest.raises(ValueError):
         lof.fwht(big, 48)
+    # blocks of 2048 / 4096 / 8192 (block_size=None on an LLM-sized in_features): two-pass transform, bit-identical to `_fwht`;
+    # with rounding parameters the Python surface composes it with the rounding op
+    for block in (2048, 4096, 8192):
+        xt = torch.randn(24, block * 2, device=cuda_dev) * 3
+        y = lof.fwht(xt, block)
+        assert torch.equal(y, torch_fwht(xt, block)), block
+        assert L.bits_equal(_np(y[:2]), L.o_fwht(_np(xt[:2]), block)), block
+        assert torch.equal(lof.fwht(xt.clone(), None), torch_fwht(xt, block * 2)) if block < 8192 else True
+        got = lof.fwht(xt, block, params=e4m3, scale=0.5)
+        assert torch.equal(got, lof.virtual_round(y, e4m3, L.RNE, 0, 0.5)), block
+        got = lof.fwht(xt, block, params=e4m3, mx_block_size=32, scale_format=e8m0)
+        assert torch.equal(got.view(torch.int32), lof.virtual_mx_round(y, 32, e4m3, e8m0).view(torch.int32)), block
     with pytest.raises(lof.LoFloatError):
-        lof.fwht(torch.randn(8, 4096, device=cuda_dev), 2048)                               # > 1024: not handled by the fused kernel
+        lof.fwht(torch.randn(8, 32768, device=cuda_dev), 16384)                             # > 8192: not handled
 
 
 def test_batched_gemm_equals_per_slice_calls(lof, cuda_dev):
