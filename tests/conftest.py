@@ -39,3 +39,15 @@ def cuda_dev():
     if not torch.cuda.is_available():
         pytest.skip("no GPU")
     return torch.device("cuda:0")
+
+
+@pytest.fixture(autouse=True)
+def _deterministic_torch_rng(request):
+    """Every test starts from a fixed torch seed (CPU and CUDA generators), derived from the test's name: no assertion in
+    this suite may depend on an unseeded draw (round 1: an unseeded randn made `pytest -m gpu` flaky on the driver's box)."""
+    try:
+        import torch
+    except ImportError:
+        return
+    import zlib
+    torch.manual_seed(zlib.crc32(request.node.nodeid.encode()) & 0x7FFFFFFF)

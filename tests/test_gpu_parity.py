@@ -884,10 +884,12 @@ def test_strict_typed_rounding_op(lof, cuda_dev):
         assert L.bits_equal(got[keep], back[keep]) and np.all(np.isnan(got[~keep])), tag
     # Python surface + full size: idempotent projection at 2^28 elements
     d = lof.create_p3109_params(8, 4, saturating=False)
-    xt = torch.randn(1 << 28, device=cuda_dev) * 37.0
+    xt = torch.randn(1 << 28, device=cuda_dev, generator=torch.Generator(device=cuda_dev).manual_seed(1887)) * 37.0
+    xt[:4] = torch.tensor([1e9, -1e9, 2.0 * mx, -2.0 * mx], device=cuda_dev)     # overflow is present whatever the draw
     y = lof.virtual_round_strict(xt, d, saturation_mode=lof.SaturationMode.SatFinite)
     assert torch.equal(lof.virtual_round_strict(y, d, saturation_mode=lof.SaturationMode.SatFinite), y)
-    assert float(y.abs().max()) == mx
+    assert float(y.abs().max()) == mx                       # nothing exceeds the largest finite value ...
+    assert y[:4].tolist() == [mx, -mx, mx, -mx]              # ... and overflow clamps to it with its sign
 
 
 def test_ste_backward_and_cuda_graph_capture(lof, cuda_dev):
