@@ -78,16 +78,20 @@ int cuda_fail(cudaError_t e, const char* what)
 
 int num_sms()
 {
-    static int cached_dev = -1, cached = 0;
+    // per-device cache, filled once (atomics: the C ABI may be called from several host threads, one per GPU)
+    static std::atomic<int> cache[64];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    if (dev != cached_dev) {
+    if (dev < 0 || dev >= 64) {
         int v = 0;
-        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-        cached = v;
-        cached_dev = dev;
+        return cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess ? v : 0;
     }
-    return cached;
+    int v = cache[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        cache[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
 }
 
 struct SrcGeom { int mant, bias; };
@@ -347,46 +351,59 @@ struct HostPipe {
     static constexpr int kBufs = 3;
     void* dev[kBufs] = {nullptr, nullptr, nullptr};
     size_t cap = 0;
-    int device = -1;
     cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
-    cudaEvent_t in_done[kBufs], k_done[kBufs], out_done[kBufs];
+    cudaEvent_t in_done[kBufs] = {nullptr, nullptr, nullptr}, k_done[kBufs] = {nullptr, nullptr, nullptr},
+                out_done[kBufs] = {nullptr, nullptr, nullptr};
     bool init = false;
     std::mutex mu;
 
-    int ensure(int dev_id, size_t bytes)
+    // the caller has made the pipe's device current
+    int ensure(size_t bytes)
     {
-        if (init && device == dev_id && cap >= bytes) return LOF_OK;
+        if (init && cap >= bytes) return LOF_OK;
         release();
-        cudaError_t e = cudaSetDevice(dev_id);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-        device = dev_id;
-        for (int i = 0; i < kBufs; ++i) {
-            e = cudaMalloc(&dev[i], bytes);
-            if (e != cudaSuccess) { release(); return fail(LOF_ERR_ALLOC, std::string("cudaMalloc staging: ") + cudaGetErrorString(e)); }
-        }
+        cudaError_t e = cudaSuccess;
+        for (int i = 0; i < kBufs && e == cudaSuccess; ++i) e = cudaMalloc(&dev[i], bytes);
+        if (e != cudaSuccess) { release(); return fail(LOF_ERR_ALLOC, std::string("cudaMalloc staging: ") + cudaGetErrorString(e)); }
         cap = bytes;
-        cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking);
-        cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking);
-        cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking);
-        for (int i = 0; i < kBufs; ++i) {
-            cudaEventCreateWithFlags(&in_done[i], cudaEventDisableTiming);
-            cudaEventCreateWithFlags(&k_done[i], cudaEventDisableTiming);
-            cudaEventCreateWithFlags(&out_done[i], cudaEventDisableTiming);
+        e = cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking);
+        for (int i = 0; i < kBufs && e == cudaSuccess; ++i) {
+            e = cudaEventCreateWithFlags(&in_done[i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&k_done[i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&out_done[i], cudaEventDisableTiming);
         }
+        if (e != cudaSuccess) { release(); return cuda_fail(e, "host pipeline: stream / event creation"); }
         init = true;
         return LOF_OK;
     }
+    void drain()
+    {
+        if (s_in) cudaStreamSynchronize(s_in);
+        if (s_k) cudaStreamSynchronize(s_k);
+        if (s_out) cudaStreamSynchronize(s_out);
+    }
     void release()
     {
-        if (init) {
-            for (int i = 0; i < kBufs; ++i) { cudaEventDestroy(in_done[i]); cudaEventDestroy(k_done[i]); cudaEventDestroy(out_done[i]); }
-            cudaStreamDestroy(s_in); cudaStreamDestroy(s_k); cudaStreamDestroy(s_out);
+        drain();
+        for (int i = 0; i < kBufs; ++i) {
+            if (in_done[i]) cudaEventDestroy(in_done[i]);
+            if (k_done[i]) cudaEventDestroy(k_done[i]);
+            if (out_done[i]) cudaEventDestroy(out_done[i]);
+            in_done[i] = k_done[i] = out_done[i] = nullptr;
+            if (dev[i]) cudaFree(dev[i]);
+            dev[i] = nullptr;
         }
-        for (int i = 0; i < kBufs; ++i) { if (dev[i]) cudaFree(dev[i]); dev[i] = nullptr; }
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_k) cudaStreamDestroy(s_k);
+        if (s_out) cudaStreamDestroy(s_out);
+        s_in = s_k = s_out = nullptr;
         cap = 0; init = false;
     }
 };
-HostPipe g_pipe;
+constexpr int kMaxDevices = 64;
+HostPipe g_pipes[kMaxDevices];          // one pipeline (staging buffers, streams, events, lock) PER DEVICE: calls for different GPUs run concurrently
 
 // kernel(dev_ptr, elems, first_index_of_chunk, stream) -> status
 template <typename KernelFn>
@@ -396,41 +413,61 @@ int run_host_pipeline(const void* in_host, void* out_host, int64_t n, size_t esi
     if (n < 0) return fail(LOF_ERR_INVALID_ARG, "n < 0");
     if (n == 0) return LOF_OK;
     if (!in_host || !out_host) return fail(LOF_ERR_INVALID_ARG, "null host pointer");
-    int dev_id = device;
-    if (dev_id < 0) {
-        cudaError_t e = cudaGetDevice(&dev_id);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    int prev_dev = 0;
+    cudaError_t e = cudaGetDevice(&prev_dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    const int dev_id = device < 0 ? prev_dev : device;
+    if (dev_id >= kMaxDevices) return fail(LOF_ERR_INVALID_ARG, "device index out of range");
+    // the pipe's device is current for the WHOLE call (kernels, occupancy queries and num_sms() act on the current device) and the
+    // caller's device is restored on every exit path
+    struct DeviceGuard {
+        int prev, cur;
+        ~DeviceGuard() { if (cur != prev) cudaSetDevice(prev); }
+    } guard{prev_dev, dev_id};
+    if (dev_id != prev_dev) {
+        e = cudaSetDevice(dev_id);
+        if (e != cudaSuccess) { guard.cur = prev_dev; return cuda_fail(e, "cudaSetDevice"); }
     }
-    std::lock_guard<std::mutex> lock(g_pipe.mu);
+    HostPipe& pipe = g_pipes[dev_id];
+    std::lock_guard<std::mutex> lock(pipe.mu);
     int64_t chunk_elems = (int64_t)(g_opt.host_chunk_bytes.load() / (int64_t)esize);
     chunk_elems = (chunk_elems / granule) * granule;
     if (chunk_elems < granule) chunk_elems = granule;
     if (chunk_elems > n) chunk_elems = ((n + granule - 1) / granule) * granule;
-    int st = g_pipe.ensure(dev_id, (size_t)chunk_elems * esize);
+    int st = pipe.ensure((size_t)chunk_elems * esize);
     if (st != LOF_OK) return st;
     const int64_t nchunks = (n + chunk_elems - 1) / chunk_elems;
     const char* src = static_cast<const char*>(in_host);
     char* dst = static_cast<char*>(out_host);
+    // On a mid-loop failure copies of earlier chunks may still be writing out_host and the staging buffers: every exit path
+    // waits for the three streams before the call returns and the next call reuses the buffers.
+    auto bail = [&](int status) { pipe.drain(); return status; };
     for (int64_t c = 0; c < nchunks; ++c) {
         const int b = (int)(c % HostPipe::kBufs);
         const int64_t e0 = c * chunk_elems;
         const int64_t ne = (n - e0) < chunk_elems ? (n - e0) : chunk_elems;
-        if (c >= HostPipe::kBufs) cudaStreamWaitEvent(g_pipe.s_in, g_pipe.out_done[b], 0);   // buffer drained
-        cudaError_t e = cudaMemcpyAsync(g_pipe.dev[b], src + (size_t)e0 * esize, (size_t)ne * esize, cudaMemcpyHostToDevice, g_pipe.s_in);
-        if (e != cudaSuccess) return cuda_fail(e, "H2D copy");
-        cudaEventRecord(g_pipe.in_done[b], g_pipe.s_in);
-        cudaStreamWaitEvent(g_pipe.s_k, g_pipe.in_done[b], 0);
-        st = kernel(g_pipe.dev[b], ne, (uint64_t)e0, (void*)g_pipe.s_k);
-        if (st != LOF_OK) return st;
-        cudaEventRecord(g_pipe.k_done[b], g_pipe.s_k);
-        cudaStreamWaitEvent(g_pipe.s_out, g_pipe.k_done[b], 0);
-        e = cudaMemcpyAsync(dst + (size_t)e0 * esize, g_pipe.dev[b], (size_t)ne * esize, cudaMemcpyDeviceToHost, g_pipe.s_out);
-        if (e != cudaSuccess) return cuda_fail(e, "D2H copy");
-        cudaEventRecord(g_pipe.out_done[b], g_pipe.s_out);
+        if (c >= HostPipe::kBufs) {
+            e = cudaStreamWaitEvent(pipe.s_in, pipe.out_done[b], 0);                           // buffer drained
+            if (e != cudaSuccess) return bail(cuda_fail(e, "host pipeline: wait for the staging buffer"));
+        }
+        e = cudaMemcpyAsync(pipe.dev[b], src + (size_t)e0 * esize, (size_t)ne * esize, cudaMemcpyHostToDevice, pipe.s_in);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "H2D copy"));
+        e = cudaEventRecord(pipe.in_done[b], pipe.s_in);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(pipe.s_k, pipe.in_done[b], 0);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "host pipeline: H2D -> kernel ordering"));
+        st = kernel(pipe.dev[b], ne, (uint64_t)e0, (void*)pipe.s_k);
+        if (st != LOF_OK) return bail(st);
+        e = cudaEventRecord(pipe.k_done[b], pipe.s_k);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(pipe.s_out, pipe.k_done[b], 0);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "host pipeline: kernel -> D2H ordering"));
+        e = cudaMemcpyAsync(dst + (size_t)e0 * esize, pipe.dev[b], (size_t)ne * esize, cudaMemcpyDeviceToHost, pipe.s_out);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "D2H copy"));
+        e = cudaEventRecord(pipe.out_done[b], pipe.s_out);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "host pipeline: D2H event"));
     }
-    cudaError_t e = cudaStreamSynchronize(g_pipe.s_out);
-    if (e != cudaSuccess) return cuda_fail(e, "host pipeline sync");
-    e = cudaStreamSynchronize(g_pipe.s_k);
+    e = cudaStreamSynchronize(pipe.s_out);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(pipe.s_k);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(pipe.s_in);
     if (e != cudaSuccess) return cuda_fail(e, "host pipeline sync");
     return LOF_OK;
 }

@@ -344,6 +344,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 #include "lof_gemm_tc2.cuh"
+#include "lof_gemm_tc3.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // operand preparation: fp32 -> tensor-core operand bytes (+ exact-representability check)
@@ -513,6 +514,40 @@ cudaError_t launch_generic(int mode, bool fmt, bool partial, const CUtensorMap& 
     return partial ? launch_mode<kEpiMant, true>(mode, ma, mb, C, a, stream) : launch_mode<kEpiMant, false>(mode, ma, mb, C, a, stream);
 }
 
+// third-generation persistent fold kernel (lof_gemm_tc3.cuh)
+template <int EPI, bool PARTIAL, bool F8>
+cudaError_t launch_fold_mode(int mode, const CUtensorMap& ma, const CUtensorMap& mb, float* C, const TcArgs& a, int sms, cudaStream_t stream)
+{
+    switch (mode) {
+#define LOF_CASE(Mo) case Mo: return launch_fold_one<Mo, EPI, PARTIAL, F8, 128>(ma, mb, C, a, sms, stream);
+        LOF_CASE(LOF_RoundToNearestEven) LOF_CASE(LOF_RoundTowardsZero) LOF_CASE(LOF_RoundAwayFromZero)
+        LOF_CASE(LOF_RoundToNearestOdd) LOF_CASE(LOF_RoundDown) LOF_CASE(LOF_RoundUp) LOF_CASE(LOF_RoundTiesToAway)
+        LOF_CASE(LOF_RoundToOdd) LOF_CASE(LOF_RoundTiesTowardsZero)
+#undef LOF_CASE
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_fold_generic(int mode, bool fmt, bool partial, bool f8, const CUtensorMap& ma, const CUtensorMap& mb, float* C,
+                                const TcArgs& a, int sms, cudaStream_t stream)
+{
+#define LOF_F(E, P) (f8 ? launch_fold_mode<E, P, true>(mode, ma, mb, C, a, sms, stream) : launch_fold_mode<E, P, false>(mode, ma, mb, C, a, sms, stream))
+    if (fmt) return partial ? LOF_F(kEpiFmt, true) : LOF_F(kEpiFmt, false);
+    return partial ? LOF_F(kEpiMant, true) : LOF_F(kEpiMant, false);
+#undef LOF_F
+}
+
+cudaError_t launch_fold_packed(int packed, bool f8, const CUtensorMap& ma, const CUtensorMap& mb, float* C, const TcArgs& a, int sms,
+                               cudaStream_t stream)
+{
+    constexpr int RNE = LOF_RoundToNearestEven;
+    if (packed == kEpiHalf2)
+        return f8 ? launch_fold_one<RNE, kEpiHalf2, true, true, 256>(ma, mb, C, a, sms, stream)
+                  : launch_fold_one<RNE, kEpiHalf2, true, false, 256>(ma, mb, C, a, sms, stream);
+    return f8 ? launch_fold_one<RNE, kEpiBf162, true, true, 256>(ma, mb, C, a, sms, stream)
+              : launch_fold_one<RNE, kEpiBf162, true, false, 256>(ma, mb, C, a, sms, stream);
+}
+
 // Is the packed half2 / bfloat162 epilogue bit-identical to the generic routine for this request?
 //   fp16 hardware == LoFloat accumulator (mantissa 10) iff every value that is ever rounded is either a normal
 //   fp16 number or a multiple of 2^-24 (fp16's subnormal quantum), and nothing reaches 65520.  8-bit operands
@@ -673,6 +708,29 @@ cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, 
         if (hw16) {         // left the fp16 range somewhere: the generic kernel recomputes C (device-side conditional launch)
             a.run_mask = LOF_GEMM_STATUS_PACKED_RANGE; a.run_value = LOF_GEMM_STATUS_PACKED_RANGE;
             e = launch_generic(mode, acc_fmt != nullptr, partial, ma, mb, C, a, stream);
+            ++*launches;
+            if (e != cudaSuccess) return fail(e);
+        }
+        if (dev_status) {
+            tc_or_status_kernel<<<1, 1, 0, stream>>>(dev_status, status);
+            ++*launches;
+        }
+        return cudaFreeAsync(ws, stream);
+    }
+    // third-generation persistent fold kernel for everything that needs the per-chunk software fold
+    if ((flags & LOF_GEMM_NO_PERSISTENT) == 0 && !hw16 && sms >= 1 && K > 0) {
+        const bool f8 = op != kOpBF16;
+        if (packed >= 0) {
+            a.run_mask = 0; a.run_value = 0;
+            e = launch_fold_packed(packed, f8, ma, mb, C, a, sms, stream);
+            ++*launches;
+            if (e != cudaSuccess) return fail(e);
+            a.run_mask = LOF_GEMM_STATUS_PACKED_RANGE; a.run_value = LOF_GEMM_STATUS_PACKED_RANGE;   // left the fp16 range: generic recompute
+        } else {
+            a.run_mask = 0; a.run_value = 0;
+        }
+        if (packed != kEpiBf162) {          // the bfloat162 fold has no range condition (packed_epi): nothing to gate
+            e = launch_fold_generic(mode, acc_fmt != nullptr, partial, f8, ma, mb, C, a, sms, stream);
             ++*launches;
             if (e != cudaSuccess) return fail(e);
         }

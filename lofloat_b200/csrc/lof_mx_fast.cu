@@ -17,6 +17,7 @@
 // formats with mantissa bits, unaligned pointers, tails) stays on the first-generation kernels.
 #include <cstring>
 
+#include <atomic>
 #include "lof_mx_kernels.cuh"
 
 namespace lof {
@@ -143,7 +144,10 @@ mx_fast_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t 
             if (step >= nsteps_total) continue;                                   // warp-uniform
             const uint32_t sb = scale_round(div_pmn(m, k), k, g);
             float4 o0, o1;
-            if ((sb - 0x00800000u) < 0x7E800000u) {                               // normal power of two, 2^-126 .. 2^126
+            // normal power of two, 2^-126 .. 2^126.  The mantissa test matters for m = 0 scale formats with a narrow exponent
+            // range and Saturating overflow: virtual_round then returns the UNROUNDED quotient, which is
+            // not a power of two -- such blocks take the generic routine (a real division).
+            if ((sb - 0x00800000u) < 0x7E800000u && (sb & 0x007FFFFFu) == 0u) {
                 const float scale = __uint_as_float(sb);
                 const float recip = __uint_as_float(0x7F000000u - sb);            // 2^-k, exact
                 o0.x = quant_fast<MODE>(v[s][0].x, recip, scale, k); o0.y = quant_fast<MODE>(v[s][0].y, recip, scale, k);
@@ -171,11 +175,13 @@ cudaError_t launch_bs_mode(const float* in, float* out, int64_t nsteps, const Mx
     constexpr int kWarps = kFastThreads / 32;
     const int64_t ngroups = (nsteps + STEPS - 1) / STEPS;
     int64_t grid = (ngroups + kWarps - 1) / kWarps;
-    static int resident = 0;                                   // CTAs of this instantiation that fit on one SM
+    static std::atomic<int> resident_cache{0};                 // CTAs of this instantiation that fit on one SM (same for every B200)
+    int resident = resident_cache.load(std::memory_order_relaxed);
     if (resident == 0) {
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mx_fast_kernel<BS, MODE, STEPS>, kFastThreads, 0) != cudaSuccess || nb < 1) nb = 1;
         resident = nb;
+        resident_cache.store(nb, std::memory_order_relaxed);
     }
     const int64_t max_ctas = (int64_t)cfg.num_sms * (resident < cfg.ctas_per_sm ? resident : cfg.ctas_per_sm);
     if (grid > max_ctas) grid = max_ctas;                      // persistent: never more CTAs than are resident at once

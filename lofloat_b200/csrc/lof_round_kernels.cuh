@@ -134,6 +134,45 @@ __device__ __forceinline__ uint4 round_vec16_w(uint4 v, const ElemOp<DTYPE, MODE
     }
 }
 
+// bf16 container on the fp32 branch-free routines, event words of the 8 elements given (w0: elements 0..3, w1: 4..7): a bf16
+// value is the fp32 value (bits << 16); rounding it into a target of <= 7 mantissa bits gives an fp32 result whose low 16 bits
+// are zero, i.e. the bf16 result.  Deterministic modes and SR-A / SR-D (host-checked; the random offset R << (r - len) is the
+// same number in both containers); fp32-subnormal inputs and whatever the fp32 routine flags go to the exact bf16 routine.
+// Equality with the exact container routine: all 65536 bf16 patterns x formats x modes, tests/test_gpu_parity.py.
+template <int MODE, int KIND>
+__device__ __forceinline__ uint4 round_vec16_bf16_w(uint4 v, const ElemOp<LOF_BF16, MODE, KIND>& op, const uint4& w0, const uint4& w1)
+{
+    constexpr bool SAT = (KIND == kKindFastSat || KIND == kKindFastSatChk || KIND == kKindMagicSat || KIND == kKindMagicSatChk);
+    // unchecked magic kinds (narrow targets such as the 8 / 6 / 4-bit formats, deterministic modes): the magic add is exact
+    // for every input incl. the fp32 subnormals, so no lane ever needs the container routine -- ~7 alu-pipe instructions
+    // per element less, which is what bounds a 4 B / element stream
+    constexpr bool CHK = !(KIND == kKindMagicSat || KIND == kKindMagicExt);
+    auto two = [&](uint32_t packed, uint32_t wa, uint32_t wb) -> uint32_t {
+        const uint32_t xlo = packed << 16, xhi = packed & 0xFFFF0000u;
+        bool rare = false;
+        if constexpr (CHK) rare = ((xlo & 0x7FFFFFFFu) - 1u) < 0x007FFFFFu || ((xhi & 0x7FFFFFFFu) - 1u) < 0x007FFFFFu;
+        uint32_t olo, ohi;
+        if constexpr (kind_is_magic(KIND)) {
+            olo = round_magic_f32<MODE, SAT, CHK>(xlo, op.magic, wa, rare);
+            ohi = round_magic_f32<MODE, SAT, CHK>(xhi, op.magic, wb, rare);
+        } else {
+            olo = round_fast_f32<MODE, SAT, true>(xlo, op.fast, wa, rare);
+            ohi = round_fast_f32<MODE, SAT, true>(xhi, op.fast, wb, rare);
+        }
+        if constexpr (CHK) {
+            if (rare) {
+                const uint16_t lo = round_params_elem<LOF_BF16, MODE>((uint16_t)(packed & 0xFFFFu), op.plan, wa);
+                const uint16_t hi = round_params_elem<LOF_BF16, MODE>((uint16_t)(packed >> 16), op.plan, wb);
+                return (uint32_t)lo | ((uint32_t)hi << 16);
+            }
+        }
+        return __byte_perm(olo, ohi, 0x7632);                 // (olo >> 16) | (ohi & 0xFFFF0000)
+    };
+    v.x = two(v.x, w0.x, w0.y); v.y = two(v.y, w0.z, w0.w);
+    v.z = two(v.z, w1.x, w1.y); v.w = two(v.w, w1.z, w1.w);
+    return v;
+}
+
 // process one 16-byte vector that starts at global element index g0
 template <int DTYPE, int MODE, int KIND>
 __device__ __forceinline__ uint4 round_vec16(uint4 v, const ElemOp<DTYPE, MODE, KIND>& op,
@@ -146,40 +185,9 @@ __device__ __forceinline__ uint4 round_vec16(uint4 v, const ElemOp<DTYPE, MODE, 
         if constexpr (kRng) w = philox_group4(rng, g0 >> 2);         // g0 % 4 == 0 (host-checked)
         return round_vec16_w<DTYPE, MODE, KIND>(v, op, w);
     } else if constexpr (DTYPE == LOF_BF16 && (kind_is_fast(KIND) || kind_is_magic(KIND))) {
-        // bf16 container on the fp32 branch-free routines: a bf16 value is the fp32 value (bits << 16); rounding it into a
-        // target of <= 7 mantissa bits gives an fp32 result whose low 16 bits are zero, i.e. the bf16 result.  Deterministic
-        // modes and SR-A / SR-D (host-checked; the random offset R << (r - len) is the same number in both containers); fp32-subnormal inputs and whatever the fp32 routine flags go to the exact bf16 routine.
-        // Equality with the exact container routine: all 65536 bf16 patterns x formats x modes, tests/test_gpu_parity.py.
-        constexpr bool SAT = (KIND == kKindFastSat || KIND == kKindFastSatChk || KIND == kKindMagicSat || KIND == kKindMagicSatChk);
-        // unchecked magic kinds (narrow targets such as the 8 / 6 / 4-bit formats, deterministic modes): the magic add is exact
-        // for every input incl. the fp32 subnormals, so no lane ever needs the container routine -- ~7 alu-pipe instructions
-        // per element less, which is what bounds a 4 B / element stream
-        constexpr bool CHK = !(KIND == kKindMagicSat || KIND == kKindMagicExt);
         uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0;               // event words of the 8 elements (stochastic kinds: SR-A / SR-D, magic path)
         if constexpr (kRng) { w0 = philox_group4(rng, g0 >> 2); w1 = philox_group4(rng, (g0 >> 2) + 1); }
-        auto two = [&](uint32_t packed, uint32_t wa, uint32_t wb) -> uint32_t {
-            const uint32_t xlo = packed << 16, xhi = packed & 0xFFFF0000u;
-            bool rare = false;
-            if constexpr (CHK) rare = ((xlo & 0x7FFFFFFFu) - 1u) < 0x007FFFFFu || ((xhi & 0x7FFFFFFFu) - 1u) < 0x007FFFFFu;
-            uint32_t olo, ohi;
-            if constexpr (kind_is_magic(KIND)) {
-                olo = round_magic_f32<MODE, SAT, CHK>(xlo, op.magic, wa, rare);
-                ohi = round_magic_f32<MODE, SAT, CHK>(xhi, op.magic, wb, rare);
-            } else {
-                olo = round_fast_f32<MODE, SAT, true>(xlo, op.fast, wa, rare);
-                ohi = round_fast_f32<MODE, SAT, true>(xhi, op.fast, wb, rare);
-            }
-            if constexpr (CHK) {
-                if (rare) {
-                    const uint16_t lo = round_params_elem<LOF_BF16, MODE>((uint16_t)(packed & 0xFFFFu), op.plan, wa);
-                    const uint16_t hi = round_params_elem<LOF_BF16, MODE>((uint16_t)(packed >> 16), op.plan, wb);
-                    return (uint32_t)lo | ((uint32_t)hi << 16);
-                }
-            }
-            return __byte_perm(olo, ohi, 0x7632);                 // (olo >> 16) | (ohi & 0xFFFF0000)
-        };
-        v.x = two(v.x, w0.x, w0.y); v.y = two(v.y, w0.z, w0.w);
-        v.z = two(v.z, w1.x, w1.y); v.w = two(v.w, w1.z, w1.w);
+        return round_vec16_bf16_w<MODE, KIND>(v, op, w0, w1);
     } else if constexpr (DTYPE == LOF_F16 && (KIND == kKindMagicSat || KIND == kKindMagicExt)) {
         // fp16 container on the fp32 magic-add routine: half -> float is exact, and the host only selects this kind when every
         // result is representable in fp16 again (target mantissa <= 10 bits, largest exponent <= 15, denorm_min >= 2^-14 -- the
@@ -229,16 +237,38 @@ round_vec_kernel(const uint4* in, uint4* out, int64_t nvec, int ntail,
     using B = typename Src<DTYPE>::bits_t;
     constexpr int VEC = 16 / (int)sizeof(B);
     constexpr int64_t TILE = (int64_t)kRoundThreads * UNROLL;
-    const int64_t ntiles = (nvec + TILE - 1) / TILE;
+    // Work split of the persistent grid: every CTA takes the same number of WHOLE tiles (tile = blockIdx.x + k * gridDim.x), and
+    // what is left -- fewer than gridDim.x tiles plus the ragged end -- is dealt out in ROWS of kRoundThreads vectors, so that no
+    // CTA carries more than one row over the average.  With tile-granular dealing the last round leaves most SMs idle: at
+    // n = 2^24 (C1; 4096 tiles on 444 CTAs) that was 10 tiles for some CTAs against an average of 9.2, ~8 % of the run.
+    const int64_t rounds = (nvec / TILE) / gridDim.x;
 
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int64_t k = 0; k < rounds; ++k) {
+        const int64_t tile = blockIdx.x + k * gridDim.x;
         const int64_t base = tile * TILE + threadIdx.x;
+        if constexpr (ModeTraits<MODE>::kUsesRng && DTYPE == LOF_BF16 && UNROLL == 4 && (kind_is_fast(KIND) || kind_is_magic(KIND))) {
+            // 16-bit containers, class-0 events: a tile is 8192 elements = two aligned runs of 4096; thread t takes, in run
+            // t >> 7, the vectors w * 128 + (t & 127), w = 0..3, i.e. the 4-element groups v = w * 256 + 2 (t & 127) + {0, 1}
+            // of that run -- all four words of the two Philox blocks (run, 2 (t & 127)) and (run, 2 (t & 127) + 1): one block
+            // per 16 elements like the fp32 layout (two blocks per 8-element vector before).  Same event stream as philox_group4.
+            if (rng.cls == 0u && (first_index & 4095u) == 0u) {
+                const uint32_t t = threadIdx.x, kk = t & 127u;
+                const uint64_t run = (first_index >> 12) + (uint64_t)tile * 2u + (t >> 7);
+                const int64_t vbase = tile * TILE + (int64_t)(t >> 7) * 512 + kk;
+                uint4 q[UNROLL];
+#pragma unroll
+                for (int w = 0; w < UNROLL; ++w) q[w] = ld_stream(in + vbase + w * 128);
+                const uint4 ba = philox_block(rng, (run << 8) | (2u * kk)), bb = philox_block(rng, (run << 8) | (2u * kk + 1u));
+                const uint32_t wa[4] = {ba.x, ba.y, ba.z, ba.w}, wb[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                for (int w = 0; w < UNROLL; ++w)
+                    st_stream(out + vbase + w * 128, round_vec16_bf16_w<MODE, KIND>(q[w], op, bytes_of(wa[w]), bytes_of(wb[w])));
+                continue;
+            }
+        }
         uint4 v[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const int64_t idx = base + (int64_t)u * kRoundThreads;
-            if (idx < nvec) v[u] = ld_stream(in + idx);
-        }
+        for (int u = 0; u < UNROLL; ++u) v[u] = ld_stream(in + base + (int64_t)u * kRoundThreads);
         if constexpr (ModeTraits<MODE>::kUsesRng && sizeof(B) == 4 && UNROLL == 4) {
             // class-0 events (<= 8 random bits): the 4 vectors of this thread in this 4096-element tile share ONE
             // Philox block by construction of the event stream (lof_core.cuh) when the tile grid is aligned with it
@@ -246,19 +276,32 @@ round_vec_kernel(const uint4* in, uint4* out, int64_t nvec, int ntail,
                 const uint4 b = philox_block(rng, ((first_index >> 12) + (uint64_t)tile) * 256u + threadIdx.x);
                 const uint32_t wu[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u) {
-                    const int64_t idx = base + (int64_t)u * kRoundThreads;
-                    if (idx < nvec) st_stream(out + idx, round_vec16_w<DTYPE, MODE, KIND>(v[u], op, bytes_of(wu[u])));
-                }
+                for (int u = 0; u < UNROLL; ++u)
+                    st_stream(out + base + (int64_t)u * kRoundThreads, round_vec16_w<DTYPE, MODE, KIND>(v[u], op, bytes_of(wu[u])));
                 continue;
             }
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const int64_t idx = base + (int64_t)u * kRoundThreads;
-            if (idx < nvec) {
-                const uint4 r = round_vec16<DTYPE, MODE, KIND>(v[u], op, rng, first_index + (uint64_t)idx * VEC);
-                st_stream(out + idx, r);
+            st_stream(out + idx, round_vec16<DTYPE, MODE, KIND>(v[u], op, rng, first_index + (uint64_t)idx * VEC));
+        }
+    }
+    // the remainder, in rows of kRoundThreads vectors dealt out cyclically (at most UNROLL + 1 rows per CTA)
+    {
+        const int64_t rem0 = rounds * gridDim.x * TILE;
+        const int64_t nrows = (nvec - rem0 + kRoundThreads - 1) / kRoundThreads;
+        for (int64_t r0 = blockIdx.x; r0 < nrows; r0 += (int64_t)gridDim.x * UNROLL) {
+            uint4 v[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int64_t idx = rem0 + (r0 + (int64_t)u * gridDim.x) * kRoundThreads + threadIdx.x;
+                if (idx < nvec) v[u] = ld_stream(in + idx);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int64_t idx = rem0 + (r0 + (int64_t)u * gridDim.x) * kRoundThreads + threadIdx.x;
+                if (idx < nvec) st_stream(out + idx, round_vec16<DTYPE, MODE, KIND>(v[u], op, rng, first_index + (uint64_t)idx * VEC));
             }
         }
     }

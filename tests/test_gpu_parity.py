@@ -296,6 +296,18 @@ def test_mx_modes_scale_modes_and_edge_cases(lof, cuda_dev, variant):
                 for en in ("e4m3_b7", "e2m1"):
                     got = _np(lof.virtual_mx_round(xg, bs, _desc(lof, L.FORMATS[en]), _desc(lof, e8)))
                     assert L.bits_equal(got, g[f"mx_{n}_{bs}_{en}_e8m0_RNE"]), (n, bs, en)
+        # narrow m = 0 scale formats whose Saturating overflow returns the UNROUNDED quotient (not a power of two), signed and
+        # unsigned, plus an Extended one whose overflow gives +inf: every block size and every deterministic element mode
+        xw = _mx_input(1 << 14, 21) * np.float32(64.0)           # amax / pmn far beyond 2^max_exp of the narrow formats
+        xw[:512] *= np.float32(2.0 ** -9)                        # ... and some blocks inside their range
+        xwt = _gpu(xw, cuda_dev)
+        for sf in (L.fmt(4, 0, 4, L.SATURATING, L.UNSIGNED), L.fmt(4, 0, 3, L.SATURATING, L.SIGNED), L.fmt(5, 0, 8, L.EXTENDED, L.UNSIGNED)):
+            for bs in (16, 32, 64, 128, 256):
+                for mode in L.DETERMINISTIC_MODES:
+                    for smode in (L.RNE, L.RU):
+                        got = _np(lof.virtual_mx_round(xwt, bs, _desc(lof, e4), _desc(lof, sf), mode, smode))
+                        want = L.o_mx_round(xw, bs, sf, e4, mode, smode)
+                        assert L.bits_equal(got, want), (variant, sf.key(), bs, L.MODE_NAMES[mode], smode, L.first_mismatch(xw, got, want))
         # shape is preserved, blocks run over the flattened contiguous tensor (LoPy_bind.cpp:175,216)
         x2 = xt[:4096].reshape(8, 512)
         assert lof.virtual_mx_round(x2, 32, _desc(lof, e4), _desc(lof, e8)).shape == (8, 512)
@@ -426,6 +438,43 @@ def test_gemm_chunked_full_size_properties(lof, cuda_dev):
     assert torch.equal(Cg, Cm[:256])
 
 
+def test_gemm_persistent_fold_kernel_equals_first_generation_and_oracle(lof, cuda_dev):
+    """Third-generation persistent per-chunk fold kernel (lof_gemm_tc3.cuh: one CTA per SM walking a tile schedule, 128 x 256
+    tiles with packed half2 / bfloat162 accumulators, 128 x 128 tiles with fp32 accumulators) must be BIT-IDENTICAL to the
+    first-generation one-tile-per-CTA kernel (same tensor-core partials, same fold) for every accumulator semantics, on
+    shapes with fewer tiles than SMs, several tiles per CTA, ragged edges and short last chunks; and bit-exact against the
+    oracle on exactly summable data."""
+    dev = cuda_dev
+    e5m10 = _desc(lof, L.fmt(16, 10, 15, L.SATURATING, L.SIGNED))
+    shapes = ((128, 256, 128), (200, 136, 400), (2560, 2560, 512), (1000, 520, 1024 + 32), (384, 4096, 256), (4000, 300, 96))
+    for (M, N, K) in shapes:
+        A, B = _e4m3_uniform((M, K), 3 * M + K), _e4m3_uniform((K, N), N + 7 * K + 1)
+        At, Bt = _gpu(A, dev), _gpu(B, dev)
+        cases = [(10, dict(k_chunk=32, partial_round=True)),                         # packed half2 fold (+ gated generic recompute)
+                 (7, dict(k_chunk=32, partial_round=True)),                          # packed bfloat162 fold
+                 (7, dict(k_chunk=64, partial_round=True, operand_dtype="bf16")),    # ... with bf16 operands (C5)
+                 (7, dict(k_chunk=32)),                                              # generic single-rounding fold, mantissa-only
+                 (5, dict(k_chunk=32, round_mode=L.RTZ, partial_round=True)),
+                 (4, dict(k_chunk=96, round_mode=L.RTO)),
+                 (0, dict(k_chunk=32, accum_format=e5m10, round_mode=L.RAZ)),        # full-format accumulator, non-RNE: no hardware path
+                 (10, dict(k_chunk=32, allow_packed=False, partial_round=True))]
+        for mant, kw in cases:
+            got = lof.lof_gemm(At, Bt, mant, **kw)
+            ref = lof.lof_gemm(At, Bt, mant, allow_persistent=False, **kw)
+            assert torch.equal(got.view(torch.int32), ref.view(torch.int32)), (M, N, K, mant, kw)
+    A, B = _ints((300, 1024), -8, 8, 5), _ints((1024, 520), -8, 8, 6)
+    for mode in L.DETERMINISTIC_MODES:
+        assert L.bits_equal(_tc(lof, dev, A, B, 6, 32, round_mode=mode, allow_packed=False), L.o_gemm_chunked(A, B, 6, 32, mode=mode)), mode
+        assert L.bits_equal(_tc(lof, dev, A, B, 5, 64, round_mode=mode, partial_round=True),
+                            L.o_gemm_chunked(A, B, 5, 64, mode=mode, partial_round=True)), mode
+    Ab, Bb = _ints((384, 640), -100, 100, 7), _ints((640, 300), -100, 100, 8)
+    assert L.bits_equal(_tc(lof, dev, Ab, Bb, 7, 32, operand_dtype="bf16", partial_round=True), L.o_gemm_chunked(Ab, Bb, 7, 32, partial_round=True))
+    # leaving the fp16 range: the packed half2 fold flags it and the gated generic kernel recomputes C
+    Ao, Bo = (_ints((128, 512), 200, 448, 15) // 32) * 32, (_ints((512, 128), 200, 448, 16) // 32) * 32
+    assert L.bits_equal(_tc(lof, dev, Ao, Bo, 10, 32, partial_round=True), L.o_gemm_chunked(Ao, Bo, 10, 32, partial_round=True))
+    assert lof.lof_gemm.last_status & 4
+
+
 def test_gemm_pair_kernel_equals_single_cta_kernel_and_oracle(lof, cuda_dev):
     """Persistent CTA-pair main loop (tcgen05 cta_group::2, 256 x 256 tiles, lof_gemm_tc2.cuh): the accumulator
     semantics it serves -- fp16 accumulation inside the tensor core (k_chunk 32, E5M10 / mantissa 10, RNE) and
@@ -486,11 +535,11 @@ def test_gemm_exact_vs_oracle_and_golden(lof, cuda_dev):
         At, Bt = _gpu(A, cuda_dev), _gpu(B, cuda_dev)
         for mode in L.DETERMINISTIC_MODES:
             for bits in (10, 7):
-                got = _np(lof.lof_gemm(At, Bt, bits, mode))
+                got = _np(lof.lof_gemm(At, Bt, bits, mode, kc=256))          # goldens: bli_sgemm + lof_sgemm_ukr, KC = 256
                 assert L.bits_equal(got, g[f"C_{M}_{N}_{K}_{L.MODE_NAMES[mode]}_{bits}"]), (M, N, K, mode, bits)
     A, B = g["kat_A"], g["kat_B"]                                # exact-representable KAT, every mode == fp64 product
     for mode in L.DETERMINISTIC_MODES:
-        got = _np(lof.lof_gemm(_gpu(A, cuda_dev), _gpu(B, cuda_dev), 10, mode))
+        got = _np(lof.lof_gemm(_gpu(A, cuda_dev), _gpu(B, cuda_dev), 10, mode, kc=256))
         assert L.bits_equal(got, g["kat_C"])
     rng = np.random.default_rng(21)
     for (M, N, K) in ((1, 1, 1), (65, 63, 129), (128, 192, 512), (200, 72, 1031)):
@@ -500,15 +549,17 @@ def test_gemm_exact_vs_oracle_and_golden(lof, cuda_dev):
         for kc in (256, 0, 100):
             got = _np(lof.lof_gemm(At, Bt, 10, L.RNE, kc=kc))
             assert L.bits_equal(got, L.o_gemm(A, B, 10, L.RNE, kc=kc)), (M, N, K, kc)
-        got = _np(lof.lof_gemm(At, Bt, 5, L.RAZ, 0, 3.0, 0.25))          # output / (scale_a * scale_b)
+        # the DEFAULT call is the reference's CUDA leaf: one accumulator over all of K (cutlass_gemms.cuh:97-168), not the BLIS panels
+        assert L.bits_equal(_np(lof.lof_gemm(At, Bt, 10)), L.o_gemm(A, B, 10, L.RNE, kc=0)), (M, N, K, "default kc")
+        got = _np(lof.lof_gemm(At, Bt, 5, L.RAZ, 0, 3.0, 0.25, kc=256))          # output / (scale_a * scale_b)
         assert L.bits_equal(got, L.o_gemm(A, B, 5, L.RAZ, kc=256, alpha=np.float32(1.0 / 0.75)))
         for mode, sl in ((L.SR_A, 6), (L.TRUE_SR, 0), (L.SR_D, 3)):
-            got = _np(lof.lof_gemm(At, Bt, 10, mode, sl, rng=(11, 12)))
+            got = _np(lof.lof_gemm(At, Bt, 10, mode, sl, kc=256, rng=(11, 12)))
             assert L.bits_equal(got, L.o_gemm(A, B, 10, mode, sl, kc=256, seed=11, offset=12)), (M, N, K, mode)
     # wide-range operands: cancellation, subnormal and overflowing partial sums exercise round_to_odd_fma
     A = (rng.standard_normal((48, 96)) * np.exp2(rng.integers(-70, 60, (48, 96)))).astype(np.float32)
     B = (rng.standard_normal((96, 40)) * np.exp2(rng.integers(-70, 60, (96, 40)))).astype(np.float32)
-    got = _np(lof.lof_gemm(_gpu(A, cuda_dev), _gpu(B, cuda_dev), 10, L.RNE))
+    got = _np(lof.lof_gemm(_gpu(A, cuda_dev), _gpu(B, cuda_dev), 10, L.RNE, kc=256))
     want = L.o_gemm(A, B, 10, L.RNE, kc=256)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
