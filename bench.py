@@ -243,12 +243,18 @@ def run_ours(args):
     except Exception as exc:  # pinned allocation can fail on a small host
         e2e = {"value": None, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(exc)}
 
+    workloads = {}
+    if not args.no_side:
+        try:
+            workloads = named_workloads(torch, dist, dev, rank, world, args)
+        except Exception as exc:
+            workloads = {"error": str(exc)}
     other = {}
     cpu_baseline = None
     if rank == 0 and not args.no_side:
         other = side_measurements(torch, lib, _lib, dev, x, y, stream)
         if world == 1:
-            cpu_baseline = cpu_reference_sample(x[: 1 << 24].cpu().numpy(), budget_s=20.0)
+            cpu_baseline = cpu_reference_sample(x[: 1 << 26].cpu().numpy(), budget_s=20.0)
             try:
                 other.update(c1_and_cpu_side(torch, dev))
             except Exception as exc:
@@ -267,9 +273,196 @@ def run_ours(args):
                    "parallelism": f"row-shard x{world}, no collective"},
         "roofline": roofline, "kernels": kernels,
         "sweep_GBps": {k: bytes_per_pass / (statistics.mean(v) * 1e-3) / 1e9 for k, v in by_combo.items()},
-        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu_baseline, "other": other,
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu_baseline, "workloads": workloads, "other": other,
     }
     print(json.dumps(line))
+
+
+def bf16_peak():
+    """(measured dense bf16 TFLOP/s burst, sustained) from MEASURED_PEAKS.json, else the profiling guide's fallback."""
+    p = ROOT / "MEASURED_PEAKS.json"
+    try:
+        d = json.loads(p.read_text())
+        return float(d["bf16_tflops"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+def named_workloads(torch, dist, dev, rank, world, args):
+    """BASELINE.json configs C3 / C4 / C5 (and C1 on rank 0) measured at THIS world size, inside the same JSON line as the
+    headline sweep: every rank takes part (row shards for MX, the R x C grid with its NCCL exchange for the GEMMs), device
+    time by CUDA events, max over ranks.  Each entry carries its own roofline fraction per GPU."""
+    import lofloat_b200 as lof
+    from lofloat_b200 import sharding as S
+    hbm_peak, hbm_src = peaks()
+    bf16_burst, bf16_sust, bf16_src = bf16_peak()
+    out = {}
+
+    def sync_max(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def timed(fn, reps, warm=2):
+        keep = None
+        for _ in range(warm):
+            keep = fn()
+        del keep
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            keep = fn()
+        b.record()
+        torch.cuda.synchronize()
+        return sync_max(a.elapsed_time(b) / reps), keep
+
+    e8m0 = lof.create_e8m0_params()
+    # ------------------------------------------------------------------ C3: mx_round, 16384 x 16384 fp32 per GPU, block 32, E8M0 scale
+    try:
+        R = Ccols = 16384
+        g = torch.Generator(device=dev).manual_seed(7 + rank)
+        x = torch.randn(R, Ccols, device=dev, generator=g)
+        x *= torch.exp2(torch.randint(-8, 9, (R, 1), device=dev, generator=g).float())
+        x[torch.rand(R, Ccols, device=dev, generator=g) < 1e-3] *= 64.0                      # 0.1 % outliers (SURVEY 8d)
+        shard = S.RowShard.make(R * world, Ccols, world, rank)                                 # this rank's rows of the (world * 16384) x 16384 tensor
+        fmts = (("mxfp8_e4m3", lof.create_p3109_params(8, 4, bias=7)), ("mxfp8_e5m2", lof.create_p3109_params(8, 3, bias=15)),
+                ("mxfp6_e3m2", lof.create_p3109_params(6, 3, bias=3)), ("mxfp6_e2m3", lof.create_p3109_params(6, 4, bias=1)),
+                ("mxfp4_e2m1", lof.create_p3109_params(4, 2, bias=1)))
+        per, tot_ms = {}, 0.0
+        for name, d in fmts:
+            ms, _ = timed(lambda: S.sharded_virtual_mx_round(x, shard, 32, d, e8m0), 5)
+            per[name] = {"ms": ms, "GBps_aggregate": 8.0 * x.numel() * world / (ms * 1e-3) / 1e9}
+            tot_ms += ms
+        agg = 8.0 * x.numel() * world * len(fmts) / (tot_ms * 1e-3) / 1e9
+        blocks = {}
+        for bs in (16, 64, 128, 256):
+            ms, _ = timed(lambda: S.sharded_virtual_mx_round(x, shard, bs, fmts[0][1], e8m0), 3)
+            blocks[f"bs{bs}"] = 8.0 * x.numel() / (ms * 1e-3) / 1e9
+        ms_sr, _ = timed(lambda: S.sharded_virtual_mx_round(x, shard, 32, fmts[0][1], e8m0, lof.RoundingMode.StochasticRoundingA, 0, 8, rng=(7, 1)), 3)
+        c3 = {"metric": "mx_round_GBps", "value": agg, "unit": "GB/s", "scaling": "weak", "elements_per_gpu": x.numel(), "block_size": 32,
+              "scale_format": "E8M0", "formats": per, "collective": None,
+              "roofline": {"bound": "hbm", "kernel": "mx_fast_kernel<32,RNE>", "achieved": agg / world, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": agg / world / hbm_peak, "algorithmic_bytes_per_launch": 8.0 * x.numel(), "peak_source": hbm_src},
+              "per_gpu_GBps_other_block_sizes_e4m3": blocks,
+              "per_gpu_GBps_stochastic_SR_A8_e4m3": 8.0 * x.numel() / (ms_sr * 1e-3) / 1e9}
+        if rank == 0 and args.e2e_steps > 0:
+            # e2e (rank 0's shard): pinned host tensor in, pinned host tensor out, through the C ABI's host entry point
+            from lofloat_b200 import _lib
+            lib = _lib.lib()
+            xh = torch.empty(x.numel(), dtype=torch.float32).pin_memory()
+            xh.copy_(x.view(-1))
+            yh = torch.empty_like(xh).pin_memory()
+            fe, fs, ps = fmts[0][1]._c(), e8m0._c(), _lib.CProjSpec(0, 0, 0)
+            call = lambda: lib.lof_mx_round_f32_host(xh.data_ptr(), yh.data_ptr(), xh.numel(), 32, C.byref(fs), C.byref(fe), C.byref(ps),
+                                                     C.byref(ps), None, 0, dev.index)
+            assert call() == 0
+            t0 = time.perf_counter()
+            assert call() == 0
+            dt = time.perf_counter() - t0
+            c3["e2e"] = {"value": 8.0 * xh.numel() / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": 4 * xh.numel(), "d2h_bytes_per_step": 4 * xh.numel(),
+                         "api": "lof_mx_round_f32_host (rank 0's shard)"}
+            del xh, yh
+        out["C3_mx_round"] = c3
+        del x
+    except Exception as exc:
+        out["C3_mx_round"] = {"error": str(exc)}
+
+    # ------------------------------------------------------------------ C4: lof-GEMM 8192^3 (strong scaling over the R x C grid)
+    grid = S.GemmGrid.create(world, rank)
+    try:
+        n = 8192
+        M = N = K = n
+        e4m3 = lof.create_p3109_params(8, 4, bias=7)
+        e5m10 = lof.FloatFormatDescriptor(16, 10, 15, lof.InfBehavior.Saturating, lof.NaNBehavior._3109, lof.Signedness.Signed,
+                                          lof.create_half_params().is_inf_checker, lof.create_half_params().is_nan_checker)
+        from lofloat_b200 import formats as _formats
+        ocp = lof.FloatFormatDescriptor(8, 3, 7, lof.InfBehavior.Saturating, lof.NaNBehavior._3109, lof.Signedness.Signed,
+                                        _formats._P3109Inf(8, True, True), _formats._BitPatternNaN(0xFF))
+        g = torch.Generator(device=dev).manual_seed(42 + rank)
+        A_loc = lof.virtual_round(torch.rand(M // world, K, device=dev, generator=g) * 2 - 1, e4m3)      # this rank's rows of A
+        Wt_loc = lof.virtual_round(torch.rand(N // world, K, device=dev, generator=g) * 2 - 1, e4m3)     # ... of B^T ([out, in] layout)
+        A8, Wt8 = lof.lof_encode(A_loc, ocp).view(M // world, K), lof.lof_encode(Wt_loc, ocp).view(N // world, K)
+        fn = lambda: S.gemm_2d_packed(A8, Wt8, grid, M, N, K, 0, k_chunk=32, accum_format=e5m10)
+        ms, _ = timed(fn, 10, warm=3)
+        tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
+        a_gather = (M // grid.R) * K * (grid.C - 1) // grid.C if world > 1 else 0                       # bytes RECEIVED per rank
+        b_recv = (N // grid.C) * K * (grid.R * grid.C - 1) // (grid.R * grid.C) if world > 1 else 0
+        c4 = {"metric": "lof_gemm_TFLOPs", "value": tf, "unit": "TFLOP/s", "scaling": "strong", "M": M, "N": N, "K": K, "ms": ms,
+              "operands": "E4M3 bytes, row-sharded (A rows, B^T rows)", "accumulator": "E5M10 re-rounded every k = 32 (RNE), in the tensor core (fp16 TMEM accumulator)",
+              "grid": f"{grid.R}x{grid.C}", "timed_region": "operand exchange + GEMM",
+              "comm": {"collectives": ["all_gather_into_tensor (A row panel, row group)", "all_to_all_single (B^T column panel, world)"] if world > 1 else [],
+                       "bytes_received_per_rank": int(a_gather + b_recv)},
+              "roofline": {"bound": "tensor", "achieved": tf / world, "peak": 4500.0, "unit": "TFLOP/s", "frac": tf / world / 4500.0,
+                           "peak_source": "nominal dense FP8 (B200_PROFILING.md)", "frac_of_2x_measured_bf16": tf / world / (2.0 * bf16_burst),
+                           "measured_bf16_source": bf16_src,
+                           "kernel": "gemm_tc_pair_kernel<Hw16,f8> (tcgen05 cta_group::2, 256x256 tiles)"}}
+        if rank == 0 and world == 1 and args.e2e_steps > 0:
+            # e2e: fp32 containers in pinned host memory -> device -> lof_gemm (conversion + GEMM) -> C back to pinned host memory
+            Ah, Bh = A_loc.cpu().pin_memory(), Wt_loc.t().contiguous().cpu().pin_memory()
+            Ch = torch.empty(M, N, dtype=torch.float32).pin_memory()
+
+            def e2e_call():
+                Ad, Bd = Ah.to(dev, non_blocking=True), Bh.to(dev, non_blocking=True)
+                Ch.copy_(lof.lof_gemm(Ad, Bd, 0, k_chunk=32, accum_format=e5m10, check=False), non_blocking=True)
+                torch.cuda.synchronize()
+            e2e_call()
+            t0 = time.perf_counter()
+            e2e_call()
+            dt = time.perf_counter() - t0
+            c4["e2e"] = {"value": 2.0 * M * N * K / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": 8 * M * K, "d2h_bytes_per_step": 4 * M * N,
+                         "api": "lof_gemm(k_chunk=32, accum_format=E5M10) on fp32 host tensors (pinned), copies inside the timed region"}
+            del Ah, Bh, Ch
+        out["C4_lof_gemm_8192"] = c4
+        del A_loc, Wt_loc, A8, Wt8
+    except Exception as exc:
+        out["C4_lof_gemm_8192"] = {"error": str(exc)}
+
+    # ------------------------------------------------------------------ C5: MXFP8 GEMM 32768^3, bf16-rounded accumulation
+    try:
+        n = args.c5_size
+        M = N = K = n
+        e4m3 = lof.create_p3109_params(8, 4, bias=7)
+        g = torch.Generator(device=dev).manual_seed(99 + rank)
+        A_loc = torch.randn(M // world, K, device=dev, generator=g)
+        Wt_loc = torch.randn(N // world, K, device=dev, generator=g)           # weight layout [out, in]: MX blocks run along K
+        ms_mx, (A_q, Wt_q) = timed(lambda: (lof.virtual_mx_round(A_loc, 32, e4m3, e8m0), lof.virtual_mx_round(Wt_loc, 32, e4m3, e8m0)), 3, warm=1)
+        del A_loc, Wt_loc
+        # an MX-rounded element (e4m3 value x power-of-two block scale) is exact in bf16; the saturating virtual_round leaves a block's
+        # overflowing maxima unrounded (SURVEY Appendix B.1), so snap once to make the tensor-core operands exact
+        A16, Wt16 = A_q.bfloat16(), Wt_q.bfloat16()
+        del A_q, Wt_q
+        fn = lambda: S.gemm_2d_packed(A16, Wt16, grid, M, N, K, 7, k_chunk=32, partial_round=True)
+        ms, Cblk = timed(fn, 2, warm=1)
+        finite = bool(torch.isfinite(Cblk).all().item())
+        del Cblk
+        tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
+        a_gather = 2 * (M // grid.R) * K * (grid.C - 1) // grid.C if world > 1 else 0
+        b_recv = 2 * (N // grid.C) * K * (world - 1) // world if world > 1 else 0
+        out["C5_mxfp8_gemm"] = {
+            "metric": "mx_gemm_TFLOPs", "value": tf, "unit": "TFLOP/s", "scaling": "strong", "M": M, "N": N, "K": K, "ms": ms,
+            "composition": "LoF_Linear(scaling='mx') (layers.py:366-377): mx_round(E4M3 / E8M0, block 32 along K) of both operands, then the GEMM "
+                           "with the accumulator rounded to 7 mantissa bits every k = 32 (= one MX block)",
+            "operands": "bf16 words (MX-rounded values are exact in bf16), row-sharded", "grid": f"{grid.R}x{grid.C}",
+            "timed_region": "operand exchange + GEMM; the two MX passes are timed separately",
+            "mx_passes": {"ms": ms_mx, "GBps_aggregate": 8.0 * (M * K + N * K) / (ms_mx * 1e-3) / 1e9},
+            "comm": {"collectives": ["all_gather_into_tensor (A row panel, row group)", "all_to_all_single (B^T column panel, world)"] if world > 1 else [],
+                     "bytes_received_per_rank": int(a_gather + b_recv)},
+            "finite": finite,
+            "roofline": {"bound": "tensor", "achieved": tf / world, "peak": bf16_burst, "unit": "TFLOP/s", "frac": tf / world / bf16_burst,
+                         "peak_source": f"{bf16_src} dense bf16 burst (operands are bf16 words)", "frac_of_nominal_bf16_2250": tf / world / 2250.0,
+                         "kernel": "gemm_tc_fold_kernel<RNE,Bf162,partial> (tcgen05 + per-chunk bfloat162 fold from TMEM)"}}
+        del A16, Wt16
+    except Exception as exc:
+        out["C5_mxfp8_gemm"] = {"error": str(exc)}
+    torch.cuda.empty_cache()
+    return out
 
 
 def side_measurements(torch, lib, _lib, dev, x, y, stream):
@@ -572,79 +765,83 @@ def _load_cpu_impl():
     return L, kind
 
 
+def _cpu_sweep_rates(L, kind, x_np, det_n, sto_n, threads):
+    """GB/s of the reference's scalar virtual_round for each of the 20 (format, mode) passes of the C2 sweep, on samples of
+    the workload's data: deterministic modes on the first det_n elements, the stochastic ones on the first sto_n (the
+    reference constructs and seeds a std::mt19937 per element there, lo_float.h:606, which is ~100x slower)."""
+    rates = {}
+    for fname, (bw, m, bias, ov, sg) in FORMATS:
+        f = L.fmt(bw, m, bias, ov, sg)
+        for mname, mode, sl in MODES:
+            xs = x_np[:sto_n] if mname.startswith("SR") else x_np[:det_n]
+            t0 = time.perf_counter()
+            if kind == "reference":
+                L.r_round_params(xs, f, mode, sl, threads=threads)
+            else:
+                L.o_round_params(xs, f, mode, sl, seed=1)
+            rates[f"{fname}/{mname}"] = 8.0 * xs.size / (time.perf_counter() - t0) / 1e9
+    return rates
+
+
+def _sweep_rate(rates):
+    """Rate of the whole sweep when every pass moves the SAME number of bytes, as it does in the workload: the harmonic mean
+    of the per-pass rates (a bytes-weighted mean over unequal samples would hide the slow stochastic passes)."""
+    return len(rates) / sum(1.0 / r for r in rates.values())
+
+
 def cpu_reference_sample(x_np, budget_s: float):
-    """Time the reference's scalar virtual_round (lo_float.h:2843-2939 looped by oracle/ref_shim.cpp,
-    OpenMP over all host threads) on a bounded sample of the same workload."""
+    """Time the reference's scalar virtual_round (lo_float.h:2843-2939 looped by oracle/ref_shim.cpp, OpenMP over all host
+    threads) on a bounded sample of the same workload; every (format, mode) pass weighs the same, as in the workload."""
     import numpy as np
     L, kind = _load_cpu_impl()
     threads = os.cpu_count() or 1
-    det_n = x_np.size
-    sto_n = min(x_np.size, 1 << 18)          # the reference re-seeds a std::mt19937 per element in the SR modes
-    total_bytes, total_s = 0.0, 0.0
-    t_start = time.perf_counter()
-    sweeps = 0
-    while True:                                  # repeat the 20-pass sweep until ~budget_s / 2 of CPU work has been timed
-        for fname, (bw, m, bias, ov, sg) in FORMATS:
-            f = L.fmt(bw, m, bias, ov, sg)
-            for mname, mode, sl in MODES:
-                xs = x_np[:sto_n] if mname.startswith("SR") else x_np[:det_n]
-                t0 = time.perf_counter()
-                if kind == "reference":
-                    L.r_round_params(xs, f, mode, sl, threads=threads)
-                else:
-                    L.o_round_params(xs, f, mode, sl, seed=1)
-                dt = time.perf_counter() - t0
-                total_bytes += 8.0 * xs.size
-                total_s += dt
-        sweeps += 1
-        if time.perf_counter() - t_start > budget_s * 0.5 or sweeps >= 64:
-            break
-    return {"value": total_bytes / total_s / 1e9, "unit": "GB/s", "cores": threads, "kind": kind,
-            "sample": f"same sweep on the first 2^{int(np.log2(det_n))} elements (SR modes: 2^{int(np.log2(sto_n))}), "
-                      f"scalar virtual_round loop, OpenMP x{threads}, {sweeps} sweeps = {total_s:.1f} s of CPU work"}
+    det_n, sto_n = x_np.size, min(x_np.size, 1 << 20)
+    t0 = time.perf_counter()
+    rates = _cpu_sweep_rates(L, kind, x_np, det_n, sto_n, threads)
+    total_s = time.perf_counter() - t0
+    det = [v for k, v in rates.items() if "SR" not in k]
+    return {"value": _sweep_rate(rates), "unit": "GB/s", "cores": threads, "kind": kind,
+            "deterministic_passes_GBps": len(det) / sum(1.0 / r for r in det),
+            "sample": f"the 20 passes of the sweep, each timed once: deterministic modes on the first 2^{int(np.log2(det_n))} elements, SR-A8 on "
+                      f"2^{int(np.log2(sto_n))}; value = harmonic mean of the per-pass rates (equal bytes per pass, as in the workload); scalar "
+                      f"virtual_round loop, OpenMP x{threads}, {total_s:.1f} s of CPU work"}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation on this box's host cores, same metric/config."""
+    """--impl reference: the reference's CPU implementation on this box's host cores, same metric/config.  One step = the
+    20-pass sweep on a 2^26-element sample of the workload's data (SR-A8 passes on 2^20 elements); the step's rate is the
+    harmonic mean of the per-pass rates, i.e. the rate of the real sweep in which every pass moves the same bytes."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     import numpy as np
     rng = np.random.default_rng(2024)
-    n = 1 << 24
-    x = (rng.standard_normal(n) * np.exp2(rng.integers(-12, 13, n))).astype(np.float32)
+    n = 1 << 26
+    x = (rng.standard_normal(n, dtype=np.float32) * np.exp2(rng.integers(-12, 13, n)).astype(np.float32)).astype(np.float32)
     L, kind = _load_cpu_impl()
     threads = os.cpu_count() or 1
-    sto_n = 1 << 18
-
-    def step():
-        nbytes = 0.0
-        for fname, (bw, m, bias, ov, sg) in FORMATS:
-            f = L.fmt(bw, m, bias, ov, sg)
-            for mname, mode, sl in MODES:
-                xs = x[:sto_n] if mname.startswith("SR") else x
-                if kind == "reference":
-                    L.r_round_params(xs, f, mode, sl, threads=threads)
-                else:
-                    L.o_round_params(xs, f, mode, sl, seed=1)
-                nbytes += 8.0 * xs.size
-        return nbytes
+    sto_n = 1 << 20
     for _ in range(min(args.warmup, 1)):
-        step()
+        _cpu_sweep_rates(L, kind, x, 1 << 22, 1 << 16, threads)
     t0 = time.perf_counter()
-    total = 0.0
+    steps = []
     for _ in range(args.steps):
-        total += step()
+        steps.append(_cpu_sweep_rates(L, kind, x, n, sto_n, threads))
+        if time.perf_counter() - t0 > 240.0:          # bounded: a slow host stops after ~4 minutes
+            break
     dt = time.perf_counter() - t0
-    value = total / dt / 1e9
-    sample = (f"each step = the 20-pass sweep on a 2^24-element sample (SR modes 2^18: the reference re-seeds a "
-              f"std::mt19937 per element), scalar virtual_round loop, OpenMP x{threads}")
+    mean_rates = {k: len(steps) / sum(1.0 / st[k] for st in steps) for k in steps[0]}
+    value = _sweep_rate(mean_rates)
+    sample = (f"each step = the 20-pass sweep on a 2^26-element sample (SR-A8 passes on 2^20: the reference seeds a std::mt19937 per "
+              f"element), value = harmonic mean of the per-pass rates (every pass weighs the same, as in the workload), scalar virtual_round "
+              f"loop, OpenMP x{threads}")
     print(json.dumps({
         "impl": "reference", "metric": "virtual_round_GBps", "value": value, "unit": "GB/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "steps": len(steps), "warmup": args.warmup, "ms_per_step": dt / len(steps) * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit arithmetic on fp32 containers", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
+        "per_pass_GBps": mean_rates,
         "cpu_baseline": {"value": value, "unit": "GB/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -657,6 +854,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--c5-size", type=int, default=32768, help="M = N = K of the C5 MXFP8 GEMM (BASELINE.json configs[4]: 32768)")
     ap.add_argument("--no-side", action="store_true", help="skip the mx/gemm side measurements and the CPU sample (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -221,6 +221,7 @@ LOF_API int lof_selftest_gemm_rne_round(uint64_t* dev_mismatches, void* stream);
 #define LOF_GEMM_NO_HW_ACCUM         4u   /* never let the tensor core keep the accumulator in fp16 (k_chunk == one MMA, E5M10, RNE) */
 #define LOF_GEMM_NO_PAIR             8u   /* never use the persistent CTA-pair (cta_group::2, 256 x 256 tile) main loop */
 #define LOF_GEMM_NO_PERSISTENT      16u   /* never use the persistent per-chunk fold kernel (keeps the first-generation one-tile-per-CTA kernel) */
+#define LOF_GEMM_NO_FLOAT_FOLD      32u   /* never round the accumulator in the float domain (integer routine only) */
 #define LOF_GEMM_STATUS_A_INEXACT    1    /* *dev_status bits */
 #define LOF_GEMM_STATUS_B_INEXACT    2
 #define LOF_GEMM_STATUS_PACKED_RANGE 4    /* informational: a hardware-format shortcut left the fp16 range, C was recomputed generically */

@@ -17,7 +17,7 @@ LOF_OK, LOF_ERR_INVALID_ARG, LOF_ERR_UNSUPPORTED, LOF_ERR_CUDA, LOF_ERR_NO_DEVIC
 # dtypes
 LOF_F32, LOF_F16, LOF_BF16, LOF_F64, LOF_E4M3, LOF_E5M2 = range(6)
 # lof_gemm_chunked_f32 flags / status bits
-LOF_GEMM_PARTIAL_ROUND, LOF_GEMM_NO_PACKED, LOF_GEMM_NO_HW_ACCUM, LOF_GEMM_NO_PAIR, LOF_GEMM_NO_PERSISTENT = 1, 2, 4, 8, 16
+LOF_GEMM_PARTIAL_ROUND, LOF_GEMM_NO_PACKED, LOF_GEMM_NO_HW_ACCUM, LOF_GEMM_NO_PAIR, LOF_GEMM_NO_PERSISTENT, LOF_GEMM_NO_FLOAT_FOLD = 1, 2, 4, 8, 16, 32
 LOF_GEMM_STATUS_A_INEXACT, LOF_GEMM_STATUS_B_INEXACT, LOF_GEMM_STATUS_PACKED_RANGE = 1, 2, 4
 
 # every symbol include/lofloat_b200.h declares (tests check the library exports all of them)

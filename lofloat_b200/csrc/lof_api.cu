@@ -60,6 +60,7 @@ struct Options {
     std::atomic<int64_t> host_chunk_bytes{32ll << 20};
     std::atomic<int64_t> pack_fast{1};           // storage codec: 0 = exact integer routine only, 1 = magic-add fast path where eligible
     std::atomic<int64_t> bf16_fast{2};           // bf16 containers on the magic path: 2 = unchecked kinds where the fp32 path is unchecked, 1 = always checked
+    std::atomic<int64_t> gemm_fold_split{1};     // packed fold GEMM, 128 x 256 tile: 1 = one N = 256 MMA per k-step (2 TMEM stages), 2 = two N = 128 MMAs (4 stages)
     std::atomic<int64_t> gemm_fast{1};           // exact GEMM: 1 = optimistic branch-free chain with a per-tile fallback, 0 = exact routines only
     std::atomic<int64_t> round_fast{2};          // 0: exact kernels; 1: branch-free fast path; 2: + magic-add path (default)
 } g_opt;
@@ -586,6 +587,7 @@ int lof_set_option(const char* key, int64_t value)
     else if (k == "stream.ctas_per_sm") { if (value < 1 || value > 64) return fail(LOF_ERR_INVALID_ARG, "stream.ctas_per_sm out of range"); g_opt.stream_ctas_per_sm = value; }
     else if (k == "pack.fast") { if (value < 0 || value > 1) return fail(LOF_ERR_INVALID_ARG, "pack.fast must be 0 or 1"); g_opt.pack_fast = value; }
     else if (k == "bf16.fast") { if (value < 1 || value > 2) return fail(LOF_ERR_INVALID_ARG, "bf16.fast must be 1 or 2"); g_opt.bf16_fast = value; }
+    else if (k == "gemm.fold_split") { if (value < 1 || value > 2) return fail(LOF_ERR_INVALID_ARG, "gemm.fold_split must be 1 or 2"); g_opt.gemm_fold_split = value; }
     else if (k == "gemm.fast") { if (value < 0 || value > 2) return fail(LOF_ERR_INVALID_ARG, "gemm.fast must be 0, 1 or 2"); g_opt.gemm_fast = value; }
     else if (k == "host.chunk_bytes") { if (value < (1 << 16)) return fail(LOF_ERR_INVALID_ARG, "host.chunk_bytes too small"); g_opt.host_chunk_bytes = value; }
     else return fail(LOF_ERR_INVALID_ARG, "unknown option: " + k);
@@ -604,6 +606,7 @@ int lof_get_option(const char* key, int64_t* value)
     else if (k == "stream.ctas_per_sm") *value = g_opt.stream_ctas_per_sm;
     else if (k == "pack.fast") *value = g_opt.pack_fast;
     else if (k == "gemm.fast") *value = g_opt.gemm_fast;
+    else if (k == "gemm.fold_split") *value = g_opt.gemm_fold_split;
     else if (k == "bf16.fast") *value = g_opt.bf16_fast;
     else if (k == "host.chunk_bytes") *value = g_opt.host_chunk_bytes;
     else return fail(LOF_ERR_INVALID_ARG, "unknown option: " + k);
@@ -798,7 +801,8 @@ int lof_gemm_chunked_f32(const float* A, const float* B, float* C, int64_t M, in
     int launches = 0;
     std::string err;
     cudaError_t e = launch_gemm_tc(A, B, C, M, N, K, mode, accum_mant_bits, acc_fmt, acc_fmt ? &plan : nullptr,
-                                   acc_fmt ? &fast : nullptr, k_chunk, alpha, operand_dtype, flags, dev_status,
+                                   acc_fmt ? &fast : nullptr, k_chunk, alpha, operand_dtype,
+                                   flags | (g_opt.gemm_fold_split.load() == 2 ? LOF_GEMM_INTERNAL_FOLD_SPLIT2 : 0u), dev_status,
                                    static_cast<cudaStream_t>(stream), &launches, &err);
     g_launches.fetch_add((uint64_t)launches);
     if (!err.empty()) return fail(LOF_ERR_UNSUPPORTED, err);
@@ -812,7 +816,7 @@ int lof_gemm_chunked_packed(const uint8_t* A, const uint8_t* Bt, float* C, int64
 {
     if (operand_dtype != LOF_E4M3 && operand_dtype != LOF_E5M2 && operand_dtype != LOF_BF16)
         return fail(LOF_ERR_INVALID_ARG, "lof_gemm_chunked_packed: operand_dtype must be LOF_E4M3, LOF_E5M2 or LOF_BF16");
-    if (flags & LOF_GEMM_INTERNAL_PACKED_OPERANDS) return fail(LOF_ERR_INVALID_ARG, "unknown flag");
+    if (flags & (LOF_GEMM_INTERNAL_PACKED_OPERANDS | LOF_GEMM_INTERNAL_FOLD_SPLIT2)) return fail(LOF_ERR_INVALID_ARG, "unknown flag");
     return lof_gemm_chunked_f32(reinterpret_cast<const float*>(A), reinterpret_cast<const float*>(Bt), C, M, N, K, accum_mant_bits,
                                 acc_fmt, ps, k_chunk, alpha, operand_dtype, flags | LOF_GEMM_INTERNAL_PACKED_OPERANDS, dev_status, stream);
 }

@@ -7,6 +7,8 @@ namespace lof {
 
 // internal flag of launch_gemm_tc (not part of the public flag set): A / B are 8-bit representations, B is K-major
 constexpr uint32_t LOF_GEMM_INTERNAL_PACKED_OPERANDS = 0x80000000u;
+// internal: the packed fold kernel issues two N = 128 MMAs per k-step into four TMEM stages (option gemm.fold_split = 2)
+constexpr uint32_t LOF_GEMM_INTERNAL_FOLD_SPLIT2 = 0x40000000u;
 
 // Operand addressing of the exact GEMM beyond plain row-major: the callers fused around lof_gemm.
 //   b_kind 0  B is K x N row-major (lof_gemm_f32 / lof_gemm_batched_f32)
@@ -53,6 +55,33 @@ __device__ __forceinline__ float rto_add(float a, float b)
     const float rd = __fadd_rd(a, b);
     const float ru = __fadd_ru(a, b);
     return (__float_as_uint(rd) & 1u) ? rd : ru;
+}
+
+
+// Mantissa rounding in the FLOAT domain (the chunked GEMM's per-chunk fold and the exact GEMM's optimistic chain): with
+// m = sign and exponent of t (+-2^e, one LOP3) and K = m * 2^r (an exact product),
+//     s = fma(m, 2^r, t) = round(t + K)      -- |t + K| stays inside the binade [2^(e+r), 2^(e+r+1)), whose ulp is 2^(e+r-23):
+//     y = fma(m, -2^r, s) = s - K   (exact)     the hardware rounds t on the grid of a (23 - r)-bit mantissa
+// The rounding MODE is the first FMA's: .rn = RoundToNearestEven (K / ulp = 2^23 is even, so ties go to even y), .rz =
+// RoundTowardsZero (K has t's sign), .rm / .rp = RoundDown / RoundUp.  Equal to the integer routine (round_bits + mask,
+// lo_float.h:2715-2756) for every NORMAL t with e + r < 127 and 1 <= r <= 22, checked on all 2^32 patterns x 22 widths x 4 modes
+// on the device (lof_selftest_gemm_rne_round); t = +-0 gives +-0; subnormal t is NOT rounded (K = 0) and larger t / inf /
+// NaN give a non-finite y -- callers guarantee the range (operands in an 8-bit format: sums are multiples of 2^-32 below 2^64).
+// One alu-pipe and two fma-pipe instructions instead of ~7 alu-pipe ones (the alu pipe is half rate).
+template <int MODE>
+__device__ __forceinline__ float round_mant_float(float t, float two_r)
+{
+    const float m = __uint_as_float(__float_as_uint(t) & 0xFF800000u);
+    float s;
+    if constexpr (MODE == LOF_RoundTowardsZero) s = __fmaf_rz(m, two_r, t);
+    else if constexpr (MODE == LOF_RoundDown) s = __fmaf_rd(m, two_r, t);
+    else if constexpr (MODE == LOF_RoundUp) s = __fmaf_ru(m, two_r, t);
+    else s = __fmaf_rn(m, two_r, t);
+    return __fmaf_rn(m, -two_r, s);
+}
+__host__ __device__ constexpr bool mode_has_float_round(int mode)
+{
+    return mode == LOF_RoundToNearestEven || mode == LOF_RoundTowardsZero || mode == LOF_RoundDown || mode == LOF_RoundUp;
 }
 
 }  // namespace lof

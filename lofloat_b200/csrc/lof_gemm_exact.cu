@@ -65,8 +65,7 @@ __device__ __forceinline__ float accum_round_signed(float t, int r, uint32_t kee
 __device__ __forceinline__ float accum_round_rne_float(float t, float two_r)
 {
     // K = m * 2^r is an exact product, so both steps are single FMAs: s = fma(m, 2^r, t) = RN(t + K), y = fma(m, -2^r, s) = s - K
-    const float m = __uint_as_float(__float_as_uint(t) & 0xFF800000u);
-    return __fmaf_rn(m, -two_r, __fmaf_rn(m, two_r, t));
+    return round_mant_float<LOF_RoundToNearestEven>(t, two_r);      // lof_gemm_common.cuh
 }
 
 // One 64 x 64 tile of C into `crun` (not stored).  VARIANT 0: the exact routines (rto_fma with its non-finite branch,
@@ -362,6 +361,19 @@ __global__ void selftest_rne_round_kernel(unsigned long long* mismatches)
             if (field == 255 || (int)field + r > 254) { bad += !nonfinite; continue; }     // out of range must surface as inf / NaN
             const uint32_t want = round_bits<LOF_RoundToNearestEven, uint32_t>(b, r, 0, true, 0) & ~((1u << r) - 1u);
             bad += __float_as_uint(y) != want && !((int)field + r == 254 && nonfinite);    // top binade: t + K may round up to 2^128
+            // the directed variants of the same step (chunked GEMM fold): RoundTowardsZero, RoundDown, RoundUp
+            const bool pos = (b >> 31) == 0u;
+            const uint32_t a = b & 0x7FFFFFFFu, sgn = b & 0x80000000u, keep = ~((1u << r) - 1u);
+            const float two_r = __uint_as_float((uint32_t)(127 + r) << 23), x = __uint_as_float(b);
+            const uint32_t w_rz = (round_bits<LOF_RoundTowardsZero, uint32_t>(a, r, 0, pos, 0) & keep) | sgn;
+            const uint32_t w_rd = (round_bits<LOF_RoundDown, uint32_t>(a, r, 0, pos, 0) & keep) | sgn;
+            const uint32_t w_ru = (round_bits<LOF_RoundUp, uint32_t>(a, r, 0, pos, 0) & keep) | sgn;
+            const float y_rz = round_mant_float<LOF_RoundTowardsZero>(x, two_r), y_rd = round_mant_float<LOF_RoundDown>(x, two_r),
+                        y_ru = round_mant_float<LOF_RoundUp>(x, two_r);
+            const bool top = (int)field + r == 254;                              // top binade: a round-up may reach 2^128 = inf
+            bad += __float_as_uint(y_rz) != w_rz;
+            bad += __float_as_uint(y_rd) != w_rd && !(top && !(fabsf(y_rd) < __int_as_float(0x7F800000)));
+            bad += __float_as_uint(y_ru) != w_ru && !(top && !(fabsf(y_ru) < __int_as_float(0x7F800000)));
         }
     }
     if (bad) atomicAdd(mismatches, bad);

@@ -74,8 +74,8 @@ constexpr int kEpiWarps = 8;
 constexpr int kColsPerThread = BN / 2;      // 64
 
 enum : int { kEpiMant = 0, kEpiFmt = 1, kEpiHalf2 = 2, kEpiBf162 = 3,
-             kEpiHw16 = 4 };     // the tensor core itself keeps the accumulator in fp16 (c_format = F16): no per-chunk read-back
-
+             kEpiHw16 = 4,      // the tensor core itself keeps the accumulator in fp16 (c_format = F16): no per-chunk read-back
+             kEpiMantFloat = 5 };
 struct TcArgs {
     int M, N, K;
     int k_steps;            // ceil(K * esize / 32): number of tcgen05.mma per output tile
@@ -84,6 +84,7 @@ struct TcArgs {
     int kind_f8;            // 1: kind::f8f6f4, 0: kind::f16
     float alpha;
     int r;                  // mantissa-only: fp32 mantissa bits to drop (23 - accum_mant_bits)
+    float two_r;            // 2^r (float-domain fold)
     RoundPlan plan;         // full-format accumulator
     FastPlan fast;
     int* status;            // device status word (never NULL)
@@ -115,6 +116,21 @@ __device__ __forceinline__ float round_acc(float t, const TcArgs& a)
 template <int MODE, int EPI, bool PARTIAL>
 __device__ __forceinline__ float fold(float acc, float p, const TcArgs& a)
 {
+    if constexpr (EPI == kEpiMantFloat) {
+        // mantissa-only accumulator, float-domain rounding (round_mant_float, lof_gemm_common.cuh): RNE / RTZ / RD / RU.
+        // The directed modes compose with the directed fp32 add (truncations / floors of truncations / floors); RNE needs the
+        // round-to-odd add so that the format rounding is the only rounding -- except under PARTIAL with a mantissa of <= 10 bits,
+        // where both summands are (m+1)-bit numbers and fp32 (24 >= 2 (m+1) + 2 bits) makes the double rounding innocuous.
+        const float two_r = a.two_r;
+        if constexpr (PARTIAL) p = round_mant_float<MODE>(p, two_r);
+        float t;
+        if constexpr (MODE == LOF_RoundTowardsZero) t = __fadd_rz(acc, p);
+        else if constexpr (MODE == LOF_RoundDown) t = __fadd_rd(acc, p);
+        else if constexpr (MODE == LOF_RoundUp) t = __fadd_ru(acc, p);
+        else if constexpr (PARTIAL) t = a.r >= 13 ? __fadd_rn(acc, p) : rto_add(acc, p);
+        else t = rto_add(acc, p);
+        return round_mant_float<MODE>(t, two_r);
+    }
     if constexpr (PARTIAL) p = round_acc<MODE, EPI>(p, a);
     return round_acc<MODE, EPI>(rto_add(acc, p), a);           // round-to-odd add: the format rounding is the only rounding
 }
@@ -515,11 +531,11 @@ cudaError_t launch_generic(int mode, bool fmt, bool partial, const CUtensorMap& 
 }
 
 // third-generation persistent fold kernel (lof_gemm_tc3.cuh)
-template <int EPI, bool PARTIAL, bool F8>
+template <int EPI, bool PARTIAL>
 cudaError_t launch_fold_mode(int mode, const CUtensorMap& ma, const CUtensorMap& mb, float* C, const TcArgs& a, int sms, cudaStream_t stream)
 {
     switch (mode) {
-#define LOF_CASE(Mo) case Mo: return launch_fold_one<Mo, EPI, PARTIAL, F8, 128>(ma, mb, C, a, sms, stream);
+#define LOF_CASE(Mo) case Mo: return launch_fold_one<Mo, EPI, PARTIAL, 128, 1>(ma, mb, C, a, sms, stream);
         LOF_CASE(LOF_RoundToNearestEven) LOF_CASE(LOF_RoundTowardsZero) LOF_CASE(LOF_RoundAwayFromZero)
         LOF_CASE(LOF_RoundToNearestOdd) LOF_CASE(LOF_RoundDown) LOF_CASE(LOF_RoundUp) LOF_CASE(LOF_RoundTiesToAway)
         LOF_CASE(LOF_RoundToOdd) LOF_CASE(LOF_RoundTiesTowardsZero)
@@ -528,24 +544,39 @@ cudaError_t launch_fold_mode(int mode, const CUtensorMap& ma, const CUtensorMap&
     }
 }
 
-cudaError_t launch_fold_generic(int mode, bool fmt, bool partial, bool f8, const CUtensorMap& ma, const CUtensorMap& mb, float* C,
-                                const TcArgs& a, int sms, cudaStream_t stream)
+template <bool PARTIAL>
+cudaError_t launch_fold_float(int mode, const CUtensorMap& ma, const CUtensorMap& mb, float* C, const TcArgs& a, int sms, cudaStream_t stream)
 {
-#define LOF_F(E, P) (f8 ? launch_fold_mode<E, P, true>(mode, ma, mb, C, a, sms, stream) : launch_fold_mode<E, P, false>(mode, ma, mb, C, a, sms, stream))
-    if (fmt) return partial ? LOF_F(kEpiFmt, true) : LOF_F(kEpiFmt, false);
-    return partial ? LOF_F(kEpiMant, true) : LOF_F(kEpiMant, false);
-#undef LOF_F
+    switch (mode) {
+    case LOF_RoundToNearestEven: return launch_fold_one<LOF_RoundToNearestEven, kEpiMantFloat, PARTIAL, 128, 1>(ma, mb, C, a, sms, stream);
+    case LOF_RoundTowardsZero:   return launch_fold_one<LOF_RoundTowardsZero, kEpiMantFloat, PARTIAL, 128, 1>(ma, mb, C, a, sms, stream);
+    case LOF_RoundDown:          return launch_fold_one<LOF_RoundDown, kEpiMantFloat, PARTIAL, 128, 1>(ma, mb, C, a, sms, stream);
+    case LOF_RoundUp:            return launch_fold_one<LOF_RoundUp, kEpiMantFloat, PARTIAL, 128, 1>(ma, mb, C, a, sms, stream);
+    default: return cudaErrorInvalidValue;
+    }
 }
 
-cudaError_t launch_fold_packed(int packed, bool f8, const CUtensorMap& ma, const CUtensorMap& mb, float* C, const TcArgs& a, int sms,
+cudaError_t launch_fold_generic(int mode, bool fmt, bool partial, const CUtensorMap& ma, const CUtensorMap& mb, float* C,
+                                const TcArgs& a, int sms, cudaStream_t stream, bool float_ok = false)
+{
+    // float-domain fold: mantissa-only accumulator, 1 <= r <= 22, RNE / RTZ / RD / RU, e4m3 operands (float_ok: every partial and
+    // accumulator is a multiple of 2^-18 below 2^50 -- normal or zero, far from the overflow of K = 2^(e+r))
+    if (float_ok && !fmt && a.r >= 1 && a.r <= 22 && mode_has_float_round(mode))
+        return partial ? launch_fold_float<true>(mode, ma, mb, C, a, sms, stream) : launch_fold_float<false>(mode, ma, mb, C, a, sms, stream);
+    if (fmt) return partial ? launch_fold_mode<kEpiFmt, true>(mode, ma, mb, C, a, sms, stream) : launch_fold_mode<kEpiFmt, false>(mode, ma, mb, C, a, sms, stream);
+    return partial ? launch_fold_mode<kEpiMant, true>(mode, ma, mb, C, a, sms, stream) : launch_fold_mode<kEpiMant, false>(mode, ma, mb, C, a, sms, stream);
+}
+
+cudaError_t launch_fold_packed(int packed, bool split2, const CUtensorMap& ma, const CUtensorMap& mb, float* C, const TcArgs& a, int sms,
                                cudaStream_t stream)
 {
     constexpr int RNE = LOF_RoundToNearestEven;
-    if (packed == kEpiHalf2)
-        return f8 ? launch_fold_one<RNE, kEpiHalf2, true, true, 256>(ma, mb, C, a, sms, stream)
-                  : launch_fold_one<RNE, kEpiHalf2, true, false, 256>(ma, mb, C, a, sms, stream);
-    return f8 ? launch_fold_one<RNE, kEpiBf162, true, true, 256>(ma, mb, C, a, sms, stream)
-              : launch_fold_one<RNE, kEpiBf162, true, false, 256>(ma, mb, C, a, sms, stream);
+    if (split2) {
+        if (packed == kEpiHalf2) return launch_fold_one<RNE, kEpiHalf2, true, 256, 2>(ma, mb, C, a, sms, stream);
+        return launch_fold_one<RNE, kEpiBf162, true, 256, 2>(ma, mb, C, a, sms, stream);
+    }
+    if (packed == kEpiHalf2) return launch_fold_one<RNE, kEpiHalf2, true, 256, 1>(ma, mb, C, a, sms, stream);
+    return launch_fold_one<RNE, kEpiBf162, true, 256, 1>(ma, mb, C, a, sms, stream);
 }
 
 // Is the packed half2 / bfloat162 epilogue bit-identical to the generic routine for this request?
@@ -674,6 +705,10 @@ cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, 
     a.kind_f8 = (op != kOpBF16);
     a.alpha = alpha;
     a.r = acc_fmt ? 0 : 23 - accum_mant_bits;
+    {
+        const uint32_t bits = (uint32_t)(127 + (a.r > 0 && a.r < 100 ? a.r : 0)) << 23;
+        memcpy(&a.two_r, &bits, 4);
+    }
     if (acc_plan) a.plan = *acc_plan;
     if (acc_fast) a.fast = *acc_fast;
     a.status = status;
@@ -719,10 +754,12 @@ cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, 
     }
     // third-generation persistent fold kernel for everything that needs the per-chunk software fold
     if ((flags & LOF_GEMM_NO_PERSISTENT) == 0 && !hw16 && sms >= 1 && K > 0) {
-        const bool f8 = op != kOpBF16;
         if (packed >= 0) {
             a.run_mask = 0; a.run_value = 0;
-            e = launch_fold_packed(packed, f8, ma, mb, C, a, sms, stream);
+            const bool split2 = (flags & LOF_GEMM_INTERNAL_FOLD_SPLIT2) != 0;
+            TcArgs ap = a;
+            if (!split2) ap.idesc = make_idesc(op, false, F_BM, 256);       // one N = 256 MMA per k-step (else two of N = 128: a.idesc as it is)
+            e = launch_fold_packed(packed, split2, ma, mb, C, ap, sms, stream);
             ++*launches;
             if (e != cudaSuccess) return fail(e);
             a.run_mask = LOF_GEMM_STATUS_PACKED_RANGE; a.run_value = LOF_GEMM_STATUS_PACKED_RANGE;   // left the fp16 range: generic recompute
@@ -730,7 +767,8 @@ cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, 
             a.run_mask = 0; a.run_value = 0;
         }
         if (packed != kEpiBf162) {          // the bfloat162 fold has no range condition (packed_epi): nothing to gate
-            e = launch_fold_generic(mode, acc_fmt != nullptr, partial, f8, ma, mb, C, a, sms, stream);
+            e = launch_fold_generic(mode, acc_fmt != nullptr, partial, ma, mb, C, a, sms, stream,
+                                    op == kOpE4M3 && (flags & LOF_GEMM_NO_FLOAT_FOLD) == 0);
             ++*launches;
             if (e != cudaSuccess) return fail(e);
         }

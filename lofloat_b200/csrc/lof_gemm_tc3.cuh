@@ -11,27 +11,43 @@
 // staging per prefetch) was latency-bound.  Here:
 //   * one CTA per SM walks a static tile schedule; the smem ring, the TMEM ring and their phases run on across tiles, so the
 //     TMA producer and the MMA issuer are always ahead of the fold (they start the next tile while C is being written);
-//   * packed accumulators (half2 / bfloat162): tile 128 x 256, thread = 1 row x 128 columns = 64 registers of accumulator,
-//     TMEM ring 2 x 256 columns; fp32 accumulators (generic fold): tile 128 x 128, 64 registers, TMEM ring 4 x 128 columns;
+//   * packed accumulators (half2 / bfloat162): tile 128 x 256, thread = 1 row x 128 columns = 64 registers of accumulator;
+//     fp32 accumulators (generic fold): tile 128 x 128, 64 registers;
+//   * TMEM is a ring of FOUR 128-column stages in both cases.  A 256-wide tile issues TWO MMAs of N = 128 per k-step (column
+//     halves j = 0, 1 into stages 2i + j) and each half is drained by the four warps that own those columns.  Why not one
+//     N = 256 MMA into two 256-column stages: scripts/probe_fold_pipeline.cu measures the issue -> commit-visible LATENCY of one
+//     128 x 256 x 32 MMA at ~420 clk (throughput 128 clk) and a barrier hop at ~60 clk, so the tensor core has to run ~550 clk
+//     ahead of the fold; two stages allow one chunk (~280 clk of fold) of look-ahead and the loop ran at RTT / 1.25 = ~710 clk per
+//     chunk with the fold and the MMA latency in series (profiles/r02d_probe_fold_pipeline.txt, ncu r02c: 34 % of the fold
+//     warps' time on the next chunk's full barrier, tensor pipe 15 %).  Four half-width stages give 1.5 chunks of look-ahead;
 //   * the partial is pulled out in 32-column units through two 32-register buffers, the tcgen05.ld of unit u + 1 in flight
 //     while unit u is folded; a TMEM stage is handed back as soon as its last unit has landed, BEFORE that unit is folded,
 //     and the full-barrier of the next chunk is only polled (try_wait) ahead of the fold -- the blocking wait comes after it.
 // Per-chunk cost model (per SM, packed fold, 128 x 256 x 32 chunk): MMA 128 clk (FP8) / 256 clk (bf16 operands), read-back
-// 128 KB / ~800 B/clk = 160 clk, fold 16384 cvt.rn.x2 (half-rate alu pipe: 256 clk) + 16384 HADD2 (128 clk on the fma pipe).
-// The fold's conversion instructions bound the kernel; the tensor pipe can reach ~50 % (FP8) / ~100 % (bf16 operands).
+// 128 KB / ~800 B/clk = 160 clk, fold 8192 cvt.rn.x2 + 8192 HADD2 per SMSP-pair of warps = ~280 clk (both half-rate, on
+// different pipes: scripts/probe_cvt.cu).  The fold's conversion / add instructions bound the kernel.
 
 constexpr int F_BM = 128;
 constexpr int F_THREADS = 384;                  // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4..11 fold
 constexpr int F_EPI_WARPS = 8;
 constexpr int F_SMEM_BUDGET = 192 * 1024;       // operand ring
 
-template <int BN> struct FoldGeom {
+// BN: columns of the CTA tile (accumulators in registers).  SPLIT: MMAs per k-step -- each covers SW = BN / SPLIT columns and
+// writes its own TMEM stage, so TMEM is a ring of 512 / SW stages:
+//   <128, 1>  fp32 accumulators:   4 stages x 128 columns, one N = 128 MMA per k-step, a stage is drained by all 8 fold warps
+//   <256, 1>  packed accumulators: 2 stages x 256 columns, one N = 256 MMA per k-step (fewest instructions on the issuing thread)
+//   <256, 2>  packed accumulators: 4 stages x 128 columns, two N = 128 MMAs per k-step, a stage is drained by the 4 warps of its
+//             column half (1.5 instead of 1 chunk of look-ahead for the tensor core, twice the issue work)
+template <int BN, int SPLIT> struct FoldGeom {
     static constexpr int kStageA = F_BM * kRowBytes;                 // 16 KB
     static constexpr int kStageB = BN * kRowBytes;                   // 16 / 32 KB
     static constexpr int kStages = F_SMEM_BUDGET / (kStageA + kStageB);   // 6 (BN = 128) / 4 (BN = 256)
     static constexpr int kSmem = kStages * (kStageA + kStageB) + 1024;
-    static constexpr int kTmemStages = 512 / BN;                     // 4 / 2
+    static constexpr int kSplit = SPLIT;
+    static constexpr int kSW = BN / SPLIT;                           // columns per TMEM stage = N of one MMA
+    static constexpr int kTmemStages = 512 / kSW;
     static constexpr int kColsPerThread = BN / 2;                    // two column halves x four lane quarters = 8 warps
+    static constexpr int kWarpsPerStage = F_EPI_WARPS / SPLIT;       // fold warps that drain one TMEM stage
 };
 
 struct FoldArgs {
@@ -50,12 +66,12 @@ __device__ __forceinline__ void fold_tile_coords(int tile, const TcArgs& a, int&
     tn = (tile % per_group) / gsz;
 }
 
-template <int MODE, int EPI, bool PARTIAL, bool F8, int BN>
+template <int MODE, int EPI, bool PARTIAL, int BN, int SPLIT>
 __global__ void __launch_bounds__(F_THREADS, 1)
 gemm_tc_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, float* __restrict__ C,
                     const FoldArgs fa)
 {
-    using G = FoldGeom<BN>;
+    using G = FoldGeom<BN, SPLIT>;
     const TcArgs& args = fa.t;
     if ((*args.status & args.run_mask) != args.run_value) return;      // device-side conditional launch (uniform)
 
@@ -77,7 +93,7 @@ gemm_tc_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
         for (int s = 0; s < G::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
 #pragma unroll
-        for (int s = 0; s < G::kTmemStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], F_EPI_WARPS); }
+        for (int s = 0; s < G::kTmemStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], G::kWarpsPerStage); }
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc(&tmem_base_slot, 512);
@@ -108,32 +124,53 @@ gemm_tc_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     } else if (warp == 1) {
         // ====================================== MMA issuer ======================================
         if (elect_one()) {
-            uint32_t stage = 0, phase = 0, ts = 0, tphase = 0;
-            const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
+            // This thread's instruction stream is the tensor core's supply line (every instruction of a single thread costs several
+            // clocks): descriptors are kept as running low words (the high word of umma_desc_k128 is a constant, and adding
+            // bytes >> 4 to the low word never carries out of its 14-bit address field), the k-steps of a shared-memory stage
+            // are unrolled, and the chunk bookkeeping is one counter.
+            uint32_t stage = 0, phase = 0, ts = 0, tphase = 0;      // ts: first TMEM stage of the current chunk
+            const uint64_t desc0 = umma_desc_k128(0);
+            const uint32_t desc_hi = (uint32_t)(desc0 >> 32), desc_lo0 = (uint32_t)desc0;
+            const uint32_t a_lo_base = desc_lo0 + (smem_u32(smem_a) >> 4), b_lo_base = desc_lo0 + (smem_u32(smem_b) >> 4);
             const uint32_t idesc = args.idesc;
+            const bool f8 = args.kind_f8 != 0;
+            const int spc = args.steps_per_chunk;
+            auto mk = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | lo; };
             for (int tile = blockIdx.x; tile < fa.n_tiles; tile += gridDim.x) {
-                int step = 0;
-                for (int c = 0; c < n_chunks; ++c) {
-                    mbar_wait(&tmem_empty_bar[ts], tphase ^ 1u);
+                int k_left = args.k_steps;              // k-steps of this tile still to issue
+                int in_chunk = 0;                       // k-steps of the current chunk still to issue (0: the next MMA opens a chunk)
+                for (int it = 0; it < n_stage_iters; ++it) {
+                    mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + ts * BN;
-                    const int steps_here = min(args.steps_per_chunk, args.k_steps - step);
-                    for (int j = 0; j < steps_here; ++j, ++step) {
-                        const int sub = step & (kStepsPerStage - 1);
-                        if (sub == 0) {
-                            mbar_wait(&full_bar[stage], phase);
-                            tc_fence_after();
-                        }
-                        const uint64_t adesc = umma_desc_k128(a_base + stage * G::kStageA + sub * kStepBytes);
-                        const uint64_t bdesc = umma_desc_k128(b_base + stage * G::kStageB + sub * kStepBytes);
-                        umma_t<F8>(tmem_d, adesc, bdesc, idesc, j > 0 ? 1u : 0u);
-                        if (sub == kStepsPerStage - 1 || step == args.k_steps - 1) {                         // stage consumed
-                            umma_commit(&empty_bar[stage]);
-                            if (++stage == (uint32_t)G::kStages) { stage = 0; phase ^= 1u; }
+                    const uint32_t a_lo = a_lo_base + stage * (G::kStageA >> 4), b_lo = b_lo_base + stage * (G::kStageB >> 4);
+#pragma unroll
+                    for (int sub = 0; sub < kStepsPerStage; ++sub) {
+                        if (k_left > 0) {
+                            const bool first = (in_chunk == 0);
+                            if (first) in_chunk = min(spc, k_left);
+                            const bool last = (in_chunk == 1);
+#pragma unroll
+                            for (int hh = 0; hh < SPLIT; ++hh) {                  // one MMA of N = kSW per TMEM stage of the chunk
+                                if (first) {                                     // first MMA into this TMEM stage: it must have been drained
+                                    mbar_wait(&tmem_empty_bar[ts + hh], tphase ^ 1u);
+                                    tc_fence_after();
+                                }
+                                const uint64_t adesc = mk(a_lo + sub * (kStepBytes >> 4));
+                                const uint64_t bdesc = mk(b_lo + hh * ((G::kSW * kRowBytes) >> 4) + sub * (kStepBytes >> 4));
+                                const uint32_t tmem_d = tmem_base + (ts + hh) * G::kSW;
+                                if (f8) umma_t<true>(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);        // uniform branch (one elected thread)
+                                else umma_t<false>(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
+                                if (last) umma_commit(&tmem_full_bar[ts + hh]);                          // this stage of the chunk is ready
+                            }
+                            --k_left;
+                            if (--in_chunk == 0) {
+                                ts += SPLIT;
+                                if (ts == (uint32_t)G::kTmemStages) { ts = 0; tphase ^= 1u; }
+                            }
                         }
                     }
-                    umma_commit(&tmem_full_bar[ts]);                                                         // chunk ready
-                    if (++ts == (uint32_t)G::kTmemStages) { ts = 0; tphase ^= 1u; }
+                    umma_commit(&empty_bar[stage]);                                                       // smem stage consumed
+                    if (++stage == (uint32_t)G::kStages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -150,13 +187,17 @@ gemm_tc_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         float acc[kPacked ? 1 : CPT];
         uint32_t accp[kPacked ? CPT / 2 : 1];
         uint32_t buf0[32], buf1[32];
-        uint32_t ts = 0, tphase = 0;                    // TMEM stage / phase of the chunk whose units are being ISSUED
-        uint32_t rs = 0;                                // TMEM stage of the chunk whose units are LANDING (released after its last unit)
+        // TMEM stage of this warp's columns of the current chunk: SPLIT = 2 -> stage cs + h holds exactly this warp's 128 columns;
+        // SPLIT = 1 -> stage cs holds all of the tile's columns, this warp's start at column h * CPT
+        uint32_t cs = 0, tphase = 0;
+        constexpr uint32_t kStageOfHalf = (G::kSplit == 2) ? 1u : 0u, kColOfHalf = (G::kSplit == 2) ? 0u : (uint32_t)CPT;
+        constexpr uint32_t kSW = (uint32_t)G::kSW;
         bool bad = false;
 
-        auto issue_unit = [&](int u, uint32_t* buf) {   // start loading unit u of the chunk in stage ts
-            tmem_ld32(tmem_base + t_lane + (uint32_t)(ts * BN + h * CPT + u * 32), buf);
+        auto issue_unit = [&](int u, uint32_t* buf) {   // start loading unit u of this warp's columns of the chunk in stage cs (+ h)
+            tmem_ld32(tmem_base + t_lane + (cs + kStageOfHalf * h) * kSW + kColOfHalf * h + (uint32_t)(u * 32), buf);
         };
+        auto full_bar_of = [&]() { return &tmem_full_bar[cs + kStageOfHalf * h]; };
         auto fold_unit = [&](int u, const uint32_t* p) {
             if constexpr (EPI == kEpiHalf2) {
 #pragma unroll
@@ -197,7 +238,7 @@ gemm_tc_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
 
             // first unit of the tile
-            mbar_wait(&tmem_full_bar[ts], tphase);
+            mbar_wait(full_bar_of(), tphase);
             tc_fence_after();
             issue_unit(0, buf0);
             for (int c = 0; c < n_chunks; ++c) {
@@ -214,17 +255,17 @@ gemm_tc_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         // last unit of chunk c has landed: hand its TMEM stage back to the MMA issuer before folding it
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&tmem_empty_bar[rs]);
-                        if (++rs == (uint32_t)G::kTmemStages) rs = 0;
-                        if (++ts == (uint32_t)G::kTmemStages) { ts = 0; tphase ^= 1u; }
+                        if (lane == 0) mbar_arrive(&tmem_empty_bar[cs + kStageOfHalf * h]);
+                        cs += G::kSplit;
+                        if (cs == (uint32_t)G::kTmemStages) { cs = 0; tphase ^= 1u; }
                         if (c + 1 < n_chunks) {
-                            issued = mbar_try_wait(&tmem_full_bar[ts], tphase);     // poll only: fold first if the next chunk is not ready
+                            issued = mbar_try_wait(full_bar_of(), tphase);          // poll only: fold first if the next chunk is not ready
                             if (issued) { tc_fence_after(); issue_unit(0, nxt); }
                         }
                     }
                     fold_unit(u, cur);
                     if (!issued) {                                      // (UNITS is even: nxt == buf0 here, as the next chunk expects)
-                        mbar_wait(&tmem_full_bar[ts], tphase);
+                        mbar_wait(full_bar_of(), tphase);
                         tc_fence_after();
                         issue_unit(0, nxt);
                     }
@@ -274,11 +315,11 @@ gemm_tc_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-template <int MODE, int EPI, bool PARTIAL, bool F8, int BN>
+template <int MODE, int EPI, bool PARTIAL, int BN, int SPLIT>
 cudaError_t launch_fold_one(const CUtensorMap& ma, const CUtensorMap& mb, float* C, const TcArgs& a, int num_sms, cudaStream_t stream)
 {
-    using G = FoldGeom<BN>;
-    auto kern = gemm_tc_fold_kernel<MODE, EPI, PARTIAL, F8, BN>;
+    using G = FoldGeom<BN, SPLIT>;
+    auto kern = gemm_tc_fold_kernel<MODE, EPI, PARTIAL, BN, SPLIT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmem);
     if (e != cudaSuccess) return e;
     FoldArgs fa;

@@ -237,21 +237,15 @@ round_vec_kernel(const uint4* in, uint4* out, int64_t nvec, int ntail,
     using B = typename Src<DTYPE>::bits_t;
     constexpr int VEC = 16 / (int)sizeof(B);
     constexpr int64_t TILE = (int64_t)kRoundThreads * UNROLL;
-    // Work split of the persistent grid: every CTA takes the same number of WHOLE tiles (tile = blockIdx.x + k * gridDim.x), and
-    // what is left -- fewer than gridDim.x tiles plus the ragged end -- is dealt out in ROWS of kRoundThreads vectors, so that no
-    // CTA carries more than one row over the average.  With tile-granular dealing the last round leaves most SMs idle: at
-    // n = 2^24 (C1; 4096 tiles on 444 CTAs) that was 10 tiles for some CTAs against an average of 9.2, ~8 % of the run.
-    const int64_t rounds = (nvec / TILE) / gridDim.x;
+    const int64_t ntiles = (nvec + TILE - 1) / TILE;
 
-    for (int64_t k = 0; k < rounds; ++k) {
-        const int64_t tile = blockIdx.x + k * gridDim.x;
-        const int64_t base = tile * TILE + threadIdx.x;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         if constexpr (ModeTraits<MODE>::kUsesRng && DTYPE == LOF_BF16 && UNROLL == 4 && (kind_is_fast(KIND) || kind_is_magic(KIND))) {
             // 16-bit containers, class-0 events: a tile is 8192 elements = two aligned runs of 4096; thread t takes, in run
             // t >> 7, the vectors w * 128 + (t & 127), w = 0..3, i.e. the 4-element groups v = w * 256 + 2 (t & 127) + {0, 1}
             // of that run -- all four words of the two Philox blocks (run, 2 (t & 127)) and (run, 2 (t & 127) + 1): one block
             // per 16 elements like the fp32 layout (two blocks per 8-element vector before).  Same event stream as philox_group4.
-            if (rng.cls == 0u && (first_index & 4095u) == 0u) {
+            if (rng.cls == 0u && (first_index & 4095u) == 0u && (tile + 1) * TILE <= nvec) {
                 const uint32_t t = threadIdx.x, kk = t & 127u;
                 const uint64_t run = (first_index >> 12) + (uint64_t)tile * 2u + (t >> 7);
                 const int64_t vbase = tile * TILE + (int64_t)(t >> 7) * 512 + kk;
@@ -266,9 +260,13 @@ round_vec_kernel(const uint4* in, uint4* out, int64_t nvec, int ntail,
                 continue;
             }
         }
+        const int64_t base = tile * TILE + threadIdx.x;
         uint4 v[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) v[u] = ld_stream(in + base + (int64_t)u * kRoundThreads);
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t idx = base + (int64_t)u * kRoundThreads;
+            if (idx < nvec) v[u] = ld_stream(in + idx);
+        }
         if constexpr (ModeTraits<MODE>::kUsesRng && sizeof(B) == 4 && UNROLL == 4) {
             // class-0 events (<= 8 random bits): the 4 vectors of this thread in this 4096-element tile share ONE
             // Philox block by construction of the event stream (lof_core.cuh) when the tile grid is aligned with it
@@ -276,32 +274,19 @@ round_vec_kernel(const uint4* in, uint4* out, int64_t nvec, int ntail,
                 const uint4 b = philox_block(rng, ((first_index >> 12) + (uint64_t)tile) * 256u + threadIdx.x);
                 const uint32_t wu[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u)
-                    st_stream(out + base + (int64_t)u * kRoundThreads, round_vec16_w<DTYPE, MODE, KIND>(v[u], op, bytes_of(wu[u])));
+                for (int u = 0; u < UNROLL; ++u) {
+                    const int64_t idx = base + (int64_t)u * kRoundThreads;
+                    if (idx < nvec) st_stream(out + idx, round_vec16_w<DTYPE, MODE, KIND>(v[u], op, bytes_of(wu[u])));
+                }
                 continue;
             }
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const int64_t idx = base + (int64_t)u * kRoundThreads;
-            st_stream(out + idx, round_vec16<DTYPE, MODE, KIND>(v[u], op, rng, first_index + (uint64_t)idx * VEC));
-        }
-    }
-    // the remainder, in rows of kRoundThreads vectors dealt out cyclically (at most UNROLL + 1 rows per CTA)
-    {
-        const int64_t rem0 = rounds * gridDim.x * TILE;
-        const int64_t nrows = (nvec - rem0 + kRoundThreads - 1) / kRoundThreads;
-        for (int64_t r0 = blockIdx.x; r0 < nrows; r0 += (int64_t)gridDim.x * UNROLL) {
-            uint4 v[UNROLL];
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int64_t idx = rem0 + (r0 + (int64_t)u * gridDim.x) * kRoundThreads + threadIdx.x;
-                if (idx < nvec) v[u] = ld_stream(in + idx);
-            }
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int64_t idx = rem0 + (r0 + (int64_t)u * gridDim.x) * kRoundThreads + threadIdx.x;
-                if (idx < nvec) st_stream(out + idx, round_vec16<DTYPE, MODE, KIND>(v[u], op, rng, first_index + (uint64_t)idx * VEC));
+            if (idx < nvec) {
+                const uint4 r = round_vec16<DTYPE, MODE, KIND>(v[u], op, rng, first_index + (uint64_t)idx * VEC);
+                st_stream(out + idx, r);
             }
         }
     }

@@ -279,7 +279,7 @@ def lof_gemm(A: torch.Tensor, B: torch.Tensor, accum_mant_bits: int, round_mode=
              stochastic_rounding_bits: int = 0, scale_a: float = 1.0, scale_b: float = 1.0, *, kc=None,
              k_chunk=None, accum_format: FloatFormatDescriptor | None = None, operand_dtype: str = "e4m3",
              partial_round: bool = False, allow_packed: bool = True, allow_hw_accum: bool = True, allow_pair: bool = True,
-             allow_persistent: bool = True, check: bool = True, rng=None) -> torch.Tensor:
+             allow_persistent: bool = True, allow_float_fold: bool = True, check: bool = True, rng=None) -> torch.Tensor:
     """Low-precision-accumulation GEMM, float32 row-major (Lof_kernel.cu:96-154, LoPy_bind.cpp:361-372).
     The output is divided by scale_a*scale_b (a zero product counts as 1, cutlass_gemms.cuh:1784-1786).
 
@@ -312,7 +312,7 @@ def lof_gemm(A: torch.Tensor, B: torch.Tensor, accum_mant_bits: int, round_mode=
             fmt = accum_format._c() if accum_format is not None else None
             flags = ((_lib.LOF_GEMM_PARTIAL_ROUND if partial_round else 0) | (0 if allow_packed else _lib.LOF_GEMM_NO_PACKED) |
                      (0 if allow_hw_accum else _lib.LOF_GEMM_NO_HW_ACCUM) | (0 if allow_pair else _lib.LOF_GEMM_NO_PAIR) |
-                     (0 if allow_persistent else _lib.LOF_GEMM_NO_PERSISTENT))
+                     (0 if allow_persistent else _lib.LOF_GEMM_NO_PERSISTENT) | (0 if allow_float_fold else _lib.LOF_GEMM_NO_FLOAT_FOLD))
             status = torch.zeros(1, dtype=torch.int32, device=A.device)
             st = L.lof_gemm_chunked_f32(A_c.data_ptr(), B_c.data_ptr(), out.data_ptr(), M, N, K, int(accum_mant_bits),
                                         C.byref(fmt) if fmt is not None else None, C.byref(ps), int(k_chunk), alpha,
@@ -653,7 +653,7 @@ def mx_encode(input: torch.Tensor, block_size: int, element_format: FloatFormatD
     x = input.contiguous()
     n = x.numel()
     if int(block_size) <= 0 or n % int(block_size) != 0:
-        raise RuntimeError(f"mx_encode: numel ({n}) must be a multiple of block_size ({block_size})")
+        raise LoFloatError(_lib.LOF_ERR_INVALID_ARG, f"mx_encode: numel ({n}) must be a multiple of block_size ({block_size})")
     cfe, cfs = codec_format(element_format), codec_format(scale_format)
     scales = torch.empty(n // int(block_size), dtype=torch.uint8, device=x.device)
     elems = torch.empty(packed_size(element_format.total_bits, n), dtype=torch.uint8, device=x.device)
@@ -673,12 +673,12 @@ def mx_decode(scales: torch.Tensor, elems: torch.Tensor, count: int, block_size:
         raise RuntimeError(f"mx_decode: scales ({scales.device}) and elems ({elems.device}) must be on the same device")
     count, block_size = int(count), int(block_size)
     if block_size <= 0 or count < 0 or count % block_size != 0:
-        raise RuntimeError(f"mx_decode: count ({count}) must be a non-negative multiple of block_size ({block_size})")
+        raise LoFloatError(_lib.LOF_ERR_INVALID_ARG, f"mx_decode: count ({count}) must be a non-negative multiple of block_size ({block_size})")
     if scales.numel() < count // block_size:
-        raise RuntimeError(f"mx_decode: {scales.numel()} scale bytes for {count // block_size} blocks")
+        raise LoFloatError(_lib.LOF_ERR_INVALID_ARG, f"mx_decode: {scales.numel()} scale bytes for {count // block_size} blocks")
     need = packed_size(element_format.total_bits, count)
     if elems.numel() < need:
-        raise RuntimeError(f"mx_decode: {elems.numel()} packed bytes, {need} needed for {count} {element_format.total_bits}-bit elements")
+        raise LoFloatError(_lib.LOF_ERR_INVALID_ARG, f"mx_decode: {elems.numel()} packed bytes, {need} needed for {count} {element_format.total_bits}-bit elements")
     L = _lib.lib()
     cfe, cfs = codec_format(element_format), codec_format(scale_format)
     out = torch.empty(int(count), dtype=torch.float32, device=elems.device)
@@ -693,7 +693,7 @@ def lof_gemm_packed(A: torch.Tensor, Bt: torch.Tensor, accum_mant_bits: int, rou
                     scale_a: float = 1.0, scale_b: float = 1.0, *, k_chunk: int = 32,
                     accum_format: FloatFormatDescriptor | None = None, operand_dtype: str = "e4m3",
                     partial_round: bool = False, allow_packed: bool = True, allow_hw_accum: bool = True,
-                    allow_pair: bool = True, allow_persistent: bool = True) -> torch.Tensor:
+                    allow_pair: bool = True, allow_persistent: bool = True, allow_float_fold: bool = True) -> torch.Tensor:
     """Chunked tensor-core GEMM on operands already stored in the tensor core's operand type: OCP 8-bit representations
     (uint8, operand_dtype "e4m3" / "e5m2") or bfloat16 tensors (operand_dtype is then "bf16").  A is [M, K], Bt is
     [N, K] (the [out_features, in_features] weight layout).  C = A @ Bt^T / (scale_a * scale_b), float32 [M, N]."""
@@ -721,7 +721,7 @@ def lof_gemm_packed(A: torch.Tensor, Bt: torch.Tensor, accum_mant_bits: int, rou
     fmt = accum_format._c() if accum_format is not None else None
     flags = ((_lib.LOF_GEMM_PARTIAL_ROUND if partial_round else 0) | (0 if allow_packed else _lib.LOF_GEMM_NO_PACKED) |
              (0 if allow_hw_accum else _lib.LOF_GEMM_NO_HW_ACCUM) | (0 if allow_pair else _lib.LOF_GEMM_NO_PAIR) |
-             (0 if allow_persistent else _lib.LOF_GEMM_NO_PERSISTENT))
+             (0 if allow_persistent else _lib.LOF_GEMM_NO_PERSISTENT) | (0 if allow_float_fold else _lib.LOF_GEMM_NO_FLOAT_FOLD))
     with torch.cuda.device(A.device):
         st = L.lof_gemm_chunked_packed(A_c.data_ptr(), B_c.data_ptr(), out.data_ptr(), M, N, K, int(accum_mant_bits),
                                        C.byref(fmt) if fmt is not None else None, C.byref(ps), int(k_chunk), alpha,

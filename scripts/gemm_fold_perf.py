@@ -46,6 +46,14 @@ cases = {
     "e4m3_k128_mant7_partial_bf162": (A8, Bt8, 7, dict(k_chunk=128, partial_round=True)),
     "e4m3_k512_mant7_single_generic": (A8, Bt8, 7, dict(k_chunk=512)),
 }
+split_cases = ("e4m3_k32_mant7_partial_bf162", "bf16ops_k32_mant7_partial_bf162", "e4m3_k128_mant7_partial_bf162")
+for name in split_cases:                                # packed fold, 128 x 256 tile: one N = 256 MMA per k-step vs two N = 128 MMAs
+    a, bt, mant, kw = cases[name]
+    for split in (1, 2):
+        lof.set_option("gemm.fold_split", split)
+        ms = timeit(lambda: lof.lof_gemm_packed(a, bt, mant, **kw))
+        res[f"{name}_split{split}"] = {"ms": round(ms, 4), "TFLOPs": round(flops / (ms * 1e-3) / 1e12, 1)}
+lof.set_option("gemm.fold_split", 1)
 for name, (a, bt, mant, kw) in cases.items():
     for pers in (True, False):
         if not pers and "generic" in name and n > 4096 and "k512" not in name:

@@ -96,6 +96,21 @@ def main():
         B = lof.virtual_round(torch.rand(M, M, device=dev, generator=g) * 2 - 1, e4m3)
         for _ in range(3):
             y = lof.lof_gemm(A, B, 10, check=False, **kw)
+    elif what == "gemm_fold":
+        # the persistent per-chunk fold kernel (lof_gemm_tc3.cuh) on operands already stored as e4m3 bytes / bf16 words
+        M = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
+        variant = sys.argv[3] if len(sys.argv) > 3 else "bf162"
+        e4m3 = fmt("e4m3")
+        A = lof.virtual_round(torch.rand(M, M, device=dev, generator=g) * 2 - 1, e4m3)
+        B = lof.virtual_round(torch.rand(M, M, device=dev, generator=g) * 2 - 1, e4m3)
+        if variant == "bf16ops":
+            a, bt = A.bfloat16(), B.t().contiguous().bfloat16()
+        else:
+            a, bt = lof.lof_encode(A, e4m3).view(M, M), lof.lof_encode(B.t().contiguous(), e4m3).view(M, M)
+        mant, kw = {"bf162": (7, dict(k_chunk=32, partial_round=True)), "half2": (10, dict(k_chunk=32, partial_round=True)),
+                    "bf16ops": (7, dict(k_chunk=32, partial_round=True)), "generic": (7, dict(k_chunk=32))}[variant]
+        for _ in range(3):
+            y = lof.lof_gemm_packed(a, bt, mant, **kw)
     else:
         M = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
         A = torch.rand(M, M, device=dev, generator=g) * 2 - 1
