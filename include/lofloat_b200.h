@@ -315,6 +315,30 @@ LOF_API int lof_gemm_chunked_packed(const uint8_t* A, const uint8_t* Bt, float* 
                                     int64_t k_chunk, float alpha, int operand_dtype, uint32_t flags, int32_t* dev_status,
                                     void* stream);
 
+/* Block-scaled (MX) tensor-core GEMM on MX STORAGE (tcgen05.mma.kind::mxf8f6f4.block_scale): the operands are what
+ * lof_mx_encode_f32 writes for block_size 32 with an E8M0 scale format and an 8-bit element format -- element codes
+ * a_elems [M x K] / bt_elems [N x K] (B transposed, K-major: the [out_features, in_features] weight layout) and one scale byte per
+ * 32 elements of K, a_scales [M x K/32] / bt_scales [N x K/32], row-major (container: src/Matrix.h:79-176 MX_Matrix).  Replaces
+ * the composition LoF_Linear(scaling="mx") runs (LoFloat/layers.py:366-377: virtual_mx_round of both operands, then lof_gemm on
+ * the fp32 containers) without ever materialising the de-quantised operands: the tensor core applies 2^(sa - 127) 2^(sb - 127)
+ * per MX block.  Accumulator semantics, flags and rounding modes as lof_gemm_chunked_f32 (k_chunk a multiple of 32; <= 0 = one
+ * chunk: plain MXFP8 GEMM with fp32 accumulation and one final rounding).  elem_dtype: LOF_E4M3 (OCP e4m3fn codes; every e3m2 /
+ * e2m3 / e2m1 value is an e4m3 value, so MXFP6 / MXFP4 tensors re-coded as e4m3 bytes run here too) or LOF_E5M2.  K % 32 == 0,
+ * element arrays 16-byte aligned.  A scale byte of 0xFF (NaN) makes its block NaN.  Asynchronous on stream. */
+LOF_API int lof_mx_gemm(const uint8_t* a_elems, const uint8_t* a_scales, const uint8_t* bt_elems, const uint8_t* bt_scales, float* C,
+                        int64_t M, int64_t N, int64_t K, int elem_dtype, int accum_mant_bits, const lof_format_t* acc_fmt,
+                        const lof_projspec_t* ps, int64_t k_chunk, float alpha, uint32_t flags, void* stream);
+
+/* fp32 containers holding MX-quantised values (lof_mx_round_f32's output, 32-element blocks along the last dimension) -> the
+ * operand form of lof_mx_gemm: OCP e4m3fn element codes (n bytes) + one E8M0 scale byte per block (n / 32 bytes).  The split into
+ * (power-of-two scale, element) is re-derived from each block's amax; every e3m2 / e2m3 / e2m1 (MXFP6 / MXFP4) block and every
+ * e4m3 block converts exactly except where a value is not on the hardware's e4m3fn grid (the reference's saturating virtual_round
+ * leaves a block's overflowing maximum unrounded, and its 8-bit e4m3 tops out at 480 where the hardware format ends at 448): those
+ * are rounded to nearest-even / saturated and LOF_MX_PACK_STATUS_SNAPPED is OR-ed into *dev_status (device int32, may be NULL).
+ * n % 32 == 0, `in` 16-byte and `elems` 4-byte aligned. */
+#define LOF_MX_PACK_STATUS_SNAPPED 1
+LOF_API int lof_mx_pack_tc_f32(const float* in, int64_t n, uint8_t* elems, uint8_t* scales, int32_t* dev_status, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Host-buffer entry points: what a binding calls when the tensor lives in host memory.
  * The library stages through device memory in chunks and overlaps H2D, kernel and D2H on

@@ -40,6 +40,12 @@ cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, 
                            int accum_mant_bits, const lof_format_t* acc_fmt, const RoundPlan* acc_plan, const FastPlan* acc_fast,
                            int64_t k_chunk, float alpha, int operand_dtype, uint32_t flags, int* dev_status,
                            cudaStream_t stream, int* launches, std::string* err);
+cudaError_t launch_gemm_mx(const uint8_t* A, const uint8_t* SA, const uint8_t* Bt, const uint8_t* SB, float* C, int64_t M, int64_t N, int64_t K,
+                           int elem_dtype, int mode, int accum_mant_bits, const lof_format_t* acc_fmt, const RoundPlan* acc_plan,
+                           const FastPlan* acc_fast, int64_t k_chunk, float alpha, uint32_t flags, cudaStream_t stream, int* launches,
+                           std::string* err);
+cudaError_t launch_mx_pack_tc(const float* y, int64_t n, uint8_t* elems, uint8_t* scales, int* dev_status, int num_sms, cudaStream_t stream);
+cudaError_t read_mx_prof(unsigned long long* out16);
 }  // namespace lof
 
 using namespace lof;
@@ -60,6 +66,7 @@ struct Options {
     std::atomic<int64_t> host_chunk_bytes{32ll << 20};
     std::atomic<int64_t> pack_fast{1};           // storage codec: 0 = exact integer routine only, 1 = magic-add fast path where eligible
     std::atomic<int64_t> bf16_fast{2};           // bf16 containers on the magic path: 2 = unchecked kinds where the fp32 path is unchecked, 1 = always checked
+    std::atomic<int64_t> gemm_mx_prof{0};        // 1: lof_mx_gemm records CTA 0's cycle breakdown (lof_debug_mx_prof)
     std::atomic<int64_t> gemm_fold_split{1};     // packed fold GEMM, 128 x 256 tile: 1 = one N = 256 MMA per k-step (2 TMEM stages), 2 = two N = 128 MMAs (4 stages)
     std::atomic<int64_t> gemm_fast{1};           // exact GEMM: 1 = optimistic branch-free chain with a per-tile fallback, 0 = exact routines only
     std::atomic<int64_t> round_fast{2};          // 0: exact kernels; 1: branch-free fast path; 2: + magic-add path (default)
@@ -587,6 +594,7 @@ int lof_set_option(const char* key, int64_t value)
     else if (k == "stream.ctas_per_sm") { if (value < 1 || value > 64) return fail(LOF_ERR_INVALID_ARG, "stream.ctas_per_sm out of range"); g_opt.stream_ctas_per_sm = value; }
     else if (k == "pack.fast") { if (value < 0 || value > 1) return fail(LOF_ERR_INVALID_ARG, "pack.fast must be 0 or 1"); g_opt.pack_fast = value; }
     else if (k == "bf16.fast") { if (value < 1 || value > 2) return fail(LOF_ERR_INVALID_ARG, "bf16.fast must be 1 or 2"); g_opt.bf16_fast = value; }
+    else if (k == "gemm.mx_prof") g_opt.gemm_mx_prof = value;
     else if (k == "gemm.fold_split") { if (value < 1 || value > 2) return fail(LOF_ERR_INVALID_ARG, "gemm.fold_split must be 1 or 2"); g_opt.gemm_fold_split = value; }
     else if (k == "gemm.fast") { if (value < 0 || value > 2) return fail(LOF_ERR_INVALID_ARG, "gemm.fast must be 0, 1 or 2"); g_opt.gemm_fast = value; }
     else if (k == "host.chunk_bytes") { if (value < (1 << 16)) return fail(LOF_ERR_INVALID_ARG, "host.chunk_bytes too small"); g_opt.host_chunk_bytes = value; }
@@ -606,6 +614,7 @@ int lof_get_option(const char* key, int64_t* value)
     else if (k == "stream.ctas_per_sm") *value = g_opt.stream_ctas_per_sm;
     else if (k == "pack.fast") *value = g_opt.pack_fast;
     else if (k == "gemm.fast") *value = g_opt.gemm_fast;
+    else if (k == "gemm.mx_prof") *value = g_opt.gemm_mx_prof;
     else if (k == "gemm.fold_split") *value = g_opt.gemm_fold_split;
     else if (k == "bf16.fast") *value = g_opt.bf16_fast;
     else if (k == "host.chunk_bytes") *value = g_opt.host_chunk_bytes;
@@ -819,6 +828,63 @@ int lof_gemm_chunked_packed(const uint8_t* A, const uint8_t* Bt, float* C, int64
     if (flags & (LOF_GEMM_INTERNAL_PACKED_OPERANDS | LOF_GEMM_INTERNAL_FOLD_SPLIT2)) return fail(LOF_ERR_INVALID_ARG, "unknown flag");
     return lof_gemm_chunked_f32(reinterpret_cast<const float*>(A), reinterpret_cast<const float*>(Bt), C, M, N, K, accum_mant_bits,
                                 acc_fmt, ps, k_chunk, alpha, operand_dtype, flags | LOF_GEMM_INTERNAL_PACKED_OPERANDS, dev_status, stream);
+}
+
+extern "C" LOF_API int lof_debug_mx_prof(unsigned long long* out16)     // not in the public header: profiling aid (scripts/mx_gemm_check.py)
+{
+    cudaDeviceSynchronize();
+    const cudaError_t e = read_mx_prof(out16);
+    return e == cudaSuccess ? LOF_OK : cuda_fail(e, "lof_debug_mx_prof");
+}
+
+int lof_mx_pack_tc_f32(const float* in, int64_t n, uint8_t* elems, uint8_t* scales, int32_t* dev_status, void* stream)
+{
+    if (n < 0 || n % 32 != 0) return fail(LOF_ERR_INVALID_ARG, "lof_mx_pack_tc_f32: n must be a non-negative multiple of 32");
+    if (n == 0) return LOF_OK;
+    if (!in || !elems || !scales) return fail(LOF_ERR_INVALID_ARG, "null tensor pointer");
+    if ((reinterpret_cast<uintptr_t>(in) & 15u) || (reinterpret_cast<uintptr_t>(elems) & 3u))
+        return fail(LOF_ERR_INVALID_ARG, "lof_mx_pack_tc_f32: `in` must be 16-byte and `elems` 4-byte aligned");
+    const int sms = num_sms();
+    if (sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    cudaError_t e = launch_mx_pack_tc(in, n, elems, scales, dev_status, sms, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "lof_mx_pack_tc launch");
+    g_launches.fetch_add(1);
+    return LOF_OK;
+}
+
+int lof_mx_gemm(const uint8_t* a_elems, const uint8_t* a_scales, const uint8_t* bt_elems, const uint8_t* bt_scales, float* C,
+                int64_t M, int64_t N, int64_t K, int elem_dtype, int accum_mant_bits, const lof_format_t* acc_fmt,
+                const lof_projspec_t* ps, int64_t k_chunk, float alpha, uint32_t flags, void* stream)
+{
+    if (M <= 0 || N <= 0 || K <= 0) return fail(LOF_ERR_INVALID_ARG, "GEMM dimensions must be positive");
+    if (!a_elems || !a_scales || !bt_elems || !bt_scales || !C || !ps) return fail(LOF_ERR_INVALID_ARG, "null argument");
+    if (flags & ~(LOF_GEMM_PARTIAL_ROUND | LOF_GEMM_NO_PACKED)) return fail(LOF_ERR_INVALID_ARG, "lof_mx_gemm: unknown flag");
+    const int mode = ps->rounding_mode;
+    if (mode < 0 || mode >= LOF_NUM_ROUNDING_MODES) return fail(LOF_ERR_INVALID_ARG, "unknown rounding mode");
+    if (mode_uses_rng(mode)) return fail(LOF_ERR_UNSUPPORTED, "MX GEMM: stochastic accumulator rounding not implemented");
+    RoundPlan plan;
+    FastPlan fast;
+    std::memset(&plan, 0, sizeof plan);
+    std::memset(&fast, 0, sizeof fast);
+    if (acc_fmt) {
+        const int st = make_plan(acc_fmt, LOF_F32, mode, 0, &plan);
+        if (st != LOF_OK) return st;
+        if (g_opt.round_fast.load()) fast = make_fast_plan(plan, mode);
+    } else if (accum_mant_bits < 0 || accum_mant_bits > 23) {
+        return fail(LOF_ERR_INVALID_ARG, "accum_mant_bits must be in [0, 23]");
+    }
+    if (num_sms() <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    int launches = 0;
+    std::string err;
+    cudaError_t e = launch_gemm_mx(a_elems, a_scales, bt_elems, bt_scales, C, M, N, K, elem_dtype, mode, accum_mant_bits, acc_fmt,
+                                   acc_fmt ? &plan : nullptr, acc_fmt ? &fast : nullptr, k_chunk, alpha,
+                                   flags | (g_opt.gemm_fold_split.load() == 2 ? LOF_GEMM_INTERNAL_FOLD_SPLIT2 : 0u) |
+                                       (g_opt.gemm_mx_prof.load() == 1 ? LOF_GEMM_INTERNAL_PROF : 0u),
+                                   static_cast<cudaStream_t>(stream), &launches, &err);
+    g_launches.fetch_add((uint64_t)launches);
+    if (!err.empty()) return fail(LOF_ERR_UNSUPPORTED, err);
+    if (e != cudaSuccess) return cuda_fail(e, "lof_mx_gemm launch");
+    return LOF_OK;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -9,6 +9,8 @@ namespace lof {
 constexpr uint32_t LOF_GEMM_INTERNAL_PACKED_OPERANDS = 0x80000000u;
 // internal: the packed fold kernel issues two N = 128 MMAs per k-step into four TMEM stages (option gemm.fold_split = 2)
 constexpr uint32_t LOF_GEMM_INTERNAL_FOLD_SPLIT2 = 0x40000000u;
+// internal: the MX GEMM records CTA 0's cycle breakdown (option gemm.mx_prof, read back with lof_debug_mx_prof)
+constexpr uint32_t LOF_GEMM_INTERNAL_PROF = 0x20000000u;
 
 // Operand addressing of the exact GEMM beyond plain row-major: the callers fused around lof_gemm.
 //   b_kind 0  B is K x N row-major (lof_gemm_f32 / lof_gemm_batched_f32)

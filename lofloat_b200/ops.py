@@ -729,3 +729,64 @@ def lof_gemm_packed(A: torch.Tensor, Bt: torch.Tensor, accum_mant_bits: int, rou
     _lib.check(st, "lof_gemm_packed")
     lof_gemm_packed.status = status
     return out
+
+
+def mx_pack_operand(y: torch.Tensor):
+    """[rows, K] float32 holding MX-quantised values (virtual_mx_round's output, blocks of 32 along K) -> the operand form of
+    mx_gemm: (elems uint8 [rows, K] OCP e4m3fn codes, scales uint8 [rows, K / 32] E8M0 bytes, status int32[1] on the device:
+    bit 0 = some value was not on the hardware's e4m3fn grid and was rounded / saturated)."""
+    if y.dtype != torch.float32 or not y.is_cuda or y.dim() != 2 or y.size(1) % 32 != 0:
+        raise RuntimeError("mx_pack_operand: a 2-D float32 CUDA tensor whose last dimension is a multiple of 32")
+    L = _lib.lib()
+    yc = y.contiguous()
+    rows, K = yc.shape
+    elems = torch.empty((rows, K), dtype=torch.uint8, device=yc.device)
+    scales = torch.empty((rows, K // 32), dtype=torch.uint8, device=yc.device)
+    status = torch.zeros(1, dtype=torch.int32, device=yc.device)
+    with torch.cuda.device(yc.device):
+        st = L.lof_mx_pack_tc_f32(yc.data_ptr(), yc.numel(), elems.data_ptr(), scales.data_ptr(), status.data_ptr(), _stream_ptr(yc))
+    _lib.check(st, "mx_pack_operand")
+    return elems, scales, status
+
+
+def mx_quantize_operand(x: torch.Tensor, element_format: FloatFormatDescriptor, scale_format: FloatFormatDescriptor | None = None,
+                        round_mode=RoundingMode.RoundToNearestEven, scale_round_mode=RoundingMode.RoundToNearestEven, stoch_len: int = 0,
+                        *, rng=None, first_index: int = 0):
+    """virtual_mx_round(x, 32, element_format, scale_format) -- the reference's MX quantisation, any element format that is a subset of
+    e4m3 x 2^k (MXFP8 e4m3, MXFP6 e3m2 / e2m3, MXFP4 e2m1) -- followed by mx_pack_operand: (elems, scales, status)."""
+    if scale_format is None:
+        scale_format = _default_e8m0()
+    y = virtual_mx_round(x, 32, element_format, scale_format, round_mode, scale_round_mode, stoch_len, rng=rng, first_index=first_index)
+    return mx_pack_operand(y)
+
+
+def mx_gemm(a_elems: torch.Tensor, a_scales: torch.Tensor, bt_elems: torch.Tensor, bt_scales: torch.Tensor, accum_mant_bits: int,
+            round_mode=RoundingMode.RoundToNearestEven, *, k_chunk: int = 32, accum_format: FloatFormatDescriptor | None = None,
+            element: str = "e4m3", partial_round: bool = False, allow_packed: bool = True, alpha: float = 1.0) -> torch.Tensor:
+    """Block-scaled tensor-core GEMM on MX storage (tcgen05.mma.kind::mxf8f6f4.block_scale): C[M, N] = alpha * A_mx @ Bt_mx^T with the
+    accumulator re-rounded every k_chunk (a multiple of the MX block, 32; 0 = fp32 accumulation over all of K, one final rounding).
+    a_elems [M, K] / bt_elems [N, K] uint8 element codes, a_scales [M, K/32] / bt_scales [N, K/32] uint8 E8M0 bytes -- what
+    mx_quantize_operand returns.  The fused form of LoF_Linear(scaling="mx") (LoFloat/layers.py:366-377)."""
+    for t, what in ((a_elems, "a_elems"), (a_scales, "a_scales"), (bt_elems, "bt_elems"), (bt_scales, "bt_scales")):
+        if t.dtype != torch.uint8 or not t.is_cuda or t.dim() != 2:
+            raise RuntimeError(f"mx_gemm: {what} must be a 2-D uint8 CUDA tensor")
+        if t.device != a_elems.device:
+            raise RuntimeError("mx_gemm: all operands must live on the same device")
+    M, K = a_elems.shape
+    N = bt_elems.shape[0]
+    if bt_elems.shape[1] != K:
+        raise RuntimeError(f"mx_gemm: a_elems.cols ({K}) != bt_elems.cols ({bt_elems.shape[1]})")
+    if K % 32 != 0 or tuple(a_scales.shape) != (M, K // 32) or tuple(bt_scales.shape) != (N, K // 32):
+        raise RuntimeError("mx_gemm: K must be a multiple of 32 and the scale tensors [rows, K / 32]")
+    L = _lib.lib()
+    ps = CProjSpec(int(RoundingMode(int(round_mode))), 0, 0)
+    ae, asc, be, bsc = a_elems.contiguous(), a_scales.contiguous(), bt_elems.contiguous(), bt_scales.contiguous()
+    out = torch.empty((M, N), dtype=torch.float32, device=ae.device)
+    fmt = accum_format._c() if accum_format is not None else None
+    flags = (_lib.LOF_GEMM_PARTIAL_ROUND if partial_round else 0) | (0 if allow_packed else _lib.LOF_GEMM_NO_PACKED)
+    with torch.cuda.device(ae.device):
+        st = L.lof_mx_gemm(ae.data_ptr(), asc.data_ptr(), be.data_ptr(), bsc.data_ptr(), out.data_ptr(), M, N, K,
+                           _OPERAND_DTYPES[element], int(accum_mant_bits), C.byref(fmt) if fmt is not None else None, C.byref(ps),
+                           int(k_chunk), float(alpha), flags, _stream_ptr(ae))
+    _lib.check(st, "mx_gemm")
+    return out

@@ -226,3 +226,57 @@ def gemm_2d_packed(A_local: torch.Tensor, Bt_local: torch.Tensor, grid: GemmGrid
         if j != grid.c:
             parts[j] = gemm_fn(A_panel[j * mw:(j + 1) * mw], Bt_panel, accum_mant_bits, round_mode, scale_a, scale_b, **gemm_kwargs)
     return torch.cat(parts, dim=0)
+
+
+def gemm_2d_mx(A_elems: torch.Tensor, A_scales: torch.Tensor, Bt_elems: torch.Tensor, Bt_scales: torch.Tensor, grid: GemmGrid,
+               M: int, N: int, K: int, accum_mant_bits: int, round_mode=0, gemm_fn: Optional[Callable] = None, overlap: bool = True,
+               **gemm_kwargs) -> torch.Tensor:
+    """gemm_2d_packed for MX STORAGE (ops.mx_quantize_operand: uint8 element codes [rows, K] + uint8 E8M0 scale bytes [rows, K / 32]),
+    consumed by the block-scaled tensor-core GEMM (ops.mx_gemm): 1.03 bytes per element on the wire instead of 2 (bf16 words) or 4.
+    Same panels and collectives as gemm_2d_packed, issued once for the element arrays and once for the scale arrays:
+      A row panel r     = shards of ranks r*C .. r*C + C - 1       -> all_gather_into_tensor inside the row group
+      Bt column panel c = shards of ranks c*R .. c*R + R - 1       -> all_to_all_single over the world (shard s goes to column s // R)
+    Returns this rank's block C[r*M/R:(r+1)*M/R, c*N/C:(c+1)*N/C] (fp32)."""
+    if gemm_fn is None:
+        from .ops import mx_gemm as gemm_fn
+    W, R, Cn = grid.world_size, grid.R, grid.C
+    if M % W or N % W or K % 32:
+        raise ValueError(f"gemm_2d_mx needs M % world == 0, N % world == 0 and K % 32 == 0 (M={M}, N={N}, K={K}, grid={R}x{Cn})")
+    kb = K // 32
+    if (tuple(A_elems.shape) != (M // W, K) or tuple(A_scales.shape) != (M // W, kb) or tuple(Bt_elems.shape) != (N // W, K)
+            or tuple(Bt_scales.shape) != (N // W, kb)):
+        raise ValueError("gemm_2d_mx: local operand shapes do not match the 1-D row partitions")
+    if W == 1:
+        return gemm_fn(A_elems, A_scales, Bt_elems, Bt_scales, accum_mant_bits, round_mode, **gemm_kwargs)
+    rows = N // W
+    my_col = grid.rank // R
+    n_dst = sum(1 for d in range(W) if d % Cn == my_col)
+    in_split = [rows if d % Cn == my_col else 0 for d in range(W)]
+    out_split = [rows if s // R == grid.c else 0 for s in range(W)]
+    works, panels = [], {}
+    for name, t in (("bt_e", Bt_elems), ("bt_s", Bt_scales)):           # B^T first: every output block needs all of it
+        send = t.contiguous().unsqueeze(0).expand(n_dst, rows, t.size(1)).reshape(n_dst * rows, t.size(1)).contiguous()
+        panels[name] = torch.empty((N // Cn, t.size(1)), dtype=t.dtype, device=t.device)
+        works.append(dist.all_to_all_single(panels[name], send, out_split, in_split, group=grid.world_group, async_op=True))
+    own = {"a_e": A_elems.contiguous(), "a_s": A_scales.contiguous()}
+    a_works = []
+    for name in ("a_e", "a_s"):
+        t = own[name]
+        panels[name] = torch.empty((M // R, t.size(1)), dtype=t.dtype, device=t.device)
+        a_works.append(dist.all_gather_into_tensor(panels[name], t, group=grid.row_group, async_op=True))
+    for w in works:
+        w.wait()
+    if not overlap:
+        for w in a_works:
+            w.wait()
+        return gemm_fn(panels["a_e"], panels["a_s"], panels["bt_e"], panels["bt_s"], accum_mant_bits, round_mode, **gemm_kwargs)
+    mw = M // W
+    parts = [None] * Cn
+    parts[grid.c] = gemm_fn(own["a_e"], own["a_s"], panels["bt_e"], panels["bt_s"], accum_mant_bits, round_mode, **gemm_kwargs)
+    for w in a_works:
+        w.wait()
+    for j in range(Cn):
+        if j != grid.c:
+            parts[j] = gemm_fn(panels["a_e"][j * mw:(j + 1) * mw], panels["a_s"][j * mw:(j + 1) * mw], panels["bt_e"], panels["bt_s"],
+                               accum_mant_bits, round_mode, **gemm_kwargs)
+    return torch.cat(parts, dim=0)

@@ -1303,3 +1303,159 @@ def test_exact_gemm_float_domain_rne_selftest(lof, cuda_dev):
     _lib.check(_lib.lib().lof_selftest_gemm_rne_round(bad.data_ptr(), None), "selftest")
     torch.cuda.synchronize()
     assert int(bad.item()) == 0
+
+
+# ------------------------------------------------------------------------- block-scaled MX GEMM (tcgen05.mma.kind::mxf8f6f4.block_scale)
+def _e4m3fn_decode_table(dev):
+    t = np.zeros(256, dtype=np.float32)
+    for c in range(256):
+        e, m = (c >> 3) & 15, c & 7
+        v = np.nan if (e == 15 and m == 7) else (m * 2.0 ** -9 if e == 0 else (1 + m / 8.0) * 2.0 ** (e - 7))
+        t[c] = -v if c & 0x80 else v
+    return torch.from_numpy(t).to(dev)
+
+
+def _mx_storage_decode(elems, scales, table):
+    v = table[elems.long()]
+    return (v.view(elems.size(0), -1, 32) * torch.exp2(scales.float() - 127.0).unsqueeze(-1)).view(elems.shape)
+
+
+def test_mx_pack_operand_is_an_exact_split_of_the_mx_rounded_tensor(lof, cuda_dev):
+    """mx_pack_operand: fp32 containers holding virtual_mx_round's output -> e4m3fn element codes + E8M0 scale bytes.  The split is
+    exact: decode(pack(y)) == y bit for bit on every element that lies on the block's element grid -- for MXFP6 / MXFP4 element
+    formats and for MXFP8 e4m3 that is every element except the block maxima the reference's saturating virtual_round leaves
+    UNROUNDED and the reference's 480 (the hardware e4m3fn ends at 448); those are snapped and flagged."""
+    torch.manual_seed(11)
+    tab = _e4m3fn_decode_table(cuda_dev)
+    e8 = lof.create_e8m0_params()
+    fmts = {"e4m3": (lof.create_p3109_params(8, 4, bias=7), L.FORMATS["e4m3_b7"]), "e3m2": (lof.create_p3109_params(6, 3, bias=3), L.FORMATS["e3m2"]),
+            "e2m3": (lof.create_p3109_params(6, 4, bias=1), L.FORMATS["e2m3"]), "e2m1": (lof.create_p3109_params(4, 2, bias=1), L.FORMATS["e2m1"])}
+    for name, (d, f) in fmts.items():
+        x = torch.randn(256, 1024, device=cuda_dev) * torch.exp2(torch.randint(-20, 21, (256, 1), device=cuda_dev).float())
+        x[5, 64:96] = 0.0                                            # an all-zero block
+        y = lof.virtual_mx_round(x, 32, d, e8)
+        assert L.bits_equal(_np(y).reshape(-1), L.o_mx_round(_np(x).reshape(-1), 32, L.FORMATS["e8m0"], f))     # the quantisation itself: reference semantics
+        el, sc, st = lof.mx_pack_operand(y)
+        assert el.shape == y.shape and sc.shape == (256, 32) and el.dtype == torch.uint8 and sc.dtype == torch.uint8
+        dec = _mx_storage_decode(el, sc, tab)
+        # elements of y that are on the element grid of their block (value / block scale representable in the element format)
+        yb, xb = y.view(256, 32, 32), x.view(256, 32, 32)
+        amax = xb.abs().amax(dim=-1, keepdim=True)
+        pmn = float(lof._lib.lib().lof_mx_priv_max_normal(C.byref(d._c())))
+        scale = lof.virtual_round(amax / pmn, e8)
+        q = torch.where(scale > 0, yb / scale, torch.zeros_like(yb))
+        # e4m3 only: a block whose largest |q| exceeds 448 (the reference's 480, or an unrounded maximum) is stored one binade up (480 -> 240 x 2
+        # exactly), which costs the block's elements below 2^-5 their last bit; every other block / format converts exactly
+        hot = q.abs().amax(dim=-1, keepdim=True) > 448.0
+        on_grid = (lof.virtual_round(q.contiguous(), d) == q) & (q.abs() <= pmn) & ~hot     # (an overflowing q comes back from virtual_round unchanged)
+        assert torch.equal(dec.view(256, 32, 32)[on_grid].view(torch.int32), yb[on_grid].view(torch.int32)), name
+        assert name == "e4m3" or not bool(hot.any().item())
+        if bool((~on_grid).any().item()) and bool((dec != y).any().item()):
+            assert bool(st.item() & 1), name
+        # snapped values: rounded to nearest on the e4m3fn grid of their block (4 significant bits; absolute floor = the grid's smallest step)
+        err = (dec - y).abs().view(256, 32, 32)
+        bound = torch.maximum(yb.abs() / 16.0, yb.abs().amax(dim=-1, keepdim=True) * 2.0 ** -16)
+        assert bool((err <= bound).all().item()), name
+
+
+def test_mx_gemm_block_scaled_tensor_core_vs_oracle(lof, cuda_dev):
+    """lof_mx_gemm (tcgen05.mma.kind::mxf8f6f4.block_scale on MX storage) against the chunked-accumulation oracle evaluated on the DECODED
+    operands, for every accumulator semantics the kernel serves.  BIT-EXACT wherever each chunk's partial sum is exactly representable in
+    the tensor core's fp32 accumulator (k_chunk = one MX block of e4m3 products: 32 products of <= 8 significant bits on a common
+    power-of-two grid), and equal to the bf16-word tensor-core path (lof_gemm_chunked_packed) on the same decoded operands; with fp32
+    accumulation over several blocks the tensor core's internal alignment truncates: tolerance = 1 ulp of the ACCUMULATOR format at the result
+    plus (K / 32) * 2^-23 * sum |a_ik b_jk| (stated inline)."""
+    torch.manual_seed(12)
+    tab = _e4m3fn_decode_table(cuda_dev)
+    e8 = lof.create_e8m0_params()
+    fm = {"e4m3": lof.create_p3109_params(8, 4, bias=7), "e3m2": lof.create_p3109_params(6, 3, bias=3), "e2m1": lof.create_p3109_params(4, 2, bias=1)}
+    e5m10 = lof.FloatFormatDescriptor(16, 10, 15, lof.InfBehavior.Saturating, lof.NaNBehavior._3109, lof.Signedness.Signed,
+                                      lof.create_half_params().is_inf_checker, lof.create_half_params().is_nan_checker)
+
+    def run(M, N, K, name, k_chunk, mant, partial, mode=L.RNE, acc_format=None, acc_fmt_oracle=None, exact=True, row_scale=True):
+        A = torch.randn(M, K, device=cuda_dev)
+        Bt = torch.randn(N, K, device=cuda_dev)
+        if row_scale:                                               # block scales spread over 2^-6 .. 2^6: the scale path is exercised
+            A = A * torch.exp2(torch.randint(-6, 7, (M, K // 32), device=cuda_dev).float()).repeat_interleave(32, dim=1)
+            Bt = Bt * torch.exp2(torch.randint(-6, 7, (N, K // 32), device=cuda_dev).float()).repeat_interleave(32, dim=1)
+        ae, asc, _ = lof.mx_quantize_operand(A, fm[name], e8)
+        be, bsc, _ = lof.mx_quantize_operand(Bt, fm[name], e8)
+        Ad, Bd = _mx_storage_decode(ae, asc, tab), _mx_storage_decode(be, bsc, tab)
+        got = lof.mx_gemm(ae, asc, be, bsc, mant, mode, k_chunk=k_chunk, partial_round=partial, accum_format=acc_format)
+        want = L.o_gemm_chunked(_np(Ad), _np(Bd.t().contiguous()), mant, k_chunk if k_chunk > 0 else K, mode=mode, acc_fmt=acc_fmt_oracle,
+                                partial_round=partial)
+        g = _np(got)
+        what = (M, N, K, name, k_chunk, mant, partial, mode)
+        if exact:
+            assert L.bits_equal(g, want), (what, L.first_mismatch(g.reshape(-1), g.reshape(-1), want.reshape(-1)))
+        else:
+            # tolerance: 1 ulp of the accumulator format at the result + the tensor core's fp32 alignment error, which scales with the sum of
+            # the |products| (cancellation): K / 32 block additions of relative error <= 2^-23 each
+            w64 = want.astype(np.float64)
+            S = _np(Ad.abs().double() @ Bd.abs().double().t())
+            tol = np.abs(w64) * 2.0 ** -mant + S * (K // 32) * 2.0 ** -23
+            if 0 < k_chunk < K:          # chunked: a partial that sits on a rounding boundary may round the other way, once per chunk at most
+                tol = tol + S * 2.0 ** -mant
+            assert bool((np.abs(g.astype(np.float64) - w64) <= tol).all()), (what, float((np.abs(g - w64) / tol).max()))
+        # the other tensor-core route to the same numbers: bf16 words of the decoded operands, chunked GEMM
+        if exact and k_chunk > 0 and acc_format is None:
+            ref_tc = lof.lof_gemm_packed(Ad.bfloat16(), Bd.bfloat16(), mant, mode, k_chunk=k_chunk, partial_round=partial)
+            assert torch.equal(ref_tc, got), what
+        return got
+
+    for name in fm:                                                  # C5 semantics: bf16-like accumulator re-rounded every MX block, packed fold
+        run(256, 448, 256, name, 32, 7, True)
+    run(200, 300, 160, "e4m3", 32, 7, True)                          # ragged M / N (TMA zero fill, partial tiles), K not a multiple of 128
+    run(128, 224, 4096, "e4m3", 32, 7, True)                         # long K: 128 chunks per tile
+    run(384, 672, 512, "e4m3", 64, 7, True, row_scale=False)         # two MX blocks per chunk, blocks of similar magnitude: still exact
+    run(384, 672, 512, "e4m3", 64, 7, True, exact=False)             # ... with block scales 2^-6 .. 2^6 the fp32 sum of two block sums rounds
+    run(256, 224, 512, "e4m3", 32, 7, False)                         # single rounding: generic fold (round-to-odd add)
+    for mode in (L.RTZ, L.RD, L.RU, L.RAZ, L.RTO, L.RNO, L.RTA, L.RTTZ):
+        run(128, 224, 256, "e4m3", 32, 5, True, mode=mode)
+        run(128, 224, 256, "e4m3", 32, 10, False, mode=mode)
+    run(256, 320, 512, "e4m3", 32, 10, False, acc_format=e5m10, acc_fmt_oracle=L.fmt(16, 10, 15), row_scale=False)   # full-format accumulator (E5M10)
+    run(128, 224, 256, "e4m3", 0, 7, False)                          # ONE chunk: plain MXFP8 GEMM, one final rounding (bf16-like output)
+    run(256, 448, 2048, "e4m3", 0, 10, False, exact=False)           # fp32 accumulation over 64 blocks: tolerance, not bit-equality
+    run(256, 448, 1024, "e4m3", 256, 7, True, exact=False)
+    # argument validation
+    ae = torch.zeros(128, 64, dtype=torch.uint8, device=cuda_dev); sc = torch.full((128, 2), 127, dtype=torch.uint8, device=cuda_dev)
+    with pytest.raises(RuntimeError):
+        lof.mx_gemm(ae, sc, ae[:, :32].contiguous(), sc, 7)          # K mismatch
+    with pytest.raises(RuntimeError):
+        lof.mx_gemm(ae, sc, ae, sc, 7, k_chunk=48)                   # k_chunk not a multiple of the MX block
+    out = lof.mx_gemm(ae, sc, ae, sc, 7, k_chunk=32, partial_round=True)
+    assert out.shape == (128, 128) and bool((out == 0).all().item())
+    # a NaN scale byte poisons exactly its rows
+    A = torch.randn(128, 64, device=cuda_dev)
+    ae, asc, _ = lof.mx_quantize_operand(A, fm["e4m3"], e8)
+    asc2 = asc.clone(); asc2[3, 1] = 0xFF
+    o2 = lof.mx_gemm(ae, asc2, ae, asc, 7, k_chunk=0)
+    assert bool(torch.isnan(o2[3]).all().item()) and not bool(torch.isnan(o2[[0, 1, 2, 4]]).any().item())
+
+
+def test_mx_gemm_full_size_properties(lof, cuda_dev):
+    """8192^3 on MX storage (C5's per-GPU shape class), bf16-like accumulator re-rounded every MX block: equals the bf16-word tensor-core
+    path on the decoded operands, linear in a power-of-two rescaling of one operand's SCALE bytes (an exact exponent shift), every output is
+    a bf16 value, and rows / columns of zero elements give exact zeros."""
+    torch.manual_seed(13)
+    n = 8192
+    tab = _e4m3fn_decode_table(cuda_dev)
+    e8 = lof.create_e8m0_params()
+    f = lof.create_p3109_params(8, 4, bias=7)
+    A = torch.randn(n, n, device=cuda_dev); Bt = torch.randn(n, n, device=cuda_dev)
+    A[100] = 0.0; Bt[7] = 0.0
+    ae, asc, _ = lof.mx_quantize_operand(A, f, e8)
+    be, bsc, _ = lof.mx_quantize_operand(Bt, f, e8)
+    del A, Bt
+    Cm = lof.mx_gemm(ae, asc, be, bsc, 7, k_chunk=32, partial_round=True)
+    assert bool(torch.isfinite(Cm).all().item())
+    assert bool(((Cm.view(torch.int32) & 0xFFFF) == 0).all().item())             # bf16 values
+    assert bool((Cm[100] == 0).all().item()) and bool((Cm[:, 7] == 0).all().item())
+    C2 = lof.mx_gemm(ae, (asc + 3).contiguous(), be, bsc, 7, k_chunk=32, partial_round=True)
+    assert torch.equal(C2, Cm * 8.0)
+    Ad16 = _mx_storage_decode(ae, asc, tab).bfloat16()
+    Bd16 = _mx_storage_decode(be, bsc, tab).bfloat16()
+    Cb = lof.lof_gemm_packed(Ad16, Bd16, 7, k_chunk=32, partial_round=True)
+    neq = int((Cb != Cm).sum().item())
+    # the two tensor-core routes agree except where one chunk's exact partial sum is a tie of the fp32 accumulator's internal alignment
+    assert neq <= n * n // 1_000_000, neq

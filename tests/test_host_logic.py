@@ -200,6 +200,25 @@ def _worker(rank, world, port, q):
                                    overlap=False,
                                    gemm_fn=lambda a, bt, bits, mode, sa, sb, **kw: _np_gemm(a, bt.t().contiguous(), bits, mode, 0, sa, sb))
         ok_gemm = ok_gemm and torch.equal(C2_seq.view(torch.int32), C2_blk.view(torch.int32))
+        # MX storage exchange (element bytes + scale bytes): stand-in GEMM = decode on the host, then the oracle GEMM
+        K3 = 64
+        Ae = torch.randint(0, 120, (M2, K3), generator=g, dtype=torch.uint8)
+        As = torch.randint(120, 134, (M2, K3 // 32), generator=g, dtype=torch.uint8)
+        Be = torch.randint(0, 120, (N2, K3), generator=g, dtype=torch.uint8)
+        Bs = torch.randint(120, 134, (N2, K3 // 32), generator=g, dtype=torch.uint8)
+
+        def _dec(e, sc):
+            return (e.float().view(e.size(0), -1, 32) * torch.exp2(sc.float() - 127.0).unsqueeze(-1)).reshape(e.shape)
+
+        def _mx_fn(ae, asc, be, bsc, bits, mode, **kw):
+            return _np_gemm(_dec(ae, asc), _dec(be, bsc).t().contiguous(), bits, mode, 0, 1.0, 1.0)
+        C3_blk = sh.gemm_2d_mx(Ae[rank * 4:(rank + 1) * 4], As[rank * 4:(rank + 1) * 4], Be[rank * 6:(rank + 1) * 6], Bs[rank * 6:(rank + 1) * 6],
+                               grid, M2, N2, K3, 10, gemm_fn=_mx_fn)
+        C3_seq = sh.gemm_2d_mx(Ae[rank * 4:(rank + 1) * 4], As[rank * 4:(rank + 1) * 4], Be[rank * 6:(rank + 1) * 6], Bs[rank * 6:(rank + 1) * 6],
+                               grid, M2, N2, K3, 10, gemm_fn=_mx_fn, overlap=False)
+        C3_full = _mx_fn(Ae, As, Be, Bs, 10, 0)
+        want3 = C3_full[r * (M2 // grid.R):(r + 1) * (M2 // grid.R), c * (N2 // grid.C):(c + 1) * (N2 // grid.C)]
+        ok_gemm = ok_gemm and torch.equal(C3_blk.view(torch.int32), want3.contiguous().view(torch.int32)) and torch.equal(C3_seq, C3_blk)
         q.put((rank, ok_round, ok_mx, ok_gemm, (grid.R, grid.C)))
     finally:
         dist.destroy_process_group()
