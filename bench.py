@@ -324,6 +324,69 @@ def named_workloads(torch, dist, dev, rank, world, args):
         return sync_max(a.elapsed_time(b) / reps), keep
 
     e8m0 = lof.create_e8m0_params()
+    # ------------------------------------------------------------------ C1: fp32 -> E4M3 RNE saturating, 2^24 elements (the reference's own CPU case)
+    try:
+        n1 = 1 << 24
+        NB = 16                                                                   # 16 input / output pairs = 2 GiB: nothing survives in the 126 MB L2
+        g = torch.Generator(device=dev).manual_seed(12345 + rank)
+        xs = [torch.randn(n1, device=dev, generator=g) * 4 for _ in range(NB)]
+        ys = [torch.empty(n1, device=dev) for _ in range(NB)]
+        e4 = lof.create_p3109_params(8, 4, bias=7)
+        from lofloat_b200 import _lib
+        lib = _lib.lib()
+        fmt_c, ps_c, rng_c = e4._c(), _lib.CProjSpec(0, 0, 0), _lib.CRng(0, 0)
+        stream = torch.cuda.current_stream().cuda_stream
+
+        def sweep():
+            for xi, yi in zip(xs, ys):
+                lib.lof_round_params(xi.data_ptr(), yi.data_ptr(), n1, 0, C.byref(fmt_c), C.byref(ps_c), 1.0, C.byref(rng_c), 0, stream)
+        ms, _ = timed(sweep, 5, warm=2)
+        per_launch_us = ms * 1e3 / NB
+        gbps = 8.0 * n1 / (per_launch_us * 1e-6) / 1e9
+
+        def copy_sweep():
+            for xi, yi in zip(xs, ys):
+                yi.copy_(xi)
+        ms_cp, _ = timed(copy_sweep, 5, warm=2)
+        gbps_cp = 8.0 * n1 / (ms_cp * 1e-3 / NB) / 1e9
+        # one launch at a time, L2 flushed by a 256 MiB fill before each (events around the single launch: includes the launch latency)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        best = 1e9
+        for _ in range(20):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            lib.lof_round_params(xs[0].data_ptr(), ys[0].data_ptr(), n1, 0, C.byref(fmt_c), C.byref(ps_c), 1.0, C.byref(rng_c), 0, stream)
+            b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        del flush
+        c1 = {"metric": "virtual_round_GBps", "value": gbps * world, "unit": "GB/s", "scaling": "weak", "elements_per_gpu": n1,
+              "format": "E4M3 (8, 3, bias 7), saturating, RNE", "us_per_launch": per_launch_us,
+              "timing": "16 distinct 64 MiB input / output pairs (2 GiB working set > L2) launched back to back, 5 repetitions, CUDA events",
+              "single_launch_l2_flushed": {"us_best_of_20": best * 1e3, "GBps": 8.0 * n1 / (best * 1e-3) / 1e9,
+                                           "note": "events around ONE launch after a 256 MiB fill: includes launch latency and the cold ramp"},
+              "roofline": {"bound": "hbm", "kernel": "round_vec_kernel<f32,RoundToNearestEven>", "achieved": gbps, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": gbps / hbm_peak, "algorithmic_bytes_per_launch": 8.0 * n1, "peak_source": hbm_src,
+                           "size_matched_copy_GBps": gbps_cp, "frac_of_size_matched_copy": gbps / gbps_cp,
+                           "size_matched_copy_note": "torch Tensor.copy_ over the same 16 buffer pairs, same timing: what a plain copy reaches at 128 MiB per launch"}}
+        if rank == 0 and args.e2e_steps > 0:
+            xh = torch.empty(n1, dtype=torch.float32).pin_memory()
+            xh.copy_(xs[0])
+            yh = torch.empty_like(xh).pin_memory()
+            call = lambda: lib.lof_round_params_host(xh.data_ptr(), yh.data_ptr(), n1, 0, C.byref(fmt_c), C.byref(ps_c), 1.0, C.byref(rng_c), 0, dev.index)
+            assert call() == 0
+            t0 = time.perf_counter()
+            for _ in range(5):
+                assert call() == 0
+            dt = (time.perf_counter() - t0) / 5
+            c1["e2e"] = {"value": 8.0 * n1 / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": 4 * n1, "d2h_bytes_per_step": 4 * n1,
+                         "api": "lof_round_params_host (pinned host buffers, copies inside the timed region)"}
+            del xh, yh
+        out["C1_virtual_round_2^24"] = c1
+        del xs, ys
+    except Exception as exc:
+        out["C1_virtual_round_2^24"] = {"error": str(exc)}
     # ------------------------------------------------------------------ C3: mx_round, 16384 x 16384 fp32 per GPU, block 32, E8M0 scale
     try:
         R = Ccols = 16384
@@ -432,33 +495,46 @@ def named_workloads(torch, dist, dev, rank, world, args):
         g = torch.Generator(device=dev).manual_seed(99 + rank)
         A_loc = torch.randn(M // world, K, device=dev, generator=g)
         Wt_loc = torch.randn(N // world, K, device=dev, generator=g)           # weight layout [out, in]: MX blocks run along K
-        ms_mx, (A_q, Wt_q) = timed(lambda: (lof.virtual_mx_round(A_loc, 32, e4m3, e8m0), lof.virtual_mx_round(Wt_loc, 32, e4m3, e8m0)), 3, warm=1)
+        # the two MX passes: virtual_mx_round (reference semantics, E4M3 elements / E8M0 scales, block 32 along K) + the exact re-split into
+        # the tensor core's MX storage (e4m3fn bytes + E8M0 scale bytes); timed together, warm allocator
+        quant = lambda: (lof.mx_quantize_operand(A_loc, e4m3, e8m0), lof.mx_quantize_operand(Wt_loc, e4m3, e8m0))
+        ms_mx, ((ae, asc, _sa), (be, bsc, _sb)) = timed(quant, 3, warm=2)
+        ms_round, _ = timed(lambda: (lof.virtual_mx_round(A_loc, 32, e4m3, e8m0), lof.virtual_mx_round(Wt_loc, 32, e4m3, e8m0)), 3, warm=2)
         del A_loc, Wt_loc
-        # an MX-rounded element (e4m3 value x power-of-two block scale) is exact in bf16; the saturating virtual_round leaves a block's
-        # overflowing maxima unrounded, so snap once to make the tensor-core operands exact
-        A16, Wt16 = A_q.bfloat16(), Wt_q.bfloat16()
-        del A_q, Wt_q
-        fn = lambda: S.gemm_2d_packed(A16, Wt16, grid, M, N, K, 7, k_chunk=32, partial_round=True)
+        torch.cuda.empty_cache()
+        fn = lambda: S.gemm_2d_mx(ae, asc, be, bsc, grid, M, N, K, 7, k_chunk=32, partial_round=True)
         ms, Cblk = timed(fn, 2, warm=1)
         finite = bool(torch.isfinite(Cblk).all().item())
         del Cblk
+        # the same product with fp32 accumulation over all of K and ONE final bf16-like rounding (plain MXFP8 GEMM): how much the per-block
+        # re-rounding costs
+        ms_1c, Cblk = timed(lambda: S.gemm_2d_mx(ae, asc, be, bsc, grid, M, N, K, 7, k_chunk=0), 2, warm=1)
+        del Cblk
         tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
-        a_gather = 2 * (M // grid.R) * K * (grid.C - 1) // grid.C if world > 1 else 0
-        b_recv = 2 * (N // grid.C) * K * (world - 1) // world if world > 1 else 0
+        per_elem = 1.0 + 1.0 / 32.0
+        a_gather = per_elem * (M // grid.R) * K * (grid.C - 1) // grid.C if world > 1 else 0
+        b_recv = per_elem * (N // grid.C) * K * (world - 1) // world if world > 1 else 0
         out["C5_mxfp8_gemm"] = {
             "metric": "mx_gemm_TFLOPs", "value": tf, "unit": "TFLOP/s", "scaling": "strong", "M": M, "N": N, "K": K, "ms": ms,
             "composition": "LoF_Linear(scaling='mx') (layers.py:366-377): mx_round(E4M3 / E8M0, block 32 along K) of both operands, then the GEMM "
-                           "with the accumulator rounded to 7 mantissa bits every k = 32 (= one MX block)",
-            "operands": "bf16 words (MX-rounded values are exact in bf16), row-sharded", "grid": f"{grid.R}x{grid.C}",
+                           "with the accumulator rounded to 7 mantissa bits (bf16-like) every k = 32 (= one MX block)",
+            "operands": "MX storage: e4m3fn bytes + E8M0 scale bytes, row-sharded; consumed by tcgen05.mma.kind::mxf8f6f4.block_scale", "grid": f"{grid.R}x{grid.C}",
             "timed_region": "operand exchange + GEMM; the two MX passes are timed separately",
-            "mx_passes": {"ms": ms_mx, "GBps_aggregate": 8.0 * (M * K + N * K) / (ms_mx * 1e-3) / 1e9},
-            "comm": {"collectives": ["all_gather_into_tensor (A row panel, row group)", "all_to_all_single (B^T column panel, world)"] if world > 1 else [],
+            "mx_passes": {"ms": ms_mx, "GBps_aggregate": (8.0 + 4.0 + per_elem) * (M * K + N * K) / (ms_mx * 1e-3) / 1e9,
+                          "bytes_per_element": "8 (virtual_mx_round: 4 read + 4 written) + 4 + 1.03 (re-split into bytes + scales)",
+                          "virtual_mx_round_only_ms": ms_round, "virtual_mx_round_only_GBps_aggregate": 8.0 * (M * K + N * K) / (ms_round * 1e-3) / 1e9},
+            "fp32_accumulation_one_final_rounding": {"ms": ms_1c, "TFLOPs": 2.0 * M * N * K / (ms_1c * 1e-3) / 1e12},
+            "comm": {"collectives": ["all_gather_into_tensor x2 (A row panel: element bytes, scale bytes; row group)",
+                                     "all_to_all_single x2 (B^T column panel: element bytes, scale bytes; world)"] if world > 1 else [],
                      "bytes_received_per_rank": int(a_gather + b_recv)},
             "finite": finite,
-            "roofline": {"bound": "tensor", "achieved": tf / world, "peak": bf16_burst, "unit": "TFLOP/s", "frac": tf / world / bf16_burst,
-                         "peak_source": f"{bf16_src} dense bf16 burst (operands are bf16 words)", "frac_of_nominal_bf16_2250": tf / world / 2250.0,
-                         "kernel": "gemm_tc_fold_kernel<RNE,Bf162,partial> (tcgen05 + per-chunk bfloat162 fold from TMEM)"}}
-        del A16, Wt16
+            "roofline": {"bound": "tensor", "achieved": tf / world, "peak": 4500.0, "unit": "TFLOP/s", "frac": tf / world / 4500.0,
+                         "peak_source": "nominal dense FP8 (B200_PROFILING.md)", "frac_of_2x_measured_bf16": tf / world / (2.0 * bf16_burst),
+                         "measured_bf16_source": bf16_src,
+                         "kernel": "gemm_mx_kernel<RNE,Bf162,partial> (tcgen05 block-scaled MMA + per-block bfloat162 fold from TMEM)",
+                         "note": "the per-block re-rounding makes this kernel bound by the MMA -> TMEM read-back -> fold hand-off, not by the tensor pipe "
+                                 "(profiles/r02j_probe_*.txt); the fp32-accumulation figure next to it is bound by L2 -> SM operand bandwidth"}}
+        del ae, asc, be, bsc
     except Exception as exc:
         out["C5_mxfp8_gemm"] = {"error": str(exc)}
     torch.cuda.empty_cache()
@@ -493,6 +569,53 @@ def side_measurements(torch, lib, _lib, dev, x, y, stream):
         _lib.set_option("mx.variant", 0)
     except Exception as exc:
         out["mx_round_error"] = str(exc)
+    try:
+        # same-box GPU baseline: the reference's OWN device code (lo_float.h virtual_round + mx_round.cuh, compiled unmodified for sm_100a into
+        # oracle/_ref/libref_gpu.so by `make -C oracle refgpu`; test / bench infrastructure) in the reference's launch shapes, next to ours
+        so = ROOT / "oracle" / "_ref" / "libref_gpu.so"
+        if so.exists():
+            R = C.CDLL(str(so))
+            R.refgpu_round_params_f32.argtypes = [C.c_void_p, C.c_int64] + [C.c_int] * 8 + [C.c_float, C.c_void_p]
+            R.refgpu_mx_round_f32.argtypes = [C.c_void_p, C.c_int64, C.c_int] + [C.c_int] * 12 + [C.c_void_p]
+            import lofloat_b200 as lof
+            n = x.numel()
+
+            def time_it(fn, reps=5):
+                fn()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(reps):
+                    fn()
+                b.record()
+                torch.cuda.synchronize()
+                return a.elapsed_time(b) / reps
+            for label, (bw, m, bias, ov), mode, sl in (("e4m3_RNE", (8, 3, 7, 1), 0, 0), ("e4m3_RTZ", (8, 3, 7, 1), 1, 0), ("e4m3_RoundToOdd", (8, 3, 7, 1), 12, 0),
+                                                       ("e4m3_SR_A8", (8, 3, 7, 1), 3, 8), ("bf16like_RNE", (16, 7, 127, 0), 0, 0)):
+                y.copy_(x)
+                assert R.refgpu_round_params_f32(y.data_ptr(), n, bw, m, bias, ov, 0, 0, mode, sl, 1.0, stream) == 0
+                entry = {}
+                if sl == 0:         # deterministic: the reference's device result on this box == ours, bit for bit
+                    d = lof.FloatFormatDescriptor(bw, m, bias, ov, 0, 0, lof.create_single_params().is_inf_checker, lof.create_single_params().is_nan_checker)
+                    entry["bit_identical_to_lofloat_b200"] = bool(torch.equal(y.view(torch.int32), lof.virtual_round(x, d, mode).view(torch.int32)))
+                ms = time_it(lambda: R.refgpu_round_params_f32(y.data_ptr(), n, bw, m, bias, ov, 0, 0, mode, sl, 1.0, stream))
+                entry.update({"GBps": 8.0 * n / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": 8.0 * n / (ms * 1e-3) / 1e9 / peak,
+                              "launch": "round_fp_params<float><<<n / 256, 256>>> in place (Lof_kernel.cu:49-60), 2^28 elements"})
+                out[f"reference_gpu_virtual_round_{label}"] = entry
+            nmx = 16384 * 16384
+            for bs in (32, 128):
+                y.copy_(x)
+                call = lambda: R.refgpu_mx_round_f32(y.data_ptr(), nmx, bs, 8, 0, 127, 0, 1, 8, 3, 7, 1, 0, 0, 0, stream)
+                assert call() == 0
+                e8p, e4p = lof.create_e8m0_params(), lof.create_p3109_params(8, 4, bias=7)
+                same = bool(torch.equal(y.view(torch.int32), lof.virtual_mx_round(x, bs, e4p, e8p).view(torch.int32)))
+                ms = time_it(call)
+                out[f"reference_gpu_mx_round_mxfp8_e4m3_bs{bs}"] = {
+                    "GBps": 8.0 * nmx / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": 8.0 * nmx / (ms * 1e-3) / 1e9 / peak, "bit_identical_to_lofloat_b200": same,
+                    "launch": "virtual_mx_round<float, 256, MX, NX><<<min(65535, n / bs), 256>>> in place (mx_round.cuh:27-214), 16384 x 16384"}
+        else:
+            out["reference_gpu"] = "oracle/_ref/libref_gpu.so not built"
+    except Exception as exc:
+        out["reference_gpu_error"] = str(exc)
     try:
         # C2's bf16-in / bf16-out variant: 2^29 bf16 containers (1 GiB), 4 B / element of algorithmic traffic
         import lofloat_b200 as lof
