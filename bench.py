@@ -596,7 +596,14 @@ def side_measurements(torch, lib, _lib, dev, x, y, stream):
                 entry = {}
                 if sl == 0:         # deterministic: the reference's device result on this box == ours, bit for bit
                     d = lof.FloatFormatDescriptor(bw, m, bias, ov, 0, 0, lof.create_single_params().is_inf_checker, lof.create_single_params().is_nan_checker)
-                    entry["bit_identical_to_lofloat_b200"] = bool(torch.equal(y.view(torch.int32), lof.virtual_round(x, d, mode).view(torch.int32)))
+                    ours = lof.virtual_round(x, d, mode)
+                    ne = y.view(torch.int32) != ours.view(torch.int32)
+                    entry["bit_identical_to_lofloat_b200"] = not bool(ne.any().item())
+                    if not entry["bit_identical_to_lofloat_b200"]:      # the reference's DEVICE helpers vs its own HOST path (ours is pinned to the host path)
+                        i = int(ne.view(-1).nonzero()[0])
+                        entry["differing_elements"] = int(ne.sum().item())
+                        entry["first_difference"] = {"x": float(x.view(-1)[i]), "reference_gpu": float(y.view(-1)[i]), "lofloat_b200_and_reference_cpu": float(ours.view(-1)[i])}
+                    del ours, ne
                 ms = time_it(lambda: R.refgpu_round_params_f32(y.data_ptr(), n, bw, m, bias, ov, 0, 0, mode, sl, 1.0, stream))
                 entry.update({"GBps": 8.0 * n / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": 8.0 * n / (ms * 1e-3) / 1e9 / peak,
                               "launch": "round_fp_params<float><<<n / 256, 256>>> in place (Lof_kernel.cu:49-60), 2^28 elements"})
@@ -607,10 +614,18 @@ def side_measurements(torch, lib, _lib, dev, x, y, stream):
                 call = lambda: R.refgpu_mx_round_f32(y.data_ptr(), nmx, bs, 8, 0, 127, 0, 1, 8, 3, 7, 1, 0, 0, 0, stream)
                 assert call() == 0
                 e8p, e4p = lof.create_e8m0_params(), lof.create_p3109_params(8, 4, bias=7)
-                same = bool(torch.equal(y.view(torch.int32), lof.virtual_mx_round(x, bs, e4p, e8p).view(torch.int32)))
+                ours = lof.virtual_mx_round(x, bs, e4p, e8p)
+                ne = y.view(torch.int32) != ours.view(torch.int32)
+                same = not bool(ne.any().item())
+                extra = {}
+                if not same:
+                    i = int(ne.view(-1).nonzero()[0])
+                    extra = {"differing_elements": int(ne.sum().item()),
+                             "first_difference": {"x": float(x.view(-1)[i]), "reference_gpu": float(y.view(-1)[i]), "lofloat_b200_and_reference_cpu": float(ours.view(-1)[i])}}
+                del ours, ne
                 ms = time_it(call)
                 out[f"reference_gpu_mx_round_mxfp8_e4m3_bs{bs}"] = {
-                    "GBps": 8.0 * nmx / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": 8.0 * nmx / (ms * 1e-3) / 1e9 / peak, "bit_identical_to_lofloat_b200": same,
+                    **extra, "GBps": 8.0 * nmx / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": 8.0 * nmx / (ms * 1e-3) / 1e9 / peak, "bit_identical_to_lofloat_b200": same,
                     "launch": "virtual_mx_round<float, 256, MX, NX><<<min(65535, n / bs), 256>>> in place (mx_round.cuh:27-214), 16384 x 16384"}
         else:
             out["reference_gpu"] = "oracle/_ref/libref_gpu.so not built"

@@ -139,8 +139,29 @@ __device__ __forceinline__ uint4 round_vec16_w(uint4 v, const ElemOp<DTYPE, MODE
 // are zero, i.e. the bf16 result.  Deterministic modes and SR-A / SR-D (host-checked; the random offset R << (r - len) is the
 // same number in both containers); fp32-subnormal inputs and whatever the fp32 routine flags go to the exact bf16 routine.
 // Equality with the exact container routine: all 65536 bf16 patterns x formats x modes, tests/test_gpu_parity.py.
+// exact container routine for one 8-element bf16 vector: the cold path of the fast kinds below, kept out of line so that the
+// streaming loop carries ONE rarely taken call instead of sixteen inlined copies of the integer routine
 template <int MODE, int KIND>
-__device__ __forceinline__ uint4 round_vec16_bf16_w(uint4 v, const ElemOp<LOF_BF16, MODE, KIND>& op, const uint4& w0, const uint4& w1)
+__device__ __noinline__ uint4 round_vec16_bf16_exact(uint4 v, const ElemOp<LOF_BF16, MODE, KIND>& op, const uint4& w0, const uint4& w1)
+{
+    auto two = [&](uint32_t packed, uint32_t wa, uint32_t wb) -> uint32_t {
+        const uint16_t lo = round_params_elem<LOF_BF16, MODE>((uint16_t)(packed & 0xFFFFu), op.plan, wa);
+        const uint16_t hi = round_params_elem<LOF_BF16, MODE>((uint16_t)(packed >> 16), op.plan, wb);
+        return (uint32_t)lo | ((uint32_t)hi << 16);
+    };
+    v.x = two(v.x, w0.x, w0.y); v.y = two(v.y, w0.z, w0.w);
+    v.z = two(v.z, w1.x, w1.y); v.w = two(v.w, w1.z, w1.w);
+    return v;
+}
+
+// bf16 container on the fp32 branch-free routines, event words of the 8 elements given (w0: elements 0..3, w1: 4..7): a bf16
+// value is the fp32 value (bits << 16); rounding it into a target of <= 7 mantissa bits gives an fp32 result whose low 16 bits
+// are zero, i.e. the bf16 result.  Deterministic modes and SR-A / SR-D (host-checked; the random offset R << (r - len) is the
+// same number in both containers); fp32-subnormal inputs and whatever the fp32 routine flags set `rare`: the caller then redoes the
+// whole vector with the exact bf16 routine (round_vec16_bf16_exact).
+// Equality with the exact container routine: all 65536 bf16 patterns x formats x modes, tests/test_gpu_parity.py.
+template <int MODE, int KIND>
+__device__ __forceinline__ uint4 round_vec16_bf16_w(uint4 v, const ElemOp<LOF_BF16, MODE, KIND>& op, const uint4& w0, const uint4& w1, bool& rare)
 {
     constexpr bool SAT = (KIND == kKindFastSat || KIND == kKindFastSatChk || KIND == kKindMagicSat || KIND == kKindMagicSatChk);
     // unchecked magic kinds (narrow targets such as the 8 / 6 / 4-bit formats, deterministic modes): the magic add is exact
@@ -149,8 +170,7 @@ __device__ __forceinline__ uint4 round_vec16_bf16_w(uint4 v, const ElemOp<LOF_BF
     constexpr bool CHK = !(KIND == kKindMagicSat || KIND == kKindMagicExt);
     auto two = [&](uint32_t packed, uint32_t wa, uint32_t wb) -> uint32_t {
         const uint32_t xlo = packed << 16, xhi = packed & 0xFFFF0000u;
-        bool rare = false;
-        if constexpr (CHK) rare = ((xlo & 0x7FFFFFFFu) - 1u) < 0x007FFFFFu || ((xhi & 0x7FFFFFFFu) - 1u) < 0x007FFFFFu;
+        if constexpr (CHK) rare |= ((xlo & 0x7FFFFFFFu) - 1u) < 0x007FFFFFu || ((xhi & 0x7FFFFFFFu) - 1u) < 0x007FFFFFu;
         uint32_t olo, ohi;
         if constexpr (kind_is_magic(KIND)) {
             olo = round_magic_f32<MODE, SAT, CHK>(xlo, op.magic, wa, rare);
@@ -159,18 +179,20 @@ __device__ __forceinline__ uint4 round_vec16_bf16_w(uint4 v, const ElemOp<LOF_BF
             olo = round_fast_f32<MODE, SAT, true>(xlo, op.fast, wa, rare);
             ohi = round_fast_f32<MODE, SAT, true>(xhi, op.fast, wb, rare);
         }
-        if constexpr (CHK) {
-            if (rare) {
-                const uint16_t lo = round_params_elem<LOF_BF16, MODE>((uint16_t)(packed & 0xFFFFu), op.plan, wa);
-                const uint16_t hi = round_params_elem<LOF_BF16, MODE>((uint16_t)(packed >> 16), op.plan, wb);
-                return (uint32_t)lo | ((uint32_t)hi << 16);
-            }
-        }
         return __byte_perm(olo, ohi, 0x7632);                 // (olo >> 16) | (ohi & 0xFFFF0000)
     };
-    v.x = two(v.x, w0.x, w0.y); v.y = two(v.y, w0.z, w0.w);
-    v.z = two(v.z, w1.x, w1.y); v.w = two(v.w, w1.z, w1.w);
-    return v;
+    uint4 o;
+    o.x = two(v.x, w0.x, w0.y); o.y = two(v.y, w0.z, w0.w);
+    o.z = two(v.z, w1.x, w1.y); o.w = two(v.w, w1.z, w1.w);
+    return o;
+}
+template <int MODE, int KIND>
+__device__ __forceinline__ uint4 round_vec16_bf16_w(uint4 v, const ElemOp<LOF_BF16, MODE, KIND>& op, const uint4& w0, const uint4& w1)
+{
+    bool rare = false;
+    const uint4 o = round_vec16_bf16_w<MODE, KIND>(v, op, w0, w1, rare);
+    if (rare) return round_vec16_bf16_exact<MODE, KIND>(v, op, w0, w1);
+    return o;
 }
 
 // process one 16-byte vector that starts at global element index g0
@@ -254,9 +276,16 @@ round_vec_kernel(const uint4* in, uint4* out, int64_t nvec, int ntail,
                 for (int w = 0; w < UNROLL; ++w) q[w] = ld_stream(in + vbase + w * 128);
                 const uint4 ba = philox_block(rng, (run << 8) | (2u * kk)), bb = philox_block(rng, (run << 8) | (2u * kk + 1u));
                 const uint32_t wa[4] = {ba.x, ba.y, ba.z, ba.w}, wb[4] = {bb.x, bb.y, bb.z, bb.w};
+                bool rare = false;
+                uint4 o[UNROLL];
 #pragma unroll
-                for (int w = 0; w < UNROLL; ++w)
-                    st_stream(out + vbase + w * 128, round_vec16_bf16_w<MODE, KIND>(q[w], op, bytes_of(wa[w]), bytes_of(wb[w])));
+                for (int w = 0; w < UNROLL; ++w) o[w] = round_vec16_bf16_w<MODE, KIND>(q[w], op, bytes_of(wa[w]), bytes_of(wb[w]), rare);
+                if (rare) {             // an fp32-subnormal / flagged lane somewhere in this thread's 32 elements: redo them exactly
+#pragma unroll 1
+                    for (int w = 0; w < UNROLL; ++w) o[w] = round_vec16_bf16_exact<MODE, KIND>(q[w], op, bytes_of(wa[w]), bytes_of(wb[w]));
+                }
+#pragma unroll
+                for (int w = 0; w < UNROLL; ++w) st_stream(out + vbase + w * 128, o[w]);
                 continue;
             }
         }
