@@ -80,6 +80,18 @@ def main():
     r0, c0 = grid.r * (M // grid.R), grid.c * (N // grid.C)
     report(f"gemm_2d_packed {grid.R}x{grid.C} (bf16 exchange of MX-rounded operands, exact: {exact_bf16}) == single GPU fp32-container GEMM",
            exact_bf16 and torch.equal(Cblk, Cfull[r0:r0 + M // grid.R, c0:c0 + N // grid.C]))
+    # MX-storage exchange + block-scaled tensor-core GEMM (C5's path): rows quantised where they live, bytes + scale bytes on the wire
+    Ax, Wx = torch.randn(M, K, device=dev, generator=g), torch.randn(N, K, device=dev, generator=g)
+    ae, asc, _ = lof.mx_quantize_operand(Ax, e4m3, e8m0)
+    we, wsc, _ = lof.mx_quantize_operand(Wx, e4m3, e8m0)
+    Cfull = lof.mx_gemm(ae, asc, we, wsc, 7, k_chunk=32, partial_round=True)
+    sa, sw = slice(rank * (M // world), (rank + 1) * (M // world)), slice(rank * (N // world), (rank + 1) * (N // world))
+    ael, ascl, _ = lof.mx_quantize_operand(Ax[sa].contiguous(), e4m3, e8m0)            # quantising the shard == the shard of the quantised tensor
+    wel, wscl, _ = lof.mx_quantize_operand(Wx[sw].contiguous(), e4m3, e8m0)
+    same_q = torch.equal(ael, ae[sa]) and torch.equal(ascl, asc[sa]) and torch.equal(wel, we[sw]) and torch.equal(wscl, wsc[sw])
+    Cblk = S.gemm_2d_mx(ael, ascl, wel, wscl, grid, M, N, K, 7, k_chunk=32, partial_round=True)
+    report(f"gemm_2d_mx {grid.R}x{grid.C} (MX storage exchange, block-scaled MMA; shard quantisation == global: {same_q}) == single GPU",
+           same_q and torch.equal(Cblk, Cfull[r0:r0 + M // grid.R, c0:c0 + N // grid.C]))
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
