@@ -60,6 +60,11 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void bulk_g2s_a(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar_addr)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar_addr) : "memory");
+}
 // shared memory -> TMEM: 32 rows x 16 bytes, replicated into the four 32-lane quarters (the scale-factor layout of block-scaled MMAs)
 __device__ __forceinline__ void tmem_cp_32x128b_warpx4(uint32_t taddr, uint64_t sdesc)
 {
@@ -186,6 +191,8 @@ gemm_mx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ===================================== TMA producer =====================================
         if (elect_one()) {
             uint32_t stage = 0, phase = 0;
+            const uint32_t empty_a = smem_addr_once(&empty_bar[0]), full_a = smem_addr_once(&full_bar[0]);
+            const uint32_t sa_a = smem_addr_once(smem_a), sb_a = smem_addr_once(smem_b), sfa_a = smem_addr_once(smem_sfa), sfb_a = smem_addr_once(smem_sfb);
             for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
                 int tm, tn;
                 x_tile_coords(tile, args, tm, tn);
@@ -193,12 +200,13 @@ gemm_mx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const uint8_t* sfa = args.sfa + (size_t)tm * args.kb4 * X_SFA_BYTES;
                 const uint8_t* sfb = args.sfb + (size_t)tn * args.kb4 * X_SFB_BYTES;
                 for (int it = 0; it < n_stage_iters; ++it) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1u);
-                    mbar_expect_tx(&full_bar[stage], X_STAGE_A + X_STAGE_B + X_SFA_BYTES + X_SFB_BYTES);
-                    tma_load_2d(smem_a + stage * X_STAGE_A, &map_a, it * X_ROW_BYTES, m0, &full_bar[stage]);
-                    tma_load_2d(smem_b + stage * X_STAGE_B, &map_b, it * X_ROW_BYTES, n0, &full_bar[stage]);       // box = 224 rows
-                    bulk_g2s(smem_sfa + stage * X_SFA_BYTES, sfa + (size_t)it * X_SFA_BYTES, X_SFA_BYTES, &full_bar[stage]);
-                    bulk_g2s(smem_sfb + stage * X_SFB_BYTES, sfb + (size_t)it * X_SFB_BYTES, X_SFB_BYTES, &full_bar[stage]);
+                    mbar_wait_a(empty_a + stage * 8u, phase ^ 1u);
+                    const uint32_t fb = full_a + stage * 8u;
+                    mbar_expect_tx_a(fb, X_STAGE_A + X_STAGE_B + X_SFA_BYTES + X_SFB_BYTES);
+                    tma_load_2d_a(sa_a + stage * X_STAGE_A, &map_a, it * X_ROW_BYTES, m0, fb);
+                    tma_load_2d_a(sb_a + stage * X_STAGE_B, &map_b, it * X_ROW_BYTES, n0, fb);                        // box = 224 rows
+                    bulk_g2s_a(sfa_a + stage * X_SFA_BYTES, sfa + (size_t)it * X_SFA_BYTES, X_SFA_BYTES, fb);
+                    bulk_g2s_a(sfb_a + stage * X_SFB_BYTES, sfb + (size_t)it * X_SFB_BYTES, X_SFB_BYTES, fb);
                     if (++stage == (uint32_t)X_STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -209,10 +217,13 @@ gemm_mx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint32_t stage = 0, phase = 0, ts = 0, tphase = 0, sf_slot = 0;
             const uint64_t desc0 = umma_desc_k128(0);
             const uint32_t desc_hi = (uint32_t)(desc0 >> 32), desc_lo0 = (uint32_t)desc0;
-            const uint32_t a_lo_base = desc_lo0 + (smem_u32(smem_a) >> 4), b_lo_base = desc_lo0 + (smem_u32(smem_b) >> 4);
+            const uint32_t a_lo_base = desc_lo0 + (smem_addr_once(smem_a) >> 4), b_lo_base = desc_lo0 + (smem_addr_once(smem_b) >> 4);
             const uint32_t idesc = args.idesc;
             const int spc = args.steps_per_chunk;
             auto mk = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | lo; };
+            const uint32_t full_a = smem_addr_once(&full_bar[0]), empty_a = smem_addr_once(&empty_bar[0]);
+            const uint32_t tfull_a = smem_addr_once(&tmem_full_bar[0]), tempty_a = smem_addr_once(&tmem_empty_bar[0]);
+            const uint32_t sfa_a = smem_addr_once(smem_sfa), sfb_a = smem_addr_once(smem_sfb);
             long long p_t0 = 0, p_full = 0, p_empty = 0, p_chunks = 0, p_x = 0;
             if constexpr (PROF) p_t0 = clock64();
             for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
@@ -220,7 +231,7 @@ gemm_mx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 int in_chunk = 0;
                 for (int it = 0; it < n_stage_iters; ++it) {
                     if constexpr (PROF) p_x = clock64();
-                    mbar_wait(&full_bar[stage], phase);
+                    mbar_wait_a(full_a + stage * 8u, phase);
                     if constexpr (PROF) p_full += clock64() - p_x;
                     tc_fence_after();
                     // this stage's scale factors -> TMEM.  tcgen05.cp and tcgen05.mma execute in issue order, so a slot may be rewritten as
@@ -228,9 +239,9 @@ gemm_mx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     // previous readers of its slot anyway
                     const uint32_t sf_col = tmem_base + X_SF_COL0 + sf_slot * X_SF_STRIDE;
                     sf_slot ^= 1u;
-                    tmem_cp_32x128b_warpx4(sf_col, sf_desc(smem_u32(smem_sfa + stage * X_SFA_BYTES)));
-                    tmem_cp_32x128b_warpx4(sf_col + 4, sf_desc(smem_u32(smem_sfb + stage * X_SFB_BYTES)));
-                    tmem_cp_32x128b_warpx4(sf_col + 8, sf_desc(smem_u32(smem_sfb + stage * X_SFB_BYTES + 512)));
+                    tmem_cp_32x128b_warpx4(sf_col, sf_desc(sfa_a + stage * X_SFA_BYTES));
+                    tmem_cp_32x128b_warpx4(sf_col + 4, sf_desc(sfb_a + stage * X_SFB_BYTES));
+                    tmem_cp_32x128b_warpx4(sf_col + 8, sf_desc(sfb_a + stage * X_SFB_BYTES + 512));
                     const uint32_t a_lo = a_lo_base + stage * (X_STAGE_A >> 4), b_lo = b_lo_base + stage * (X_STAGE_B >> 4);
 #pragma unroll
                     for (int sub = 0; sub < X_STEPS_PER_STAGE; ++sub) {
@@ -239,7 +250,7 @@ gemm_mx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             if (first) {
                                 in_chunk = min(spc, k_left);
                                 if constexpr (PROF) { p_x = clock64(); ++p_chunks; }
-                                mbar_wait(&tmem_empty_bar[ts], tphase ^ 1u);        // the accumulator stage must have been drained
+                                mbar_wait_a(tempty_a + ts * 8u, tphase ^ 1u);       // the accumulator stage must have been drained
                                 if constexpr (PROF) p_empty += clock64() - p_x;
                                 tc_fence_after();
                             }
@@ -247,14 +258,14 @@ gemm_mx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             const uint32_t id = idesc | ((uint32_t)sub << 29) | ((uint32_t)sub << 4);      // a_sf_id / b_sf_id = block in stage
                             umma_mx(tmem_base + ts * X_ACC_STRIDE, mk(a_lo + sub * (X_STEP_BYTES >> 4)), mk(b_lo + sub * (X_STEP_BYTES >> 4)), id,
                                     first ? 0u : 1u, sf_col, sf_col + 4);
-                            if (last) umma_commit(&tmem_full_bar[ts]);
+                            if (last) umma_commit_a(tfull_a + ts * 8u);
                             --k_left;
                             if (--in_chunk == 0) {
                                 if (++ts == (uint32_t)X_ACC_STAGES) { ts = 0; tphase ^= 1u; }
                             }
                         }
                     }
-                    umma_commit(&empty_bar[stage]);                                 // operands and scales of this stage consumed
+                    umma_commit_a(empty_a + stage * 8u);                            // operands and scales of this stage consumed
                     if (++stage == (uint32_t)X_STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -277,10 +288,11 @@ gemm_mx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t buf[UB];
         uint32_t cs = 0, tphase = 0;
 
+        const uint32_t tfull_a = smem_addr_once(&tmem_full_bar[0]), tempty_a = smem_addr_once(&tmem_empty_bar[0]);
         auto release_stage = [&]() {                     // every load of this warp from stage cs has landed
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[cs]);
+            if (lane == 0) mbar_arrive_a(tempty_a + cs * 8u);
             if (++cs == (uint32_t)X_ACC_STAGES) { cs = 0; tphase ^= 1u; }
         };
 
@@ -301,7 +313,7 @@ gemm_mx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
             for (int c = 0; c < n_chunks; ++c) {
                 if constexpr (PROF) { p_x = clock64(); ++p_chunks; }
-                mbar_wait(&tmem_full_bar[cs], tphase);
+                mbar_wait_a(tfull_a + cs * 8u, tphase);
                 if constexpr (PROF) { const long long t = clock64(); p_wait += t - p_x; p_x = t; }
                 tc_fence_after();
                 const uint32_t ta = tmem_base + t_lane + cs * X_ACC_STRIDE + (uint32_t)(h * CPT);

@@ -80,15 +80,18 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // ===================================== TMA producer (both CTAs) =====================================
         if (elect_one()) {
             uint32_t stage = 0, phase = 0;
+            // shared-window addresses as opaque values: rebuilt at every use otherwise (S2UR SR_CgaCtaId + address arithmetic inside the loops, ncu r02p)
+            const uint32_t full_a = smem_addr_once(&full_bar[0]), empty_a = smem_addr_once(&empty_bar[0]);
+            const uint32_t sa_a = smem_addr_once(smem_a), sb_a = smem_addr_once(smem_b);
             for (int tile = pair; tile < n_tiles; tile += n_pairs) {
                 int tm, tn;
                 pair_tile_coords(tile, args, tm, tn);
                 const int row_a = tm * 256 + (int)rank * 128, row_b = tn * P_BN + (int)rank * 128;
                 for (int it = 0; it < args.n_iters; ++it) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1u);                      // this CTA's slot is free (multicast commit)
-                    if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (P_STAGE_A + P_STAGE_B));   // both CTAs' bytes land on the leader's barrier
-                    tma_load_2d_pair(smem_a + stage * P_STAGE_A, &map_a, it * kRowBytes, row_a, &full_bar[stage]);
-                    tma_load_2d_pair(smem_b + stage * P_STAGE_B, &map_b, it * kRowBytes, row_b, &full_bar[stage]);
+                    mbar_wait_a(empty_a + stage * 8u, phase ^ 1u);                 // this CTA's slot is free (multicast commit)
+                    if (rank == 0) mbar_expect_tx_a(full_a + stage * 8u, 2 * (P_STAGE_A + P_STAGE_B));   // both CTAs' bytes land on the leader's barrier
+                    tma_load_2d_pair_a(sa_a + stage * P_STAGE_A, &map_a, it * kRowBytes, row_a, full_a + stage * 8u);
+                    tma_load_2d_pair_a(sb_a + stage * P_STAGE_B, &map_b, it * kRowBytes, row_b, full_a + stage * 8u);
                     if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -97,24 +100,26 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // ====================================== MMA issuer (leader) ======================================
         if (rank == 0 && elect_one()) {
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
+            const uint32_t a_base = smem_addr_once(smem_a), b_base = smem_addr_once(smem_b);
+            const uint32_t full_a = smem_addr_once(&full_bar[0]), empty_a = smem_addr_once(&empty_bar[0]);
+            const uint32_t accf_a = smem_addr_once(&acc_full_bar[0]), acce_a = smem_addr_once(&acc_empty_bar[0]);
             const uint32_t idesc = args.t.idesc;
             for (int tile = pair; tile < n_tiles; tile += n_pairs) {
-                mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1u);                     // both CTAs drained this accumulator stage
+                mbar_wait_a(acce_a + acc * 8u, acc_phase ^ 1u);                     // both CTAs drained this accumulator stage
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * P_BN;
                 for (int it = 0; it < args.n_iters; ++it) {
-                    mbar_wait(&full_bar[stage], phase);
+                    mbar_wait_a(full_a + stage * 8u, phase);
                     tc_fence_after();
                     const uint32_t a_addr = a_base + stage * P_STAGE_A, b_addr = b_base + stage * P_STAGE_B;
 #pragma unroll
                     for (int sub = 0; sub < kStepsPerStage; ++sub)
                         umma_pair<F8>(tmem_d, umma_desc_k128(a_addr + sub * kStepBytes), umma_desc_k128(b_addr + sub * kStepBytes),
                                       idesc, (it | sub) != 0 ? 1u : 0u);
-                    umma_commit_pair(&empty_bar[stage]);                            // frees the slot in BOTH CTAs
+                    umma_commit_pair_a(empty_a + stage * 8u);                       // frees the slot in BOTH CTAs
                     if (++stage == P_STAGES) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit_pair(&acc_full_bar[acc]);                               // tile done: wake both epilogues
+                umma_commit_pair_a(accf_a + acc * 8u);                              // tile done: wake both epilogues
                 acc ^= 1u;
                 if (acc == 0) acc_phase ^= 1u;
             }
@@ -126,12 +131,13 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         uint32_t acc = 0, acc_phase = 0;
         bool bad = false;
         const bool vec_ok = ((args.t.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
+        const uint32_t accf_a = smem_addr_once(&acc_full_bar[0]), acce_a = smem_addr_once(&acc_empty_bar[0]);
         for (int tile = pair; tile < n_tiles; tile += n_pairs) {
             int tm, tn;
             pair_tile_coords(tile, args, tm, tn);
             const int row = tm * 256 + (int)rank * 128 + q * 32 + lane;
             const int col0 = tn * P_BN;
-            mbar_wait(&acc_full_bar[acc], acc_phase);
+            mbar_wait_a(accf_a + acc * 8u, acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + t_lane + acc * P_BN;
             float* crow = C + (int64_t)row * args.t.N + col0;
@@ -179,7 +185,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 else {                                                              // everything is in registers: hand the stage back
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_leader(&acc_empty_bar[acc]);
+                    if (lane == 0) mbar_arrive_leader_a(acce_a + acc * 8u);
                 }
                 emit(buf1, g + 1);
             }

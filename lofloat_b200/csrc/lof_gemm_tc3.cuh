@@ -106,17 +106,20 @@ gemm_tc_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // ===================================== TMA producer =====================================
         if (elect_one()) {
             uint32_t stage = 0, phase = 0;
+            // shared-window addresses as opaque values (rebuilt at every use otherwise: S2UR SR_CgaCtaId inside the loops, ncu r02p)
+            const uint32_t full_a = smem_addr_once(&full_bar[0]), empty_a = smem_addr_once(&empty_bar[0]);
+            const uint32_t sa_a = smem_addr_once(smem_a), sb_a = smem_addr_once(smem_b);
             for (int tile = blockIdx.x; tile < fa.n_tiles; tile += gridDim.x) {
                 int tm, tn;
                 fold_tile_coords(tile, args, tm, tn);
                 const int m0 = tm * F_BM, n0 = tn * BN;
                 for (int it = 0; it < n_stage_iters; ++it) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1u);
-                    mbar_expect_tx(&full_bar[stage], G::kStageA + G::kStageB);
-                    tma_load_2d(smem_a + stage * G::kStageA, &map_a, it * kRowBytes, m0, &full_bar[stage]);   // coords in BYTES of K (uint8 map)
+                    mbar_wait_a(empty_a + stage * 8u, phase ^ 1u);
+                    mbar_expect_tx_a(full_a + stage * 8u, G::kStageA + G::kStageB);
+                    tma_load_2d_a(sa_a + stage * G::kStageA, &map_a, it * kRowBytes, m0, full_a + stage * 8u);   // coords in BYTES of K (uint8 map)
 #pragma unroll
                     for (int h = 0; h < BN / 128; ++h)                                                       // the operand maps' box is 128 rows
-                        tma_load_2d(smem_b + stage * G::kStageB + h * (128 * kRowBytes), &map_b, it * kRowBytes, n0 + h * 128, &full_bar[stage]);
+                        tma_load_2d_a(sb_a + stage * G::kStageB + h * (128 * kRowBytes), &map_b, it * kRowBytes, n0 + h * 128, full_a + stage * 8u);
                     if (++stage == (uint32_t)G::kStages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -131,7 +134,9 @@ gemm_tc_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             uint32_t stage = 0, phase = 0, ts = 0, tphase = 0;      // ts: first TMEM stage of the current chunk
             const uint64_t desc0 = umma_desc_k128(0);
             const uint32_t desc_hi = (uint32_t)(desc0 >> 32), desc_lo0 = (uint32_t)desc0;
-            const uint32_t a_lo_base = desc_lo0 + (smem_u32(smem_a) >> 4), b_lo_base = desc_lo0 + (smem_u32(smem_b) >> 4);
+            const uint32_t a_lo_base = desc_lo0 + (smem_addr_once(smem_a) >> 4), b_lo_base = desc_lo0 + (smem_addr_once(smem_b) >> 4);
+            const uint32_t full_a = smem_addr_once(&full_bar[0]), empty_a = smem_addr_once(&empty_bar[0]);
+            const uint32_t tfull_a = smem_addr_once(&tmem_full_bar[0]), tempty_a = smem_addr_once(&tmem_empty_bar[0]);
             const uint32_t idesc = args.idesc;
             const bool f8 = args.kind_f8 != 0;
             const int spc = args.steps_per_chunk;
@@ -140,7 +145,7 @@ gemm_tc_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 int k_left = args.k_steps;              // k-steps of this tile still to issue
                 int in_chunk = 0;                       // k-steps of the current chunk still to issue (0: the next MMA opens a chunk)
                 for (int it = 0; it < n_stage_iters; ++it) {
-                    mbar_wait(&full_bar[stage], phase);
+                    mbar_wait_a(full_a + stage * 8u, phase);
                     tc_fence_after();
                     const uint32_t a_lo = a_lo_base + stage * (G::kStageA >> 4), b_lo = b_lo_base + stage * (G::kStageB >> 4);
 #pragma unroll
@@ -152,7 +157,7 @@ gemm_tc_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
                             for (int hh = 0; hh < SPLIT; ++hh) {                  // one MMA of N = kSW per TMEM stage of the chunk
                                 if (first) {                                     // first MMA into this TMEM stage: it must have been drained
-                                    mbar_wait(&tmem_empty_bar[ts + hh], tphase ^ 1u);
+                                    mbar_wait_a(tempty_a + (ts + hh) * 8u, tphase ^ 1u);
                                     tc_fence_after();
                                 }
                                 const uint64_t adesc = mk(a_lo + sub * (kStepBytes >> 4));
@@ -160,7 +165,7 @@ gemm_tc_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                                 const uint32_t tmem_d = tmem_base + (ts + hh) * G::kSW;
                                 if (f8) umma_t<true>(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);        // uniform branch (one elected thread)
                                 else umma_t<false>(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
-                                if (last) umma_commit(&tmem_full_bar[ts + hh]);                          // this stage of the chunk is ready
+                                if (last) umma_commit_a(tfull_a + (ts + hh) * 8u);                       // this stage of the chunk is ready
                             }
                             --k_left;
                             if (--in_chunk == 0) {
@@ -169,7 +174,7 @@ gemm_tc_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                             }
                         }
                     }
-                    umma_commit(&empty_bar[stage]);                                                       // smem stage consumed
+                    umma_commit_a(empty_a + stage * 8u);                                                  // smem stage consumed
                     if (++stage == (uint32_t)G::kStages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -197,7 +202,8 @@ gemm_tc_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         auto issue_unit = [&](int u, uint32_t* buf) {   // start loading unit u of this warp's columns of the chunk in stage cs (+ h)
             tmem_ld32(tmem_base + t_lane + (cs + kStageOfHalf * h) * kSW + kColOfHalf * h + (uint32_t)(u * 32), buf);
         };
-        auto full_bar_of = [&]() { return &tmem_full_bar[cs + kStageOfHalf * h]; };
+        const uint32_t tfull_a = smem_addr_once(&tmem_full_bar[0]), tempty_a = smem_addr_once(&tmem_empty_bar[0]);
+        auto full_bar_of = [&]() { return tfull_a + (cs + kStageOfHalf * h) * 8u; };
         auto fold_unit = [&](int u, const uint32_t* p) {
             if constexpr (EPI == kEpiHalf2) {
 #pragma unroll
@@ -238,7 +244,7 @@ gemm_tc_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
 
             // first unit of the tile
-            mbar_wait(full_bar_of(), tphase);
+            mbar_wait_a(full_bar_of(), tphase);
             tc_fence_after();
             issue_unit(0, buf0);
             for (int c = 0; c < n_chunks; ++c) {
@@ -255,17 +261,17 @@ gemm_tc_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         // last unit of chunk c has landed: hand its TMEM stage back to the MMA issuer before folding it
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&tmem_empty_bar[cs + kStageOfHalf * h]);
+                        if (lane == 0) mbar_arrive_a(tempty_a + (cs + kStageOfHalf * h) * 8u);
                         cs += G::kSplit;
                         if (cs == (uint32_t)G::kTmemStages) { cs = 0; tphase ^= 1u; }
                         if (c + 1 < n_chunks) {
-                            issued = mbar_try_wait(full_bar_of(), tphase);          // poll only: fold first if the next chunk is not ready
+                            issued = mbar_try_wait_a(full_bar_of(), tphase);          // poll only: fold first if the next chunk is not ready
                             if (issued) { tc_fence_after(); issue_unit(0, nxt); }
                         }
                     }
                     fold_unit(u, cur);
                     if (!issued) {                                      // (UNITS is even: nxt == buf0 here, as the next chunk expects)
-                        mbar_wait(full_bar_of(), tphase);
+                        mbar_wait_a(full_bar_of(), tphase);
                         tc_fence_after();
                         issue_unit(0, nxt);
                     }

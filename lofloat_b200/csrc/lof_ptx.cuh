@@ -61,6 +61,47 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     }
 }
 
+// The same on a shared-window ADDRESS computed once (smem_u32 of a generic pointer makes the compiler rebuild the window base -- an S2UR
+// of SR_CgaCtaId plus address arithmetic -- at every use inside a loop: ncu r02p showed ~10 % of a fold warp's stall samples there).
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_addr)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar_addr, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(bar_addr), "r"(parity) : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity)
+{
+    if (mbar_try_wait_a(bar_addr, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_a(bar_addr, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar_addr, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+}
+// shared-window address of p as an opaque value: computed once, never rematerialised inside a loop
+__device__ __forceinline__ uint32_t smem_addr_once(const void* p)
+{
+    uint32_t a = smem_u32(p);
+    asm volatile("" : "+r"(a));
+    return a;
+}
+__device__ __forceinline__ void umma_commit_a(uint32_t bar_addr)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
+
 // ---------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map)
 {
@@ -173,6 +214,27 @@ __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot, uint32_t nc
 __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols)
 {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader_a(uint32_t bar_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_addr & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_a(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_addr)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_dst), "l"(map), "r"(c0), "r"(c1), "r"(bar_addr & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_a(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_addr)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_dst), "l"(map), "r"(c0), "r"(c1), "r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_a(uint32_t bar_addr)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar_addr), "h"((uint16_t)3) : "memory");
 }
 // D[tmem, both CTAs] (+)= A * B with M = 256 across the pair; issued by one thread of the leader CTA
 template <bool F8>

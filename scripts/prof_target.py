@@ -111,6 +111,16 @@ def main():
                     "bf16ops": (7, dict(k_chunk=32, partial_round=True)), "generic": (7, dict(k_chunk=32))}[variant]
         for _ in range(3):
             y = lof.lof_gemm_packed(a, bt, mant, **kw)
+    elif what == "mx_gemm":
+        # block-scaled MX GEMM (lof_gemm_mx.cu): python scripts/prof_target.py mx_gemm [M] [fold|onechunk|k128]
+        M = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
+        variant = sys.argv[3] if len(sys.argv) > 3 else "fold"
+        e4m3, e8m0 = fmt("e4m3"), lof.create_e8m0_params()
+        ae, asc, _ = lof.mx_quantize_operand(torch.randn(M, M, device=dev, generator=g), e4m3, e8m0)
+        be, bsc, _ = lof.mx_quantize_operand(torch.randn(M, M, device=dev, generator=g), e4m3, e8m0)
+        kw = {"fold": dict(k_chunk=32, partial_round=True), "k128": dict(k_chunk=128, partial_round=True), "onechunk": dict(k_chunk=0)}[variant]
+        for _ in range(3):
+            y = lof.mx_gemm(ae, asc, be, bsc, 7, **kw)
     else:
         M = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
         A = torch.rand(M, M, device=dev, generator=g) * 2 - 1
