@@ -8,7 +8,7 @@ liblofloat_b200.so (C ABI: include/lofloat_b200.h); there is no CPU fallback.
 """
 from ._lib import LoFloatError, get_option, kernel_launch_count, set_option  # noqa: F401
 from .ops import (FloatFormatDescriptor, InfBehavior, NaNBehavior, PackEndian, RoundingMode, SaturationMode, Signedness,  # noqa: F401
-                  codec_format, fwht, lof_decode, lof_encode, lof_gemm, lof_conv2d, lof_gemm_batched, lof_gemm_packed, lof_linear, mx_decode, mx_encode, mx_gemm, mx_pack_operand, mx_quantize_operand, packed_size, manual_seed, set_gemm_panel, set_seed, virtual_mx_round, virtual_round, virtual_round_strict)
+                  codec_format, fwht, lof_decode, lof_encode, lof_gemm, lof_conv2d, lof_gemm_batched, lof_gemm_packed, lof_linear, mx_decode, mx_encode, mx_gemm, mx_pack_operand, mx_quantize_operand, packed_size, manual_seed, set_gemm_panel, set_gemm_tensor_core, set_seed, virtual_mx_round, virtual_round, virtual_round_strict)
 from .formats import (create_bfloat16_params, create_e8m0_params, create_half_params,  # noqa: F401
                       create_mx_element_params, create_p3109_params, create_single_params)
 from . import _custom_ops  # noqa: F401  (registers torch.ops.lofloat.*)
@@ -20,6 +20,6 @@ __all__ = [
     "virtual_round", "virtual_mx_round", "lof_gemm", "RoundingMode", "InfBehavior", "NaNBehavior", "Signedness",
     "FloatFormatDescriptor", "create_p3109_params", "create_half_params", "create_single_params",
     "create_e8m0_params", "create_bfloat16_params", "create_mx_element_params", "register_format", "get_format",
-    "manual_seed", "set_seed", "set_gemm_panel", "set_option", "get_option", "kernel_launch_count", "LoFloatError",
+    "manual_seed", "set_seed", "set_gemm_panel", "set_gemm_tensor_core", "set_option", "get_option", "kernel_launch_count", "LoFloatError",
     "sharding", "lof_encode", "lof_decode", "lof_gemm_packed", "packed_size", "codec_format", "SaturationMode", "PackEndian", "virtual_round_strict", "mx_encode", "mx_decode", "mx_gemm", "mx_pack_operand", "mx_quantize_operand", "fwht", "lof_gemm_batched", "lof_linear", "lof_conv2d", "STERound", "STEMXRound",
 ]

@@ -30,7 +30,7 @@ cudaError_t launch_mx_tma(int mode, const float* in, float* out, int64_t n, cons
                           int* launches, bool* handled);
 cudaError_t launch_mx_fast(int mode, int scale_mode, const float* in, float* out, int64_t n, const MxArgs& g,
                            const MagicPlan& elem_magic, const MagicPlan& scale_magic, const FastPlan& scale_fast, int scale_mantissa_bits,
-                           const MxLaunchCfg& cfg, cudaStream_t stream, int64_t* main_elems, int* launches);
+                           const MxLaunchCfg& cfg, cudaStream_t stream, int64_t* main_elems, int* launches, const RngArgs* rng_elem, uint64_t first_index);
 cudaError_t launch_fwht(int op, int mode, const float* in, float* out, int64_t n, int hadamard_block, const RoundPlan* plan,
                         float pre_scale, const MxArgs* mx, const MagicPlan* scale_magic, const FastPlan* scale_fast,
                         const MagicPlan* elem_magic, const RngArgs& rng, const RngArgs& rng_scale, uint64_t first_index, int num_sms,
@@ -291,6 +291,10 @@ int round_common(bool params, const void* in, void* out, int64_t n, int dtype, c
                         // checked kinds only where the fp32 path itself needs them (wide targets, stochastic offsets) or bf16.fast = 1
                         const bool chk = magic.lo_rare != 0u || magic.limit != 0xFFFFFFFFu || mode_uses_rng(mode) || g_opt.bf16_fast.load() < 2;
                         kind = chk ? (p32.saturating ? kKindMagicSatChk : kKindMagicExtChk) : (p32.saturating ? kKindMagicSat : kKindMagicExt);
+                        if (chk) {      // the bf16 kernel tests running extrema once per vector: bf16-subnormal inputs and NaN are "rare" lanes there
+                            if (magic.lo_rare < 0x007FFFFFu) magic.lo_rare = 0x007FFFFFu;
+                            if (magic.limit > 0x7F800001u) magic.limit = 0x7F800001u;
+                        }
                     }
                 }
             }
@@ -515,13 +519,14 @@ int mx_common(const float* in, float* out, int64_t n, int block_size, const lof_
     // variant 0 (default): second-generation fast kernel for the eligible bulk, generic kernels for the rest
     // variant 1: TMA-staged kernel; variant 2: first-generation shuffle kernel only (comparison / fallback)
     int64_t done = 0;
-    if (cfg.variant == 0 && g_opt.round_fast.load() >= 2 && !mode_uses_rng(ps_elem->rounding_mode) &&
+    const bool elem_sr_fast = ps_elem->rounding_mode == LOF_StochasticRoundingA || ps_elem->rounding_mode == LOF_StochasticRoundingD;
+    if (cfg.variant == 0 && g_opt.round_fast.load() >= 2 && (!mode_uses_rng(ps_elem->rounding_mode) || elem_sr_fast) &&
         !mode_uses_rng(ps_scale->rounding_mode)) {
         const MagicPlan em = make_magic_plan(a.elem, ps_elem->rounding_mode);
         const MagicPlan sm = make_magic_plan(a.scale, ps_scale->rounding_mode);
         const FastPlan sf = make_fast_plan(a.scale, ps_scale->rounding_mode);
         e = launch_mx_fast(ps_elem->rounding_mode, ps_scale->rounding_mode, in, out, n, a, em, sm, sf, scale_fmt->mantissa_bits,
-                           cfg, cs, &done, &launches);
+                           cfg, cs, &done, &launches, &re, first_index);
         if (e != cudaSuccess) return cuda_fail(e, "virtual_mx_round (fast) launch");
         if (done == n) handled = true;
     }

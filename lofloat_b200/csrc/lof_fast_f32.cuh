@@ -247,6 +247,22 @@ __device__ __forceinline__ uint32_t round_magic_f32(uint32_t x, const MagicPlan&
     return out;
 }
 
+// The same with the per-lane range test reduced to two running extrema (checked kinds on 16-bit containers, where a 4 B / element stream
+// leaves ~11 instructions per element and pipe): the caller keeps mn = min(|x| bits - 1) and mx = max(|x| bits) over its elements and
+// tests ONCE  mn < lo_rare || mx >= limit  (zero inputs give mn = 0xFFFFFFFF and never trip the lower test).  NaN inputs are not patched
+// here: the host clamps `limit` to 0x7F800001 for these kinds, so a NaN sends the element group to the exact routine.
+template <int MODE, bool SAT>
+__device__ __forceinline__ uint32_t round_magic_f32_acc(uint32_t x, const MagicPlan& p, uint32_t w, uint32_t& mn, uint32_t& mx)
+{
+    uint32_t mag, rs;
+    if constexpr (MagicTraits<MODE>::kStochastic) rs = magic_round_sr<MODE>(x, p, w, mag);
+    else rs = magic_round_core<MODE>(x, p.c_add, p.c_floor, mag);
+    const uint32_t a = x & 0x7FFFFFFFu;
+    mn = min(mn, a - 1u);
+    mx = max(mx, a);
+    return (mag >= p.ovf_thresh) ? (SAT ? x : 0x7F800000u) : rs;
+}
+
 // out-of-line exact routine for the rare lanes of the fast kernels
 template <int MODE>
 __device__ __noinline__ uint32_t exact_params_f32(uint32_t v, const RoundPlan& plan, uint32_t w)

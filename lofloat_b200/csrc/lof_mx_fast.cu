@@ -109,6 +109,104 @@ __device__ __forceinline__ float quant_fast(float x, float recip, float scale, c
     return (x != x) ? __uint_as_float(0x7FC00000u) : o;                     // NaN element -> +qNaN (x86 keeps the quieted operand)
 }
 
+// stochastic element modes (SR-A / SR-D): the same with the magic-add stochastic step (lof_fast_f32.cuh magic_round_sr), event word w
+template <int MODE>
+__device__ __forceinline__ float quant_fast_sr(float x, float recip, float scale, const MxFastArgs& k, uint32_t w)
+{
+    const float q = __fmul_rn(x, recip);
+    uint32_t mag;
+    const uint32_t rs = magic_round_sr<MODE>(__float_as_uint(q), k.elem_magic, w, mag);
+    const uint32_t rb = (mag >= k.elem_magic.ovf_thresh) ? (k.elem_sat ? __float_as_uint(q) : 0x7F800000u) : rs;
+    const float o = __fmul_rn(__uint_as_float(rb), scale);
+    return (x != x) ? __uint_as_float(0x7FC00000u) : o;
+}
+
+// Stochastic element rounding (class-0 events: <= 8 random bits each) on the fast path.  The event stream gives the 4-element group v
+// of a 4096-element run the word (v >> 8) of Philox block (run, v & 255) (lof_core.cuh philox_group4), so a lane that takes the SAME
+// float4 position of the steps s, s + 4, s + 8, s + 12 of a 16-step run uses all four words of one block: a warp group walks a run with
+// stride 4 and draws 2 blocks per lane for its 64 elements -- one block per 16 elements, like the elementwise kernels.  Scale rounding stays
+// deterministic; first_index is a multiple of 4096 (host-checked); the steps beyond the last whole run go to the generic kernel.
+template <int BS, int MODE>
+__global__ void __launch_bounds__(kFastThreads)
+mx_fast_sr_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t nruns, MxArgs g, MxFastArgs k, RngArgs rng, uint64_t first_run)
+{
+    constexpr int G = BS / 8;
+    constexpr int kWarps = kFastThreads / 32;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int blk = lane / G, j = lane % G;
+    const int f0 = blk * (2 * G) + j;
+    const int64_t ngroups = nruns * 4;
+    for (int64_t grp = (int64_t)blockIdx.x * kWarps + warp; grp < ngroups; grp += (int64_t)gridDim.x * kWarps) {
+        const int64_t run = grp >> 2;
+        const int sub = (int)(grp & 3);
+        float4 v[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t step = run * 16 + sub + 4 * i;
+            v[i][0] = ld_stream_f4(in + step * 64 + f0);
+            v[i][1] = ld_stream_f4(in + step * 64 + f0 + G);
+        }
+        const uint64_t blk0 = ((first_run + (uint64_t)run) << 8) | (uint32_t)(sub * 64 + f0);
+        const uint4 ba = philox_block(rng, blk0), bb = philox_block(rng, blk0 + (uint32_t)G);
+        const uint32_t wa[4] = {ba.x, ba.y, ba.z, ba.w}, wb[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t step = run * 16 + sub + 4 * i;
+            float m = fmaxf(amax4(v[i][0]), amax4(v[i][1]));
+#pragma unroll
+            for (int off = G / 2; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, off));
+            const uint32_t sb = scale_round(div_pmn(m, k), k, g);
+            const uint4 e0 = bytes_of(wa[i]), e1 = bytes_of(wb[i]);
+            float4 o0, o1;
+            if ((sb - 0x00800000u) < 0x7E800000u && (sb & 0x007FFFFFu) == 0u) {
+                const float scale = __uint_as_float(sb);
+                const float recip = __uint_as_float(0x7F000000u - sb);
+                o0.x = quant_fast_sr<MODE>(v[i][0].x, recip, scale, k, e0.x); o0.y = quant_fast_sr<MODE>(v[i][0].y, recip, scale, k, e0.y);
+                o0.z = quant_fast_sr<MODE>(v[i][0].z, recip, scale, k, e0.z); o0.w = quant_fast_sr<MODE>(v[i][0].w, recip, scale, k, e0.w);
+                o1.x = quant_fast_sr<MODE>(v[i][1].x, recip, scale, k, e1.x); o1.y = quant_fast_sr<MODE>(v[i][1].y, recip, scale, k, e1.y);
+                o1.z = quant_fast_sr<MODE>(v[i][1].z, recip, scale, k, e1.z); o1.w = quant_fast_sr<MODE>(v[i][1].w, recip, scale, k, e1.w);
+            } else {
+                const MxBlockCtx c = mx_make_ctx(__uint_as_float(sb));
+                o0.x = mx_quant<MODE>(v[i][0].x, c, g, e0.x); o0.y = mx_quant<MODE>(v[i][0].y, c, g, e0.y);
+                o0.z = mx_quant<MODE>(v[i][0].z, c, g, e0.z); o0.w = mx_quant<MODE>(v[i][0].w, c, g, e0.w);
+                o1.x = mx_quant<MODE>(v[i][1].x, c, g, e1.x); o1.y = mx_quant<MODE>(v[i][1].y, c, g, e1.y);
+                o1.z = mx_quant<MODE>(v[i][1].z, c, g, e1.z); o1.w = mx_quant<MODE>(v[i][1].w, c, g, e1.w);
+            }
+            st_stream_f4(out + step * 64 + f0, o0);
+            st_stream_f4(out + step * 64 + f0 + G, o1);
+        }
+    }
+}
+
+template <int BS, int MODE>
+cudaError_t launch_bs_sr(const float* in, float* out, int64_t nruns, const MxArgs& g, const MxFastArgs& k, const RngArgs& rng, uint64_t first_run,
+                         const MxLaunchCfg& cfg, cudaStream_t stream)
+{
+    constexpr int kWarps = kFastThreads / 32;
+    int64_t grid = (nruns * 4 + kWarps - 1) / kWarps;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mx_fast_sr_kernel<BS, MODE>, kFastThreads, 0) != cudaSuccess || nb < 1) nb = 1;
+    const int64_t max_ctas = (int64_t)cfg.num_sms * (nb < cfg.ctas_per_sm ? nb : cfg.ctas_per_sm);
+    if (grid > max_ctas) grid = max_ctas;
+    mx_fast_sr_kernel<BS, MODE><<<(unsigned)grid, kFastThreads, 0, stream>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out),
+                                                                              nruns, g, k, rng, first_run);
+    return cudaGetLastError();
+}
+template <int MODE>
+cudaError_t launch_sr(const float* in, float* out, int64_t nruns, const MxArgs& g, const MxFastArgs& k, const RngArgs& rng, uint64_t first_run,
+                      const MxLaunchCfg& cfg, cudaStream_t stream)
+{
+    switch (g.block_size) {
+    case 16:  return launch_bs_sr<16, MODE>(in, out, nruns, g, k, rng, first_run, cfg, stream);
+    case 32:  return launch_bs_sr<32, MODE>(in, out, nruns, g, k, rng, first_run, cfg, stream);
+    case 64:  return launch_bs_sr<64, MODE>(in, out, nruns, g, k, rng, first_run, cfg, stream);
+    case 128: return launch_bs_sr<128, MODE>(in, out, nruns, g, k, rng, first_run, cfg, stream);
+    case 256: return launch_bs_sr<256, MODE>(in, out, nruns, g, k, rng, first_run, cfg, stream);
+    default:  return cudaErrorInvalidValue;
+    }
+}
+
 // BS in {16, 32, 64, 128, 256}.  A warp step covers 256 consecutive floats = 256 / BS blocks; G = BS / 8 lanes
 // share a block and each lane holds the block's float4 number j and j + G (j = lane % G).
 template <int BS, int MODE, int STEPS>
@@ -260,7 +358,7 @@ cudaError_t run_mx_div_selftest(float pmn, unsigned long long* host_mismatches, 
 cudaError_t launch_mx_fast(int mode, int scale_mode, const float* in, float* out, int64_t n, const MxArgs& g,
                            const MagicPlan& elem_magic, const MagicPlan& scale_magic, const FastPlan& scale_fast,
                            int scale_mantissa_bits, const MxLaunchCfg& cfg, cudaStream_t stream, int64_t* main_elems,
-                           int* launches)
+                           int* launches, const RngArgs* rng_elem, uint64_t first_index)
 {
     *main_elems = 0;
     const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
@@ -273,6 +371,17 @@ cudaError_t launch_mx_fast(int mode, int scale_mode, const float* in, float* out
     const MxFastArgs k = make_fast_args(g, elem_magic, scale_magic, scale_fast, scale_mode);
     const int64_t nsteps = n / kStepFloats;
     cudaError_t e;
+    if (mode == LOF_StochasticRoundingA || mode == LOF_StochasticRoundingD) {
+        // class-0 events only (<= 8 random bits), whole 4096-element runs aligned with the event stream, no per-lane range conditions
+        const int64_t nruns = n / 4096;
+        if (!rng_elem || rng_elem->cls != 0u || (first_index & 4095u) != 0u || elem_magic.lo_rare != 0u || nruns < 1) return cudaSuccess;
+        e = (mode == LOF_StochasticRoundingA) ? launch_sr<LOF_StochasticRoundingA>(in, out, nruns, g, k, *rng_elem, first_index >> 12, cfg, stream)
+                                              : launch_sr<LOF_StochasticRoundingD>(in, out, nruns, g, k, *rng_elem, first_index >> 12, cfg, stream);
+        if (e != cudaSuccess) return e;
+        ++*launches;
+        *main_elems = nruns * 4096;
+        return cudaSuccess;
+    }
     switch (mode) {
 #define LOF_CASE(M) case M: e = launch_mode<M>(in, out, nsteps, g, k, cfg, stream); break;
         LOF_CASE(LOF_RoundToNearestEven) LOF_CASE(LOF_RoundTowardsZero) LOF_CASE(LOF_RoundAwayFromZero)

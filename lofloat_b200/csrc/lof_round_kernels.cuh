@@ -168,6 +168,21 @@ __device__ __forceinline__ uint4 round_vec16_bf16_w(uint4 v, const ElemOp<LOF_BF
     // for every input incl. the fp32 subnormals, so no lane ever needs the container routine -- ~7 alu-pipe instructions
     // per element less, which is what bounds a 4 B / element stream
     constexpr bool CHK = !(KIND == kKindMagicSat || KIND == kKindMagicExt);
+    if constexpr (kind_is_magic(KIND) && CHK) {
+        // checked magic kinds: ONE range test per vector on running extrema (the host folds the bf16-subnormal inputs into lo_rare and
+        // NaN into limit for this container, lof_api.cu round_common)
+        uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+        auto two = [&](uint32_t packed, uint32_t wa, uint32_t wb) -> uint32_t {
+            const uint32_t olo = round_magic_f32_acc<MODE, SAT>(packed << 16, op.magic, wa, mn, mx);
+            const uint32_t ohi = round_magic_f32_acc<MODE, SAT>(packed & 0xFFFF0000u, op.magic, wb, mn, mx);
+            return __byte_perm(olo, ohi, 0x7632);
+        };
+        uint4 o;
+        o.x = two(v.x, w0.x, w0.y); o.y = two(v.y, w0.z, w0.w);
+        o.z = two(v.z, w1.x, w1.y); o.w = two(v.w, w1.z, w1.w);
+        rare |= (mn < op.magic.lo_rare) || (mx >= op.magic.limit);
+        return o;
+    }
     auto two = [&](uint32_t packed, uint32_t wa, uint32_t wb) -> uint32_t {
         const uint32_t xlo = packed << 16, xhi = packed & 0xFFFF0000u;
         if constexpr (CHK) rare |= ((xlo & 0x7FFFFFFFu) - 1u) < 0x007FFFFFu || ((xhi & 0x7FFFFFFFu) - 1u) < 0x007FFFFFu;

@@ -267,6 +267,23 @@ def virtual_mx_round(input: torch.Tensor, block_size: int, element_format: Float
 _gemm_kc = 0
 
 
+# Opt-in for callers that cannot pass keywords -- the reference's LoF_Linear / torch.ops.lofloat.lof_gemm call
+# lof_gemm(A, B, bits, mode, sr_bits, scale_a, scale_b) positionally (LoFloat/_custom_ops.py:92-99, layers.py:152-168): with
+# set_gemm_tensor_core(32) every such call runs the tensor-core chunked mode (accumulator re-rounded every k_chunk) instead of the
+# per-FMA SIMT kernel.  None (default) = the reference semantics, bit-exact vs BLIS / the CUDA leaf.
+_gemm_tc = None
+
+
+def set_gemm_tensor_core(k_chunk: int | None, operand_dtype: str = "e4m3", partial_round: bool = False, check: bool = False) -> None:
+    global _gemm_tc
+    if k_chunk is None:
+        _gemm_tc = None
+        return
+    if operand_dtype not in _OPERAND_DTYPES:
+        raise RuntimeError("set_gemm_tensor_core: operand_dtype must be 'e4m3', 'e5m2' or 'bf16'")
+    _gemm_tc = (int(k_chunk), operand_dtype, bool(partial_round), bool(check))
+
+
 def set_gemm_panel(kc: int) -> None:
     global _gemm_kc
     _gemm_kc = int(kc)
@@ -289,6 +306,8 @@ def lof_gemm(A: torch.Tensor, B: torch.Tensor, accum_mant_bits: int, round_mode=
     be exactly representable in `operand_dtype` ("e4m3", "e5m2" or "bf16") -- with check=True (default) the
     call synchronises like the reference (Lof_kernel.cu:149) and raises if they are not.
     """
+    if k_chunk is None and kc is None and _gemm_tc is not None and RoundingMode(int(round_mode)) not in _STOCHASTIC:
+        k_chunk, operand_dtype, partial_round, check = _gemm_tc          # global opt-in (set_gemm_tensor_core)
     if A.dim() != 2 or B.dim() != 2:
         raise RuntimeError("LoF_gemm: A and B must be 2-D")
     if A.size(1) != B.size(0):

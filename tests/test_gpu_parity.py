@@ -308,6 +308,16 @@ def test_mx_modes_scale_modes_and_edge_cases(lof, cuda_dev, variant):
                         got = _np(lof.virtual_mx_round(xwt, bs, _desc(lof, e4), _desc(lof, sf), mode, smode))
                         want = L.o_mx_round(xw, bs, sf, e4, mode, smode)
                         assert L.bits_equal(got, want), (variant, sf.key(), bs, L.MODE_NAMES[mode], smode, L.first_mismatch(xw, got, want))
+        # stochastic element modes on the fast path (one Philox block per 16 elements, runs of 4096 elements): every block size, a shard whose
+        # first_index is run-aligned (fast kernel) and one that is not (generic kernel), a length that leaves a remainder for the generic kernel
+        xs = _mx_input((1 << 15) + 4096 + 512, 33)
+        xst = _gpu(xs, cuda_dev)
+        for bs in (16, 32, 64, 128, 256):
+            for mode, sl in ((L.SR_A, 8), (L.SR_A, 3), (L.SR_D, 7)):
+                for fi in (0, 3 * 4096, 1024):
+                    got = _np(lof.virtual_mx_round(xst, bs, _desc(lof, e4), _desc(lof, e8), mode, L.RNE, sl, rng=(9, 2), first_index=fi))
+                    want = L.o_mx_round(xs, bs, e8, e4, mode, L.RNE, sl, seed=9, offset=2, first_index=fi)
+                    assert L.bits_equal(got, want), (variant, bs, L.MODE_NAMES[mode], sl, fi, L.first_mismatch(xs, got, want))
         # shape is preserved, blocks run over the flattened contiguous tensor (LoPy_bind.cpp:175,216)
         x2 = xt[:4096].reshape(8, 512)
         assert lof.virtual_mx_round(x2, 32, _desc(lof, e4), _desc(lof, e8)).shape == (8, 512)
@@ -1459,3 +1469,22 @@ def test_mx_gemm_full_size_properties(lof, cuda_dev):
     neq = int((Cb != Cm).sum().item())
     # the two tensor-core routes agree except where one chunk's exact partial sum is a tie of the fp32 accumulator's internal alignment
     assert neq <= n * n // 1_000_000, neq
+
+
+def test_positional_lof_gemm_on_the_tensor_core_path(lof, cuda_dev):
+    """set_gemm_tensor_core(k_chunk): the reference's positional call sites (torch.ops.lofloat.lof_gemm, LoFloat/_custom_ops.py:92-99; _lof_linear,
+    layers.py:152-168) run the chunked tensor-core mode without being changed; None restores the per-FMA reference semantics."""
+    torch.manual_seed(21)
+    e4m3 = lof.create_p3109_params(8, 4, bias=7)
+    A = lof.virtual_round(torch.rand(256, 512, device=cuda_dev) * 2 - 1, e4m3)
+    B = lof.virtual_round(torch.rand(512, 384, device=cuda_dev) * 2 - 1, e4m3)
+    exact = lof.lof_gemm(A, B, 10)
+    try:
+        lof.set_gemm_tensor_core(32)
+        via_op = torch.ops.lofloat.lof_gemm(A, B, 10, 0, 0, 1.0, 1.0)
+        assert torch.equal(via_op, lof.lof_gemm(A, B, 10, k_chunk=32))
+        assert L.bits_equal(_np(via_op), L.o_gemm_chunked(_np(A), _np(B), 10, 32))
+        assert torch.equal(lof.lof_gemm(A, B, 10, kc=0), exact)                  # an explicit panel length keeps the exact mode
+    finally:
+        lof.set_gemm_tensor_core(None)
+    assert torch.equal(torch.ops.lofloat.lof_gemm(A, B, 10, 0, 0, 1.0, 1.0), exact)
