@@ -570,6 +570,38 @@ def side_measurements(torch, lib, _lib, dev, x, y, stream):
     except Exception as exc:
         out["mx_round_error"] = str(exc)
     try:
+        # binding overhead on a small tensor (4096 elements: the kernel is ~3 us): calls per second through the ctypes mirror (lofloat_b200.ops)
+        # and through the compiled extension (lofloat_b200/LoFloat.so, the reference's module surface), launches queued back to back
+        import importlib.machinery
+        import importlib.util
+        import lofloat_b200 as lof
+        xs = x[:4096].contiguous()
+        e4 = lof.create_p3109_params(8, 4, bias=7)
+        reps = 2000
+
+        def per_call_us(fn):
+            for _ in range(50):
+                fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / reps * 1e6
+        entry = {"elements": 4096, "calls": reps, "ctypes_ops_us_per_call": per_call_us(lambda: lof.virtual_round(xs, e4)),
+                 "torch_copy_us_per_call": per_call_us(lambda: xs.clone())}
+        ext_path = ROOT / "lofloat_b200" / "LoFloat.so"
+        if ext_path.exists():
+            loader = importlib.machinery.ExtensionFileLoader("LoFloat", str(ext_path))
+            ext = importlib.util.module_from_spec(importlib.util.spec_from_loader("LoFloat", loader))
+            loader.exec_module(ext)
+            fd = ext.FloatFormatDescriptor(8, 3, 7, ext.InfBehavior.Saturating, ext.NaNBehavior._3109, ext.Signedness.Signed, e4.is_inf_checker, e4.is_nan_checker)
+            entry["compiled_extension_us_per_call"] = per_call_us(lambda: ext.virtual_round(xs, fd))
+            entry["results_identical"] = bool(torch.equal(ext.virtual_round(xs, fd), lof.virtual_round(xs, e4)))
+        out["binding_overhead_virtual_round_4096"] = entry
+    except Exception as exc:
+        out["binding_overhead_error"] = str(exc)
+    try:
         # same-box GPU baseline: the reference's OWN device code (lo_float.h virtual_round + mx_round.cuh, compiled unmodified for sm_100a into
         # oracle/_ref/libref_gpu.so by `make -C oracle refgpu`; test / bench infrastructure) in the reference's launch shapes, next to ours
         so = ROOT / "oracle" / "_ref" / "libref_gpu.so"

@@ -398,12 +398,16 @@ cudaError_t launch_round_mode(const void* in, void* out, int64_t n, const ElemOp
 #define LOF_LAUNCH_VEC(U) round_vec_kernel<DTYPE, MODE, KIND, U><<<(unsigned)grid, kRoundThreads, 0, stream>>>( \
             vin, vout, nvec, ntail, op, rng, first_index)
         if constexpr (DTYPE == LOF_F32) {
+#ifdef LOF_ROUND_TUNING_VARIANTS          // `make TUNING=1`: the 1 / 2 / 8-vector instantiations the tuning scripts sweep (3x the fp32 rounding kernels)
             switch (cfg.unroll) {
             case 1: LOF_LAUNCH_VEC(1); break;
             case 2: LOF_LAUNCH_VEC(2); break;
             case 8: LOF_LAUNCH_VEC(8); break;
             default: LOF_LAUNCH_VEC(4); break;
             }
+#else                                     // product build: 4 vectors in flight per thread (the B200 optimum, scripts/geom_tune2.py); other settings map to it
+            LOF_LAUNCH_VEC(4);
+#endif
         } else {
             LOF_LAUNCH_VEC(4);
         }
