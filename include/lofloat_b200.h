@@ -230,13 +230,22 @@ LOF_API int lof_gemm_chunked_f32(const float* A, const float* B, float* C, int64
                          int64_t k_chunk, float alpha, int operand_dtype, uint32_t flags, int32_t* dev_status,
                          void* stream);
 
+/* The same with STOCHASTIC accumulator rounding (any of the six stochastic modes; mantissa-only accumulator, acc_fmt == NULL): the reference
+ * GEMM leaf honours every rounding mode (src/blis_lof_gemm.hpp:217-228).  One dense Philox word per rounding event (stream of
+ * lof_gemm_f32), event index = ((which * n_chunks + chunk) * M + row) * N + col with which = 0 for the partial's rounding
+ * (LOF_GEMM_PARTIAL_ROUND) and 1 for the accumulator's; rng == NULL = seed 0.  Deterministic modes behave exactly like lof_gemm_chunked_f32. */
+LOF_API int lof_gemm_chunked_rng_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                             int accum_mant_bits, const lof_format_t* acc_fmt, const lof_projspec_t* ps,
+                             int64_t k_chunk, float alpha, int operand_dtype, uint32_t flags, const lof_rng_t* rng,
+                             int32_t* dev_status, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Callers fused around the path: the orthonormal block-diagonal Walsh-Hadamard rotation
  * LoF_Linear applies to its activations (LoFloat/layers.py:182-216 `_fwht`, used at :363-365) fused with the rounding
  * that follows it -- STERound (:378, with its fused pre-scale) or STEMXRound (:366-369).  One pass over HBM; bit-identical
  * to `_fwht` followed by the separate op (same butterflies in the same stage order, then * fl32(1 / sqrt(block_size))).
  * block_size: a power of two up to 1024 that divides the last dimension; n % 128 == 0; 16-byte aligned; out may alias in.
- * lof_fwht_f32 (the plain transform) also takes block sizes 2048, 4096 and 8192 -- `hadamard_block_size=None` on an LLM-sized
+ * lof_fwht_f32 (the plain transform) also takes block sizes 2048 ... 32768 -- `hadamard_block_size=None` on an LLM-sized
  * in_features -- as two passes (inside the 1024-element chunks, then across them), still bit-identical to `_fwht`.
  * ------------------------------------------------------------------------------------- */
 LOF_API int lof_fwht_f32(const float* in, float* out, int64_t n, int block_size, void* stream);

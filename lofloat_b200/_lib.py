@@ -27,7 +27,7 @@ ABI_SYMBOLS = (
     "lof_abi_version", "lof_status_string", "lof_last_error_string", "lof_kernel_launch_count",
     "lof_mx_priv_max_normal", "lof_set_option", "lof_get_option", "lof_selftest_mx_division",
     "lof_packed_size", "lof_encode_f32", "lof_decode_f32", "lof_gemm_chunked_packed", "lof_round_strict_f32", "lof_mx_encode_f32", "lof_mx_decode_f32", "lof_gemm_batched_f32", "lof_fwht_f32", "lof_fwht_round_f32", "lof_fwht_mx_round_f32",
-    "lof_linear_f32", "lof_conv2d_f32", "lof_conv2d_out_size", "lof_selftest_gemm_rne_round", "lof_mx_gemm", "lof_mx_pack_tc_f32",
+    "lof_linear_f32", "lof_conv2d_f32", "lof_conv2d_out_size", "lof_selftest_gemm_rne_round", "lof_mx_gemm", "lof_mx_pack_tc_f32", "lof_gemm_chunked_rng_f32",
 )
 LOF_PACK_FORWARD, LOF_PACK_REVERSE = 0, 1
 LOF_CONV_K_CRS, LOF_CONV_K_RSC = 0, 1
@@ -118,6 +118,8 @@ def _declare(lib):
     lib.lof_round_strict_f32.restype = i32
     lib.lof_gemm_chunked_packed.argtypes = [vp, vp, vp, i64, i64, i64, i32, PF, PP, i64, f32, i32, C.c_uint32, vp, vp]
     lib.lof_gemm_chunked_packed.restype = i32
+    lib.lof_gemm_chunked_rng_f32.argtypes = [vp, vp, vp, i64, i64, i64, i32, PF, PP, i64, f32, i32, C.c_uint32, PR, vp, vp]
+    lib.lof_gemm_chunked_rng_f32.restype = i32
     lib.lof_mx_gemm.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, PF, PP, i64, f32, C.c_uint32, vp]
     lib.lof_mx_gemm.restype = i32
     lib.lof_mx_pack_tc_f32.argtypes = [vp, i64, vp, vp, vp, vp]

@@ -39,7 +39,7 @@ cudaError_t run_mx_div_selftest(float pmn, unsigned long long* host_mismatches, 
 cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int mode,
                            int accum_mant_bits, const lof_format_t* acc_fmt, const RoundPlan* acc_plan, const FastPlan* acc_fast,
                            int64_t k_chunk, float alpha, int operand_dtype, uint32_t flags, int* dev_status,
-                           cudaStream_t stream, int* launches, std::string* err);
+                           cudaStream_t stream, int* launches, std::string* err, const RngArgs* rng, int stoch_len);
 cudaError_t launch_gemm_mx(const uint8_t* A, const uint8_t* SA, const uint8_t* Bt, const uint8_t* SB, float* C, int64_t M, int64_t N, int64_t K,
                            int elem_dtype, int mode, int accum_mant_bits, const lof_format_t* acc_fmt, const RoundPlan* acc_plan,
                            const FastPlan* acc_fast, int64_t k_chunk, float alpha, uint32_t flags, cudaStream_t stream, int* launches,
@@ -791,15 +791,15 @@ int lof_conv2d_f32(const float* input, const float* weight, const float* bias, f
     return LOF_OK;
 }
 
-int lof_gemm_chunked_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
-                         int accum_mant_bits, const lof_format_t* acc_fmt, const lof_projspec_t* ps, int64_t k_chunk,
-                         float alpha, int operand_dtype, uint32_t flags, int32_t* dev_status, void* stream)
+namespace {
+int gemm_chunked_common(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                        int accum_mant_bits, const lof_format_t* acc_fmt, const lof_projspec_t* ps, int64_t k_chunk,
+                        float alpha, int operand_dtype, uint32_t flags, const lof_rng_t* rng, int32_t* dev_status, void* stream)
 {
     if (M <= 0 || N <= 0 || K <= 0) return fail(LOF_ERR_INVALID_ARG, "GEMM dimensions must be positive");
     if (!A || !B || !C || !ps) return fail(LOF_ERR_INVALID_ARG, "null argument");
     const int mode = ps->rounding_mode;
     if (mode < 0 || mode >= LOF_NUM_ROUNDING_MODES) return fail(LOF_ERR_INVALID_ARG, "unknown rounding mode");
-    if (mode_uses_rng(mode)) return fail(LOF_ERR_UNSUPPORTED, "chunked GEMM: stochastic accumulator rounding not implemented");
     RoundPlan plan;
     FastPlan fast;
     std::memset(&plan, 0, sizeof plan);
@@ -811,17 +811,39 @@ int lof_gemm_chunked_f32(const float* A, const float* B, float* C, int64_t M, in
     } else if (accum_mant_bits < 0 || accum_mant_bits > 23) {
         return fail(LOF_ERR_INVALID_ARG, "accum_mant_bits must be in [0, 23]");
     }
+    if (mode_uses_rng(mode) && !acc_fmt) {
+        const int r = 23 - accum_mant_bits;                 // the reference's precondition for the shifted-offset modes (lo_float.h:653-860)
+        if (r > 0 && (mode == LOF_StochasticRoundingA || mode == LOF_StochasticRoundingB || mode == LOF_StochasticRoundingC ||
+                      mode == LOF_StochasticRoundingD) && (ps->stoch_length < 1 || ps->stoch_length > r))
+            return fail(LOF_ERR_INVALID_ARG, "stochastic rounding needs 1 <= stoch_length <= dropped mantissa bits");
+    }
     if (num_sms() <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
     int launches = 0;
     std::string err;
+    const RngArgs ra = make_rng(rng, kStreamGemm);
     cudaError_t e = launch_gemm_tc(A, B, C, M, N, K, mode, accum_mant_bits, acc_fmt, acc_fmt ? &plan : nullptr,
                                    acc_fmt ? &fast : nullptr, k_chunk, alpha, operand_dtype,
                                    flags | (g_opt.gemm_fold_split.load() == 2 ? LOF_GEMM_INTERNAL_FOLD_SPLIT2 : 0u), dev_status,
-                                   static_cast<cudaStream_t>(stream), &launches, &err);
+                                   static_cast<cudaStream_t>(stream), &launches, &err, &ra, ps->stoch_length);
     g_launches.fetch_add((uint64_t)launches);
     if (!err.empty()) return fail(LOF_ERR_UNSUPPORTED, err);
     if (e != cudaSuccess) return cuda_fail(e, "lof_gemm_chunked launch");
     return LOF_OK;
+}
+}  // namespace
+
+int lof_gemm_chunked_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                         int accum_mant_bits, const lof_format_t* acc_fmt, const lof_projspec_t* ps, int64_t k_chunk,
+                         float alpha, int operand_dtype, uint32_t flags, int32_t* dev_status, void* stream)
+{
+    return gemm_chunked_common(A, B, C, M, N, K, accum_mant_bits, acc_fmt, ps, k_chunk, alpha, operand_dtype, flags, nullptr, dev_status, stream);
+}
+
+int lof_gemm_chunked_rng_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                             int accum_mant_bits, const lof_format_t* acc_fmt, const lof_projspec_t* ps, int64_t k_chunk,
+                             float alpha, int operand_dtype, uint32_t flags, const lof_rng_t* rng, int32_t* dev_status, void* stream)
+{
+    return gemm_chunked_common(A, B, C, M, N, K, accum_mant_bits, acc_fmt, ps, k_chunk, alpha, operand_dtype, flags, rng, dev_status, stream);
 }
 
 int lof_gemm_chunked_packed(const uint8_t* A, const uint8_t* Bt, float* C, int64_t M, int64_t N, int64_t K,
@@ -901,7 +923,7 @@ int fwht_check(const float* in, float* out, int64_t n, int block, int max_block 
     if (n < 0) return fail(LOF_ERR_INVALID_ARG, "n < 0");
     if (block <= 0 || (block & (block - 1)) != 0) return fail(LOF_ERR_INVALID_ARG, "fwht: block_size must be a power of 2");   // layers.py:196-197
     if (block > max_block)
-        return fail(LOF_ERR_UNSUPPORTED, max_block > 1024 ? "fwht: block sizes up to 8192 are handled" : "fwht: the fused kernels handle block sizes up to 1024 "
+        return fail(LOF_ERR_UNSUPPORTED, max_block > 1024 ? "fwht: block sizes up to 32768 are handled" : "fwht: the fused kernels handle block sizes up to 1024 "
                                                             "(transform with lof_fwht_f32, then round)");
     if (n % block != 0) return fail(LOF_ERR_INVALID_ARG, "fwht: block_size must divide the tensor's last dimension");          // layers.py:198-199
     if (n % 128 != 0) return fail(LOF_ERR_UNSUPPORTED, "fwht: fused kernel needs the element count to be a multiple of 128");
@@ -914,7 +936,7 @@ int fwht_check(const float* in, float* out, int64_t n, int block, int max_block 
 
 int lof_fwht_f32(const float* in, float* out, int64_t n, int block_size, void* stream)
 {
-    const int st = fwht_check(in, out, n, block_size, 8192);
+    const int st = fwht_check(in, out, n, block_size, 32768);
     if (st != LOF_OK) return st;
     if (n == 0) return LOF_OK;
     const int sms = num_sms();

@@ -222,7 +222,7 @@ cudaError_t launch_mode(int mode, int rows_per_block, const float* in, float* ou
     }
 }
 
-// Hadamard blocks of G x 1024 elements (G = 2, 4, 8): the stages h = 1 .. 512 run inside the 1024-element chunks (fwht_kernel,
+// Hadamard blocks of G x 1024 elements (G = 2, 4, 8, 16, 32): the stages h = 1 .. 512 run inside the 1024-element chunks (fwht_kernel,
 // unnormalised), this kernel runs the remaining log2(G) stages h = 1024 .. B / 2 ACROSS the chunks -- a thread owns one float4
 // column of the G chunks, so every pair (i, i + h) sits in its registers -- and applies fl32(1 / sqrt(B)) once at the end.
 // Same adds and subtracts on the same operands in the same stage order as the reference's formulation: bit-identical.
@@ -256,7 +256,7 @@ fwht_cross_kernel(float4* __restrict__ data, int64_t nblocks, float inv_sqrt_b)
 
 }  // namespace
 
-// Plain transform for Hadamard blocks of 2048, 4096 or 8192 elements: two passes (16 B / element) instead of the reference's
+// Plain transform for Hadamard blocks of 2048 ... 32768 elements: two passes (16 B / element) instead of the reference's
 // log2(B) stage tensors.
 cudaError_t launch_fwht_large(const float* in, float* out, int64_t n, int hadamard_block, int num_sms, cudaStream_t stream)
 {
@@ -277,6 +277,8 @@ cudaError_t launch_fwht_large(const float* in, float* out, int64_t n, int hadama
     case 2: fwht_cross_kernel<2><<<grid, 256, 0, stream>>>(v, nblocks, norm); break;
     case 4: fwht_cross_kernel<4><<<grid, 256, 0, stream>>>(v, nblocks, norm); break;
     case 8: fwht_cross_kernel<8><<<grid, 256, 0, stream>>>(v, nblocks, norm); break;
+    case 16: fwht_cross_kernel<16><<<grid, 256, 0, stream>>>(v, nblocks, norm); break;       // 16384: an LLM-sized in_features with hadamard_block_size=None
+    case 32: fwht_cross_kernel<32><<<grid, 256, 0, stream>>>(v, nblocks, norm); break;       // 32768 (32 float4 = 128 registers per thread)
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -90,31 +90,36 @@ struct TcArgs {
     int* status;            // device status word (never NULL)
     int run_mask, run_value;    // the kernel runs iff (*status & run_mask) == run_value
     int tiles_m, tiles_n;
+    // stochastic accumulator rounding (persistent fold kernel, mantissa-only accumulators): one dense Philox word per rounding event,
+    // event index = ((which * n_chunks + chunk) * M + row) * N + col, which = 0 for the partial's rounding (PARTIAL_ROUND), 1 for the accumulator's
+    RngArgs rng;
+    int stoch_len;
+    int n_chunks;
 };
 
 // ------------------------------------------------------------------------------------------------
 // accumulator update  acc <- round(acc + P)
 // ------------------------------------------------------------------------------------------------
 template <int MODE, int EPI>
-__device__ __forceinline__ float round_acc(float t, const TcArgs& a)
+__device__ __forceinline__ float round_acc(float t, const TcArgs& a, uint32_t w = 0u)
 {
     if constexpr (EPI == kEpiMant) {
-        return __uint_as_float(round_mantissa_elem<LOF_F32, MODE>(__float_as_uint(t), a.r, 0, 0u));
+        return __uint_as_float(round_mantissa_elem<LOF_F32, MODE>(__float_as_uint(t), a.r, ModeTraits<MODE>::kUsesRng ? a.stoch_len : 0, w));
     } else {
         uint32_t rb;
         if (a.fast.valid) {
             bool rare = false;
-            rb = round_fast_f32_rt<MODE>(__float_as_uint(t), a.fast, a.plan.saturating != 0, 0u, rare);
-            if (rare) rb = exact_params_f32<MODE>(__float_as_uint(t), a.plan, 0u);
+            rb = round_fast_f32_rt<MODE>(__float_as_uint(t), a.fast, a.plan.saturating != 0, w, rare);
+            if (rare) rb = exact_params_f32<MODE>(__float_as_uint(t), a.plan, w);
         } else {
-            rb = exact_params_f32<MODE>(__float_as_uint(t), a.plan, 0u);
+            rb = exact_params_f32<MODE>(__float_as_uint(t), a.plan, w);
         }
         return __uint_as_float(rb);
     }
 }
 
 template <int MODE, int EPI, bool PARTIAL>
-__device__ __forceinline__ float fold(float acc, float p, const TcArgs& a)
+__device__ __forceinline__ float fold(float acc, float p, const TcArgs& a, uint32_t w_part = 0u, uint32_t w_acc = 0u)
 {
     if constexpr (EPI == kEpiMantFloat) {
         // mantissa-only accumulator, float-domain rounding (round_mant_float, lof_gemm_common.cuh): RNE / RTZ / RD / RU.
@@ -131,8 +136,8 @@ __device__ __forceinline__ float fold(float acc, float p, const TcArgs& a)
         else t = rto_add(acc, p);
         return round_mant_float<MODE>(t, two_r);
     }
-    if constexpr (PARTIAL) p = round_acc<MODE, EPI>(p, a);
-    return round_acc<MODE, EPI>(rto_add(acc, p), a);           // round-to-odd add: the format rounding is the only rounding
+    if constexpr (PARTIAL) p = round_acc<MODE, EPI>(p, a, w_part);
+    return round_acc<MODE, EPI>(rto_add(acc, p), a, w_acc);    // round-to-odd add: the format rounding is the only rounding
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -567,6 +572,18 @@ cudaError_t launch_fold_generic(int mode, bool fmt, bool partial, const CUtensor
     return partial ? launch_fold_mode<kEpiMant, true>(mode, ma, mb, C, a, sms, stream) : launch_fold_mode<kEpiMant, false>(mode, ma, mb, C, a, sms, stream);
 }
 
+template <bool PARTIAL>
+cudaError_t launch_fold_stochastic(int mode, const CUtensorMap& ma, const CUtensorMap& mb, float* C, const TcArgs& a, int sms, cudaStream_t stream)
+{
+    switch (mode) {
+#define LOF_CASE(Mo) case Mo: return launch_fold_one<Mo, kEpiMant, PARTIAL, 128, 1>(ma, mb, C, a, sms, stream);
+        LOF_CASE(LOF_StochasticRoundingA) LOF_CASE(LOF_StochasticRoundingB) LOF_CASE(LOF_StochasticRoundingC)
+        LOF_CASE(LOF_StochasticRoundingD) LOF_CASE(LOF_True_StochasticRounding) LOF_CASE(LOF_ProbabilisticRounding)
+#undef LOF_CASE
+    default: return cudaErrorInvalidValue;
+    }
+}
+
 cudaError_t launch_fold_packed(int packed, bool split2, const CUtensorMap& ma, const CUtensorMap& mb, float* C, const TcArgs& a, int sms,
                                cudaStream_t stream)
 {
@@ -619,7 +636,7 @@ bool hw_f16_accum_ok(int op, int mode, bool partial, bool allow, int accum_mant_
 cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int mode,
                            int accum_mant_bits, const lof_format_t* acc_fmt, const RoundPlan* acc_plan, const FastPlan* acc_fast,
                            int64_t k_chunk, float alpha, int operand_dtype, uint32_t flags, int* dev_status,
-                           cudaStream_t stream, int* launches, std::string* err)
+                           cudaStream_t stream, int* launches, std::string* err, const RngArgs* rng, int stoch_len)
 {
     const int op = operand_dtype == LOF_E4M3 ? kOpE4M3 : operand_dtype == LOF_E5M2 ? kOpE5M2 : operand_dtype == LOF_BF16 ? kOpBF16 : -1;
     if (op < 0) { *err = "chunked GEMM: operand_dtype must be LOF_E4M3, LOF_E5M2 or LOF_BF16"; return cudaSuccess; }
@@ -629,7 +646,8 @@ cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, 
     if (k_chunk % kstep != 0) { *err = "chunked GEMM: k_chunk must be a multiple of " + std::to_string(kstep) + " for this operand type"; return cudaSuccess; }
     if ((K * esize) % 16 != 0) { *err = "chunked GEMM: K * sizeof(operand) must be a multiple of 16 bytes (TMA row pitch)"; return cudaSuccess; }
     if (M > (1 << 24) || N > (1 << 24) || K > (1ll << 30)) { *err = "chunked GEMM: dimension too large"; return cudaSuccess; }
-    if (mode_uses_rng(mode)) { *err = "chunked GEMM: stochastic accumulator rounding is not implemented"; return cudaSuccess; }
+    const bool stochastic = mode_uses_rng(mode);
+    if (stochastic && acc_fmt) { *err = "chunked GEMM: stochastic accumulator rounding needs a mantissa-only accumulator (accum_format = NULL)"; return cudaSuccess; }
 
     // operands already stored in the tensor core's operand type (lof_gemm_chunked_packed): A = M x K, B = Bt = N x K, e4m3 / e5m2
     // bytes or bf16 words
@@ -714,6 +732,9 @@ cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, 
     a.status = status;
     a.tiles_m = (int)((M + BM - 1) / BM);
     a.tiles_n = (int)((N + BN - 1) / BN);
+    if (rng) a.rng = *rng;
+    a.stoch_len = stoch_len;
+    a.n_chunks = (a.k_steps + a.steps_per_chunk - 1) / a.steps_per_chunk;
 
     const bool partial = (flags & LOF_GEMM_PARTIAL_ROUND) != 0;
     const int packed = packed_epi(op, mode, partial, (flags & LOF_GEMM_NO_PACKED) == 0, accum_mant_bits, acc_fmt);
@@ -724,6 +745,17 @@ cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, 
     int sms = 0, dev_id = 0;
     cudaGetDevice(&dev_id);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
+    if (stochastic) {       // persistent fold kernel, generic fold with one Philox word per rounding event
+        a.run_mask = 0; a.run_value = 0;
+        e = partial ? launch_fold_stochastic<true>(mode, ma, mb, C, a, sms, stream) : launch_fold_stochastic<false>(mode, ma, mb, C, a, sms, stream);
+        ++*launches;
+        if (e != cudaSuccess) return fail(e);
+        if (dev_status) {
+            tc_or_status_kernel<<<1, 1, 0, stream>>>(dev_status, status);
+            ++*launches;
+        }
+        return cudaFreeAsync(ws, stream);
+    }
     const bool pair_ok = (flags & LOF_GEMM_NO_PAIR) == 0 && sms >= 2 && K > 0 &&
                          (hw16 || (one_chunk && mode == LOF_RoundToNearestEven));
     if (pair_ok) {

@@ -198,6 +198,7 @@ gemm_tc_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         constexpr uint32_t kStageOfHalf = (G::kSplit == 2) ? 1u : 0u, kColOfHalf = (G::kSplit == 2) ? 0u : (uint32_t)CPT;
         constexpr uint32_t kSW = (uint32_t)G::kSW;
         bool bad = false;
+        int chunk_now = 0, row_now = 0, col_now = 0;    // position of the fold in the event stream (stochastic accumulator rounding)
 
         auto issue_unit = [&](int u, uint32_t* buf) {   // start loading unit u of this warp's columns of the chunk in stage cs (+ h)
             tmem_ld32(tmem_base + t_lane + (cs + kStageOfHalf * h) * kSW + kColOfHalf * h + (uint32_t)(u * 32), buf);
@@ -219,6 +220,30 @@ gemm_tc_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     const __nv_bfloat162 r0 = __hadd2(a0, __floats2bfloat162_rn(__uint_as_float(p[2 * i]), __uint_as_float(p[2 * i + 1])));
                     accp[u * 16 + i] = *reinterpret_cast<const uint32_t*>(&r0);
                 }
+            } else if constexpr (ModeTraits<MODE>::kUsesRng) {
+                // stochastic accumulator rounding: one dense Philox word per event, index = ((which * n_chunks + chunk) * M + row) * N + col;
+                // four consecutive columns share a block when N % 4 == 0 (col0 and the unit offsets are multiples of 4)
+                const uint64_t e_acc = (((uint64_t)args.n_chunks + (uint64_t)chunk_now) * (uint64_t)args.M + (uint64_t)row_now) * (uint64_t)args.N + (uint64_t)(col_now + u * 32);
+                const uint64_t e_part = ((uint64_t)chunk_now * (uint64_t)args.M + (uint64_t)row_now) * (uint64_t)args.N + (uint64_t)(col_now + u * 32);
+                const bool grp = (args.N & 3) == 0;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    uint32_t wa[4], wp[4] = {0u, 0u, 0u, 0u};
+                    if (grp) {
+                        const uint4 b = philox_block(args.rng, (e_acc + i) >> 2);
+                        wa[0] = b.x; wa[1] = b.y; wa[2] = b.z; wa[3] = b.w;
+                        if constexpr (PARTIAL) { const uint4 bp = philox_block(args.rng, (e_part + i) >> 2); wp[0] = bp.x; wp[1] = bp.y; wp[2] = bp.z; wp[3] = bp.w; }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            wa[e] = philox_word(args.rng, e_acc + i + e);
+                            if constexpr (PARTIAL) wp[e] = philox_word(args.rng, e_part + i + e);
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        acc[u * 32 + i + e] = fold<MODE, EPI, PARTIAL>(acc[u * 32 + i + e], __uint_as_float(p[i + e]), args, wp[e], wa[e]);
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
@@ -235,6 +260,7 @@ gemm_tc_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             fold_tile_coords(tile, args, tm, tn);
             const int row = tm * F_BM + q * 32 + lane;
             const int col0 = tn * BN + h * CPT;
+            row_now = row; col_now = col0;
             if constexpr (kPacked) {
 #pragma unroll
                 for (int i = 0; i < CPT / 2; ++i) accp[i] = 0u;
@@ -248,6 +274,7 @@ gemm_tc_fold_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             tc_fence_after();
             issue_unit(0, buf0);
             for (int c = 0; c < n_chunks; ++c) {
+                chunk_now = c;
 #pragma unroll
                 for (int u = 0; u < UNITS; ++u) {
                     uint32_t* cur = (u & 1) ? buf1 : buf0;

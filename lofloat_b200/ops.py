@@ -306,7 +306,7 @@ def lof_gemm(A: torch.Tensor, B: torch.Tensor, accum_mant_bits: int, round_mode=
     be exactly representable in `operand_dtype` ("e4m3", "e5m2" or "bf16") -- with check=True (default) the
     call synchronises like the reference (Lof_kernel.cu:149) and raises if they are not.
     """
-    if k_chunk is None and kc is None and _gemm_tc is not None and RoundingMode(int(round_mode)) not in _STOCHASTIC:
+    if k_chunk is None and kc is None and _gemm_tc is not None:
         k_chunk, operand_dtype, partial_round, check = _gemm_tc          # global opt-in (set_gemm_tensor_core)
     if A.dim() != 2 or B.dim() != 2:
         raise RuntimeError("LoF_gemm: A and B must be 2-D")
@@ -333,9 +333,10 @@ def lof_gemm(A: torch.Tensor, B: torch.Tensor, accum_mant_bits: int, round_mode=
                      (0 if allow_hw_accum else _lib.LOF_GEMM_NO_HW_ACCUM) | (0 if allow_pair else _lib.LOF_GEMM_NO_PAIR) |
                      (0 if allow_persistent else _lib.LOF_GEMM_NO_PERSISTENT) | (0 if allow_float_fold else _lib.LOF_GEMM_NO_FLOAT_FOLD))
             status = torch.zeros(1, dtype=torch.int32, device=A.device)
-            st = L.lof_gemm_chunked_f32(A_c.data_ptr(), B_c.data_ptr(), out.data_ptr(), M, N, K, int(accum_mant_bits),
-                                        C.byref(fmt) if fmt is not None else None, C.byref(ps), int(k_chunk), alpha,
-                                        _OPERAND_DTYPES[operand_dtype], flags, status.data_ptr(), _stream_ptr(A_c))
+            r = _next_rng(mode in _STOCHASTIC, rng)          # stochastic accumulator rounding: one Philox word per rounding event
+            st = L.lof_gemm_chunked_rng_f32(A_c.data_ptr(), B_c.data_ptr(), out.data_ptr(), M, N, K, int(accum_mant_bits),
+                                            C.byref(fmt) if fmt is not None else None, C.byref(ps), int(k_chunk), alpha,
+                                            _OPERAND_DTYPES[operand_dtype], flags, C.byref(r), status.data_ptr(), _stream_ptr(A_c))
         else:
             r = _next_rng(mode in _STOCHASTIC, rng)
             st = L.lof_gemm_f32(A_c.data_ptr(), B_c.data_ptr(), out.data_ptr(), M, N, K, int(accum_mant_bits),
@@ -622,7 +623,7 @@ def fwht(input: torch.Tensor, block_size=None, *, params: FloatFormatDescriptor 
     n = x.numel()
     mode = RoundingMode(int(round_mode))
     if block_size > 1024 and params is not None:
-        # blocks of 2048 .. 8192 (block_size=None on an LLM-sized in_features): two-pass transform, then the rounding op (the
+        # blocks of 2048 .. 32768 (block_size=None on an LLM-sized in_features): two-pass transform, then the rounding op (the
         # single-pass fused kernels hold a whole Hadamard block in one warp's registers, up to 1024 elements)
         y = fwht(x, block_size)
         if mx_block_size is None:

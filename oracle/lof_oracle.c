@@ -526,30 +526,48 @@ float lofo_rto_add(float a, float b)
  * data; the GPU tests state that tolerance and also run exactly-summable data bit for bit), then
  *     partial_round == 0:  acc = round_to_format(acc + P)            -- single rounding (round-to-odd add, then format rounding)
  *     partial_round != 0:  acc = round_to_format(acc + round_to_format(P)) */
+void lofo_gemm_chunked_rng_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                               int accum_mant_bits, const lofo_format* acc_fmt, const lofo_projspec* ps,
+                               int64_t k_chunk, float alpha, int partial_round, const lofo_rng* rng);
+
 void lofo_gemm_chunked_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
                            int accum_mant_bits, const lofo_format* acc_fmt, const lofo_projspec* ps,
                            int64_t k_chunk, float alpha, int partial_round)
 {
+    lofo_gemm_chunked_rng_f32(A, B, C, M, N, K, accum_mant_bits, acc_fmt, ps, k_chunk, alpha, partial_round, NULL);
+}
+
+/* ... with stochastic accumulator rounding: one dense Philox word per rounding event (the stream of lofo_gemm_f32), event index
+ * ((which * n_chunks + chunk) * M + i) * N + j, which = 0 for the partial's rounding, 1 for the accumulator's (rng == NULL: word 0). */
+void lofo_gemm_chunked_rng_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                               int accum_mant_bits, const lofo_format* acc_fmt, const lofo_projspec* ps,
+                               int64_t k_chunk, float alpha, int partial_round, const lofo_rng* rng)
+{
     const int mode = ps->rounding_mode, len = ps->stoch_length;
+    const int need_rng = mode_uses_rng(mode) && rng != NULL;
     if (k_chunk <= 0 || k_chunk > K) k_chunk = K > 0 ? K : 1;
+    const int64_t n_chunks = (K + k_chunk - 1) / k_chunk;
     lofo_consts kacc = {0, 0, 0.0f};
     if (acc_fmt) kacc = lofo_consts_make(acc_fmt);
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < M; ++i) {
         for (int64_t j = 0; j < N; ++j) {
             float acc = 0.0f;
-            for (int64_t k0 = 0; k0 < K; k0 += k_chunk) {
+            int64_t c = 0;
+            for (int64_t k0 = 0; k0 < K; k0 += k_chunk, ++c) {
                 const int64_t k1 = (k0 + k_chunk < K) ? k0 + k_chunk : K;
                 double part = 0.0;
                 for (int64_t l = k0; l < k1; ++l) part += (double)A[i * K + l] * (double)B[l * N + j];
                 float partf = (float)part;
+                const uint32_t wp = need_rng ? lofo_rand_word(rng, (((uint64_t)c) * (uint64_t)M + (uint64_t)i) * (uint64_t)N + (uint64_t)j, LOFO_STREAM_GEMM) : 0u;
+                const uint32_t wa = need_rng ? lofo_rand_word(rng, (((uint64_t)(n_chunks + c)) * (uint64_t)M + (uint64_t)i) * (uint64_t)N + (uint64_t)j, LOFO_STREAM_GEMM) : 0u;
                 if (partial_round) {
-                    if (acc_fmt) partf = u2f(vround_params_f32(f2u(partf), acc_fmt, &kacc, mode, len, 0u));
-                    else         partf = u2f(vround_mant_f32(f2u(partf), accum_mant_bits, mode, len, 0u));
+                    if (acc_fmt) partf = u2f(vround_params_f32(f2u(partf), acc_fmt, &kacc, mode, len, wp));
+                    else         partf = u2f(vround_mant_f32(f2u(partf), accum_mant_bits, mode, len, wp));
                 }
                 const float t = lofo_rto_add(acc, partf);
-                if (acc_fmt) acc = u2f(vround_params_f32(f2u(t), acc_fmt, &kacc, mode, len, 0u));
-                else         acc = u2f(vround_mant_f32(f2u(t), accum_mant_bits, mode, len, 0u));
+                if (acc_fmt) acc = u2f(vround_params_f32(f2u(t), acc_fmt, &kacc, mode, len, wa));
+                else         acc = u2f(vround_mant_f32(f2u(t), accum_mant_bits, mode, len, wa));
             }
             C[i * N + j] = acc * alpha;
         }

@@ -124,6 +124,11 @@ float lofo_rto_add(float a, float b);
 void lofo_gemm_chunked_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
                            int accum_mant_bits, const lofo_format* acc_fmt, const lofo_projspec* ps,
                            int64_t k_chunk, float alpha, int partial_round);
+/* ... with stochastic accumulator rounding: one dense Philox word per event (lofo_gemm_f32's stream), event index
+ * ((which * n_chunks + chunk) * M + i) * N + j, which = 0 partial / 1 accumulator; rng == NULL draws the word 0. */
+void lofo_gemm_chunked_rng_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                               int accum_mant_bits, const lofo_format* acc_fmt, const lofo_projspec* ps,
+                               int64_t k_chunk, float alpha, int partial_round, const lofo_rng* rng);
 
 /* ------------------------------------------------------------------------------------
  * Low-bit storage codec ("next" row f-1): /root/reference/src/lo_pack.hpp.

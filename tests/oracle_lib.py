@@ -177,6 +177,7 @@ def oracle():
         lib.lofo_round_to_odd_fma.restype = C.c_float
         lib.lofo_gemm_f32.argtypes = [vp, vp, vp, i64, i64, i64, i32, PP, i64, C.c_float, C.c_float, PR]
         lib.lofo_gemm_chunked_f32.argtypes = [vp, vp, vp, i64, i64, i64, i32, PF, PP, i64, C.c_float, i32]
+        lib.lofo_gemm_chunked_rng_f32.argtypes = [vp, vp, vp, i64, i64, i64, i32, PF, PP, i64, C.c_float, i32, PR]
         lib.lofo_num_threads.restype = i32
         PC, u8p = C.POINTER(CodecFormat), C.c_void_p
         lib.lofo_float_to_rep.argtypes = [C.c_float, PC, PP, u32]
@@ -307,16 +308,22 @@ def o_gemm(A: np.ndarray, B: np.ndarray, accum_mant_bits: int, mode=RNE, stoch_l
 
 
 def o_gemm_chunked(A, B, accum_mant_bits, k_chunk, mode=RNE, acc_fmt: Format | None = None, alpha=1.0,
-                   partial_round=False):
+                   partial_round=False, stoch_len=0, seed=None, offset=0):
     A = np.ascontiguousarray(A, dtype=np.float32)
     B = np.ascontiguousarray(B, dtype=np.float32)
     M, K = A.shape
     _, N = B.shape
     out = np.zeros((M, N), np.float32)
-    ps = ProjSpec(mode, 0, 0)
-    oracle().lofo_gemm_chunked_f32(_ptr(A), _ptr(B), _ptr(out), M, N, K, accum_mant_bits,
-                                   C.byref(acc_fmt) if acc_fmt is not None else None, C.byref(ps), k_chunk, alpha,
-                                   1 if partial_round else 0)
+    ps = ProjSpec(mode, 0, stoch_len)
+    if seed is None:
+        oracle().lofo_gemm_chunked_f32(_ptr(A), _ptr(B), _ptr(out), M, N, K, accum_mant_bits,
+                                       C.byref(acc_fmt) if acc_fmt is not None else None, C.byref(ps), k_chunk, alpha,
+                                       1 if partial_round else 0)
+    else:
+        rng = _rng(seed, offset)
+        oracle().lofo_gemm_chunked_rng_f32(_ptr(A), _ptr(B), _ptr(out), M, N, K, accum_mant_bits,
+                                           C.byref(acc_fmt) if acc_fmt is not None else None, C.byref(ps), k_chunk, alpha,
+                                           1 if partial_round else 0, C.byref(rng))
     return out
 
 

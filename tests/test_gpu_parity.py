@@ -1161,20 +1161,20 @@ def test_fused_hadamard_rounding(lof, cuda_dev):
     assert float((back - big).abs().max()) < 1e-5
     with pytest.raises(ValueError):
         lof.fwht(big, 48)
-    # blocks of 2048 / 4096 / 8192 (block_size=None on an LLM-sized in_features): two-pass transform, bit-identical to `_fwht`;
+    # blocks of 2048 ... 32768 (block_size=None on an LLM-sized in_features): two-pass transform, bit-identical to `_fwht`;
     # with rounding parameters the Python surface composes it with the rounding op
-    for block in (2048, 4096, 8192):
+    for block in (2048, 4096, 8192, 16384, 32768):
         xt = torch.randn(24, block * 2, device=cuda_dev) * 3
         y = lof.fwht(xt, block)
         assert torch.equal(y, torch_fwht(xt, block)), block
         assert L.bits_equal(_np(y[:2]), L.o_fwht(_np(xt[:2]), block)), block
-        assert torch.equal(lof.fwht(xt.clone(), None), torch_fwht(xt, block * 2)) if block < 8192 else True
+        assert torch.equal(lof.fwht(xt.clone(), None), torch_fwht(xt, block * 2)) if block < 32768 else True
         got = lof.fwht(xt, block, params=e4m3, scale=0.5)
         assert torch.equal(got, lof.virtual_round(y, e4m3, L.RNE, 0, 0.5)), block
         got = lof.fwht(xt, block, params=e4m3, mx_block_size=32, scale_format=e8m0)
         assert torch.equal(got.view(torch.int32), lof.virtual_mx_round(y, 32, e4m3, e8m0).view(torch.int32)), block
     with pytest.raises(lof.LoFloatError):
-        lof.fwht(torch.randn(8, 32768, device=cuda_dev), 16384)                             # > 8192: not handled
+        lof.fwht(torch.randn(4, 131072, device=cuda_dev), 65536)                            # > 32768: not handled
 
 
 def test_batched_gemm_equals_per_slice_calls(lof, cuda_dev):
@@ -1488,3 +1488,31 @@ def test_positional_lof_gemm_on_the_tensor_core_path(lof, cuda_dev):
     finally:
         lof.set_gemm_tensor_core(None)
     assert torch.equal(torch.ops.lofloat.lof_gemm(A, B, 10, 0, 0, 1.0, 1.0), exact)
+
+
+def test_chunked_gemm_stochastic_accumulator_rounding(lof, cuda_dev):
+    """The chunked tensor-core GEMM with STOCHASTIC accumulator rounding (the reference leaf honours every mode, blis_lof_gemm.hpp:217-228):
+    bit-exact against the oracle's Philox stream (one dense word per rounding event, index ((which * n_chunks + chunk) * M + i) * N + j) for all
+    six stochastic modes, single and partial rounding, ragged shapes (N % 4 != 0 takes the per-element word path), and unbiased on average."""
+    torch.manual_seed(31)
+    e4m3 = lof.create_p3109_params(8, 4, bias=7)
+    for (M, N, K) in ((192, 256, 512), (100, 130, 96)):
+        A = lof.virtual_round(torch.rand(M, K, device=cuda_dev) * 2 - 1, e4m3)
+        B = lof.virtual_round(torch.rand(K, N, device=cuda_dev) * 2 - 1, e4m3)
+        for mode, sl in ((L.SR_A, 6), (L.SR_B, 4), (L.SR_C, 5), (L.SR_D, 3), (L.TRUE_SR, 0), (L.PROB, 0)):
+            for partial in (False, True):
+                got = lof.lof_gemm(A, B, 7, mode, sl, k_chunk=32, partial_round=partial, rng=(5, 9))
+                want = L.o_gemm_chunked(_np(A), _np(B), 7, 32, mode=mode, partial_round=partial, stoch_len=sl, seed=5, offset=9)
+                assert L.bits_equal(_np(got), want), (M, N, K, L.MODE_NAMES[mode], partial, L.first_mismatch(_np(got).reshape(-1), _np(got).reshape(-1), want.reshape(-1)))
+    # unbiased: the mean over many seeds approaches the fp32-accumulated product, where RNE into 4 mantissa bits every chunk drifts
+    A = lof.virtual_round(torch.rand(128, 1024, device=cuda_dev), e4m3)
+    B = lof.virtual_round(torch.rand(1024, 128, device=cuda_dev), e4m3)
+    ref = A.double() @ B.double()
+    mean = torch.zeros_like(ref)
+    reps = 48
+    for s in range(reps):
+        mean += lof.lof_gemm(A, B, 4, L.TRUE_SR, 0, k_chunk=32, rng=(100 + s, 0)).double()
+    mean /= reps
+    err_sr = float(((mean - ref).abs() / ref.abs()).mean())
+    err_rne = float(((lof.lof_gemm(A, B, 4, k_chunk=32).double() - ref).abs() / ref.abs()).mean())
+    assert err_sr < 0.5 * err_rne, (err_sr, err_rne)          # (48 repetitions leave ~ sigma / 7 of sampling noise in the mean)
