@@ -772,9 +772,14 @@ cudaError_t launch_gemm_tc(const float* A, const float* B, float* C, int64_t M, 
         else e = f8 ? launch_pair<kEpiMant, true>(ma, mb, C, pa, sms, stream) : launch_pair<kEpiMant, false>(ma, mb, C, pa, sms, stream);
         ++*launches;
         if (e != cudaSuccess) return fail(e);
-        if (hw16) {         // left the fp16 range somewhere: the generic kernel recomputes C (device-side conditional launch)
+        if (hw16) {         // left the fp16 range somewhere: the generic fold recomputes C (device-side conditional launch; the persistent
+                            // kernel makes the untaken gate one wave of 148 CTAs instead of a 4096-CTA launch: ~15 us of a 0.41 ms call)
             a.run_mask = LOF_GEMM_STATUS_PACKED_RANGE; a.run_value = LOF_GEMM_STATUS_PACKED_RANGE;
-            e = launch_generic(mode, acc_fmt != nullptr, partial, ma, mb, C, a, stream);
+            if ((flags & LOF_GEMM_NO_PERSISTENT) == 0)
+                e = launch_fold_generic(mode, acc_fmt != nullptr, partial, ma, mb, C, a, sms, stream,
+                                        op == kOpE4M3 && (flags & LOF_GEMM_NO_FLOAT_FOLD) == 0);
+            else
+                e = launch_generic(mode, acc_fmt != nullptr, partial, ma, mb, C, a, stream);
             ++*launches;
             if (e != cudaSuccess) return fail(e);
         }
