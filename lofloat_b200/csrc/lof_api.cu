@@ -322,6 +322,7 @@ int round_common(bool params, const void* in, void* out, int64_t n, int dtype, c
                 magic = make_magic_plan(plan, mode);
                 if (magic.valid) {
                     const bool chk = magic.lo_rare != 0u || magic.limit != 0xFFFFFFFFu;
+                    if (chk && magic.limit > 0x7F800001u) magic.limit = 0x7F800001u;      // checked kinds: NaN inputs are "rare" lanes (lof_round_kernels.cuh)
                     kind = chk ? (plan.saturating ? kKindMagicSatChk : kKindMagicExtChk)
                                : (plan.saturating ? kKindMagicSat : kKindMagicExt);
                 }

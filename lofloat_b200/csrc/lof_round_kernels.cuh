@@ -107,10 +107,21 @@ __device__ __forceinline__ uint4 round_vec16_magic(uint4 v, const ElemOp<LOF_F32
     const uint32_t x3 = __float_as_uint(__fmul_rn(op.scale, __uint_as_float(v.w)));
     bool rare = false;
     uint4 o;
-    o.x = round_magic_f32<MODE, SAT, CHK>(x0, op.magic, w.x, rare);
-    o.y = round_magic_f32<MODE, SAT, CHK>(x1, op.magic, w.y, rare);
-    o.z = round_magic_f32<MODE, SAT, CHK>(x2, op.magic, w.z, rare);
-    o.w = round_magic_f32<MODE, SAT, CHK>(x3, op.magic, w.w, rare);
+    if constexpr (CHK) {
+        // checked kinds: ONE range test per vector on running extrema; NaN inputs trip it too (the host clamps `limit` to 0x7F800001
+        // for these kinds) and take the exact routine, so the per-lane NaN select disappears as well
+        uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+        o.x = round_magic_f32_acc<MODE, SAT>(x0, op.magic, w.x, mn, mx);
+        o.y = round_magic_f32_acc<MODE, SAT>(x1, op.magic, w.y, mn, mx);
+        o.z = round_magic_f32_acc<MODE, SAT>(x2, op.magic, w.z, mn, mx);
+        o.w = round_magic_f32_acc<MODE, SAT>(x3, op.magic, w.w, mn, mx);
+        rare = (mn < op.magic.lo_rare) || (mx >= op.magic.limit);
+    } else {
+        o.x = round_magic_f32<MODE, SAT, CHK>(x0, op.magic, w.x, rare);
+        o.y = round_magic_f32<MODE, SAT, CHK>(x1, op.magic, w.y, rare);
+        o.z = round_magic_f32<MODE, SAT, CHK>(x2, op.magic, w.z, rare);
+        o.w = round_magic_f32<MODE, SAT, CHK>(x3, op.magic, w.w, rare);
+    }
     if constexpr (CHK) {
         if (rare) {
             o.x = exact_params_f32<MODE>(x0, op.plan, w.x);
