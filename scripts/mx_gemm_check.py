@@ -85,13 +85,13 @@ for n in (8192,):
     A = torch.randn(n, n, device=dev, generator=g); Bt = torch.randn(n, n, device=dev, generator=g)
     ae, asc, _ = lof.mx_quantize_operand(A, fmts["e4m3"]); be, bsc, _ = lof.mx_quantize_operand(Bt, fmts["e4m3"])
     Ad16, Bd16 = decode(ae, asc).bfloat16(), decode(be, bsc).bfloat16()
-    def fw8():
+    def fw16():                                  # option gemm.fold_split = 2: 16 fold warps x 56 columns instead of 8 x 112
         _lib.set_option("gemm.fold_split", 2)
         r = lof.mx_gemm(ae, asc, be, bsc, 7, k_chunk=32, partial_round=True)
         _lib.set_option("gemm.fold_split", 1)
         return r
     for label, fn in (("mx_k32_bf16acc_partial", lambda: lof.mx_gemm(ae, asc, be, bsc, 7, k_chunk=32, partial_round=True)),
-                      ("mx_k32_bf16acc_partial_8foldwarps", fw8),
+                      ("mx_k32_bf16acc_partial_16foldwarps", fw16),
                       ("mx_k64_bf16acc_partial", lambda: lof.mx_gemm(ae, asc, be, bsc, 7, k_chunk=64, partial_round=True)),
                       ("mx_k128_bf16acc_partial", lambda: lof.mx_gemm(ae, asc, be, bsc, 7, k_chunk=128, partial_round=True)),
                       ("mx_onechunk_fp32acc", lambda: lof.mx_gemm(ae, asc, be, bsc, 7, k_chunk=0)),
@@ -110,10 +110,10 @@ for n in (8192,):
             _lib.lib().lof_debug_mx_prof(arr)
             v = list(arr)
             ch = max(v[3], 1); fch = max(v[13], 1)
-            print(f"prof fold_warps={16 if fs == 1 else 8} k_chunk={kc}: MMA thread total {v[0]} clk, {v[3]} chunks -> {v[0]/ch:.0f} clk/chunk; wait smem full {v[1]/ch:.0f}, "
+            print(f"prof fold_warps={8 if fs == 1 else 16} k_chunk={kc}: MMA thread total {v[0]} clk, {v[3]} chunks -> {v[0]/ch:.0f} clk/chunk; wait smem full {v[1]/ch:.0f}, "
                   f"wait tmem empty {v[2]/ch:.0f} | fold warp0: total {v[8]/fch:.0f} clk/chunk: wait tmem full {v[9]/fch:.0f}, read-back {v[10]/fch:.0f}, "
                   f"fold {v[11]/fch:.0f}, C store {v[12]/fch:.0f}", flush=True)
-            out[f"prof_fw{16 if fs == 1 else 8}_k{kc}"] = v
+            out[f"prof_fw{8 if fs == 1 else 16}_k{kc}"] = v
         _lib.set_option("gemm.fold_split", 1); _lib.set_option("gemm.mx_prof", 0)
     same = int((lof.mx_gemm(ae, asc, be, bsc, 7, k_chunk=32, partial_round=True) == lof.lof_gemm_packed(Ad16, Bd16, 7, k_chunk=32, partial_round=True)).sum().item())
     out[f"big_{n}_bit_equal_to_bf16_word_path"] = {"equal": same, "of": n * n}
