@@ -16,7 +16,7 @@ using namespace lof::ptx;
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
 // SELF = false: warp 1 issues, fold warps arrive on empty mbarriers.  SELF = true: the last fold warp to finish a stage's read-back issues.
-template <bool SELF, bool FOLD>
+template <bool SELF, bool FOLD, int NISSUE = 1>
 __global__ void __launch_bounds__(128 + 8 * 32, 1)
 probe(int n_chunks, uint32_t idesc, long long* clk_out)
 {
@@ -40,7 +40,19 @@ probe(int n_chunks, uint32_t idesc, long long* clk_out)
     const uint32_t a_base = smem_addr_once(smem), b_base = smem_addr_once(smem + 128 * 128);
     const uint32_t full_a = smem_addr_once(&full_bar[0]), empty_a = smem_addr_once(&empty_bar[0]);
     const long long t_start = clock64();
-    if (warp == 1) {
+    if (NISSUE == 2 && (warp == 1 || warp == 3)) {
+        if (elect_one()) {                              // one issuing thread PER TMEM stage (hoisted addresses)
+            const uint32_t ts = (warp == 1) ? 0u : 1u;
+            uint32_t tphase = 0;
+            for (int c = (int)ts; c < n_chunks; c += 2) {
+                mbar_wait_a(empty_a + ts * 8u, tphase ^ 1u);
+                tc_fence_after();
+                umma_t<true>(tmem_base + ts * 256, umma_desc_k128(a_base + (c & 3) * 32), umma_desc_k128(b_base + (c & 3) * 32), idesc, 0u);
+                umma_commit_a(full_a + ts * 8u);
+                tphase ^= 1u;
+            }
+        }
+    } else if (warp == 1) {
         if (elect_one()) {
             if constexpr (SELF) {                       // prime the two stages, the fold warps take over
                 for (int c = 0; c < 2 && c < n_chunks; ++c) {
@@ -116,12 +128,12 @@ probe(int n_chunks, uint32_t idesc, long long* clk_out)
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-template <bool SELF, bool FOLD>
+template <bool SELF, bool FOLD, int NISSUE = 1>
 void run(const char* what, int grid, long long* d_clk)
 {
     const int n_chunks = 4096;
     const uint32_t idesc = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    auto kern = probe<SELF, FOLD>;
+    auto kern = probe<SELF, FOLD, NISSUE>;
     const int smem = (128 + 256) * 128 + 1024;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<grid, 128 + 8 * 32, smem>>>(n_chunks, idesc, d_clk);
@@ -141,6 +153,8 @@ int main()
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     run<false, false>("issuing thread + empty mbarriers, read-back only", sms, d_clk);
+    run<false, false, 2>("TWO issuing threads (one per stage) + empty mbarriers, read-back only", sms, d_clk);
+    run<false, true, 2>("TWO issuing threads (one per stage), read-back + bfloat162 fold (spills)", sms, d_clk);
     run<true, false>("last fold warp issues the next MMA, read-back only", sms, d_clk);
     run<false, true>("issuing thread + empty mbarriers, read-back + bfloat162 fold (spills: 192 registers wanted)", sms, d_clk);
     run<true, true>("last fold warp issues the next MMA, read-back + bfloat162 fold (spills)", sms, d_clk);
