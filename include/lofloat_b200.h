@@ -348,6 +348,27 @@ LOF_API int lof_mx_gemm(const uint8_t* a_elems, const uint8_t* a_scales, const u
 #define LOF_MX_PACK_STATUS_SNAPPED 1
 LOF_API int lof_mx_pack_tc_f32(const float* in, int64_t n, uint8_t* elems, uint8_t* scales, int32_t* dev_status, void* stream);
 
+/* Flag hand-shake of the GEMM's peer-to-peer operand exchange (lofloat_b200/sharding.py PeerPanels): every rank maps its peers' operand
+ * shards and a 16-byte flag block per rank (int32[4], zero-initialised) through CUDA IPC and pulls the panels it needs over NVLink with plain
+ * copies; these one-thread kernels order the pulls against the owners' writes.  flags[0] = published epoch, flags[1] = completed remote
+ * pulls (all epochs), flags[3] = sticky protocol-error flag (a bounded spin expired).
+ *   lof_p2p_post(my_flags, epoch, expected_done)   owner's stream, after the shards were written: waits for flags[1] >= expected_done (all pulls
+ *                                                 of the previous epoch), then publishes `epoch`
+ *   lof_p2p_wait(peer_flags, my_flags, epoch)      consumer's stream, before copying from that peer
+ *   lof_p2p_done(peer_flags)                       consumer's stream, after its copies from that peer */
+LOF_API int lof_p2p_post(int32_t* my_flags, int epoch, int expected_done, void* stream);
+LOF_API int lof_p2p_wait(const int32_t* peer_flags, int32_t* my_flags, int epoch, void* stream);
+LOF_API int lof_p2p_done(int32_t* peer_flags, void* stream);
+/* cudaDeviceEnablePeerAccess(peer_device) from the current device (kernels of this device may then dereference IPC-mapped memory of that peer;
+ * already-enabled is not an error), and a plain asynchronous copy between two UVA pointers (peer or local) on `stream`. */
+LOF_API int lof_p2p_enable_peer(int peer_device);
+LOF_API int lof_p2p_copy(void* dst, const void* src, int64_t bytes, void* stream);
+/* CUDA IPC by hand, so that the mapping is opened from the CONSUMER's device (cudaIpcMemLazyEnablePeerAccess): export = the 64-byte
+ * cudaIpcMemHandle_t of the allocation that contains `ptr` (cudaMalloc memory; not stream-ordered pools) + the offset of `ptr` inside it;
+ * import opens the handle once per process (cached by its bytes) and returns base + offset, valid for kernels and copies of the current device. */
+LOF_API int lof_p2p_export(const void* ptr, uint8_t handle[64], uint64_t* offset);
+LOF_API int lof_p2p_import(const uint8_t handle[64], uint64_t offset, void** ptr);
+
 /* ---------------------------------------------------------------------------------------
  * Host-buffer entry points: what a binding calls when the tensor lives in host memory.
  * The library stages through device memory in chunks and overlaps H2D, kernel and D2H on

@@ -27,7 +27,7 @@ ABI_SYMBOLS = (
     "lof_abi_version", "lof_status_string", "lof_last_error_string", "lof_kernel_launch_count",
     "lof_mx_priv_max_normal", "lof_set_option", "lof_get_option", "lof_selftest_mx_division",
     "lof_packed_size", "lof_encode_f32", "lof_decode_f32", "lof_gemm_chunked_packed", "lof_round_strict_f32", "lof_mx_encode_f32", "lof_mx_decode_f32", "lof_gemm_batched_f32", "lof_fwht_f32", "lof_fwht_round_f32", "lof_fwht_mx_round_f32",
-    "lof_linear_f32", "lof_conv2d_f32", "lof_conv2d_out_size", "lof_selftest_gemm_rne_round", "lof_mx_gemm", "lof_mx_pack_tc_f32", "lof_gemm_chunked_rng_f32",
+    "lof_linear_f32", "lof_conv2d_f32", "lof_conv2d_out_size", "lof_selftest_gemm_rne_round", "lof_mx_gemm", "lof_mx_pack_tc_f32", "lof_gemm_chunked_rng_f32", "lof_p2p_post", "lof_p2p_wait", "lof_p2p_done", "lof_p2p_enable_peer", "lof_p2p_copy", "lof_p2p_export", "lof_p2p_import",
 )
 LOF_PACK_FORWARD, LOF_PACK_REVERSE = 0, 1
 LOF_CONV_K_CRS, LOF_CONV_K_RSC = 0, 1
@@ -120,6 +120,19 @@ def _declare(lib):
     lib.lof_gemm_chunked_packed.restype = i32
     lib.lof_gemm_chunked_rng_f32.argtypes = [vp, vp, vp, i64, i64, i64, i32, PF, PP, i64, f32, i32, C.c_uint32, PR, vp, vp]
     lib.lof_gemm_chunked_rng_f32.restype = i32
+    lib.lof_p2p_post.argtypes = [vp, i32, i32, vp]
+    lib.lof_p2p_wait.argtypes = [vp, vp, i32, vp]
+    lib.lof_p2p_done.argtypes = [vp, vp]
+    lib.lof_p2p_enable_peer.argtypes = [i32]
+    lib.lof_p2p_enable_peer.restype = i32
+    lib.lof_p2p_copy.argtypes = [vp, vp, i64, vp]
+    lib.lof_p2p_copy.restype = i32
+    lib.lof_p2p_export.argtypes = [vp, vp, C.POINTER(u64)]
+    lib.lof_p2p_export.restype = i32
+    lib.lof_p2p_import.argtypes = [vp, u64, C.POINTER(vp)]
+    lib.lof_p2p_import.restype = i32
+    for _n in ("lof_p2p_post", "lof_p2p_wait", "lof_p2p_done"):
+        getattr(lib, _n).restype = i32
     lib.lof_mx_gemm.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, PF, PP, i64, f32, C.c_uint32, vp]
     lib.lof_mx_gemm.restype = i32
     lib.lof_mx_pack_tc_f32.argtypes = [vp, i64, vp, vp, vp, vp]

@@ -11,6 +11,9 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <utility>
+#include <vector>
+#include <cuda.h>
 
 #include "lof_core.cuh"
 #include "lof_gemm_common.cuh"
@@ -46,6 +49,9 @@ cudaError_t launch_gemm_mx(const uint8_t* A, const uint8_t* SA, const uint8_t* B
                            std::string* err);
 cudaError_t launch_mx_pack_tc(const float* y, int64_t n, uint8_t* elems, uint8_t* scales, int* dev_status, int num_sms, cudaStream_t stream);
 cudaError_t read_mx_prof(unsigned long long* out16);
+cudaError_t launch_p2p_post(int* flags, int epoch, int expected_done, cudaStream_t stream);
+cudaError_t launch_p2p_wait(const int* peer_flags, int* my_flags, int epoch, cudaStream_t stream);
+cudaError_t launch_p2p_done(int* peer_flags, cudaStream_t stream);
 }  // namespace lof
 
 using namespace lof;
@@ -863,6 +869,98 @@ extern "C" LOF_API int lof_debug_mx_prof(unsigned long long* out16)     // not i
     cudaDeviceSynchronize();
     const cudaError_t e = read_mx_prof(out16);
     return e == cudaSuccess ? LOF_OK : cuda_fail(e, "lof_debug_mx_prof");
+}
+
+int lof_p2p_post(int32_t* my_flags, int epoch, int expected_done, void* stream)
+{
+    if (!my_flags) return fail(LOF_ERR_INVALID_ARG, "null flag block");
+    const cudaError_t e = launch_p2p_post(my_flags, epoch, expected_done, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "lof_p2p_post launch");
+    g_launches.fetch_add(1);
+    return LOF_OK;
+}
+int lof_p2p_wait(const int32_t* peer_flags, int32_t* my_flags, int epoch, void* stream)
+{
+    if (!peer_flags || !my_flags) return fail(LOF_ERR_INVALID_ARG, "null flag block");
+    const cudaError_t e = launch_p2p_wait(peer_flags, my_flags, epoch, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "lof_p2p_wait launch");
+    g_launches.fetch_add(1);
+    return LOF_OK;
+}
+int lof_p2p_done(int32_t* peer_flags, void* stream)
+{
+    if (!peer_flags) return fail(LOF_ERR_INVALID_ARG, "null flag block");
+    const cudaError_t e = launch_p2p_done(peer_flags, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "lof_p2p_done launch");
+    g_launches.fetch_add(1);
+    return LOF_OK;
+}
+
+int lof_p2p_enable_peer(int peer_device)
+{
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (peer_device == cur) return LOF_OK;
+    int can = 0;
+    cudaError_t e = cudaDeviceCanAccessPeer(&can, cur, peer_device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceCanAccessPeer");
+    if (!can) return fail(LOF_ERR_UNSUPPORTED, "lof_p2p_enable_peer: the two devices have no peer access");
+    e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return LOF_OK; }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+    return LOF_OK;
+}
+int lof_p2p_copy(void* dst, const void* src, int64_t bytes, void* stream)
+{
+    if (bytes < 0 || (bytes > 0 && (!dst || !src))) return fail(LOF_ERR_INVALID_ARG, "lof_p2p_copy: bad arguments");
+    if (bytes == 0) return LOF_OK;
+    const cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "lof_p2p_copy");
+    return LOF_OK;
+}
+
+int lof_p2p_export(const void* ptr, uint8_t handle[64], uint64_t* offset)
+{
+    if (!ptr || !handle || !offset) return fail(LOF_ERR_INVALID_ARG, "lof_p2p_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    // the driver entry point is looked up at run time: the library must keep loading on hosts without libcuda.so.1 (CPU test boxes)
+    using RangeFn = CUresult (*)(CUdeviceptr*, size_t*, CUdeviceptr);
+    static RangeFn range_fn = nullptr;
+    if (!range_fn) {
+        void* fp = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fp, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fp)
+            return fail(LOF_ERR_NO_DEVICE, "lof_p2p_export: cuMemGetAddressRange is not available");
+        range_fn = reinterpret_cast<RangeFn>(fp);
+    }
+    if (range_fn(&base, &size, reinterpret_cast<CUdeviceptr>(ptr)) != CUDA_SUCCESS)
+        return fail(LOF_ERR_INVALID_ARG, "lof_p2p_export: not a device allocation");
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaIpcGetMemHandle");
+    std::memcpy(handle, &h, 64);
+    *offset = (uint64_t)(reinterpret_cast<CUdeviceptr>(ptr) - base);
+    return LOF_OK;
+}
+int lof_p2p_import(const uint8_t handle[64], uint64_t offset, void** ptr)
+{
+    if (!handle || !ptr) return fail(LOF_ERR_INVALID_ARG, "lof_p2p_import: null argument");
+    static std::mutex mu;
+    static std::vector<std::pair<std::string, void*>> opened;          // a handle can be opened once per process: cache by its bytes
+    std::lock_guard<std::mutex> lock(mu);
+    const std::string key(reinterpret_cast<const char*>(handle), 64);
+    for (auto& kv : opened)
+        if (kv.first == key) { *ptr = static_cast<uint8_t*>(kv.second) + offset; return LOF_OK; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    void* base = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle");
+    opened.emplace_back(key, base);
+    *ptr = static_cast<uint8_t*>(base) + offset;
+    return LOF_OK;
 }
 
 int lof_mx_pack_tc_f32(const float* in, int64_t n, uint8_t* elems, uint8_t* scales, int32_t* dev_status, void* stream)

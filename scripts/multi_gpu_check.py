@@ -92,6 +92,27 @@ def main():
     Cblk = S.gemm_2d_mx(ael, ascl, wel, wscl, grid, M, N, K, 7, k_chunk=32, partial_round=True)
     report(f"gemm_2d_mx {grid.R}x{grid.C} (MX storage exchange, block-scaled MMA; shard quantisation == global: {same_q}) == single GPU",
            same_q and torch.equal(Cblk, Cfull[r0:r0 + M // grid.R, c0:c0 + N // grid.C]))
+    # the same two products with the operand panels PULLED over NVLink peer memory (CUDA IPC mappings, device-side flag hand-shake) instead of NCCL
+    try:
+        pp = S.PeerPanels(grid)
+        pp.register([ael, ascl], [wel, wscl])
+        fn = lambda a_e, a_s, b_e, b_s: lof.mx_gemm(a_e, a_s, b_e, b_s, 7, k_chunk=32, partial_round=True)
+        ok = True
+        for it in range(3):
+            for split in (False, True):
+                ok = ok and torch.equal(pp.gemm(M, N, K, fn, split=split), Cblk)
+        # shards rewritten between calls (activations): the hand-shake orders the pulls against the owner's writes without any host sync
+        Ax2 = torch.randn(M, K, device=dev, generator=g)
+        ae2, asc2, _ = lof.mx_quantize_operand(Ax2, e4m3, e8m0)
+        want2 = lof.mx_gemm(ae2, asc2, we, wsc, 7, k_chunk=32, partial_round=True)[r0:r0 + M // grid.R, c0:c0 + N // grid.C]
+        ael.copy_(ae2[sa]); ascl.copy_(asc2[sa])
+        ok2 = torch.equal(pp.gemm(M, N, K, fn), want2)
+        ael.copy_(ae[sa]); ascl.copy_(asc[sa])
+        ok3 = torch.equal(pp.gemm(M, N, K, fn), Cblk)
+        report(f"PeerPanels {grid.R}x{grid.C} (P2P pulls of MX storage over NVLink) == gemm_2d_mx (NCCL), also after the shards were rewritten in place",
+               ok and ok2 and ok3 and pp.error_flag() == 0)
+    except Exception as exc:
+        report(f"PeerPanels raised {exc!r}", False)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
