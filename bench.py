@@ -452,16 +452,36 @@ def named_workloads(torch, dist, dev, rank, world, args):
         A_loc = lof.virtual_round(torch.rand(M // world, K, device=dev, generator=g) * 2 - 1, e4m3)      # this rank's rows of A
         Wt_loc = lof.virtual_round(torch.rand(N // world, K, device=dev, generator=g) * 2 - 1, e4m3)     # ... of B^T ([out, in] layout)
         A8, Wt8 = lof.lof_encode(A_loc, ocp).view(M // world, K), lof.lof_encode(Wt_loc, ocp).view(N // world, K)
-        fn = lambda: S.gemm_2d_packed(A8, Wt8, grid, M, N, K, 0, k_chunk=32, accum_format=e5m10)
-        ms, _ = timed(fn, 10, warm=3)
+        fn_nccl = lambda: S.gemm_2d_packed(A8, Wt8, grid, M, N, K, 0, k_chunk=32, accum_format=e5m10)
+        ms_nccl, _ = timed(fn_nccl, 10, warm=3)
+        ms, exchange = ms_nccl, "nccl"
+        if world > 1:
+            # the same operand broadcast as PULLS over NVLink peer memory (sharding.PeerPanels: CUDA IPC mappings, cudaMemcpyAsync on side streams,
+            # device-side flag hand-shake): no collective, no rendez-vous latency
+            try:
+                pp4 = S.PeerPanels(grid)
+                pp4.register([A8], [Wt8])
+                g4 = lambda a_, bt_, out=None: lof.lof_gemm_packed(a_, bt_, 0, k_chunk=32, accum_format=e5m10, out=out)
+                same = torch.equal(pp4.gemm(M, N, K, g4), fn_nccl())
+                ms_p2p, _ = timed(lambda: pp4.gemm(M, N, K, g4), 10, warm=3)
+                ok = torch.tensor([1 if (same and pp4.error_flag() == 0) else 0], device=dev)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if int(ok.item()) == 1:
+                    ms, exchange = ms_p2p, "p2p"
+            except Exception as exc:
+                exchange = f"nccl (PeerPanels unavailable: {exc!r})"[:200]
         tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
         a_gather = (M // grid.R) * K * (grid.C - 1) // grid.C if world > 1 else 0                       # bytes RECEIVED per rank
         b_recv = (N // grid.C) * K * (grid.R * grid.C - 1) // (grid.R * grid.C) if world > 1 else 0
         c4 = {"metric": "lof_gemm_TFLOPs", "value": tf, "unit": "TFLOP/s", "scaling": "strong", "M": M, "N": N, "K": K, "ms": ms,
               "operands": "E4M3 bytes, row-sharded (A rows, B^T rows)", "accumulator": "E5M10 re-rounded every k = 32 (RNE), in the tensor core (fp16 TMEM accumulator)",
-              "grid": f"{grid.R}x{grid.C}", "timed_region": "operand exchange + GEMM",
-              "comm": {"collectives": ["all_gather_into_tensor (A row panel, row group)", "all_to_all_single (B^T column panel, world)"] if world > 1 else [],
-                       "bytes_received_per_rank": int(a_gather + b_recv)},
+              "grid": f"{grid.R}x{grid.C}", "timed_region": "operand exchange + GEMM (every call pulls / gathers the panels again)",
+              "comm": {"exchange": ("peer-to-peer pulls over NVLink (CUDA IPC mappings, cudaMemcpyAsync on side streams, device-side flag hand-shake; no collective)"
+                                    if exchange == "p2p" else exchange) if world > 1 else None,
+                       "collectives": ([] if exchange == "p2p" else ["all_gather_into_tensor (A row panel, row group)", "all_to_all_single (B^T column panel, world)"]) if world > 1 else [],
+                       "bytes_received_per_rank": int(a_gather + b_recv),
+                       "nccl_exchange_ms": ms_nccl if world > 1 else None,
+                       "nccl_exchange_TFLOPs": (2.0 * M * N * K / (ms_nccl * 1e-3) / 1e12) if world > 1 else None},
               "roofline": {"bound": "tensor", "achieved": tf / world, "peak": 4500.0, "unit": "TFLOP/s", "frac": tf / world / 4500.0,
                            "peak_source": "nominal dense FP8 (B200_PROFILING.md)", "frac_of_2x_measured_bf16": tf / world / (2.0 * bf16_burst),
                            "measured_bf16_source": bf16_src,
@@ -503,12 +523,31 @@ def named_workloads(torch, dist, dev, rank, world, args):
         del A_loc, Wt_loc
         torch.cuda.empty_cache()
         fn = lambda: S.gemm_2d_mx(ae, asc, be, bsc, grid, M, N, K, 7, k_chunk=32, partial_round=True)
-        ms, Cblk = timed(fn, 2, warm=1)
+        ms_nccl5, Cblk = timed(fn, 2, warm=1)
         finite = bool(torch.isfinite(Cblk).all().item())
+        ms, exchange5 = ms_nccl5, "nccl"
+        if world > 1:
+            try:
+                pp5 = S.PeerPanels(grid)
+                pp5.register([ae, asc], [be, bsc])
+                g5 = lambda a_e, a_s, b_e, b_s, out=None: lof.mx_gemm(a_e, a_s, b_e, b_s, 7, k_chunk=32, partial_round=True, out=out)
+                same = torch.equal(pp5.gemm(M, N, K, g5), Cblk)
+                ms_p2p5, _ = timed(lambda: pp5.gemm(M, N, K, g5), 2, warm=1)
+                ok = torch.tensor([1 if (same and pp5.error_flag() == 0) else 0], device=dev)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if int(ok.item()) == 1:
+                    ms, exchange5 = ms_p2p5, "p2p"
+                    fn = lambda: pp5.gemm(M, N, K, g5)
+            except Exception as exc:
+                exchange5 = f"nccl (PeerPanels unavailable: {exc!r})"[:200]
         del Cblk
         # the same product with fp32 accumulation over all of K and ONE final bf16-like rounding (plain MXFP8 GEMM): how much the per-block
         # re-rounding costs
-        ms_1c, Cblk = timed(lambda: S.gemm_2d_mx(ae, asc, be, bsc, grid, M, N, K, 7, k_chunk=0), 2, warm=1)
+        if world > 1 and exchange5 == "p2p":
+            g5c = lambda a_e, a_s, b_e, b_s, out=None: lof.mx_gemm(a_e, a_s, b_e, b_s, 7, k_chunk=0, out=out)
+            ms_1c, Cblk = timed(lambda: pp5.gemm(M, N, K, g5c), 2, warm=1)
+        else:
+            ms_1c, Cblk = timed(lambda: S.gemm_2d_mx(ae, asc, be, bsc, grid, M, N, K, 7, k_chunk=0), 2, warm=1)
         del Cblk
         tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
         per_elem = 1.0 + 1.0 / 32.0
@@ -524,9 +563,13 @@ def named_workloads(torch, dist, dev, rank, world, args):
                           "bytes_per_element": "8 (virtual_mx_round: 4 read + 4 written) + 4 + 1.03 (re-split into bytes + scales)",
                           "virtual_mx_round_only_ms": ms_round, "virtual_mx_round_only_GBps_aggregate": 8.0 * (M * K + N * K) / (ms_round * 1e-3) / 1e9},
             "fp32_accumulation_one_final_rounding": {"ms": ms_1c, "TFLOPs": 2.0 * M * N * K / (ms_1c * 1e-3) / 1e12},
-            "comm": {"collectives": ["all_gather_into_tensor x2 (A row panel: element bytes, scale bytes; row group)",
-                                     "all_to_all_single x2 (B^T column panel: element bytes, scale bytes; world)"] if world > 1 else [],
-                     "bytes_received_per_rank": int(a_gather + b_recv)},
+            "comm": {"exchange": ("peer-to-peer pulls over NVLink (CUDA IPC mappings, cudaMemcpyAsync on side streams, device-side flag hand-shake; no collective)"
+                                  if exchange5 == "p2p" else exchange5) if world > 1 else None,
+                     "collectives": ([] if exchange5 == "p2p" else ["all_gather_into_tensor x2 (A row panel: element bytes, scale bytes; row group)",
+                                     "all_to_all_single x2 (B^T column panel: element bytes, scale bytes; world)"]) if world > 1 else [],
+                     "bytes_received_per_rank": int(a_gather + b_recv),
+                     "nccl_exchange_ms": ms_nccl5 if world > 1 else None,
+                     "nccl_exchange_TFLOPs": (2.0 * M * N * K / (ms_nccl5 * 1e-3) / 1e12) if world > 1 else None},
             "finite": finite,
             "roofline": {"bound": "tensor", "achieved": tf / world, "peak": 4500.0, "unit": "TFLOP/s", "frac": tf / world / 4500.0,
                          "peak_source": "nominal dense FP8 (B200_PROFILING.md)", "frac_of_2x_measured_bf16": tf / world / (2.0 * bf16_burst),

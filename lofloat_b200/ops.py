@@ -709,11 +709,21 @@ def mx_decode(scales: torch.Tensor, elems: torch.Tensor, count: int, block_size:
     return out
 
 
+def _gemm_out(out, M: int, N: int, device, what: str) -> torch.Tensor:
+    """The caller's output block (a contiguous float32 [M, N] CUDA tensor, e.g. a row slice of a larger result) or a fresh one."""
+    if out is None:
+        return torch.empty((M, N), dtype=torch.float32, device=device)
+    if out.dtype != torch.float32 or tuple(out.shape) != (M, N) or not out.is_contiguous() or out.device != device:
+        raise RuntimeError(f"{what}: out must be a contiguous float32 [{M}, {N}] tensor on {device}")
+    return out
+
+
 def lof_gemm_packed(A: torch.Tensor, Bt: torch.Tensor, accum_mant_bits: int, round_mode=RoundingMode.RoundToNearestEven,
                     scale_a: float = 1.0, scale_b: float = 1.0, *, k_chunk: int = 32,
                     accum_format: FloatFormatDescriptor | None = None, operand_dtype: str = "e4m3",
                     partial_round: bool = False, allow_packed: bool = True, allow_hw_accum: bool = True,
-                    allow_pair: bool = True, allow_persistent: bool = True, allow_float_fold: bool = True) -> torch.Tensor:
+                    allow_pair: bool = True, allow_persistent: bool = True, allow_float_fold: bool = True,
+                    out: torch.Tensor | None = None) -> torch.Tensor:
     """Chunked tensor-core GEMM on operands already stored in the tensor core's operand type: OCP 8-bit representations
     (uint8, operand_dtype "e4m3" / "e5m2") or bfloat16 tensors (operand_dtype is then "bf16").  A is [M, K], Bt is
     [N, K] (the [out_features, in_features] weight layout).  C = A @ Bt^T / (scale_a * scale_b), float32 [M, N]."""
@@ -736,7 +746,7 @@ def lof_gemm_packed(A: torch.Tensor, Bt: torch.Tensor, accum_mant_bits: int, rou
     A_c, B_c = A.contiguous(), Bt.contiguous()
     M, K = A_c.shape
     N = B_c.shape[0]
-    out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    out = _gemm_out(out, M, N, A.device, "lof_gemm_packed")
     status = torch.zeros(1, dtype=torch.int32, device=A.device)
     fmt = accum_format._c() if accum_format is not None else None
     flags = ((_lib.LOF_GEMM_PARTIAL_ROUND if partial_round else 0) | (0 if allow_packed else _lib.LOF_GEMM_NO_PACKED) |
@@ -782,7 +792,8 @@ def mx_quantize_operand(x: torch.Tensor, element_format: FloatFormatDescriptor, 
 
 def mx_gemm(a_elems: torch.Tensor, a_scales: torch.Tensor, bt_elems: torch.Tensor, bt_scales: torch.Tensor, accum_mant_bits: int,
             round_mode=RoundingMode.RoundToNearestEven, *, k_chunk: int = 32, accum_format: FloatFormatDescriptor | None = None,
-            element: str = "e4m3", partial_round: bool = False, allow_packed: bool = True, alpha: float = 1.0) -> torch.Tensor:
+            element: str = "e4m3", partial_round: bool = False, allow_packed: bool = True, alpha: float = 1.0,
+            out: torch.Tensor | None = None) -> torch.Tensor:
     """Block-scaled tensor-core GEMM on MX storage (tcgen05.mma.kind::mxf8f6f4.block_scale): C[M, N] = alpha * A_mx @ Bt_mx^T with the
     accumulator re-rounded every k_chunk (a multiple of the MX block, 32; 0 = fp32 accumulation over all of K, one final rounding).
     a_elems [M, K] / bt_elems [N, K] uint8 element codes, a_scales [M, K/32] / bt_scales [N, K/32] uint8 E8M0 bytes -- what
@@ -801,7 +812,7 @@ def mx_gemm(a_elems: torch.Tensor, a_scales: torch.Tensor, bt_elems: torch.Tenso
     L = _lib.lib()
     ps = CProjSpec(int(RoundingMode(int(round_mode))), 0, 0)
     ae, asc, be, bsc = a_elems.contiguous(), a_scales.contiguous(), bt_elems.contiguous(), bt_scales.contiguous()
-    out = torch.empty((M, N), dtype=torch.float32, device=ae.device)
+    out = _gemm_out(out, M, N, ae.device, "mx_gemm")
     fmt = accum_format._c() if accum_format is not None else None
     flags = (_lib.LOF_GEMM_PARTIAL_ROUND if partial_round else 0) | (0 if allow_packed else _lib.LOF_GEMM_NO_PACKED)
     with torch.cuda.device(ae.device):

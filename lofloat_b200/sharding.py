@@ -395,11 +395,12 @@ class PeerPanels:
         return a_pan, bt_pan, ev_bt, ev_a
 
     def gemm(self, M: int, N: int, K: int, gemm_fn: Callable, split: Optional[bool] = None) -> torch.Tensor:
-        """C block of this rank = gemm_fn(*a_panel_tensors, *bt_panel_tensors).  split=True computes the rows that come from the rank's own A
-        shard while the other A shards are still in flight (default: when the per-rank problem is large enough to pay for the extra launches)."""
+        """C block of this rank = gemm_fn(*a_panel_tensors, *bt_panel_tensors, out=block).  split=True computes the rows that come from the rank's
+        own A shard while the other A shards are still in flight (default: when the per-rank problem is large enough to pay for the extra
+        launches); every part is written straight into its rows of the result (gemm_fn must accept `out=`)."""
         g = self.grid
         if g.world_size == 1:
-            return gemm_fn(*self.a_mine, *self.bt_mine)
+            return gemm_fn(*self.a_mine, *self.bt_mine, out=None)
         W, R, Cn = g.world_size, g.R, g.C
         mw = M // W
         cur = torch.cuda.current_stream(self.dev)
@@ -414,15 +415,15 @@ class PeerPanels:
                 pan[j * mw:(j + 1) * mw].copy_(t, non_blocking=True)
             for e in ev_a:
                 cur.wait_event(e)
-            return gemm_fn(*a_pan, *bt_pan)
-        parts = [None] * Cn
-        parts[g.c] = gemm_fn(*self.a_mine, *bt_pan)
+            return gemm_fn(*a_pan, *bt_pan, out=None)
+        Cblk = torch.empty((M // R, N // Cn), dtype=torch.float32, device=self.dev)
+        gemm_fn(*self.a_mine, *bt_pan, out=Cblk[g.c * mw:(g.c + 1) * mw])
         for e in ev_a:
             cur.wait_event(e)
         for j in range(Cn):
             if j != g.c:
-                parts[j] = gemm_fn(*[pan[j * mw:(j + 1) * mw] for pan in a_pan], *bt_pan)
-        return torch.cat(parts, dim=0)
+                gemm_fn(*[pan[j * mw:(j + 1) * mw] for pan in a_pan], *bt_pan, out=Cblk[j * mw:(j + 1) * mw])
+        return Cblk
 
     def error_flag(self) -> int:
         """Nonzero if a bounded spin of the hand-shake expired on this rank (protocol error: unequal call sequences)."""

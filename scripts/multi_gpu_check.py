@@ -96,7 +96,7 @@ def main():
     try:
         pp = S.PeerPanels(grid)
         pp.register([ael, ascl], [wel, wscl])
-        fn = lambda a_e, a_s, b_e, b_s: lof.mx_gemm(a_e, a_s, b_e, b_s, 7, k_chunk=32, partial_round=True)
+        fn = lambda a_e, a_s, b_e, b_s, out=None: lof.mx_gemm(a_e, a_s, b_e, b_s, 7, k_chunk=32, partial_round=True, out=out)
         ok = True
         for it in range(3):
             for split in (False, True):
