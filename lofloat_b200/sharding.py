@@ -295,9 +295,9 @@ class PeerPanels:
     with `cudaMemcpyAsync` peer copies on side streams -- no collective, no rendez-vous: ~0.09 ms for a 32 MB shard where the NCCL
     all-gather + all-to-all pair costs ~0.15 ms of latency alone -- while the rows of C that need only the rank's own A shard are computed.
     Ordering is a flag hand-shake on the device (csrc/lof_p2p.cu: post / wait / done), so the shards may be rewritten between calls
-    (activations) without any host synchronisation: `post` publishes epoch e after the owner's writes and after every pull of epoch e - 1
-    has completed, a consumer's side stream waits for the peer's epoch before copying and reports `done` after.  Every rank must make the
-    same sequence of calls.  One list of tensors per operand: [elements] for packed operands, [elements, scales] for MX storage."""
+    (activations) without any host synchronisation: `begin_update()` makes the owner's stream wait until every pull of the latest epoch has
+    completed (call it before overwriting the shards), `post` publishes epoch e after the owner's writes, a consumer's side stream waits for the
+    peer's epoch before copying and reports `done` after.  Every rank must make the same sequence of calls.  One list of tensors per operand: [elements] for packed operands, [elements, scales] for MX storage."""
 
     def __init__(self, grid: GemmGrid):
         import ctypes as _C
@@ -424,6 +424,14 @@ class PeerPanels:
             if j != g.c:
                 gemm_fn(*[pan[j * mw:(j + 1) * mw] for pan in a_pan], *bt_pan, out=Cblk[j * mw:(j + 1) * mw])
         return Cblk
+
+    def begin_update(self) -> None:
+        """Enqueue (current stream) a wait until every peer has finished pulling the shards of the latest epoch: call it BEFORE rewriting the
+        registered shards in place (the next gemm() publishes the new contents)."""
+        if self.grid.world_size == 1 or self.epoch == 0:
+            return
+        cur = torch.cuda.current_stream(self.dev)
+        self._lib.check(self._lib.lib().lof_p2p_post(self.flags.data_ptr(), self.epoch, self.epoch * self.n_consumers, cur.cuda_stream), "lof_p2p_post")
 
     def error_flag(self) -> int:
         """Nonzero if a bounded spin of the hand-shake expired on this rank (protocol error: unequal call sequences)."""

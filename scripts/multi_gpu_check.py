@@ -105,12 +105,14 @@ def main():
         Ax2 = torch.randn(M, K, device=dev, generator=g)
         ae2, asc2, _ = lof.mx_quantize_operand(Ax2, e4m3, e8m0)
         want2 = lof.mx_gemm(ae2, asc2, we, wsc, 7, k_chunk=32, partial_round=True)[r0:r0 + M // grid.R, c0:c0 + N // grid.C]
+        pp.begin_update()                                   # every peer has finished pulling the old contents
         ael.copy_(ae2[sa]); ascl.copy_(asc2[sa])
         ok2 = torch.equal(pp.gemm(M, N, K, fn), want2)
+        pp.begin_update()
         ael.copy_(ae[sa]); ascl.copy_(asc[sa])
         ok3 = torch.equal(pp.gemm(M, N, K, fn), Cblk)
-        report(f"PeerPanels {grid.R}x{grid.C} (P2P pulls of MX storage over NVLink) == gemm_2d_mx (NCCL), also after the shards were rewritten in place",
-               ok and ok2 and ok3 and pp.error_flag() == 0)
+        report(f"PeerPanels {grid.R}x{grid.C} (P2P pulls of MX storage over NVLink) == gemm_2d_mx (NCCL), also after the shards were rewritten in place "
+               f"[static {ok}, rewritten {ok2}, restored {ok3}, error flag {pp.error_flag()}]", ok and ok2 and ok3 and pp.error_flag() == 0)
     except Exception as exc:
         report(f"PeerPanels raised {exc!r}", False)
     dist.barrier()
