@@ -70,7 +70,7 @@ struct Options {
     std::atomic<int64_t> mx_ctas_per_sm{3};
     std::atomic<int64_t> stream_ctas_per_sm{8};  // codec / strict rounding / MX storage / fused Hadamard kernels: ALU-heavier, they want full residency (scripts/stream_tune.py)
     std::atomic<int64_t> host_chunk_bytes{32ll << 20};
-    std::atomic<int64_t> pack_fast{1};           // storage codec: 0 = exact integer routine only, 1 = magic-add fast path where eligible
+    std::atomic<int64_t> pack_fast{2};           // storage codec: 0 = exact integer routine only, 1 = magic-add fast path where eligible, 2 = + register-lane kernels
     std::atomic<int64_t> bf16_fast{2};           // bf16 containers on the magic path: 2 = unchecked kinds where the fp32 path is unchecked, 1 = always checked
     std::atomic<int64_t> gemm_mx_prof{0};        // 1: lof_mx_gemm records CTA 0's cycle breakdown (lof_debug_mx_prof)
     std::atomic<int64_t> gemm_fold_split{1};     // packed fold GEMM, 128 x 256 tile: 1 = one N = 256 MMA per k-step (2 TMEM stages), 2 = two N = 128 MMAs (4 stages)
@@ -604,7 +604,7 @@ int lof_set_option(const char* key, int64_t value)
     else if (k == "mx.ctas_per_sm") { if (value < 1 || value > 64) return fail(LOF_ERR_INVALID_ARG, "mx.ctas_per_sm out of range"); g_opt.mx_ctas_per_sm = value; }
     else if (k == "round.fast") { if (value < 0 || value > 2) return fail(LOF_ERR_INVALID_ARG, "round.fast must be 0, 1 or 2"); g_opt.round_fast = value; }
     else if (k == "stream.ctas_per_sm") { if (value < 1 || value > 64) return fail(LOF_ERR_INVALID_ARG, "stream.ctas_per_sm out of range"); g_opt.stream_ctas_per_sm = value; }
-    else if (k == "pack.fast") { if (value < 0 || value > 1) return fail(LOF_ERR_INVALID_ARG, "pack.fast must be 0 or 1"); g_opt.pack_fast = value; }
+    else if (k == "pack.fast") { if (value < 0 || value > 2) return fail(LOF_ERR_INVALID_ARG, "pack.fast must be 0, 1 or 2"); g_opt.pack_fast = value; }
     else if (k == "bf16.fast") { if (value < 1 || value > 2) return fail(LOF_ERR_INVALID_ARG, "bf16.fast must be 1 or 2"); g_opt.bf16_fast = value; }
     else if (k == "gemm.mx_prof") g_opt.gemm_mx_prof = value;
     else if (k == "gemm.fold_split") { if (value < 1 || value > 2) return fail(LOF_ERR_INVALID_ARG, "gemm.fold_split must be 1 or 2"); g_opt.gemm_fold_split = value; }
@@ -1170,6 +1170,23 @@ int make_codec_plan(const lof_codec_format_t* cf, const lof_projspec_t* ps, int 
     p->f_cadd = (uint32_t)ds << 23;
     p->f_cfloor = (uint32_t)(emin_b + ds) << 23;
     p->f_big = (uint32_t)(to_max_exp + 128) << 23;
+    p->lanes = g_opt.pack_fast.load() >= 2;
+    // arithmetic decode (lof_pack.cu decode_lane_kernel): every finite code's value is a normal fp32 number or zero, and the
+    // smallest magnitude among the infinity / NaN codes (the sign-bit-only NaN of the P3109 formats is tested separately)
+    const int max_ef = (1 << ebits) - 1;
+    p->dec_ok = f.bias >= 0 && f.bias <= 127 && f.bias + f.mantissa_bits <= 127 && max_ef - f.bias + 127 <= 254;
+    p->d_special = 0xFFFFFFFFu;
+    if (p->dec_ok) {
+        const uint32_t magmask = to_signed ? p->signmask - 1u : p->rep_mask;
+        for (uint32_t rep = 0; rep <= p->rep_mask; ++rep) {
+            const bool is_inf = p->has_inf && (rep & p->inf_mask) == p->inf_value;
+            const bool is_nan = (rep & p->nan_mask) == p->nan_value && (p->nan_mant_mask == 0u || (rep & p->nan_mant_mask) != 0u);
+            if (!is_inf && !is_nan) continue;
+            if (to_signed && rep == p->signmask && p->sign_is_nan) continue;
+            if ((rep & magmask) < p->d_special) p->d_special = rep & magmask;
+        }
+        if (p->d_special == 0u) p->dec_ok = 0;               // a special code of magnitude 0 other than the sign-only NaN: table path
+    }
     return LOF_OK;
 }
 }  // namespace

@@ -152,6 +152,111 @@ __device__ __forceinline__ uint32_t float_to_rep_fast(uint32_t x, const FastCons
     return (int32_t)x < 0 ? k.neg_unsigned : mag;             // any negative input incl. -0, -inf, -NaN (:156-161)
 }
 
+// ------------------------------------------------------------------------------------------------
+// Third-generation fast encode ("register lanes"): the SASS of the kernels above spends ~30 instructions per element, two
+// thirds of them on launch-uniform decisions (bit width, signedness, slot order, bounds) and on the per-element test for
+// certain overflow / infinity / NaN.  Here the bit width N and the sign policy SGN are template parameters, the rare
+// inputs (infinities, NaNs) are detected ONCE per thread tile on a running maximum of the exponent fields, and the sign bits of the four
+// elements of a vector are attached with byte permutes on the packed word: ~8 alu-pipe + 3 fma-pipe instructions per
+// element, which keeps a 4.5 .. 6 B / element stream HBM-bound.  Same arithmetic as float_to_rep_fast (equality on every
+// fp32 pattern: tests/test_gpu_parity.py::test_pack_fast_path_equals_exact_every_fp32_pattern, which now runs these).
+// SGN: 0 = unsigned target, 1 = signed, 2 = signed and the sign-bit-only pattern is the NaN (no -0).
+struct LaneConsts {
+    uint32_t e0, cfloor, clampv, dcap, neg_unsigned;
+    int ds;
+    __device__ __forceinline__ explicit LaneConsts(const CodecPlan& p)
+        : e0(p.f_cfloor - p.f_cadd), cfloor(p.f_cfloor), clampv(p.ovf_rep), dcap(p.f_big - (p.f_cfloor - p.f_cadd) - 0x00800000u),
+          neg_unsigned(p.neg_unsigned_rep), ds(p.digit_drop)
+    {
+        asm volatile("" : "+r"(e0), "+r"(cfloor), "+r"(clampv), "+r"(dcap), "+r"(ds));
+    }
+};
+constexpr uint32_t kLaneRare = 0x7F800000u;       // running maximum of the exponent fields >= kLaneRare: an infinity or a NaN among the inputs
+
+// magnitude code of x (no sign attached) and the word whose bit 31 is the sign to attach.  The exponent distance d above the
+// smallest normal is clamped to the format's top binade 2^E: a finite |x| >= 2^(E + 1) (certain overflow -- common for the narrow
+// formats on unscaled data) then adds at least 2^(m + 1) quanta to c = 2^(E + 23 - m), so the code comes out >= 2^(ebits + m), above
+// every magnitude, and the min below turns it into ovf_rep like any other overflow (ovf_rep is max_finite_rep or max_finite_rep + 1,
+// make_codec_plan).  Only infinities and NaNs (emax accumulates the exponent fields) need the second-generation routine.
+template <int MODE, int SGN>
+__device__ __forceinline__ uint32_t lane_mag(uint32_t x, const LaneConsts& k, uint32_t& emax, uint32_t& sx)
+{
+    const uint32_t ef = x & 0x7F800000u;
+    emax = max(emax, ef);
+    const int32_t d = min(max((int32_t)(ef - k.e0), 0), (int32_t)k.dcap);
+    const uint32_t c = (uint32_t)d + k.cfloor;
+    const float cf = __uint_as_float(c), ax = fabsf(__uint_as_float(x));
+    float t;
+    if constexpr (MODE == LOF_RoundToNearestEven) t = __fadd_rn(ax, cf);
+    else if constexpr (MODE == LOF_RoundTowardsZero) t = __fadd_rz(ax, cf);
+    else if constexpr (MODE == LOF_RoundAwayFromZero) t = __fadd_ru(ax, cf);
+    else {                                                    // RoundToOdd: truncate, LSB |= inexact
+        const float tz = __fadd_rz(ax, cf), tu = __fadd_ru(ax, cf);
+        t = __uint_as_float(__float_as_uint(tz) | (tz != tu ? 1u : 0u));
+    }
+    uint32_t mag = min(__float_as_uint(t) - c + ((uint32_t)d >> k.ds), k.clampv);
+    if constexpr (SGN == 0) { mag = (int32_t)x < 0 ? k.neg_unsigned : mag; sx = 0u; }
+    else if constexpr (SGN == 2) sx = mag == 0u ? 0u : x;
+    else sx = x;
+    return mag;
+}
+
+// the rare inputs of a lane (infinity, NaN): the second-generation routine, split into magnitude + sign carrier
+template <int MODE>
+__device__ __noinline__ uint2 lane_mag_rare(uint32_t x, const CodecPlan& p)      // (magnitude, sign carrier)
+{
+    const FastConsts fk(p);
+    const uint32_t rep = float_to_rep_fast<MODE>(x, fk) & p.rep_mask;
+    return make_uint2(rep & ~p.signmask, (rep & p.signmask) ? 0x80000000u : 0u);
+}
+
+// four codes of one 16-byte vector -> packed bits.  pack8: one word; pack16: two words; pack4: 16 bits; pack6: 24 bits.
+template <int SGN>
+__device__ __forceinline__ uint32_t pack8(const uint32_t (&m)[4], const uint32_t (&s)[4])
+{
+    uint32_t w = __byte_perm(__byte_perm(m[0], m[1], 0x0040), __byte_perm(m[2], m[3], 0x0040), 0x5410);
+    if constexpr (SGN != 0) {
+        const uint32_t sg = __byte_perm(__byte_perm(s[0], s[1], 0x0073), __byte_perm(s[2], s[3], 0x0073), 0x5410);
+        w |= sg & 0x80808080u;
+    }
+    return w;
+}
+template <int SGN>
+__device__ __forceinline__ uint2 pack16(const uint32_t (&m)[4], const uint32_t (&s)[4])
+{
+    uint2 w = make_uint2(__byte_perm(m[0], m[1], 0x5410), __byte_perm(m[2], m[3], 0x5410));
+    if constexpr (SGN != 0) {
+        w.x |= __byte_perm(s[0], s[1], 0x7632) & 0x80008000u;
+        w.y |= __byte_perm(s[2], s[3], 0x7632) & 0x80008000u;
+    }
+    return w;
+}
+template <int SGN>
+__device__ __forceinline__ uint32_t pack4(const uint32_t (&m)[4], const uint32_t (&s)[4], bool reverse)
+{
+    uint32_t q[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) q[e] = SGN != 0 ? (m[e] | ((s[e] >> 28) & 8u)) : m[e];
+    uint32_t half = (q[1] * 16u + q[0]) + (q[3] * 16u + q[2]) * 256u;
+    if (reverse) half = ((half & 0x0F0Fu) << 4) | ((half >> 4) & 0x0F0Fu);      // slot order inside a byte (launch-uniform)
+    return half;
+}
+template <int SGN>
+__device__ __forceinline__ uint32_t pack6(const uint32_t (&m)[4], const uint32_t (&s)[4], bool reverse)
+{
+    uint32_t q[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) q[e] = SGN != 0 ? (m[e] | ((s[e] >> 26) & 32u)) : m[e];
+    return reverse ? (q[2] * 64u + q[3]) + (q[0] * 64u + q[1]) * 4096u : (q[1] * 64u + q[0]) + (q[3] * 64u + q[2]) * 4096u;
+}
+// 6-bit lanes: four consecutive lanes hold the 24-bit chunks c0..c3 of 16 consecutive elements = three words
+// (c0 | c1 << 24, c1 >> 8 | c2 << 16, c2 >> 16 | c3 << 8); lane r = lane & 3 builds word r from its own and the next lane's chunk
+__device__ __forceinline__ uint32_t word6(uint32_t chunk, int r)
+{
+    const uint32_t next = __shfl_down_sync(0xFFFFFFFFu, chunk, 1);
+    return __funnelshift_r(chunk | (next << 24), next >> 8, 8 * r);
+}
+
 __device__ __noinline__ float rep_to_float_wide(uint32_t ef, uint32_t mf, bool sign, int mant, int bias)
 {
     const double v = ef == 0u ? ldexp((double)mf, 1 - bias - mant)
@@ -283,6 +388,53 @@ encode_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int64_t 
     }
 }
 
+// whole tiles of 4096 elements, 16-byte aligned source, 8-byte aligned destination (launch_encode sends the remainder to
+// encode_kernel); N in {8, 16, 4, 6}
+template <int MODE, int N, int SGN>
+__global__ void __launch_bounds__(kPackThreads)
+encode_lane_kernel(const uint4* __restrict__ src, uint8_t* __restrict__ dst, int64_t ntiles, const CodecPlan p)
+{
+    const LaneConsts k(p);
+    const bool reverse = p.reverse != 0;
+    constexpr int VPT = kPackPerThread / 4;                   // vectors per thread and tile
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t vbase = tile * (kPackTile / 4) + threadIdx.x;
+        uint4 v[VPT];
+#pragma unroll
+        for (int u = 0; u < VPT; ++u) v[u] = __ldcs(src + vbase + u * kPackThreads);
+        uint32_t m[VPT][4], s[VPT][4], emax = 0u;
+#pragma unroll
+        for (int u = 0; u < VPT; ++u) {
+            const uint32_t x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) m[u][e] = lane_mag<MODE, SGN>(x[e], k, emax, s[u][e]);
+        }
+        if (emax >= kLaneRare) {                              // an infinity / NaN among the thread's 16 elements: rare
+#pragma unroll
+            for (int u = 0; u < VPT; ++u) {
+                const uint32_t x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const uint2 r = lane_mag_rare<MODE>(x[e], p); m[u][e] = r.x; s[u][e] = r.y; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < VPT; ++u) {
+            const int64_t vi = vbase + u * kPackThreads;
+            if constexpr (N == 8) {
+                __stcs(reinterpret_cast<uint32_t*>(dst) + vi, pack8<SGN>(m[u], s[u]));
+            } else if constexpr (N == 16) {
+                __stcs(reinterpret_cast<uint2*>(dst) + vi, pack16<SGN>(m[u], s[u]));
+            } else if constexpr (N == 4) {
+                __stcs(reinterpret_cast<uint16_t*>(dst) + vi, (uint16_t)pack4<SGN>(m[u], s[u], reverse));
+            } else {
+                const int r = (int)threadIdx.x & 3;
+                const uint32_t w = word6(pack6<SGN>(m[u], s[u], reverse), r);
+                if (r != 3) __stcs(reinterpret_cast<uint32_t*>(dst) + (vi >> 2) * 3 + r, w);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kPackThreads)
 decode_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int64_t count, uint64_t packed_bytes,
               const CodecPlan p, int vec_ok, int word_ok)
@@ -378,6 +530,98 @@ decode_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int64_t 
             }
         }
         __syncthreads();
+    }
+}
+
+// Register-lane decode (mirror of encode_lane_kernel): a finite code is  (mag << (23 - m)) reinterpreted as fp32 times
+// 2^(127 - bias) -- exact for normal codes (exponent re-bias) and for subnormal codes (the fp32 subnormal mf * 2^-(126 + m)
+// scaled to mf * 2^(1 - bias - m)) -- with the sign bit moved to bit 31.  Infinity / NaN codes are found on the host
+// (make_codec_plan: every special code has magnitude >= d_special, or is the sign-bit-only pattern when SGN = 2) and
+// detected per thread tile on a running maximum; such tiles are redone with rep_to_float.  ~6 alu-pipe instructions per
+// element instead of a shared-memory table look-up behind launch-uniform branches.
+__device__ __noinline__ float rep_to_float_rare(uint32_t rep, const CodecPlan& p) { return rep_to_float(rep, p); }
+
+struct DecConsts {
+    uint32_t magmask, special, signmask;
+    float k;
+    int ds;
+    __device__ __forceinline__ explicit DecConsts(const CodecPlan& p)
+        : magmask(p.to_signed ? p.signmask - 1u : p.rep_mask), special(p.d_special), signmask(p.signmask), k(0.0f), ds(p.digit_drop)
+    {
+        k = __uint_as_float((uint32_t)(254 - p.bias) << 23);
+        asm volatile("" : "+r"(magmask), "+r"(special), "+r"(ds), "+f"(k));
+    }
+};
+
+// the N-bit code at bit `pos` of `chunk` (compile-time position): value, running maximum of the magnitudes and (SGN = 2) running
+// minimum of rep ^ signmask (0 <=> the sign-bit-only pattern occurred)
+template <int N, int SGN>
+__device__ __forceinline__ float lane_decode(uint32_t chunk, int pos, const DecConsts& k, uint32_t& mmax, uint32_t& nmin)
+{
+    const uint32_t rep = chunk >> pos;
+    const uint32_t mag = rep & k.magmask;
+    mmax = max(mmax, mag);
+    if constexpr (SGN == 2) nmin = min(nmin, (rep & (k.magmask | k.signmask)) ^ k.signmask);
+    const float f = __fmul_rn(__uint_as_float(mag << k.ds), k.k);
+    if constexpr (SGN == 0) return f;
+    else return __uint_as_float(__float_as_uint(f) | ((chunk << (32 - N - pos)) & 0x80000000u));
+}
+
+template <int N, int SGN>
+__global__ void __launch_bounds__(kPackThreads)
+decode_lane_kernel(const uint8_t* __restrict__ src, float4* __restrict__ dst, int64_t ntiles, const CodecPlan p)
+{
+    const DecConsts k(p);
+    const bool reverse = p.reverse != 0;
+    constexpr int VPT = kPackPerThread / 4;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t vbase = tile * (kPackTile / 4) + threadIdx.x;
+        uint32_t c0[VPT], c1[VPT];
+#pragma unroll
+        for (int u = 0; u < VPT; ++u) {
+            const int64_t vi = vbase + u * kPackThreads;
+            c1[u] = 0u;
+            if constexpr (N == 8) c0[u] = __ldcs(reinterpret_cast<const uint32_t*>(src) + vi);
+            else if constexpr (N == 16) { const uint2 w = __ldcs(reinterpret_cast<const uint2*>(src) + vi); c0[u] = w.x; c1[u] = w.y; }
+            else if constexpr (N == 4) c0[u] = __ldcs(reinterpret_cast<const uint16_t*>(src) + vi);
+            else {
+                const int r = (int)threadIdx.x & 3;
+                c0[u] = r != 3 ? __ldcs(reinterpret_cast<const uint32_t*>(src) + (vi >> 2) * 3 + r) : 0u;
+            }
+        }
+        float o[VPT][4];
+        uint32_t mmax = 0u, nmin = 0xFFFFFFFFu;
+#pragma unroll
+        for (int u = 0; u < VPT; ++u) {
+            if constexpr (N == 6) {        // lanes 4g .. 4g + 3 hold the three words of 16 codes: lane r takes bits [24 r, 24 r + 24)
+                const int lane = (int)threadIdx.x & 31, r = lane & 3, g = lane & ~3;
+                const uint32_t lo = __shfl_sync(0xFFFFFFFFu, c0[u], g + max(r - 1, 0)), hi = __shfl_sync(0xFFFFFFFFu, c0[u], g + min(r, 2));
+                c0[u] = __funnelshift_r(lo, hi, (32 - 8 * r) & 31) & 0x00FFFFFFu;
+            }
+            if constexpr (N == 4) { if (reverse) c0[u] = ((c0[u] & 0x0F0Fu) << 4) | ((c0[u] >> 4) & 0x0F0Fu); }
+            if constexpr (N == 16) {
+                o[u][0] = lane_decode<16, SGN>(c0[u], 0, k, mmax, nmin); o[u][1] = lane_decode<16, SGN>(c0[u], 16, k, mmax, nmin);
+                o[u][2] = lane_decode<16, SGN>(c1[u], 0, k, mmax, nmin); o[u][3] = lane_decode<16, SGN>(c1[u], 16, k, mmax, nmin);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[u][e] = lane_decode<N, SGN>(c0[u], N * e, k, mmax, nmin);
+            }
+        }
+        if (mmax >= k.special || (SGN == 2 && nmin == 0u)) {         // an infinity / NaN code among the thread's 16: rare
+#pragma unroll
+            for (int u = 0; u < VPT; ++u) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t rep = N == 16 ? ((e < 2 ? c0[u] : c1[u]) >> (16 * (e & 1))) : (c0[u] >> (N * e));
+                    o[u][e] = rep_to_float_rare(rep, p);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < VPT; ++u) {
+            const bool flip = N == 6 && reverse;
+            __stcs(dst + vbase + u * kPackThreads, flip ? make_float4(o[u][3], o[u][2], o[u][1], o[u][0]) : make_float4(o[u][0], o[u][1], o[u][2], o[u][3]));
+        }
     }
 }
 
@@ -631,6 +875,96 @@ mx_encode_fast_kernel(const float4* __restrict__ in, int64_t nvec, MxArgs a, MxS
     }
 }
 
+// Third-generation MX encode: the warp-step structure of mx_encode_fast_kernel with the register-lane element path
+// (lane_mag + pack8 / pack4 / pack6, bit width as a template parameter, rare inputs detected once per vector).  Signed
+// element formats (SGN = 1: with a -0, SGN = 2: P3109-style, the sign-bit-only pattern is the NaN); anything else stays on the kernels above.
+template <int MODE, int LANES, int N, int SGN>
+__global__ void __launch_bounds__(kPackThreads)
+mx_encode_lane_kernel(const float4* __restrict__ in, int64_t nvec, MxArgs a, MxScaleQuick sq, CodecPlan scale_codec, CodecPlan elem_codec,
+                      RngArgs rng_scale, uint64_t first_index, uint8_t* __restrict__ scales, uint8_t* __restrict__ elems)
+{
+    constexpr int V = LANES;                         // vectors (rows of 128 floats) per lane and warp step
+    constexpr int BPR = 32 / LANES;                  // blocks per row
+    constexpr int kWarps = kPackThreads / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t nsteps = (nvec + 32 * V - 1) / (32 * V);
+    const int64_t nblocks = (nvec * 4) / a.block_size;
+    const int log2_bs = 31 - __clz(a.block_size);
+    const LaneConsts k(elem_codec);
+    const bool reverse = elem_codec.reverse != 0;
+    const bool e8m0_like = scale_codec.mant == 0 && !scale_codec.to_signed;
+    for (int64_t step = (int64_t)blockIdx.x * kWarps + warp; step < nsteps; step += (int64_t)gridDim.x * kWarps) {
+        const int64_t v0 = step * (32 * V) + lane;
+        float4 x[V];
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            const int64_t v = v0 + u * 32;
+            x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (v < nvec) x[u] = __ldcs(in + v);
+        }
+        float mine = 0.0f;
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            float m = fmaxf(fmaxf(fabsf(x[u].x), fabsf(x[u].y)), fmaxf(fabsf(x[u].z), fabsf(x[u].w)));
+#pragma unroll
+            for (int o = LANES / 2; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+            const float t = __shfl_sync(0xFFFFFFFFu, m, (lane % BPR) * LANES);
+            if (lane / BPR == u) mine = t;
+        }
+        const int64_t gblock_local = step * 32 + lane;
+        const uint64_t gblock = (first_index >> log2_bs) + (uint64_t)gblock_local;
+        const float scale = mx_scale_quick(mine, a, sq, rng_scale, gblock);
+        const uint32_t sb = __float_as_uint(scale);
+        const bool pow2 = (sb & 0x807FFFFFu) == 0u && (sb - 0x00800000u) < 0x7E800000u;
+        // what the consumers multiply by: exact 2^-k for a normal power-of-two scale, 0 for a dead block (scale <= 0 or NaN: codes 0),
+        // NaN = "divide by the scale" (never for E8M0-like scale formats)
+        const float recip = pow2 ? __uint_as_float(0x7F000000u - sb) : (scale > 0.0f ? __uint_as_float(0x7FC00000u) : 0.0f);
+        if (gblock_local < nblocks) {
+            const int code = (int)(sb >> 23) + scale_codec.exp_offset;
+            uint32_t byte;
+            if (e8m0_like && pow2 && (sb >> 23) <= 254u && code >= 1 && code <= (int)scale_codec.max_finite_rep)
+                byte = (uint32_t)code;
+            else
+                byte = float_to_rep<LOF_RoundTowardsZero>(sb, scale_codec, 0u);
+            scales[gblock_local] = (uint8_t)byte;
+        }
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            const int owner = u * BPR + lane / LANES;
+            const float rc = __shfl_sync(0xFFFFFFFFu, recip, owner), sc = __shfl_sync(0xFFFFFFFFu, scale, owner);
+            const int64_t v = v0 + u * 32;
+            float y[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+            if (rc != rc) {                                                  // non-power-of-two scale: the reference's division
+#pragma unroll
+                for (int e = 0; e < 4; ++e) y[e] = __fdiv_rn(y[e], sc);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) y[e] = __fmul_rn(y[e], rc);
+            }
+            uint32_t m[4], s[4], emax = 0u;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) m[e] = lane_mag<MODE, SGN>(__float_as_uint(y[e]), k, emax, s[e]);
+            if (emax >= kLaneRare) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const uint2 r = lane_mag_rare<MODE>(__float_as_uint(y[e]), elem_codec); m[e] = r.x; s[e] = r.y; }
+            }
+            if (rc == 0.0f) {                                                // dead block: all-zero codes (also drops the signs)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { m[e] = 0u; s[e] = 0u; }
+            }
+            if constexpr (N == 8) {
+                if (v < nvec) __stcs(reinterpret_cast<uint32_t*>(elems) + v, pack8<SGN>(m, s));
+            } else if constexpr (N == 4) {
+                if (v < nvec) __stcs(reinterpret_cast<uint16_t*>(elems) + v, (uint16_t)pack4<SGN>(m, s, reverse));
+            } else {
+                const int r = lane & 3;
+                const uint32_t w = word6(pack6<SGN>(m, s, reverse), r);     // nvec % 4 == 0 (block sizes >= 16): groups of 4 lanes are whole
+                if (r != 3 && v < nvec) __stcs(reinterpret_cast<uint32_t*>(elems) + (v >> 2) * 3 + r, w);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kPackThreads)
 mx_decode_kernel(const uint8_t* __restrict__ scales, const uint8_t* __restrict__ elems, float4* __restrict__ out, int64_t nvec,
                  int block_size, CodecPlan scale_codec, CodecPlan elem_codec)
@@ -678,7 +1012,32 @@ cudaError_t launch_encode(int mode, const float* src, uint8_t* dst, int64_t coun
 {
     const int vec_ok = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
     const int word_ok = (reinterpret_cast<uintptr_t>(dst) & 3u) == 0;
-    const unsigned grid = pack_grid(count, num_sms);
+    unsigned grid = pack_grid(count, num_sms);
+    const int fast_mode = mode == LOF_RoundToNearestEven || mode == LOF_RoundTowardsZero || mode == LOF_RoundAwayFromZero || mode == LOF_RoundToOdd;
+    if (p.fast_ok && p.lanes && fast_mode && (p.n == 8 || p.n == 16 || p.n == 4 || p.n == 6) && vec_ok &&
+        (reinterpret_cast<uintptr_t>(dst) & 7u) == 0 && count >= kPackTile) {
+        // whole tiles on the register-lane kernel, the remainder (< 4096 elements) on encode_kernel below
+        const int64_t ntiles = count / kPackTile;
+        const unsigned lgrid = pack_grid(ntiles * kPackTile, num_sms);
+        const uint4* vsrc = reinterpret_cast<const uint4*>(src);
+        const int sgn = !p.to_signed ? 0 : (p.sign_is_nan ? 2 : 1);
+#define LOF_LANE3(M, N, S) encode_lane_kernel<M, N, S><<<lgrid, kPackThreads, 0, stream>>>(vsrc, dst, ntiles, p)
+#define LOF_LANE2(M, N) do { if (sgn == 0) LOF_LANE3(M, N, 0); else if (sgn == 1) LOF_LANE3(M, N, 1); else LOF_LANE3(M, N, 2); } while (0)
+#define LOF_LANE(M) case M: if (p.n == 8) LOF_LANE2(M, 8); else if (p.n == 16) LOF_LANE2(M, 16); else if (p.n == 4) LOF_LANE2(M, 4); else LOF_LANE2(M, 6); break;
+        switch (mode) {
+            LOF_LANE(LOF_RoundToNearestEven) LOF_LANE(LOF_RoundTowardsZero) LOF_LANE(LOF_RoundAwayFromZero) LOF_LANE(LOF_RoundToOdd)
+        default: break;
+        }
+#undef LOF_LANE
+#undef LOF_LANE2
+#undef LOF_LANE3
+        cudaError_t e = cudaGetLastError();
+        const int64_t done = ntiles * kPackTile;
+        if (e != cudaSuccess || done == count) return e;
+        const uint64_t done_bytes = (uint64_t)done / 8u * (uint64_t)p.n;
+        src += done; dst += done_bytes; count -= done; packed_bytes -= done_bytes; first_index += (uint64_t)done;
+        grid = pack_grid(count, num_sms);
+    }
     if (p.fast_ok) {
         switch (mode) {
 #define LOF_CASE(M) case M: encode_kernel<M, true><<<grid, kPackThreads, 0, stream>>>(src, dst, count, packed_bytes, p, rng, first_index, vec_ok, word_ok); return cudaGetLastError();
@@ -748,6 +1107,21 @@ cudaError_t launch_mx_encode(int mode, const float* in, int64_t n, const MxArgs&
         const int64_t nsteps = (nvec + 32 * lanes - 1) / (32 * lanes);
         const int64_t want2 = (nsteps + kWarps - 1) / kWarps;
         const unsigned grid2 = (unsigned)(want2 < 1 ? 1 : want2 < cap ? want2 : cap);
+        if (elem_codec.lanes && elem_codec.to_signed && (elem_codec.n == 8 || elem_codec.n == 4 || elem_codec.n == 6)) {
+            const bool nz = elem_codec.sign_is_nan != 0;         // P3109-style element formats: no -0
+#define LOF_MXL4(M, L, N, S) mx_encode_lane_kernel<M, L, N, S><<<grid2, kPackThreads, 0, stream>>>(vin, nvec, a, sq, scale_codec, elem_codec, rng_scale, first_index, scales, elems)
+#define LOF_MXL3(M, L, N) do { if (nz) LOF_MXL4(M, L, N, 2); else LOF_MXL4(M, L, N, 1); } while (0)
+#define LOF_MXL2(M, L) do { if (elem_codec.n == 8) LOF_MXL3(M, L, 8); else if (elem_codec.n == 4) LOF_MXL3(M, L, 4); else LOF_MXL3(M, L, 6); } while (0)
+#define LOF_MXL(M) case M: if (lanes == 4) LOF_MXL2(M, 4); else if (lanes == 8) LOF_MXL2(M, 8); else LOF_MXL2(M, 16); return cudaGetLastError();
+            switch (mode) {
+                LOF_MXL(LOF_RoundToNearestEven) LOF_MXL(LOF_RoundTowardsZero) LOF_MXL(LOF_RoundAwayFromZero) LOF_MXL(LOF_RoundToOdd)
+            default: break;
+            }
+#undef LOF_MXL
+#undef LOF_MXL2
+#undef LOF_MXL3
+#undef LOF_MXL4
+        }
 #define LOF_CASE2(M, L) mx_encode_fast_kernel<M, L><<<grid2, kPackThreads, 0, stream>>>(vin, nvec, a, sq, scale_codec, elem_codec, rng_scale, first_index, scales, elems)
 #define LOF_CASE(M) case M: if (lanes == 4) LOF_CASE2(M, 4); else if (lanes == 8) LOF_CASE2(M, 8); else LOF_CASE2(M, 16); return cudaGetLastError();
         switch (mode) {
@@ -794,6 +1168,24 @@ cudaError_t launch_decode(const uint8_t* src, float* dst, int64_t count, uint64_
 {
     const int vec_ok = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
     const int word_ok = (reinterpret_cast<uintptr_t>(src) & 3u) == 0;
+    if (p.lanes && p.dec_ok && (p.n == 8 || p.n == 16 || p.n == 4 || p.n == 6) && vec_ok && (reinterpret_cast<uintptr_t>(src) & 7u) == 0 &&
+        count >= kPackTile) {
+        // whole tiles on the register-lane kernel, the remainder (< 4096 elements) on decode_kernel below
+        const int64_t ntiles = count / kPackTile;
+        const unsigned lgrid = pack_grid(ntiles * kPackTile, num_sms);
+        float4* vdst = reinterpret_cast<float4*>(dst);
+        const int sgn = !p.to_signed ? 0 : (p.sign_is_nan ? 2 : 1);
+#define LOF_LANE3(N, S) decode_lane_kernel<N, S><<<lgrid, kPackThreads, 0, stream>>>(src, vdst, ntiles, p)
+#define LOF_LANE2(N) do { if (sgn == 0) LOF_LANE3(N, 0); else if (sgn == 1) LOF_LANE3(N, 1); else LOF_LANE3(N, 2); } while (0)
+        if (p.n == 8) LOF_LANE2(8); else if (p.n == 16) LOF_LANE2(16); else if (p.n == 4) LOF_LANE2(4); else LOF_LANE2(6);
+#undef LOF_LANE2
+#undef LOF_LANE3
+        cudaError_t e = cudaGetLastError();
+        const int64_t done = ntiles * kPackTile;
+        if (e != cudaSuccess || done == count) return e;
+        const uint64_t done_bytes = (uint64_t)done / 8u * (uint64_t)p.n;
+        src += done_bytes; dst += done; count -= done; packed_bytes -= done_bytes;
+    }
     decode_kernel<<<pack_grid(count, num_sms), kPackThreads, 0, stream>>>(src, dst, count, packed_bytes, p, vec_ok, word_ok);
     return cudaGetLastError();
 }

@@ -35,6 +35,8 @@ struct CodecPlan {
     uint32_t fast_ok;
     uint32_t f_cadd, f_cfloor;      // (23 - m) << 23, (emin_biased + 23 - m) << 23
     uint32_t f_big;                 // |x| bits >= f_big: certain overflow, infinity or NaN
+    uint32_t dec_ok, d_special;     // arithmetic decode eligible; every infinity / NaN code has magnitude >= d_special (or is the sign-bit-only pattern)
+    uint32_t lanes;                 // pack.fast = 2: register-lane kernels (bit width / sign policy as template parameters) where eligible
 };
 
 cudaError_t launch_encode(int mode, const float* src, uint8_t* dst, int64_t count, uint64_t packed_bytes, const CodecPlan& p,

@@ -8,6 +8,9 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import lofloat_b200 as lof  # noqa: E402
 from lofloat_b200 import formats  # noqa: E402
 
+import os  # noqa: E402
+
+lof.set_option("pack.fast", int(os.environ.get("LOF_PACK_FAST", "2")))     # 2 = register-lane kernels (default), 1 = second-generation kernels
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev).manual_seed(7)
 x = torch.randn(16384, 16384, device=dev, generator=g) * torch.exp2(torch.randint(-8, 9, (16384, 1), device=dev, generator=g).float())

@@ -7,6 +7,9 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import lofloat_b200 as lof  # noqa: E402
 
+import os  # noqa: E402
+
+lof.set_option("pack.fast", int(os.environ.get("LOF_PACK_FAST", "2")))     # 2 = register-lane kernels (default), 1 = second-generation kernels
 dev = torch.device("cuda:0")
 n = 1 << 28
 g = torch.Generator(device=dev).manual_seed(1)

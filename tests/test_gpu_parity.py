@@ -779,6 +779,18 @@ def test_pack_codec_bit_exact_all_formats_modes(lof, cuda_dev):
         for endian in (0, 1):
             packed = L.o_pack_reps(reps, n, endian)
             assert L.bits_equal(_abi_decode(cuda_dev, packed, reps.size, f, endian), L.o_rep_to_float(reps, f)), (name, endian)
+        # every representation again over several whole tiles + a ragged tail: the register-lane decode kernels (pack.fast = 2,
+        # 4 / 6 / 8 / 16-bit formats: arithmetic decode, infinity / NaN codes through the rare path) and the table kernel (pack.fast = 1)
+        from lofloat_b200 import _lib as _l
+        many = np.resize(np.roll(reps, 5), 5 * 4096 + 37).astype(np.uint32)
+        try:
+            for gen in (2, 1):
+                _l.set_option("pack.fast", gen)
+                for endian in (0, 1):
+                    packed = L.o_pack_reps(many, n, endian)
+                    assert L.bits_equal(_abi_decode(cuda_dev, packed, many.size, f, endian), L.o_rep_to_float(many, f)), (name, endian, gen)
+        finally:
+            _l.set_option("pack.fast", 2)
         for count in (1, 3, 15, 16, 17, 1001, 4095, 4096, 4097, 3 * 4096 + 5):
             xs_ = np.resize(x, count)
             want = L.o_encode(xs_, f, endian=count & 1)
@@ -853,9 +865,10 @@ def test_gemm_on_packed_operands_equals_fp32_container_path(lof, cuda_dev):
 
 
 def test_pack_fast_path_equals_exact_every_fp32_pattern(lof, cuda_dev):
-    """The magic-add encode path (pack.fast = 1, default) against the exact integer routine (pack.fast = 0, pinned to
-    the oracle / compiled reference above) on EVERY fp32 bit pattern, for every eligible codec format, the four
-    IEEE-like modes and all three saturation modes under RNE.  Compared on the device."""
+    """The magic-add encode paths (pack.fast = 2, default: register-lane kernels for 4 / 6 / 8 / 16-bit formats, the
+    second-generation kernel for the other widths; pack.fast = 1: second-generation kernel everywhere) against the exact
+    integer routine (pack.fast = 0, pinned to the oracle / compiled reference above) on EVERY fp32 bit pattern, for every
+    eligible codec format, the four IEEE-like modes and all three saturation modes under RNE.  Compared on the device."""
     from lofloat_b200 import _lib
     lib = _lib.lib()
     chunk = 1 << 28
@@ -879,17 +892,18 @@ def test_pack_fast_path_equals_exact_every_fp32_pattern(lof, cuda_dev):
                     x = torch.arange(base, base + chunk, device=cuda_dev, dtype=torch.int64).to(torch.int32).view(torch.float32)
                     _lib.set_option("pack.fast", 0)
                     enc(x, f, mode, sat, b)
-                    _lib.set_option("pack.fast", 1)
-                    enc(x, f, mode, sat, a)
-                    if not torch.equal(a, b):
-                        idx = int((a != b).nonzero()[0])
-                        raise AssertionError(f"{name} {L.MODE_NAMES[mode]} sat{sat}: packed byte {idx} of chunk 0x{base:08x} "
-                                             f"fast=0x{int(a[idx]):02x} exact=0x{int(b[idx]):02x}")
+                    for gen in ((2, 1) if (name in ("e4m3fn", "e2m1", "e3m2", "half") and mode == L.RNE and sat == 0) else (2,)):
+                        _lib.set_option("pack.fast", gen)
+                        enc(x, f, mode, sat, a)
+                        if not torch.equal(a, b):
+                            idx = int((a != b).nonzero()[0])
+                            raise AssertionError(f"{name} {L.MODE_NAMES[mode]} sat{sat} pack.fast={gen}: packed byte {idx} of chunk 0x{base:08x} "
+                                                 f"fast=0x{int(a[idx]):02x} exact=0x{int(b[idx]):02x}")
                     checked += chunk
                     del x
             del a, b
     finally:
-        _lib.set_option("pack.fast", 1)
+        _lib.set_option("pack.fast", 2)
     assert checked == 12 * 6 * (1 << 32)
 
 
