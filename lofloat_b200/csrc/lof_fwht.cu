@@ -40,6 +40,18 @@ __device__ __forceinline__ void butterfly(float& a, float& b)
     a = s; b = d;
 }
 
+// generic element path of one lane's four elements (any scale, any element format / mode): out of line, the streaming loop
+// carries one call instead of four inlined copies of the division + exact rounding per row
+template <int MODE>
+__device__ __noinline__ float4 mx_quant_row_generic(float4 v, float scale, const MxArgs& mx, uint4 w)
+{
+    const MxBlockCtx c = mx_make_ctx(scale);
+    float4 o;
+    o.x = mx_quant<MODE>(v.x, c, mx, w.x); o.y = mx_quant<MODE>(v.y, c, mx, w.y);
+    o.z = mx_quant<MODE>(v.z, c, mx, w.z); o.w = mx_quant<MODE>(v.w, c, mx, w.w);
+    return o;
+}
+
 // ROWS = rows (of 128 floats) one warp step holds per lane; a Hadamard block spans max(1, B / 128) of them
 template <int ROWS, int OP, int MODE>
 __global__ void __launch_bounds__(kFwhtThreads)
@@ -70,15 +82,17 @@ fwht_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t nro
         // h = 4 .. 64: across lanes
         for (int s = 0; s < lane_stages; ++s) {
             const int m = 1 << s;
-            const bool upper = (lane & m) != 0;
+            // lower lane: v + p, upper lane: p - v -- one fused multiply-add with sg = +-1 (the product is exact, so the single rounding
+            // is that of the sum / difference: bit-identical to fadd / fsub) instead of two adds and a select per element
+            const float sg = (lane & m) != 0 ? -1.0f : 1.0f;
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) {
                 const float px = __shfl_xor_sync(0xFFFFFFFFu, v[r].x, m), py = __shfl_xor_sync(0xFFFFFFFFu, v[r].y, m);
                 const float pz = __shfl_xor_sync(0xFFFFFFFFu, v[r].z, m), pw = __shfl_xor_sync(0xFFFFFFFFu, v[r].w, m);
-                v[r].x = upper ? __fsub_rn(px, v[r].x) : __fadd_rn(v[r].x, px);
-                v[r].y = upper ? __fsub_rn(py, v[r].y) : __fadd_rn(v[r].y, py);
-                v[r].z = upper ? __fsub_rn(pz, v[r].z) : __fadd_rn(v[r].z, pz);
-                v[r].w = upper ? __fsub_rn(pw, v[r].w) : __fadd_rn(v[r].w, pw);
+                v[r].x = __fmaf_rn(v[r].x, sg, px);
+                v[r].y = __fmaf_rn(v[r].y, sg, py);
+                v[r].z = __fmaf_rn(v[r].z, sg, pz);
+                v[r].w = __fmaf_rn(v[r].w, sg, pw);
             }
         }
         // h = 128 ..: across the rows this lane holds (rows of one block are consecutive and aligned: nrows-tail rows are zero)
@@ -155,11 +169,7 @@ fwht_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t nro
                         done = true;
                     }
                 }
-                if (!done) {
-                    const MxBlockCtx c = mx_make_ctx(scale);
-                    o.x = mx_quant<MODE>(v[r].x, c, a.mx, w.x); o.y = mx_quant<MODE>(v[r].y, c, a.mx, w.y);
-                    o.z = mx_quant<MODE>(v[r].z, c, a.mx, w.z); o.w = mx_quant<MODE>(v[r].w, c, a.mx, w.w);
-                }
+                if (!done) o = mx_quant_row_generic<MODE>(v[r], scale, a.mx, w);
                 st_stream_f4(out + (row0 + r) * 32 + lane, o);
             }
         } else {

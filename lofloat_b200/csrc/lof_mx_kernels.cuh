@@ -43,6 +43,12 @@ __device__ __forceinline__ float mx_block_scale(float amax, const MxArgs& a, con
     return __uint_as_float(round_params_elem_rt<LOF_F32>(a.scale_mode, __float_as_uint(ratio), sp, w));
 }
 
+// the generic routine out of line: the cold tail of mx_scale_quick
+static __device__ __noinline__ float mx_block_scale_generic(float amax, const MxArgs& a, const RngArgs& rng_scale, uint64_t gblock)
+{
+    return mx_block_scale(amax, a, rng_scale, gblock);
+}
+
 // virtual_round(amax / pmn, scale format) on the branch-free routines of lof_fast_f32.cuh where they apply (the same
 // selection lof_mx_fast.cu makes; every one of them is proven equal to the exact routine by the exhaustive sweeps),
 // the generic 15-mode routine otherwise
@@ -84,7 +90,7 @@ __device__ __forceinline__ float mx_scale_quick(float amax, const MxArgs& a, con
             if (!rare) return __uint_as_float(rb);
         }
     }
-    return mx_block_scale(amax, a, rng_scale, gblock);
+    return mx_block_scale_generic(amax, a, rng_scale, gblock);
 }
 
 // Per-block constants for the element pass.  x / scale is evaluated as x * (1/scale) when

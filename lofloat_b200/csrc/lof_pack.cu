@@ -686,6 +686,63 @@ round_strict_kernel(const float* __restrict__ src, float* __restrict__ dst, int6
     }
 }
 
+// Register-lane strict rounding: lane_mag (encode) composed with the arithmetic decode of lane_decode, no table, no bit
+// width dependence (nothing is packed).  An overflow code above max_finite_rep (the infinity code under OvfInf) and the
+// negative-input code of unsigned formats decode to launch constants; infinity / NaN inputs redo the thread tile with the
+// second-generation routine.  Whole tiles, 16-byte aligned tensors.
+template <int MODE, int SGN>
+__global__ void __launch_bounds__(kPackThreads)
+round_strict_lane_kernel(const uint4* __restrict__ src, float4* __restrict__ dst, int64_t ntiles, const CodecPlan p)
+{
+    const LaneConsts k(p);
+    const DecConsts dk(p);
+    const uint32_t max_finite = p.max_finite_rep;
+    const float ovf_value = fabsf(rep_to_float_rare(p.ovf_rep, p));                   // max finite, or +inf
+    const float neg_value = SGN == 0 ? rep_to_float_rare(p.neg_unsigned_rep, p) : 0.0f;
+    // codes are <= ovf_rep.  An infinity code above max_finite_rep as ovf_rep is the select below; infinity / NaN codes that some
+    // formats keep inside [0, max_finite_rep] (e4m3fn's 0x7F, the top codes of a saturating e5m2, the second infinity pattern 0x7E of the
+    // unsigned extended P3109 formats) are reachable by rounding: running maximum of the codes, tile redone through the exact decode
+    const uint32_t special = p.d_special > p.max_finite_rep ? 0xFFFFFFFFu : p.d_special;
+    constexpr int VPT = kPackPerThread / 4;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t vbase = tile * (kPackTile / 4) + threadIdx.x;
+        uint4 v[VPT];
+#pragma unroll
+        for (int u = 0; u < VPT; ++u) v[u] = __ldcs(src + vbase + u * kPackThreads);
+        float o[VPT][4];
+        uint32_t emax = 0u, mmax = 0u;
+#pragma unroll
+        for (int u = 0; u < VPT; ++u) {
+            const uint32_t x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                uint32_t sx;
+                // unsigned targets: the magnitude path on |x|, negative inputs replaced by their constant below
+                const uint32_t mag = lane_mag<MODE, SGN == 0 ? 1 : SGN>(x[e], k, emax, sx);
+                mmax = max(mmax, mag);
+                float f = __fmul_rn(__uint_as_float(mag << dk.ds), dk.k);
+                f = mag > max_finite ? ovf_value : f;
+                if constexpr (SGN == 0) f = (int32_t)x[e] < 0 ? neg_value : f;
+                else f = __uint_as_float(__float_as_uint(f) | (sx & 0x80000000u));
+                o[u][e] = f;
+            }
+        }
+        if (emax >= kLaneRare || mmax >= special) {           // an infinity / NaN input, or a NaN code, among the thread's 16 elements: rare
+#pragma unroll
+            for (int u = 0; u < VPT; ++u) {
+                const uint32_t x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint2 r = lane_mag_rare<MODE>(x[e], p);
+                    o[u][e] = rep_to_float_rare(r.x | (r.y ? p.signmask : 0u), p);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < VPT; ++u) __stcs(dst + vbase + u * kPackThreads, make_float4(o[u][0], o[u][1], o[u][2], o[u][3]));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // MX quantisation with MATERIALISED scales: virtual_mx_round's block / amax / scale / element rounding
 // (lo_float.h:4311-4383, same device routines as lof_mx_kernels.cuh) composed with the codec above:
@@ -1064,7 +1121,29 @@ cudaError_t launch_round_strict(int mode, const float* src, float* dst, int64_t 
                                 uint64_t first_index, int num_sms, cudaStream_t stream)
 {
     const int vec_ok = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
-    const unsigned grid = pack_grid(count, num_sms);
+    unsigned grid = pack_grid(count, num_sms);
+    const int fast_mode = mode == LOF_RoundToNearestEven || mode == LOF_RoundTowardsZero || mode == LOF_RoundAwayFromZero || mode == LOF_RoundToOdd;
+    if (p.fast_ok && p.lanes && p.dec_ok && fast_mode && vec_ok && count >= kPackTile) {
+        // whole tiles on the register-lane kernel, the remainder (< 4096 elements) on round_strict_kernel below
+        const int64_t ntiles = count / kPackTile;
+        const unsigned lgrid = pack_grid(ntiles * kPackTile, num_sms);
+        const uint4* vsrc = reinterpret_cast<const uint4*>(src);
+        float4* vdst = reinterpret_cast<float4*>(dst);
+        const int sgn = !p.to_signed ? 0 : (p.sign_is_nan ? 2 : 1);
+#define LOF_LANE2(M, S) round_strict_lane_kernel<M, S><<<lgrid, kPackThreads, 0, stream>>>(vsrc, vdst, ntiles, p)
+#define LOF_LANE(M) case M: if (sgn == 0) LOF_LANE2(M, 0); else if (sgn == 1) LOF_LANE2(M, 1); else LOF_LANE2(M, 2); break;
+        switch (mode) {
+            LOF_LANE(LOF_RoundToNearestEven) LOF_LANE(LOF_RoundTowardsZero) LOF_LANE(LOF_RoundAwayFromZero) LOF_LANE(LOF_RoundToOdd)
+        default: break;
+        }
+#undef LOF_LANE
+#undef LOF_LANE2
+        cudaError_t e = cudaGetLastError();
+        const int64_t done = ntiles * kPackTile;
+        if (e != cudaSuccess || done == count) return e;
+        src += done; dst += done; count -= done; first_index += (uint64_t)done;
+        grid = pack_grid(count, num_sms);
+    }
     if (p.fast_ok) {
         switch (mode) {
 #define LOF_CASE(M) case M: round_strict_kernel<M, true><<<grid, kPackThreads, 0, stream>>>(src, dst, count, p, rng, first_index, vec_ok); return cudaGetLastError();

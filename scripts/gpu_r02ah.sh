@@ -1,0 +1,6 @@
+#!/usr/bin/env bash
+set -u
+OUT=gpurun_out/r02ah; mkdir -p $OUT
+(time timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -x -q --durations=6 -k "strict or ste_backward or hadamard") > $OUT/pytest_sel.log 2>&1; echo "pytest exit $?"; tail -8 $OUT/pytest_sel.log | cut -c1-300
+timeout 300 python scripts/strict_perf.py 2>&1 | grep -v Warning | tee $OUT/strict_perf.txt
+timeout 300 python scripts/fwht_perf.py 2>&1 | grep -v Warning | tee $OUT/fwht_perf.txt

@@ -907,6 +907,45 @@ def test_pack_fast_path_equals_exact_every_fp32_pattern(lof, cuda_dev):
     assert checked == 12 * 6 * (1 << 32)
 
 
+def test_strict_lane_kernel_equals_exact_every_fp32_pattern(lof, cuda_dev):
+    """lof_round_strict_f32 on the register-lane kernel (pack.fast = 2: magic-add encode + arithmetic decode, overflow / negative
+    codes as launch constants) against the exact integer routine + table decode (pack.fast = 0, pinned to the oracle in
+    test_strict_typed_rounding_op) on EVERY fp32 bit pattern: signed / unsigned / no -0 formats, with and without infinities,
+    widths 4 .. 16, the four IEEE-like modes, all saturation modes under RNE.  Compared on the device, NaN == NaN by bit pattern."""
+    from lofloat_b200 import _lib
+    lib = _lib.lib()
+    chunk = 1 << 28
+    stream = torch.cuda.current_stream().cuda_stream
+    a = torch.empty(chunk, dtype=torch.float32, device=cuda_dev)
+    b = torch.empty(chunk, dtype=torch.float32, device=cuda_dev)
+
+    def strict(x, f, mode, sat, out):
+        ps, rng = _lib.CProjSpec(mode, sat, 0), _lib.CRng(0, 0)
+        st = lib.lof_round_strict_f32(x.data_ptr(), out.data_ptr(), x.numel(), C.cast(C.byref(f), C.POINTER(_lib.CCodecFormat)),
+                                      C.byref(ps), C.byref(rng), 0, stream)
+        assert st == 0, lib.lof_last_error_string().decode()
+    checked = 0
+    try:
+        for name in ("e2m1", "e3m2", "p3109_5p2", "e5m2", "e4m3fn", "p3109_8p4", "p3109_8p4_ext", "p3109_8p3_unsigned",
+                     "p3109_8p3_unsigned_ext_nan", "p3109_11p5", "half"):
+            f = L.CODEC_FORMATS[name]
+            for mode, sat in ((L.RNE, 0), (L.RNE, 1), (L.RNE, 2), (L.RTZ, 0), (L.RAZ, 0), (L.RTO, 0)):
+                for base in range(0, 1 << 32, chunk):
+                    x = torch.arange(base, base + chunk, device=cuda_dev, dtype=torch.int64).to(torch.int32).view(torch.float32)
+                    _lib.set_option("pack.fast", 0)
+                    strict(x, f, mode, sat, b)
+                    _lib.set_option("pack.fast", 2)
+                    strict(x, f, mode, sat, a)
+                    if not torch.equal(a.view(torch.int32), b.view(torch.int32)):
+                        idx = int((a.view(torch.int32) != b.view(torch.int32)).nonzero()[0])
+                        raise AssertionError(f"{name} {L.MODE_NAMES[mode]} sat{sat}: x bits 0x{base + idx:08x} lanes={float(a[idx])!r} exact={float(b[idx])!r}")
+                    checked += chunk
+                    del x
+    finally:
+        _lib.set_option("pack.fast", 2)
+    assert checked == 11 * 6 * (1 << 32)
+
+
 def test_strict_typed_rounding_op(lof, cuda_dev):
     """Row f-2: lof_round_strict_f32 == decode(encode(x)) of the oracle codec (pinned to the compiled reference's lo_pack.hpp,
     itself validated against Templated_Float<Fp> by test/test_pack.cpp) for every codec format x deterministic mode x
