@@ -487,15 +487,28 @@ def virtual_round_strict(input: torch.Tensor, params: FloatFormatDescriptor, rou
 
 
 def lof_gemm_batched(A: torch.Tensor, B: torch.Tensor, accum_mant_bits: int, round_mode=RoundingMode.RoundToNearestEven,
-                     stochastic_rounding_bits: int = 0, scale_a: float = 1.0, scale_b: float = 1.0, *, kc=None, rng=None) -> torch.Tensor:
+                     stochastic_rounding_bits: int = 0, scale_a: float = 1.0, scale_b: float = 1.0, *, kc=None, rng=None,
+                     k_chunk=None, **tensor_core_kwargs) -> torch.Tensor:
     """(..., M, K) x (..., K, N) -> (..., M, N) with LoFloat accumulation, the `_lof_gemm_2d` of LoFloat/layers.py:121-150,
-    as ONE launch over the flattened batch instead of a Python loop; every slice equals lof_gemm on that slice."""
+    as ONE launch over the flattened batch instead of a Python loop; every slice equals lof_gemm on that slice.
+    With `k_chunk` (or after set_gemm_tensor_core()) every slice runs the tensor-core chunked mode of lof_gemm (same keyword
+    arguments: accum_format, operand_dtype, partial_round, check, ...): one launch per slice, written into one result tensor."""
     if A.dim() < 2 or B.dim() < 2 or A.shape[:-2] != B.shape[:-2] or A.shape[-1] != B.shape[-2]:
         raise RuntimeError(f"lof_gemm_batched: incompatible shapes {tuple(A.shape)} x {tuple(B.shape)}")
     if A.dtype != torch.float32 or B.dtype != torch.float32:
         raise RuntimeError("LoF_gemm: only float32 inputs are supported")
     if not (A.is_cuda and B.is_cuda):
         raise RuntimeError("LoF_gemm requires CUDA tensors")
+    if k_chunk is not None or (kc is None and _gemm_tc is not None):
+        M, K, N = A.shape[-2], A.shape[-1], B.shape[-1]
+        A_f, B_f = A.reshape(-1, M, K), B.reshape(-1, K, N)
+        out = torch.empty((A_f.shape[0], M, N), dtype=torch.float32, device=A.device)
+        for b in range(A_f.shape[0]):
+            out[b] = lof_gemm(A_f[b], B_f[b], accum_mant_bits, round_mode, stochastic_rounding_bits, scale_a, scale_b, k_chunk=k_chunk,
+                              rng=rng, **tensor_core_kwargs)
+        return out.reshape(*A.shape[:-2], M, N)
+    if tensor_core_kwargs:
+        raise TypeError(f"lof_gemm_batched: {sorted(tensor_core_kwargs)} need k_chunk (tensor-core chunked mode)")
     L = _lib.lib()
     mode = RoundingMode(int(round_mode))
     ps = CProjSpec(int(mode), 0, int(stochastic_rounding_bits))

@@ -1245,6 +1245,19 @@ def test_batched_gemm_equals_per_slice_calls(lof, cuda_dev):
             assert torch.equal(got, want), (bh, M, K, N, mant)
     A0, B0 = _np(A.reshape(-1, M, K)[3]), _np(B.reshape(-1, K, N)[3])
     assert L.bits_equal(_np(lof.lof_gemm_batched(A, B, 10).reshape(-1, M, N)[3]), L.o_gemm(A0, B0, 10, L.RNE, kc=256))
+    # tensor-core chunked mode per slice (k_chunk keyword, or the global opt-in the reference's positional call sites use)
+    Aq = _gpu(_e4m3_uniform((3, 2, 128, 256), 31), cuda_dev)
+    Bq = _gpu(_e4m3_uniform((3, 2, 256, 160), 32), cuda_dev)
+    want = torch.stack([lof.lof_gemm(Aq.reshape(-1, 128, 256)[i], Bq.reshape(-1, 256, 160)[i], 7, k_chunk=32, partial_round=True)
+                        for i in range(6)]).reshape(3, 2, 128, 160)
+    assert torch.equal(lof.lof_gemm_batched(Aq, Bq, 7, k_chunk=32, partial_round=True), want)
+    lof.set_gemm_tensor_core(32, partial_round=True)
+    try:
+        assert torch.equal(lof.lof_gemm_batched(Aq, Bq, 7), want)
+    finally:
+        lof.set_gemm_tensor_core(None)
+    with pytest.raises(TypeError):
+        lof.lof_gemm_batched(Aq, Bq, 7, partial_round=True)
 
 
 def test_conv2d_implicit_gemm_and_fused_linear(lof, cuda_dev):
