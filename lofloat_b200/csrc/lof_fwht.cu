@@ -53,8 +53,10 @@ __device__ __noinline__ float4 mx_quant_row_generic(float4 v, float scale, const
 }
 
 // ROWS = rows (of 128 floats) one warp step holds per lane; a Hadamard block spans max(1, B / 128) of them
-template <int ROWS, int OP, int MODE>
-__global__ void __launch_bounds__(kFwhtThreads)
+// LG = log2(lanes per MX block) as a compile-time constant (3: the OCP block of 32 elements), -1 = taken from the arguments
+// FULL = the Hadamard block spans at least one row (log2_b >= 7): all two in-lane and five cross-lane stages, unrolled
+template <int ROWS, int OP, int MODE, int LG, bool FULL>
+__global__ void __launch_bounds__(kFwhtThreads, ROWS == 4 ? 4 : 2)
 fwht_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t nrows, FwhtArgs a, RngArgs rng, RngArgs rng_scale,
             uint64_t first_index)
 {
@@ -62,7 +64,7 @@ fwht_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t nro
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int64_t nsteps = (nrows + ROWS - 1) / ROWS;
-    const int lane_stages = min(a.log2_b, 7) - 2;            // shuffle stages h = 4 .. min(B, 128) / 2
+    const int lane_stages = FULL ? 5 : min(a.log2_b, 7) - 2; // shuffle stages h = 4 .. min(B, 128) / 2
     const int row_stages = max(a.log2_b - 7, 0);             // register stages across rows, h = 128 ..
 
     for (int64_t step = (int64_t)blockIdx.x * kWarps + warp; step < nsteps; step += (int64_t)gridDim.x * kWarps) {
@@ -76,14 +78,12 @@ fwht_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t nro
         // h = 1, 2: inside the lane's four elements
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) {
-            if (a.log2_b >= 1) { butterfly(v[r].x, v[r].y); butterfly(v[r].z, v[r].w); }
-            if (a.log2_b >= 2) { butterfly(v[r].x, v[r].z); butterfly(v[r].y, v[r].w); }
+            if (FULL || a.log2_b >= 1) { butterfly(v[r].x, v[r].y); butterfly(v[r].z, v[r].w); }
+            if (FULL || a.log2_b >= 2) { butterfly(v[r].x, v[r].z); butterfly(v[r].y, v[r].w); }
         }
-        // h = 4 .. 64: across lanes
-        for (int s = 0; s < lane_stages; ++s) {
-            const int m = 1 << s;
-            // lower lane: v + p, upper lane: p - v -- one fused multiply-add with sg = +-1 (the product is exact, so the single rounding
-            // is that of the sum / difference: bit-identical to fadd / fsub) instead of two adds and a select per element
+        // h = 4 .. 64: across lanes.  lower lane: v + p, upper lane: p - v -- one fused multiply-add with sg = +-1 (the product is exact, so
+        // the single rounding is that of the sum / difference: bit-identical to fadd / fsub) instead of two adds and a select per element
+        auto lane_stage = [&](int m) {
             const float sg = (lane & m) != 0 ? -1.0f : 1.0f;
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) {
@@ -94,6 +94,11 @@ fwht_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t nro
                 v[r].z = __fmaf_rn(v[r].z, sg, pz);
                 v[r].w = __fmaf_rn(v[r].w, sg, pw);
             }
+        };
+        if constexpr (FULL) {
+            lane_stage(1); lane_stage(2); lane_stage(4); lane_stage(8); lane_stage(16);
+        } else {
+            for (int s = 0; s < lane_stages; ++s) lane_stage(1 << s);
         }
         // h = 128 ..: across the rows this lane holds (rows of one block are consecutive and aligned: nrows-tail rows are zero)
 #pragma unroll
@@ -115,32 +120,39 @@ fwht_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t nro
             v[r].z = __fmul_rn(v[r].z, a.inv_sqrt_b); v[r].w = __fmul_rn(v[r].w, a.inv_sqrt_b);
         }
         if constexpr (OP == kFwhtMx) {
-            const int group = a.mx.block_size >> 2;               // lanes per MX block (4 .. 32)
             const int log2_mx = 31 - __clz(a.mx.block_size);
+            const int log2_group = LG >= 0 ? LG : log2_mx - 2;        // lanes per MX block: 4 .. 32, a power of two
+            const int group = 1 << log2_group;
             float m[ROWS];
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) {
                 float t = amax4(v[r]);
-                for (int off = group >> 1; off > 0; off >>= 1) t = fmaxf(t, __shfl_xor_sync(0xFFFFFFFFu, t, off));
+                if constexpr (LG >= 0) {
+#pragma unroll
+                    for (int off = (1 << LG) >> 1; off > 0; off >>= 1) t = fmaxf(t, __shfl_xor_sync(0xFFFFFFFFu, t, off));
+                } else {
+                    for (int off = group >> 1; off > 0; off >>= 1) t = fmaxf(t, __shfl_xor_sync(0xFFFFFFFFu, t, off));
+                }
                 m[r] = t;
             }
             // scales: the ROWS * (32 / group) block maxima are transposed onto the lanes so that every lane rounds ONE scale
             // (no divergent per-block path); when that is more than 32 blocks the first lane of each block does it
-            const int bpr = 32 / group;                               // blocks per row
+            const int log2_bpr = 5 - log2_group, bpr = 1 << log2_bpr;    // blocks per row
             const bool transposed = ROWS * bpr <= 32;
             float scales_r[ROWS];
             if (transposed) {
                 float mine = 0.0f;
+                const int src_lane = (lane & (bpr - 1)) << log2_group, my_row = lane >> log2_bpr, blk_in_row = lane >> log2_group;
 #pragma unroll
                 for (int r = 0; r < ROWS; ++r) {
-                    const float t = __shfl_sync(0xFFFFFFFFu, m[r], (lane % bpr) * group);
-                    if (lane / bpr == r) mine = t;
+                    const float t = __shfl_sync(0xFFFFFFFFu, m[r], src_lane);
+                    if (my_row == r) mine = t;
                 }
                 const uint64_t gb0 = (first_index + (uint64_t)row0 * 128u) >> log2_mx;
                 float sc = 0.0f;
                 if (lane < ROWS * bpr) sc = mx_scale_quick(mine, a.mx, a.sq, rng_scale, gb0 + (uint64_t)lane);
 #pragma unroll
-                for (int r = 0; r < ROWS; ++r) scales_r[r] = __shfl_sync(0xFFFFFFFFu, sc, r * bpr + lane / group);
+                for (int r = 0; r < ROWS; ++r) scales_r[r] = __shfl_sync(0xFFFFFFFFu, sc, (r << log2_bpr) + blk_in_row);
             } else {
 #pragma unroll
                 for (int r = 0; r < ROWS; ++r) {
@@ -208,9 +220,17 @@ cudaError_t launch_rows(int rows_per_block, const float* in, float* out, int64_t
         const int64_t want = (nsteps + kWarps - 1) / kWarps, cap = (int64_t)num_sms /* = SMs x resident CTAs per SM, chosen by the caller */;
         return (unsigned)(want < 1 ? 1 : want < cap ? want : cap);
     };
+    if constexpr (OP == kFwhtMx) {
+        if (a.mx.block_size == 32) {                              // the OCP MX block: lanes per block as a compile-time constant
+            if (rows_per_block == 8) fwht_kernel<8, OP, MODE, 3, true><<<grid_for(8), kFwhtThreads, 0, stream>>>(vin, vout, nrows, a, rng, rng_scale, first_index);
+            else if (a.log2_b >= 7) fwht_kernel<4, OP, MODE, 3, true><<<grid_for(4), kFwhtThreads, 0, stream>>>(vin, vout, nrows, a, rng, rng_scale, first_index);
+            else fwht_kernel<4, OP, MODE, 3, false><<<grid_for(4), kFwhtThreads, 0, stream>>>(vin, vout, nrows, a, rng, rng_scale, first_index);
+            return cudaGetLastError();
+        }
+    }
     switch (rows_per_block) {
-    case 8: fwht_kernel<8, OP, MODE><<<grid_for(8), kFwhtThreads, 0, stream>>>(vin, vout, nrows, a, rng, rng_scale, first_index); break;
-    default: fwht_kernel<4, OP, MODE><<<grid_for(4), kFwhtThreads, 0, stream>>>(vin, vout, nrows, a, rng, rng_scale, first_index); break;   // B <= 512
+    case 8: fwht_kernel<8, OP, MODE, -1, false><<<grid_for(8), kFwhtThreads, 0, stream>>>(vin, vout, nrows, a, rng, rng_scale, first_index); break;
+    default: fwht_kernel<4, OP, MODE, -1, false><<<grid_for(4), kFwhtThreads, 0, stream>>>(vin, vout, nrows, a, rng, rng_scale, first_index); break;   // B <= 512
     }
     return cudaGetLastError();
 }
