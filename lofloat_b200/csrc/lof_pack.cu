@@ -211,6 +211,17 @@ __device__ __noinline__ uint2 lane_mag_rare(uint32_t x, const CodecPlan& p)     
 }
 
 // four codes of one 16-byte vector -> packed bits.  pack8: one word; pack16: two words; pack4: 16 bits; pack6: 24 bits.
+// SGN = 2 (the sign-bit-only pattern is the NaN: a zero magnitude takes no sign): instead of a compare + select per element the sign
+// mask is cleared on the packed word for every field whose magnitude bits are all zero -- z + ones carries into the field's top bit
+// exactly when z != 0 and never beyond it (z <= ones).  `mags` = the magnitude bits of every field, `signs` = the sign bit of every field.
+template <int SGN>
+__device__ __forceinline__ uint32_t no_minus_zero(uint32_t w, uint32_t mags, uint32_t signs)
+{
+    if constexpr (SGN != 2) return w;
+    const uint32_t z = w & mags;
+    return w & (((z + mags) | z) | ~signs);
+}
+
 template <int SGN>
 __device__ __forceinline__ uint32_t pack8(const uint32_t (&m)[4], const uint32_t (&s)[4])
 {
@@ -219,7 +230,7 @@ __device__ __forceinline__ uint32_t pack8(const uint32_t (&m)[4], const uint32_t
         const uint32_t sg = __byte_perm(__byte_perm(s[0], s[1], 0x0073), __byte_perm(s[2], s[3], 0x0073), 0x5410);
         w |= sg & 0x80808080u;
     }
-    return w;
+    return no_minus_zero<SGN>(w, 0x7F7F7F7Fu, 0x80808080u);
 }
 template <int SGN>
 __device__ __forceinline__ uint2 pack16(const uint32_t (&m)[4], const uint32_t (&s)[4])
@@ -229,6 +240,8 @@ __device__ __forceinline__ uint2 pack16(const uint32_t (&m)[4], const uint32_t (
         w.x |= __byte_perm(s[0], s[1], 0x7632) & 0x80008000u;
         w.y |= __byte_perm(s[2], s[3], 0x7632) & 0x80008000u;
     }
+    w.x = no_minus_zero<SGN>(w.x, 0x7FFF7FFFu, 0x80008000u);
+    w.y = no_minus_zero<SGN>(w.y, 0x7FFF7FFFu, 0x80008000u);
     return w;
 }
 template <int SGN>
@@ -237,7 +250,7 @@ __device__ __forceinline__ uint32_t pack4(const uint32_t (&m)[4], const uint32_t
     uint32_t q[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) q[e] = SGN != 0 ? (m[e] | ((s[e] >> 28) & 8u)) : m[e];
-    uint32_t half = (q[1] * 16u + q[0]) + (q[3] * 16u + q[2]) * 256u;
+    uint32_t half = no_minus_zero<SGN>((q[1] * 16u + q[0]) + (q[3] * 16u + q[2]) * 256u, 0x7777u, 0x8888u);
     if (reverse) half = ((half & 0x0F0Fu) << 4) | ((half >> 4) & 0x0F0Fu);      // slot order inside a byte (launch-uniform)
     return half;
 }
@@ -247,7 +260,8 @@ __device__ __forceinline__ uint32_t pack6(const uint32_t (&m)[4], const uint32_t
     uint32_t q[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) q[e] = SGN != 0 ? (m[e] | ((s[e] >> 26) & 32u)) : m[e];
-    return reverse ? (q[2] * 64u + q[3]) + (q[0] * 64u + q[1]) * 4096u : (q[1] * 64u + q[0]) + (q[3] * 64u + q[2]) * 4096u;
+    const uint32_t chunk = reverse ? (q[2] * 64u + q[3]) + (q[0] * 64u + q[1]) * 4096u : (q[1] * 64u + q[0]) + (q[3] * 64u + q[2]) * 4096u;
+    return no_minus_zero<SGN>(chunk, 0x7DF7DFu, 0x820820u);
 }
 // 6-bit lanes: four consecutive lanes hold the 24-bit chunks c0..c3 of 16 consecutive elements = three words
 // (c0 | c1 << 24, c1 >> 8 | c2 << 16, c2 >> 16 | c3 << 8); lane r = lane & 3 builds word r from its own and the next lane's chunk
@@ -407,9 +421,10 @@ encode_lane_kernel(const uint4* __restrict__ src, uint8_t* __restrict__ dst, int
         for (int u = 0; u < VPT; ++u) {
             const uint32_t x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) m[u][e] = lane_mag<MODE, SGN>(x[e], k, emax, s[u][e]);
+            for (int e = 0; e < 4; ++e) m[u][e] = lane_mag<MODE, SGN == 2 ? 1 : SGN>(x[e], k, emax, s[u][e]);      // SGN = 2: the no -0 rule is applied on the packed word
         }
-        if (emax >= kLaneRare) {                              // an infinity / NaN among the thread's 16 elements: rare
+        const bool rare = emax >= kLaneRare;
+        if (rare) {                                           // an infinity / NaN among the thread's 16 elements: redone exactly (incl. the no -0 rule)
 #pragma unroll
             for (int u = 0; u < VPT; ++u) {
                 const uint32_t x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
@@ -420,15 +435,16 @@ encode_lane_kernel(const uint4* __restrict__ src, uint8_t* __restrict__ dst, int
 #pragma unroll
         for (int u = 0; u < VPT; ++u) {
             const int64_t vi = vbase + u * kPackThreads;
+            constexpr int S1 = SGN == 2 ? 1 : SGN;            // packer of the exactly redone elements (a sign-bit-only NaN code must survive)
             if constexpr (N == 8) {
-                __stcs(reinterpret_cast<uint32_t*>(dst) + vi, pack8<SGN>(m[u], s[u]));
+                __stcs(reinterpret_cast<uint32_t*>(dst) + vi, rare ? pack8<S1>(m[u], s[u]) : pack8<SGN>(m[u], s[u]));
             } else if constexpr (N == 16) {
-                __stcs(reinterpret_cast<uint2*>(dst) + vi, pack16<SGN>(m[u], s[u]));
+                __stcs(reinterpret_cast<uint2*>(dst) + vi, rare ? pack16<S1>(m[u], s[u]) : pack16<SGN>(m[u], s[u]));
             } else if constexpr (N == 4) {
-                __stcs(reinterpret_cast<uint16_t*>(dst) + vi, (uint16_t)pack4<SGN>(m[u], s[u], reverse));
+                __stcs(reinterpret_cast<uint16_t*>(dst) + vi, (uint16_t)(rare ? pack4<S1>(m[u], s[u], reverse) : pack4<SGN>(m[u], s[u], reverse)));
             } else {
                 const int r = (int)threadIdx.x & 3;
-                const uint32_t w = word6(pack6<SGN>(m[u], s[u], reverse), r);
+                const uint32_t w = word6(rare ? pack6<S1>(m[u], s[u], reverse) : pack6<SGN>(m[u], s[u], reverse), r);
                 if (r != 3) __stcs(reinterpret_cast<uint32_t*>(dst) + (vi >> 2) * 3 + r, w);
             }
         }
@@ -1000,8 +1016,10 @@ mx_encode_lane_kernel(const float4* __restrict__ in, int64_t nvec, MxArgs a, MxS
             }
             uint32_t m[4], s[4], emax = 0u;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) m[e] = lane_mag<MODE, SGN>(__float_as_uint(y[e]), k, emax, s[e]);
-            if (emax >= kLaneRare) {
+            for (int e = 0; e < 4; ++e) m[e] = lane_mag<MODE, 1>(__float_as_uint(y[e]), k, emax, s[e]);      // SGN = 2: no -0 on the packed word
+            const bool rare = emax >= kLaneRare;
+            constexpr int S1 = 1;
+            if (rare) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) { const uint2 r = lane_mag_rare<MODE>(__float_as_uint(y[e]), elem_codec); m[e] = r.x; s[e] = r.y; }
             }
@@ -1010,12 +1028,12 @@ mx_encode_lane_kernel(const float4* __restrict__ in, int64_t nvec, MxArgs a, MxS
                 for (int e = 0; e < 4; ++e) { m[e] = 0u; s[e] = 0u; }
             }
             if constexpr (N == 8) {
-                if (v < nvec) __stcs(reinterpret_cast<uint32_t*>(elems) + v, pack8<SGN>(m, s));
+                if (v < nvec) __stcs(reinterpret_cast<uint32_t*>(elems) + v, rare ? pack8<S1>(m, s) : pack8<SGN>(m, s));
             } else if constexpr (N == 4) {
-                if (v < nvec) __stcs(reinterpret_cast<uint16_t*>(elems) + v, (uint16_t)pack4<SGN>(m, s, reverse));
+                if (v < nvec) __stcs(reinterpret_cast<uint16_t*>(elems) + v, (uint16_t)(rare ? pack4<S1>(m, s, reverse) : pack4<SGN>(m, s, reverse)));
             } else {
                 const int r = lane & 3;
-                const uint32_t w = word6(pack6<SGN>(m, s, reverse), r);     // nvec % 4 == 0 (block sizes >= 16): groups of 4 lanes are whole
+                const uint32_t w = word6(rare ? pack6<S1>(m, s, reverse) : pack6<SGN>(m, s, reverse), r);     // nvec % 4 == 0 (block sizes >= 16): groups of 4 lanes are whole
                 if (r != 3 && v < nvec) __stcs(reinterpret_cast<uint32_t*>(elems) + (v >> 2) * 3 + r, w);
             }
         }
