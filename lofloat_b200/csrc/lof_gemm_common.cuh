@@ -25,6 +25,7 @@ struct ExactView {
     int b_kind = 0, k_order = 0, bias_axis = 0;
     const float* bias = nullptr;
     int C = 0, H = 0, W = 0, Cg = 0, R = 0, S = 0, Q = 0, ph = 0, pw = 0, sh = 1, sw = 1, dh = 1, dw = 1, groups = 1;
+    int swap_xy = 0;        // M tiles on grid.x (more than 65535 of them: flattened token dimensions), N tiles on grid.y
 };
 
 // round-to-odd fused multiply-add, bit-identical to the host routine

@@ -87,7 +87,7 @@ gemm_exact_tile(const float* __restrict__ A, const float* __restrict__ B, const 
 
     const int tx = threadIdx.x & 15;     // n direction
     const int ty = threadIdx.x >> 4;     // m direction
-    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+    const int m0 = (v.swap_xy ? blockIdx.x : blockIdx.y) * TM, n0 = (v.swap_xy ? blockIdx.y : blockIdx.x) * TN;
 
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -284,7 +284,7 @@ gemm_exact_body(const float* __restrict__ A, const float* __restrict__ B, float*
     __shared__ float Bs[TK][TN + 4];
     const int tx = threadIdx.x & 15;     // n direction
     const int ty = threadIdx.x >> 4;     // m direction
-    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+    const int m0 = (v.swap_xy ? blockIdx.x : blockIdx.y) * TM, n0 = (v.swap_xy ? blockIdx.y : blockIdx.x) * TN;
 
     float crun[4][4];
     bool redo = true;
@@ -392,12 +392,15 @@ cudaError_t launch_gemm_exact(int mode, const float* A, const float* B, float* C
                               cudaStream_t stream, int64_t batch, int64_t stride_a, int64_t stride_b, int64_t stride_c, const ExactView* view,
                               int fast)
 {
-    const ExactView v = view ? *view : ExactView{};
+    ExactView v = view ? *view : ExactView{};
     if (M <= 0 || N <= 0 || batch <= 0) return cudaSuccess;
     const bool custom = accum_mant_bits >= 0;
     const int r = custom ? 23 - accum_mant_bits : 0;
     int kci = (kc <= 0 || kc > K) ? (int)(K > 0 ? K : 1) : (int)kc;
-    dim3 grid((unsigned)((N + TN - 1) / TN), (unsigned)((M + TM - 1) / TM), (unsigned)batch);
+    const int64_t mt = (M + TM - 1) / TM, nt = (N + TN - 1) / TN;
+    v.swap_xy = mt > 65535;                                   // grid.y / grid.z hold at most 65535 blocks
+    if ((v.swap_xy ? nt : mt) > 65535 || batch > 65535) return cudaErrorInvalidConfiguration;
+    dim3 grid((unsigned)(v.swap_xy ? mt : nt), (unsigned)(v.swap_xy ? nt : mt), (unsigned)batch);
     switch (mode) {
 #define LOF_CASE(Mo) case Mo: exact_kernel_for<Mo>()<<<grid, kGemmThreads, 0, stream>>>(A, B, C, (int)M, (int)N, (int)K, r, len, kci, alpha, beta, custom, fast, rng, stride_a, stride_b, stride_c, v); break;
         LOF_CASE(LOF_RoundToNearestEven) LOF_CASE(LOF_RoundTowardsZero) LOF_CASE(LOF_RoundAwayFromZero)

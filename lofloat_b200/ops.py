@@ -153,6 +153,12 @@ def _next_rng(stochastic: bool, rng) -> CRng:
     return r
 
 
+def _chunk_rng(r: CRng, chunk: int) -> CRng:
+    """Philox stream of the `chunk`-th launch of one logical call that had to be split (grid limits): the event index restarts at 0 in
+    every launch, so the launches differ in the high word of the offset (the global stream only ever advances the low word)."""
+    return r if chunk == 0 else CRng(r.seed, (r.offset + (int(chunk) << 32)) & 0xFFFFFFFFFFFFFFFF)
+
+
 _DTYPES = {torch.float32: _lib.LOF_F32, torch.float16: _lib.LOF_F16, torch.bfloat16: _lib.LOF_BF16,
            torch.float64: _lib.LOF_F64}
 
@@ -523,8 +529,9 @@ def lof_gemm_batched(A: torch.Tensor, B: torch.Tensor, accum_mant_bits: int, rou
     with torch.cuda.device(A.device):
         for b0 in range(0, nb, 65535):                       # grid.z limit
             cnt = min(65535, nb - b0)
+            rc = _chunk_rng(r, b0 // 65535)                  # a later chunk must not replay the event stream of the first
             st = L.lof_gemm_batched_f32(A_f[b0].data_ptr(), B_f[b0].data_ptr(), out[b0].data_ptr(), cnt, M, N, K, M * K, K * N, M * N,
-                                        int(accum_mant_bits), C.byref(ps), int(_gemm_kc if kc is None else kc), alpha, 0.0, C.byref(r),
+                                        int(accum_mant_bits), C.byref(ps), int(_gemm_kc if kc is None else kc), alpha, 0.0, C.byref(rc),
                                         _stream_ptr(A_f))
             _lib.check(st, "LoF_gemm (batched)")
     return out.reshape(*batch_shape, M, N)
@@ -609,8 +616,8 @@ def lof_conv2d(input: torch.Tensor, weight: torch.Tensor, pad_h: int, pad_w: int
             geo = _lib.CConv2d(cnt, C_in, H, W, C_out, R, S, pad_h, pad_w, stride_h, stride_w, dilation_h, dilation_w, groups,
                                _lib.LOF_CONV_K_RSC if k_order == "rsc" else _lib.LOF_CONV_K_CRS)
             st = L.lof_conv2d_f32(x_c[b0].data_ptr(), w_c.data_ptr(), b_c.data_ptr() if b_c is not None else None, out[b0].data_ptr(),
-                                  C.byref(geo), int(accum_mant_bits), C.byref(ps), int(0 if kc is None else kc), alpha, C.byref(r),
-                                  _stream_ptr(x_c))
+                                  C.byref(geo), int(accum_mant_bits), C.byref(ps), int(0 if kc is None else kc), alpha,
+                                  C.byref(_chunk_rng(r, b0 // per_call)), _stream_ptr(x_c))
             _lib.check(st, "LoF_conv2d")
     return out
 

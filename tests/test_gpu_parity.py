@@ -1260,6 +1260,19 @@ def test_batched_gemm_equals_per_slice_calls(lof, cuda_dev):
         lof.lof_gemm_batched(Aq, Bq, 7, partial_round=True)
 
 
+def test_exact_gemm_more_than_65535_row_tiles(lof, cuda_dev):
+    """lof_gemm / lof_linear flatten every leading dimension into M: more than 65535 tiles of 64 rows (4.19 M tokens) put the row
+    tiles on grid.x.  Row blocks of the big product == the same rows computed on their own (deterministic mode)."""
+    M, K, N = 65535 * 64 + 70, 8, 16
+    g = torch.Generator(device=cuda_dev).manual_seed(77)
+    A = torch.rand(M, K, device=cuda_dev, generator=g) * 2 - 1
+    B = torch.rand(K, N, device=cuda_dev, generator=g) * 2 - 1
+    Cb = lof.lof_gemm(A, B, 10)
+    for lo in (0, 2_000_000, M - 135):
+        assert torch.equal(Cb[lo:lo + 135], lof.lof_gemm(A[lo:lo + 135].contiguous(), B, 10)), lo
+    assert L.bits_equal(_np(Cb[M - 70:]), L.o_gemm(_np(A[M - 70:]), _np(B), 10, L.RNE, kc=0))
+
+
 def test_conv2d_implicit_gemm_and_fused_linear(lof, cuda_dev):
     """Row f-3: lof_conv2d (implicit GEMM, no im2col matrix) == F.unfold + one lof_gemm per image and group, which is what
     LoF_Conv2d's im2col backend computes (layers.py:710-745), bit for bit -- strides, dilation, padding, groups, ragged
