@@ -1073,6 +1073,58 @@ mx_decode_kernel(const uint8_t* __restrict__ scales, const uint8_t* __restrict__
     }
 }
 
+// Register-lane MX decode: the tile structure of decode_lane_kernel (four vectors and their scale bytes in flight per thread) with the
+// arithmetic element decode of lane_decode; the scale byte goes through a 256-entry table (one look-up per four elements).  Whole
+// tiles of 4096 elements (launch_mx_decode sends the remainder to mx_decode_kernel), power-of-two block sizes, signed element formats.
+template <int N, int SGN>
+__global__ void __launch_bounds__(kPackThreads)
+mx_decode_lane_kernel(const uint8_t* __restrict__ scales, const uint8_t* __restrict__ elems, float4* __restrict__ out, int64_t ntiles,
+                      int log2_bs, const CodecPlan scale_codec, const CodecPlan elem_codec)
+{
+    __shared__ float lut_s[256];
+    for (int r = threadIdx.x; r < 256; r += kPackThreads) lut_s[r] = rep_to_float_rare((uint32_t)r & scale_codec.rep_mask, scale_codec);
+    __syncthreads();
+    const DecConsts k(elem_codec);
+    const bool reverse = elem_codec.reverse != 0;
+    constexpr int VPT = kPackPerThread / 4;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t vbase = tile * (kPackTile / 4) + threadIdx.x;
+        uint32_t c[VPT], sb[VPT];
+#pragma unroll
+        for (int u = 0; u < VPT; ++u) {
+            const int64_t vi = vbase + u * kPackThreads;
+            if constexpr (N == 8) c[u] = __ldcs(reinterpret_cast<const uint32_t*>(elems) + vi);
+            else if constexpr (N == 4) c[u] = __ldcs(reinterpret_cast<const uint16_t*>(elems) + vi);
+            else {
+                const int r = (int)threadIdx.x & 3;
+                c[u] = r != 3 ? __ldcs(reinterpret_cast<const uint32_t*>(elems) + (vi >> 2) * 3 + r) : 0u;
+            }
+            sb[u] = __ldg(scales + ((vi * 4) >> log2_bs));
+        }
+#pragma unroll
+        for (int u = 0; u < VPT; ++u) {
+            if constexpr (N == 6) {
+                const int lane = (int)threadIdx.x & 31, r = lane & 3, g = lane & ~3;
+                const uint32_t lo = __shfl_sync(0xFFFFFFFFu, c[u], g + max(r - 1, 0)), hi = __shfl_sync(0xFFFFFFFFu, c[u], g + min(r, 2));
+                c[u] = __funnelshift_r(lo, hi, (32 - 8 * r) & 31) & 0x00FFFFFFu;
+            }
+            if constexpr (N == 4) { if (reverse) c[u] = ((c[u] & 0x0F0Fu) << 4) | ((c[u] >> 4) & 0x0F0Fu); }
+            const float sc = lut_s[sb[u]];
+            float o[4];
+            uint32_t mmax = 0u, nmin = 0xFFFFFFFFu;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = lane_decode<N, SGN>(c[u], N * e, k, mmax, nmin);
+            if (mmax >= k.special || (SGN == 2 && nmin == 0u)) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = rep_to_float_rare(c[u] >> (N * e), elem_codec);
+            }
+            const bool flip = N == 6 && reverse;
+            __stcs(out + vbase + u * kPackThreads, flip ? make_float4(__fmul_rn(o[3], sc), __fmul_rn(o[2], sc), __fmul_rn(o[1], sc), __fmul_rn(o[0], sc))
+                                                        : make_float4(__fmul_rn(o[0], sc), __fmul_rn(o[1], sc), __fmul_rn(o[2], sc), __fmul_rn(o[3], sc)));
+        }
+    }
+}
+
 unsigned pack_grid(int64_t count, int num_sms)
 {
     const int64_t ntiles = (count + kPackTile - 1) / kPackTile;
@@ -1253,6 +1305,24 @@ cudaError_t launch_mx_encode(int mode, const float* in, int64_t n, const MxArgs&
 cudaError_t launch_mx_decode(const uint8_t* scales, const uint8_t* elems, float* out, int64_t n, int block_size, const CodecPlan& scale_codec,
                              const CodecPlan& elem_codec, int num_sms, cudaStream_t stream)
 {
+    if (elem_codec.lanes && elem_codec.dec_ok && elem_codec.to_signed && (block_size & (block_size - 1)) == 0 && block_size >= 4 && block_size <= kPackTile && n >= kPackTile &&
+        (reinterpret_cast<uintptr_t>(elems) & 3u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0 &&
+        (elem_codec.n == 8 || elem_codec.n == 4 || elem_codec.n == 6)) {
+        // whole tiles on the register-lane kernel, the remainder (< 4096 elements: whole blocks, byte-aligned packed offset) on mx_decode_kernel
+        const int64_t ntiles = n / kPackTile;
+        int log2_bs = 0;
+        while ((1 << log2_bs) < block_size) ++log2_bs;
+        const unsigned lgrid = pack_grid(ntiles * kPackTile, num_sms);
+        float4* vout = reinterpret_cast<float4*>(out);
+#define LOF_MXD(N) do { if (elem_codec.sign_is_nan) mx_decode_lane_kernel<N, 2><<<lgrid, kPackThreads, 0, stream>>>(scales, elems, vout, ntiles, log2_bs, scale_codec, elem_codec); \
+                        else mx_decode_lane_kernel<N, 1><<<lgrid, kPackThreads, 0, stream>>>(scales, elems, vout, ntiles, log2_bs, scale_codec, elem_codec); } while (0)
+        if (elem_codec.n == 8) LOF_MXD(8); else if (elem_codec.n == 4) LOF_MXD(4); else LOF_MXD(6);
+#undef LOF_MXD
+        cudaError_t e = cudaGetLastError();
+        const int64_t done = ntiles * kPackTile;
+        if (e != cudaSuccess || done == n) return e;
+        scales += done / block_size; elems += (uint64_t)done / 8u * (uint64_t)elem_codec.n; out += done; n -= done;
+    }
     const int64_t nvec = n / 4;
     const int64_t want = (nvec + kPackThreads - 1) / kPackThreads, cap = (int64_t)num_sms /* = SMs x resident CTAs per SM, chosen by the caller */;
     const unsigned grid = (unsigned)(want < 1 ? 1 : want < cap ? want : cap);
