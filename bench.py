@@ -865,6 +865,7 @@ def side_measurements(torch, lib, _lib, dev, x, y, stream):
         sc, el = lof.mx_encode(x2, 32, e4, d8)
         extra = (("strict_round_e4m3_RNE", lambda: lof.virtual_round_strict(x, e4), 8.0),
                  ("fwht128", lambda: lof.fwht(x2, 128), 8.0),
+                 ("fwht128_fused_virtual_round_e4m3", lambda: lof.fwht(x2, 128, params=e4), 8.0),
                  ("fwht128_fused_mx_round_mxfp8", lambda: lof.fwht(x2, 128, params=e4, mx_block_size=32, scale_format=lof.create_e8m0_params()), 8.0),
                  ("mx_encode_mxfp8_scale_bytes_plus_packed", lambda: lof.mx_encode(x2, 32, e4, d8), 4.0 + 1.0 + 1.0 / 32),
                  ("mx_decode_mxfp8", lambda: lof.mx_decode(sc, el, x.numel(), 32, e4, d8), 4.0 + 1.0 + 1.0 / 32))

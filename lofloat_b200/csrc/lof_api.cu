@@ -1070,7 +1070,10 @@ int lof_fwht_round_f32(const float* in, float* out, int64_t n, int block_size, c
     const int sms = num_sms();
     if (sms <= 0) return fail(LOF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
     const RngArgs ra = make_rng(rng, kStreamElem, mode, ps->stoch_length);
-    cudaError_t e = launch_fwht(1, mode, in, out, n, block_size, &plan, (float)scale, nullptr, nullptr, nullptr, nullptr, ra, ra, first_index, sms * (int)g_opt.stream_ctas_per_sm.load(),
+    MagicPlan rmagic;
+    std::memset(&rmagic, 0, sizeof rmagic);
+    if (g_opt.round_fast.load() >= 2) rmagic = make_magic_plan(plan, mode);
+    cudaError_t e = launch_fwht(1, mode, in, out, n, block_size, &plan, (float)scale, nullptr, nullptr, nullptr, &rmagic, ra, ra, first_index, sms * (int)g_opt.stream_ctas_per_sm.load(),
                                 static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "lof_fwht_round launch");
     g_launches.fetch_add(1);

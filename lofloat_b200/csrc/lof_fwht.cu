@@ -197,10 +197,36 @@ fwht_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t nro
                         o.x = __fmul_rn(a.pre_scale, o.x); o.y = __fmul_rn(a.pre_scale, o.y);
                         o.z = __fmul_rn(a.pre_scale, o.z); o.w = __fmul_rn(a.pre_scale, o.w);
                     }
-                    o.x = __uint_as_float(round_params_elem<LOF_F32, MODE>(__float_as_uint(o.x), a.plan, w.x));
-                    o.y = __uint_as_float(round_params_elem<LOF_F32, MODE>(__float_as_uint(o.y), a.plan, w.y));
-                    o.z = __uint_as_float(round_params_elem<LOF_F32, MODE>(__float_as_uint(o.z), a.plan, w.z));
-                    o.w = __uint_as_float(round_params_elem<LOF_F32, MODE>(__float_as_uint(o.w), a.plan, w.w));
+                    bool done = false;
+                    if constexpr (MagicTraits<MODE>::kOk) {
+                        // the magic-add rounding of the elementwise kernels (lof_fast_f32.cuh, checked variant: lanes it cannot take set `rare`
+                        // and the vector is redone by the exact routine) instead of the ~35-instruction integer routine per element
+                        if (a.elem_fast_ok) {
+                            const uint32_t q[4] = {__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)};
+                            const uint32_t wq[4] = {w.x, w.y, w.z, w.w};
+                            uint32_t rr[4];
+                            bool rare = false;
+                            if (a.plan.saturating) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) rr[e] = round_magic_f32<MODE, true, true>(q[e], a.elem_magic, wq[e], rare);
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) rr[e] = round_magic_f32<MODE, false, true>(q[e], a.elem_magic, wq[e], rare);
+                            }
+                            if (rare) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) rr[e] = exact_params_f32<MODE>(q[e], a.plan, wq[e]);
+                            }
+                            o = make_float4(__uint_as_float(rr[0]), __uint_as_float(rr[1]), __uint_as_float(rr[2]), __uint_as_float(rr[3]));
+                            done = true;
+                        }
+                    }
+                    if (!done) {
+                        o.x = __uint_as_float(round_params_elem<LOF_F32, MODE>(__float_as_uint(o.x), a.plan, w.x));
+                        o.y = __uint_as_float(round_params_elem<LOF_F32, MODE>(__float_as_uint(o.y), a.plan, w.y));
+                        o.z = __uint_as_float(round_params_elem<LOF_F32, MODE>(__float_as_uint(o.z), a.plan, w.z));
+                        o.w = __uint_as_float(round_params_elem<LOF_F32, MODE>(__float_as_uint(o.w), a.plan, w.w));
+                    }
                 }
                 st_stream_f4(out + (row0 + r) * 32 + lane, o);
             }
@@ -225,6 +251,13 @@ cudaError_t launch_rows(int rows_per_block, const float* in, float* out, int64_t
             if (rows_per_block == 8) fwht_kernel<8, OP, MODE, 3, true><<<grid_for(8), kFwhtThreads, 0, stream>>>(vin, vout, nrows, a, rng, rng_scale, first_index);
             else if (a.log2_b >= 7) fwht_kernel<4, OP, MODE, 3, true><<<grid_for(4), kFwhtThreads, 0, stream>>>(vin, vout, nrows, a, rng, rng_scale, first_index);
             else fwht_kernel<4, OP, MODE, 3, false><<<grid_for(4), kFwhtThreads, 0, stream>>>(vin, vout, nrows, a, rng, rng_scale, first_index);
+            return cudaGetLastError();
+        }
+    }
+    if constexpr (OP == kFwhtRound) {
+        if (a.log2_b >= 7) {                                      // Hadamard blocks >= 128: the stage structure compile-time
+            if (rows_per_block == 8) fwht_kernel<8, OP, MODE, -1, true><<<grid_for(8), kFwhtThreads, 0, stream>>>(vin, vout, nrows, a, rng, rng_scale, first_index);
+            else fwht_kernel<4, OP, MODE, -1, true><<<grid_for(4), kFwhtThreads, 0, stream>>>(vin, vout, nrows, a, rng, rng_scale, first_index);
             return cudaGetLastError();
         }
     }
@@ -336,6 +369,9 @@ cudaError_t launch_fwht(int op, int mode, const float* in, float* out, int64_t n
         const int sm = mx->scale_mode;
         a.sq.quick_mode_ok = sm == LOF_RoundToNearestEven || sm == LOF_RoundTowardsZero || sm == LOF_RoundAwayFromZero ||
                              sm == LOF_RoundUp || sm == LOF_RoundDown || sm == LOF_RoundToOdd;
+    } else if (elem_magic && elem_magic->valid) {               // op 1: magic-add plan of the fused virtual_round
+        a.elem_magic = *elem_magic;
+        a.elem_fast_ok = 1;
     }
     const int rows_per_block = hadamard_block > 512 ? 8 : 4;
     const int64_t nrows = n / 128;

@@ -25,6 +25,9 @@ e4m3, e8m0 = lof.create_p3109_params(8, 4, bias=7), lof.create_e8m0_params()
 n = x.numel()
 for block in (32, 128, 1024):
     for name, fn in ((f"fused fwht{block} + mx_round", lambda: lof.fwht(x, block, params=e4m3, mx_block_size=32, scale_format=e8m0)),
+                     (f"fused fwht{block} + virtual_round e4m3 RNE", lambda: lof.fwht(x, block, params=e4m3)),
+                     (f"fused fwht{block} + virtual_round e4m3 SR-A8", lambda: lof.fwht(x, block, params=e4m3, round_mode=3, stoch_len=8)),
+                     (f"fused fwht{block} + virtual_round, magic add off", lambda: (lof.set_option("round.fast", 1), lof.fwht(x, block, params=e4m3), lof.set_option("round.fast", 2))),
                      (f"fused fwht{block} only", lambda: lof.fwht(x, block)),
                      (f"torch fwht{block} then lof.virtual_mx_round", lambda: lof.virtual_mx_round(torch_fwht(x, block), 32, e4m3, e8m0))):
         fn()
