@@ -539,10 +539,12 @@ def lof_gemm_batched(A: torch.Tensor, B: torch.Tensor, accum_mant_bits: int, rou
 
 def lof_linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, accum_mant_bits: int,
                round_mode=RoundingMode.RoundToNearestEven, stochastic_rounding_bits: int = 0, scale_a: float = 1.0, scale_b: float = 1.0,
-               *, kc=None, rng=None) -> torch.Tensor:
+               *, kc=None, rng=None, k_chunk=None, **tensor_core_kwargs) -> torch.Tensor:
     """F.linear with LoFloat accumulation: x (..., K), weight (N, K) -> (..., N) -- `_lof_linear` of LoFloat/layers.py:152-168
     as ONE kernel: the weight is read as stored (no `weight.t().contiguous()` copy) and the already quantised `bias` is added in
-    the epilogue (plain fp32 add, `out + bias`).  Bit-identical to lof_gemm(x_2d, weight.t().contiguous(), ...) + bias."""
+    the epilogue (plain fp32 add, `out + bias`).  Bit-identical to lof_gemm(x_2d, weight.t().contiguous(), ...) + bias.
+    With `k_chunk` (or after set_gemm_tensor_core()) the product runs the tensor-core chunked mode of lof_gemm (same keyword
+    arguments) and the bias is added afterwards."""
     if weight.dim() != 2 or x.dim() < 1 or x.shape[-1] != weight.shape[1]:
         raise RuntimeError(f"lof_linear: incompatible shapes {tuple(x.shape)} x {tuple(weight.shape)}")
     if x.dtype != torch.float32 or weight.dtype != torch.float32 or (bias is not None and bias.dtype != torch.float32):
@@ -552,6 +554,14 @@ def lof_linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None,
     N, K = weight.shape
     if bias is not None and bias.numel() != N:
         raise RuntimeError(f"lof_linear: bias has {bias.numel()} values, expected {N}")
+    if k_chunk is not None or (kc is None and _gemm_tc is not None):
+        out = lof_gemm(x.reshape(-1, K), weight.t().contiguous(), accum_mant_bits, round_mode, stochastic_rounding_bits, scale_a, scale_b,
+                       k_chunk=k_chunk, rng=rng, **tensor_core_kwargs)
+        if bias is not None:
+            out += bias
+        return out.reshape(*x.shape[:-1], N)
+    if tensor_core_kwargs:
+        raise TypeError(f"lof_linear: {sorted(tensor_core_kwargs)} need k_chunk (tensor-core chunked mode)")
     mode = RoundingMode(int(round_mode))
     ps = CProjSpec(int(mode), 0, int(stochastic_rounding_bits))
     denom = float(scale_a) * float(scale_b)

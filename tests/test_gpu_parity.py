@@ -1258,6 +1258,11 @@ def test_batched_gemm_equals_per_slice_calls(lof, cuda_dev):
         lof.set_gemm_tensor_core(None)
     with pytest.raises(TypeError):
         lof.lof_gemm_batched(Aq, Bq, 7, partial_round=True)
+    # lof_linear on the tensor-core chunked mode == lof_gemm(k_chunk) on the transposed weight + bias
+    W = _gpu(_e4m3_uniform((160, 256), 33), cuda_dev)
+    bias = torch.rand(160, device=cuda_dev, generator=g)
+    want = lof.lof_gemm(Aq.reshape(-1, 256), W.t().contiguous(), 7, k_chunk=32, partial_round=True) + bias
+    assert torch.equal(lof.lof_linear(Aq, W, bias, 7, k_chunk=32, partial_round=True), want.reshape(3, 2, 128, 160))
 
 
 def test_exact_gemm_more_than_65535_row_tiles(lof, cuda_dev):
