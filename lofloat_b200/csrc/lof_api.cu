@@ -604,7 +604,7 @@ int lof_set_option(const char* key, int64_t value)
     else if (k == "mx.ctas_per_sm") { if (value < 1 || value > 64) return fail(LOF_ERR_INVALID_ARG, "mx.ctas_per_sm out of range"); g_opt.mx_ctas_per_sm = value; }
     else if (k == "round.fast") { if (value < 0 || value > 2) return fail(LOF_ERR_INVALID_ARG, "round.fast must be 0, 1 or 2"); g_opt.round_fast = value; }
     else if (k == "stream.ctas_per_sm") { if (value < 1 || value > 64) return fail(LOF_ERR_INVALID_ARG, "stream.ctas_per_sm out of range"); g_opt.stream_ctas_per_sm = value; }
-    else if (k == "pack.fast") { if (value < 0 || value > 2) return fail(LOF_ERR_INVALID_ARG, "pack.fast must be 0, 1 or 2"); g_opt.pack_fast = value; }
+    else if (k == "pack.fast") { if (value < 0 || value > 3) return fail(LOF_ERR_INVALID_ARG, "pack.fast must be 0 .. 3"); g_opt.pack_fast = value; }
     else if (k == "bf16.fast") { if (value < 1 || value > 2) return fail(LOF_ERR_INVALID_ARG, "bf16.fast must be 1 or 2"); g_opt.bf16_fast = value; }
     else if (k == "gemm.mx_prof") g_opt.gemm_mx_prof = value;
     else if (k == "gemm.fold_split") { if (value < 1 || value > 2) return fail(LOF_ERR_INVALID_ARG, "gemm.fold_split must be 1 or 2"); g_opt.gemm_fold_split = value; }
@@ -1173,7 +1173,7 @@ int make_codec_plan(const lof_codec_format_t* cf, const lof_projspec_t* ps, int 
     p->f_cadd = (uint32_t)ds << 23;
     p->f_cfloor = (uint32_t)(emin_b + ds) << 23;
     p->f_big = (uint32_t)(to_max_exp + 128) << 23;
-    p->lanes = g_opt.pack_fast.load() >= 2;
+    p->lanes = g_opt.pack_fast.load() >= 2 ? (g_opt.pack_fast.load() >= 3 ? 1u : 2u) : 0u;     // 2: + block-per-thread MX encode (default); pack.fast = 3 keeps the warp-step MX encode
     // arithmetic decode (lof_pack.cu decode_lane_kernel): every finite code's value is a normal fp32 number or zero, and the
     // smallest magnitude among the infinity / NaN codes (the sign-bit-only NaN of the P3109 formats is tested separately)
     const int max_ef = (1 << ebits) - 1;

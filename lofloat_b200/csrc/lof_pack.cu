@@ -1040,6 +1040,99 @@ mx_encode_lane_kernel(const float4* __restrict__ in, int64_t nvec, MxArgs a, MxS
     }
 }
 
+__device__ __forceinline__ void ld_nc_256(const float4* p, float4& a, float4& b)        // p 32-byte aligned
+{
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+
+// Fourth-generation MX encode: ONE MX block per thread (VPB = block_size / 4 vectors of four elements, 64 .. 256 contiguous bytes).
+// No shuffles at all -- the block maximum, the scale, its reciprocal and the scale byte are thread-local -- and a thread stores its
+// block's codes as one contiguous run (16-byte stores), so a warp writes 32 runs back to back.  The loads are 16 bytes per thread at
+// a stride of one block: every 128-byte line is fetched by 8 / VPB-dependent neighbouring instructions of the same thread and stays in
+// L1 in between (ld.global.nc).  Element path: lane_mag + the register packers, as in the lane kernel above.
+template <int MODE, int VPB, int N, int SGN>
+__global__ void __launch_bounds__(kPackThreads)
+mx_encode_block_kernel(const float4* __restrict__ in, int64_t nblocks, MxArgs a, MxScaleQuick sq, CodecPlan scale_codec, CodecPlan elem_codec,
+                       RngArgs rng_scale, uint64_t first_block, uint8_t* __restrict__ scales, uint8_t* __restrict__ elems)
+{
+    const LaneConsts k(elem_codec);
+    const bool reverse = elem_codec.reverse != 0;
+    const bool e8m0_like = scale_codec.mant == 0 && !scale_codec.to_signed;
+    const int64_t stride = (int64_t)gridDim.x * kPackThreads;
+    for (int64_t b = (int64_t)blockIdx.x * kPackThreads + threadIdx.x; b < nblocks; b += stride) {
+        float4 x[VPB];
+#pragma unroll
+        for (int u = 0; u < VPB; u += 2) ld_nc_256(in + b * VPB + u, x[u], x[u + 1]);     // 32-byte loads: half the L1 tag look-ups of the strided pattern
+        float amax = 0.0f;
+#pragma unroll
+        for (int u = 0; u < VPB; ++u) amax = fmaxf(amax, fmaxf(fmaxf(fabsf(x[u].x), fabsf(x[u].y)), fmaxf(fabsf(x[u].z), fabsf(x[u].w))));
+        const float scale = mx_scale_quick(amax, a, sq, rng_scale, first_block + (uint64_t)b);
+        const uint32_t sb = __float_as_uint(scale);
+        const bool pow2 = (sb & 0x807FFFFFu) == 0u && (sb - 0x00800000u) < 0x7E800000u;
+        const bool live = scale > 0.0f;                                  // dead block (scale <= 0 or NaN): all-zero codes
+        const float recip = __uint_as_float(0x7F000000u - sb);          // exact 2^-k when pow2
+        {
+            const int code = (int)(sb >> 23) + scale_codec.exp_offset;
+            uint32_t byte;
+            if (e8m0_like && pow2 && (sb >> 23) <= 254u && code >= 1 && code <= (int)scale_codec.max_finite_rep) byte = (uint32_t)code;
+            else byte = float_to_rep<LOF_RoundTowardsZero>(sb, scale_codec, 0u);
+            scales[b] = (uint8_t)byte;
+        }
+        uint32_t w[VPB];
+#pragma unroll
+        for (int u = 0; u < VPB; ++u) {
+            float y[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+            if (pow2) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) y[e] = __fmul_rn(y[e], recip);
+            } else {                                                     // non-power-of-two scale: the reference's division (never for E8M0)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) y[e] = __fdiv_rn(y[e], scale);
+            }
+            uint32_t m[4], s[4], emax = 0u;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) m[e] = lane_mag<MODE, 1>(__float_as_uint(y[e]), k, emax, s[e]);
+            const bool rare = emax >= kLaneRare;
+            if (rare) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const uint2 r = lane_mag_rare<MODE>(__float_as_uint(y[e]), elem_codec); m[e] = r.x; s[e] = r.y; }
+            }
+            uint32_t c;
+            if constexpr (N == 8) c = rare ? pack8<1>(m, s) : pack8<SGN>(m, s);
+            else if constexpr (N == 4) c = rare ? pack4<1>(m, s, reverse) : pack4<SGN>(m, s, reverse);
+            else c = rare ? pack6<1>(m, s, reverse) : pack6<SGN>(m, s, reverse);
+            w[u] = live ? c : 0u;
+        }
+        if constexpr (N == 8) {
+            uint4* d = reinterpret_cast<uint4*>(elems) + b * (VPB / 4);
+#pragma unroll
+            for (int q = 0; q < VPB / 4; ++q) __stcs(d + q, make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]));
+        } else if constexpr (N == 4) {                                    // 16 bits per vector
+            uint32_t h[VPB / 2];
+#pragma unroll
+            for (int q = 0; q < VPB / 2; ++q) h[q] = w[2 * q] | (w[2 * q + 1] << 16);
+            if constexpr (VPB == 4) __stcs(reinterpret_cast<uint2*>(elems) + b, make_uint2(h[0], h[1]));
+            else {
+                uint4* d = reinterpret_cast<uint4*>(elems) + b * (VPB / 8);
+#pragma unroll
+                for (int q = 0; q < VPB / 8; ++q) __stcs(d + q, make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]));
+            }
+        } else {                                                          // 24 bits per vector: four vectors = three words
+            uint32_t t[VPB / 4 * 3];
+#pragma unroll
+            for (int q = 0; q < VPB / 4; ++q) {
+                t[3 * q] = w[4 * q] | (w[4 * q + 1] << 24);
+                t[3 * q + 1] = (w[4 * q + 1] >> 8) | (w[4 * q + 2] << 16);
+                t[3 * q + 2] = (w[4 * q + 2] >> 16) | (w[4 * q + 3] << 8);
+            }
+            uint32_t* d = reinterpret_cast<uint32_t*>(elems) + b * (VPB / 4 * 3);
+#pragma unroll
+            for (int q = 0; q < VPB / 4 * 3; ++q) __stcs(d + q, t[q]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kPackThreads)
 mx_decode_kernel(const uint8_t* __restrict__ scales, const uint8_t* __restrict__ elems, float4* __restrict__ out, int64_t nvec,
                  int block_size, CodecPlan scale_codec, CodecPlan elem_codec)
@@ -1256,6 +1349,27 @@ cudaError_t launch_mx_encode(int mode, const float* in, int64_t n, const MxArgs&
         const int64_t nsteps = (nvec + 32 * lanes - 1) / (32 * lanes);
         const int64_t want2 = (nsteps + kWarps - 1) / kWarps;
         const unsigned grid2 = (unsigned)(want2 < 1 ? 1 : want2 < cap ? want2 : cap);
+        if (elem_codec.lanes >= 2 && elem_codec.to_signed && (elem_codec.n == 8 || elem_codec.n == 4 || elem_codec.n == 6) &&
+            (reinterpret_cast<uintptr_t>(elems) & 15u) == 0 && (reinterpret_cast<uintptr_t>(in) & 31u) == 0 && first_index % (uint64_t)a.block_size == 0) {
+            // one MX block per thread (pack.fast = 2, default)
+            const int64_t nblocks = n / a.block_size;
+            const int64_t want3 = (nblocks + kPackThreads - 1) / kPackThreads;
+            const unsigned grid3 = (unsigned)(want3 < 1 ? 1 : want3 < cap ? want3 : cap);
+            const uint64_t first_block = first_index / (uint64_t)a.block_size;
+            const bool nz = elem_codec.sign_is_nan != 0;
+#define LOF_MXB4(M, V, N, S) mx_encode_block_kernel<M, V, N, S><<<grid3, kPackThreads, 0, stream>>>(vin, nblocks, a, sq, scale_codec, elem_codec, rng_scale, first_block, scales, elems)
+#define LOF_MXB3(M, V, N) do { if (nz) LOF_MXB4(M, V, N, 2); else LOF_MXB4(M, V, N, 1); } while (0)
+#define LOF_MXB2(M, V) do { if (elem_codec.n == 8) LOF_MXB3(M, V, 8); else if (elem_codec.n == 4) LOF_MXB3(M, V, 4); else LOF_MXB3(M, V, 6); } while (0)
+#define LOF_MXB(M) case M: if (lanes == 4) LOF_MXB2(M, 4); else if (lanes == 8) LOF_MXB2(M, 8); else LOF_MXB2(M, 16); return cudaGetLastError();
+            switch (mode) {
+                LOF_MXB(LOF_RoundToNearestEven) LOF_MXB(LOF_RoundTowardsZero) LOF_MXB(LOF_RoundAwayFromZero) LOF_MXB(LOF_RoundToOdd)
+            default: break;
+            }
+#undef LOF_MXB
+#undef LOF_MXB2
+#undef LOF_MXB3
+#undef LOF_MXB4
+        }
         if (elem_codec.lanes && elem_codec.to_signed && (elem_codec.n == 8 || elem_codec.n == 4 || elem_codec.n == 6)) {
             const bool nz = elem_codec.sign_is_nan != 0;         // P3109-style element formats: no -0
 #define LOF_MXL4(M, L, N, S) mx_encode_lane_kernel<M, L, N, S><<<grid2, kPackThreads, 0, stream>>>(vin, nvec, a, sq, scale_codec, elem_codec, rng_scale, first_index, scales, elems)
