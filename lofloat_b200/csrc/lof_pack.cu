@@ -1064,13 +1064,22 @@ mx_encode_block_kernel(const float4* __restrict__ in, int64_t nblocks, MxArgs a,
         float4 x[VPB];
 #pragma unroll
         for (int u = 0; u < VPB; u += 2) ld_nc_256(in + b * VPB + u, x[u], x[u + 1]);     // 32-byte loads: half the L1 tag look-ups of the strided pattern
-        float amax = 0.0f;
+        float amax = 0.0f, nansum = 0.0f;
 #pragma unroll
-        for (int u = 0; u < VPB; ++u) amax = fmaxf(amax, fmaxf(fmaxf(fabsf(x[u].x), fabsf(x[u].y)), fmaxf(fabsf(x[u].z), fabsf(x[u].w))));
+        for (int u = 0; u < VPB; ++u) {
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(x[u].x), fabsf(x[u].y)), fmaxf(fabsf(x[u].z), fabsf(x[u].w))));
+            nansum += (x[u].x + x[u].y) + (x[u].z + x[u].w);             // fma pipe (idle here): NaN iff the block holds a NaN (or +inf and -inf)
+        }
+        // with a power-of-two scale, NaN elements are the only inputs the lane path cannot encode (x * 2^-k is NaN only for a NaN x; an
+        // overflowing product clamps to max_finite_rep like the exact routine does for these formats without infinities): one test per
+        // block instead of a running maximum per element
+        const bool nan_in = nansum != nansum;
         const float scale = mx_scale_quick(amax, a, sq, rng_scale, first_block + (uint64_t)b);
         const uint32_t sb = __float_as_uint(scale);
         const bool pow2 = (sb & 0x807FFFFFu) == 0u && (sb - 0x00800000u) < 0x7E800000u;
         const bool live = scale > 0.0f;                                  // dead block (scale <= 0 or NaN): all-zero codes
+        const bool rare = nan_in || !pow2;                               // a non-power-of-two scale (e.g. the infinite scale of a block with an infinite element:
+                                                                         // inf / inf = NaN) takes the exact element routine as well
         const float recip = __uint_as_float(0x7F000000u - sb);          // exact 2^-k when pow2
         {
             const int code = (int)(sb >> 23) + scale_codec.exp_offset;
@@ -1090,10 +1099,9 @@ mx_encode_block_kernel(const float4* __restrict__ in, int64_t nblocks, MxArgs a,
 #pragma unroll
                 for (int e = 0; e < 4; ++e) y[e] = __fdiv_rn(y[e], scale);
             }
-            uint32_t m[4], s[4], emax = 0u;
+            uint32_t m[4], s[4], unused = 0u;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) m[e] = lane_mag<MODE, 1>(__float_as_uint(y[e]), k, emax, s[e]);
-            const bool rare = emax >= kLaneRare;
+            for (int e = 0; e < 4; ++e) m[e] = lane_mag<MODE, 1>(__float_as_uint(y[e]), k, unused, s[e]);
             if (rare) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) { const uint2 r = lane_mag_rare<MODE>(__float_as_uint(y[e]), elem_codec); m[e] = r.x; s[e] = r.y; }
@@ -1133,6 +1141,21 @@ mx_encode_block_kernel(const float4* __restrict__ in, int64_t nblocks, MxArgs a,
     }
 }
 
+// element * scale of the MX decode with the NaN bit patterns of the oracle's CPU arithmetic (x86 SSE, like mx_quant in lof_mx_kernels.cuh):
+// a NaN operand (both decode to +qNaN) propagates as 0x7FC00000, an invalid product (inf code * zero scale) is the negative
+// "indefinite" 0xFFC00000; the GPU multiply would return 0x7FFFFFFF for all of them.  One test per vector on the sum of the products.
+__device__ __forceinline__ float mx_nan_fix(float r, float a, float s)
+{
+    return r != r ? __uint_as_float((a != a || s != s) ? 0x7FC00000u : 0xFFC00000u) : r;
+}
+__device__ __forceinline__ float4 mx_scale_mul(float a0, float a1, float a2, float a3, float s)
+{
+    float4 r = make_float4(__fmul_rn(a0, s), __fmul_rn(a1, s), __fmul_rn(a2, s), __fmul_rn(a3, s));
+    const float chk = (r.x + r.y) + (r.z + r.w);
+    if (chk != chk) { r.x = mx_nan_fix(r.x, a0, s); r.y = mx_nan_fix(r.y, a1, s); r.z = mx_nan_fix(r.z, a2, s); r.w = mx_nan_fix(r.w, a3, s); }
+    return r;
+}
+
 __global__ void __launch_bounds__(kPackThreads)
 mx_decode_kernel(const uint8_t* __restrict__ scales, const uint8_t* __restrict__ elems, float4* __restrict__ out, int64_t nvec,
                  int block_size, CodecPlan scale_codec, CodecPlan elem_codec)
@@ -1162,7 +1185,7 @@ mx_decode_kernel(const uint8_t* __restrict__ scales, const uint8_t* __restrict__
             else { uint32_t t = r[0]; r[0] = r[3]; r[3] = t; t = r[1]; r[1] = r[2]; r[2] = t; }
         }
         const float s = lut_s[scales[(v * 4) / block_size]];
-        __stcs(out + v, make_float4(__fmul_rn(lut_e[r[0]], s), __fmul_rn(lut_e[r[1]], s), __fmul_rn(lut_e[r[2]], s), __fmul_rn(lut_e[r[3]], s)));
+        __stcs(out + v, mx_scale_mul(lut_e[r[0]], lut_e[r[1]], lut_e[r[2]], lut_e[r[3]], s));
     }
 }
 
@@ -1212,8 +1235,7 @@ mx_decode_lane_kernel(const uint8_t* __restrict__ scales, const uint8_t* __restr
                 for (int e = 0; e < 4; ++e) o[e] = rep_to_float_rare(c[u] >> (N * e), elem_codec);
             }
             const bool flip = N == 6 && reverse;
-            __stcs(out + vbase + u * kPackThreads, flip ? make_float4(__fmul_rn(o[3], sc), __fmul_rn(o[2], sc), __fmul_rn(o[1], sc), __fmul_rn(o[0], sc))
-                                                        : make_float4(__fmul_rn(o[0], sc), __fmul_rn(o[1], sc), __fmul_rn(o[2], sc), __fmul_rn(o[3], sc)));
+            __stcs(out + vbase + u * kPackThreads, flip ? mx_scale_mul(o[3], o[2], o[1], o[0], sc) : mx_scale_mul(o[0], o[1], o[2], o[3], sc));
         }
     }
 }

@@ -1083,16 +1083,27 @@ def test_mx_storage_encode_decode(lof, cuda_dev):
     x[:128] = 0.0
     x[128:256] = 2.0 ** -140                                                              # fp32-subnormal block
     x[300] = np.float32(3e38)
+    x[128 * 7 + 5] = np.nan                                                              # a NaN element: dropped from the block maximum, encodes as the NaN code
+    x[128 * 9 + 17] = np.inf                                                             # infinite elements: the block's scale saturates
+    x[128 * 11 + 3] = -np.inf
+    x[128 * 13 + 1], x[128 * 13 + 2] = np.inf, -np.inf                                   # both signs in one block
     xt = _gpu(x, cuda_dev)
+    from lofloat_b200 import _lib as _l
+    try:
+        for gen in (2, 3, 1):       # block-per-thread encode + lane decode (default) / warp-step lane encode / second-generation kernels
+            _l.set_option("pack.fast", gen)
+            for name, (cf, d, ff) in elem.items():
+                for bs in (16, 32, 64, 128):
+                    for endian in (0, 1):
+                        sc, el = lof.mx_encode(xt, bs, d, d8, endian=endian)
+                        wsc, wel = L.o_mx_encode(x, bs, e8, cf, endian=endian)
+                        assert np.array_equal(_np(sc), wsc), (gen, name, bs, endian, "scales")
+                        assert np.array_equal(_np(el), wel), (gen, name, bs, endian, "elements")
+                        back = _np(lof.mx_decode(sc, el, n, bs, d, d8, endian))
+                        assert L.bits_equal(back, L.o_mx_decode(wsc, wel, n, bs, e8, cf, endian)), (gen, name, bs, endian, "decode")
+    finally:
+        _l.set_option("pack.fast", 2)
     for name, (cf, d, ff) in elem.items():
-        for bs in (16, 32, 64, 128):
-            for endian in (0, 1):
-                sc, el = lof.mx_encode(xt, bs, d, d8, endian=endian)
-                wsc, wel = L.o_mx_encode(x, bs, e8, cf, endian=endian)
-                assert np.array_equal(_np(sc), wsc), (name, bs, endian, "scales")
-                assert np.array_equal(_np(el), wel), (name, bs, endian, "elements")
-                back = _np(lof.mx_decode(sc, el, n, bs, d, d8, endian))
-                assert L.bits_equal(back, L.o_mx_decode(wsc, wel, n, bs, e8, cf, endian)), (name, bs, endian, "decode")
         for mode, smode, sl in ((L.RTZ, L.RNE, 0), (L.RAZ, L.RU, 0), (L.RTO, L.RD, 0), (L.RNE, L.RAZ, 0), (L.SR_A, L.RNE, 6), (L.TRUE_SR, L.RNE, 0)):
             sc, el = lof.mx_encode(xt, 32, d, d8, mode, smode, sl, rng=(5, 7))
             wsc, wel = L.o_mx_encode(x, 32, e8, cf, mode, smode, sl, seed=5, offset=7)
@@ -1100,6 +1111,7 @@ def test_mx_storage_encode_decode(lof, cuda_dev):
         # against the fake-quant op: identical wherever virtual_mx_round's value is representable in the element format
         xr = x.copy()
         xr[128:256] = 1.5                                  # (a 2^-127 scale has no nonzero E8M0 code in lo_pack.hpp's decoder: exp field 0 reads as 0)
+        xr[~np.isfinite(xr)] = 1.0                         # (NaN / infinite elements are covered by the byte comparison above)
         xrt = _gpu(xr, cuda_dev)
         sc, el = lof.mx_encode(xrt, 32, d, d8, scale_round_mode=lof.RoundingMode.RoundUp)
         fake = _np(lof.virtual_mx_round(xrt, 32, d, d8, scale_round_mode=lof.RoundingMode.RoundUp))
